@@ -1,0 +1,208 @@
+/*
+ * mphsir.h — C ABI of libmphsir.so, the B200 (sm_100a) kernel library behind the drop-in
+ * MP_HSIR_Net module (mp_hsir_b200/model.py).
+ *
+ * The reference (ZhehuiWu/MP-HSIR) has no FFI: its hot path is the Python nn.Module
+ * net/MP_HSIR.py, every op an ATen call.  Each entry point below therefore names the
+ * reference *Python* interface it replaces (file:line of net/MP_HSIR.py); INTEGRATION.md
+ * shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - Activations are fp32, token-major ("channels-last"): row n = (b*H + y)*W + x, `ld` floats
+ *     per row.  This is the layout PGSSTB itself uses (net/MP_HSIR.py:665-668).
+ *   - Every pointer is a CUDA device pointer owned by the caller (PyTorch allocates); the
+ *     library allocates nothing and keeps no state besides the last error string.
+ *   - Calls enqueue asynchronously on `stream` (a cudaStream_t passed as void*), never
+ *     synchronise, are re-entrant and CUDA-graph capturable.
+ *   - Return 0 on success; non-zero -> mphsir_last_error() describes it.  No CPU fallback.
+ */
+#ifndef MPHSIR_H_
+#define MPHSIR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPHSIR_VERSION 100 /* round 1 */
+
+#if defined(__GNUC__)
+#define MPHSIR_API __attribute__((visibility("default")))
+#else
+#define MPHSIR_API
+#endif
+
+enum { MPHSIR_OK = 0, MPHSIR_ERR_INVALID = 1, MPHSIR_ERR_CUDA = 2 };
+
+MPHSIR_API int mphsir_version(void);
+MPHSIR_API const char* mphsir_last_error(void);
+/* sm_100 check + SM count; returns MPHSIR_ERR_CUDA if the device is not compute capability 10.x */
+MPHSIR_API int mphsir_device_check(int device, int* sm_count);
+
+/* ---------------------------------------------------------------------------------------
+ * Layout conversion at the module boundary: NCHW image -> token-major rows, channels
+ * [C, ld_out) zero-filled.  Replaces the implicit layout of `inp_img` (net/MP_HSIR.py:810-814).
+ * ------------------------------------------------------------------------------------- */
+MPHSIR_API int mphsir_nchw_to_tokens(const float* in, float* out, int B, int C, int HW, int ld_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * GEMM family  Y = epilogue( prologue(A) @ Bt )   A:[M,K] token-major, Bt:[Kp,ldb] (pre-packed
+ * "in x out" weights, Kp = K rounded up to 16, zero padded).
+ *
+ * prologue : optional LayerNorm over the K columns of each row (ln_gamma/ln_beta != NULL),
+ *            replacing nn.LayerNorm (net/MP_HSIR.py:618-619,667,719) and WithBias_LayerNorm
+ *            (:354-357) in front of the projection that consumes it.
+ * epilogue : see enum below.  Replaces nn.Linear / 1x1 nn.Conv2d call sites:
+ *            Spatial_Attention.qkv/.proj (:195,:216), Spectral_Attention.qkv/.project_out
+ *            (:98,:113), GatedMlp.fc1/.fc2 (:77-80), FeedForward/FFN project_in/out (:387-390,
+ *            :261-264), CrossAttention q/kv/project_out (:236-248), PromptFusion.conv (:597),
+ *            reduce_chan_level2 (:828), and the residual adds of PGSSTB.forward (:715-719),
+ *            TransformerBlock.forward (:476-477), BaseBlock.forward (:760).
+ * ------------------------------------------------------------------------------------- */
+enum {
+  MPHSIR_EPI_BIAS = 0,     /* Y = acc + bias                                                     */
+  MPHSIR_EPI_RESIDUAL = 1, /* Y = res1 + scale_b*(acc + bias) [+ res2]                           */
+  MPHSIR_EPI_GLU = 2,      /* packed cols (2j,2j+1)=(value_j,gate_j): Y[:,j] = v*gelu_erf(g)     */
+  MPHSIR_EPI_SPECTRAL = 3  /* Y = res1 + scale_b*(gsrc*gate[window(row)] + acc)   (:715-718)     */
+};
+
+typedef struct {
+  const float* A;      /* [M, lda] */
+  int lda;
+  int a_row_mod;       /* >0: A row index = m % a_row_mod (operand shared by all samples)        */
+  const float* Bt;     /* [Kp, ldb]; ldb multiple of 64, >= N rounded up to the tile              */
+  int ldb;
+  long long b_batch_stride; /* floats between per-sample weight matrices; 0 = shared            */
+  int rows_per_batch;  /* H*W; needed when b_batch_stride != 0 or epi needs sample / window ids  */
+  float* Y;
+  int ldy;
+  int M, N, K;         /* K = number of valid A columns (multiple of 4)                           */
+  const float* ln_gamma; /* [K] or NULL */
+  const float* ln_beta;
+  const float* bias;   /* [N] (packed order) or NULL */
+  int epi;
+  const float* res1;
+  int ldr1;
+  const float* res2;   /* optional second residual (BaseBlock shortcut) */
+  int ldr2;
+  const float* gsrc;   /* SPECTRAL: spatial-attention output sa [M, ldg] */
+  int ldg;
+  const float* gate;   /* SPECTRAL: per-window channel gate [B*nW, N]    */
+  int H, W, shift;     /* SPECTRAL: image size at this level and cyclic shift (0 or 4)            */
+  const float* row_scale; /* [B] DropPath keep/keep_prob per sample, NULL = 1 (eval)              */
+} mphsir_gemm_params;
+
+MPHSIR_API int mphsir_gemm_fwd(const mphsir_gemm_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Dense 3x3 convolution (zero pad 1, no bias) as an implicit GEMM over token-major input.
+ * Replaces OverlapPatchEmbed.proj (:458), Downsample/Upsample bodies incl. PixelUnshuffle /
+ * PixelShuffle (:436-437,:446-447), TVSP.conv_last (:581) and `output(x)+inp_img` (:841).
+ * Wt is packed [9*Cin, ldb]: row = tap*Cin + c, tap = 3*(dy+1)+(dx+1).
+ * ------------------------------------------------------------------------------------- */
+enum {
+  MPHSIR_CONV_TOKENS = 0,    /* Y[n, c]                                                          */
+  MPHSIR_CONV_UNSHUFFLE = 1, /* Y[(b,y/2,x/2), c*4+2(y&1)+(x&1)]                                 */
+  MPHSIR_CONV_SHUFFLE = 2,   /* packed col q*Cn+cn (q=2i+j) -> Y[(b,2y+i,2x+j), cn]              */
+  MPHSIR_CONV_NCHW_RES = 3   /* Y[b,c,y,x] = acc + R[b,c,y,x]  (NCHW, c < N)                     */
+};
+
+typedef struct {
+  const float* X;  /* [B*H*W, ldx] token-major, channels [0,Cin) valid (Cin multiple of 16)      */
+  int ldx;
+  const float* Wt; /* [9*Cin, ldb] */
+  int ldb;
+  float* Y;
+  int ldy;
+  int B, H, W, Cin, N; /* N = number of output channels */
+  int out_mode;
+  const float* R;  /* NCHW residual for MPHSIR_CONV_NCHW_RES */
+} mphsir_conv3x3_params;
+
+MPHSIR_API int mphsir_conv3x3_fwd(const mphsir_conv3x3_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Window attention core: for every (shifted) 8x8 window and head
+ *     softmax(q k^T * hd^-0.5 + rel_pos_bias + shift_mask) v
+ * qkv is the token-major [B*H*W, 3C] output of the LN+qkv GEMM in *image* order; the roll,
+ * window_partition, window_reverse and un-roll of PGSSTB.forward (:671-678,:689-696) are
+ * folded into the addressing, the Swin mask of calculate_mask (:639-660) is evaluated in
+ * closed form, and the per-window token mean of the result (needed by the local spectral
+ * branch, :135) is emitted as well.  Replaces Spatial_Attention.forward :195-215 (proj is a GEMM).
+ *   bias : [heads,64,64] pre-gathered relative-position bias (:200-202)
+ *   out  : [B*H*W, ldo] image order;  win_mean : [B*nW, C] in shifted-window order
+ * ------------------------------------------------------------------------------------- */
+MPHSIR_API int mphsir_window_attn_fwd(const float* qkv, int ldqkv, const float* bias, float* out, int ldo,
+                           float* win_mean, int B, int H, int W, int C, int heads, int shift,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Local spectral branch (low-rank spectral-prompt gate), one fused kernel per window:
+ * PG_Spectral_Attention.forward :135-152 collapsed to a per-window channel gate g[B_,C];
+ * the caller applies sa*g in the MPHSIR_EPI_SPECTRAL epilogue (:153).
+ *   core_mean [B_,C] : token mean of the attention core (before proj)
+ *   all weights pre-transposed to "in x out":
+ *   projT[C,C] projb[C] (Spatial_Attention.proj, mean commutes with it), promptT[C,128],
+ *   downT[C,r], param[128,r], qT[r,r], kvT[r,2r], p2T[r,r], p2b[r], upT[r,C]
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* core_mean;
+  const float *projT, *projb, *promptT, *downT, *param, *qT, *kvT, *p2T, *p2b, *upT;
+  float* gate; /* [B_, C] */
+  int B_, C, r;
+} mphsir_local_gate_params;
+
+MPHSIR_API int mphsir_local_gate_fwd(const mphsir_local_gate_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Depthwise 3x3 conv (zero pad 1, no bias) on token-major data, optional GDFN gate.
+ * Replaces qkv_dwconv (:98), q_dwconv/kv_dwconv (:236-237), FeedForward.dwconv + gelu gate
+ * (:388-389, :262-263).   w9 packed [9, C].
+ *   gate_half = 0 : Y[n,c] = dw(X)[n,c]                                 (Y has C columns)
+ *   gate_half = h : Y[n,j] = gelu_erf(dw[n,j]) * dw[n,h+j],  j < h      (C == 2h)
+ * ------------------------------------------------------------------------------------- */
+MPHSIR_API int mphsir_dwconv3x3_fwd(const float* X, int ldx, const float* w9, float* Y, int ldy, int B, int H,
+                         int W, int C, int gate_half, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Global spectral ("transposed") attention statistics and weight folding, replacing
+ * Spectral_Attention.forward :101-113 / Attention.forward :412-426 / CrossAttention :239-248.
+ *  1. gram_partial : per (sample, head, token chunk) partial  q^T k [c,c], sum q^2 [c], sum k^2 [c]
+ *  2. gram_softmax : reduce partials, A = softmax_j( G_ij / (max(|q_i|,eps) max(|k_j|,eps)) * T_h )
+ *  3. fold         : Mt_b[h*c+j, o] = sum_i WoutT[h*c+i, o] * A_h[i, j]   ("in x out" for the
+ *                    apply GEMM, which then computes project_out(attn @ v) in one pass)
+ * q,k are column slices of token-major buffers; *_shared != 0 means the operand has a single
+ * sample that every batch element uses (TVSP visual prompt).
+ * ------------------------------------------------------------------------------------- */
+MPHSIR_API size_t mphsir_gram_partial_floats(int B, int heads, int c, int HW, int* n_chunks);
+MPHSIR_API int mphsir_gram_partial_fwd(const float* q, int ldq, int q_shared, const float* k, int ldk,
+                            int k_shared, float* partial, int B, int HW, int heads, int c,
+                            void* stream);
+MPHSIR_API int mphsir_gram_softmax_fwd(const float* partial, int n_chunks, const float* temperature,
+                            float* attn /* [B,heads,c,c] */, int B, int heads, int c, void* stream);
+MPHSIR_API int mphsir_spectral_fold_fwd(const float* attn, const float* WoutT /* [C,C] in x out */,
+                             float* Mt /* [B, Cp, ldm] */, int ldm, long long m_batch_stride, int B,
+                             int heads, int c, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * TVSP helpers.
+ *  tvsp_query : Q[b,i,j,d] = tp[b,d] * clip_b[floor(i*B/ps), floor(j*512/ps)] with
+ *               tp = (weights @ learnable)/T  — the broadcast + nearest interpolate of :575-577.
+ *  bilinear   : F.interpolate(mode="bilinear", align_corners=False) on token-major data (:580).
+ * ------------------------------------------------------------------------------------- */
+MPHSIR_API int mphsir_tvsp_query_fwd(const float* clip_b /* [B,512] */, const float* weights /* [B,T] */,
+                          const float* learnable /* [T,D] */, float* Q /* [B*ps*ps, D] */, int B,
+                          int T, int D, int ps, void* stream);
+MPHSIR_API int mphsir_bilinear_fwd(const float* X, int ldx, float* Y, int ldy, int B, int h, int w, int H,
+                        int W, int C, void* stream);
+
+/* Text_Prompt.forward :517-532: clip_b[B,512] = (weights @ clip)/T */
+MPHSIR_API int mphsir_text_prompt_fwd(const float* weights /* [B,T] */, const float* clip /* [T,512] */,
+                           float* clip_b, int B, int T, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPHSIR_H_ */

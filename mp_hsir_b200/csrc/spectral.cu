@@ -1,0 +1,281 @@
+// Bandwidth-bound pieces of the global spectral ("transposed") attention and the GDFN:
+//   * depthwise 3x3 conv on token-major data, optional GELU gate   (net/MP_HSIR.py:98, :236-237, :388-389)
+//   * split-K Gram statistics over H*W: q^T k, sum q^2, sum k^2     (:104-107 with the L2 normalisation
+//     applied AFTER the reduction: q^k^ = (q.k)/(|q||k|))
+//   * softmax with temperature (:107-108) and folding of project_out (:113) into one C x C matrix
+//     per sample:  out = W_out (A v)  ==  (W_out blockdiag(A)) v
+#include "common.cuh"
+
+namespace mphsir {
+
+// ---------------------------------------------------------------------------------------------
+// depthwise 3x3: one thread per (pixel, 4 channels); 128-bit loads along channels.
+// ---------------------------------------------------------------------------------------------
+template <bool GATE>
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(const float* __restrict__ X, long long ldx,
+                                                        const float* __restrict__ w9, float* __restrict__ Y,
+                                                        long long ldy, int B, int H, int W, int C, int half) {
+  const int c4n = (GATE ? half : C) >> 2;
+  const long long total = (long long)B * H * W * c4n;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % c4n) * 4;
+    const long long pix = idx / c4n;
+    const int x = (int)(pix % W);
+    const int y = (int)((pix / W) % H);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), g = a;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= W) continue;
+        const int tap = (dy + 1) * 3 + (dx + 1);
+        const float* src = X + (pix + dy * W + dx) * ldx + c;
+        const float4 v = ldg4(src);
+        const float4 w = ldg4(w9 + tap * C + c);
+        a.x = fmaf(v.x, w.x, a.x); a.y = fmaf(v.y, w.y, a.y);
+        a.z = fmaf(v.z, w.z, a.z); a.w = fmaf(v.w, w.w, a.w);
+        if (GATE) {
+          const float4 v2 = ldg4(src + half);
+          const float4 w2 = ldg4(w9 + tap * C + half + c);
+          g.x = fmaf(v2.x, w2.x, g.x); g.y = fmaf(v2.y, w2.y, g.y);
+          g.z = fmaf(v2.z, w2.z, g.z); g.w = fmaf(v2.w, w2.w, g.w);
+        }
+      }
+    }
+    if (GATE) {
+      a.x = gelu_erf(a.x) * g.x; a.y = gelu_erf(a.y) * g.y;
+      a.z = gelu_erf(a.z) * g.z; a.w = gelu_erf(a.w) * g.w;
+    }
+    *reinterpret_cast<float4*>(Y + pix * ldy + c) = a;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gram partials.  grid = (n_chunks, B*heads); CTA = (c/4)^2 threads, each a 4x4 block of q^T k.
+// partial layout: [B*heads][n_chunks][c*c + 2c]  (G row-major [i][j], then sum q_i^2, sum k_j^2)
+// ---------------------------------------------------------------------------------------------
+constexpr int GT = 32;  // tokens staged per shared-memory tile
+
+template <int CH>
+__global__ void __launch_bounds__((CH / 4) * (CH / 4)) gram_partial_kernel(
+    const float* __restrict__ q, long long ldq, int q_shared, const float* __restrict__ k, long long ldk,
+    int k_shared, float* __restrict__ partial, int HW, int heads, int chunk) {
+  constexpr int NB = CH / 4;
+  constexpr int NTH = NB * NB;
+  __shared__ __align__(16) float qs[GT][CH];
+  __shared__ __align__(16) float ks[GT][CH];
+  const int tid = threadIdx.x;
+  const int bi = tid / NB, bj = tid - bi * NB;
+  const int bh = blockIdx.y;
+  const int b = bh / heads, h = bh - b * heads;
+  const int t0 = blockIdx.x * chunk;
+  const int t1 = min(HW, t0 + chunk);
+  const float* qb = q + ((long long)(q_shared ? 0 : b) * HW) * ldq + h * CH;
+  const float* kb = k + ((long long)(k_shared ? 0 : b) * HW) * ldk + h * CH;
+
+  float g[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g[i][j] = 0.f;
+  float sq[4] = {0.f, 0.f, 0.f, 0.f}, sk[4] = {0.f, 0.f, 0.f, 0.f};
+
+  for (int t = t0; t < t1; t += GT) {
+    const int nt = min(GT, t1 - t);
+    for (int idx = tid; idx < GT * NB; idx += NTH) {
+      const int tt = idx / NB, c4 = idx - tt * NB;
+      float4 vq = make_float4(0.f, 0.f, 0.f, 0.f), vk = vq;
+      if (tt < nt) {
+        vq = ldg4(qb + (long long)(t + tt) * ldq + c4 * 4);
+        vk = ldg4(kb + (long long)(t + tt) * ldk + c4 * 4);
+      }
+      *reinterpret_cast<float4*>(&qs[tt][c4 * 4]) = vq;
+      *reinterpret_cast<float4*>(&ks[tt][c4 * 4]) = vk;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int tt = 0; tt < GT; ++tt) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&qs[tt][bi * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&ks[tt][bj * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g[i][j] = fmaf(a[i], bb[j], g[i][j]);
+      if (bj == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sq[i] = fmaf(a[i], a[i], sq[i]);
+      }
+      if (bi == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sk[j] = fmaf(bb[j], bb[j], sk[j]);
+      }
+    }
+    __syncthreads();
+  }
+  float* dst = partial + ((long long)bh * gridDim.x + blockIdx.x) * (CH * CH + 2 * CH);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(dst + (bi * 4 + i) * CH + bj * 4) = make_float4(g[i][0], g[i][1], g[i][2], g[i][3]);
+  if (bj == 0) *reinterpret_cast<float4*>(dst + CH * CH + bi * 4) = make_float4(sq[0], sq[1], sq[2], sq[3]);
+  if (bi == 0) *reinterpret_cast<float4*>(dst + CH * CH + CH + bj * 4) = make_float4(sk[0], sk[1], sk[2], sk[3]);
+}
+
+static int gram_chunk(int B, int heads, int HW) {
+  // aim for >= ~592 CTAs (4 per SM) but keep chunks in [256, 4096] tokens, multiples of GT
+  long long total = (long long)B * heads * HW;
+  long long chunk = total / 592;
+  if (chunk < 256) chunk = 256;
+  if (chunk > 4096) chunk = 4096;
+  chunk = (chunk + GT - 1) / GT * GT;
+  if (chunk > HW) chunk = (HW + GT - 1) / GT * GT;
+  return (int)chunk;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reduce partials + normalise + temperature + row softmax.  grid = B*heads, 256 threads.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gram_softmax_kernel(const float* __restrict__ partial, int n_chunks,
+                                                           const float* __restrict__ temperature,
+                                                           float* __restrict__ attn, int heads, int c) {
+  extern __shared__ float sm[];
+  const int per = c * c + 2 * c;
+  float* G = sm;  // [c*c + 2c]
+  const int bh = blockIdx.x;
+  const int h = bh % heads;
+  const float* src = partial + (long long)bh * n_chunks * per;
+  for (int e = threadIdx.x; e < per; e += blockDim.x) {
+    float s = 0.f;
+    for (int ch = 0; ch < n_chunks; ++ch) s += __ldg(src + (long long)ch * per + e);
+    G[e] = s;
+  }
+  __syncthreads();
+  // F.normalize: x / max(||x||, 1e-12)
+  for (int e = threadIdx.x; e < 2 * c; e += blockDim.x) G[c * c + e] = fmaxf(sqrtf(G[c * c + e]), 1e-12f);
+  __syncthreads();
+  const float temp = __ldg(temperature + h);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = warp; i < c; i += blockDim.x >> 5) {
+    const float nq = G[c * c + i];
+    float mx = -INFINITY;
+    for (int j = lane; j < c; j += 32) {
+      const float v = G[i * c + j] / (nq * G[c * c + c + j]) * temp;
+      G[i * c + j] = v;
+      mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int j = lane; j < c; j += 32) {
+      const float e = expf(G[i * c + j] - mx);
+      G[i * c + j] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    const float inv = 1.0f / s;
+    for (int j = lane; j < c; j += 32) attn[(long long)bh * c * c + i * c + j] = G[i * c + j] * inv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fold: Mt[b][h*c + j][o] = sum_i WoutT[h*c + i][o] * A[b,h][i][j].  grid = (B*heads, C/64), 256 thr.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) spectral_fold_kernel(const float* __restrict__ attn,
+                                                            const float* __restrict__ WoutT,
+                                                            float* __restrict__ Mt, long long ldm,
+                                                            long long m_batch_stride, int heads, int c) {
+  extern __shared__ float sm[];
+  const int C = heads * c;
+  float* A = sm;            // [c][c]
+  float* Wt = A + c * c;    // [c][64]
+  const int bh = blockIdx.x;
+  const int b = bh / heads, h = bh - b * heads;
+  const int o0 = blockIdx.y * 64;
+  for (int e = threadIdx.x; e < c * c; e += 256) A[e] = __ldg(attn + (long long)bh * c * c + e);
+  for (int e = threadIdx.x; e < c * 64; e += 256) {
+    const int i = e >> 6, o = e & 63;
+    Wt[e] = (o0 + o < C) ? __ldg(WoutT + (long long)(h * c + i) * C + o0 + o) : 0.f;
+  }
+  __syncthreads();
+  const int o = threadIdx.x & 63;
+  for (int j = threadIdx.x >> 6; j < c; j += 4) {
+    float s = 0.f;
+    for (int i = 0; i < c; ++i) s = fmaf(Wt[i * 64 + o], A[i * c + j], s);
+    if (o0 + o < C) Mt[(long long)b * m_batch_stride + (long long)(h * c + j) * ldm + o0 + o] = s;
+  }
+}
+
+}  // namespace mphsir
+
+using namespace mphsir;
+
+extern "C" int mphsir_dwconv3x3_fwd(const float* X, int ldx, const float* w9, float* Y, int ldy, int B, int H,
+                                    int W, int C, int gate_half, void* stream) {
+  MPHSIR_REQUIRE(X && w9 && Y, "dwconv3x3: null operand");
+  MPHSIR_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldx >= C, "dwconv3x3: bad shape C=%d ldx=%d ldy=%d", C, ldx, ldy);
+  MPHSIR_REQUIRE(gate_half == 0 || (2 * gate_half == C && gate_half % 4 == 0), "dwconv3x3: gate_half=%d must be C/2 and a multiple of 4", gate_half);
+  MPHSIR_REQUIRE(((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(w9)) & 15) == 0, "dwconv3x3: operands must be 16-byte aligned");
+  const long long total = (long long)B * H * W * ((gate_half ? gate_half : C) / 4);
+  const int blocks = (int)((total + 255) / 256 > 148LL * 64 ? 148LL * 64 : (total + 255) / 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (gate_half)
+    dwconv3x3_kernel<true><<<blocks, 256, 0, st>>>(X, ldx, w9, Y, ldy, B, H, W, C, gate_half);
+  else
+    dwconv3x3_kernel<false><<<blocks, 256, 0, st>>>(X, ldx, w9, Y, ldy, B, H, W, C, 0);
+  return check_launch("dwconv3x3");
+}
+
+extern "C" size_t mphsir_gram_partial_floats(int B, int heads, int c, int HW, int* n_chunks) {
+  const int chunk = gram_chunk(B, heads, HW);
+  const int n = (HW + chunk - 1) / chunk;
+  if (n_chunks) *n_chunks = n;
+  return (size_t)B * heads * n * ((size_t)c * c + 2 * c);
+}
+
+extern "C" int mphsir_gram_partial_fwd(const float* q, int ldq, int q_shared, const float* k, int ldk,
+                                       int k_shared, float* partial, int B, int HW, int heads, int c,
+                                       void* stream) {
+  MPHSIR_REQUIRE(q && k && partial, "gram_partial: null operand");
+  MPHSIR_REQUIRE(B > 0 && HW > 0 && heads > 0 && ldq % 4 == 0 && ldk % 4 == 0, "gram_partial: bad shape");
+  MPHSIR_REQUIRE(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(partial)) & 15) == 0, "gram_partial: operands must be 16-byte aligned");
+  const int chunk = gram_chunk(B, heads, HW);
+  dim3 grid((HW + chunk - 1) / chunk, B * heads);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (c) {
+    case 32: gram_partial_kernel<32><<<grid, 64, 0, st>>>(q, ldq, q_shared, k, ldk, k_shared, partial, HW, heads, chunk); break;
+    case 48: gram_partial_kernel<48><<<grid, 144, 0, st>>>(q, ldq, q_shared, k, ldk, k_shared, partial, HW, heads, chunk); break;
+    case 64: gram_partial_kernel<64><<<grid, 256, 0, st>>>(q, ldq, q_shared, k, ldk, k_shared, partial, HW, heads, chunk); break;
+    case 96: gram_partial_kernel<96><<<grid, 576, 0, st>>>(q, ldq, q_shared, k, ldk, k_shared, partial, HW, heads, chunk); break;
+    default: MPHSIR_REQUIRE(false, "gram_partial: channels per head %d not in {32,48,64,96}", c);
+  }
+  return check_launch("gram_partial");
+}
+
+extern "C" int mphsir_gram_softmax_fwd(const float* partial, int n_chunks, const float* temperature, float* attn,
+                                       int B, int heads, int c, void* stream) {
+  MPHSIR_REQUIRE(partial && temperature && attn && n_chunks > 0 && B > 0 && heads > 0 && c > 0, "gram_softmax: bad arguments");
+  const size_t smem = sizeof(float) * ((size_t)c * c + 2 * c);
+  gram_softmax_kernel<<<B * heads, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(partial, n_chunks, temperature, attn, heads, c);
+  return check_launch("gram_softmax");
+}
+
+extern "C" int mphsir_spectral_fold_fwd(const float* attn, const float* WoutT, float* Mt, int ldm,
+                                        long long m_batch_stride, int B, int heads, int c, void* stream) {
+  MPHSIR_REQUIRE(attn && WoutT && Mt && B > 0 && heads > 0 && c > 0 && ldm >= heads * c, "spectral_fold: bad arguments");
+  const int C = heads * c;
+  const size_t smem = sizeof(float) * ((size_t)c * c + (size_t)c * 64);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(spectral_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("spectral_fold: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+      return MPHSIR_ERR_CUDA;
+    }
+  }
+  dim3 grid(B * heads, (C + 63) / 64);
+  spectral_fold_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(attn, WoutT, Mt, ldm, m_batch_stride, heads, c);
+  return check_launch("spectral_fold");
+}

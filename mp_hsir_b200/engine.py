@@ -1,0 +1,480 @@
+"""Forward executor: packed weights + workspace + the static kernel sequence of MP_HSIR_Net.forward.
+
+Host logic only (Python): every arithmetic step of the hot path is a libmphsir.so launch
+(mp_hsir_b200/lib.py).  torch is used to allocate device memory, to re-lay-out *weights* once
+(transpose / pad / interleave — data movement, cached until a parameter changes) and to build the
+tiny [B,T] one-hot task weights.
+
+Activation layout: token-major fp32 rows (see include/mphsir.h).  Concatenations of the reference
+(net/MP_HSIR.py:595, :827, :835) never materialise: producers write straight into column slices of
+the consumer's buffer.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import lib
+from .config import PROMPT_LEN, SHIFT, Stage
+from .lib import View
+
+
+def _ceil(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+def _ldb(n: int) -> int:
+    return 64 if n <= 64 else _ceil(n, 128)
+
+
+# ------------------------------------------------------------------------------------------------
+# weight packing (pure data movement; runs once per parameter version)
+# ------------------------------------------------------------------------------------------------
+
+
+def pack_linear_t(w: torch.Tensor, k_pad: Optional[int] = None) -> torch.Tensor:
+    """[out,in] (nn.Linear / squeezed 1x1 conv) -> Bt [Kp, ldb] "in x out", zero padded."""
+    w = w.reshape(w.shape[0], -1)
+    n, k = w.shape
+    kp = _ceil(k if k_pad is None else k_pad, 16)
+    out = w.new_zeros(kp, _ldb(n))
+    out[:k, :n] = w.t()
+    return out.contiguous()
+
+
+def pack_glu_fc1(w: torch.Tensor, b: torch.Tensor, hid: int, hid_pad: int):
+    """GatedMlp.fc1 [2*hid, C]: value rows [0,hid), gate rows [hid,2hid) (net/MP_HSIR.py:77) ->
+    interleaved columns (2j, 2j+1) = (value_j, gate_j), padded to 2*hid_pad columns."""
+    c = w.shape[1]
+    n = 2 * hid_pad
+    wt = w.new_zeros(_ceil(c, 16), _ldb(n))
+    bias = w.new_zeros(_ldb(n))
+    wt[:c, 0:2 * hid:2] = w[:hid].t()
+    wt[:c, 1:2 * hid:2] = w[hid:].t()
+    bias[0:2 * hid:2] = b[:hid]
+    bias[1:2 * hid:2] = b[hid:]
+    return wt.contiguous(), bias.contiguous()
+
+
+def pack_gdfn(project_in: torch.Tensor, dw: torch.Tensor, project_out: torch.Tensor, hid: int, hid_pad: int):
+    """GDFN (net/MP_HSIR.py:380-391): halves of project_in / dwconv placed at [0,hid) and
+    [hid_pad, hid_pad+hid) so the gate kernel sees 16-byte aligned halves."""
+    d = project_in.shape[1]
+    pin = project_in.reshape(2 * hid, d)
+    n = 2 * hid_pad
+    wt = pin.new_zeros(_ceil(d, 16), _ldb(n))
+    wt[:d, :hid] = pin[:hid].t()
+    wt[:d, hid_pad:hid_pad + hid] = pin[hid:].t()
+    w9 = pin.new_zeros(9, n)
+    dwf = dw.reshape(2 * hid, 9)
+    w9[:, :hid] = dwf[:hid].t()
+    w9[:, hid_pad:hid_pad + hid] = dwf[hid:].t()
+    pout = pack_linear_t(project_out.reshape(d, hid), k_pad=hid_pad)
+    return wt.contiguous(), w9.contiguous(), pout
+
+
+def pack_conv3x3(w: torch.Tensor, cin_pad: Optional[int] = None, shuffle: bool = False) -> torch.Tensor:
+    """[Cout,Cin,3,3] -> Wt [9*Cin_p, ldb], row = tap*Cin_p + c, tap = 3*ky + kx.  With
+    ``shuffle`` the output columns are permuted to q*Cn+cn (q = 2i+j) so that the PixelShuffle(2)
+    store of MPHSIR_CONV_SHUFFLE is a 128-bit write (reference order is cn*4+q, net/MP_HSIR.py:447)."""
+    cout, cin = w.shape[:2]
+    cp = _ceil(cin if cin_pad is None else cin_pad, 16)
+    if shuffle:
+        cn = cout // 4
+        w = w.view(cn, 4, cin, 3, 3).permute(1, 0, 2, 3, 4).reshape(cout, cin, 3, 3)
+    out = w.new_zeros(9, cp, _ldb(cout))
+    out[:, :cin, :cout] = w.permute(2, 3, 1, 0).reshape(9, cin, cout)
+    return out.reshape(9 * cp, -1).contiguous()
+
+
+def pack_dw(w: torch.Tensor) -> torch.Tensor:
+    """depthwise [C,1,3,3] -> [9, C]."""
+    return w.reshape(w.shape[0], 9).t().contiguous()
+
+
+def rel_pos_bias(table: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    """pre-gather [225,heads] -> [heads,64,64] (net/MP_HSIR.py:200-202)."""
+    return table[index.reshape(-1)].view(64, 64, -1).permute(2, 0, 1).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+
+
+class Workspace:
+    """Named, grow-only fp32 device buffers; a forward at a fixed shape allocates nothing after the
+    first call (CUDA-graph friendly)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs: Dict[str, torch.Tensor] = {}
+
+    def mat(self, name: str, rows: int, cols: int) -> View:
+        n = rows * cols
+        t = self.bufs.get(name)
+        if t is None or t.numel() < n:
+            t = torch.empty(max(n, 1), device=self.device, dtype=torch.float32)
+            self.bufs[name] = t
+        return View(t.data_ptr(), cols, rows, cols, t)
+
+    def flat(self, name: str, n: int) -> torch.Tensor:
+        t = self.bufs.get(name)
+        if t is None or t.numel() < n:
+            t = torch.empty(max(n, 1), device=self.device, dtype=torch.float32)
+            self.bufs[name] = t
+        return t
+
+    def bytes(self) -> int:
+        return sum(t.numel() * 4 for t in self.bufs.values())
+
+
+class Engine:
+    def __init__(self, net):
+        self.net = net
+        self.cfg = net.cfg
+        p0 = next(net.parameters())
+        if not p0.is_cuda:
+            raise RuntimeError("MP_HSIR_Net parameters must live on a CUDA device before forward()")
+        self.device = p0.device
+        lib.load()
+        with torch.cuda.device(self.device):
+            self.sm_count = lib.device_check(self.device.index or 0)
+        self.ws = Workspace(self.device)
+        self.packed: Optional[dict] = None
+        self._versions = None
+        self._graphs: Dict[tuple, tuple] = {}
+
+    # -- weights -------------------------------------------------------------------------------
+    def invalidate(self):
+        self.packed = None
+        self._graphs.clear()
+
+    def _param_versions(self):
+        return tuple(p._version for p in self.net.parameters())
+
+    def _ensure_packed(self):
+        v = self._param_versions()
+        if self.packed is None or v != self._versions:
+            self.packed = self._pack()
+            self._versions = v
+            self._graphs.clear()
+
+    @torch.no_grad()
+    def _pack(self) -> dict:
+        net, cfg = self.net, self.cfg
+        f32 = lambda t: t.detach().to(device=self.device, dtype=torch.float32)  # noqa: E731
+        P: dict = {}
+        cin_p = _ceil(cfg.in_channel, 16)
+        P["cin_p"] = cin_p
+        P["patch_embed"] = pack_conv3x3(f32(net.patch_embed.proj.weight), cin_pad=cin_p)
+        P["down1_2"] = pack_conv3x3(f32(net.down1_2.body[0].weight))
+        P["down2_3"] = pack_conv3x3(f32(net.down2_3.body[0].weight))
+        P["up3_2"] = pack_conv3x3(f32(net.up3_2.body[0].weight), shuffle=True)
+        P["up2_1"] = pack_conv3x3(f32(net.up2_1.body[0].weight), shuffle=True)
+        P["reduce_chan_level2"] = pack_linear_t(f32(net.reduce_chan_level2.weight))
+        P["output"] = pack_conv3x3(f32(net.output.weight))
+        P["clip"] = f32(net.text_prompt.clip_prompt).contiguous()
+
+        for st in cfg.stages():
+            hid = cfg.hidden(st.dim)
+            hid_pad = _ceil(hid, 16)
+            blocks = []
+            for blk in getattr(net, st.name).blocks:
+                d = {"hid_pad": hid_pad}
+                d["ln1"] = (f32(blk.norm1.weight).contiguous(), f32(blk.norm1.bias).contiguous())
+                d["ln2"] = (f32(blk.norm2.weight).contiguous(), f32(blk.norm2.bias).contiguous())
+                a = blk.attn
+                d["qkv_w"] = pack_linear_t(f32(a.qkv.weight))
+                d["qkv_b"] = f32(a.qkv.bias).contiguous()
+                d["proj_w"] = pack_linear_t(f32(a.proj.weight))
+                d["proj_b"] = f32(a.proj.bias).contiguous()
+                d["rpb"] = rel_pos_bias(f32(a.relative_position_bias_table), a.relative_position_index.to(self.device))
+                g = blk.gobal_spectral_attn
+                d["temp"] = f32(g.temperature).reshape(-1).contiguous()
+                d["sqkv_w"] = pack_linear_t(f32(g.qkv.weight))
+                d["sdw"] = pack_dw(f32(g.qkv_dwconv.weight))
+                d["sout_t"] = f32(g.project_out.weight).reshape(st.dim, st.dim).t().contiguous()
+                l = blk.local_spectral_attn
+                r = st.rank
+                d["gate"] = {
+                    "projT": f32(a.proj.weight).t().contiguous(),
+                    "projb": d["proj_b"],
+                    "promptT": f32(l.linear_prompt.weight).t().contiguous(),
+                    "downT": f32(l.linear_down.weight).t().contiguous(),
+                    "param": f32(l.prompt_param).reshape(PROMPT_LEN, r).contiguous(),
+                    "qT": f32(l.q.weight).t().contiguous(),
+                    "kvT": f32(l.kv.weight).t().contiguous(),
+                    "p2T": f32(l.proj.weight).t().contiguous(),
+                    "p2b": f32(l.proj.bias).contiguous(),
+                    "upT": f32(l.linear_up.weight).t().contiguous(),
+                }
+                d["fc1_w"], d["fc1_b"] = pack_glu_fc1(f32(blk.mlp.fc1.weight), f32(blk.mlp.fc1.bias), hid, hid_pad)
+                d["fc2_w"] = pack_linear_t(f32(blk.mlp.fc2.weight), k_pad=hid_pad)
+                d["fc2_b"] = f32(blk.mlp.fc2.bias).contiguous()
+                blocks.append(d)
+            P[st.name] = blocks
+
+        def ln(m):
+            return (f32(m.body.weight).contiguous(), f32(m.body.bias).contiguous())
+
+        for name in ("prompt1", "prompt2"):
+            m = getattr(net, name)
+            D = m.visual_prompt.shape[1]
+            ps = m.prompt_size
+            hid = cfg.hidden(D)
+            hid_pad = _ceil(hid, 16)
+            ct = m.cross_transformer
+            d = {"D": D, "ps": ps, "hid_pad": hid_pad}
+            d["learnable"] = f32(m.text_prompt_learnable).reshape(cfg.task_classes, D).contiguous()
+            d["visual"] = f32(m.visual_prompt)[0].permute(1, 2, 0).reshape(ps * ps, D).contiguous()
+            d["ln11"], d["ln12"], d["ln2"] = ln(ct.norm11), ln(ct.norm12), ln(ct.norm2)
+            d["q_w"] = pack_linear_t(f32(ct.attn.q.weight))
+            d["q_dw"] = pack_dw(f32(ct.attn.q_dwconv.weight))
+            d["kv_w"] = pack_linear_t(f32(ct.attn.kv.weight))
+            d["kv_dw"] = pack_dw(f32(ct.attn.kv_dwconv.weight))
+            d["temp"] = f32(ct.attn.temperature).reshape(-1).contiguous()
+            d["out_t"] = f32(ct.attn.project_out.weight).reshape(D, D).t().contiguous()
+            d["pin_w"], d["ffn_dw"], d["pout_w"] = pack_gdfn(
+                f32(ct.ffn.project_in.weight), f32(ct.ffn.dwconv.weight), f32(ct.ffn.project_out.weight), hid, hid_pad)
+            d["conv_last"] = pack_conv3x3(f32(m.conv_last.weight))
+            P[name] = d
+
+        for name in ("fusion1", "fusion2"):
+            m = getattr(net, name)
+            tb = m.transformer
+            C2 = tb.norm1.body.weight.shape[0]
+            hid = cfg.hidden(C2)
+            hid_pad = _ceil(hid, 16)
+            d = {"C": C2, "heads": m.heads, "hid_pad": hid_pad}
+            d["ln1"], d["ln2"] = ln(tb.norm1), ln(tb.norm2)
+            d["qkv_w"] = pack_linear_t(f32(tb.attn.qkv.weight))
+            d["dw"] = pack_dw(f32(tb.attn.qkv_dwconv.weight))
+            d["temp"] = f32(tb.attn.temperature).reshape(-1).contiguous()
+            d["out_t"] = f32(tb.attn.project_out.weight).reshape(C2, C2).t().contiguous()
+            d["pin_w"], d["ffn_dw"], d["pout_w"] = pack_gdfn(
+                f32(tb.ffn.project_in.weight), f32(tb.ffn.dwconv.weight), f32(tb.ffn.project_out.weight), hid, hid_pad)
+            d["conv_w"] = pack_linear_t(f32(m.conv.weight))
+            P[name] = d
+        return P
+
+    # -- building blocks -------------------------------------------------------------------------
+    def _spectral_attention(self, tag: str, q: View, q_shared: bool, k: View, k_shared: bool, temp, out_t,
+                            B: int, HW: int, heads: int, c: int) -> torch.Tensor:
+        """Gram statistics -> softmax -> folded per-sample matrix Mt [B, C, ldm] ("in x out")."""
+        ws = self.ws
+        C = heads * c
+        nfl, nch = lib.gram_partial_floats(B, heads, c, HW)
+        partial = ws.flat(tag + ".partial", nfl)
+        attn = ws.flat(tag + ".attn", B * heads * c * c)
+        ldm = _ldb(C)
+        Mt = ws.flat(tag + ".Mt", B * _ceil(C, 16) * ldm).view(-1)[: B * _ceil(C, 16) * ldm].view(B, _ceil(C, 16), ldm)
+        lib.gram_partial(q, q_shared, k, k_shared, partial, B, HW, heads, c)
+        lib.gram_softmax(partial, nch, temp, attn, B, heads, c)
+        lib.spectral_fold(attn, out_t, Mt, B, heads, c)
+        return Mt
+
+    def _pgsstb(self, w: dict, st: Stage, shift: int, x: View, out: View, res2: Optional[View], B: int, H: int,
+                W: int, row_scales=None, taps: Optional[dict] = None):
+        ws = self.ws
+        C, heads = st.dim, st.heads
+        N = B * H * W
+        B_ = N // 64
+        qkv = ws.mat("qkv", N, 3 * C)
+        core = ws.mat("core", N, C)
+        sa = ws.mat("sa", N, C)
+        dw3 = ws.mat("dw3", N, 3 * C)
+        mid = ws.mat("mid", N, C)
+        hidden = ws.mat("hidden", N, w["hid_pad"])
+        wmean = ws.flat("wmean", B_ * C)
+        gate = ws.flat("gate", B_ * C)
+        s1 = None if row_scales is None else row_scales[0]
+        s2 = None if row_scales is None else row_scales[1]
+
+        # LN1 + qkv projection (net/MP_HSIR.py:667, :195)
+        lib.gemm(x, w["qkv_w"], qkv, 3 * C, ln=w["ln1"], bias=w["qkv_b"])
+        # shifted-window attention core + per-window mean (:671-683, :198-215)
+        lib.window_attn(qkv, w["rpb"], core, wmean, B, H, W, C, heads, shift)
+        # local spectral gate (:132-152)
+        lib.local_gate(wmean, w["gate"], gate, B_, C, st.rank)
+        # attention output projection (:216) in image order
+        lib.gemm(core, w["proj_w"], sa, C, bias=w["proj_b"])
+        # global spectral attention: 1x1 -> dw3x3 -> Gram/softmax/fold -> apply (:98-113)
+        t3 = ws.mat("qkv", N, 3 * C)  # qkv is dead: reuse
+        lib.gemm(sa, w["sqkv_w"], t3, 3 * C)
+        lib.dwconv3x3(t3, w["sdw"], dw3, B, H, W, 3 * C)
+        Mt = self._spectral_attention("spec", dw3.cols_slice(0, C), False, dw3.cols_slice(C, 2 * C), False,
+                                      w["temp"], w["sout_t"], B, H * W, heads, C // heads)
+        # x = shortcut + DropPath(sa*gate + project_out(attn v))   (:715-718)
+        lib.gemm(dw3.cols_slice(2 * C, 3 * C), Mt, mid, C, epi=lib.EPI_SPECTRAL, res1=x, gsrc=sa, gate=gate,
+                 H=H, W=W, shift=shift, rows_per_batch=H * W, b_batch_stride=Mt.shape[1] * Mt.shape[2],
+                 row_scale=s1)
+        # x = x + DropPath(fc2(value * gelu(gate)))  with LN2 fused in front (:719, :76-82)
+        lib.gemm(mid, w["fc1_w"], hidden, 2 * w["hid_pad"], ln=w["ln2"], bias=w["fc1_b"], epi=lib.EPI_GLU)
+        lib.gemm(hidden, w["fc2_w"], out, C, bias=w["fc2_b"], epi=lib.EPI_RESIDUAL, res1=mid, res2=res2,
+                 rows_per_batch=H * W, row_scale=s2)
+        if taps is not None:
+            taps.update(core=core.torch().clone(), wmean=wmean[: B_ * C].view(B_, C).clone(),
+                        gate=gate[: B_ * C].view(B_, C).clone(), sa=sa.torch().clone(), mid=mid.torch().clone(),
+                        out=out.torch().clone())
+
+    def _stage(self, name: str, x_in: View, out: View, B: int, H: int, W: int):
+        st = {s.name: s for s in self.cfg.stages()}[name]
+        blocks = self.packed[name]
+        N = B * H * W
+        ping = [self.ws.mat("xping", N, st.dim), self.ws.mat("xpong", N, st.dim)]
+        x = x_in
+        for i, w in enumerate(blocks):
+            last = i == len(blocks) - 1
+            dst = out if last else ping[i % 2]
+            # BaseBlock residual `x + shortcut` (net/MP_HSIR.py:760) rides on the last fc2 epilogue
+            self._pgsstb(w, st, SHIFT if i % 2 else 0, x, dst, x_in if last else None, B, H, W)
+            x = dst
+
+    def _gdfn(self, tag: str, w: dict, x: View, out: View, ln, B: int, H: int, W: int, D: int):
+        """x + GDFN(LN(x)) (net/MP_HSIR.py:477, :286, :386-391)."""
+        N = B * H * W
+        hp = w["hid_pad"]
+        hin = self.ws.mat(tag + ".hin", N, 2 * hp)
+        hg = self.ws.mat(tag + ".hg", N, hp)
+        lib.gemm(x, w["pin_w"], hin, 2 * hp, ln=ln)
+        lib.dwconv3x3(hin, w["ffn_dw"], hg, B, H, W, 2 * hp, gate_half=hp)
+        lib.gemm(hg, w["pout_w"], out, D, epi=lib.EPI_RESIDUAL, res1=x)
+
+    def _tvsp(self, name: str, clip_b: torch.Tensor, weights: torch.Tensor, B: int, Hs: int, Ws: int, out: View):
+        """TVSP.forward (net/MP_HSIR.py:572-583) -> writes [B*Hs*Ws, D] into `out` (a column slice)."""
+        w = self.packed[name]
+        ws = self.ws
+        D, ps = w["D"], w["ps"]
+        T = self.cfg.task_classes
+        n = ps * ps
+        Q = ws.mat(name + ".Q", B * n, D)
+        lib.tvsp_query(clip_b, weights, w["learnable"], Q, B, T, D, ps)
+        q1 = ws.mat(name + ".q1", B * n, D)
+        qd = ws.mat(name + ".qd", B * n, D)
+        lib.gemm(Q, w["q_w"], q1, D, ln=w["ln11"])
+        lib.dwconv3x3(q1, w["q_dw"], qd, B, ps, ps, D)
+        vis = View.of(w["visual"])
+        kv1 = ws.mat(name + ".kv1", n, 2 * D)
+        kvd = ws.mat(name + ".kvd", n, 2 * D)
+        lib.gemm(vis, w["kv_w"], kv1, 2 * D, ln=w["ln12"])
+        lib.dwconv3x3(kv1, w["kv_dw"], kvd, 1, ps, ps, 2 * D)
+        Mt = self._spectral_attention(name + ".spec", qd, False, kvd.cols_slice(0, D), True, w["temp"], w["out_t"],
+                                      B, n, 2, D // 2)
+        xa = ws.mat(name + ".xa", B * n, D)
+        lib.gemm(kvd.cols_slice(D, 2 * D), Mt, xa, D, epi=lib.EPI_RESIDUAL, res1=Q, rows_per_batch=n,
+                 b_batch_stride=Mt.shape[1] * Mt.shape[2], a_row_mod=n, M=B * n)
+        pr = ws.mat(name + ".pr", B * n, D)
+        self._gdfn(name + ".ffn", w, xa, pr, w["ln2"], B, ps, ps, D)
+        if (Hs, Ws) != (ps, ps):
+            prr = ws.mat(name + ".prr", B * Hs * Ws, D)
+            lib.bilinear(pr, prr, B, ps, ps, Hs, Ws, D)
+            pr = prr
+        lib.conv3x3(pr, w["conv_last"], out.ptr, out.ld, B, Hs, Ws, D, D, lib.CONV_TOKENS)
+
+    def _fusion(self, name: str, xcat: View, out: View, B: int, H: int, W: int):
+        """PromptFusion.forward (net/MP_HSIR.py:594-599) on the already-concatenated buffer."""
+        w = self.packed[name]
+        ws = self.ws
+        C2, heads = w["C"], w["heads"]
+        N = B * H * W
+        t3 = ws.mat(name + ".t3", N, 3 * C2)
+        dw3 = ws.mat(name + ".dw3", N, 3 * C2)
+        lib.gemm(xcat, w["qkv_w"], t3, 3 * C2, ln=w["ln1"])
+        lib.dwconv3x3(t3, w["dw"], dw3, B, H, W, 3 * C2)
+        Mt = self._spectral_attention(name + ".spec", dw3.cols_slice(0, C2), False, dw3.cols_slice(C2, 2 * C2), False,
+                                      w["temp"], w["out_t"], B, H * W, heads, C2 // heads)
+        y1 = ws.mat(name + ".y1", N, C2)
+        lib.gemm(dw3.cols_slice(2 * C2, 3 * C2), Mt, y1, C2, epi=lib.EPI_RESIDUAL, res1=xcat, rows_per_batch=H * W,
+                 b_batch_stride=Mt.shape[1] * Mt.shape[2])
+        y2 = ws.mat(name + ".y2", N, C2)
+        self._gdfn(name + ".ffn", w, y1, y2, w["ln2"], B, H, W, C2)
+        lib.gemm(y2, w["conv_w"], out, out.cols)
+
+    # -- whole network ----------------------------------------------------------------------------
+    def task_weights(self, task_id: torch.Tensor) -> torch.Tensor:
+        """prompt_weights of Text_Prompt.forward (net/MP_HSIR.py:519-525) as fp32 [B,T]."""
+        T = self.cfg.task_classes
+        tid = task_id.to(self.device).long()
+        w = F.one_hot(tid, T).to(torch.float32)
+        if tid.dim() > 1:
+            w = w.mean(dim=1)
+        return w.contiguous()
+
+    @torch.no_grad()
+    def forward(self, inp: torch.Tensor, task_id: torch.Tensor) -> torch.Tensor:
+        cfg = self.cfg
+        if inp.dim() != 4 or inp.shape[1] != cfg.in_channel:
+            raise ValueError(f"expected input [B,{cfg.in_channel},H,W], got {tuple(inp.shape)}")
+        B, _, H, W = inp.shape
+        if H % 32 or W % 32:
+            raise ValueError(f"H and W must be multiples of 32 (two 2x down-samplings x window 8), got {H}x{W}")
+        if task_id.shape[0] != B:
+            raise ValueError("task_id batch dimension does not match the input")
+        if inp.device != self.device:
+            raise RuntimeError(f"input on {inp.device} but parameters on {self.device}")
+        if cfg.in_channel != cfg.out_channel:
+            raise ValueError("global residual requires in_channel == out_channel (net/MP_HSIR.py:841)")
+        self._ensure_packed()
+        x = inp.detach().to(torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            weights = self.task_weights(task_id)
+            out = torch.empty_like(x)
+            self._run(x, weights, out)
+        return out.to(inp.dtype)
+
+    def _run(self, x: torch.Tensor, weights: torch.Tensor, out: torch.Tensor, taps: Optional[dict] = None):
+        cfg, P, ws = self.cfg, self.packed, self.ws
+        B, _, H, W = x.shape
+        d = cfg.dim
+        N1, N2, N3 = B * H * W, B * H * W // 4, B * H * W // 16
+        H2, W2, H3, W3 = H // 2, W // 2, H // 4, W // 4
+        T = cfg.task_classes
+
+        clip_b = ws.flat("clip_b", B * 512)
+        lib.text_prompt(weights, P["clip"], clip_b, B, T)
+
+        tok = ws.mat("tok_in", N1, P["cin_p"])
+        lib.nchw_to_tokens(x, tok)
+        x1 = ws.mat("x1", N1, d)
+        lib.conv3x3(tok, P["patch_embed"], x1.ptr, x1.ld, B, H, W, P["cin_p"], d)
+
+        fcat1 = ws.mat("fcat1", N1, 2 * d)          # [e1 | prompt1]
+        e1 = fcat1.cols_slice(0, d)
+        self._stage("encoder_level1", x1, e1, B, H, W)
+
+        x2 = ws.mat("x2", N2, 2 * d)
+        lib.conv3x3(e1, P["down1_2"], x2.ptr, x2.ld, B, H, W, d, d // 2, lib.CONV_UNSHUFFLE)
+        fcat2 = ws.mat("fcat2", N2, 4 * d)          # [e2 | prompt2]
+        e2 = fcat2.cols_slice(0, 2 * d)
+        self._stage("encoder_level2", x2, e2, B, H2, W2)
+
+        x3 = ws.mat("x3", N3, 4 * d)
+        lib.conv3x3(e2, P["down2_3"], x3.ptr, x3.ld, B, H2, W2, 2 * d, d, lib.CONV_UNSHUFFLE)
+        lat = ws.mat("lat", N3, 4 * d)
+        self._stage("latent", x3, lat, B, H3, W3)
+
+        cat2 = ws.mat("cat2", N2, 4 * d)            # [up3_2(latent) | fusion2]
+        lib.conv3x3(lat, P["up3_2"], cat2.ptr, cat2.ld, B, H3, W3, 4 * d, 8 * d, lib.CONV_SHUFFLE)
+        self._tvsp("prompt2", clip_b, weights, B, H2, W2, fcat2.cols_slice(2 * d, 4 * d))
+        self._fusion("fusion2", fcat2, cat2.cols_slice(2 * d, 4 * d), B, H2, W2)
+        d2in = ws.mat("d2in", N2, 2 * d)
+        lib.gemm(cat2, P["reduce_chan_level2"], d2in, 2 * d)
+        d2 = ws.mat("d2", N2, 2 * d)
+        self._stage("decoder_level2", d2in, d2, B, H2, W2)
+
+        cat1 = ws.mat("cat1", N1, 2 * d)            # [up2_1(d2) | fusion1]
+        lib.conv3x3(d2, P["up2_1"], cat1.ptr, cat1.ld, B, H2, W2, 2 * d, 4 * d, lib.CONV_SHUFFLE)
+        self._tvsp("prompt1", clip_b, weights, B, H, W, fcat1.cols_slice(d, 2 * d))
+        self._fusion("fusion1", fcat1, cat1.cols_slice(d, 2 * d), B, H, W)
+        dd1 = ws.mat("dd1", N1, 2 * d)
+        self._stage("decoder_level1", cat1, dd1, B, H, W)
+        ref = ws.mat("ref", N1, 2 * d)
+        self._stage("refinement", dd1, ref, B, H, W)
+
+        lib.conv3x3(ref, P["output"], out.data_ptr(), 0, B, H, W, 2 * d, cfg.out_channel, lib.CONV_NCHW_RES, R=x)
+        if taps is not None:
+            taps.update(x1=x1.torch().clone(), e1=e1.torch().clone(), e2=e2.torch().clone(), lat=lat.torch().clone(),
+                        p1=fcat1.cols_slice(d, 2 * d).torch().clone(), p2=fcat2.cols_slice(2 * d, 4 * d).torch().clone(),
+                        f1=cat1.cols_slice(d, 2 * d).torch().clone(), f2=cat2.cols_slice(2 * d, 4 * d).torch().clone(),
+                        d1=ref.torch().clone())

@@ -1,0 +1,261 @@
+"""ctypes binding of libmphsir.so (the C ABI in include/mphsir.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every compute call below goes
+through the C ABI with raw device pointers.  There is NO fallback: if the library is missing or
+a call fails, a RuntimeError carrying ``mphsir_last_error()`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmphsir.so")
+
+_lib: Optional[C.CDLL] = None
+LAUNCHES = 0  # number of kernel-launching ABI calls made by this process (bench.py reports it)
+
+
+class GemmParams(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("lda", C.c_int), ("a_row_mod", C.c_int),
+        ("Bt", C.c_void_p), ("ldb", C.c_int),
+        ("b_batch_stride", C.c_longlong), ("rows_per_batch", C.c_int),
+        ("Y", C.c_void_p), ("ldy", C.c_int),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+        ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p),
+        ("bias", C.c_void_p), ("epi", C.c_int),
+        ("res1", C.c_void_p), ("ldr1", C.c_int),
+        ("res2", C.c_void_p), ("ldr2", C.c_int),
+        ("gsrc", C.c_void_p), ("ldg", C.c_int),
+        ("gate", C.c_void_p),
+        ("H", C.c_int), ("W", C.c_int), ("shift", C.c_int),
+        ("row_scale", C.c_void_p),
+    ]
+
+
+class ConvParams(C.Structure):
+    _fields_ = [
+        ("X", C.c_void_p), ("ldx", C.c_int),
+        ("Wt", C.c_void_p), ("ldb", C.c_int),
+        ("Y", C.c_void_p), ("ldy", C.c_int),
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("N", C.c_int),
+        ("out_mode", C.c_int),
+        ("R", C.c_void_p),
+    ]
+
+
+class LocalGateParams(C.Structure):
+    _fields_ = [("core_mean", C.c_void_p)] + [
+        (n, C.c_void_p) for n in ("projT", "projb", "promptT", "downT", "param", "qT", "kvT", "p2T", "p2b", "upT")
+    ] + [("gate", C.c_void_p), ("B_", C.c_int), ("C", C.c_int), ("r", C.c_int)]
+
+
+EPI_BIAS, EPI_RESIDUAL, EPI_GLU, EPI_SPECTRAL = 0, 1, 2, 3
+CONV_TOKENS, CONV_UNSHUFFLE, CONV_SHUFFLE, CONV_NCHW_RES = 0, 1, 2, 3
+
+# symbol -> (restype, argtypes); also the list tests/test_abi.py checks against include/mphsir.h
+_VP, _I, _LL = C.c_void_p, C.c_int, C.c_longlong
+SIGNATURES = {
+    "mphsir_version": (_I, []),
+    "mphsir_last_error": (C.c_char_p, []),
+    "mphsir_device_check": (_I, [_I, C.POINTER(_I)]),
+    "mphsir_nchw_to_tokens": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
+    "mphsir_gemm_fwd": (_I, [C.POINTER(GemmParams), _VP]),
+    "mphsir_conv3x3_fwd": (_I, [C.POINTER(ConvParams), _VP]),
+    "mphsir_window_attn_fwd": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _VP]),
+    "mphsir_local_gate_fwd": (_I, [C.POINTER(LocalGateParams), _VP]),
+    "mphsir_dwconv3x3_fwd": (_I, [_VP, _I, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
+    "mphsir_gram_partial_floats": (C.c_size_t, [_I, _I, _I, _I, C.POINTER(_I)]),
+    "mphsir_gram_partial_fwd": (_I, [_VP, _I, _I, _VP, _I, _I, _VP, _I, _I, _I, _I, _VP]),
+    "mphsir_gram_softmax_fwd": (_I, [_VP, _I, _VP, _VP, _I, _I, _I, _VP]),
+    "mphsir_spectral_fold_fwd": (_I, [_VP, _VP, _VP, _I, _LL, _I, _I, _I, _VP]),
+    "mphsir_tvsp_query_fwd": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
+    "mphsir_bilinear_fwd": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
+    "mphsir_text_prompt_fwd": (_I, [_VP, _VP, _VP, _I, _I, _VP]),
+}
+
+
+def load() -> C.CDLL:
+    """dlopen libmphsir.so and declare every prototype.  Raises if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m mp_hsir_b200.build` "
+            "(there is no CPU / PyTorch fallback for the MP-HSIR hot path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mphsir_version() < 100:
+        raise RuntimeError("libmphsir.so is older than this Python package; rebuild it")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().mphsir_last_error().decode(errors="replace")
+
+
+def _check(rc: int, what: str) -> None:
+    global LAUNCHES
+    if rc != 0:
+        raise RuntimeError(f"libmphsir {what} failed (rc={rc}): {last_error()}")
+    LAUNCHES += 1
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class View:
+    """A token-major fp32 matrix living inside a (possibly wider) device buffer."""
+
+    __slots__ = ("ptr", "ld", "rows", "cols", "keep")
+
+    def __init__(self, ptr_: int, ld: int, rows: int, cols: int, keep=None):
+        self.ptr, self.ld, self.rows, self.cols, self.keep = ptr_, ld, rows, cols, keep
+
+    @staticmethod
+    def of(t: torch.Tensor) -> "View":
+        assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous() and t.dim() == 2
+        return View(t.data_ptr(), t.shape[1], t.shape[0], t.shape[1], t)
+
+    def cols_slice(self, c0: int, c1: int) -> "View":
+        assert 0 <= c0 < c1 <= self.cols and c0 % 4 == 0
+        return View(self.ptr + 4 * c0, self.ld, self.rows, c1 - c0, self.keep)
+
+    def rows_slice(self, r0: int, r1: int) -> "View":
+        return View(self.ptr + 4 * r0 * self.ld, self.ld, r1 - r0, self.cols, self.keep)
+
+    def torch(self) -> torch.Tensor:
+        """Materialise as a torch tensor (debug / tests only)."""
+        base = self.keep
+        off = (self.ptr - base.data_ptr()) // 4
+        return base.reshape(-1).as_strided((self.rows, self.cols), (self.ld, 1), off)
+
+
+# ------------------------------------------------------------------------------------------
+# thin typed wrappers
+# ------------------------------------------------------------------------------------------
+
+
+def device_check(device: int) -> int:
+    n = C.c_int(0)
+    rc = load().mphsir_device_check(device, C.byref(n))
+    if rc != 0:
+        raise RuntimeError(f"libmphsir device check failed: {last_error()}")
+    return n.value
+
+
+def nchw_to_tokens(inp: torch.Tensor, out: View) -> None:
+    B, Cc, H, W = inp.shape
+    _check(load().mphsir_nchw_to_tokens(inp.data_ptr(), out.ptr, B, Cc, H * W, out.ld, stream_ptr()), "nchw_to_tokens")
+
+
+def gemm(A: View, Bt: torch.Tensor, Y: View, N: int, *, K: Optional[int] = None, ln=None, bias=None,
+         epi: int = EPI_BIAS, res1: Optional[View] = None, res2: Optional[View] = None,
+         gsrc: Optional[View] = None, gate: Optional[torch.Tensor] = None, H: int = 0, W: int = 0,
+         shift: int = 0, rows_per_batch: int = 0, b_batch_stride: int = 0, a_row_mod: int = 0,
+         M: Optional[int] = None, row_scale: Optional[torch.Tensor] = None) -> None:
+    p = GemmParams()
+    p.A, p.lda, p.a_row_mod = A.ptr, A.ld, a_row_mod
+    p.Bt, p.ldb = Bt.data_ptr(), Bt.shape[-1]
+    p.b_batch_stride, p.rows_per_batch = b_batch_stride, rows_per_batch
+    p.Y, p.ldy = Y.ptr, Y.ld
+    p.M, p.N, p.K = (A.rows if M is None else M), N, (A.cols if K is None else K)
+    if ln is not None:
+        p.ln_gamma, p.ln_beta = ln[0].data_ptr(), ln[1].data_ptr()
+    p.bias = ptr(bias)
+    p.epi = epi
+    if res1 is not None:
+        p.res1, p.ldr1 = res1.ptr, res1.ld
+    if res2 is not None:
+        p.res2, p.ldr2 = res2.ptr, res2.ld
+    if gsrc is not None:
+        p.gsrc, p.ldg = gsrc.ptr, gsrc.ld
+    p.gate = ptr(gate)
+    p.H, p.W, p.shift = H, W, shift
+    p.row_scale = ptr(row_scale)
+    _check(load().mphsir_gemm_fwd(C.byref(p), stream_ptr()), "gemm_fwd")
+
+
+def conv3x3(X: View, Wt: torch.Tensor, Y_ptr: int, ldy: int, B: int, H: int, W: int, Cin: int, N: int,
+            out_mode: int = CONV_TOKENS, R: Optional[torch.Tensor] = None) -> None:
+    p = ConvParams()
+    p.X, p.ldx = X.ptr, X.ld
+    p.Wt, p.ldb = Wt.data_ptr(), Wt.shape[-1]
+    p.Y, p.ldy = Y_ptr, ldy
+    p.B, p.H, p.W, p.Cin, p.N = B, H, W, Cin, N
+    p.out_mode = out_mode
+    p.R = ptr(R)
+    _check(load().mphsir_conv3x3_fwd(C.byref(p), stream_ptr()), "conv3x3_fwd")
+
+
+def window_attn(qkv: View, bias: torch.Tensor, out: View, win_mean: torch.Tensor, B: int, H: int, W: int,
+                Cc: int, heads: int, shift: int) -> None:
+    _check(load().mphsir_window_attn_fwd(qkv.ptr, qkv.ld, bias.data_ptr(), out.ptr, out.ld, win_mean.data_ptr(),
+                                         B, H, W, Cc, heads, shift, stream_ptr()), "window_attn_fwd")
+
+
+def local_gate(core_mean: torch.Tensor, w: dict, gate: torch.Tensor, B_: int, Cc: int, r: int) -> None:
+    p = LocalGateParams()
+    p.core_mean = core_mean.data_ptr()
+    for n in ("projT", "projb", "promptT", "downT", "param", "qT", "kvT", "p2T", "p2b", "upT"):
+        setattr(p, n, w[n].data_ptr())
+    p.gate, p.B_, p.C, p.r = gate.data_ptr(), B_, Cc, r
+    _check(load().mphsir_local_gate_fwd(C.byref(p), stream_ptr()), "local_gate_fwd")
+
+
+def dwconv3x3(X: View, w9: torch.Tensor, Y: View, B: int, H: int, W: int, Cc: int, gate_half: int = 0) -> None:
+    _check(load().mphsir_dwconv3x3_fwd(X.ptr, X.ld, w9.data_ptr(), Y.ptr, Y.ld, B, H, W, Cc, gate_half,
+                                       stream_ptr()), "dwconv3x3_fwd")
+
+
+def gram_partial_floats(B: int, heads: int, c: int, HW: int):
+    n = C.c_int(0)
+    f = load().mphsir_gram_partial_floats(B, heads, c, HW, C.byref(n))
+    return int(f), n.value
+
+
+def gram_partial(q: View, q_shared: bool, k: View, k_shared: bool, partial: torch.Tensor, B: int, HW: int,
+                 heads: int, c: int) -> None:
+    _check(load().mphsir_gram_partial_fwd(q.ptr, q.ld, int(q_shared), k.ptr, k.ld, int(k_shared),
+                                          partial.data_ptr(), B, HW, heads, c, stream_ptr()), "gram_partial_fwd")
+
+
+def gram_softmax(partial: torch.Tensor, n_chunks: int, temperature: torch.Tensor, attn: torch.Tensor, B: int,
+                 heads: int, c: int) -> None:
+    _check(load().mphsir_gram_softmax_fwd(partial.data_ptr(), n_chunks, temperature.data_ptr(), attn.data_ptr(),
+                                          B, heads, c, stream_ptr()), "gram_softmax_fwd")
+
+
+def spectral_fold(attn: torch.Tensor, WoutT: torch.Tensor, Mt: torch.Tensor, B: int, heads: int, c: int) -> None:
+    # Mt: [B, Cp, ldm]
+    _check(load().mphsir_spectral_fold_fwd(attn.data_ptr(), WoutT.data_ptr(), Mt.data_ptr(), Mt.shape[2],
+                                           Mt.shape[1] * Mt.shape[2], B, heads, c, stream_ptr()), "spectral_fold_fwd")
+
+
+def tvsp_query(clip_b: torch.Tensor, weights: torch.Tensor, learnable: torch.Tensor, Q: View, B: int, T: int,
+               D: int, ps: int) -> None:
+    _check(load().mphsir_tvsp_query_fwd(clip_b.data_ptr(), weights.data_ptr(), learnable.data_ptr(), Q.ptr, B, T, D,
+                                        ps, stream_ptr()), "tvsp_query_fwd")
+
+
+def bilinear(X: View, Y: View, B: int, h: int, w: int, H: int, W: int, Cc: int) -> None:
+    _check(load().mphsir_bilinear_fwd(X.ptr, X.ld, Y.ptr, Y.ld, B, h, w, H, W, Cc, stream_ptr()), "bilinear_fwd")
+
+
+def text_prompt(weights: torch.Tensor, clip: torch.Tensor, clip_b: torch.Tensor, B: int, T: int) -> None:
+    _check(load().mphsir_text_prompt_fwd(weights.data_ptr(), clip.data_ptr(), clip_b.data_ptr(), B, T, stream_ptr()),
+           "text_prompt_fwd")

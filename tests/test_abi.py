@@ -1,0 +1,58 @@
+"""CPU: the C-ABI library builds, loads, and exports every symbol include/mphsir.h declares.
+No compute call is made (there is no GPU in the authoring container)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from mp_hsir_b200 import build, lib
+from tests.conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def so_path():
+    return build.build()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mphsir.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mphsir_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_expected_surface():
+    syms = declared_symbols()
+    assert "mphsir_gemm_fwd" in syms and "mphsir_window_attn_fwd" in syms and len(syms) >= 15
+
+
+def test_library_exports_every_declared_symbol(so_path):
+    dll = ctypes.CDLL(so_path)
+    for s in declared_symbols():
+        assert hasattr(dll, s), f"{s} declared in mphsir.h but not exported"
+    assert dll.mphsir_version() == 100
+
+
+def test_python_binding_covers_header(so_path):
+    assert sorted(lib.SIGNATURES) == declared_symbols()
+    lib.load()
+
+
+def test_only_abi_symbols_are_exported(so_path):
+    out = subprocess.run(["nm", "-D", "--defined-only", so_path], capture_output=True, text=True).stdout
+    exported = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    assert exported and all(s.startswith("mphsir_") for s in exported), exported
+
+
+def test_library_is_sm100a_only(so_path):
+    out = subprocess.run(["cuobjdump", "-lelf", so_path], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_struct_layouts_match_header():
+    # 64-bit pointers, natural alignment: sizes computed by hand from include/mphsir.h
+    assert ctypes.sizeof(lib.GemmParams) == 8 + 4 + 4 + 8 + 4 + 4 + 8 + 4 + 4 + 8 + 4 + 4 * 3 + 8 * 3 + 4 + 4 + 8 + 4 + 4 + 8 + 4 + 4 + 8 + 4 + 4 + 8 + 4 * 3 + 4 + 8
+    assert ctypes.sizeof(lib.ConvParams) == 8 + 8 + 8 + 8 + 8 + 8 + 4 * 5 + 4 + 8
+    assert ctypes.sizeof(lib.LocalGateParams) == 8 * 12 + 16

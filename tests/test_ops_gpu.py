@@ -1,0 +1,305 @@
+"""GPU: every C-ABI op of libmphsir.so against the CPU oracle on seeded inputs (fp32).
+
+Tolerance: the north_star fp32 bound is max|d|/max|ref| <= 1e-4 end to end; single ops are held to
+2e-5 (fp32 re-association noise only — the library accumulates in fp32 FFMA).
+"""
+import math
+
+import pytest
+import torch
+
+from mp_hsir_b200 import engine as E
+from mp_hsir_b200 import lib
+from mp_hsir_b200.lib import View
+from oracle import mp_hsir_oracle as O
+from tests.conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-5
+DEV = "cuda"
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return scale * torch.randn(*shape, generator=g)
+
+
+def dev(t):
+    return t.to(DEV).contiguous()
+
+
+def V(t):
+    return View.of(t)
+
+
+def out_mat(rows, cols):
+    return torch.full((rows, cols), float("nan"), device=DEV)
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM family
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("M,K,N", [(256, 64, 192), (4096, 128, 384), (300, 96, 288), (64, 256, 64), (1000, 176, 64)])
+def test_gemm_bias(M, K, N):
+    a, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5), rnd(N, seed=3)
+    y = out_mat(M, N)
+    lib.gemm(V(dev(a)), dev(E.pack_linear_t(w)), V(y), N, bias=dev(b))
+    assert rel_err(y.cpu(), a @ w.t() + b) < TOL
+
+
+@pytest.mark.parametrize("K", [64, 96, 256, 384])
+def test_gemm_layernorm_prologue(K):
+    M, N = 640, 3 * K
+    a, w, b = rnd(M, K, seed=4) * 3 + 1, rnd(N, K, seed=5, scale=K ** -0.5), rnd(N, seed=6)
+    g, be = 1 + 0.1 * rnd(K, seed=7), 0.1 * rnd(K, seed=8)
+    y = out_mat(M, N)
+    lib.gemm(V(dev(a)), dev(E.pack_linear_t(w)), V(y), N, ln=(dev(g), dev(be)), bias=dev(b))
+    assert rel_err(y.cpu(), O.layer_norm(a, g, be) @ w.t() + b) < TOL
+
+
+def test_gemm_residual_two_sources_and_row_scale():
+    M, K, N, hw = 512, 176, 128, 128
+    a, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5), rnd(N, seed=3)
+    r1, r2 = rnd(M, N, seed=4), rnd(M, N, seed=5)
+    s = torch.tensor([0.0, 1.25, 1.0, 1.1])
+    y = out_mat(M, N)
+    lib.gemm(V(dev(a)), dev(E.pack_linear_t(w)), V(y), N, bias=dev(b), epi=lib.EPI_RESIDUAL, res1=V(dev(r1)),
+             res2=V(dev(r2)), rows_per_batch=hw, row_scale=dev(s))
+    ref = r1 + s.repeat_interleave(hw)[:, None] * (a @ w.t() + b) + r2
+    assert rel_err(y.cpu(), ref) < TOL
+
+
+@pytest.mark.parametrize("C,hid", [(64, 170), (128, 340), (96, 255)])
+def test_gemm_glu_matches_gated_mlp(C, hid):
+    """LN + fc1 + value*gelu(gate) then fc2 + residual == x + GatedMlp(LN(x)) (net/MP_HSIR.py:76-82, :719)."""
+    M = 384
+    hp = E._ceil(hid, 16)
+    sd = {"fc1.weight": rnd(2 * hid, C, seed=1, scale=C ** -0.5), "fc1.bias": 0.1 * rnd(2 * hid, seed=2),
+          "fc2.weight": rnd(C, hid, seed=3, scale=hid ** -0.5), "fc2.bias": 0.1 * rnd(C, seed=4)}
+    g, be = 1 + 0.1 * rnd(C, seed=7), 0.1 * rnd(C, seed=8)
+    x = rnd(M, C, seed=9)
+    w1, b1 = E.pack_glu_fc1(sd["fc1.weight"], sd["fc1.bias"], hid, hp)
+    w2 = E.pack_linear_t(sd["fc2.weight"], k_pad=hp)
+    xd = dev(x)
+    h, y = out_mat(M, hp), out_mat(M, C)
+    lib.gemm(V(xd), dev(w1), V(h), 2 * hp, ln=(dev(g), dev(be)), bias=dev(b1), epi=lib.EPI_GLU)
+    lib.gemm(V(h), dev(w2), V(y), C, bias=dev(sd["fc2.bias"]), epi=lib.EPI_RESIDUAL, res1=V(xd))
+    ref = x + O.gated_mlp(O.layer_norm(x, g, be), sd, "")
+    assert torch.isfinite(h).all()
+    assert rel_err(y.cpu(), ref) < TOL
+
+
+def test_gemm_per_sample_weights_and_shared_operand():
+    B, hw, K, N = 3, 192, 64, 64   # hw not a multiple of the 128-row tile
+    a = rnd(hw, K, seed=1)          # shared by all samples (a_row_mod)
+    wb = rnd(B, K, N, seed=2, scale=K ** -0.5)  # per-sample "in x out"
+    r1 = rnd(B * hw, N, seed=3)
+    y = out_mat(B * hw, N)
+    lib.gemm(V(dev(a)), dev(wb), V(y), N, epi=lib.EPI_RESIDUAL, res1=V(dev(r1)), rows_per_batch=hw,
+             b_batch_stride=K * N, a_row_mod=hw, M=B * hw)
+    ref = r1 + torch.cat([a @ wb[b] for b in range(B)])
+    assert rel_err(y.cpu(), ref) < TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# dense 3x3 conv
+# ------------------------------------------------------------------------------------------------
+
+
+def tokens(x_nhwc):
+    B, H, W, C = x_nhwc.shape
+    return x_nhwc.reshape(B * H * W, C)
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 64), (32, 64), (96, 48)])
+def test_conv3x3_tokens(cin, cout):
+    B, H, W = 2, 16, 24
+    x, w = rnd(B, H, W, cin, seed=1), rnd(cout, cin, 3, 3, seed=2, scale=(9 * cin) ** -0.5)
+    y = out_mat(B * H * W, cout)
+    lib.conv3x3(V(dev(tokens(x))), dev(E.pack_conv3x3(w)), y.data_ptr(), cout, B, H, W, E._ceil(cin, 16), cout)
+    assert rel_err(y.cpu(), tokens(O.conv3x3(x, w))) < TOL
+
+
+def test_conv3x3_nchw_input_padding_and_residual_output():
+    """patch_embed on a 31-band cube and `output(x)+inp` (net/MP_HSIR.py:814, :841)."""
+    B, H, W, cin = 1, 32, 32, 31
+    img = rnd(B, cin, H, W, seed=1)
+    w = rnd(64, cin, 3, 3, seed=2, scale=(9 * cin) ** -0.5)
+    tok = out_mat(B * H * W, 32)
+    lib.nchw_to_tokens(dev(img), V(tok))
+    assert torch.equal(tok[:, :31].cpu(), tokens(img.permute(0, 2, 3, 1))) and (tok[:, 31] == 0).all()
+    y = out_mat(B * H * W, 64)
+    lib.conv3x3(V(tok), dev(E.pack_conv3x3(w, cin_pad=32)), y.data_ptr(), 64, B, H, W, 32, 64)
+    ref = O.conv3x3(img.permute(0, 2, 3, 1), w)
+    assert rel_err(y.cpu(), tokens(ref)) < TOL
+    w2 = rnd(cin, 64, 3, 3, seed=3, scale=(9 * 64) ** -0.5)
+    out = torch.full((B, cin, H, W), float("nan"), device=DEV)
+    lib.conv3x3(V(y), dev(E.pack_conv3x3(w2)), out.data_ptr(), 0, B, H, W, 64, cin, lib.CONV_NCHW_RES, R=dev(img))
+    ref2 = O.conv3x3(ref, w2).permute(0, 3, 1, 2) + img
+    assert rel_err(out.cpu(), ref2) < TOL
+
+
+def test_conv3x3_pixel_unshuffle_and_shuffle():
+    B, H, W, C = 2, 16, 16, 64
+    x = rnd(B, H, W, C, seed=1)
+    wd = rnd(C // 2, C, 3, 3, seed=2, scale=(9 * C) ** -0.5)
+    y = out_mat(B * H * W // 4, 2 * C)
+    lib.conv3x3(V(dev(tokens(x))), dev(E.pack_conv3x3(wd)), y.data_ptr(), 2 * C, B, H, W, C, C // 2, lib.CONV_UNSHUFFLE)
+    assert rel_err(y.cpu(), tokens(O.pixel_unshuffle2(O.conv3x3(x, wd)))) < TOL
+    wu = rnd(2 * C, C, 3, 3, seed=3, scale=(9 * C) ** -0.5)
+    cat = torch.zeros(B * H * W * 4, C, device=DEV)          # writes the left half of a concat buffer
+    lib.conv3x3(V(dev(tokens(x))), dev(E.pack_conv3x3(wu, shuffle=True)), cat.data_ptr(), C, B, H, W, C, 2 * C,
+                lib.CONV_SHUFFLE)
+    assert rel_err(cat[:, : C // 2].cpu(), tokens(O.pixel_shuffle2(O.conv3x3(x, wu)))) < TOL
+    assert (cat[:, C // 2:] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# window attention + local gate
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("C,heads", [(64, 2), (128, 2), (96, 2), (192, 2), (256, 8)])
+@pytest.mark.parametrize("shift", [0, 4])
+def test_window_attention_core(C, heads, shift):
+    B, H, W = 2, 16, 24
+    qkv = rnd(B, H, W, 3 * C, seed=1)
+    table = 0.5 * rnd(225, heads, seed=2)
+    # oracle: feed pre-computed qkv through identity weights
+    sd = {"qkv.weight": torch.eye(3 * C), "qkv.bias": torch.zeros(3 * C), "relative_position_bias_table": table}
+    xw = O.to_windows(qkv, shift)
+    mask = O.shift_mask(H, W) if shift else None
+    hd = C // heads
+    # window_attention_core applies the qkv Linear itself: emulate with q|k|v = x @ I
+    B_, N = xw.shape[:2]
+    q, k, v = xw.view(B_, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    attn = (q * hd ** -0.5) @ k.transpose(-2, -1) + O.relative_position_bias(table)[None]
+    if mask is not None:
+        nW = mask.shape[0]
+        attn = (attn.view(B_ // nW, nW, heads, N, N) + mask[None, :, None]).view(B_, heads, N, N)
+    core_w = (attn.softmax(-1) @ v).transpose(1, 2).reshape(B_, N, C)
+    ref = tokens(O.from_windows(core_w, shift, B, H, W))
+    out = out_mat(B * H * W, C)
+    wm = torch.full((B_, C), float("nan"), device=DEV)
+    lib.window_attn(V(dev(tokens(qkv))), dev(O.relative_position_bias(table)), V(out), wm, B, H, W, C, heads, shift)
+    assert rel_err(out.cpu(), ref) < TOL
+    assert rel_err(wm.cpu(), core_w.mean(dim=1)) < TOL
+    del sd
+
+
+@pytest.mark.parametrize("C,r", [(64, 8), (128, 16), (256, 8), (96, 12), (192, 24)])
+def test_local_gate(C, r):
+    B_ = 37
+    pfx = "l."
+    sd = {pfx + "linear_down.weight": rnd(r, C, seed=1, scale=C ** -0.5),
+          pfx + "linear_up.weight": rnd(C, r, seed=2, scale=r ** -0.5),
+          pfx + "linear_prompt.weight": rnd(128, C, seed=3, scale=C ** -0.5),
+          pfx + "prompt_param": torch.rand(1, 1, 128, r, generator=torch.Generator().manual_seed(4)),
+          pfx + "q.weight": rnd(r, r, seed=5, scale=r ** -0.5), pfx + "kv.weight": rnd(2 * r, r, seed=6, scale=r ** -0.5),
+          pfx + "proj.weight": rnd(r, r, seed=7, scale=r ** -0.5), pfx + "proj.bias": 0.1 * rnd(r, seed=8)}
+    pw, pb = rnd(C, C, seed=9, scale=C ** -0.5), 0.1 * rnd(C, seed=10)
+    core_mean = rnd(B_, C, seed=11)
+    ref = O.local_spectral_gate(core_mean @ pw.t() + pb, sd, pfx)
+    w = {"projT": pw.t(), "projb": pb, "promptT": sd[pfx + "linear_prompt.weight"].t(),
+         "downT": sd[pfx + "linear_down.weight"].t(), "param": sd[pfx + "prompt_param"].view(128, r),
+         "qT": sd[pfx + "q.weight"].t(), "kvT": sd[pfx + "kv.weight"].t(), "p2T": sd[pfx + "proj.weight"].t(),
+         "p2b": sd[pfx + "proj.bias"], "upT": sd[pfx + "linear_up.weight"].t()}
+    w = {k: dev(v) for k, v in w.items()}
+    gate = torch.full((B_, C), float("nan"), device=DEV)
+    lib.local_gate(dev(core_mean), w, gate, B_, C, r)
+    assert rel_err(gate.cpu(), ref) < TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# spectral attention pieces
+# ------------------------------------------------------------------------------------------------
+
+
+def test_dwconv_plain_and_gated():
+    B, H, W, C = 2, 16, 24, 96
+    x, w = rnd(B, H, W, C, seed=1), rnd(C, 1, 3, 3, seed=2, scale=1 / 3)
+    y = out_mat(B * H * W, C)
+    lib.dwconv3x3(V(dev(tokens(x))), dev(E.pack_dw(w)), V(y), B, H, W, C)
+    assert rel_err(y.cpu(), tokens(O.dwconv3x3(x, w))) < TOL
+    # GDFN: project_in -> dw -> gelu(x1)*x2 -> project_out (+residual), hidden 170 padded to 176
+    D, hid, hp = 64, 170, 176
+    sd = {"project_in.weight": rnd(2 * hid, D, 1, 1, seed=3, scale=D ** -0.5),
+          "dwconv.weight": rnd(2 * hid, 1, 3, 3, seed=4, scale=1 / 3),
+          "project_out.weight": rnd(D, hid, 1, 1, seed=5, scale=hid ** -0.5)}
+    xin = rnd(B, H, W, D, seed=6)
+    pin, w9, pout = E.pack_gdfn(sd["project_in.weight"], sd["dwconv.weight"], sd["project_out.weight"], hid, hp)
+    N = B * H * W
+    xd = dev(tokens(xin))
+    hin, hg, yo = out_mat(N, 2 * hp), out_mat(N, hp), out_mat(N, D)
+    lib.gemm(V(xd), dev(pin), V(hin), 2 * hp)
+    lib.dwconv3x3(V(hin), dev(w9), V(hg), B, H, W, 2 * hp, gate_half=hp)
+    lib.gemm(V(hg), dev(pout), V(yo), D, epi=lib.EPI_RESIDUAL, res1=V(xd))
+    assert rel_err(yo.cpu(), tokens(xin + O.gdfn(xin, sd, ""))) < TOL
+
+
+@pytest.mark.parametrize("C,heads,HW", [(64, 2, 1024), (128, 2, 4096), (256, 8, 256), (96, 2, 640), (192, 2, 320)])
+def test_spectral_attention_gram_softmax_fold_apply(C, heads, HW):
+    """out = project_out(softmax(norm(q) norm(k)^T * T) v) via Gram partials + folded weights."""
+    B = 2
+    c = C // heads
+    qkv = rnd(B, HW, 3 * C, seed=1)
+    temp = 0.5 + torch.rand(heads, 1, 1, generator=torch.Generator().manual_seed(2))
+    wout = rnd(C, C, 1, 1, seed=3, scale=C ** -0.5)
+    q, k, v = qkv.split(C, dim=-1)
+    ref = O.conv1x1(O.transposed_attention(q, k, v, temp, heads), wout).reshape(B * HW, C)
+    buf = dev(qkv.reshape(B * HW, 3 * C))
+    vw = V(buf)
+    nfl, nch = lib.gram_partial_floats(B, heads, c, HW)
+    partial = torch.full((nfl,), float("nan"), device=DEV)
+    attn = torch.full((B * heads * c * c,), float("nan"), device=DEV)
+    Mt = torch.zeros(B, E._ceil(C, 16), E._ldb(C), device=DEV)
+    lib.gram_partial(vw.cols_slice(0, C), False, vw.cols_slice(C, 2 * C), False, partial, B, HW, heads, c)
+    lib.gram_softmax(partial, nch, dev(temp.reshape(-1)), attn, B, heads, c)
+    lib.spectral_fold(attn, dev(wout.reshape(C, C).t()), Mt, B, heads, c)
+    y = out_mat(B * HW, C)
+    lib.gemm(vw.cols_slice(2 * C, 3 * C), Mt, V(y), C, rows_per_batch=HW, b_batch_stride=Mt.shape[1] * Mt.shape[2])
+    assert rel_err(y.cpu(), ref) < TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# prompt helpers
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("B,ps,D", [(1, 64, 64), (4, 32, 128), (3, 64, 96)])
+def test_text_prompt_and_tvsp_query(B, ps, D):
+    T = 6
+    clip = rnd(T, 512, seed=1)
+    tid = torch.arange(B) % T
+    clip_ref, w = O.text_prompt(tid, clip, T)
+    learn = rnd(T, D, seed=2)
+    clip_b = torch.full((B, 512), float("nan"), device=DEV)
+    wd = dev(w.float())
+    lib.text_prompt(wd, dev(clip), clip_b, B, T)
+    assert rel_err(clip_b.cpu(), clip_ref) < 1e-6
+    Q = out_mat(B * ps * ps, D)
+    lib.tvsp_query(clip_b, wd, dev(learn), V(Q), B, T, D, ps)
+    assert rel_err(Q.cpu(), O.tvsp_query(clip_ref, w, learn, ps).reshape(B * ps * ps, D)) < 1e-6
+
+
+@pytest.mark.parametrize("h,w,H,W", [(64, 64, 128, 96), (32, 32, 48, 64), (32, 32, 16, 16), (64, 64, 512, 512)])
+def test_bilinear_matches_torch_interpolate(h, w, H, W):
+    B, C = 2, 16
+    x = rnd(B, h, w, C, seed=1)
+    y = out_mat(B * H * W, C)
+    lib.bilinear(V(dev(tokens(x))), V(y), B, h, w, H, W, C)
+    ref = torch.nn.functional.interpolate(x.permute(0, 3, 1, 2), (H, W), mode="bilinear").permute(0, 2, 3, 1)
+    assert rel_err(y.cpu(), tokens(ref)) < 1e-5
+    assert rel_err(tokens(O.bilinear_resize(x, H, W)), tokens(ref)) < 1e-5
+
+
+def test_errors_are_reported_not_swallowed():
+    a = torch.zeros(8, 6, device=DEV)
+    with pytest.raises(RuntimeError, match="gemm"):
+        lib.gemm(V(a), torch.zeros(16, 64, device=DEV), V(torch.zeros(8, 64, device=DEV)), 64)  # K=6 not %4
+    with pytest.raises(RuntimeError, match="head_dim"):
+        lib.window_attn(V(torch.zeros(64, 120, device=DEV)), torch.zeros(1, 64, 64, device=DEV),
+                        V(torch.zeros(64, 40, device=DEV)), torch.zeros(40, device=DEV), 1, 8, 8, 40, 1, 0)
+    assert math.isfinite(float(a.sum()))
