@@ -110,6 +110,42 @@ def _check(rc: int, what: str) -> None:
     LAUNCHES += 1
 
 
+class Profiler:
+    """Per-launch CUDA-event timing on the launching stream + algorithmic flops/bytes per kernel
+    family (bench.py's roofline leg).  Off the timed path: enable only for an instrumented pass."""
+
+    def __init__(self):
+        self.records = []  # (tag, flops, bytes, start_event, end_event)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for tag, fl, by, e0, e1 in self.records:
+            a = agg.setdefault(tag, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            a["launches"] += 1
+            a["ms"] += e0.elapsed_time(e1)
+            a["flops"] += fl
+            a["bytes"] += by
+        return agg
+
+
+PROFILER: Optional[Profiler] = None
+
+
+def _launch(what: str, call, cost=None) -> None:
+    """Run one ABI call; when PROFILER is set, bracket it with events and record its cost."""
+    if PROFILER is None:
+        _check(call(), what)
+        return
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _check(call(), what)
+    e1.record()
+    fl, by, tag = cost() if cost is not None else (0.0, 0.0, what)
+    PROFILER.records.append((tag, fl, by, e0, e1))
+
+
 def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -160,7 +196,8 @@ def device_check(device: int) -> int:
 
 def nchw_to_tokens(inp: torch.Tensor, out: View) -> None:
     B, Cc, H, W = inp.shape
-    _check(load().mphsir_nchw_to_tokens(inp.data_ptr(), out.ptr, B, Cc, H * W, out.ld, stream_ptr()), "nchw_to_tokens")
+    _launch("nchw_to_tokens", lambda: load().mphsir_nchw_to_tokens(inp.data_ptr(), out.ptr, B, Cc, H * W, out.ld, stream_ptr()),
+            lambda: (0.0, 4.0 * B * H * W * (Cc + out.ld), "nchw_to_tokens"))
 
 
 def gemm(A: View, Bt: torch.Tensor, Y: View, N: int, *, K: Optional[int] = None, ln=None, bias=None,
@@ -187,7 +224,14 @@ def gemm(A: View, Bt: torch.Tensor, Y: View, N: int, *, K: Optional[int] = None,
     p.gate = ptr(gate)
     p.H, p.W, p.shift = H, W, shift
     p.row_scale = ptr(row_scale)
-    _check(load().mphsir_gemm_fwd(C.byref(p), stream_ptr()), "gemm_fwd")
+    def cost():
+        m, n, k = p.M, p.N, p.K
+        n_out = n // 2 if epi == EPI_GLU else n
+        reads = m * k + k * n + sum(m * n for t in (res1, res2, gsrc) if t is not None)
+        tag = "gemm" + ("+ln" if ln is not None else "") + ("", "+res", "+glu", "+spectral")[epi]
+        return 2.0 * m * n * k, 4.0 * (reads + m * n_out), tag
+
+    _launch("gemm_fwd", lambda: load().mphsir_gemm_fwd(C.byref(p), stream_ptr()), cost)
 
 
 def conv3x3(X: View, Wt: torch.Tensor, Y_ptr: int, ldy: int, B: int, H: int, W: int, Cin: int, N: int,
@@ -199,13 +243,18 @@ def conv3x3(X: View, Wt: torch.Tensor, Y_ptr: int, ldy: int, B: int, H: int, W: 
     p.B, p.H, p.W, p.Cin, p.N = B, H, W, Cin, N
     p.out_mode = out_mode
     p.R = ptr(R)
-    _check(load().mphsir_conv3x3_fwd(C.byref(p), stream_ptr()), "conv3x3_fwd")
+    m = B * H * W
+    _launch("conv3x3_fwd", lambda: load().mphsir_conv3x3_fwd(C.byref(p), stream_ptr()),
+            lambda: (2.0 * m * N * 9 * Cin, 4.0 * (m * Cin + m * N * (2 if R is not None else 1) + 9 * Cin * N), "conv3x3"))
 
 
 def window_attn(qkv: View, bias: torch.Tensor, out: View, win_mean: torch.Tensor, B: int, H: int, W: int,
                 Cc: int, heads: int, shift: int) -> None:
-    _check(load().mphsir_window_attn_fwd(qkv.ptr, qkv.ld, bias.data_ptr(), out.ptr, out.ld, win_mean.data_ptr(),
-                                         B, H, W, Cc, heads, shift, stream_ptr()), "window_attn_fwd")
+    n = B * H * W
+    _launch("window_attn_fwd",
+            lambda: load().mphsir_window_attn_fwd(qkv.ptr, qkv.ld, bias.data_ptr(), out.ptr, out.ld,
+                                                  win_mean.data_ptr(), B, H, W, Cc, heads, shift, stream_ptr()),
+            lambda: (4.0 * n * 64 * Cc, 4.0 * (4 * n * Cc + n // 64 * Cc), "window_attn"))
 
 
 def local_gate(core_mean: torch.Tensor, w: dict, gate: torch.Tensor, B_: int, Cc: int, r: int) -> None:
@@ -214,12 +263,17 @@ def local_gate(core_mean: torch.Tensor, w: dict, gate: torch.Tensor, B_: int, Cc
     for n in ("projT", "projb", "promptT", "downT", "param", "qT", "kvT", "p2T", "p2b", "upT"):
         setattr(p, n, w[n].data_ptr())
     p.gate, p.B_, p.C, p.r = gate.data_ptr(), B_, Cc, r
-    _check(load().mphsir_local_gate_fwd(C.byref(p), stream_ptr()), "local_gate_fwd")
+    _launch("local_gate_fwd", lambda: load().mphsir_local_gate_fwd(C.byref(p), stream_ptr()),
+            lambda: (2.0 * B_ * (Cc * Cc + Cc * 128 + 2 * Cc * r + 128 * r), 8.0 * B_ * Cc, "local_gate"))
 
 
 def dwconv3x3(X: View, w9: torch.Tensor, Y: View, B: int, H: int, W: int, Cc: int, gate_half: int = 0) -> None:
-    _check(load().mphsir_dwconv3x3_fwd(X.ptr, X.ld, w9.data_ptr(), Y.ptr, Y.ld, B, H, W, Cc, gate_half,
-                                       stream_ptr()), "dwconv3x3_fwd")
+    n = B * H * W
+    _launch("dwconv3x3_fwd",
+            lambda: load().mphsir_dwconv3x3_fwd(X.ptr, X.ld, w9.data_ptr(), Y.ptr, Y.ld, B, H, W, Cc, gate_half,
+                                                stream_ptr()),
+            lambda: (18.0 * n * Cc, 4.0 * n * (Cc + (gate_half if gate_half else Cc)),
+                     "dwconv3x3+gate" if gate_half else "dwconv3x3"))
 
 
 def gram_partial_floats(B: int, heads: int, c: int, HW: int):
@@ -230,32 +284,44 @@ def gram_partial_floats(B: int, heads: int, c: int, HW: int):
 
 def gram_partial(q: View, q_shared: bool, k: View, k_shared: bool, partial: torch.Tensor, B: int, HW: int,
                  heads: int, c: int) -> None:
-    _check(load().mphsir_gram_partial_fwd(q.ptr, q.ld, int(q_shared), k.ptr, k.ld, int(k_shared),
-                                          partial.data_ptr(), B, HW, heads, c, stream_ptr()), "gram_partial_fwd")
+    _launch("gram_partial_fwd",
+            lambda: load().mphsir_gram_partial_fwd(q.ptr, q.ld, int(q_shared), k.ptr, k.ld, int(k_shared),
+                                                   partial.data_ptr(), B, HW, heads, c, stream_ptr()),
+            lambda: (2.0 * B * HW * heads * c * (c + 2), 8.0 * B * HW * heads * c, "gram_partial"))
 
 
 def gram_softmax(partial: torch.Tensor, n_chunks: int, temperature: torch.Tensor, attn: torch.Tensor, B: int,
                  heads: int, c: int) -> None:
-    _check(load().mphsir_gram_softmax_fwd(partial.data_ptr(), n_chunks, temperature.data_ptr(), attn.data_ptr(),
-                                          B, heads, c, stream_ptr()), "gram_softmax_fwd")
+    _launch("gram_softmax_fwd",
+            lambda: load().mphsir_gram_softmax_fwd(partial.data_ptr(), n_chunks, temperature.data_ptr(),
+                                                   attn.data_ptr(), B, heads, c, stream_ptr()),
+            lambda: (0.0, 4.0 * B * heads * (n_chunks + 1) * c * c, "gram_softmax"))
 
 
 def spectral_fold(attn: torch.Tensor, WoutT: torch.Tensor, Mt: torch.Tensor, B: int, heads: int, c: int) -> None:
     # Mt: [B, Cp, ldm]
-    _check(load().mphsir_spectral_fold_fwd(attn.data_ptr(), WoutT.data_ptr(), Mt.data_ptr(), Mt.shape[2],
-                                           Mt.shape[1] * Mt.shape[2], B, heads, c, stream_ptr()), "spectral_fold_fwd")
+    _launch("spectral_fold_fwd",
+            lambda: load().mphsir_spectral_fold_fwd(attn.data_ptr(), WoutT.data_ptr(), Mt.data_ptr(), Mt.shape[2],
+                                                    Mt.shape[1] * Mt.shape[2], B, heads, c, stream_ptr()),
+            lambda: (2.0 * B * heads * c * c * heads * c, 4.0 * B * (heads * c) ** 2, "spectral_fold"))
 
 
 def tvsp_query(clip_b: torch.Tensor, weights: torch.Tensor, learnable: torch.Tensor, Q: View, B: int, T: int,
                D: int, ps: int) -> None:
-    _check(load().mphsir_tvsp_query_fwd(clip_b.data_ptr(), weights.data_ptr(), learnable.data_ptr(), Q.ptr, B, T, D,
-                                        ps, stream_ptr()), "tvsp_query_fwd")
+    _launch("tvsp_query_fwd",
+            lambda: load().mphsir_tvsp_query_fwd(clip_b.data_ptr(), weights.data_ptr(), learnable.data_ptr(), Q.ptr,
+                                                 B, T, D, ps, stream_ptr()),
+            lambda: (0.0, 4.0 * B * ps * ps * D, "tvsp_query"))
 
 
 def bilinear(X: View, Y: View, B: int, h: int, w: int, H: int, W: int, Cc: int) -> None:
-    _check(load().mphsir_bilinear_fwd(X.ptr, X.ld, Y.ptr, Y.ld, B, h, w, H, W, Cc, stream_ptr()), "bilinear_fwd")
+    _launch("bilinear_fwd",
+            lambda: load().mphsir_bilinear_fwd(X.ptr, X.ld, Y.ptr, Y.ld, B, h, w, H, W, Cc, stream_ptr()),
+            lambda: (0.0, 4.0 * B * Cc * (h * w + H * W), "bilinear"))
 
 
 def text_prompt(weights: torch.Tensor, clip: torch.Tensor, clip_b: torch.Tensor, B: int, T: int) -> None:
-    _check(load().mphsir_text_prompt_fwd(weights.data_ptr(), clip.data_ptr(), clip_b.data_ptr(), B, T, stream_ptr()),
-           "text_prompt_fwd")
+    _launch("text_prompt_fwd",
+            lambda: load().mphsir_text_prompt_fwd(weights.data_ptr(), clip.data_ptr(), clip_b.data_ptr(), B, T,
+                                                  stream_ptr()),
+            lambda: (0.0, 4.0 * B * 512, "text_prompt"))
