@@ -61,6 +61,13 @@ MPHSIR_API int mphsir_nchw_to_tokens(const float* in, float* out, int B, int C, 
  *            reduce_chan_level2 (:828), and the residual adds of PGSSTB.forward (:715-719),
  *            TransformerBlock.forward (:476-477), BaseBlock.forward (:760).
  * ------------------------------------------------------------------------------------- */
+/* arithmetic of the contraction (accumulation is always fp32) */
+enum {
+  MPHSIR_PREC_FP32_SIMT = 0, /* FFMA, bit-for-bit fp32 products (gemm_simt.cu)                            */
+  MPHSIR_PREC_BF16X3 = 1,    /* tcgen05, operands split hi+lo bf16: hi*hi + hi*lo + lo*hi (fp32-grade)    */
+  MPHSIR_PREC_BF16 = 2       /* tcgen05, operands rounded to bf16                                          */
+};
+
 enum {
   MPHSIR_EPI_BIAS = 0,     /* Y = acc + bias                                                     */
   MPHSIR_EPI_RESIDUAL = 1, /* Y = res1 + scale_b*(acc + bias) [+ res2]                           */
@@ -92,7 +99,18 @@ typedef struct {
   const float* gate;   /* SPECTRAL: per-window channel gate [B*nW, N]    */
   int H, W, shift;     /* SPECTRAL: image size at this level and cyclic shift (0 or 4)            */
   const float* row_scale; /* [B] DropPath keep/keep_prob per sample, NULL = 1 (eval)              */
+  int precision;       /* MPHSIR_PREC_*: FP32_SIMT uses Bt; the tensor-core modes use Bimg             */
+  const void* Bimg;    /* packed bf16 hi/lo weight image (mphsir_pack_bimg) of the logical [N,K] matrix */
+  long long bimg_batch_bytes; /* bytes between per-sample images; 0 = shared                          */
 } mphsir_gemm_params;
+
+/* Tensor-core weight image: logical W[N,K] fp32 (row n at W + n*ld, or W + k*ld + n when
+ * `transposed`) -> bf16 hi/lo parts in the 128-byte-swizzled K-major layout the MMA reads
+ * (mp_hsir_b200/csrc/gemm_tc.cuh: bimg_offset).  `batch` independent matrices, w_batch_stride floats
+ * apart, produce images mphsir_bimg_bytes(N,K) bytes apart.  img must be 128-byte aligned. */
+MPHSIR_API size_t mphsir_bimg_bytes(int N, int K);
+MPHSIR_API int mphsir_pack_bimg(const float* W, int ld, int transposed, long long w_batch_stride, void* img,
+                                int batch, int N, int K, void* stream);
 
 MPHSIR_API int mphsir_gemm_fwd(const mphsir_gemm_params* p, void* stream);
 
@@ -119,6 +137,8 @@ typedef struct {
   int B, H, W, Cin, N; /* N = number of output channels */
   int out_mode;
   const float* R;  /* NCHW residual for MPHSIR_CONV_NCHW_RES */
+  int precision;   /* MPHSIR_PREC_* */
+  const void* Bimg; /* packed image of the logical [N, 9*Cin] matrix for the tensor-core modes */
 } mphsir_conv3x3_params;
 
 MPHSIR_API int mphsir_conv3x3_fwd(const mphsir_conv3x3_params* p, void* stream);

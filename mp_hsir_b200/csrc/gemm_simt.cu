@@ -10,6 +10,7 @@
 // 2-3 LDS.128 per 32-64 FFMA; Bt is pre-packed "in x out" so its tile loads are already in
 // inner-loop order.
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace mphsir {
 
@@ -352,8 +353,12 @@ using namespace mphsir;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+static int gemm_tc_dispatch(const mphsir_gemm_params* p, cudaStream_t st);
+
 extern "C" int mphsir_gemm_fwd(const mphsir_gemm_params* p, void* stream) {
   MPHSIR_REQUIRE(p != nullptr, "gemm: null params");
+  MPHSIR_REQUIRE(p->precision >= MPHSIR_PREC_FP32_SIMT && p->precision <= MPHSIR_PREC_BF16, "gemm: unknown precision %d", p->precision);
+  if (p->precision != MPHSIR_PREC_FP32_SIMT) return gemm_tc_dispatch(p, reinterpret_cast<cudaStream_t>(stream));
   MPHSIR_REQUIRE(p->A && p->Bt && p->Y, "gemm: null operand");
   MPHSIR_REQUIRE(p->M > 0 && p->N > 0 && p->K > 0, "gemm: bad shape M=%d N=%d K=%d", p->M, p->N, p->K);
   MPHSIR_REQUIRE(p->K % 4 == 0 && p->lda % 4 == 0 && p->lda >= p->K, "gemm: K=%d lda=%d must be multiples of 4, lda>=K", p->K, p->lda);
@@ -388,8 +393,80 @@ extern "C" int mphsir_gemm_fwd(const mphsir_gemm_params* p, void* stream) {
   return p->ln_gamma ? launch<MODE_LN>(a, st, "gemm(ln)") : launch<MODE_PLAIN>(a, st, "gemm");
 }
 
+static int gemm_tc_dispatch(const mphsir_gemm_params* p, cudaStream_t st) {
+  MPHSIR_REQUIRE(p->A && p->Bimg && p->Y, "gemm(tc): null operand (Bimg is required for tensor-core precisions)");
+  MPHSIR_REQUIRE(p->M > 0 && p->N > 0 && p->K > 0, "gemm(tc): bad shape M=%d N=%d K=%d", p->M, p->N, p->K);
+  MPHSIR_REQUIRE(p->K % 8 == 0 && p->lda % 4 == 0 && p->lda >= p->K, "gemm(tc): K=%d must be a multiple of 8, lda=%d a multiple of 4", p->K, p->lda);
+  MPHSIR_REQUIRE(p->N % 4 == 0 && p->ldy % 4 == 0, "gemm(tc): N=%d ldy=%d must be multiples of 4", p->N, p->ldy);
+  MPHSIR_REQUIRE(aligned16(p->A) && aligned16(p->Y) && (reinterpret_cast<uintptr_t>(p->Bimg) & 127) == 0, "gemm(tc): operands misaligned");
+  MPHSIR_REQUIRE((p->ln_gamma == nullptr) == (p->ln_beta == nullptr), "gemm(tc): ln_gamma/ln_beta must both be set");
+  MPHSIR_REQUIRE(p->epi >= MPHSIR_EPI_BIAS && p->epi <= MPHSIR_EPI_SPECTRAL, "gemm(tc): unknown epilogue %d", p->epi);
+  const bool per_sample = p->bimg_batch_bytes != 0 || p->row_scale != nullptr || p->epi == MPHSIR_EPI_SPECTRAL;
+  if (per_sample)
+    MPHSIR_REQUIRE(p->rows_per_batch > 0 && p->M % p->rows_per_batch == 0, "gemm(tc): rows_per_batch=%d must divide M=%d", p->rows_per_batch, p->M);
+  if (p->epi == MPHSIR_EPI_RESIDUAL || p->epi == MPHSIR_EPI_SPECTRAL)
+    MPHSIR_REQUIRE(p->res1 != nullptr && p->ldr1 % 4 == 0 && aligned16(p->res1), "gemm(tc): residual epilogue needs aligned res1");
+  if (p->res2) MPHSIR_REQUIRE(p->ldr2 % 4 == 0 && aligned16(p->res2), "gemm(tc): res2 misaligned");
+  if (p->epi == MPHSIR_EPI_SPECTRAL) {
+    MPHSIR_REQUIRE(p->gsrc && p->gate && p->ldg % 4 == 0, "gemm(tc): spectral epilogue needs gsrc/gate");
+    MPHSIR_REQUIRE(p->H > 0 && p->W > 0 && p->H % 8 == 0 && p->W % 8 == 0 && p->H * p->W == p->rows_per_batch, "gemm(tc): spectral epilogue needs H,W multiples of 8 with H*W == rows_per_batch");
+    MPHSIR_REQUIRE(p->shift == 0 || p->shift == 4, "gemm(tc): shift must be 0 or 4");
+  }
+  tc::TcArgs a{};
+  a.A = p->A; a.lda = p->lda; a.a_row_mod = p->a_row_mod; a.Ka = p->K;
+  a.Bimg = p->Bimg; a.b_batch_bytes = p->bimg_batch_bytes; a.rows_per_batch = p->rows_per_batch;
+  a.tiles_per_batch = p->bimg_batch_bytes != 0 ? (p->rows_per_batch + 127) / 128 : 0;
+  a.num_tiles = a.tiles_per_batch > 0 ? (p->M / p->rows_per_batch) * a.tiles_per_batch : (p->M + 127) / 128;
+  a.Y = p->Y; a.ldy = p->ldy; a.M = p->M; a.N = p->N; a.Np = (p->N + 15) / 16 * 16; a.ks = (p->K + 63) / 64;
+  a.parts = p->precision == MPHSIR_PREC_BF16X3 ? 2 : 1;
+  a.ln_g = p->ln_gamma; a.ln_b = p->ln_beta; a.bias = p->bias; a.epi = p->epi;
+  a.res1 = p->res1; a.ldr1 = p->ldr1; a.res2 = p->res2; a.ldr2 = p->ldr2;
+  a.gsrc = p->gsrc; a.ldg = p->ldg; a.gate = p->gate; a.H = p->H; a.W = p->W; a.shift = p->shift;
+  a.row_scale = p->row_scale;
+  return tc::launch_gemm_tc(a, false, st);
+}
+
+static int conv_tc_dispatch(const mphsir_conv3x3_params* p, cudaStream_t st) {
+  MPHSIR_REQUIRE(p->X && p->Bimg && p->Y, "conv3x3(tc): null operand (Bimg is required for tensor-core precisions)");
+  MPHSIR_REQUIRE(p->B > 0 && p->H > 0 && p->W > 0, "conv3x3(tc): bad image");
+  MPHSIR_REQUIRE(p->Cin % 8 == 0 && p->ldx >= p->Cin && p->ldx % 4 == 0, "conv3x3(tc): Cin=%d must be a multiple of 8, ldx=%d", p->Cin, p->ldx);
+  MPHSIR_REQUIRE(aligned16(p->X) && (reinterpret_cast<uintptr_t>(p->Bimg) & 127) == 0, "conv3x3(tc): operands misaligned");
+  tc::TcArgs a{};
+  a.A = p->X; a.lda = p->ldx; a.Ka = 9 * p->Cin; a.Cin = p->Cin;
+  a.Bimg = p->Bimg;
+  a.M = p->B * p->H * p->W; a.num_tiles = (a.M + 127) / 128;
+  a.Y = p->Y; a.ldy = p->ldy; a.N = p->N; a.Np = (p->N + 15) / 16 * 16; a.ks = (9 * p->Cin + 63) / 64;
+  a.parts = p->precision == MPHSIR_PREC_BF16X3 ? 2 : 1;
+  a.H = p->H; a.W = p->W; a.rows_per_batch = p->H * p->W;
+  switch (p->out_mode) {
+    case MPHSIR_CONV_TOKENS:
+      MPHSIR_REQUIRE(p->N % 4 == 0 && p->ldy % 4 == 0 && aligned16(p->Y), "conv3x3(tc): token output needs N,ldy multiples of 4");
+      a.epi = MPHSIR_EPI_BIAS;
+      break;
+    case MPHSIR_CONV_UNSHUFFLE:
+      MPHSIR_REQUIRE(p->N % 4 == 0 && p->H % 2 == 0 && p->W % 2 == 0, "conv3x3(tc): unshuffle needs even H,W");
+      a.epi = tc::TC_OUT_UNSHUFFLE;
+      break;
+    case MPHSIR_CONV_SHUFFLE:
+      MPHSIR_REQUIRE(p->N % 16 == 0 && p->ldy % 4 == 0 && aligned16(p->Y), "conv3x3(tc): shuffle needs N multiple of 16");
+      a.epi = tc::TC_OUT_SHUFFLE;
+      break;
+    case MPHSIR_CONV_NCHW_RES:
+      MPHSIR_REQUIRE(p->R != nullptr, "conv3x3(tc): NCHW residual output needs R");
+      a.epi = tc::TC_OUT_NCHW_RES;
+      a.R = p->R;
+      break;
+    default:
+      MPHSIR_REQUIRE(false, "conv3x3(tc): unknown out_mode %d", p->out_mode);
+  }
+  return tc::launch_gemm_tc(a, true, st);
+}
+
 extern "C" int mphsir_conv3x3_fwd(const mphsir_conv3x3_params* p, void* stream) {
-  MPHSIR_REQUIRE(p != nullptr && p->X && p->Wt && p->Y, "conv3x3: null operand");
+  MPHSIR_REQUIRE(p != nullptr, "conv3x3: null params");
+  MPHSIR_REQUIRE(p->precision >= MPHSIR_PREC_FP32_SIMT && p->precision <= MPHSIR_PREC_BF16, "conv3x3: unknown precision %d", p->precision);
+  if (p->precision != MPHSIR_PREC_FP32_SIMT) return conv_tc_dispatch(p, reinterpret_cast<cudaStream_t>(stream));
+  MPHSIR_REQUIRE(p->X && p->Wt && p->Y, "conv3x3: null operand");
   MPHSIR_REQUIRE(p->B > 0 && p->H > 0 && p->W > 0 && p->W % 8 == 0, "conv3x3: bad image %dx%dx%d (W must be a multiple of 8)", p->B, p->H, p->W);
   MPHSIR_REQUIRE(p->Cin % 16 == 0 && p->ldx >= p->Cin && p->ldx % 4 == 0, "conv3x3: Cin=%d must be a multiple of 16 (zero-pad the input), ldx=%d", p->Cin, p->ldx);
   MPHSIR_REQUIRE(p->ldb % 64 == 0 && p->ldb >= ((p->N + 63) / 64) * 64, "conv3x3: ldb=%d must be a multiple of 64 covering N=%d", p->ldb, p->N);

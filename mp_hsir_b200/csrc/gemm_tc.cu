@@ -1,0 +1,603 @@
+// tcgen05 GEMM engine (sm_100a): Y = epilogue( prologue(A) @ W^T ) with fp32 activations in HBM.
+//
+//   * A (fp32, token-major) is read by 8 "converter" warps, LayerNorm-ed if requested, split into bf16
+//     hi (+ lo) parts and written into 128-byte-swizzled K-major shared-memory slabs (128 rows x 64 k).
+//   * W lives in HBM as a pre-swizzled bf16 hi/lo image ("Bimg", see bimg_offset) so that one
+//     cp.async.bulk (TMA bulk copy, mbarrier complete_tx) moves a 128-row x 64-k block straight into
+//     its shared-memory slot.
+//   * one thread issues tcgen05.mma (kind::f16, M=128, N<=128 per instruction, fp32 accumulators in
+//     TMEM).  precision 1 ("bf16x3"): hi*hi + hi*lo + lo*hi -> ~2^-16 relative product error, which keeps the
+//     whole network inside the fp32 parity contract (1e-4); precision 2 ("bf16x1"): hi*hi only.
+//   * 4 epilogue warps drain TMEM with tcgen05.ld and apply bias / residual / GLU / spectral-gate
+//     epilogues, writing fp32 rows.
+//
+// Persistent CTAs (one per SM), warp-specialised, three mbarrier pipelines:
+//   A slabs (converters -> MMA), B blocks (bulk copy -> MMA), accumulators (MMA -> epilogue), so the
+//   conversion of tile i+1, the MMAs of tile i and the epilogue of tile i-1 overlap.
+// Loop nest per 128-row tile:  pass (<=256 output columns, double-buffered in TMEM)
+//                                -> k-slab (64) -> n-tile (128 columns) -> 4 x {1|3} MMAs (K=16 each)
+// If all k-slabs of a tile fit the A ring (K <= 256) the tile is converted once and reused by every pass.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+namespace mphsir {
+namespace tc {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 version 1):
+// rows are 128 B (64 bf16), 8-row groups are 1024 B apart (SBO); LBO is unused for swizzled K-major.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n.
+__device__ __forceinline__ uint32_t make_idesc(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int kThreads = 448;  // warp 0: B loader, warp 1: MMA + TMEM owner, warps 2-5: epilogue, warps 6-13: converters
+constexpr int kConvThreads = 256;
+constexpr int kEpiThreads = 128;
+constexpr int SLAB_BYTES = 128 * 128;  // one part (hi or lo) of a 128-row x 64-k slab
+constexpr int MAX_RING = 8;
+
+struct Smem {
+  // barriers first (8-byte aligned), rings after (1024-byte aligned, carved dynamically)
+  uint64_t a_full[MAX_RING], a_empty[MAX_RING], b_full[MAX_RING], b_empty[MAX_RING];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+template <bool CONV>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Smem* sm = reinterpret_cast<Smem*>(smem_raw);
+  const int parts = p.parts;                       // 1 (bf16x1) or 2 (bf16x3)
+  const int a_slot_bytes = SLAB_BYTES * parts;
+  const int b_slot_bytes = SLAB_BYTES * parts;
+  uint8_t* a_ring = smem_raw + 1024;
+  uint8_t* b_ring = a_ring + (size_t)p.na * a_slot_bytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Ks = p.ks;
+  const int NT = (p.Np + 127) >> 7;                // 128-column n-tiles
+  const int npass = (NT + 1) >> 1;
+  const bool stationary = Ks <= p.na;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MAX_RING; ++i) {
+      mbar_init(smem_u32(&sm->a_full[i]), kConvThreads / 32);
+      mbar_init(smem_u32(&sm->a_empty[i]), 1);
+      mbar_init(smem_u32(&sm->b_full[i]), 1);
+      mbar_init(smem_u32(&sm->b_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&sm->acc_full[i]), 1);
+      mbar_init(smem_u32(&sm->acc_empty[i]), kEpiThreads / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&sm->tmem_base), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm->tmem_base;
+
+  const int num_tiles = p.num_tiles;
+
+  if (warp == 0) {
+    // =============================== B loader ===============================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const uint8_t* bimg = reinterpret_cast<const uint8_t*>(p.Bimg);
+        if (p.tiles_per_batch > 0) bimg += (size_t)(tile / p.tiles_per_batch) * p.b_batch_bytes;
+        for (int pass = 0; pass < npass; ++pass) {
+          for (int s = 0; s < Ks; ++s) {
+            for (int j = 2 * pass; j < min(NT, 2 * pass + 2); ++j, ++it) {
+              const int slot = it % p.nb;
+              const uint32_t par = (it / p.nb) & 1;
+              mbar_wait(smem_u32(&sm->b_empty[slot]), par ^ 1);
+              const int rows = min(128, p.Np - j * 128);
+              const uint32_t bytes = rows * 128;
+              const uint32_t full = smem_u32(&sm->b_full[slot]);
+              mbar_expect_tx(full, bytes * parts);
+              for (int part = 0; part < parts; ++part) {
+                const uint8_t* src = bimg + ((size_t)(part * Ks + s) * p.Np + j * 128) * 128;
+                bulk_g2s(smem_u32(b_ring + (size_t)slot * b_slot_bytes + part * SLAB_BYTES), src, bytes, full);
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =============================================
+    if (lane == 0) {
+      uint32_t a_it = 0, b_it = 0, acc_it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const uint32_t a_base = a_it;
+        for (int pass = 0; pass < npass; ++pass, ++acc_it) {
+          const int buf = acc_it & 1;
+          mbar_wait(smem_u32(&sm->acc_empty[buf]), ((acc_it >> 1) & 1) ^ 1);
+          tc_fence_after();
+          for (int s = 0; s < Ks; ++s) {
+            uint32_t a_slot;
+            if (stationary) {
+              a_slot = (a_base + s) % p.na;
+              if (pass == 0) mbar_wait(smem_u32(&sm->a_full[a_slot]), ((a_base + s) / p.na) & 1);
+            } else {
+              a_slot = a_it % p.na;
+              mbar_wait(smem_u32(&sm->a_full[a_slot]), (a_it / p.na) & 1);
+            }
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(a_ring + (size_t)a_slot * a_slot_bytes);
+            for (int j = 2 * pass; j < min(NT, 2 * pass + 2); ++j, ++b_it) {
+              const int b_slot = b_it % p.nb;
+              mbar_wait(smem_u32(&sm->b_full[b_slot]), (b_it / p.nb) & 1);
+              tc_fence_after();
+              const uint32_t b_addr = smem_u32(b_ring + (size_t)b_slot * b_slot_bytes);
+              const int ncols = min(128, p.Np - j * 128);
+              const uint32_t idesc = make_idesc(ncols);
+              const uint32_t d_addr = tmem_base + buf * 256 + (j - 2 * pass) * 128;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ah = make_desc(a_addr + k * 32);
+                const uint64_t bh = make_desc(b_addr + k * 32);
+                umma_bf16(d_addr, ah, bh, idesc, (s | k) != 0);
+                if (parts == 2) {
+                  const uint64_t al = make_desc(a_addr + SLAB_BYTES + k * 32);
+                  const uint64_t bl = make_desc(b_addr + SLAB_BYTES + k * 32);
+                  umma_bf16(d_addr, ah, bl, idesc, 1);
+                  umma_bf16(d_addr, al, bh, idesc, 1);
+                }
+              }
+              umma_commit(smem_u32(&sm->b_empty[b_slot]));
+            }
+            const bool last_use = stationary ? (pass == npass - 1) : true;
+            if (last_use) umma_commit(smem_u32(&sm->a_empty[a_slot]));
+            if (!stationary) ++a_it;
+          }
+          umma_commit(smem_u32(&sm->acc_full[buf]));
+        }
+        if (stationary) a_it += Ks;
+      }
+    }
+  } else if (warp < 6) {
+    // =============================== epilogue (warps 2..5) ==================================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    uint32_t acc_it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m0, m_end;
+      if (p.tiles_per_batch > 0) {
+        const int b = tile / p.tiles_per_batch;
+        m0 = b * p.rows_per_batch + (tile - b * p.tiles_per_batch) * 128;
+        m_end = (b + 1) * p.rows_per_batch;
+      } else {
+        m0 = tile * 128;
+        m_end = p.M;
+      }
+      const int m = m0 + quad * 32 + lane;
+      const bool row_ok = m < m_end;
+      float scale = 1.f;
+      if (p.row_scale != nullptr && row_ok) scale = __ldg(p.row_scale + m / p.rows_per_batch);
+      const float* gate_row = nullptr;
+      int ib = 0, iy = 0, ix = 0;
+      if ((p.epi == MPHSIR_EPI_SPECTRAL || p.epi >= TC_OUT_UNSHUFFLE) && row_ok) {
+        const int hw = p.H * p.W;
+        ib = m / hw;
+        const int rem = m - ib * hw;
+        iy = rem / p.W;
+        ix = rem - iy * p.W;
+        if (p.epi == MPHSIR_EPI_SPECTRAL) {
+          int ys = iy - p.shift, xs = ix - p.shift;
+          if (ys < 0) ys += p.H;
+          if (xs < 0) xs += p.W;
+          gate_row = p.gate + (size_t)(ib * (hw >> 6) + (ys >> 3) * (p.W >> 3) + (xs >> 3)) * p.N;
+        }
+      }
+      for (int pass = 0; pass < npass; ++pass, ++acc_it) {
+        const int buf = acc_it & 1;
+        mbar_wait(smem_u32(&sm->acc_full[buf]), (acc_it >> 1) & 1);
+        tc_fence_after();
+        const int ncols_pass = min(256, p.Np - pass * 256);
+        for (int c0 = 0; c0 < ncols_pass; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256 + c0, r);
+          if (!row_ok) continue;
+          const int n0 = pass * 256 + c0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int n = n0 + q * 4;
+            if (n >= p.N) break;
+            float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            if (p.bias != nullptr) {
+              const float4 bb = ldg4(p.bias + n);
+              v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+            }
+            switch (p.epi) {
+              case MPHSIR_EPI_BIAS:
+                *reinterpret_cast<float4*>(p.Y + (size_t)m * p.ldy + n) = v;
+                break;
+              case MPHSIR_EPI_RESIDUAL: {
+                const float4 r1 = ldg4(p.res1 + (size_t)m * p.ldr1 + n);
+                float4 o = make_float4(r1.x + scale * v.x, r1.y + scale * v.y, r1.z + scale * v.z, r1.w + scale * v.w);
+                if (p.res2 != nullptr) {
+                  const float4 r2 = ldg4(p.res2 + (size_t)m * p.ldr2 + n);
+                  o.x += r2.x; o.y += r2.y; o.z += r2.z; o.w += r2.w;
+                }
+                *reinterpret_cast<float4*>(p.Y + (size_t)m * p.ldy + n) = o;
+                break;
+              }
+              case MPHSIR_EPI_GLU: {
+                const float2 o = make_float2(v.x * gelu_erf(v.y), v.z * gelu_erf(v.w));
+                *reinterpret_cast<float2*>(p.Y + (size_t)m * p.ldy + (n >> 1)) = o;
+                break;
+              }
+              case MPHSIR_EPI_SPECTRAL: {
+                const float4 gt = ldg4(gate_row + n);
+                const float4 sa = ldg4(p.gsrc + (size_t)m * p.ldg + n);
+                const float4 r1 = ldg4(p.res1 + (size_t)m * p.ldr1 + n);
+                float4 o;
+                o.x = r1.x + scale * (sa.x * gt.x + v.x);
+                o.y = r1.y + scale * (sa.y * gt.y + v.y);
+                o.z = r1.z + scale * (sa.z * gt.z + v.z);
+                o.w = r1.w + scale * (sa.w * gt.w + v.w);
+                *reinterpret_cast<float4*>(p.Y + (size_t)m * p.ldy + n) = o;
+                break;
+              }
+              case TC_OUT_UNSHUFFLE: {
+                float* dst = p.Y + ((size_t)(ib * (p.H >> 1) + (iy >> 1)) * (p.W >> 1) + (ix >> 1)) * p.ldy +
+                             2 * (iy & 1) + (ix & 1);
+                dst[(n + 0) * 4] = v.x;
+                dst[(n + 1) * 4] = v.y;
+                dst[(n + 2) * 4] = v.z;
+                dst[(n + 3) * 4] = v.w;
+                break;
+              }
+              case TC_OUT_SHUFFLE: {
+                const int cn_total = p.N >> 2;
+                const int qq = n / cn_total, cn = n - qq * cn_total;
+                float* dst = p.Y +
+                             ((size_t)(ib * 2 * p.H + 2 * iy + (qq >> 1)) * (2 * p.W) + 2 * ix + (qq & 1)) * p.ldy + cn;
+                *reinterpret_cast<float4*>(dst) = v;
+                break;
+              }
+              case TC_OUT_NCHW_RES: {
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int c = n + e;
+                  if (c < p.N) {
+                    const size_t idx = ((size_t)(ib * p.N + c) * p.H + iy) * p.W + ix;
+                    p.Y[idx] = vv[e] + __ldg(p.R + idx);
+                  }
+                }
+                break;
+              }
+              default:
+                break;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[buf]));
+      }
+    }
+  } else {
+    // =============================== A converters (warps 6..13) =============================
+    const int ct = threadIdx.x - 6 * 32;  // 0..255
+    const int chunk = ct & 7;             // 8-element (16-byte bf16) chunk inside the 64-k slab
+    const int rbase = ct >> 3;            // rows rbase + 32*i, i = 0..3
+    uint32_t a_it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m0, m_end;
+      if (p.tiles_per_batch > 0) {
+        const int b = tile / p.tiles_per_batch;
+        m0 = b * p.rows_per_batch + (tile - b * p.tiles_per_batch) * 128;
+        m_end = (b + 1) * p.rows_per_batch;
+      } else {
+        m0 = tile * 128;
+        m_end = p.M;
+      }
+      bool valid[4];
+      const float* arow[4];
+      int pb[4], py[4], px[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + rbase + 32 * i;
+        valid[i] = m < m_end;
+        const int mm = valid[i] ? m : m0;
+        if (CONV) {
+          const int hw = p.H * p.W;
+          pb[i] = mm / hw;
+          const int rem = mm - pb[i] * hw;
+          py[i] = rem / p.W;
+          px[i] = rem - py[i] * p.W;
+          arow[i] = nullptr;
+        } else {
+          arow[i] = p.A + (size_t)(p.a_row_mod > 0 ? mm % p.a_row_mod : mm) * p.lda;
+          pb[i] = py[i] = px[i] = 0;
+        }
+      }
+      // LayerNorm statistics: the 8 lanes that share a row reduce sum / sum-of-squares over K.
+      float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f};
+      if (!CONV && p.ln_g != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float s = 0.f, q = 0.f;
+          if (valid[i]) {
+            for (int k = chunk * 4; k < p.Ka; k += 32) {
+              const float4 v = ldg4(arow[i] + k);
+              s += (v.x + v.y) + (v.z + v.w);
+              q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+            }
+          }
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+          }
+          const float mu = s / (float)p.Ka;
+          mean[i] = mu;
+          rstd[i] = rsqrtf(fmaxf(q / (float)p.Ka - mu * mu, 0.f) + 1e-5f);
+        }
+      }
+      const int conv_passes = stationary ? 1 : npass;
+      for (int pass = 0; pass < conv_passes; ++pass) {
+        for (int s = 0; s < Ks; ++s, ++a_it) {
+          const int slot = a_it % p.na;
+          mbar_wait(smem_u32(&sm->a_empty[slot]), ((a_it / p.na) & 1) ^ 1);
+          uint8_t* dst = a_ring + (size_t)slot * a_slot_bytes;
+          const int k = s * 64 + chunk * 8;
+          const bool kin = k < p.Ka;
+          float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = g0;
+          float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
+          if (!CONV && p.ln_g != nullptr && kin) {
+            g0 = ldg4(p.ln_g + k); g1 = ldg4(p.ln_g + k + 4);
+            e0 = ldg4(p.ln_b + k); e1 = ldg4(p.ln_b + k + 4);
+          }
+          int dy = 0, dx = 0, cc = 0;
+          if (CONV) {
+            const int tap = k / p.Cin;
+            cc = k - tap * p.Cin;
+            dy = tap / 3 - 1;
+            dx = tap - (tap / 3) * 3 - 1;
+          }
+          float4 v0[4], v1[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            bool ok = valid[i] && kin;
+            const float* src;
+            if (CONV) {
+              const int yy = py[i] + dy, xx = px[i] + dx;
+              ok = ok && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+              src = p.A + ((size_t)(pb[i] * p.H + yy) * p.W + xx) * p.lda + cc;
+            } else {
+              src = arow[i] + k;
+            }
+            if (ok) {
+              v0[i] = ldg4(src);
+              v1[i] = ldg4(src + 4);
+            } else {
+              v0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              v1[i] = v0[i];
+            }
+            if (!CONV && p.ln_g != nullptr && ok) {
+              const float a = rstd[i], mu = mean[i];
+              v0[i].x = (v0[i].x - mu) * a * g0.x + e0.x; v0[i].y = (v0[i].y - mu) * a * g0.y + e0.y;
+              v0[i].z = (v0[i].z - mu) * a * g0.z + e0.z; v0[i].w = (v0[i].w - mu) * a * g0.w + e0.w;
+              v1[i].x = (v1[i].x - mu) * a * g1.x + e1.x; v1[i].y = (v1[i].y - mu) * a * g1.y + e1.y;
+              v1[i].z = (v1[i].z - mu) * a * g1.z + e1.z; v1[i].w = (v1[i].w - mu) * a * g1.w + e1.w;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = rbase + 32 * i;
+            uint4 hi, lo;
+            split2(v0[i].x, v0[i].y, hi.x, lo.x);
+            split2(v0[i].z, v0[i].w, hi.y, lo.y);
+            split2(v1[i].x, v1[i].y, hi.z, lo.z);
+            split2(v1[i].z, v1[i].w, hi.w, lo.w);
+            const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst + off) = hi;
+            if (parts == 2) *reinterpret_cast<uint4*>(dst + SLAB_BYTES + off) = lo;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&sm->a_full[slot]));
+        }
+      }
+    }
+  }
+
+  // teardown: everything issued has completed once the epilogue warps are done with the last tile
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bimg packing kernels
+// ------------------------------------------------------------------------------------------------
+// W logical [N][K] fp32 (row n, ld floats per row; optionally transposed source) -> bf16 hi/lo image.
+__global__ void __launch_bounds__(256) pack_bimg_kernel(const float* __restrict__ W, long long ld, int transposed,
+                                                        long long w_batch_stride, uint16_t* __restrict__ img,
+                                                        long long img_batch_elems, int N, int K, int Np, int Ks) {
+  const int b = blockIdx.y;
+  const float* Wb = W + (long long)b * w_batch_stride;
+  uint16_t* out = img + (long long)b * img_batch_elems;
+  const long long total = (long long)Ks * Np * 8;  // 16-byte chunks per part
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx & 7);
+    const long long rn = idx >> 3;
+    const int n = (int)(rn % Np);
+    const int s = (int)(rn / Np);
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = s * 64 + c * 8 + 2 * e + h;
+        v[h] = (n < N && k < K) ? __ldg(Wb + (transposed ? (long long)k * ld + n : (long long)n * ld + k)) : 0.f;
+      }
+      split2(v[0], v[1], hi[e], lo[e]);
+    }
+    const size_t off = bimg_offset(0, s, n, c, Np, Ks);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out) + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    const size_t off_lo = bimg_offset(1, s, n, c, Np, Ks);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out) + off_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+static size_t smem_bytes(int na, int nb, int parts) { return 1024 + (size_t)(na + nb) * SLAB_BYTES * parts; }
+
+int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
+  static int sm_count = 0;
+  static bool configured = false;
+  if (!configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    const int max_smem = 227 * 1024;
+    cudaError_t e1 = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaError_t e2 = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+      return MPHSIR_ERR_CUDA;
+    }
+    configured = true;
+  }
+  // ring sizes: bf16x3 slots are 32 KB (A 4 + B 3 = 224 KB); bf16x1 slots are 16 KB (A 8 + B 5 = 208 KB)
+  a.na = a.parts == 2 ? 4 : 8;
+  a.nb = a.parts == 2 ? 3 : 5;
+  const size_t smem = smem_bytes(a.na, a.nb, a.parts);
+  const int grid = a.num_tiles < sm_count ? a.num_tiles : sm_count;
+  if (conv)
+    gemm_tc_kernel<true><<<grid, kThreads, smem, st>>>(a);
+  else
+    gemm_tc_kernel<false><<<grid, kThreads, smem, st>>>(a);
+  return check_launch(conv ? "conv3x3(tc)" : "gemm(tc)");
+}
+
+}  // namespace tc
+}  // namespace mphsir
+
+using namespace mphsir;
+
+extern "C" size_t mphsir_bimg_bytes(int N, int K) {
+  const int Np = (N + 15) / 16 * 16, Ks = (K + 63) / 64;
+  return (size_t)2 * Ks * Np * 128;
+}
+
+extern "C" int mphsir_pack_bimg(const float* W, int ld, int transposed, long long w_batch_stride, void* img,
+                                int batch, int N, int K, void* stream) {
+  MPHSIR_REQUIRE(W && img && batch > 0 && N > 0 && K > 0 && ld > 0, "pack_bimg: bad arguments");
+  MPHSIR_REQUIRE((reinterpret_cast<uintptr_t>(img) & 127) == 0, "pack_bimg: image must be 128-byte aligned");
+  const int Np = (N + 15) / 16 * 16, Ks = (K + 63) / 64;
+  const long long total = (long long)Ks * Np * 8;
+  dim3 grid((unsigned)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256), batch);
+  tc::pack_bimg_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      W, ld, transposed, w_batch_stride, reinterpret_cast<uint16_t*>(img), (long long)(mphsir_bimg_bytes(N, K) / 2), N,
+      K, Np, Ks);
+  return check_launch("pack_bimg");
+}

@@ -1,0 +1,53 @@
+// Shared declarations of the tcgen05 GEMM engine (gemm_tc.cu) and its callers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mphsir {
+namespace tc {
+
+enum { TC_OUT_UNSHUFFLE = 10, TC_OUT_SHUFFLE = 11, TC_OUT_NCHW_RES = 12 };
+
+// Byte offset of the 16-byte chunk (8 bf16: k = s*64 + c*8 .. +7) of weight row n in the packed image:
+//   [part (hi, lo)][k-slab s][row n] x 128 bytes, chunks XOR-swizzled by (n & 7) — i.e. exactly the
+//   SWIZZLE_128B K-major shared-memory image, so a block of rows is one contiguous bulk copy.
+__host__ __device__ inline size_t bimg_offset(int part, int s, int n, int c, int Np, int Ks) {
+  return ((size_t)(part * Ks + s) * Np + n) * 128 + (size_t)((c ^ (n & 7)) << 4);
+}
+
+struct TcArgs {
+  const float* A;
+  long long lda;
+  int a_row_mod;
+  int Ka;  // valid A columns (multiple of 8)
+  const void* Bimg;
+  long long b_batch_bytes;
+  int rows_per_batch;
+  int tiles_per_batch;
+  int num_tiles;
+  float* Y;
+  long long ldy;
+  int M, N, Np, ks;
+  int parts;   // 1 = bf16x1, 2 = bf16x3 (hi/lo split)
+  int na, nb;  // ring depths (set by the launcher)
+  const float* ln_g;
+  const float* ln_b;
+  const float* bias;
+  int epi;
+  const float* res1;
+  long long ldr1;
+  const float* res2;
+  long long ldr2;
+  const float* gsrc;
+  long long ldg;
+  const float* gate;
+  int H, W, shift;
+  const float* row_scale;
+  int Cin;
+  const float* R;
+};
+
+int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st);
+
+}  // namespace tc
+}  // namespace mphsir

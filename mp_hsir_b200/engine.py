@@ -102,6 +102,9 @@ def rel_pos_bias(table: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 
 
+PRECISIONS = {"fp32": lib.PREC_BF16X3, "fp32_exact": lib.PREC_FP32_SIMT, "bf16": lib.PREC_BF16}
+
+
 class Workspace:
     """Named, grow-only fp32 device buffers; a forward at a fixed shape allocates nothing after the
     first call (CUDA-graph friendly)."""
@@ -125,8 +128,15 @@ class Workspace:
             self.bufs[name] = t
         return t
 
+    def raw(self, name: str, nbytes: int) -> torch.Tensor:
+        t = self.bufs.get(name)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(nbytes, 128), device=self.device, dtype=torch.uint8)
+            self.bufs[name] = t
+        return t
+
     def bytes(self) -> int:
-        return sum(t.numel() * 4 for t in self.bufs.values())
+        return sum(t.numel() * t.element_size() for t in self.bufs.values())
 
 
 class Engine:
@@ -141,6 +151,7 @@ class Engine:
         with torch.cuda.device(self.device):
             self.sm_count = lib.device_check(self.device.index or 0)
         self.ws = Workspace(self.device)
+        self.prec = PRECISIONS[net.precision]
         self.packed: Optional[dict] = None
         self._versions = None
         self._graphs: Dict[tuple, tuple] = {}
@@ -165,15 +176,21 @@ class Engine:
         net, cfg = self.net, self.cfg
         f32 = lambda t: t.detach().to(device=self.device, dtype=torch.float32)  # noqa: E731
         P: dict = {}
+        tc = self.prec != lib.PREC_FP32_SIMT
+
+        def W(bt: torch.Tensor, n: int, k: int) -> lib.Weight:
+            """fp32 "in x out" matrix -> Weight (adds the tensor-core image when that engine is selected)."""
+            return lib.Weight(bt, lib.pack_bimg(bt, n, k, transposed=True) if tc else None, n, k)
+
         cin_p = _ceil(cfg.in_channel, 16)
         P["cin_p"] = cin_p
-        P["patch_embed"] = pack_conv3x3(f32(net.patch_embed.proj.weight), cin_pad=cin_p)
-        P["down1_2"] = pack_conv3x3(f32(net.down1_2.body[0].weight))
-        P["down2_3"] = pack_conv3x3(f32(net.down2_3.body[0].weight))
-        P["up3_2"] = pack_conv3x3(f32(net.up3_2.body[0].weight), shuffle=True)
-        P["up2_1"] = pack_conv3x3(f32(net.up2_1.body[0].weight), shuffle=True)
-        P["reduce_chan_level2"] = pack_linear_t(f32(net.reduce_chan_level2.weight))
-        P["output"] = pack_conv3x3(f32(net.output.weight))
+        P["patch_embed"] = W(pack_conv3x3(f32(net.patch_embed.proj.weight), cin_pad=cin_p), cfg.dim, 9 * cin_p)
+        P["down1_2"] = W(pack_conv3x3(f32(net.down1_2.body[0].weight)), cfg.dim // 2, 9 * cfg.dim)
+        P["down2_3"] = W(pack_conv3x3(f32(net.down2_3.body[0].weight)), cfg.dim, 18 * cfg.dim)
+        P["up3_2"] = W(pack_conv3x3(f32(net.up3_2.body[0].weight), shuffle=True), 8 * cfg.dim, 36 * cfg.dim)
+        P["up2_1"] = W(pack_conv3x3(f32(net.up2_1.body[0].weight), shuffle=True), 4 * cfg.dim, 18 * cfg.dim)
+        P["reduce_chan_level2"] = W(pack_linear_t(f32(net.reduce_chan_level2.weight)), 2 * cfg.dim, 4 * cfg.dim)
+        P["output"] = W(pack_conv3x3(f32(net.output.weight)), cfg.out_channel, 18 * cfg.dim)
         P["clip"] = f32(net.text_prompt.clip_prompt).contiguous()
 
         for st in cfg.stages():
@@ -185,14 +202,14 @@ class Engine:
                 d["ln1"] = (f32(blk.norm1.weight).contiguous(), f32(blk.norm1.bias).contiguous())
                 d["ln2"] = (f32(blk.norm2.weight).contiguous(), f32(blk.norm2.bias).contiguous())
                 a = blk.attn
-                d["qkv_w"] = pack_linear_t(f32(a.qkv.weight))
+                d["qkv_w"] = W(pack_linear_t(f32(a.qkv.weight)), 3 * st.dim, st.dim)
                 d["qkv_b"] = f32(a.qkv.bias).contiguous()
-                d["proj_w"] = pack_linear_t(f32(a.proj.weight))
+                d["proj_w"] = W(pack_linear_t(f32(a.proj.weight)), st.dim, st.dim)
                 d["proj_b"] = f32(a.proj.bias).contiguous()
                 d["rpb"] = rel_pos_bias(f32(a.relative_position_bias_table), a.relative_position_index.to(self.device))
                 g = blk.gobal_spectral_attn
                 d["temp"] = f32(g.temperature).reshape(-1).contiguous()
-                d["sqkv_w"] = pack_linear_t(f32(g.qkv.weight))
+                d["sqkv_w"] = W(pack_linear_t(f32(g.qkv.weight)), 3 * st.dim, st.dim)
                 d["sdw"] = pack_dw(f32(g.qkv_dwconv.weight))
                 d["sout_t"] = f32(g.project_out.weight).reshape(st.dim, st.dim).t().contiguous()
                 l = blk.local_spectral_attn
@@ -209,8 +226,9 @@ class Engine:
                     "p2b": f32(l.proj.bias).contiguous(),
                     "upT": f32(l.linear_up.weight).t().contiguous(),
                 }
-                d["fc1_w"], d["fc1_b"] = pack_glu_fc1(f32(blk.mlp.fc1.weight), f32(blk.mlp.fc1.bias), hid, hid_pad)
-                d["fc2_w"] = pack_linear_t(f32(blk.mlp.fc2.weight), k_pad=hid_pad)
+                fc1_w, d["fc1_b"] = pack_glu_fc1(f32(blk.mlp.fc1.weight), f32(blk.mlp.fc1.bias), hid, hid_pad)
+                d["fc1_w"] = W(fc1_w, 2 * hid_pad, st.dim)
+                d["fc2_w"] = W(pack_linear_t(f32(blk.mlp.fc2.weight), k_pad=hid_pad), st.dim, hid_pad)
                 d["fc2_b"] = f32(blk.mlp.fc2.bias).contiguous()
                 blocks.append(d)
             P[st.name] = blocks
@@ -229,15 +247,16 @@ class Engine:
             d["learnable"] = f32(m.text_prompt_learnable).reshape(cfg.task_classes, D).contiguous()
             d["visual"] = f32(m.visual_prompt)[0].permute(1, 2, 0).reshape(ps * ps, D).contiguous()
             d["ln11"], d["ln12"], d["ln2"] = ln(ct.norm11), ln(ct.norm12), ln(ct.norm2)
-            d["q_w"] = pack_linear_t(f32(ct.attn.q.weight))
+            d["q_w"] = W(pack_linear_t(f32(ct.attn.q.weight)), D, D)
             d["q_dw"] = pack_dw(f32(ct.attn.q_dwconv.weight))
-            d["kv_w"] = pack_linear_t(f32(ct.attn.kv.weight))
+            d["kv_w"] = W(pack_linear_t(f32(ct.attn.kv.weight)), 2 * D, D)
             d["kv_dw"] = pack_dw(f32(ct.attn.kv_dwconv.weight))
             d["temp"] = f32(ct.attn.temperature).reshape(-1).contiguous()
             d["out_t"] = f32(ct.attn.project_out.weight).reshape(D, D).t().contiguous()
-            d["pin_w"], d["ffn_dw"], d["pout_w"] = pack_gdfn(
+            pin_w, d["ffn_dw"], pout_w = pack_gdfn(
                 f32(ct.ffn.project_in.weight), f32(ct.ffn.dwconv.weight), f32(ct.ffn.project_out.weight), hid, hid_pad)
-            d["conv_last"] = pack_conv3x3(f32(m.conv_last.weight))
+            d["pin_w"], d["pout_w"] = W(pin_w, 2 * hid_pad, D), W(pout_w, D, hid_pad)
+            d["conv_last"] = W(pack_conv3x3(f32(m.conv_last.weight)), D, 9 * D)
             P[name] = d
 
         for name in ("fusion1", "fusion2"):
@@ -248,19 +267,26 @@ class Engine:
             hid_pad = _ceil(hid, 16)
             d = {"C": C2, "heads": m.heads, "hid_pad": hid_pad}
             d["ln1"], d["ln2"] = ln(tb.norm1), ln(tb.norm2)
-            d["qkv_w"] = pack_linear_t(f32(tb.attn.qkv.weight))
+            d["qkv_w"] = W(pack_linear_t(f32(tb.attn.qkv.weight)), 3 * C2, C2)
             d["dw"] = pack_dw(f32(tb.attn.qkv_dwconv.weight))
             d["temp"] = f32(tb.attn.temperature).reshape(-1).contiguous()
             d["out_t"] = f32(tb.attn.project_out.weight).reshape(C2, C2).t().contiguous()
-            d["pin_w"], d["ffn_dw"], d["pout_w"] = pack_gdfn(
+            pin_w, d["ffn_dw"], pout_w = pack_gdfn(
                 f32(tb.ffn.project_in.weight), f32(tb.ffn.dwconv.weight), f32(tb.ffn.project_out.weight), hid, hid_pad)
-            d["conv_w"] = pack_linear_t(f32(m.conv.weight))
+            d["pin_w"], d["pout_w"] = W(pin_w, 2 * hid_pad, C2), W(pout_w, C2, hid_pad)
+            d["conv_w"] = W(pack_linear_t(f32(m.conv.weight)), C2 // 2, C2)
             P[name] = d
         return P
 
     # -- building blocks -------------------------------------------------------------------------
+    def _gemm(self, *a, **k):
+        lib.gemm(*a, precision=self.prec, **k)
+
+    def _conv(self, *a, **k):
+        lib.conv3x3(*a, precision=self.prec, **k)
+
     def _spectral_attention(self, tag: str, q: View, q_shared: bool, k: View, k_shared: bool, temp, out_t,
-                            B: int, HW: int, heads: int, c: int) -> torch.Tensor:
+                            B: int, HW: int, heads: int, c: int) -> lib.Weight:
         """Gram statistics -> softmax -> folded per-sample matrix Mt [B, C, ldm] ("in x out")."""
         ws = self.ws
         C = heads * c
@@ -272,7 +298,12 @@ class Engine:
         lib.gram_partial(q, q_shared, k, k_shared, partial, B, HW, heads, c)
         lib.gram_softmax(partial, nch, temp, attn, B, heads, c)
         lib.spectral_fold(attn, out_t, Mt, B, heads, c)
-        return Mt
+        img = None
+        if self.prec != lib.PREC_FP32_SIMT:
+            nb = lib.bimg_bytes(C, C)
+            img = ws.raw(tag + ".img", B * nb)[: B * nb].view(B, nb)
+            lib.pack_bimg(Mt, C, C, transposed=True, img=img)
+        return lib.Weight(Mt, img, C, C)
 
     def _pgsstb(self, w: dict, st: Stage, shift: int, x: View, out: View, res2: Optional[View], B: int, H: int,
                 W: int, row_scales=None, taps: Optional[dict] = None):
@@ -292,26 +323,25 @@ class Engine:
         s2 = None if row_scales is None else row_scales[1]
 
         # LN1 + qkv projection (net/MP_HSIR.py:667, :195)
-        lib.gemm(x, w["qkv_w"], qkv, 3 * C, ln=w["ln1"], bias=w["qkv_b"])
+        self._gemm(x, w["qkv_w"], qkv, 3 * C, ln=w["ln1"], bias=w["qkv_b"])
         # shifted-window attention core + per-window mean (:671-683, :198-215)
         lib.window_attn(qkv, w["rpb"], core, wmean, B, H, W, C, heads, shift)
         # local spectral gate (:132-152)
         lib.local_gate(wmean, w["gate"], gate, B_, C, st.rank)
         # attention output projection (:216) in image order
-        lib.gemm(core, w["proj_w"], sa, C, bias=w["proj_b"])
+        self._gemm(core, w["proj_w"], sa, C, bias=w["proj_b"])
         # global spectral attention: 1x1 -> dw3x3 -> Gram/softmax/fold -> apply (:98-113)
         t3 = ws.mat("qkv", N, 3 * C)  # qkv is dead: reuse
-        lib.gemm(sa, w["sqkv_w"], t3, 3 * C)
+        self._gemm(sa, w["sqkv_w"], t3, 3 * C)
         lib.dwconv3x3(t3, w["sdw"], dw3, B, H, W, 3 * C)
         Mt = self._spectral_attention("spec", dw3.cols_slice(0, C), False, dw3.cols_slice(C, 2 * C), False,
                                       w["temp"], w["sout_t"], B, H * W, heads, C // heads)
         # x = shortcut + DropPath(sa*gate + project_out(attn v))   (:715-718)
-        lib.gemm(dw3.cols_slice(2 * C, 3 * C), Mt, mid, C, epi=lib.EPI_SPECTRAL, res1=x, gsrc=sa, gate=gate,
-                 H=H, W=W, shift=shift, rows_per_batch=H * W, b_batch_stride=Mt.shape[1] * Mt.shape[2],
-                 row_scale=s1)
+        self._gemm(dw3.cols_slice(2 * C, 3 * C), Mt, mid, C, epi=lib.EPI_SPECTRAL, res1=x, gsrc=sa, gate=gate,
+                 H=H, W=W, shift=shift, rows_per_batch=H * W, row_scale=s1)
         # x = x + DropPath(fc2(value * gelu(gate)))  with LN2 fused in front (:719, :76-82)
-        lib.gemm(mid, w["fc1_w"], hidden, 2 * w["hid_pad"], ln=w["ln2"], bias=w["fc1_b"], epi=lib.EPI_GLU)
-        lib.gemm(hidden, w["fc2_w"], out, C, bias=w["fc2_b"], epi=lib.EPI_RESIDUAL, res1=mid, res2=res2,
+        self._gemm(mid, w["fc1_w"], hidden, 2 * w["hid_pad"], ln=w["ln2"], bias=w["fc1_b"], epi=lib.EPI_GLU)
+        self._gemm(hidden, w["fc2_w"], out, C, bias=w["fc2_b"], epi=lib.EPI_RESIDUAL, res1=mid, res2=res2,
                  rows_per_batch=H * W, row_scale=s2)
         if taps is not None:
             taps.update(core=core.torch().clone(), wmean=wmean[: B_ * C].view(B_, C).clone(),
@@ -337,9 +367,9 @@ class Engine:
         hp = w["hid_pad"]
         hin = self.ws.mat(tag + ".hin", N, 2 * hp)
         hg = self.ws.mat(tag + ".hg", N, hp)
-        lib.gemm(x, w["pin_w"], hin, 2 * hp, ln=ln)
+        self._gemm(x, w["pin_w"], hin, 2 * hp, ln=ln)
         lib.dwconv3x3(hin, w["ffn_dw"], hg, B, H, W, 2 * hp, gate_half=hp)
-        lib.gemm(hg, w["pout_w"], out, D, epi=lib.EPI_RESIDUAL, res1=x)
+        self._gemm(hg, w["pout_w"], out, D, epi=lib.EPI_RESIDUAL, res1=x)
 
     def _tvsp(self, name: str, clip_b: torch.Tensor, weights: torch.Tensor, B: int, Hs: int, Ws: int, out: View):
         """TVSP.forward (net/MP_HSIR.py:572-583) -> writes [B*Hs*Ws, D] into `out` (a column slice)."""
@@ -352,25 +382,24 @@ class Engine:
         lib.tvsp_query(clip_b, weights, w["learnable"], Q, B, T, D, ps)
         q1 = ws.mat(name + ".q1", B * n, D)
         qd = ws.mat(name + ".qd", B * n, D)
-        lib.gemm(Q, w["q_w"], q1, D, ln=w["ln11"])
+        self._gemm(Q, w["q_w"], q1, D, ln=w["ln11"])
         lib.dwconv3x3(q1, w["q_dw"], qd, B, ps, ps, D)
         vis = View.of(w["visual"])
         kv1 = ws.mat(name + ".kv1", n, 2 * D)
         kvd = ws.mat(name + ".kvd", n, 2 * D)
-        lib.gemm(vis, w["kv_w"], kv1, 2 * D, ln=w["ln12"])
+        self._gemm(vis, w["kv_w"], kv1, 2 * D, ln=w["ln12"])
         lib.dwconv3x3(kv1, w["kv_dw"], kvd, 1, ps, ps, 2 * D)
         Mt = self._spectral_attention(name + ".spec", qd, False, kvd.cols_slice(0, D), True, w["temp"], w["out_t"],
                                       B, n, 2, D // 2)
         xa = ws.mat(name + ".xa", B * n, D)
-        lib.gemm(kvd.cols_slice(D, 2 * D), Mt, xa, D, epi=lib.EPI_RESIDUAL, res1=Q, rows_per_batch=n,
-                 b_batch_stride=Mt.shape[1] * Mt.shape[2], a_row_mod=n, M=B * n)
+        self._gemm(kvd.cols_slice(D, 2 * D), Mt, xa, D, epi=lib.EPI_RESIDUAL, res1=Q, rows_per_batch=n, a_row_mod=n, M=B * n)
         pr = ws.mat(name + ".pr", B * n, D)
         self._gdfn(name + ".ffn", w, xa, pr, w["ln2"], B, ps, ps, D)
         if (Hs, Ws) != (ps, ps):
             prr = ws.mat(name + ".prr", B * Hs * Ws, D)
             lib.bilinear(pr, prr, B, ps, ps, Hs, Ws, D)
             pr = prr
-        lib.conv3x3(pr, w["conv_last"], out.ptr, out.ld, B, Hs, Ws, D, D, lib.CONV_TOKENS)
+        self._conv(pr, w["conv_last"], out.ptr, out.ld, B, Hs, Ws, D, D, lib.CONV_TOKENS)
 
     def _fusion(self, name: str, xcat: View, out: View, B: int, H: int, W: int):
         """PromptFusion.forward (net/MP_HSIR.py:594-599) on the already-concatenated buffer."""
@@ -380,16 +409,15 @@ class Engine:
         N = B * H * W
         t3 = ws.mat(name + ".t3", N, 3 * C2)
         dw3 = ws.mat(name + ".dw3", N, 3 * C2)
-        lib.gemm(xcat, w["qkv_w"], t3, 3 * C2, ln=w["ln1"])
+        self._gemm(xcat, w["qkv_w"], t3, 3 * C2, ln=w["ln1"])
         lib.dwconv3x3(t3, w["dw"], dw3, B, H, W, 3 * C2)
         Mt = self._spectral_attention(name + ".spec", dw3.cols_slice(0, C2), False, dw3.cols_slice(C2, 2 * C2), False,
                                       w["temp"], w["out_t"], B, H * W, heads, C2 // heads)
         y1 = ws.mat(name + ".y1", N, C2)
-        lib.gemm(dw3.cols_slice(2 * C2, 3 * C2), Mt, y1, C2, epi=lib.EPI_RESIDUAL, res1=xcat, rows_per_batch=H * W,
-                 b_batch_stride=Mt.shape[1] * Mt.shape[2])
+        self._gemm(dw3.cols_slice(2 * C2, 3 * C2), Mt, y1, C2, epi=lib.EPI_RESIDUAL, res1=xcat, rows_per_batch=H * W)
         y2 = ws.mat(name + ".y2", N, C2)
         self._gdfn(name + ".ffn", w, y1, y2, w["ln2"], B, H, W, C2)
-        lib.gemm(y2, w["conv_w"], out, out.cols)
+        self._gemm(y2, w["conv_w"], out, out.cols)
 
     # -- whole network ----------------------------------------------------------------------------
     def task_weights(self, task_id: torch.Tensor) -> torch.Tensor:
@@ -437,34 +465,34 @@ class Engine:
         tok = ws.mat("tok_in", N1, P["cin_p"])
         lib.nchw_to_tokens(x, tok)
         x1 = ws.mat("x1", N1, d)
-        lib.conv3x3(tok, P["patch_embed"], x1.ptr, x1.ld, B, H, W, P["cin_p"], d)
+        self._conv(tok, P["patch_embed"], x1.ptr, x1.ld, B, H, W, P["cin_p"], d)
 
         fcat1 = ws.mat("fcat1", N1, 2 * d)          # [e1 | prompt1]
         e1 = fcat1.cols_slice(0, d)
         self._stage("encoder_level1", x1, e1, B, H, W)
 
         x2 = ws.mat("x2", N2, 2 * d)
-        lib.conv3x3(e1, P["down1_2"], x2.ptr, x2.ld, B, H, W, d, d // 2, lib.CONV_UNSHUFFLE)
+        self._conv(e1, P["down1_2"], x2.ptr, x2.ld, B, H, W, d, d // 2, lib.CONV_UNSHUFFLE)
         fcat2 = ws.mat("fcat2", N2, 4 * d)          # [e2 | prompt2]
         e2 = fcat2.cols_slice(0, 2 * d)
         self._stage("encoder_level2", x2, e2, B, H2, W2)
 
         x3 = ws.mat("x3", N3, 4 * d)
-        lib.conv3x3(e2, P["down2_3"], x3.ptr, x3.ld, B, H2, W2, 2 * d, d, lib.CONV_UNSHUFFLE)
+        self._conv(e2, P["down2_3"], x3.ptr, x3.ld, B, H2, W2, 2 * d, d, lib.CONV_UNSHUFFLE)
         lat = ws.mat("lat", N3, 4 * d)
         self._stage("latent", x3, lat, B, H3, W3)
 
         cat2 = ws.mat("cat2", N2, 4 * d)            # [up3_2(latent) | fusion2]
-        lib.conv3x3(lat, P["up3_2"], cat2.ptr, cat2.ld, B, H3, W3, 4 * d, 8 * d, lib.CONV_SHUFFLE)
+        self._conv(lat, P["up3_2"], cat2.ptr, cat2.ld, B, H3, W3, 4 * d, 8 * d, lib.CONV_SHUFFLE)
         self._tvsp("prompt2", clip_b, weights, B, H2, W2, fcat2.cols_slice(2 * d, 4 * d))
         self._fusion("fusion2", fcat2, cat2.cols_slice(2 * d, 4 * d), B, H2, W2)
         d2in = ws.mat("d2in", N2, 2 * d)
-        lib.gemm(cat2, P["reduce_chan_level2"], d2in, 2 * d)
+        self._gemm(cat2, P["reduce_chan_level2"], d2in, 2 * d)
         d2 = ws.mat("d2", N2, 2 * d)
         self._stage("decoder_level2", d2in, d2, B, H2, W2)
 
         cat1 = ws.mat("cat1", N1, 2 * d)            # [up2_1(d2) | fusion1]
-        lib.conv3x3(d2, P["up2_1"], cat1.ptr, cat1.ld, B, H2, W2, 2 * d, 4 * d, lib.CONV_SHUFFLE)
+        self._conv(d2, P["up2_1"], cat1.ptr, cat1.ld, B, H2, W2, 2 * d, 4 * d, lib.CONV_SHUFFLE)
         self._tvsp("prompt1", clip_b, weights, B, H, W, fcat1.cols_slice(d, 2 * d))
         self._fusion("fusion1", fcat1, cat1.cols_slice(d, 2 * d), B, H, W)
         dd1 = ws.mat("dd1", N1, 2 * d)
@@ -472,7 +500,7 @@ class Engine:
         ref = ws.mat("ref", N1, 2 * d)
         self._stage("refinement", dd1, ref, B, H, W)
 
-        lib.conv3x3(ref, P["output"], out.data_ptr(), 0, B, H, W, 2 * d, cfg.out_channel, lib.CONV_NCHW_RES, R=x)
+        self._conv(ref, P["output"], out.data_ptr(), 0, B, H, W, 2 * d, cfg.out_channel, lib.CONV_NCHW_RES, R=x)
         if taps is not None:
             taps.update(x1=x1.torch().clone(), e1=e1.torch().clone(), e2=e2.torch().clone(), lat=lat.torch().clone(),
                         p1=fcat1.cols_slice(d, 2 * d).torch().clone(), p2=fcat2.cols_slice(2 * d, 4 * d).torch().clone(),

@@ -34,6 +34,7 @@ class GemmParams(C.Structure):
         ("gate", C.c_void_p),
         ("H", C.c_int), ("W", C.c_int), ("shift", C.c_int),
         ("row_scale", C.c_void_p),
+        ("precision", C.c_int), ("Bimg", C.c_void_p), ("bimg_batch_bytes", C.c_longlong),
     ]
 
 
@@ -45,6 +46,7 @@ class ConvParams(C.Structure):
         ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("N", C.c_int),
         ("out_mode", C.c_int),
         ("R", C.c_void_p),
+        ("precision", C.c_int), ("Bimg", C.c_void_p),
     ]
 
 
@@ -55,6 +57,7 @@ class LocalGateParams(C.Structure):
 
 
 EPI_BIAS, EPI_RESIDUAL, EPI_GLU, EPI_SPECTRAL = 0, 1, 2, 3
+PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16 = 0, 1, 2
 CONV_TOKENS, CONV_UNSHUFFLE, CONV_SHUFFLE, CONV_NCHW_RES = 0, 1, 2, 3
 
 # symbol -> (restype, argtypes); also the list tests/test_abi.py checks against include/mphsir.h
@@ -64,6 +67,8 @@ SIGNATURES = {
     "mphsir_last_error": (C.c_char_p, []),
     "mphsir_device_check": (_I, [_I, C.POINTER(_I)]),
     "mphsir_nchw_to_tokens": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
+    "mphsir_bimg_bytes": (C.c_size_t, [_I, _I]),
+    "mphsir_pack_bimg": (_I, [_VP, _I, _I, _LL, _VP, _I, _I, _I, _VP]),
     "mphsir_gemm_fwd": (_I, [C.POINTER(GemmParams), _VP]),
     "mphsir_conv3x3_fwd": (_I, [C.POINTER(ConvParams), _VP]),
     "mphsir_window_attn_fwd": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _VP]),
@@ -200,15 +205,61 @@ def nchw_to_tokens(inp: torch.Tensor, out: View) -> None:
             lambda: (0.0, 4.0 * B * H * W * (Cc + out.ld), "nchw_to_tokens"))
 
 
-def gemm(A: View, Bt: torch.Tensor, Y: View, N: int, *, K: Optional[int] = None, ln=None, bias=None,
+class Weight:
+    """A GEMM weight in both engine layouts: `bt` fp32 "in x out" [Kp, ldb] (SIMT engine) and `img`, the
+    bf16 hi/lo tensor-core image of the logical [N, K] matrix (tcgen05 engine).  Either may be None.
+    3-D `bt` / batched `img` ([B, bytes]) hold per-sample matrices."""
+
+    __slots__ = ("bt", "img", "n", "k")
+
+    def __init__(self, bt: Optional[torch.Tensor], img: Optional[torch.Tensor], n: int, k: int):
+        self.bt, self.img, self.n, self.k = bt, img, n, k
+
+
+def bimg_bytes(n: int, k: int) -> int:
+    return int(load().mphsir_bimg_bytes(n, k))
+
+
+def pack_bimg(w: torch.Tensor, n: int, k: int, transposed: bool = False, img: Optional[torch.Tensor] = None):
+    """Pack logical W[N,K] (2-D, or 3-D batch) into the tensor-core image (uint8 tensor).  `transposed`:
+    the source is stored "in x out" (w[..., k, n])."""
+    w3 = w if w.dim() == 3 else w.unsqueeze(0)
+    assert w3.is_cuda and w3.dtype == torch.float32 and w3.stride(-1) == 1
+    batch = w3.shape[0]
+    nbytes = bimg_bytes(n, k)
+    if img is None:
+        img = torch.empty(batch, nbytes, device=w.device, dtype=torch.uint8)
+    assert img.numel() >= batch * nbytes and img.data_ptr() % 128 == 0
+    _launch("pack_bimg", lambda: load().mphsir_pack_bimg(w3.data_ptr(), w3.stride(1), int(transposed),
+                                                         w3.stride(0) if batch > 1 else 0, img.data_ptr(), batch, n, k,
+                                                         stream_ptr()),
+            lambda: (0.0, 4.0 * batch * n * k + batch * nbytes, "pack_bimg"))
+    return img
+
+
+def gemm(A: View, Bt, Y: View, N: int, *, K: Optional[int] = None, ln=None, bias=None, precision: int = 0,
          epi: int = EPI_BIAS, res1: Optional[View] = None, res2: Optional[View] = None,
          gsrc: Optional[View] = None, gate: Optional[torch.Tensor] = None, H: int = 0, W: int = 0,
          shift: int = 0, rows_per_batch: int = 0, b_batch_stride: int = 0, a_row_mod: int = 0,
          M: Optional[int] = None, row_scale: Optional[torch.Tensor] = None) -> None:
     p = GemmParams()
     p.A, p.lda, p.a_row_mod = A.ptr, A.ld, a_row_mod
-    p.Bt, p.ldb = Bt.data_ptr(), Bt.shape[-1]
-    p.b_batch_stride, p.rows_per_batch = b_batch_stride, rows_per_batch
+    if isinstance(Bt, Weight):
+        wobj = Bt
+        if precision == PREC_FP32_SIMT:
+            Bt = wobj.bt
+        else:
+            Bt = None
+            p.Bimg = wobj.img.data_ptr()
+            if wobj.img.dim() == 2 and wobj.img.shape[0] > 1:
+                p.bimg_batch_bytes = wobj.img.stride(0)
+                b_batch_stride = 1  # marks per-sample weights for the cost model below
+    if Bt is not None:
+        p.Bt, p.ldb = Bt.data_ptr(), Bt.shape[-1]
+        if Bt.dim() == 3 and b_batch_stride == 0:
+            b_batch_stride = Bt.stride(0)
+    p.precision = precision
+    p.b_batch_stride, p.rows_per_batch = (b_batch_stride if Bt is not None else 0), rows_per_batch
     p.Y, p.ldy = Y.ptr, Y.ld
     p.M, p.N, p.K = (A.rows if M is None else M), N, (A.cols if K is None else K)
     if ln is not None:
@@ -228,24 +279,32 @@ def gemm(A: View, Bt: torch.Tensor, Y: View, N: int, *, K: Optional[int] = None,
         m, n, k = p.M, p.N, p.K
         n_out = n // 2 if epi == EPI_GLU else n
         reads = m * k + k * n + sum(m * n for t in (res1, res2, gsrc) if t is not None)
-        tag = "gemm" + ("+ln" if ln is not None else "") + ("", "+res", "+glu", "+spectral")[epi]
+        tag = ("gemm", "gemm_tc3", "gemm_tc1")[precision] + ("+ln" if ln is not None else "") + ("", "+res", "+glu", "+spectral")[epi]
         return 2.0 * m * n * k, 4.0 * (reads + m * n_out), tag
 
     _launch("gemm_fwd", lambda: load().mphsir_gemm_fwd(C.byref(p), stream_ptr()), cost)
 
 
-def conv3x3(X: View, Wt: torch.Tensor, Y_ptr: int, ldy: int, B: int, H: int, W: int, Cin: int, N: int,
-            out_mode: int = CONV_TOKENS, R: Optional[torch.Tensor] = None) -> None:
+def conv3x3(X: View, Wt, Y_ptr: int, ldy: int, B: int, H: int, W: int, Cin: int, N: int,
+            out_mode: int = CONV_TOKENS, R: Optional[torch.Tensor] = None, precision: int = 0) -> None:
     p = ConvParams()
     p.X, p.ldx = X.ptr, X.ld
-    p.Wt, p.ldb = Wt.data_ptr(), Wt.shape[-1]
+    if isinstance(Wt, Weight):
+        if precision == PREC_FP32_SIMT:
+            p.Wt, p.ldb = Wt.bt.data_ptr(), Wt.bt.shape[-1]
+        else:
+            p.Bimg = Wt.img.data_ptr()
+    else:
+        p.Wt, p.ldb = Wt.data_ptr(), Wt.shape[-1]
+    p.precision = precision
     p.Y, p.ldy = Y_ptr, ldy
     p.B, p.H, p.W, p.Cin, p.N = B, H, W, Cin, N
     p.out_mode = out_mode
     p.R = ptr(R)
     m = B * H * W
     _launch("conv3x3_fwd", lambda: load().mphsir_conv3x3_fwd(C.byref(p), stream_ptr()),
-            lambda: (2.0 * m * N * 9 * Cin, 4.0 * (m * Cin + m * N * (2 if R is not None else 1) + 9 * Cin * N), "conv3x3"))
+            lambda: (2.0 * m * N * 9 * Cin, 4.0 * (m * Cin + m * N * (2 if R is not None else 1) + 9 * Cin * N),
+                     ("conv3x3", "conv3x3_tc3", "conv3x3_tc1")[precision]))
 
 
 def window_attn(qkv: View, bias: torch.Tensor, out: View, win_mean: torch.Tensor, B: int, H: int, W: int,

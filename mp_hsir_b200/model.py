@@ -206,14 +206,21 @@ class _TextPrompt(nn.Module):
 class MP_HSIR_Net(nn.Module):
     """B200-native MP-HSIR network.  API == reference ``MP_HSIR_Net`` (net/MP_HSIR.py:763-844) plus one
     optional keyword, ``clip_prompt`` ([task_classes,512] text embeddings; defaults to the cached
-    synthetic tensor because CLIP weights cannot be downloaded here)."""
+    synthetic tensor because CLIP weights cannot be downloaded here) and ``precision``:
+      "fp32"       tcgen05 tensor cores with operands split into bf16 hi+lo (3 MMAs, fp32 accumulate):
+                   fp32-grade products, meets the 1e-4 parity bound (default)
+      "fp32_exact" FFMA everywhere (bit-for-bit fp32 products; slow; numerical baseline)
+      "bf16"       tcgen05 with bf16-rounded operands, fp32 accumulate/activations (1e-2 bound)"""
 
     def __init__(self, in_channel: int = 31, out_channel: int = 31, dim: int = 64,
                  num_blocks: Sequence[int] = (2, 4, 6), window_size: Sequence[int] = (8, 8, 8),
                  task_classes: int = 6, num_refinement_blocks: int = 4, heads: Sequence[int] = (2, 4, 8),
                  ffn_expansion_factor: float = 2.66, bias: bool = False,
-                 clip_prompt: Optional[torch.Tensor] = None):
+                 clip_prompt: Optional[torch.Tensor] = None, precision: str = "fp32"):
         super().__init__()
+        if precision not in ("fp32", "fp32_exact", "bf16"):
+            raise ValueError("precision must be 'fp32' (tcgen05, bf16x3 split operands), 'fp32_exact' (FFMA) or 'bf16'")
+        self.precision = precision
         cfg = NetConfig(in_channel, out_channel, dim, tuple(num_blocks), tuple(window_size), task_classes,
                         num_refinement_blocks, tuple(heads), ffn_expansion_factor, bias)
         self.cfg = cfg
@@ -251,6 +258,13 @@ class MP_HSIR_Net(nn.Module):
         if self._engine is None:
             self._engine = Engine(self)
         return self._engine
+
+    def set_precision(self, precision: str) -> "MP_HSIR_Net":
+        if precision not in ("fp32", "fp32_exact", "bf16"):
+            raise ValueError(precision)
+        self.precision = precision
+        self._engine = None
+        return self
 
     def invalidate_packed_weights(self) -> None:
         """Call after mutating parameters in place if automatic version tracking cannot see it."""

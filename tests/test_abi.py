@@ -53,6 +53,26 @@ def test_library_is_sm100a_only(so_path):
 
 def test_struct_layouts_match_header():
     # 64-bit pointers, natural alignment: sizes computed by hand from include/mphsir.h
-    assert ctypes.sizeof(lib.GemmParams) == 8 + 4 + 4 + 8 + 4 + 4 + 8 + 4 + 4 + 8 + 4 + 4 * 3 + 8 * 3 + 4 + 4 + 8 + 4 + 4 + 8 + 4 + 4 + 8 + 4 + 4 + 8 + 4 * 3 + 4 + 8
-    assert ctypes.sizeof(lib.ConvParams) == 8 + 8 + 8 + 8 + 8 + 8 + 4 * 5 + 4 + 8
-    assert ctypes.sizeof(lib.LocalGateParams) == 8 * 12 + 16
+    # compile a C probe against the real header and compare sizeof / offsetof with the ctypes mirrors
+    import subprocess, tempfile, os
+    src = r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "mphsir.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(mphsir_gemm_params), offsetof(mphsir_gemm_params, row_scale),
+         offsetof(mphsir_gemm_params, Bimg), offsetof(mphsir_gemm_params, bimg_batch_bytes),
+         sizeof(mphsir_conv3x3_params), offsetof(mphsir_conv3x3_params, Bimg), sizeof(mphsir_local_gate_params));
+  return 0;
+}
+"""
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "probe.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "probe")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        got = [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    G, Cv, L = lib.GemmParams, lib.ConvParams, lib.LocalGateParams
+    want = [ctypes.sizeof(G), G.row_scale.offset, G.Bimg.offset, G.bimg_batch_bytes.offset, ctypes.sizeof(Cv),
+            Cv.Bimg.offset, ctypes.sizeof(L)]
+    assert got == want
