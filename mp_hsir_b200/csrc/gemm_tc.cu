@@ -127,9 +127,10 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kThreads = 448;  // warp 0: B loader, warp 1: MMA + TMEM owner, warps 2-5: epilogue, warps 6-13: converters
+constexpr int kThreads = 576;  // warp 0: B loader, warp 1: MMA + TMEM owner, warps 2-9: epilogue, warps 10-17: converters
 constexpr int kConvThreads = 256;
-constexpr int kEpiThreads = 128;
+constexpr int kEpiThreads = 256;
+constexpr int kFirstConvWarp = 10;
 constexpr int SLAB_BYTES = 128 * 128;  // one part (hi or lo) of a 128-row x 64-k slab
 constexpr int MAX_RING = 8;
 
@@ -140,8 +141,9 @@ struct Smem {
   uint32_t tmem_base;
 };
 
-template <bool CONV>
+template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
+  constexpr bool CONV = EPI >= TC_OUT_TOKENS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem* sm = reinterpret_cast<Smem*>(smem_raw);
   const int parts = p.parts;                       // 1 (bf16x1) or 2 (bf16x3)
@@ -255,9 +257,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
         if (stationary) a_it += Ks;
       }
     }
-  } else if (warp < 6) {
-    // =============================== epilogue (warps 2..5) ==================================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+  } else if (warp < kFirstConvWarp) {
+    // =============================== epilogue (warps 2..9) ==================================
+    // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant alternate 32-column chunks.
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     uint32_t acc_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m0, m_end;
@@ -271,105 +275,148 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
       }
       const int m = m0 + quad * 32 + lane;
       const bool row_ok = m < m_end;
+      const int mm = row_ok ? m : m0;
       float scale = 1.f;
-      if (p.row_scale != nullptr && row_ok) scale = __ldg(p.row_scale + m / p.rows_per_batch);
+      if (p.row_scale != nullptr) scale = __ldg(p.row_scale + mm / p.rows_per_batch);
       const float* gate_row = nullptr;
       int ib = 0, iy = 0, ix = 0;
-      if ((p.epi == MPHSIR_EPI_SPECTRAL || p.epi >= TC_OUT_UNSHUFFLE) && row_ok) {
+      if (EPI == MPHSIR_EPI_SPECTRAL || EPI >= TC_OUT_UNSHUFFLE) {
         const int hw = p.H * p.W;
-        ib = m / hw;
-        const int rem = m - ib * hw;
+        ib = mm / hw;
+        const int rem = mm - ib * hw;
         iy = rem / p.W;
         ix = rem - iy * p.W;
-        if (p.epi == MPHSIR_EPI_SPECTRAL) {
+        if (EPI == MPHSIR_EPI_SPECTRAL) {
           int ys = iy - p.shift, xs = ix - p.shift;
           if (ys < 0) ys += p.H;
           if (xs < 0) xs += p.W;
           gate_row = p.gate + (size_t)(ib * (hw >> 6) + (ys >> 3) * (p.W >> 3) + (xs >> 3)) * p.N;
         }
       }
+      float* yrow = p.Y + (size_t)mm * p.ldy;
+      const float* r1row = (EPI == MPHSIR_EPI_RESIDUAL || EPI == MPHSIR_EPI_SPECTRAL) ? p.res1 + (size_t)mm * p.ldr1 : nullptr;
+      const float* r2row = (EPI == MPHSIR_EPI_RESIDUAL && p.res2 != nullptr) ? p.res2 + (size_t)mm * p.ldr2 : nullptr;
+      const float* sarow = (EPI == MPHSIR_EPI_SPECTRAL) ? p.gsrc + (size_t)mm * p.ldg : nullptr;
+
       for (int pass = 0; pass < npass; ++pass, ++acc_it) {
         const int buf = acc_it & 1;
         mbar_wait(smem_u32(&sm->acc_full[buf]), (acc_it >> 1) & 1);
         tc_fence_after();
         const int ncols_pass = min(256, p.Np - pass * 256);
-        for (int c0 = 0; c0 < ncols_pass; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256 + c0, r);
-          if (!row_ok) continue;
+        for (int c0 = half * 32; c0 < ncols_pass; c0 += 64) {
           const int n0 = pass * 256 + c0;
+          // issue every load of this chunk before the first use: one exposed latency per chunk
+          uint32_t r[32];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256 + c0)
+              : "memory");
+          float bias_lane = 0.f;
+          if (p.bias != nullptr && n0 + lane < p.N) bias_lane = __ldg(p.bias + n0 + lane);
+          float4 x1[8], x2[8];
+          if (EPI == MPHSIR_EPI_RESIDUAL || EPI == MPHSIR_EPI_SPECTRAL) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int n = n0 + q * 4;
-            if (n >= p.N) break;
-            float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-            if (p.bias != nullptr) {
-              const float4 bb = ldg4(p.bias + n);
-              v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+            for (int q = 0; q < 8; ++q)
+              x1[q] = (row_ok && n0 + 4 * q < p.N) ? ldg4(r1row + n0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (EPI == MPHSIR_EPI_RESIDUAL) {
+            if (r2row != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                x2[q] = (row_ok && n0 + 4 * q < p.N) ? ldg4(r2row + n0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) x2[q] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            switch (p.epi) {
-              case MPHSIR_EPI_BIAS:
-                *reinterpret_cast<float4*>(p.Y + (size_t)m * p.ldy + n) = v;
-                break;
-              case MPHSIR_EPI_RESIDUAL: {
-                const float4 r1 = ldg4(p.res1 + (size_t)m * p.ldr1 + n);
-                float4 o = make_float4(r1.x + scale * v.x, r1.y + scale * v.y, r1.z + scale * v.z, r1.w + scale * v.w);
-                if (p.res2 != nullptr) {
-                  const float4 r2 = ldg4(p.res2 + (size_t)m * p.ldr2 + n);
-                  o.x += r2.x; o.y += r2.y; o.z += r2.z; o.w += r2.w;
-                }
-                *reinterpret_cast<float4*>(p.Y + (size_t)m * p.ldy + n) = o;
-                break;
-              }
-              case MPHSIR_EPI_GLU: {
-                const float2 o = make_float2(v.x * gelu_erf(v.y), v.z * gelu_erf(v.w));
-                *reinterpret_cast<float2*>(p.Y + (size_t)m * p.ldy + (n >> 1)) = o;
-                break;
-              }
-              case MPHSIR_EPI_SPECTRAL: {
-                const float4 gt = ldg4(gate_row + n);
-                const float4 sa = ldg4(p.gsrc + (size_t)m * p.ldg + n);
-                const float4 r1 = ldg4(p.res1 + (size_t)m * p.ldr1 + n);
-                float4 o;
-                o.x = r1.x + scale * (sa.x * gt.x + v.x);
-                o.y = r1.y + scale * (sa.y * gt.y + v.y);
-                o.z = r1.z + scale * (sa.z * gt.z + v.z);
-                o.w = r1.w + scale * (sa.w * gt.w + v.w);
-                *reinterpret_cast<float4*>(p.Y + (size_t)m * p.ldy + n) = o;
-                break;
-              }
-              case TC_OUT_UNSHUFFLE: {
-                float* dst = p.Y + ((size_t)(ib * (p.H >> 1) + (iy >> 1)) * (p.W >> 1) + (ix >> 1)) * p.ldy +
-                             2 * (iy & 1) + (ix & 1);
-                dst[(n + 0) * 4] = v.x;
-                dst[(n + 1) * 4] = v.y;
-                dst[(n + 2) * 4] = v.z;
-                dst[(n + 3) * 4] = v.w;
-                break;
-              }
-              case TC_OUT_SHUFFLE: {
-                const int cn_total = p.N >> 2;
-                const int qq = n / cn_total, cn = n - qq * cn_total;
-                float* dst = p.Y +
-                             ((size_t)(ib * 2 * p.H + 2 * iy + (qq >> 1)) * (2 * p.W) + 2 * ix + (qq & 1)) * p.ldy + cn;
-                *reinterpret_cast<float4*>(dst) = v;
-                break;
-              }
-              case TC_OUT_NCHW_RES: {
-                const float vv[4] = {v.x, v.y, v.z, v.w};
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float v[32];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int c = n + e;
-                  if (c < p.N) {
-                    const size_t idx = ((size_t)(ib * p.N + c) * p.H + iy) * p.W + ix;
-                    p.Y[idx] = vv[e] + __ldg(p.R + idx);
-                  }
-                }
-                break;
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_lane, j);
+
+          if (EPI == MPHSIR_EPI_BIAS || EPI == TC_OUT_TOKENS) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (row_ok && n0 + 4 * q < p.N)
+                *reinterpret_cast<float4*>(yrow + n0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          } else if (EPI == MPHSIR_EPI_RESIDUAL) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (row_ok && n0 + 4 * q < p.N) {
+                float4 o;
+                o.x = x1[q].x + scale * v[4 * q] + x2[q].x;
+                o.y = x1[q].y + scale * v[4 * q + 1] + x2[q].y;
+                o.z = x1[q].z + scale * v[4 * q + 2] + x2[q].z;
+                o.w = x1[q].w + scale * v[4 * q + 3] + x2[q].w;
+                *reinterpret_cast<float4*>(yrow + n0 + 4 * q) = o;
               }
-              default:
-                break;
+          } else if (EPI == MPHSIR_EPI_GLU) {
+            // packed columns (2j, 2j+1) = (value_j, gate_j)  ->  16 outputs per 32-column chunk
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (row_ok && n0 + 8 * q < p.N) {
+                float4 o;
+                o.x = v[8 * q + 0] * gelu_erf(v[8 * q + 1]);
+                o.y = v[8 * q + 2] * gelu_erf(v[8 * q + 3]);
+                o.z = v[8 * q + 4] * gelu_erf(v[8 * q + 5]);
+                o.w = v[8 * q + 6] * gelu_erf(v[8 * q + 7]);
+                *reinterpret_cast<float4*>(yrow + (n0 >> 1) + 4 * q) = o;
+              }
+          } else if (EPI == MPHSIR_EPI_SPECTRAL) {
+#pragma unroll
+            for (int hq = 0; hq < 2; ++hq) {
+              float4 sa[4], gt[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int n = n0 + 16 * hq + 4 * q;
+                const bool ok = row_ok && n < p.N;
+                sa[q] = ok ? ldg4(sarow + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                gt[q] = ok ? ldg4(gate_row + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int n = n0 + 16 * hq + 4 * q;
+                const int j = 16 * hq + 4 * q;
+                if (row_ok && n < p.N) {
+                  float4 o;
+                  o.x = x1[4 * hq + q].x + scale * (sa[q].x * gt[q].x + v[j]);
+                  o.y = x1[4 * hq + q].y + scale * (sa[q].y * gt[q].y + v[j + 1]);
+                  o.z = x1[4 * hq + q].z + scale * (sa[q].z * gt[q].z + v[j + 2]);
+                  o.w = x1[4 * hq + q].w + scale * (sa[q].w * gt[q].w + v[j + 3]);
+                  *reinterpret_cast<float4*>(yrow + n) = o;
+                }
+              }
+            }
+          } else if (EPI == TC_OUT_UNSHUFFLE) {
+            float* dst = p.Y + ((size_t)(ib * (p.H >> 1) + (iy >> 1)) * (p.W >> 1) + (ix >> 1)) * p.ldy + 2 * (iy & 1) + (ix & 1);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (row_ok && n0 + j < p.N) dst[(size_t)(n0 + j) * 4] = v[j];
+          } else if (EPI == TC_OUT_SHUFFLE) {
+            const int cn_total = p.N >> 2;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int n = n0 + 4 * q;
+              if (row_ok && n < p.N) {
+                const int qq = n / cn_total, cn = n - qq * cn_total;
+                float* dst = p.Y + ((size_t)(ib * 2 * p.H + 2 * iy + (qq >> 1)) * (2 * p.W) + 2 * ix + (qq & 1)) * p.ldy + cn;
+                *reinterpret_cast<float4*>(dst) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              }
+            }
+          } else if (EPI == TC_OUT_NCHW_RES) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int c = n0 + j;
+              if (row_ok && c < p.N) {
+                const size_t idx = ((size_t)(ib * p.N + c) * p.H + iy) * p.W + ix;
+                p.Y[idx] = v[j] + __ldg(p.R + idx);
+              }
             }
           }
         }
@@ -380,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
     }
   } else {
     // =============================== A converters (warps 6..13) =============================
-    const int ct = threadIdx.x - 6 * 32;  // 0..255
+    const int ct = threadIdx.x - kFirstConvWarp * 32;  // 0..255
     const int chunk = ct & 7;             // 8-element (16-byte bf16) chunk inside the 64-k slab
     const int rbase = ct >> 3;            // rows rbase + 32*i, i = 0..3
     uint32_t a_it = 0;
@@ -417,24 +464,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
       // LayerNorm statistics: the 8 lanes that share a row reduce sum / sum-of-squares over K.
       float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f};
       if (!CONV && p.ln_g != nullptr) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+        for (int k = chunk * 4; k < p.Ka; k += 32) {
+          float4 v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = valid[i] ? ldg4(arow[i] + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            s[i] += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            q[i] += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          float s = 0.f, q = 0.f;
-          if (valid[i]) {
-            for (int k = chunk * 4; k < p.Ka; k += 32) {
-              const float4 v = ldg4(arow[i] + k);
-              s += (v.x + v.y) + (v.z + v.w);
-              q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-            }
-          }
 #pragma unroll
           for (int o = 4; o > 0; o >>= 1) {
-            s += __shfl_xor_sync(0xffffffffu, s, o);
-            q += __shfl_xor_sync(0xffffffffu, q, o);
+            s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+            q[i] += __shfl_xor_sync(0xffffffffu, q[i], o);
           }
-          const float mu = s / (float)p.Ka;
+          const float mu = s[i] / (float)p.Ka;
           mean[i] = mu;
-          rstd[i] = rsqrtf(fmaxf(q / (float)p.Ka - mu * mu, 0.f) + 1e-5f);
+          rstd[i] = rsqrtf(fmaxf(q[i] / (float)p.Ka - mu * mu, 0.f) + 1e-5f);
         }
       }
       const int conv_passes = stationary ? 1 : npass;
@@ -551,32 +602,47 @@ __global__ void __launch_bounds__(256) pack_bimg_kernel(const float* __restrict_
 
 static size_t smem_bytes(int na, int nb, int parts) { return 1024 + (size_t)(na + nb) * SLAB_BYTES * parts; }
 
-int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
-  static int sm_count = 0;
+template <int EPI>
+static int launch_epi(const TcArgs& a, size_t smem, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    const int max_smem = 227 * 1024;
-    cudaError_t e1 = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaError_t e2 = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) {
-      set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return MPHSIR_ERR_CUDA;
     }
     configured = true;
   }
-  // ring sizes: bf16x3 slots are 32 KB (A 4 + B 3 = 224 KB); bf16x1 slots are 16 KB (A 8 + B 5 = 208 KB)
-  a.na = a.parts == 2 ? 4 : 8;
-  a.nb = a.parts == 2 ? 3 : 5;
+  gemm_tc_kernel<EPI><<<grid, kThreads, smem, st>>>(a);
+  return check_launch("gemm(tc)");
+}
+
+int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  // ring sizes: bf16x3 slots are 32 KB (A 4 + B 3 = 224 KB); bf16x1 slots are 16 KB (A 4 + B 8 = 192 KB)
+  a.na = 4;
+  a.nb = a.parts == 2 ? 3 : 8;
   const size_t smem = smem_bytes(a.na, a.nb, a.parts);
   const int grid = a.num_tiles < sm_count ? a.num_tiles : sm_count;
-  if (conv)
-    gemm_tc_kernel<true><<<grid, kThreads, smem, st>>>(a);
-  else
-    gemm_tc_kernel<false><<<grid, kThreads, smem, st>>>(a);
-  return check_launch(conv ? "conv3x3(tc)" : "gemm(tc)");
+  if (conv && a.epi == MPHSIR_EPI_BIAS) a.epi = TC_OUT_TOKENS;
+  switch (a.epi) {
+    case MPHSIR_EPI_BIAS: return launch_epi<MPHSIR_EPI_BIAS>(a, smem, grid, st);
+    case MPHSIR_EPI_RESIDUAL: return launch_epi<MPHSIR_EPI_RESIDUAL>(a, smem, grid, st);
+    case MPHSIR_EPI_GLU: return launch_epi<MPHSIR_EPI_GLU>(a, smem, grid, st);
+    case MPHSIR_EPI_SPECTRAL: return launch_epi<MPHSIR_EPI_SPECTRAL>(a, smem, grid, st);
+    case TC_OUT_TOKENS: return launch_epi<TC_OUT_TOKENS>(a, smem, grid, st);
+    case TC_OUT_UNSHUFFLE: return launch_epi<TC_OUT_UNSHUFFLE>(a, smem, grid, st);
+    case TC_OUT_SHUFFLE: return launch_epi<TC_OUT_SHUFFLE>(a, smem, grid, st);
+    case TC_OUT_NCHW_RES: return launch_epi<TC_OUT_NCHW_RES>(a, smem, grid, st);
+    default:
+      set_error("gemm_tc: unknown epilogue %d", a.epi);
+      return MPHSIR_ERR_INVALID;
+  }
 }
 
 }  // namespace tc

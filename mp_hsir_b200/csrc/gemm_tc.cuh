@@ -6,7 +6,7 @@
 namespace mphsir {
 namespace tc {
 
-enum { TC_OUT_UNSHUFFLE = 10, TC_OUT_SHUFFLE = 11, TC_OUT_NCHW_RES = 12 };
+enum { TC_OUT_TOKENS = 9, TC_OUT_UNSHUFFLE = 10, TC_OUT_SHUFFLE = 11, TC_OUT_NCHW_RES = 12 };  // conv epilogues
 
 // Byte offset of the 16-byte chunk (8 bf16: k = s*64 + c*8 .. +7) of weight row n in the packed image:
 //   [part (hi, lo)][k-slab s][row n] x 128 bytes, chunks XOR-swizzled by (n & 7) — i.e. exactly the
