@@ -129,9 +129,14 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 // ------------------------------------------------------------------------------------------------
 constexpr int kThreads = 576;  // warp 0: B loader, warp 1: MMA + TMEM owner, warps 2-9: epilogue, warps 10-17: converters
 constexpr int kConvThreads = 256;
-constexpr int kEpiThreads = 256;
+constexpr int kEpiWarps = 8;
 constexpr int kFirstConvWarp = 10;
-constexpr int SLAB_BYTES = 128 * 128;  // one part (hi or lo) of a 128-row x 64-k slab
+constexpr int SLAB_BYTES = 128 * 128;   // one part (hi or lo) of a 128-row x 64-k A slab
+constexpr int BN = 64;                  // columns per B block / per MMA instruction
+constexpr int BBLK_BYTES = BN * 128;    // one part of a 64-row x 64-k B block
+constexpr int PASS_COLS = 256;          // accumulator columns per pass (x2 buffers = 512 TMEM columns)
+constexpr int STG_LD = 36;              // staging row stride in floats (16-byte aligned, conflict-free)
+constexpr int STG_FLOATS = 32 * STG_LD;
 constexpr int MAX_RING = 8;
 
 struct Smem {
@@ -141,21 +146,36 @@ struct Smem {
   uint32_t tmem_base;
 };
 
+__device__ __forceinline__ void tile_rows(const TcArgs& p, int tile, int& m0, int& m_end) {
+  if (p.tiles_per_batch > 0) {
+    const int b = tile / p.tiles_per_batch;
+    m0 = b * p.rows_per_batch + (tile - b * p.tiles_per_batch) * 128;
+    m_end = (b + 1) * p.rows_per_batch;
+  } else {
+    m0 = tile * 128;
+    m_end = p.M;
+  }
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
   constexpr bool CONV = EPI >= TC_OUT_TOKENS;
+  // NCHW / pixel-unshuffle stores are already coalesced (or hopeless) in the row-per-thread TMEM mapping
+  constexpr bool DIRECT = (EPI == TC_OUT_NCHW_RES || EPI == TC_OUT_UNSHUFFLE);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem* sm = reinterpret_cast<Smem*>(smem_raw);
   const int parts = p.parts;                       // 1 (bf16x1) or 2 (bf16x3)
   const int a_slot_bytes = SLAB_BYTES * parts;
-  const int b_slot_bytes = SLAB_BYTES * parts;
+  const int b_slot_bytes = BBLK_BYTES * parts;
   uint8_t* a_ring = smem_raw + 1024;
   uint8_t* b_ring = a_ring + (size_t)p.na * a_slot_bytes;
+  float* staging = reinterpret_cast<float*>(b_ring + (size_t)p.nb * b_slot_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Ks = p.ks;
-  const int NT = (p.Np + 127) >> 7;                // 128-column n-tiles
-  const int npass = (NT + 1) >> 1;
+  const int NT = (p.Np + BN - 1) / BN;             // 64-column n-tiles
+  constexpr int TPP = PASS_COLS / BN;              // n-tiles per pass
+  const int npass = (NT + TPP - 1) / TPP;
   const bool stationary = Ks <= p.na;
 
   if (threadIdx.x == 0) {
@@ -167,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&sm->acc_full[i]), 1);
-      mbar_init(smem_u32(&sm->acc_empty[i]), kEpiThreads / 32);
+      mbar_init(smem_u32(&sm->acc_empty[i]), kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -176,7 +196,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sm->tmem_base;
-
   const int num_tiles = p.num_tiles;
 
   if (warp == 0) {
@@ -188,17 +207,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
         if (p.tiles_per_batch > 0) bimg += (size_t)(tile / p.tiles_per_batch) * p.b_batch_bytes;
         for (int pass = 0; pass < npass; ++pass) {
           for (int s = 0; s < Ks; ++s) {
-            for (int j = 2 * pass; j < min(NT, 2 * pass + 2); ++j, ++it) {
+            for (int j = TPP * pass; j < min(NT, TPP * pass + TPP); ++j, ++it) {
               const int slot = it % p.nb;
-              const uint32_t par = (it / p.nb) & 1;
-              mbar_wait(smem_u32(&sm->b_empty[slot]), par ^ 1);
-              const int rows = min(128, p.Np - j * 128);
+              mbar_wait(smem_u32(&sm->b_empty[slot]), ((it / p.nb) & 1) ^ 1);
+              const int rows = min(BN, p.Np - j * BN);
               const uint32_t bytes = rows * 128;
               const uint32_t full = smem_u32(&sm->b_full[slot]);
               mbar_expect_tx(full, bytes * parts);
               for (int part = 0; part < parts; ++part) {
-                const uint8_t* src = bimg + ((size_t)(part * Ks + s) * p.Np + j * 128) * 128;
-                bulk_g2s(smem_u32(b_ring + (size_t)slot * b_slot_bytes + part * SLAB_BYTES), src, bytes, full);
+                const uint8_t* src = bimg + ((size_t)(part * Ks + s) * p.Np + j * BN) * 128;
+                bulk_g2s(smem_u32(b_ring + (size_t)slot * b_slot_bytes + part * BBLK_BYTES), src, bytes, full);
               }
             }
           }
@@ -226,14 +244,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
             }
             tc_fence_after();
             const uint32_t a_addr = smem_u32(a_ring + (size_t)a_slot * a_slot_bytes);
-            for (int j = 2 * pass; j < min(NT, 2 * pass + 2); ++j, ++b_it) {
+            for (int j = TPP * pass; j < min(NT, TPP * pass + TPP); ++j, ++b_it) {
               const int b_slot = b_it % p.nb;
               mbar_wait(smem_u32(&sm->b_full[b_slot]), (b_it / p.nb) & 1);
               tc_fence_after();
               const uint32_t b_addr = smem_u32(b_ring + (size_t)b_slot * b_slot_bytes);
-              const int ncols = min(128, p.Np - j * 128);
+              const int ncols = min(BN, p.Np - j * BN);
               const uint32_t idesc = make_idesc(ncols);
-              const uint32_t d_addr = tmem_base + buf * 256 + (j - 2 * pass) * 128;
+              const uint32_t d_addr = tmem_base + buf * PASS_COLS + (j - TPP * pass) * BN;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint64_t ah = make_desc(a_addr + k * 32);
@@ -241,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
                 umma_bf16(d_addr, ah, bh, idesc, (s | k) != 0);
                 if (parts == 2) {
                   const uint64_t al = make_desc(a_addr + SLAB_BYTES + k * 32);
-                  const uint64_t bl = make_desc(b_addr + SLAB_BYTES + k * 32);
+                  const uint64_t bl = make_desc(b_addr + BBLK_BYTES + k * 32);
                   umma_bf16(d_addr, ah, bl, idesc, 1);
                   umma_bf16(d_addr, al, bh, idesc, 1);
                 }
@@ -260,52 +278,60 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
   } else if (warp < kFirstConvWarp) {
     // =============================== epilogue (warps 2..9) ==================================
     // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant alternate 32-column chunks.
+    // Staged path: the warp's 32x32 fp32 block goes TMEM -> registers (row per thread) -> padded smem ->
+    // registers in a (4 rows x 8 float4) mapping, so every global access is a full 128-byte line segment.
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
+    float* stg = staging + (warp - 2) * STG_FLOATS;
+    const int c4 = lane & 7, rsub = lane >> 3;
     uint32_t acc_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m0, m_end;
-      if (p.tiles_per_batch > 0) {
-        const int b = tile / p.tiles_per_batch;
-        m0 = b * p.rows_per_batch + (tile - b * p.tiles_per_batch) * 128;
-        m_end = (b + 1) * p.rows_per_batch;
-      } else {
-        m0 = tile * 128;
-        m_end = p.M;
-      }
-      const int m = m0 + quad * 32 + lane;
-      const bool row_ok = m < m_end;
-      const int mm = row_ok ? m : m0;
-      float scale = 1.f;
-      if (p.row_scale != nullptr) scale = __ldg(p.row_scale + mm / p.rows_per_batch);
-      const float* gate_row = nullptr;
+      tile_rows(p, tile, m0, m_end);
+      const int mrow0 = m0 + quad * 32;
+      // ---- per-row state ----
+      // DIRECT: one row per thread (row = lane).  Staged: 8 rows per thread (row = it*4 + rsub).
+      float scale_d = 1.f;
       int ib = 0, iy = 0, ix = 0;
-      if (EPI == MPHSIR_EPI_SPECTRAL || EPI >= TC_OUT_UNSHUFFLE) {
+      const bool row_ok_d = mrow0 + lane < m_end;
+      if (DIRECT) {
+        const int mm = row_ok_d ? mrow0 + lane : m0;
         const int hw = p.H * p.W;
         ib = mm / hw;
         const int rem = mm - ib * hw;
         iy = rem / p.W;
         ix = rem - iy * p.W;
-        if (EPI == MPHSIR_EPI_SPECTRAL) {
-          int ys = iy - p.shift, xs = ix - p.shift;
-          if (ys < 0) ys += p.H;
-          if (xs < 0) xs += p.W;
-          gate_row = p.gate + (size_t)(ib * (hw >> 6) + (ys >> 3) * (p.W >> 3) + (xs >> 3)) * p.N;
+      }
+      uint32_t win[8];
+      float scl[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        win[it] = 0;
+        scl[it] = 1.f;
+        const int m = mrow0 + it * 4 + rsub;
+        if (!DIRECT && m < m_end) {
+          if (p.row_scale != nullptr) scl[it] = __ldg(p.row_scale + m / p.rows_per_batch);
+          if (EPI == MPHSIR_EPI_SPECTRAL) {
+            const int hw = p.H * p.W;
+            const int b = m / hw;
+            const int rem = m - b * hw;
+            const int y = rem / p.W, x = rem - y * p.W;
+            int ys = y - p.shift, xs = x - p.shift;
+            if (ys < 0) ys += p.H;
+            if (xs < 0) xs += p.W;
+            win[it] = b * (hw >> 6) + (ys >> 3) * (p.W >> 3) + (xs >> 3);
+          }
         }
       }
-      float* yrow = p.Y + (size_t)mm * p.ldy;
-      const float* r1row = (EPI == MPHSIR_EPI_RESIDUAL || EPI == MPHSIR_EPI_SPECTRAL) ? p.res1 + (size_t)mm * p.ldr1 : nullptr;
-      const float* r2row = (EPI == MPHSIR_EPI_RESIDUAL && p.res2 != nullptr) ? p.res2 + (size_t)mm * p.ldr2 : nullptr;
-      const float* sarow = (EPI == MPHSIR_EPI_SPECTRAL) ? p.gsrc + (size_t)mm * p.ldg : nullptr;
+      (void)scale_d;
 
       for (int pass = 0; pass < npass; ++pass, ++acc_it) {
         const int buf = acc_it & 1;
         mbar_wait(smem_u32(&sm->acc_full[buf]), (acc_it >> 1) & 1);
         tc_fence_after();
-        const int ncols_pass = min(256, p.Np - pass * 256);
+        const int ncols_pass = min(PASS_COLS, p.Np - pass * PASS_COLS);
         for (int c0 = half * 32; c0 < ncols_pass; c0 += 64) {
-          const int n0 = pass * 256 + c0;
-          // issue every load of this chunk before the first use: one exposed latency per chunk
+          const int n0 = pass * PASS_COLS + c0;
           uint32_t r[32];
           asm volatile(
               "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -315,107 +341,96 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
                 "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
                 "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-              : "r"(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256 + c0)
+              : "r"(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * PASS_COLS + c0)
               : "memory");
-          float bias_lane = 0.f;
-          if (p.bias != nullptr && n0 + lane < p.N) bias_lane = __ldg(p.bias + n0 + lane);
-          float4 x1[8], x2[8];
-          if (EPI == MPHSIR_EPI_RESIDUAL || EPI == MPHSIR_EPI_SPECTRAL) {
+          if (DIRECT) {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (EPI == TC_OUT_UNSHUFFLE) {
+              float* dst = p.Y + ((size_t)(ib * (p.H >> 1) + (iy >> 1)) * (p.W >> 1) + (ix >> 1)) * p.ldy + 2 * (iy & 1) + (ix & 1);
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-              x1[q] = (row_ok && n0 + 4 * q < p.N) ? ldg4(r1row + n0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          if (EPI == MPHSIR_EPI_RESIDUAL) {
-            if (r2row != nullptr) {
+              for (int j = 0; j < 32; ++j)
+                if (row_ok_d && n0 + j < p.N) dst[(size_t)(n0 + j) * 4] = __uint_as_float(r[j]);
+            } else {  // TC_OUT_NCHW_RES: lanes are 32 consecutive pixels of one channel -> 128-byte lines
 #pragma unroll
-              for (int q = 0; q < 8; ++q)
-                x2[q] = (row_ok && n0 + 4 * q < p.N) ? ldg4(r2row + n0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) x2[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_lane, j);
-
-          if (EPI == MPHSIR_EPI_BIAS || EPI == TC_OUT_TOKENS) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (row_ok && n0 + 4 * q < p.N)
-                *reinterpret_cast<float4*>(yrow + n0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          } else if (EPI == MPHSIR_EPI_RESIDUAL) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (row_ok && n0 + 4 * q < p.N) {
-                float4 o;
-                o.x = x1[q].x + scale * v[4 * q] + x2[q].x;
-                o.y = x1[q].y + scale * v[4 * q + 1] + x2[q].y;
-                o.z = x1[q].z + scale * v[4 * q + 2] + x2[q].z;
-                o.w = x1[q].w + scale * v[4 * q + 3] + x2[q].w;
-                *reinterpret_cast<float4*>(yrow + n0 + 4 * q) = o;
-              }
-          } else if (EPI == MPHSIR_EPI_GLU) {
-            // packed columns (2j, 2j+1) = (value_j, gate_j)  ->  16 outputs per 32-column chunk
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (row_ok && n0 + 8 * q < p.N) {
-                float4 o;
-                o.x = v[8 * q + 0] * gelu_erf(v[8 * q + 1]);
-                o.y = v[8 * q + 2] * gelu_erf(v[8 * q + 3]);
-                o.z = v[8 * q + 4] * gelu_erf(v[8 * q + 5]);
-                o.w = v[8 * q + 6] * gelu_erf(v[8 * q + 7]);
-                *reinterpret_cast<float4*>(yrow + (n0 >> 1) + 4 * q) = o;
-              }
-          } else if (EPI == MPHSIR_EPI_SPECTRAL) {
-#pragma unroll
-            for (int hq = 0; hq < 2; ++hq) {
-              float4 sa[4], gt[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int n = n0 + 16 * hq + 4 * q;
-                const bool ok = row_ok && n < p.N;
-                sa[q] = ok ? ldg4(sarow + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-                gt[q] = ok ? ldg4(gate_row + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int n = n0 + 16 * hq + 4 * q;
-                const int j = 16 * hq + 4 * q;
-                if (row_ok && n < p.N) {
-                  float4 o;
-                  o.x = x1[4 * hq + q].x + scale * (sa[q].x * gt[q].x + v[j]);
-                  o.y = x1[4 * hq + q].y + scale * (sa[q].y * gt[q].y + v[j + 1]);
-                  o.z = x1[4 * hq + q].z + scale * (sa[q].z * gt[q].z + v[j + 2]);
-                  o.w = x1[4 * hq + q].w + scale * (sa[q].w * gt[q].w + v[j + 3]);
-                  *reinterpret_cast<float4*>(yrow + n) = o;
+              for (int j = 0; j < 32; ++j) {
+                const int c = n0 + j;
+                if (row_ok_d && c < p.N) {
+                  const size_t idx = ((size_t)(ib * p.N + c) * p.H + iy) * p.W + ix;
+                  p.Y[idx] = __uint_as_float(r[j]) + __ldg(p.R + idx);
                 }
               }
             }
-          } else if (EPI == TC_OUT_UNSHUFFLE) {
-            float* dst = p.Y + ((size_t)(ib * (p.H >> 1) + (iy >> 1)) * (p.W >> 1) + (ix >> 1)) * p.ldy + 2 * (iy & 1) + (ix & 1);
+            continue;
+          }
+          // ---- staged path ----
+          const int n = n0 + 4 * c4;          // this thread's 4 output columns (packed order)
+          const bool col_ok = n < p.N;
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr && col_ok) bias4 = ldg4(p.bias + n);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          __syncwarp();  // previous chunk's smem reads are done
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (row_ok && n0 + j < p.N) dst[(size_t)(n0 + j) * 4] = v[j];
-          } else if (EPI == TC_OUT_SHUFFLE) {
-            const int cn_total = p.N >> 2;
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(stg + lane * STG_LD + 4 * q) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+          __syncwarp();
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int n = n0 + 4 * q;
-              if (row_ok && n < p.N) {
-                const int qq = n / cn_total, cn = n - qq * cn_total;
-                float* dst = p.Y + ((size_t)(ib * 2 * p.H + 2 * iy + (qq >> 1)) * (2 * p.W) + 2 * ix + (qq & 1)) * p.ldy + cn;
-                *reinterpret_cast<float4*>(dst) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          for (int hb = 0; hb < 2; ++hb) {  // two batches of 4 rows-groups: loads first, then math + stores
+            float4 acc[4], x1[4], x2[4], x3[4];
+            bool ok[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int it = hb * 4 + i;
+              const int row = it * 4 + rsub;
+              const int m = mrow0 + row;
+              ok[i] = col_ok && m < m_end;
+              acc[i] = *reinterpret_cast<const float4*>(stg + row * STG_LD + 4 * c4);
+              x1[i] = x2[i] = x3[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ok[i]) {
+                if (EPI == MPHSIR_EPI_RESIDUAL || EPI == MPHSIR_EPI_SPECTRAL) x1[i] = ldg4(p.res1 + (size_t)m * p.ldr1 + n);
+                if (EPI == MPHSIR_EPI_RESIDUAL && p.res2 != nullptr) x2[i] = ldg4(p.res2 + (size_t)m * p.ldr2 + n);
+                if (EPI == MPHSIR_EPI_SPECTRAL) {
+                  x2[i] = ldg4(p.gsrc + (size_t)m * p.ldg + n);
+                  x3[i] = ldg4(p.gate + (size_t)win[it] * p.N + n);
+                }
               }
             }
-          } else if (EPI == TC_OUT_NCHW_RES) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int c = n0 + j;
-              if (row_ok && c < p.N) {
-                const size_t idx = ((size_t)(ib * p.N + c) * p.H + iy) * p.W + ix;
-                p.Y[idx] = v[j] + __ldg(p.R + idx);
+            for (int i = 0; i < 4; ++i) {
+              if (!ok[i]) continue;
+              const int it = hb * 4 + i;
+              const int m = mrow0 + it * 4 + rsub;
+              float4 v = make_float4(acc[i].x + bias4.x, acc[i].y + bias4.y, acc[i].z + bias4.z, acc[i].w + bias4.w);
+              if (EPI == MPHSIR_EPI_BIAS || EPI == TC_OUT_TOKENS) {
+                *reinterpret_cast<float4*>(p.Y + (size_t)m * p.ldy + n) = v;
+              } else if (EPI == MPHSIR_EPI_RESIDUAL) {
+                const float sc = scl[it];
+                float4 o;
+                o.x = x1[i].x + sc * v.x + x2[i].x;
+                o.y = x1[i].y + sc * v.y + x2[i].y;
+                o.z = x1[i].z + sc * v.z + x2[i].z;
+                o.w = x1[i].w + sc * v.w + x2[i].w;
+                *reinterpret_cast<float4*>(p.Y + (size_t)m * p.ldy + n) = o;
+              } else if (EPI == MPHSIR_EPI_GLU) {
+                // packed columns (2j, 2j+1) = (value_j, gate_j)
+                const float2 o = make_float2(v.x * gelu_erf(v.y), v.z * gelu_erf(v.w));
+                *reinterpret_cast<float2*>(p.Y + (size_t)m * p.ldy + (n >> 1)) = o;
+              } else if (EPI == MPHSIR_EPI_SPECTRAL) {
+                const float sc = scl[it];
+                float4 o;
+                o.x = x1[i].x + sc * (x2[i].x * x3[i].x + v.x);
+                o.y = x1[i].y + sc * (x2[i].y * x3[i].y + v.y);
+                o.z = x1[i].z + sc * (x2[i].z * x3[i].z + v.z);
+                o.w = x1[i].w + sc * (x2[i].w * x3[i].w + v.w);
+                *reinterpret_cast<float4*>(p.Y + (size_t)m * p.ldy + n) = o;
+              } else if (EPI == TC_OUT_SHUFFLE) {
+                const int hw = p.H * p.W;
+                const int b = m / hw;
+                const int rem = m - b * hw;
+                const int y = rem / p.W, x = rem - y * p.W;
+                const int cn_total = p.N >> 2;
+                const int qq = n / cn_total, cn = n - qq * cn_total;
+                float* dst = p.Y + ((size_t)(b * 2 * p.H + 2 * y + (qq >> 1)) * (2 * p.W) + 2 * x + (qq & 1)) * p.ldy + cn;
+                *reinterpret_cast<float4*>(dst) = v;
               }
             }
           }
@@ -426,21 +441,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
       }
     }
   } else {
-    // =============================== A converters (warps 6..13) =============================
+    // =============================== A converters (warps 10..17) ============================
     const int ct = threadIdx.x - kFirstConvWarp * 32;  // 0..255
     const int chunk = ct & 7;             // 8-element (16-byte bf16) chunk inside the 64-k slab
     const int rbase = ct >> 3;            // rows rbase + 32*i, i = 0..3
     uint32_t a_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m0, m_end;
-      if (p.tiles_per_batch > 0) {
-        const int b = tile / p.tiles_per_batch;
-        m0 = b * p.rows_per_batch + (tile - b * p.tiles_per_batch) * 128;
-        m_end = (b + 1) * p.rows_per_batch;
-      } else {
-        m0 = tile * 128;
-        m_end = p.M;
-      }
+      tile_rows(p, tile, m0, m_end);
       bool valid[4];
       const float* arow[4];
       int pb[4], py[4], px[4];
@@ -600,7 +608,9 @@ __global__ void __launch_bounds__(256) pack_bimg_kernel(const float* __restrict_
   }
 }
 
-static size_t smem_bytes(int na, int nb, int parts) { return 1024 + (size_t)(na + nb) * SLAB_BYTES * parts; }
+static size_t smem_bytes(int na, int nb, int parts) {
+  return 1024 + (size_t)na * SLAB_BYTES * parts + (size_t)nb * BBLK_BYTES * parts + (size_t)kEpiWarps * STG_FLOATS * sizeof(float);
+}
 
 template <int EPI>
 static int launch_epi(const TcArgs& a, size_t smem, int grid, cudaStream_t st) {
@@ -624,9 +634,10 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
   }
-  // ring sizes: bf16x3 slots are 32 KB (A 4 + B 3 = 224 KB); bf16x1 slots are 16 KB (A 4 + B 8 = 192 KB)
-  a.na = 4;
-  a.nb = a.parts == 2 ? 3 : 8;
+  // shared-memory plan (227 KB): 1 KB barriers + A ring + B ring + 36 KB epilogue staging
+  //   bf16x3: A 4 x 32 KB, B 3 x 16 KB (213 KB)      bf16x1: A 8 x 16 KB, B 6 x 8 KB (213 KB)
+  a.na = a.parts == 2 ? 4 : 8;
+  a.nb = a.parts == 2 ? 3 : 6;
   const size_t smem = smem_bytes(a.na, a.nb, a.parts);
   const int grid = a.num_tiles < sm_count ? a.num_tiles : sm_count;
   if (conv && a.epi == MPHSIR_EPI_BIAS) a.epi = TC_OUT_TOKENS;
