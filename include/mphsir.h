@@ -201,7 +201,8 @@ MPHSIR_API int mphsir_gram_partial_fwd(const float* q, int ldq, int q_shared, co
                             int k_shared, float* partial, int B, int HW, int heads, int c,
                             void* stream);
 MPHSIR_API int mphsir_gram_softmax_fwd(const float* partial, int n_chunks, const float* temperature,
-                            float* attn /* [B,heads,c,c] */, int B, int heads, int c, void* stream);
+                            float* attn /* [B,heads,c,c] */, float* scratch /* [B*heads*(c*c+2c)] */, int B,
+                            int heads, int c, void* stream);
 MPHSIR_API int mphsir_spectral_fold_fwd(const float* attn, const float* WoutT /* [C,C] in x out */,
                              float* Mt /* [B, Cp, ldm] */, int ldm, long long m_batch_stride, int B,
                              int heads, int c, void* stream);

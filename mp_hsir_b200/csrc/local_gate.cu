@@ -10,8 +10,8 @@
 //   A   = softmax_j(q_i k_j r^-0.5) ; o_i = sum_j A_ij v_j     (:146-149, outer-product attention)
 //   g   = upT^T (p2T^T o + p2b)                (:151-152)
 //
-// One CTA (128 threads) handles WPB windows; every weight is read "in x out" so that thread o
-// reads W[k][o] coalesced.  < 20 kFLOP per window: latency-, not throughput-, bound.
+// One CTA (128 threads) handles WPB = 8 windows so each weight element is fetched once per 8 windows;
+// every weight is read "in x out" so that thread o reads W[k][o] coalesced.
 #include "common.cuh"
 
 namespace mphsir {
@@ -19,94 +19,143 @@ namespace mphsir {
 constexpr int LG_THREADS = 128;
 constexpr int PLEN = 128;
 constexpr int RMAX = 32;
+constexpr int WPB = 8;  // windows per CTA: every weight element is fetched once per 8 windows
 
 __global__ void __launch_bounds__(LG_THREADS) local_gate_kernel(const mphsir_local_gate_params p) {
   extern __shared__ float sm[];
   const int C = p.C, r = p.r;
-  float* cm = sm;            // [C] core mean
-  float* m = cm + C;         // [C]
-  float* pw = m + C;         // [128]
-  float* dn = pw + PLEN;     // [RMAX]
-  float* sp = dn + RMAX;
-  float* q = sp + RMAX;
-  float* kv = q + RMAX;      // [2*RMAX]
-  float* o = kv + 2 * RMAX;
-  float* u = o + RMAX;
-  float* red = u + RMAX;     // [8]
+  float* cm = sm;                 // [WPB][C] core mean
+  float* m = cm + WPB * C;        // [WPB][C]
+  float* pw = m + WPB * C;        // [WPB][128]
+  float* dn = pw + WPB * PLEN;    // [WPB][RMAX]
+  float* sp = dn + WPB * RMAX;
+  float* q = sp + WPB * RMAX;
+  float* kv = q + WPB * RMAX;     // [WPB][2*RMAX]
+  float* o = kv + WPB * 2 * RMAX;
+  float* u = o + WPB * RMAX;
+  float* red = u + WPB * RMAX;    // [WPB][8]
   const int tid = threadIdx.x;
-  const int win = blockIdx.x;
-  if (win >= p.B_) return;
+  const int w0 = blockIdx.x * WPB;
+  const int nw = min(WPB, p.B_ - w0);
 
-  for (int c = tid; c < C; c += LG_THREADS) cm[c] = __ldg(p.core_mean + (long long)win * C + c);
+  for (int e = tid; e < WPB * C; e += LG_THREADS) {
+    const int w = e / C, c = e - w * C;
+    cm[e] = (w < nw) ? __ldg(p.core_mean + (long long)(w0 + w) * C + c) : 0.f;
+  }
   __syncthreads();
+  // m = projT^T cm + projb
   for (int c = tid; c < C; c += LG_THREADS) {
-    float a = __ldg(p.projb + c);
-    for (int k = 0; k < C; ++k) a = fmaf(cm[k], __ldg(p.projT + (long long)k * C + c), a);
-    m[c] = a;
+    float a[WPB];
+    const float b0 = __ldg(p.projb + c);
+#pragma unroll
+    for (int w = 0; w < WPB; ++w) a[w] = b0;
+    for (int k = 0; k < C; ++k) {
+      const float wv = __ldg(p.projT + (long long)k * C + c);
+#pragma unroll
+      for (int w = 0; w < WPB; ++w) a[w] = fmaf(cm[w * C + k], wv, a[w]);
+    }
+#pragma unroll
+    for (int w = 0; w < WPB; ++w) m[w * C + c] = a[w];
   }
   __syncthreads();
   // prompt logits (thread == prompt index) and the low-rank projection
-  float logit = 0.f;
-  for (int k = 0; k < C; ++k) logit = fmaf(m[k], __ldg(p.promptT + k * PLEN + tid), logit);
-  if (tid < r) {
-    float a = 0.f;
-    for (int k = 0; k < C; ++k) a = fmaf(m[k], __ldg(p.downT + k * r + tid), a);
-    dn[tid] = a;
+  float logit[WPB];
+#pragma unroll
+  for (int w = 0; w < WPB; ++w) logit[w] = 0.f;
+  for (int k = 0; k < C; ++k) {
+    const float wv = __ldg(p.promptT + k * PLEN + tid);
+#pragma unroll
+    for (int w = 0; w < WPB; ++w) logit[w] = fmaf(m[w * C + k], wv, logit[w]);
   }
-  // softmax over the 128 logits (4 warps)
-  float mx = warp_max(logit);
-  if ((tid & 31) == 0) red[tid >> 5] = mx;
-  __syncthreads();
-  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-  const float e = expf(logit - mx);
-  float s = warp_sum(e);
-  if ((tid & 31) == 0) red[4 + (tid >> 5)] = s;
-  __syncthreads();
-  s = (red[4] + red[5]) + (red[6] + red[7]);
-  pw[tid] = e / s;
-  __syncthreads();
   if (tid < r) {
-    float a = 0.f;
-    for (int k = 0; k < PLEN; ++k) a = fmaf(pw[k], __ldg(p.param + k * r + tid), a);
-    sp[tid] = a;
+    float a[WPB];
+#pragma unroll
+    for (int w = 0; w < WPB; ++w) a[w] = 0.f;
+    for (int k = 0; k < C; ++k) {
+      const float wv = __ldg(p.downT + k * r + tid);
+#pragma unroll
+      for (int w = 0; w < WPB; ++w) a[w] = fmaf(m[w * C + k], wv, a[w]);
+    }
+#pragma unroll
+    for (int w = 0; w < WPB; ++w) dn[w * RMAX + tid] = a[w];
   }
-  __syncthreads();
-  if (tid < r) {
-    float a = 0.f;
-    for (int k = 0; k < r; ++k) a = fmaf(sp[k], __ldg(p.qT + k * r + tid), a);
-    q[tid] = a;
-  }
-  if (tid >= 32 && tid < 32 + 2 * r) {
-    const int j = tid - 32;
-    float a = 0.f;
-    for (int k = 0; k < r; ++k) a = fmaf(dn[k], __ldg(p.kvT + k * 2 * r + j), a);
-    kv[j] = a;
+  // softmax over the 128 logits of each window (4 warps)
+#pragma unroll
+  for (int w = 0; w < WPB; ++w) {
+    const float mx = warp_max(logit[w]);
+    if ((tid & 31) == 0) red[w * 8 + (tid >> 5)] = mx;
   }
   __syncthreads();
-  if (tid < r) {
-    const float sc = rsqrtf((float)r);
-    const float qi = q[tid] * sc;
+  float ex[WPB];
+#pragma unroll
+  for (int w = 0; w < WPB; ++w) {
+    const float mx = fmaxf(fmaxf(red[w * 8 + 0], red[w * 8 + 1]), fmaxf(red[w * 8 + 2], red[w * 8 + 3]));
+    ex[w] = expf(logit[w] - mx);
+    const float s = warp_sum(ex[w]);
+    if ((tid & 31) == 0) red[w * 8 + 4 + (tid >> 5)] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < WPB; ++w) {
+    const float s = (red[w * 8 + 4] + red[w * 8 + 5]) + (red[w * 8 + 6] + red[w * 8 + 7]);
+    pw[w * PLEN + tid] = ex[w] / s;
+  }
+  __syncthreads();
+  // the remaining r-sized steps: thread -> (window, index)
+  for (int e = tid; e < WPB * r; e += LG_THREADS) {
+    const int w = e / r, i = e - w * r;
+    float a = 0.f;
+    for (int k = 0; k < PLEN; ++k) a = fmaf(pw[w * PLEN + k], __ldg(p.param + k * r + i), a);
+    sp[w * RMAX + i] = a;
+  }
+  __syncthreads();
+  for (int e = tid; e < WPB * 3 * r; e += LG_THREADS) {
+    const int w = e / (3 * r), j = e - w * 3 * r;
+    float a = 0.f;
+    if (j < r) {
+      for (int k = 0; k < r; ++k) a = fmaf(sp[w * RMAX + k], __ldg(p.qT + k * r + j), a);
+      q[w * RMAX + j] = a;
+    } else {
+      const int jj = j - r;
+      for (int k = 0; k < r; ++k) a = fmaf(dn[w * RMAX + k], __ldg(p.kvT + k * 2 * r + jj), a);
+      kv[w * 2 * RMAX + jj] = a;
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < WPB * r; e += LG_THREADS) {
+    const int w = e / r, i = e - w * r;
+    const float* kvw = kv + w * 2 * RMAX;
+    const float qi = q[w * RMAX + i] * rsqrtf((float)r);
     float mxl = -INFINITY;
-    for (int j = 0; j < r; ++j) mxl = fmaxf(mxl, qi * kv[j]);
+    for (int j = 0; j < r; ++j) mxl = fmaxf(mxl, qi * kvw[j]);
     float den = 0.f, num = 0.f;
     for (int j = 0; j < r; ++j) {
-      const float w = expf(qi * kv[j] - mxl);
-      den += w;
-      num = fmaf(w, kv[r + j], num);
+      const float wgt = expf(qi * kvw[j] - mxl);
+      den += wgt;
+      num = fmaf(wgt, kvw[r + j], num);
     }
-    o[tid] = num / den;
+    o[w * RMAX + i] = num / den;
   }
   __syncthreads();
-  if (tid < r) {
-    float a = __ldg(p.p2b + tid);
-    for (int k = 0; k < r; ++k) a = fmaf(o[k], __ldg(p.p2T + k * r + tid), a);
-    u[tid] = a;
+  for (int e = tid; e < WPB * r; e += LG_THREADS) {
+    const int w = e / r, i = e - w * r;
+    float a = __ldg(p.p2b + i);
+    for (int k = 0; k < r; ++k) a = fmaf(o[w * RMAX + k], __ldg(p.p2T + k * r + i), a);
+    u[w * RMAX + i] = a;
   }
   __syncthreads();
   for (int c = tid; c < C; c += LG_THREADS) {
-    float a = 0.f;
-    for (int k = 0; k < r; ++k) a = fmaf(u[k], __ldg(p.upT + k * C + c), a);
-    p.gate[(long long)win * C + c] = a;
+    float a[WPB];
+#pragma unroll
+    for (int w = 0; w < WPB; ++w) a[w] = 0.f;
+    for (int k = 0; k < r; ++k) {
+      const float wv = __ldg(p.upT + k * C + c);
+#pragma unroll
+      for (int w = 0; w < WPB; ++w) a[w] = fmaf(u[w * RMAX + k], wv, a[w]);
+    }
+#pragma unroll
+    for (int w = 0; w < WPB; ++w)
+      if (w < nw) p.gate[(long long)(w0 + w) * C + c] = a[w];
   }
 }
 
@@ -118,7 +167,7 @@ extern "C" int mphsir_local_gate_fwd(const mphsir_local_gate_params* p, void* st
   MPHSIR_REQUIRE(p && p->core_mean && p->gate, "local_gate: null operand");
   MPHSIR_REQUIRE(p->projT && p->projb && p->promptT && p->downT && p->param && p->qT && p->kvT && p->p2T && p->p2b && p->upT, "local_gate: null weight");
   MPHSIR_REQUIRE(p->B_ > 0 && p->C > 0 && p->r > 0 && p->r <= RMAX, "local_gate: bad shape B_=%d C=%d r=%d (r<=%d)", p->B_, p->C, p->r, RMAX);
-  const size_t smem = sizeof(float) * (2 * p->C + PLEN + 7 * RMAX + 8);
-  local_gate_kernel<<<p->B_, LG_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*p);
+  const size_t smem = sizeof(float) * WPB * (2 * p->C + PLEN + 7 * RMAX + 8);
+  local_gate_kernel<<<(p->B_ + WPB - 1) / WPB, LG_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*p);
   return check_launch("local_gate");
 }

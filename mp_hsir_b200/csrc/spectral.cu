@@ -9,48 +9,65 @@
 namespace mphsir {
 
 // ---------------------------------------------------------------------------------------------
-// depthwise 3x3: one thread per (pixel, 4 channels); 128-bit loads along channels.
+// depthwise 3x3: one thread per (1x4 pixel strip, 4 channels).  The 3x6 input patch of the strip is
+// loaded once (128-bit loads along channels, neighbouring threads = neighbouring channels) and reused
+// by the 4 outputs, the 9 weight vectors once per strip: 27 loads per 4 outputs instead of 72, which
+// moves the kernel from L1-bandwidth-bound to HBM-bound.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dw_row(const float* __restrict__ rowp, long long ldx, int x0, int W,
+                                       const float4 w0, const float4 w1, const float4 w2, float4 (&acc)[4]) {
+  // rowp points at pixel (y+dy, x0) + channel offset; columns x0-1 .. x0+4
+  float4 v[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const int xx = x0 - 1 + j;
+    v[j] = (xx >= 0 && xx < W) ? ldg4(rowp + (long long)(j - 1) * ldx) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    acc[o].x = fmaf(v[o].x, w0.x, fmaf(v[o + 1].x, w1.x, fmaf(v[o + 2].x, w2.x, acc[o].x)));
+    acc[o].y = fmaf(v[o].y, w0.y, fmaf(v[o + 1].y, w1.y, fmaf(v[o + 2].y, w2.y, acc[o].y)));
+    acc[o].z = fmaf(v[o].z, w0.z, fmaf(v[o + 1].z, w1.z, fmaf(v[o + 2].z, w2.z, acc[o].z)));
+    acc[o].w = fmaf(v[o].w, w0.w, fmaf(v[o + 1].w, w1.w, fmaf(v[o + 2].w, w2.w, acc[o].w)));
+  }
+}
+
 template <bool GATE>
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const float* __restrict__ X, long long ldx,
                                                         const float* __restrict__ w9, float* __restrict__ Y,
                                                         long long ldy, int B, int H, int W, int C, int half) {
   const int c4n = (GATE ? half : C) >> 2;
-  const long long total = (long long)B * H * W * c4n;
+  const int W4 = W >> 2;
+  const long long total = (long long)B * H * W4 * c4n;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(idx % c4n) * 4;
-    const long long pix = idx / c4n;
-    const int x = (int)(pix % W);
-    const int y = (int)((pix / W) % H);
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), g = a;
+    const long long strip = idx / c4n;
+    const int x0 = (int)(strip % W4) * 4;
+    const long long by = strip / W4;  // b*H + y
+    const int y = (int)(by % H);
+    const long long pix0 = by * W + x0;
+    float4 a[4], g[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) a[o] = g[o] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy) {
       const int yy = y + dy;
       if (yy < 0 || yy >= H) continue;
+      const float* rowp = X + (pix0 + (long long)dy * W) * ldx + c;
+      const float* wr = w9 + (dy + 1) * 3 * C + c;
+      dw_row(rowp, ldx, x0, W, ldg4(wr), ldg4(wr + C), ldg4(wr + 2 * C), a);
+      if (GATE) dw_row(rowp + half, ldx, x0, W, ldg4(wr + half), ldg4(wr + C + half), ldg4(wr + 2 * C + half), g);
+    }
 #pragma unroll
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int xx = x + dx;
-        if (xx < 0 || xx >= W) continue;
-        const int tap = (dy + 1) * 3 + (dx + 1);
-        const float* src = X + (pix + dy * W + dx) * ldx + c;
-        const float4 v = ldg4(src);
-        const float4 w = ldg4(w9 + tap * C + c);
-        a.x = fmaf(v.x, w.x, a.x); a.y = fmaf(v.y, w.y, a.y);
-        a.z = fmaf(v.z, w.z, a.z); a.w = fmaf(v.w, w.w, a.w);
-        if (GATE) {
-          const float4 v2 = ldg4(src + half);
-          const float4 w2 = ldg4(w9 + tap * C + half + c);
-          g.x = fmaf(v2.x, w2.x, g.x); g.y = fmaf(v2.y, w2.y, g.y);
-          g.z = fmaf(v2.z, w2.z, g.z); g.w = fmaf(v2.w, w2.w, g.w);
-        }
+    for (int o = 0; o < 4; ++o) {
+      float4 r = a[o];
+      if (GATE) {
+        r.x = gelu_erf(r.x) * g[o].x; r.y = gelu_erf(r.y) * g[o].y;
+        r.z = gelu_erf(r.z) * g[o].z; r.w = gelu_erf(r.w) * g[o].w;
       }
+      *reinterpret_cast<float4*>(Y + (pix0 + o) * ldy + c) = r;
     }
-    if (GATE) {
-      a.x = gelu_erf(a.x) * g.x; a.y = gelu_erf(a.y) * g.y;
-      a.z = gelu_erf(a.z) * g.z; a.w = gelu_erf(a.w) * g.w;
-    }
-    *reinterpret_cast<float4*>(Y + pix * ldy + c) = a;
   }
 }
 
@@ -138,6 +155,33 @@ static int gram_chunk(int B, int heads, int HW) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// stage-2 reduction of the Gram partials: grid = (ceil(per/64), B*heads), 256 threads = 64 elements x 4
+// chunk groups, 4 independent accumulators per thread (the chunk count is in the hundreds at 512x512).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gram_reduce_kernel(const float* __restrict__ partial, int n_chunks, int per,
+                                                          float* __restrict__ reduced) {
+  __shared__ float red[4][64];
+  const int e = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int g = threadIdx.x >> 6;
+  const float* src = partial + (long long)blockIdx.y * n_chunks * per;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (e < per) {
+    int ch = g;
+    for (; ch + 12 < n_chunks; ch += 16) {
+      a0 += __ldg(src + (long long)ch * per + e);
+      a1 += __ldg(src + (long long)(ch + 4) * per + e);
+      a2 += __ldg(src + (long long)(ch + 8) * per + e);
+      a3 += __ldg(src + (long long)(ch + 12) * per + e);
+    }
+    for (; ch < n_chunks; ch += 4) a0 += __ldg(src + (long long)ch * per + e);
+  }
+  red[g][threadIdx.x & 63] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (g == 0 && e < per)
+    reduced[(long long)blockIdx.y * per + e] = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------------
 // reduce partials + normalise + temperature + row softmax.  grid = B*heads, 256 threads.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gram_softmax_kernel(const float* __restrict__ partial, int n_chunks,
@@ -219,8 +263,9 @@ extern "C" int mphsir_dwconv3x3_fwd(const float* X, int ldx, const float* w9, fl
   MPHSIR_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldx >= C, "dwconv3x3: bad shape C=%d ldx=%d ldy=%d", C, ldx, ldy);
   MPHSIR_REQUIRE(gate_half == 0 || (2 * gate_half == C && gate_half % 4 == 0), "dwconv3x3: gate_half=%d must be C/2 and a multiple of 4", gate_half);
   MPHSIR_REQUIRE(((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(w9)) & 15) == 0, "dwconv3x3: operands must be 16-byte aligned");
-  const long long total = (long long)B * H * W * ((gate_half ? gate_half : C) / 4);
-  const int blocks = (int)((total + 255) / 256 > 148LL * 64 ? 148LL * 64 : (total + 255) / 256);
+  MPHSIR_REQUIRE(W % 4 == 0, "dwconv3x3: W=%d must be a multiple of 4", W);
+  const long long total = (long long)B * H * (W / 4) * ((gate_half ? gate_half : C) / 4);
+  const int blocks = (int)((total + 255) / 256 > 148LL * 32 ? 148LL * 32 : (total + 255) / 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (gate_half)
     dwconv3x3_kernel<true><<<blocks, 256, 0, st>>>(X, ldx, w9, Y, ldy, B, H, W, C, gate_half);
@@ -256,10 +301,20 @@ extern "C" int mphsir_gram_partial_fwd(const float* q, int ldq, int q_shared, co
 }
 
 extern "C" int mphsir_gram_softmax_fwd(const float* partial, int n_chunks, const float* temperature, float* attn,
-                                       int B, int heads, int c, void* stream) {
+                                       float* scratch, int B, int heads, int c, void* stream) {
   MPHSIR_REQUIRE(partial && temperature && attn && n_chunks > 0 && B > 0 && heads > 0 && c > 0, "gram_softmax: bad arguments");
   const size_t smem = sizeof(float) * ((size_t)c * c + 2 * c);
-  gram_softmax_kernel<<<B * heads, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(partial, n_chunks, temperature, attn, heads, c);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int per = c * c + 2 * c;
+  if (n_chunks > 8) {
+    // two-stage: parallel reduction into chunk slot 0 of a scratch area placed right after the partials
+    MPHSIR_REQUIRE(scratch != nullptr, "gram_softmax: scratch [B*heads*(c*c+2c)] is required when n_chunks > 8");
+    dim3 grid((per + 63) / 64, B * heads);
+    gram_reduce_kernel<<<grid, 256, 0, st>>>(partial, n_chunks, per, scratch);
+    gram_softmax_kernel<<<B * heads, 256, smem, st>>>(scratch, 1, temperature, attn, heads, c);
+  } else {
+    gram_softmax_kernel<<<B * heads, 256, smem, st>>>(partial, n_chunks, temperature, attn, heads, c);
+  }
   return check_launch("gram_softmax");
 }
 

@@ -296,7 +296,8 @@ class Engine:
         ldm = _ldb(C)
         Mt = ws.flat(tag + ".Mt", B * _ceil(C, 16) * ldm).view(-1)[: B * _ceil(C, 16) * ldm].view(B, _ceil(C, 16), ldm)
         lib.gram_partial(q, q_shared, k, k_shared, partial, B, HW, heads, c)
-        lib.gram_softmax(partial, nch, temp, attn, B, heads, c)
+        scratch = ws.flat(tag + ".gsum", B * heads * (c * c + 2 * c))
+        lib.gram_softmax(partial, nch, temp, attn, B, heads, c, scratch=scratch)
         lib.spectral_fold(attn, out_t, Mt, B, heads, c)
         img = None
         if self.prec != lib.PREC_FP32_SIMT:

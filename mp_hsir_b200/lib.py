@@ -76,7 +76,7 @@ SIGNATURES = {
     "mphsir_dwconv3x3_fwd": (_I, [_VP, _I, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "mphsir_gram_partial_floats": (C.c_size_t, [_I, _I, _I, _I, C.POINTER(_I)]),
     "mphsir_gram_partial_fwd": (_I, [_VP, _I, _I, _VP, _I, _I, _VP, _I, _I, _I, _I, _VP]),
-    "mphsir_gram_softmax_fwd": (_I, [_VP, _I, _VP, _VP, _I, _I, _I, _VP]),
+    "mphsir_gram_softmax_fwd": (_I, [_VP, _I, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "mphsir_spectral_fold_fwd": (_I, [_VP, _VP, _VP, _I, _LL, _I, _I, _I, _VP]),
     "mphsir_tvsp_query_fwd": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "mphsir_bilinear_fwd": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
@@ -350,10 +350,12 @@ def gram_partial(q: View, q_shared: bool, k: View, k_shared: bool, partial: torc
 
 
 def gram_softmax(partial: torch.Tensor, n_chunks: int, temperature: torch.Tensor, attn: torch.Tensor, B: int,
-                 heads: int, c: int) -> None:
+                 heads: int, c: int, scratch: Optional[torch.Tensor] = None) -> None:
+    if scratch is None:
+        scratch = torch.empty(B * heads * (c * c + 2 * c), device=partial.device, dtype=torch.float32)
     _launch("gram_softmax_fwd",
             lambda: load().mphsir_gram_softmax_fwd(partial.data_ptr(), n_chunks, temperature.data_ptr(),
-                                                   attn.data_ptr(), B, heads, c, stream_ptr()),
+                                                   attn.data_ptr(), scratch.data_ptr(), B, heads, c, stream_ptr()),
             lambda: (0.0, 4.0 * B * heads * (n_chunks + 1) * c * c, "gram_softmax"))
 
 
