@@ -163,13 +163,15 @@ MPHSIR_API int mphsir_window_attn_fwd(const float* qkv, int ldqkv, const float* 
  * PG_Spectral_Attention.forward :135-152 collapsed to a per-window channel gate g[B_,C];
  * the caller applies sa*g in the MPHSIR_EPI_SPECTRAL epilogue (:153).
  *   core_mean [B_,C] : token mean of the attention core (before proj)
- *   all weights pre-transposed to "in x out":
- *   projT[C,C] projb[C] (Spatial_Attention.proj, mean commutes with it), promptT[C,128],
- *   downT[C,r], param[128,r], qT[r,r], kvT[r,2r], p2T[r,r], p2b[r], upT[r,C]
+ *   all weights pre-transposed to "in x out".  Spatial_Attention.proj (the mean over tokens commutes
+ *   with it) is folded into the two matrices that consume its output:
+ *     promptT[C,128] = projT @ linear_prompt^T,  promptb[128] = linear_prompt @ projb
+ *     downT[C,r]     = projT @ linear_down^T,    downb[r]     = linear_down @ projb
+ *   param[128,r], qT[r,r], kvT[r,2r], p2T[r,r], p2b[r], upT[r,C]
  * ------------------------------------------------------------------------------------- */
 typedef struct {
   const float* core_mean;
-  const float *projT, *projb, *promptT, *downT, *param, *qT, *kvT, *p2T, *p2b, *upT;
+  const float *promptT, *promptb, *downT, *downb, *param, *qT, *kvT, *p2T, *p2b, *upT;
   float* gate; /* [B_, C] */
   int B_, C, r;
 } mphsir_local_gate_params;

@@ -3,8 +3,9 @@
 // of the attention core into a per-window channel gate g[B_,C].
 //
 //   m   = projT^T core_mean + projb            (mean over tokens commutes with Spatial_Attention.proj)
-//   pw  = softmax(promptT^T m)   [128]         (:136)
-//   dn  = downT^T m              [r]           (:137)
+//   pw  = softmax(promptT^T m)   [128]         (:136)   } m is never formed: the host folds proj into
+//   dn  = downT^T m              [r]           (:137)   } promptT/downT (promptT := projT promptT, bias
+//                                                          promptb := promptT^T projb; same for down)
 //   sp  = pw @ param             [r]           (:139-140)
 //   q   = qT^T sp ; [k;v] = kvT^T dn           (:142-144)
 //   A   = softmax_j(q_i k_j r^-0.5) ; o_i = sum_j A_ij v_j     (:146-149, outer-product attention)
@@ -16,7 +17,7 @@
 
 namespace mphsir {
 
-constexpr int LG_THREADS = 128;
+constexpr int LG_THREADS = 160;  // 128 prompt threads + 32 low-rank threads
 constexpr int PLEN = 128;
 constexpr int RMAX = 32;
 constexpr int WPB = 8;  // windows per CTA: every weight element is fetched once per 8 windows
@@ -25,8 +26,7 @@ __global__ void __launch_bounds__(LG_THREADS) local_gate_kernel(const mphsir_loc
   extern __shared__ float sm[];
   const int C = p.C, r = p.r;
   float* cm = sm;                 // [WPB][C] core mean
-  float* m = cm + WPB * C;        // [WPB][C]
-  float* pw = m + WPB * C;        // [WPB][128]
+  float* pw = cm + WPB * C;       // [WPB][128]
   float* dn = pw + WPB * PLEN;    // [WPB][RMAX]
   float* sp = dn + WPB * RMAX;
   float* q = sp + WPB * RMAX;
@@ -43,62 +43,57 @@ __global__ void __launch_bounds__(LG_THREADS) local_gate_kernel(const mphsir_loc
     cm[e] = (w < nw) ? __ldg(p.core_mean + (long long)(w0 + w) * C + c) : 0.f;
   }
   __syncthreads();
-  // m = projT^T cm + projb
-  for (int c = tid; c < C; c += LG_THREADS) {
-    float a[WPB];
-    const float b0 = __ldg(p.projb + c);
-#pragma unroll
-    for (int w = 0; w < WPB; ++w) a[w] = b0;
-    for (int k = 0; k < C; ++k) {
-      const float wv = __ldg(p.projT + (long long)k * C + c);
-#pragma unroll
-      for (int w = 0; w < WPB; ++w) a[w] = fmaf(cm[w * C + k], wv, a[w]);
-    }
-#pragma unroll
-    for (int w = 0; w < WPB; ++w) m[w * C + c] = a[w];
-  }
-  __syncthreads();
-  // prompt logits (thread == prompt index) and the low-rank projection
+  // prompt logits (threads 0..127 == prompt index) and the low-rank projection (threads 128..128+r-1);
+  // proj is pre-folded into promptT/downT, so both read the core mean directly.
   float logit[WPB];
+  {
+    const bool is_prompt = tid < PLEN;
+    const int j = is_prompt ? tid : tid - PLEN;
+    const bool active = is_prompt || j < r;
+    const float* wsrc = is_prompt ? p.promptT : p.downT;
+    const int ldw = is_prompt ? PLEN : r;
+    const float b0 = active ? __ldg((is_prompt ? p.promptb : p.downb) + j) : 0.f;
 #pragma unroll
-  for (int w = 0; w < WPB; ++w) logit[w] = 0.f;
-  for (int k = 0; k < C; ++k) {
-    const float wv = __ldg(p.promptT + k * PLEN + tid);
+    for (int w = 0; w < WPB; ++w) logit[w] = b0;
+    if (active) {
+#pragma unroll 4
+      for (int k = 0; k < C; ++k) {
+        const float wv = __ldg(wsrc + k * ldw + j);
 #pragma unroll
-    for (int w = 0; w < WPB; ++w) logit[w] = fmaf(m[w * C + k], wv, logit[w]);
-  }
-  if (tid < r) {
-    float a[WPB];
-#pragma unroll
-    for (int w = 0; w < WPB; ++w) a[w] = 0.f;
-    for (int k = 0; k < C; ++k) {
-      const float wv = __ldg(p.downT + k * r + tid);
-#pragma unroll
-      for (int w = 0; w < WPB; ++w) a[w] = fmaf(m[w * C + k], wv, a[w]);
+        for (int w = 0; w < WPB; ++w) logit[w] = fmaf(cm[w * C + k], wv, logit[w]);
+      }
     }
+    if (!is_prompt && active) {
 #pragma unroll
-    for (int w = 0; w < WPB; ++w) dn[w * RMAX + tid] = a[w];
+      for (int w = 0; w < WPB; ++w) dn[w * RMAX + j] = logit[w];
+    }
   }
   // softmax over the 128 logits of each window (4 warps)
+  if (tid < PLEN) {
 #pragma unroll
-  for (int w = 0; w < WPB; ++w) {
-    const float mx = warp_max(logit[w]);
-    if ((tid & 31) == 0) red[w * 8 + (tid >> 5)] = mx;
+    for (int w = 0; w < WPB; ++w) {
+      const float mx = warp_max(logit[w]);
+      if ((tid & 31) == 0) red[w * 8 + (tid >> 5)] = mx;
+    }
   }
   __syncthreads();
   float ex[WPB];
+  if (tid < PLEN) {
 #pragma unroll
-  for (int w = 0; w < WPB; ++w) {
-    const float mx = fmaxf(fmaxf(red[w * 8 + 0], red[w * 8 + 1]), fmaxf(red[w * 8 + 2], red[w * 8 + 3]));
-    ex[w] = expf(logit[w] - mx);
-    const float s = warp_sum(ex[w]);
-    if ((tid & 31) == 0) red[w * 8 + 4 + (tid >> 5)] = s;
+    for (int w = 0; w < WPB; ++w) {
+      const float mx = fmaxf(fmaxf(red[w * 8 + 0], red[w * 8 + 1]), fmaxf(red[w * 8 + 2], red[w * 8 + 3]));
+      ex[w] = expf(logit[w] - mx);
+      const float s = warp_sum(ex[w]);
+      if ((tid & 31) == 0) red[w * 8 + 4 + (tid >> 5)] = s;
+    }
   }
   __syncthreads();
+  if (tid < PLEN) {
 #pragma unroll
-  for (int w = 0; w < WPB; ++w) {
-    const float s = (red[w * 8 + 4] + red[w * 8 + 5]) + (red[w * 8 + 6] + red[w * 8 + 7]);
-    pw[w * PLEN + tid] = ex[w] / s;
+    for (int w = 0; w < WPB; ++w) {
+      const float s = (red[w * 8 + 4] + red[w * 8 + 5]) + (red[w * 8 + 6] + red[w * 8 + 7]);
+      pw[w * PLEN + tid] = ex[w] / s;
+    }
   }
   __syncthreads();
   // the remaining r-sized steps: thread -> (window, index)
@@ -165,9 +160,9 @@ using namespace mphsir;
 
 extern "C" int mphsir_local_gate_fwd(const mphsir_local_gate_params* p, void* stream) {
   MPHSIR_REQUIRE(p && p->core_mean && p->gate, "local_gate: null operand");
-  MPHSIR_REQUIRE(p->projT && p->projb && p->promptT && p->downT && p->param && p->qT && p->kvT && p->p2T && p->p2b && p->upT, "local_gate: null weight");
+  MPHSIR_REQUIRE(p->promptT && p->promptb && p->downT && p->downb && p->param && p->qT && p->kvT && p->p2T && p->p2b && p->upT, "local_gate: null weight");
   MPHSIR_REQUIRE(p->B_ > 0 && p->C > 0 && p->r > 0 && p->r <= RMAX, "local_gate: bad shape B_=%d C=%d r=%d (r<=%d)", p->B_, p->C, p->r, RMAX);
-  const size_t smem = sizeof(float) * WPB * (2 * p->C + PLEN + 7 * RMAX + 8);
+  const size_t smem = sizeof(float) * WPB * (p->C + PLEN + 7 * RMAX + 8);
   local_gate_kernel<<<(p->B_ + WPB - 1) / WPB, LG_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*p);
   return check_launch("local_gate");
 }

@@ -214,11 +214,15 @@ class Engine:
                 d["sout_t"] = f32(g.project_out.weight).reshape(st.dim, st.dim).t().contiguous()
                 l = blk.local_spectral_attn
                 r = st.rank
+                # fold Spatial_Attention.proj into the two matrices that consume its (window-mean) output;
+                # done in fp64 so the fold itself adds no rounding beyond the final fp32 cast
+                pw64, pb64 = a.proj.weight.detach().double().to(self.device), a.proj.bias.detach().double().to(self.device)
+                lp64, ld64 = l.linear_prompt.weight.detach().double().to(self.device), l.linear_down.weight.detach().double().to(self.device)
                 d["gate"] = {
-                    "projT": f32(a.proj.weight).t().contiguous(),
-                    "projb": d["proj_b"],
-                    "promptT": f32(l.linear_prompt.weight).t().contiguous(),
-                    "downT": f32(l.linear_down.weight).t().contiguous(),
+                    "promptT": (lp64 @ pw64).t().float().contiguous(),
+                    "promptb": (lp64 @ pb64).float().contiguous(),
+                    "downT": (ld64 @ pw64).t().float().contiguous(),
+                    "downb": (ld64 @ pb64).float().contiguous(),
                     "param": f32(l.prompt_param).reshape(PROMPT_LEN, r).contiguous(),
                     "qT": f32(l.q.weight).t().contiguous(),
                     "kvT": f32(l.kv.weight).t().contiguous(),

@@ -52,7 +52,7 @@ class ConvParams(C.Structure):
 
 class LocalGateParams(C.Structure):
     _fields_ = [("core_mean", C.c_void_p)] + [
-        (n, C.c_void_p) for n in ("projT", "projb", "promptT", "downT", "param", "qT", "kvT", "p2T", "p2b", "upT")
+        (n, C.c_void_p) for n in ("promptT", "promptb", "downT", "downb", "param", "qT", "kvT", "p2T", "p2b", "upT")
     ] + [("gate", C.c_void_p), ("B_", C.c_int), ("C", C.c_int), ("r", C.c_int)]
 
 
@@ -319,11 +319,11 @@ def window_attn(qkv: View, bias: torch.Tensor, out: View, win_mean: torch.Tensor
 def local_gate(core_mean: torch.Tensor, w: dict, gate: torch.Tensor, B_: int, Cc: int, r: int) -> None:
     p = LocalGateParams()
     p.core_mean = core_mean.data_ptr()
-    for n in ("projT", "projb", "promptT", "downT", "param", "qT", "kvT", "p2T", "p2b", "upT"):
+    for n in ("promptT", "promptb", "downT", "downb", "param", "qT", "kvT", "p2T", "p2b", "upT"):
         setattr(p, n, w[n].data_ptr())
     p.gate, p.B_, p.C, p.r = gate.data_ptr(), B_, Cc, r
     _launch("local_gate_fwd", lambda: load().mphsir_local_gate_fwd(C.byref(p), stream_ptr()),
-            lambda: (2.0 * B_ * (Cc * Cc + Cc * 128 + 2 * Cc * r + 128 * r), 8.0 * B_ * Cc, "local_gate"))
+            lambda: (2.0 * B_ * (Cc * 128 + 2 * Cc * r + 128 * r), 8.0 * B_ * Cc, "local_gate"))
 
 
 def dwconv3x3(X: View, w9: torch.Tensor, Y: View, B: int, H: int, W: int, Cc: int, gate_half: int = 0) -> None:

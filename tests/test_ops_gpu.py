@@ -202,8 +202,9 @@ def test_local_gate(C, r):
     pw, pb = rnd(C, C, seed=9, scale=C ** -0.5), 0.1 * rnd(C, seed=10)
     core_mean = rnd(B_, C, seed=11)
     ref = O.local_spectral_gate(core_mean @ pw.t() + pb, sd, pfx)
-    w = {"projT": pw.t(), "projb": pb, "promptT": sd[pfx + "linear_prompt.weight"].t(),
-         "downT": sd[pfx + "linear_down.weight"].t(), "param": sd[pfx + "prompt_param"].view(128, r),
+    lp, ld = sd[pfx + "linear_prompt.weight"], sd[pfx + "linear_down.weight"]
+    w = {"promptT": (lp @ pw).t(), "promptb": lp @ pb, "downT": (ld @ pw).t(), "downb": ld @ pb,
+         "param": sd[pfx + "prompt_param"].view(128, r),
          "qT": sd[pfx + "q.weight"].t(), "kvT": sd[pfx + "kv.weight"].t(), "p2T": sd[pfx + "proj.weight"].t(),
          "p2b": sd[pfx + "proj.bias"], "upT": sd[pfx + "linear_up.weight"].t()}
     w = {k: dev(v) for k, v in w.items()}
