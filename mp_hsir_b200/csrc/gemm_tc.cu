@@ -157,7 +157,7 @@ __device__ __forceinline__ void tile_rows(const TcArgs& p, int tile, int& m0, in
   }
 }
 
-template <int EPI>
+template <int EPI, bool LN>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
   constexpr bool CONV = EPI >= TC_OUT_TOKENS;
   // NCHW / pixel-unshuffle stores are already coalesced (or hopeless) in the row-per-thread TMEM mapping
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_RING; ++i) {
-      mbar_init(smem_u32(&sm->a_full[i]), kConvThreads / 32);
+      mbar_init(smem_u32(&sm->a_full[i]), kConvThreads / 64);  // one converter group (4 warps) fills a slab
       mbar_init(smem_u32(&sm->a_empty[i]), 1);
       mbar_init(smem_u32(&sm->b_full[i]), 1);
       mbar_init(smem_u32(&sm->b_empty[i]), 1);
@@ -442,74 +442,67 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
     }
   } else {
     // =============================== A converters (warps 10..17) ============================
-    const int ct = threadIdx.x - kFirstConvWarp * 32;  // 0..255
-    const int chunk = ct & 7;             // 8-element (16-byte bf16) chunk inside the 64-k slab
-    const int rbase = ct >> 3;            // rows rbase + 32*i, i = 0..3
-    uint32_t a_it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    // Two independent groups of 4 warps.  Stationary tiles alternate between the groups (group g converts
+    // local tiles with parity g), streamed slabs alternate slab by slab: while one group converts, the
+    // other has its global loads in flight, so ~64 KB of reads are outstanding per SM.
+    const int cg = (warp - kFirstConvWarp) >> 2;
+    const int gt = threadIdx.x - (kFirstConvWarp + 4 * cg) * 32;  // 0..127 inside the group
+    const int chunk = gt & 7;              // 8-element (16-byte bf16) chunk inside the 64-k slab
+    const int rbase = gt >> 3;             // rows rbase + 16*i, i = 0..7
+    constexpr bool has_ln = LN;
+    // A ring slot must always be refilled by the same group (an mbarrier parity wait is only safe one phase
+    // ahead): whole tiles alternate when a tile pair tiles the ring exactly, otherwise slabs alternate
+    // (slot parity == slab-counter parity because the ring depth is even).
+    const bool tile_alt = stationary && (p.na % (2 * Ks) == 0);
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      if (tile_alt && (lt & 1) != cg) continue;
       int m0, m_end;
       tile_rows(p, tile, m0, m_end);
-      bool valid[4];
-      const float* arow[4];
-      int pb[4], py[4], px[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int m = m0 + rbase + 32 * i;
-        valid[i] = m < m_end;
-        const int mm = valid[i] ? m : m0;
-        if (CONV) {
-          const int hw = p.H * p.W;
-          pb[i] = mm / hw;
-          const int rem = mm - pb[i] * hw;
-          py[i] = rem / p.W;
-          px[i] = rem - py[i] * p.W;
-          arow[i] = nullptr;
-        } else {
-          arow[i] = p.A + (size_t)(p.a_row_mod > 0 ? mm % p.a_row_mod : mm) * p.lda;
-          pb[i] = py[i] = px[i] = 0;
-        }
-      }
       // LayerNorm statistics: the 8 lanes that share a row reduce sum / sum-of-squares over K.
-      float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f};
-      if (!CONV && p.ln_g != nullptr) {
-        float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
+      float mean[8], rstd[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        mean[i] = 0.f;
+        rstd[i] = 1.f;
+      }
+      if (has_ln) {
+        float sm_[8], sq_[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sm_[i] = sq_[i] = 0.f;
         for (int k = chunk * 4; k < p.Ka; k += 32) {
-          float4 v[4];
+          float4 v[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = valid[i] ? ldg4(arow[i] + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < 8; ++i) {
+            const int m = m0 + rbase + 16 * i;
+            v[i] = (m < m_end) ? ldg4(p.A + (size_t)(p.a_row_mod > 0 ? m % p.a_row_mod : m) * p.lda + k)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            s[i] += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-            q[i] += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+          for (int i = 0; i < 8; ++i) {
+            sm_[i] += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            sq_[i] += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
           }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 8; ++i) {
 #pragma unroll
           for (int o = 4; o > 0; o >>= 1) {
-            s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
-            q[i] += __shfl_xor_sync(0xffffffffu, q[i], o);
+            sm_[i] += __shfl_xor_sync(0xffffffffu, sm_[i], o);
+            sq_[i] += __shfl_xor_sync(0xffffffffu, sq_[i], o);
           }
-          const float mu = s[i] / (float)p.Ka;
+          const float mu = sm_[i] / (float)p.Ka;
           mean[i] = mu;
-          rstd[i] = rsqrtf(fmaxf(q[i] / (float)p.Ka - mu * mu, 0.f) + 1e-5f);
+          rstd[i] = rsqrtf(fmaxf(sq_[i] / (float)p.Ka - mu * mu, 0.f) + 1e-5f);
         }
       }
       const int conv_passes = stationary ? 1 : npass;
       for (int pass = 0; pass < conv_passes; ++pass) {
-        for (int s = 0; s < Ks; ++s, ++a_it) {
-          const int slot = a_it % p.na;
-          mbar_wait(smem_u32(&sm->a_empty[slot]), ((a_it / p.na) & 1) ^ 1);
-          uint8_t* dst = a_ring + (size_t)slot * a_slot_bytes;
+        for (int s = 0; s < Ks; ++s) {
+          const uint32_t a_it = stationary ? (uint32_t)(lt * Ks + s) : (uint32_t)((lt * npass + pass) * Ks + s);
+          if (!tile_alt && (int)(a_it & 1) != cg) continue;
           const int k = s * 64 + chunk * 8;
           const bool kin = k < p.Ka;
-          float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = g0;
-          float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
-          if (!CONV && p.ln_g != nullptr && kin) {
-            g0 = ldg4(p.ln_g + k); g1 = ldg4(p.ln_g + k + 4);
-            e0 = ldg4(p.ln_b + k); e1 = ldg4(p.ln_b + k + 4);
-          }
           int dy = 0, dx = 0, cc = 0;
           if (CONV) {
             const int tap = k / p.Cin;
@@ -517,17 +510,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
             dy = tap / 3 - 1;
             dx = tap - (tap / 3) * 3 - 1;
           }
-          float4 v0[4], v1[4];
+          // issue every global load of this slab before waiting for the smem slot
+          float4 v0[8], v1[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            bool ok = valid[i] && kin;
-            const float* src;
+          for (int i = 0; i < 8; ++i) {
+            const int m = m0 + rbase + 16 * i;
+            bool ok = kin && m < m_end;
+            const float* src = p.A;
             if (CONV) {
-              const int yy = py[i] + dy, xx = px[i] + dx;
+              const int hw = p.H * p.W;
+              const int mm = ok ? m : m0;
+              const int b = mm / hw;
+              const int rem = mm - b * hw;
+              const int y = rem / p.W, x = rem - y * p.W;
+              const int yy = y + dy, xx = x + dx;
               ok = ok && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
-              src = p.A + ((size_t)(pb[i] * p.H + yy) * p.W + xx) * p.lda + cc;
-            } else {
-              src = arow[i] + k;
+              src = p.A + ((size_t)(b * p.H + yy) * p.W + xx) * p.lda + cc;
+            } else if (ok) {
+              src = p.A + (size_t)(p.a_row_mod > 0 ? m % p.a_row_mod : m) * p.lda + k;
             }
             if (ok) {
               v0[i] = ldg4(src);
@@ -536,17 +536,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
               v0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
               v1[i] = v0[i];
             }
-            if (!CONV && p.ln_g != nullptr && ok) {
+          }
+          float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = g0;
+          float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
+          if (has_ln && kin) {
+            g0 = ldg4(p.ln_g + k); g1 = ldg4(p.ln_g + k + 4);
+            e0 = ldg4(p.ln_b + k); e1 = ldg4(p.ln_b + k + 4);
+          }
+          const int slot = a_it % p.na;
+          mbar_wait(smem_u32(&sm->a_empty[slot]), ((a_it / p.na) & 1) ^ 1);
+          uint8_t* dst = a_ring + (size_t)slot * a_slot_bytes;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = rbase + 16 * i;
+            if (has_ln && kin && m0 + r < m_end) {
               const float a = rstd[i], mu = mean[i];
               v0[i].x = (v0[i].x - mu) * a * g0.x + e0.x; v0[i].y = (v0[i].y - mu) * a * g0.y + e0.y;
               v0[i].z = (v0[i].z - mu) * a * g0.z + e0.z; v0[i].w = (v0[i].w - mu) * a * g0.w + e0.w;
               v1[i].x = (v1[i].x - mu) * a * g1.x + e1.x; v1[i].y = (v1[i].y - mu) * a * g1.y + e1.y;
               v1[i].z = (v1[i].z - mu) * a * g1.z + e1.z; v1[i].w = (v1[i].w - mu) * a * g1.w + e1.w;
             }
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = rbase + 32 * i;
             uint4 hi, lo;
             split2(v0[i].x, v0[i].y, hi.x, lo.x);
             split2(v0[i].z, v0[i].w, hi.y, lo.y);
@@ -612,19 +621,25 @@ static size_t smem_bytes(int na, int nb, int parts) {
   return 1024 + (size_t)na * SLAB_BYTES * parts + (size_t)nb * BBLK_BYTES * parts + (size_t)kEpiWarps * STG_FLOATS * sizeof(float);
 }
 
-template <int EPI>
-static int launch_epi(const TcArgs& a, size_t smem, int grid, cudaStream_t st) {
+template <int EPI, bool LN>
+static int launch_epi2(const TcArgs& a, size_t smem, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return MPHSIR_ERR_CUDA;
     }
     configured = true;
   }
-  gemm_tc_kernel<EPI><<<grid, kThreads, smem, st>>>(a);
+  gemm_tc_kernel<EPI, LN><<<grid, kThreads, smem, st>>>(a);
   return check_launch("gemm(tc)");
+}
+
+template <int EPI>
+static int launch_epi(const TcArgs& a, size_t smem, int grid, cudaStream_t st) {
+  if (EPI < TC_OUT_TOKENS && a.ln_g != nullptr) return launch_epi2<EPI, (EPI < TC_OUT_TOKENS)>(a, smem, grid, st);
+  return launch_epi2<EPI, false>(a, smem, grid, st);
 }
 
 int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
