@@ -108,6 +108,9 @@ typedef struct {
  * `transposed`) -> bf16 hi/lo parts in the 128-byte-swizzled K-major layout the MMA reads
  * (mp_hsir_b200/csrc/gemm_tc.cuh: bimg_offset).  `batch` independent matrices, w_batch_stride floats
  * apart, produce images mphsir_bimg_bytes(N,K) bytes apart.  img must be 128-byte aligned. */
+/* Debug: when buf != NULL every subsequent tensor-core GEMM launch writes per-CTA cycle counters of its
+ * warp roles into buf[grid][16] (tools/gemm_bench.py --profile).  Pass NULL to switch it off. */
+MPHSIR_API void mphsir_debug_tc_counters(long long* buf);
 MPHSIR_API size_t mphsir_bimg_bytes(int N, int K);
 MPHSIR_API int mphsir_pack_bimg(const float* W, int ld, int transposed, long long w_batch_stride, void* img,
                                 int batch, int N, int K, void* stream);

@@ -139,6 +139,10 @@ constexpr int STG_LD = 36;              // staging row stride in floats (16-byte
 constexpr int STG_FLOATS = 32 * STG_LD;
 constexpr int MAX_RING = 8;
 
+// optional in-kernel cycle accounting (one lane per role; p.dbg == NULL in production)
+#define TC_T0() (p.dbg ? clock64() : 0)
+#define TC_ACC(var, t0) do { if (p.dbg) var += clock64() - (t0); } while (0)
+
 struct Smem {
   // barriers first (8-byte aligned), rings after (1024-byte aligned, carved dynamically)
   uint64_t a_full[MAX_RING], a_empty[MAX_RING], b_full[MAX_RING], b_empty[MAX_RING];
@@ -202,6 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
     // =============================== B loader ===============================================
     if (lane == 0) {
       uint32_t it = 0;
+      long long t_wait = 0, t_all0 = TC_T0();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const uint8_t* bimg = reinterpret_cast<const uint8_t*>(p.Bimg);
         if (p.tiles_per_batch > 0) bimg += (size_t)(tile / p.tiles_per_batch) * p.b_batch_bytes;
@@ -209,7 +214,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
           for (int s = 0; s < Ks; ++s) {
             for (int j = TPP * pass; j < min(NT, TPP * pass + TPP); ++j, ++it) {
               const int slot = it % p.nb;
+              const long long tw = TC_T0();
               mbar_wait(smem_u32(&sm->b_empty[slot]), ((it / p.nb) & 1) ^ 1);
+              TC_ACC(t_wait, tw);
               const int rows = min(BN, p.Np - j * BN);
               const uint32_t bytes = rows * 128;
               const uint32_t full = smem_u32(&sm->b_full[slot]);
@@ -222,19 +229,27 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
           }
         }
       }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 16 + 0] = clock64() - t_all0;
+        p.dbg[blockIdx.x * 16 + 1] = t_wait;
+      }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =============================================
     if (lane == 0) {
       uint32_t a_it = 0, b_it = 0, acc_it = 0;
+      long long t_acc = 0, t_a = 0, t_b = 0, t_all0 = TC_T0();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const uint32_t a_base = a_it;
         for (int pass = 0; pass < npass; ++pass, ++acc_it) {
           const int buf = acc_it & 1;
+          long long tw = TC_T0();
           mbar_wait(smem_u32(&sm->acc_empty[buf]), ((acc_it >> 1) & 1) ^ 1);
+          TC_ACC(t_acc, tw);
           tc_fence_after();
           for (int s = 0; s < Ks; ++s) {
             uint32_t a_slot;
+            tw = TC_T0();
             if (stationary) {
               a_slot = (a_base + s) % p.na;
               if (pass == 0) mbar_wait(smem_u32(&sm->a_full[a_slot]), ((a_base + s) / p.na) & 1);
@@ -242,11 +257,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
               a_slot = a_it % p.na;
               mbar_wait(smem_u32(&sm->a_full[a_slot]), (a_it / p.na) & 1);
             }
+            TC_ACC(t_a, tw);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(a_ring + (size_t)a_slot * a_slot_bytes);
             for (int j = TPP * pass; j < min(NT, TPP * pass + TPP); ++j, ++b_it) {
               const int b_slot = b_it % p.nb;
+              tw = TC_T0();
               mbar_wait(smem_u32(&sm->b_full[b_slot]), (b_it / p.nb) & 1);
+              TC_ACC(t_b, tw);
               tc_fence_after();
               const uint32_t b_addr = smem_u32(b_ring + (size_t)b_slot * b_slot_bytes);
               const int ncols = min(BN, p.Np - j * BN);
@@ -274,6 +292,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
         }
         if (stationary) a_it += Ks;
       }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 16 + 2] = clock64() - t_all0;
+        p.dbg[blockIdx.x * 16 + 3] = t_acc;
+        p.dbg[blockIdx.x * 16 + 4] = t_a;
+        p.dbg[blockIdx.x * 16 + 5] = t_b;
+      }
     }
   } else if (warp < kFirstConvWarp) {
     // =============================== epilogue (warps 2..9) ==================================
@@ -285,6 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
     float* stg = staging + (warp - 2) * STG_FLOATS;
     const int c4 = lane & 7, rsub = lane >> 3;
     uint32_t acc_it = 0;
+    long long t_wait = 0, t_tmem = 0, t_all0 = TC_T0();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m0, m_end;
       tile_rows(p, tile, m0, m_end);
@@ -327,12 +352,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
 
       for (int pass = 0; pass < npass; ++pass, ++acc_it) {
         const int buf = acc_it & 1;
+        long long tw = TC_T0();
         mbar_wait(smem_u32(&sm->acc_full[buf]), (acc_it >> 1) & 1);
+        TC_ACC(t_wait, tw);
         tc_fence_after();
         const int ncols_pass = min(PASS_COLS, p.Np - pass * PASS_COLS);
         for (int c0 = half * 32; c0 < ncols_pass; c0 += 64) {
           const int n0 = pass * PASS_COLS + c0;
           uint32_t r[32];
+          tw = TC_T0();
           asm volatile(
               "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -368,6 +396,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
           float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.bias != nullptr && col_ok) bias4 = ldg4(p.bias + n);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          TC_ACC(t_tmem, tw);
           __syncwarp();  // previous chunk's smem reads are done
 #pragma unroll
           for (int q = 0; q < 8; ++q)
@@ -440,6 +469,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
         if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[buf]));
       }
     }
+    if (p.dbg && warp == 2 && lane == 0) {
+      p.dbg[blockIdx.x * 16 + 6] = clock64() - t_all0;
+      p.dbg[blockIdx.x * 16 + 7] = t_wait;
+      p.dbg[blockIdx.x * 16 + 8] = t_tmem;
+    }
   } else {
     // =============================== A converters (warps 10..17) ============================
     // Two independent groups of 4 warps.  Stationary tiles alternate between the groups (group g converts
@@ -454,6 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
     // ahead): whole tiles alternate when a tile pair tiles the ring exactly, otherwise slabs alternate
     // (slot parity == slab-counter parity because the ring depth is even).
     const bool tile_alt = stationary && (p.na % (2 * Ks) == 0);
+    long long t_slot = 0, t_ld = 0, t_all0 = TC_T0();
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       if (tile_alt && (lt & 1) != cg) continue;
@@ -512,6 +547,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
           }
           // issue every global load of this slab before waiting for the smem slot
           float4 v0[8], v1[8];
+          long long tw = TC_T0();
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int m = m0 + rbase + 16 * i;
@@ -544,7 +580,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
             e0 = ldg4(p.ln_b + k); e1 = ldg4(p.ln_b + k + 4);
           }
           const int slot = a_it % p.na;
+          long long tw2 = TC_T0();
           mbar_wait(smem_u32(&sm->a_empty[slot]), ((a_it / p.na) & 1) ^ 1);
+          TC_ACC(t_slot, tw2);
           uint8_t* dst = a_ring + (size_t)slot * a_slot_bytes;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -568,8 +606,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&sm->a_full[slot]));
+          TC_ACC(t_ld, tw);
         }
       }
+    }
+    if (p.dbg && gt == 0) {
+      p.dbg[blockIdx.x * 16 + 9 + 3 * cg] = clock64() - t_all0;
+      p.dbg[blockIdx.x * 16 + 10 + 3 * cg] = t_slot;
+      p.dbg[blockIdx.x * 16 + 11 + 3 * cg] = t_ld;
     }
   }
 
@@ -642,7 +686,11 @@ static int launch_epi(const TcArgs& a, size_t smem, int grid, cudaStream_t st) {
   return launch_epi2<EPI, false>(a, smem, grid, st);
 }
 
+static long long* g_dbg = nullptr;
+void set_debug_buffer(long long* p) { g_dbg = p; }
+
 int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
+  a.dbg = g_dbg;
   static int sm_count = 0;
   if (sm_count == 0) {
     int dev = 0;
@@ -675,6 +723,8 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
 }  // namespace mphsir
 
 using namespace mphsir;
+
+extern "C" MPHSIR_API void mphsir_debug_tc_counters(long long* buf) { tc::set_debug_buffer(buf); }
 
 extern "C" size_t mphsir_bimg_bytes(int N, int K) {
   const int Np = (N + 15) / 16 * 16, Ks = (K + 63) / 64;

@@ -45,9 +45,11 @@ struct TcArgs {
   const float* row_scale;
   int Cin;
   const float* R;
+  long long* dbg;  // optional [grid][16] cycle counters (tools/gemm_bench.py --profile); NULL in production
 };
 
 int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st);
+void set_debug_buffer(long long* p);
 
 }  // namespace tc
 }  // namespace mphsir
