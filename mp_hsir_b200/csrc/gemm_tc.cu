@@ -18,6 +18,7 @@
 //                                -> k-slab (64) -> n-tile (128 columns) -> 4 x {1|3} MMAs (K=16 each)
 // If all k-slabs of a tile fit the A ring (K <= 256) the tile is converted once and reused by every pass.
 #include <cuda_bf16.h>
+#include <cudaTypedefs.h>
 
 #include "common.cuh"
 #include "gemm_tc.cuh"
@@ -60,6 +61,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -127,10 +139,14 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kThreads = 576;  // warp 0: B loader, warp 1: MMA + TMEM owner, warps 2-9: epilogue, warps 10-17: converters
+// warp 0: B loader, warp 1: MMA + TMEM owner, warps 2-9: epilogue, warps 10-17: converters, warp 18: A loader
+constexpr int kThreads = 608;
 constexpr int kConvThreads = 256;
 constexpr int kEpiWarps = 8;
 constexpr int kFirstConvWarp = 10;
+constexpr int kLoaderWarp = 18;
+constexpr int NSTAGE = 2;                 // fp32 staging slabs (128 rows x 64 floats = 32 KB each)
+constexpr int STAGE_BYTES = 128 * 64 * 4;
 constexpr int SLAB_BYTES = 128 * 128;   // one part (hi or lo) of a 128-row x 64-k A slab
 constexpr int BN = 64;                  // columns per B block / per MMA instruction
 constexpr int BBLK_BYTES = BN * 128;    // one part of a 64-row x 64-k B block
@@ -147,6 +163,7 @@ struct Smem {
   // barriers first (8-byte aligned), rings after (1024-byte aligned, carved dynamically)
   uint64_t a_full[MAX_RING], a_empty[MAX_RING], b_full[MAX_RING], b_empty[MAX_RING];
   uint64_t acc_full[2], acc_empty[2];
+  uint64_t stage_full[NSTAGE], stage_empty[NSTAGE];
   uint32_t tmem_base;
 };
 
@@ -162,7 +179,7 @@ __device__ __forceinline__ void tile_rows(const TcArgs& p, int tile, int& m0, in
 }
 
 template <int EPI, bool LN>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcArgs p) {
   constexpr bool CONV = EPI >= TC_OUT_TOKENS;
   // NCHW / pixel-unshuffle stores are already coalesced (or hopeless) in the row-per-thread TMEM mapping
   constexpr bool DIRECT = (EPI == TC_OUT_NCHW_RES || EPI == TC_OUT_UNSHUFFLE);
@@ -174,6 +191,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
   uint8_t* a_ring = smem_raw + 1024;
   uint8_t* b_ring = a_ring + (size_t)p.na * a_slot_bytes;
   float* staging = reinterpret_cast<float*>(b_ring + (size_t)p.nb * b_slot_bytes);
+  uint8_t* a_stage = reinterpret_cast<uint8_t*>(staging) + (size_t)kEpiWarps * STG_FLOATS * sizeof(float);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Ks = p.ks;
@@ -184,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_RING; ++i) {
-      mbar_init(smem_u32(&sm->a_full[i]), kConvThreads / 64);  // one converter group (4 warps) fills a slab
+      mbar_init(smem_u32(&sm->a_full[i]), kConvThreads / 32);
       mbar_init(smem_u32(&sm->a_empty[i]), 1);
       mbar_init(smem_u32(&sm->b_full[i]), 1);
       mbar_init(smem_u32(&sm->b_empty[i]), 1);
@@ -192,6 +210,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&sm->acc_full[i]), 1);
       mbar_init(smem_u32(&sm->acc_empty[i]), kEpiWarps);
+    }
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(smem_u32(&sm->stage_full[i]), 1);
+      mbar_init(smem_u32(&sm->stage_empty[i]), kConvThreads / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -474,53 +496,172 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
       p.dbg[blockIdx.x * 16 + 7] = t_wait;
       p.dbg[blockIdx.x * 16 + 8] = t_tmem;
     }
-  } else {
-    // =============================== A converters (warps 10..17) ============================
-    // Two independent groups of 4 warps.  Stationary tiles alternate between the groups (group g converts
-    // local tiles with parity g), streamed slabs alternate slab by slab: while one group converts, the
-    // other has its global loads in flight, so ~64 KB of reads are outstanding per SM.
-    const int cg = (warp - kFirstConvWarp) >> 2;
-    const int gt = threadIdx.x - (kFirstConvWarp + 4 * cg) * 32;  // 0..127 inside the group
-    const int chunk = gt & 7;              // 8-element (16-byte bf16) chunk inside the 64-k slab
-    const int rbase = gt >> 3;             // rows rbase + 16*i, i = 0..7
-    constexpr bool has_ln = LN;
-    // A ring slot must always be refilled by the same group (an mbarrier parity wait is only safe one phase
-    // ahead): whole tiles alternate when a tile pair tiles the ring exactly, otherwise slabs alternate
-    // (slot parity == slab-counter parity because the ring depth is even).
-    const bool tile_alt = stationary && (p.na % (2 * Ks) == 0);
-    long long t_slot = 0, t_ld = 0, t_all0 = TC_T0();
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      if (tile_alt && (lt & 1) != cg) continue;
+  } else if (warp == kLoaderWarp) {
+    // =============================== A loader (TMA bulk copies, warp 18) ====================
+    // Streams raw fp32 rows of A into the staging slabs: one cp.async.bulk per (row, contiguous k segment),
+    // all landing on the slab's stage_full mbarrier.  Runs up to NSTAGE slabs (64 KB) ahead of the converters,
+    // so the memory-level parallelism lives in shared memory instead of registers.
+    uint32_t st_it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m0, m_end;
       tile_rows(p, tile, m0, m_end);
-      // LayerNorm statistics: the 8 lanes that share a row reduce sum / sum-of-squares over K.
-      float mean[8], rstd[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        mean[i] = 0.f;
-        rstd[i] = 1.f;
-      }
-      if (has_ln) {
-        float sm_[8], sq_[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sm_[i] = sq_[i] = 0.f;
-        for (int k = chunk * 4; k < p.Ka; k += 32) {
-          float4 v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int m = m0 + rbase + 16 * i;
-            v[i] = (m < m_end) ? ldg4(p.A + (size_t)(p.a_row_mod > 0 ? m % p.a_row_mod : m) * p.lda + k)
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int conv_passes = stationary ? 1 : npass;
+      for (int pass = 0; pass < conv_passes; ++pass) {
+        for (int s = 0; s < Ks; ++s, ++st_it) {
+          const int st = st_it % NSTAGE;
+          mbar_wait(smem_u32(&sm->stage_empty[st]), ((st_it / NSTAGE) & 1) ^ 1);
+          const uint32_t full = smem_u32(&sm->stage_full[st]);
+          uint8_t* dst = a_stage + (size_t)st * STAGE_BYTES;
+          const int k0 = s * 64;
+          const int kend = min(k0 + 64, p.Ka);
+          if (p.a_mode == A_TMAP2D) {
+            // one TMA box [128 rows x 64 floats]; rows beyond M and columns beyond K are zero-filled by the TMA unit
+            if (lane == 0) {
+              mbar_expect_tx(full, STAGE_BYTES);
+              const int row = p.a_row_mod > 0 ? m0 % p.a_row_mod : m0;
+              tma_load_2d(smem_u32(dst), &p.tmA, k0, row, full);
+            }
+            __syncwarp();
+            continue;
           }
+          if (p.a_mode == A_TMAP4D) {
+            // conv: one box [by x bx pixels x seg channels] per (tap, channel segment); the zero padding of the
+            // 3x3 conv is the TMA out-of-bounds fill (coordinates -1 / W / H)
+            if (lane == 0) {
+              const int hw = p.H * p.W;
+              const int b = m0 / hw, rem = m0 - b * hw;
+              const int y0 = rem / p.W, x0 = rem - y0 * p.W;
+              const int nsub = (kend - k0) / p.seg;
+              const uint32_t sub_bytes = 128u * p.seg * 4u;
+              mbar_expect_tx(full, nsub * sub_bytes);
+              for (int j = 0; j < nsub; ++j) {
+                const int k = k0 + j * p.seg;
+                const int tap = k / p.Cin, cc = k - tap * p.Cin;
+                tma_load_4d(smem_u32(dst + j * sub_bytes), &p.tmA, cc, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b, full);
+              }
+            }
+            __syncwarp();
+            continue;
+          }
+          // pass 1: bytes this lane will copy (rows lane, lane+32, lane+64, lane+96)
+          uint32_t bytes = 0;
+          if (!CONV) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            sm_[i] += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-            sq_[i] += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+            for (int i = 0; i < 4; ++i)
+              if (m0 + lane + 32 * i < m_end) bytes += (uint32_t)(kend - k0) * 4u;
+          } else {
+            const int hw = p.H * p.W;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int m = m0 + lane + 32 * i;
+              if (m >= m_end) continue;
+              const int b = m / hw, rem = m - b * hw;
+              const int y = rem / p.W, x = rem - y * p.W;
+              for (int k = k0; k < kend;) {
+                const int tap = k / p.Cin, cc = k - tap * p.Cin;
+                const int len = min(p.Cin - cc, kend - k);
+                const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+                if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) bytes += (uint32_t)len * 4u;
+                k += len;
+              }
+            }
+          }
+          uint32_t total = bytes;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+          if (lane == 0) {
+            if (total > 0) mbar_expect_tx(full, total);
+            else mbar_arrive(full);
+          }
+          __syncwarp();
+          // pass 2: issue the copies
+          if (!CONV) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = lane + 32 * i, m = m0 + r;
+              if (m < m_end) {
+                const float* src = p.A + (size_t)(p.a_row_mod > 0 ? m % p.a_row_mod : m) * p.lda + k0;
+                bulk_g2s(smem_u32(dst + r * 256), src, (uint32_t)(kend - k0) * 4u, full);
+              }
+            }
+          } else {
+            const int hw = p.H * p.W;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = lane + 32 * i, m = m0 + r;
+              if (m >= m_end) continue;
+              const int b = m / hw, rem = m - b * hw;
+              const int y = rem / p.W, x = rem - y * p.W;
+              for (int k = k0; k < kend;) {
+                const int tap = k / p.Cin, cc = k - tap * p.Cin;
+                const int len = min(p.Cin - cc, kend - k);
+                const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+                if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+                  const float* src = p.A + ((size_t)(b * p.H + yy) * p.W + xx) * p.lda + cc;
+                  bulk_g2s(smem_u32(dst + r * 256 + (k - k0) * 4), src, (uint32_t)len * 4u, full);
+                }
+                k += len;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // =============================== A converters (warps 10..17) ============================
+    // fp32 staging slab -> (LayerNorm) -> bf16 hi/lo split -> 128B-swizzled K-major MMA slab.
+    const int ct = threadIdx.x - kFirstConvWarp * 32;  // 0..255
+    const int chunk = ct & 7;              // 8-element (16-byte bf16) chunk inside the 64-k slab
+    const int rbase = ct >> 3;             // rows rbase + 32*i, i = 0..3
+    constexpr bool has_ln = LN;
+    const bool ln_from_stage = has_ln && Ks <= NSTAGE;
+    long long t_slot = 0, t_ld = 0, t_all0 = TC_T0();
+    uint32_t a_it = 0, st_it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m0, m_end;
+      tile_rows(p, tile, m0, m_end);
+      float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f};
+      if (has_ln) {
+        float sm_[4] = {0.f, 0.f, 0.f, 0.f}, sq_[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ln_from_stage) {
+          // the whole row (K <= 128) is resident in the staging slabs: statistics straight from smem
+          for (int s = 0; s < Ks; ++s) {
+            const int st = (st_it + s) % NSTAGE;
+            mbar_wait(smem_u32(&sm->stage_full[st]), ((st_it + s) / NSTAGE) & 1);
+            const int k = s * 64 + chunk * 8;
+            if (k < p.Ka) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int r = rbase + 32 * i;
+                if (m0 + r < m_end) {
+                  const float* sp = reinterpret_cast<const float*>(a_stage + (size_t)st * STAGE_BYTES + r * 256 + chunk * 32);
+                  const float4 a = *reinterpret_cast<const float4*>(sp);
+                  const float4 b = *reinterpret_cast<const float4*>(sp + 4);
+                  sm_[i] += ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+                  sq_[i] += ((a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w)) +
+                            ((b.x * b.x + b.y * b.y) + (b.z * b.z + b.w * b.w));
+                }
+              }
+            }
+          }
+        } else {
+          for (int k = chunk * 4; k < p.Ka; k += 32) {
+            float4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int m = m0 + rbase + 32 * i;
+              v[i] = (m < m_end) ? ldg4(p.A + (size_t)(p.a_row_mod > 0 ? m % p.a_row_mod : m) * p.lda + k)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              sm_[i] += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+              sq_[i] += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+            }
           }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
 #pragma unroll
           for (int o = 4; o > 0; o >>= 1) {
             sm_[i] += __shfl_xor_sync(0xffffffffu, sm_[i], o);
@@ -533,41 +674,51 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
       }
       const int conv_passes = stationary ? 1 : npass;
       for (int pass = 0; pass < conv_passes; ++pass) {
-        for (int s = 0; s < Ks; ++s) {
-          const uint32_t a_it = stationary ? (uint32_t)(lt * Ks + s) : (uint32_t)((lt * npass + pass) * Ks + s);
-          if (!tile_alt && (int)(a_it & 1) != cg) continue;
+        for (int s = 0; s < Ks; ++s, ++a_it, ++st_it) {
           const int k = s * 64 + chunk * 8;
           const bool kin = k < p.Ka;
-          int dy = 0, dx = 0, cc = 0;
-          if (CONV) {
-            const int tap = k / p.Cin;
-            cc = k - tap * p.Cin;
-            dy = tap / 3 - 1;
-            dx = tap - (tap / 3) * 3 - 1;
-          }
-          // issue every global load of this slab before waiting for the smem slot
-          float4 v0[8], v1[8];
           long long tw = TC_T0();
+          const int st = st_it % NSTAGE;
+          mbar_wait(smem_u32(&sm->stage_full[st]), (st_it / NSTAGE) & 1);
+          TC_ACC(t_ld, tw);
+          // which of this thread's (row, 8-float chunk) cells were actually copied (else: zero)
+          bool ok[4];
+          if (p.a_mode != A_ROWCOPY) {
+            // TMA boxes are complete (hardware zero fill); only whole segments beyond K are absent
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int m = m0 + rbase + 16 * i;
-            bool ok = kin && m < m_end;
-            const float* src = p.A;
-            if (CONV) {
-              const int hw = p.H * p.W;
-              const int mm = ok ? m : m0;
-              const int b = mm / hw;
-              const int rem = mm - b * hw;
-              const int y = rem / p.W, x = rem - y * p.W;
-              const int yy = y + dy, xx = x + dx;
-              ok = ok && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
-              src = p.A + ((size_t)(b * p.H + yy) * p.W + xx) * p.lda + cc;
-            } else if (ok) {
-              src = p.A + (size_t)(p.a_row_mod > 0 ? m % p.a_row_mod : m) * p.lda + k;
+            for (int i = 0; i < 4; ++i) ok[i] = kin;
+          } else if (!CONV) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ok[i] = kin && (m0 + rbase + 32 * i < m_end);
+          } else {
+            const int tap = k / p.Cin;
+            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+            const int hw = p.H * p.W;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int m = m0 + rbase + 32 * i;
+              ok[i] = kin && m < m_end;
+              if (ok[i]) {
+                const int b = m / hw, rem = m - b * hw;
+                const int y = rem / p.W, x = rem - y * p.W;
+                const int yy = y + dy, xx = x + dx;
+                ok[i] = yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+              }
             }
-            if (ok) {
-              v0[i] = ldg4(src);
-              v1[i] = ldg4(src + 4);
+          }
+          float4 v0[4], v1[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = rbase + 32 * i;
+            if (ok[i]) {
+              int off = r * 256 + chunk * 32;
+              if (p.a_mode == A_TMAP4D) {
+                const int kl = chunk * 8, sub = kl / p.seg;
+                off = (sub * 128 + r) * p.seg * 4 + (kl - sub * p.seg) * 4;
+              }
+              const float* sp = reinterpret_cast<const float*>(a_stage + (size_t)st * STAGE_BYTES + off);
+              v0[i] = *reinterpret_cast<const float4*>(sp);
+              v1[i] = *reinterpret_cast<const float4*>(sp + 4);
             } else {
               v0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
               v1[i] = v0[i];
@@ -585,9 +736,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
           TC_ACC(t_slot, tw2);
           uint8_t* dst = a_ring + (size_t)slot * a_slot_bytes;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = rbase + 16 * i;
-            if (has_ln && kin && m0 + r < m_end) {
+          for (int i = 0; i < 4; ++i) {
+            const int r = rbase + 32 * i;
+            if (has_ln && ok[i]) {
               const float a = rstd[i], mu = mean[i];
               v0[i].x = (v0[i].x - mu) * a * g0.x + e0.x; v0[i].y = (v0[i].y - mu) * a * g0.y + e0.y;
               v0[i].z = (v0[i].z - mu) * a * g0.z + e0.z; v0[i].w = (v0[i].w - mu) * a * g0.w + e0.w;
@@ -605,15 +756,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs p) {
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&sm->a_full[slot]));
-          TC_ACC(t_ld, tw);
+          if (lane == 0) {
+            mbar_arrive(smem_u32(&sm->a_full[slot]));
+            mbar_arrive(smem_u32(&sm->stage_empty[st]));
+          }
         }
       }
     }
-    if (p.dbg && gt == 0) {
-      p.dbg[blockIdx.x * 16 + 9 + 3 * cg] = clock64() - t_all0;
-      p.dbg[blockIdx.x * 16 + 10 + 3 * cg] = t_slot;
-      p.dbg[blockIdx.x * 16 + 11 + 3 * cg] = t_ld;
+    if (p.dbg && ct == 0) {
+      p.dbg[blockIdx.x * 16 + 9] = clock64() - t_all0;
+      p.dbg[blockIdx.x * 16 + 10] = t_slot;
+      p.dbg[blockIdx.x * 16 + 11] = t_ld;
     }
   }
 
@@ -662,7 +815,8 @@ __global__ void __launch_bounds__(256) pack_bimg_kernel(const float* __restrict_
 }
 
 static size_t smem_bytes(int na, int nb, int parts) {
-  return 1024 + (size_t)na * SLAB_BYTES * parts + (size_t)nb * BBLK_BYTES * parts + (size_t)kEpiWarps * STG_FLOATS * sizeof(float);
+  return 1024 + (size_t)na * SLAB_BYTES * parts + (size_t)nb * BBLK_BYTES * parts +
+         (size_t)kEpiWarps * STG_FLOATS * sizeof(float) + (size_t)NSTAGE * STAGE_BYTES;
 }
 
 template <int EPI, bool LN>
@@ -686,6 +840,65 @@ static int launch_epi(const TcArgs& a, size_t smem, int grid, cudaStream_t st) {
   return launch_epi2<EPI, false>(a, smem, grid, st);
 }
 
+static PFN_cuTensorMapEncodeTiled get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// Describe the fp32 A operand to the TMA unit.  Returns false when the shape has no box decomposition
+// (the loader then falls back to per-row bulk copies).
+static bool make_a_tensor_map(TcArgs& a, bool conv) {
+  PFN_cuTensorMapEncodeTiled enc = get_encode_fn();
+  if (enc == nullptr) return false;
+  if (!conv) {
+    const cuuint64_t rows = a.a_row_mod > 0 ? (cuuint64_t)a.a_row_mod : (cuuint64_t)a.M;
+    cuuint64_t gdim[2] = {(cuuint64_t)a.Ka, rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)a.lda * 4};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    a.seg = 64;
+    if (enc(&a.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.A), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+    a.a_mode = A_TMAP2D;
+    return true;
+  }
+  const int hw = a.H * a.W;
+  const int rows = hw < 128 ? hw : 128;
+  int bx, by;
+  if (a.W >= rows) {
+    if (a.W % rows != 0) return false;
+    bx = rows;
+    by = 1;
+  } else {
+    if (rows % a.W != 0) return false;
+    bx = a.W;
+    by = rows / a.W;
+  }
+  if (hw % rows != 0) return false;
+  int seg = 64;
+  while (a.Cin % seg != 0) seg >>= 1;
+  if (seg < 8) return false;
+  const int B = a.M / hw;
+  cuuint64_t gdim[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)a.lda * 4, (cuuint64_t)a.W * a.lda * 4, (cuuint64_t)hw * a.lda * 4};
+  cuuint32_t box[4] = {(cuuint32_t)seg, (cuuint32_t)bx, (cuuint32_t)by, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (enc(&a.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.A), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  a.seg = seg;
+  a.box_w = bx;
+  a.a_mode = A_TMAP4D;
+  return true;
+}
+
 static long long* g_dbg = nullptr;
 void set_debug_buffer(long long* p) { g_dbg = p; }
 
@@ -697,11 +910,19 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
   }
-  // shared-memory plan (227 KB): 1 KB barriers + A ring + B ring + 36 KB epilogue staging
-  //   bf16x3: A 4 x 32 KB, B 3 x 16 KB (213 KB)      bf16x1: A 8 x 16 KB, B 6 x 8 KB (213 KB)
-  a.na = a.parts == 2 ? 4 : 8;
+  // shared-memory plan (227 KB): 1 KB barriers + bf16 A ring + B ring + 36 KB epilogue staging + 2 x 32 KB fp32
+  // A staging (the TMA landing zone).   bf16x3: A 2 x 32 KB, B 3 x 16 KB (213 KB)   bf16x1: A 4 x 16 KB, B 6 x 8 KB
+  a.na = a.parts == 2 ? 2 : 4;
   a.nb = a.parts == 2 ? 3 : 6;
   const size_t smem = smem_bytes(a.na, a.nb, a.parts);
+  a.a_mode = A_ROWCOPY;
+  a.seg = 64;
+  if (conv) {
+    // conv tiles never straddle samples so that a tile is a box of the [B,H,W,C] tensor
+    a.tiles_per_batch = (a.rows_per_batch + 127) / 128;
+    a.num_tiles = (a.M / a.rows_per_batch) * a.tiles_per_batch;
+  }
+  make_a_tensor_map(a, conv);
   const int grid = a.num_tiles < sm_count ? a.num_tiles : sm_count;
   if (conv && a.epi == MPHSIR_EPI_BIAS) a.epi = TC_OUT_TOKENS;
   switch (a.epi) {

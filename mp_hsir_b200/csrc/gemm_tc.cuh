@@ -1,5 +1,6 @@
 // Shared declarations of the tcgen05 GEMM engine (gemm_tc.cu) and its callers.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -15,7 +16,13 @@ __host__ __device__ inline size_t bimg_offset(int part, int s, int n, int c, int
   return ((size_t)(part * Ks + s) * Np + n) * 128 + (size_t)((c ^ (n & 7)) << 4);
 }
 
+enum { A_ROWCOPY = 0, A_TMAP2D = 1, A_TMAP4D = 2 };  // how the A loader warp fetches fp32 rows
+
 struct TcArgs {
+  alignas(64) CUtensorMap tmA;  // TMA descriptor of the fp32 A operand (2-D [M,K] or 4-D [B,H,W,C])
+  int a_mode;                   // A_*
+  int seg;                      // floats per TMA box row (64 for GEMMs, gcd(Cin,64) for convs)
+  int box_w;                    // conv: pixels per box row (min(W,128))
   const float* A;
   long long lda;
   int a_row_mod;
