@@ -145,8 +145,7 @@ constexpr int kConvThreads = 256;
 constexpr int kEpiWarps = 8;
 constexpr int kFirstConvWarp = 10;
 constexpr int kLoaderWarp = 18;
-constexpr int NSTAGE = 2;                 // fp32 staging slabs (128 rows x 64 floats = 32 KB each)
-constexpr int STAGE_BYTES = 128 * 64 * 4;
+constexpr int STAGE_BYTES = 128 * 64 * 4; // an A ring slot: fp32 TMA landing zone (32 KB), converted IN PLACE to bf16 hi|lo
 constexpr int SLAB_BYTES = 128 * 128;   // one part (hi or lo) of a 128-row x 64-k A slab
 constexpr int BN = 64;                  // columns per B block / per MMA instruction
 constexpr int BBLK_BYTES = BN * 128;    // one part of a 64-row x 64-k B block
@@ -163,7 +162,7 @@ struct Smem {
   // barriers first (8-byte aligned), rings after (1024-byte aligned, carved dynamically)
   uint64_t a_full[MAX_RING], a_empty[MAX_RING], b_full[MAX_RING], b_empty[MAX_RING];
   uint64_t acc_full[2], acc_empty[2];
-  uint64_t stage_full[NSTAGE], stage_empty[NSTAGE];
+  uint64_t stage_full[MAX_RING];  // TMA landed the fp32 slab (a_full: converted to bf16; a_empty: MMAs done)
   uint32_t tmem_base;
 };
 
@@ -186,12 +185,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem* sm = reinterpret_cast<Smem*>(smem_raw);
   const int parts = p.parts;                       // 1 (bf16x1) or 2 (bf16x3)
-  const int a_slot_bytes = SLAB_BYTES * parts;
+  const int a_slot_bytes = STAGE_BYTES;
   const int b_slot_bytes = BBLK_BYTES * parts;
   uint8_t* a_ring = smem_raw + 1024;
   uint8_t* b_ring = a_ring + (size_t)p.na * a_slot_bytes;
   float* staging = reinterpret_cast<float*>(b_ring + (size_t)p.nb * b_slot_bytes);
-  uint8_t* a_stage = reinterpret_cast<uint8_t*>(staging) + (size_t)kEpiWarps * STG_FLOATS * sizeof(float);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Ks = p.ks;
@@ -211,10 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       mbar_init(smem_u32(&sm->acc_full[i]), 1);
       mbar_init(smem_u32(&sm->acc_empty[i]), kEpiWarps);
     }
-    for (int i = 0; i < NSTAGE; ++i) {
-      mbar_init(smem_u32(&sm->stage_full[i]), 1);
-      mbar_init(smem_u32(&sm->stage_empty[i]), kConvThreads / 32);
-    }
+    for (int i = 0; i < MAX_RING; ++i) mbar_init(smem_u32(&sm->stage_full[i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&sm->tmem_base), 512);
@@ -463,7 +458,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 *reinterpret_cast<float4*>(p.Y + (size_t)m * p.ldy + n) = o;
               } else if (EPI == MPHSIR_EPI_GLU) {
                 // packed columns (2j, 2j+1) = (value_j, gate_j)
-                const float2 o = make_float2(v.x * gelu_erf(v.y), v.z * gelu_erf(v.w));
+                const float2 o = make_float2(v.x * gelu_erf_fast(v.y), v.z * gelu_erf_fast(v.w));
                 *reinterpret_cast<float2*>(p.Y + (size_t)m * p.ldy + (n >> 1)) = o;
               } else if (EPI == MPHSIR_EPI_SPECTRAL) {
                 const float sc = scl[it];
@@ -498,8 +493,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
   } else if (warp == kLoaderWarp) {
     // =============================== A loader (TMA bulk copies, warp 18) ====================
-    // Streams raw fp32 rows of A into the staging slabs: one cp.async.bulk per (row, contiguous k segment),
-    // all landing on the slab's stage_full mbarrier.  Runs up to NSTAGE slabs (64 KB) ahead of the converters,
+    // Streams raw fp32 slabs of A into the ring slots (TMA tensor-map boxes; per-row bulk copies as the general
+    // fallback), landing on the slot's stage_full mbarrier.  It runs as far ahead as the ring allows (4 x 32 KB),
     // so the memory-level parallelism lives in shared memory instead of registers.
     uint32_t st_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -508,10 +503,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       const int conv_passes = stationary ? 1 : npass;
       for (int pass = 0; pass < conv_passes; ++pass) {
         for (int s = 0; s < Ks; ++s, ++st_it) {
-          const int st = st_it % NSTAGE;
-          mbar_wait(smem_u32(&sm->stage_empty[st]), ((st_it / NSTAGE) & 1) ^ 1);
+          const int st = st_it % p.na;
+          mbar_wait(smem_u32(&sm->a_empty[st]), ((st_it / p.na) & 1) ^ 1);
           const uint32_t full = smem_u32(&sm->stage_full[st]);
-          uint8_t* dst = a_stage + (size_t)st * STAGE_BYTES;
+          uint8_t* dst = a_ring + (size_t)st * STAGE_BYTES;
           const int k0 = s * 64;
           const int kend = min(k0 + 64, p.Ka);
           if (p.a_mode == A_TMAP2D) {
@@ -532,7 +527,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               const int b = m0 / hw, rem = m0 - b * hw;
               const int y0 = rem / p.W, x0 = rem - y0 * p.W;
               const int nsub = (kend - k0) / p.seg;
-              const uint32_t sub_bytes = 128u * p.seg * 4u;
+              const uint32_t sub_bytes = (uint32_t)p.box_rows * p.seg * 4u;
               mbar_expect_tx(full, nsub * sub_bytes);
               for (int j = 0; j < nsub; ++j) {
                 const int k = k0 + j * p.seg;
@@ -614,9 +609,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int chunk = ct & 7;              // 8-element (16-byte bf16) chunk inside the 64-k slab
     const int rbase = ct >> 3;             // rows rbase + 32*i, i = 0..3
     constexpr bool has_ln = LN;
-    const bool ln_from_stage = has_ln && Ks <= NSTAGE;
+    const bool ln_from_stage = has_ln && stationary;  // the whole row is resident in the ring
     long long t_slot = 0, t_ld = 0, t_all0 = TC_T0();
-    uint32_t a_it = 0, st_it = 0;
+    uint32_t a_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m0, m_end;
       tile_rows(p, tile, m0, m_end);
@@ -626,15 +621,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         if (ln_from_stage) {
           // the whole row (K <= 128) is resident in the staging slabs: statistics straight from smem
           for (int s = 0; s < Ks; ++s) {
-            const int st = (st_it + s) % NSTAGE;
-            mbar_wait(smem_u32(&sm->stage_full[st]), ((st_it + s) / NSTAGE) & 1);
+            const int st = (a_it + s) % p.na;
+            mbar_wait(smem_u32(&sm->stage_full[st]), ((a_it + s) / p.na) & 1);
             const int k = s * 64 + chunk * 8;
             if (k < p.Ka) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int r = rbase + 32 * i;
                 if (m0 + r < m_end) {
-                  const float* sp = reinterpret_cast<const float*>(a_stage + (size_t)st * STAGE_BYTES + r * 256 + chunk * 32);
+                  const float* sp = reinterpret_cast<const float*>(a_ring + (size_t)st * STAGE_BYTES + r * 256 + chunk * 32);
                   const float4 a = *reinterpret_cast<const float4*>(sp);
                   const float4 b = *reinterpret_cast<const float4*>(sp + 4);
                   sm_[i] += ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
@@ -674,19 +669,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
       const int conv_passes = stationary ? 1 : npass;
       for (int pass = 0; pass < conv_passes; ++pass) {
-        for (int s = 0; s < Ks; ++s, ++a_it, ++st_it) {
+        for (int s = 0; s < Ks; ++s, ++a_it) {
           const int k = s * 64 + chunk * 8;
           const bool kin = k < p.Ka;
           long long tw = TC_T0();
-          const int st = st_it % NSTAGE;
-          mbar_wait(smem_u32(&sm->stage_full[st]), (st_it / NSTAGE) & 1);
+          const int st = a_it % p.na;
+          mbar_wait(smem_u32(&sm->stage_full[st]), (a_it / p.na) & 1);
           TC_ACC(t_ld, tw);
           // which of this thread's (row, 8-float chunk) cells were actually copied (else: zero)
           bool ok[4];
           if (p.a_mode != A_ROWCOPY) {
-            // TMA boxes are complete (hardware zero fill); only whole segments beyond K are absent
+            // TMA boxes are complete (hardware zero fill); only whole segments beyond K (and, for images smaller
+            // than a tile, rows beyond the box) are absent
 #pragma unroll
-            for (int i = 0; i < 4; ++i) ok[i] = kin;
+            for (int i = 0; i < 4; ++i) ok[i] = kin && (p.a_mode != A_TMAP4D || rbase + 32 * i < p.box_rows);
           } else if (!CONV) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) ok[i] = kin && (m0 + rbase + 32 * i < m_end);
@@ -714,9 +710,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               int off = r * 256 + chunk * 32;
               if (p.a_mode == A_TMAP4D) {
                 const int kl = chunk * 8, sub = kl / p.seg;
-                off = (sub * 128 + r) * p.seg * 4 + (kl - sub * p.seg) * 4;
+                off = (sub * p.box_rows + r) * p.seg * 4 + (kl - sub * p.seg) * 4;
               }
-              const float* sp = reinterpret_cast<const float*>(a_stage + (size_t)st * STAGE_BYTES + off);
+              const float* sp = reinterpret_cast<const float*>(a_ring + (size_t)st * STAGE_BYTES + off);
               v0[i] = *reinterpret_cast<const float4*>(sp);
               v1[i] = *reinterpret_cast<const float4*>(sp + 4);
             } else {
@@ -730,9 +726,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             g0 = ldg4(p.ln_g + k); g1 = ldg4(p.ln_g + k + 4);
             e0 = ldg4(p.ln_b + k); e1 = ldg4(p.ln_b + k + 4);
           }
-          const int slot = a_it % p.na;
+          const int slot = st;
+          // in-place conversion: every converter thread has read its fp32 cells; now the slot may be overwritten
           long long tw2 = TC_T0();
-          mbar_wait(smem_u32(&sm->a_empty[slot]), ((a_it / p.na) & 1) ^ 1);
+          asm volatile("bar.sync 1, %0;" ::"n"(kConvThreads) : "memory");
           TC_ACC(t_slot, tw2);
           uint8_t* dst = a_ring + (size_t)slot * a_slot_bytes;
 #pragma unroll
@@ -756,10 +753,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(smem_u32(&sm->a_full[slot]));
-            mbar_arrive(smem_u32(&sm->stage_empty[st]));
-          }
+          if (lane == 0) mbar_arrive(smem_u32(&sm->a_full[slot]));
         }
       }
     }
@@ -815,8 +809,7 @@ __global__ void __launch_bounds__(256) pack_bimg_kernel(const float* __restrict_
 }
 
 static size_t smem_bytes(int na, int nb, int parts) {
-  return 1024 + (size_t)na * SLAB_BYTES * parts + (size_t)nb * BBLK_BYTES * parts +
-         (size_t)kEpiWarps * STG_FLOATS * sizeof(float) + (size_t)NSTAGE * STAGE_BYTES;
+  return 1024 + (size_t)na * STAGE_BYTES + (size_t)nb * BBLK_BYTES * parts + (size_t)kEpiWarps * STG_FLOATS * sizeof(float);
 }
 
 template <int EPI, bool LN>
@@ -894,7 +887,7 @@ static bool make_a_tensor_map(TcArgs& a, bool conv) {
           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return false;
   a.seg = seg;
-  a.box_w = bx;
+  a.box_rows = rows;
   a.a_mode = A_TMAP4D;
   return true;
 }
@@ -910,9 +903,9 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
   }
-  // shared-memory plan (227 KB): 1 KB barriers + bf16 A ring + B ring + 36 KB epilogue staging + 2 x 32 KB fp32
-  // A staging (the TMA landing zone).   bf16x3: A 2 x 32 KB, B 3 x 16 KB (213 KB)   bf16x1: A 4 x 16 KB, B 6 x 8 KB
-  a.na = a.parts == 2 ? 2 : 4;
+  // shared-memory plan (227 KB): 1 KB barriers + A ring 4 x 32 KB (fp32 TMA landing zone, converted in place to
+  // bf16 hi|lo) + B ring (bf16x3: 3 x 16 KB, bf16x1: 6 x 8 KB) + 36 KB epilogue staging = 213 KB
+  a.na = 4;
   a.nb = a.parts == 2 ? 3 : 6;
   const size_t smem = smem_bytes(a.na, a.nb, a.parts);
   a.a_mode = A_ROWCOPY;

@@ -22,7 +22,7 @@ struct TcArgs {
   alignas(64) CUtensorMap tmA;  // TMA descriptor of the fp32 A operand (2-D [M,K] or 4-D [B,H,W,C])
   int a_mode;                   // A_*
   int seg;                      // floats per TMA box row (64 for GEMMs, gcd(Cin,64) for convs)
-  int box_w;                    // conv: pixels per box row (min(W,128))
+  int box_rows;                 // conv: pixels per TMA box (= rows of a tile: min(128, H*W))
   const float* A;
   long long lda;
   int a_row_mod;
