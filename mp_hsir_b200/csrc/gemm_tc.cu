@@ -147,10 +147,10 @@ constexpr int kFirstConvWarp = 10;
 constexpr int kLoaderWarp = 18;
 constexpr int STAGE_BYTES = 128 * 64 * 4; // an A ring slot: fp32 TMA landing zone (32 KB), converted IN PLACE to bf16 hi|lo
 constexpr int SLAB_BYTES = 128 * 128;   // one part (hi or lo) of a 128-row x 64-k A slab
-constexpr int BN = 64;                  // columns per B block / per MMA instruction
-constexpr int BBLK_BYTES = BN * 128;    // one part of a 64-row x 64-k B block
+constexpr int BN = 128;                 // columns per B block / per MMA instruction (N=128: A and B smem reads balance)
+constexpr int BBLK_BYTES = BN * 128;    // one part of a 128-row x 64-k B block
 constexpr int PASS_COLS = 256;          // accumulator columns per pass (x2 buffers = 512 TMEM columns)
-constexpr int STG_LD = 36;              // staging row stride in floats (16-byte aligned, conflict-free)
+constexpr int STG_LD = 32;              // staging rows are dense; 16-byte chunks are XOR-swizzled by (row & 7)
 constexpr int STG_FLOATS = 32 * STG_LD;
 constexpr int MAX_RING = 8;
 
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // =============================== MMA issuer =============================================
     if (lane == 0) {
       uint32_t a_it = 0, b_it = 0, acc_it = 0;
-      long long t_acc = 0, t_a = 0, t_b = 0, t_all0 = TC_T0();
+      long long t_acc = 0, t_a = 0, t_b = 0, t_issue = 0, t_commit = 0, t_all0 = TC_T0();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const uint32_t a_base = a_it;
         for (int pass = 0; pass < npass; ++pass, ++acc_it) {
@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               const int ncols = min(BN, p.Np - j * BN);
               const uint32_t idesc = make_idesc(ncols);
               const uint32_t d_addr = tmem_base + buf * PASS_COLS + (j - TPP * pass) * BN;
+              tw = TC_T0();
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint64_t ah = make_desc(a_addr + k * 32);
@@ -299,7 +300,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                   umma_bf16(d_addr, al, bh, idesc, 1);
                 }
               }
+              TC_ACC(t_issue, tw);
+              tw = TC_T0();
               umma_commit(smem_u32(&sm->b_empty[b_slot]));
+              TC_ACC(t_commit, tw);
             }
             const bool last_use = stationary ? (pass == npass - 1) : true;
             if (last_use) umma_commit(smem_u32(&sm->a_empty[a_slot]));
@@ -314,6 +318,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         p.dbg[blockIdx.x * 16 + 3] = t_acc;
         p.dbg[blockIdx.x * 16 + 4] = t_a;
         p.dbg[blockIdx.x * 16 + 5] = t_b;
+        p.dbg[blockIdx.x * 16 + 12] = t_issue;
+        p.dbg[blockIdx.x * 16 + 13] = t_commit;
       }
     }
   } else if (warp < kFirstConvWarp) {
@@ -417,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           __syncwarp();  // previous chunk's smem reads are done
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<uint4*>(stg + lane * STG_LD + 4 * q) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+            *reinterpret_cast<uint4*>(stg + lane * STG_LD + 4 * (q ^ (lane & 7))) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
           __syncwarp();
 #pragma unroll
           for (int hb = 0; hb < 2; ++hb) {  // two batches of 4 rows-groups: loads first, then math + stores
@@ -429,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               const int row = it * 4 + rsub;
               const int m = mrow0 + row;
               ok[i] = col_ok && m < m_end;
-              acc[i] = *reinterpret_cast<const float4*>(stg + row * STG_LD + 4 * c4);
+              acc[i] = *reinterpret_cast<const float4*>(stg + row * STG_LD + 4 * (c4 ^ (row & 7)));
               x1[i] = x2[i] = x3[i] = make_float4(0.f, 0.f, 0.f, 0.f);
               if (ok[i]) {
                 if (EPI == MPHSIR_EPI_RESIDUAL || EPI == MPHSIR_EPI_SPECTRAL) x1[i] = ldg4(p.res1 + (size_t)m * p.ldr1 + n);
@@ -903,10 +909,11 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
   }
-  // shared-memory plan (227 KB): 1 KB barriers + A ring 4 x 32 KB (fp32 TMA landing zone, converted in place to
-  // bf16 hi|lo) + B ring (bf16x3: 3 x 16 KB, bf16x1: 6 x 8 KB) + 36 KB epilogue staging = 213 KB
-  a.na = 4;
-  a.nb = a.parts == 2 ? 3 : 6;
+  // shared-memory plan (225 KB of 227): 1 KB barriers + A ring (32 KB slots: fp32 TMA landing zone, converted in
+  // place to bf16 hi|lo) + B ring (128-row blocks) + 32 KB epilogue staging
+  //   bf16x3: A 3 x 32 KB + B 3 x 32 KB        bf16x1: A 4 x 32 KB + B 4 x 16 KB
+  a.na = a.parts == 2 ? 3 : 4;
+  a.nb = a.parts == 2 ? 3 : 4;
   const size_t smem = smem_bytes(a.na, a.nb, a.parts);
   a.a_mode = A_ROWCOPY;
   a.seg = 64;

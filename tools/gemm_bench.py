@@ -49,7 +49,7 @@ for name, K, N, epi, ln in shapes:
             lib.load().mphsir_debug_tc_counters(None)
             d = dbg.double().mean(0).tolist()
             names = ["Bload.total", "Bload.wait_empty", "MMA.total", "MMA.wait_acc", "MMA.wait_A", "MMA.wait_B", "EPI.total",
-                     "EPI.wait_full", "EPI.tmem_ld", "CV0.total", "CV0.wait_slot", "CV0.load+cvt", "CV1.total", "CV1.wait_slot", "CV1.load+cvt"]
+                     "EPI.wait_full", "EPI.tmem_ld", "CV.total", "CV.bar", "CV.wait_tma", "MMA.issue", "MMA.commit", "-"]
             print("      " + "  ".join(f"{n}={v/1e3:.0f}k" for n, v in zip(names, d)))
         byts = 4.0 * (M * K + M * n_out + (M * N if res is not None else 0))
         print(f"{name:28s} {pn}  {ms*1e3:8.1f} us  {byts/ms/1e6:7.1f} GB/s  {2.0*M*N*K/ms/1e9:7.1f} TFLOP/s")
