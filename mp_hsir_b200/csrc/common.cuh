@@ -20,12 +20,14 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // fp32 rounding level), 2 MUFU + ~12 FMA-pipe instructions instead of erff's two-branch polynomial.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float pl = fmaf(1.061405429f, t, -1.453152027f);
   pl = fmaf(pl, t, 1.421413741f);
   pl = fmaf(pl, t, -0.284496736f);
   pl = fmaf(pl, t, 0.254829592f);
-  const float e = exp2f(-1.4426950408889634f * z * z);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
   const float erf_abs = fmaf(-pl * t, e, 1.0f);  // erf(|x|/sqrt2)
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }

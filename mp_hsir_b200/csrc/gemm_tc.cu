@@ -380,6 +380,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         TC_ACC(t_wait, tw);
         tc_fence_after();
         const int ncols_pass = min(PASS_COLS, p.Np - pass * PASS_COLS);
+        // software-pipelined bias: the float4 for the NEXT chunk is requested while this one is processed
+        float4 bias_nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!DIRECT && p.bias != nullptr && pass * PASS_COLS + half * 32 + 4 * c4 < p.N)
+          bias_nxt = ldg4(p.bias + pass * PASS_COLS + half * 32 + 4 * c4);
         for (int c0 = half * 32; c0 < ncols_pass; c0 += 64) {
           const int n0 = pass * PASS_COLS + c0;
           uint32_t r[32];
@@ -416,8 +420,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           // ---- staged path ----
           const int n = n0 + 4 * c4;          // this thread's 4 output columns (packed order)
           const bool col_ok = n < p.N;
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias != nullptr && col_ok) bias4 = ldg4(p.bias + n);
+          const float4 bias4 = bias_nxt;
+          if (p.bias != nullptr && c0 + 64 < ncols_pass && n + 64 < p.N) bias_nxt = ldg4(p.bias + n + 64);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           TC_ACC(t_tmem, tw);
           __syncwarp();  // previous chunk's smem reads are done
