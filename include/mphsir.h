@@ -159,6 +159,7 @@ MPHSIR_API int mphsir_conv3x3_fwd(const mphsir_conv3x3_params* p, void* stream);
  * ------------------------------------------------------------------------------------- */
 MPHSIR_API int mphsir_window_attn_fwd(const float* qkv, int ldqkv, const float* bias, float* out, int ldo,
                            float* win_mean, int B, int H, int W, int C, int heads, int shift,
+                           int precision /* MPHSIR_PREC_*: SIMT fp32, or tensor cores with bf16x3 / bf16 operands */,
                            void* stream);
 
 /* ---------------------------------------------------------------------------------------

@@ -190,13 +190,18 @@ static int launch_wa(const float* qkv, int ldqkv, const float* bias, float* out,
   return check_launch("window_attn");
 }
 
+namespace wa {
+int launch_window_attn_mma(const float* qkv, int ldqkv, const float* bias, float* out, int ldo, float* win_mean, int B,
+                           int H, int W, int C, int heads, int shift, int parts, cudaStream_t st);
+}
+
 }  // namespace mphsir
 
 using namespace mphsir;
 
 extern "C" int mphsir_window_attn_fwd(const float* qkv, int ldqkv, const float* bias, float* out, int ldo,
                                       float* win_mean, int B, int H, int W, int C, int heads, int shift,
-                                      void* stream) {
+                                      int precision, void* stream) {
   MPHSIR_REQUIRE(qkv && bias && out && win_mean, "window_attn: null operand");
   MPHSIR_REQUIRE(B > 0 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0, "window_attn: H=%d W=%d must be multiples of 8", H, W);
   MPHSIR_REQUIRE(heads > 0 && C % heads == 0, "window_attn: C=%d not divisible by heads=%d", C, heads);
@@ -204,6 +209,10 @@ extern "C" int mphsir_window_attn_fwd(const float* qkv, int ldqkv, const float* 
   MPHSIR_REQUIRE(ldqkv >= 3 * C && ldqkv % 4 == 0 && ldo >= C, "window_attn: bad leading dimensions");
   MPHSIR_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "window_attn: qkv/bias must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MPHSIR_REQUIRE(precision >= MPHSIR_PREC_FP32_SIMT && precision <= MPHSIR_PREC_BF16, "window_attn: unknown precision %d", precision);
+  if (precision != MPHSIR_PREC_FP32_SIMT)
+    return wa::launch_window_attn_mma(qkv, ldqkv, bias, out, ldo, win_mean, B, H, W, C, heads, shift,
+                                      precision == MPHSIR_PREC_BF16X3 ? 2 : 1, st);
   switch (C / heads) {
     case 32: return launch_wa<32>(qkv, ldqkv, bias, out, ldo, win_mean, B, H, W, C, heads, shift, st);
     case 48: return launch_wa<48>(qkv, ldqkv, bias, out, ldo, win_mean, B, H, W, C, heads, shift, st);

@@ -330,7 +330,7 @@ class Engine:
         # LN1 + qkv projection (net/MP_HSIR.py:667, :195)
         self._gemm(x, w["qkv_w"], qkv, 3 * C, ln=w["ln1"], bias=w["qkv_b"])
         # shifted-window attention core + per-window mean (:671-683, :198-215)
-        lib.window_attn(qkv, w["rpb"], core, wmean, B, H, W, C, heads, shift)
+        lib.window_attn(qkv, w["rpb"], core, wmean, B, H, W, C, heads, shift, precision=self.prec)
         # local spectral gate (:132-152)
         lib.local_gate(wmean, w["gate"], gate, B_, C, st.rank)
         # attention output projection (:216) in image order

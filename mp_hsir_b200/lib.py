@@ -72,7 +72,7 @@ SIGNATURES = {
     "mphsir_pack_bimg": (_I, [_VP, _I, _I, _LL, _VP, _I, _I, _I, _VP]),
     "mphsir_gemm_fwd": (_I, [C.POINTER(GemmParams), _VP]),
     "mphsir_conv3x3_fwd": (_I, [C.POINTER(ConvParams), _VP]),
-    "mphsir_window_attn_fwd": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _VP]),
+    "mphsir_window_attn_fwd": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "mphsir_local_gate_fwd": (_I, [C.POINTER(LocalGateParams), _VP]),
     "mphsir_dwconv3x3_fwd": (_I, [_VP, _I, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "mphsir_gram_partial_floats": (C.c_size_t, [_I, _I, _I, _I, C.POINTER(_I)]),
@@ -309,12 +309,12 @@ def conv3x3(X: View, Wt, Y_ptr: int, ldy: int, B: int, H: int, W: int, Cin: int,
 
 
 def window_attn(qkv: View, bias: torch.Tensor, out: View, win_mean: torch.Tensor, B: int, H: int, W: int,
-                Cc: int, heads: int, shift: int) -> None:
+                Cc: int, heads: int, shift: int, precision: int = 0) -> None:
     n = B * H * W
     _launch("window_attn_fwd",
             lambda: load().mphsir_window_attn_fwd(qkv.ptr, qkv.ld, bias.data_ptr(), out.ptr, out.ld,
-                                                  win_mean.data_ptr(), B, H, W, Cc, heads, shift, stream_ptr()),
-            lambda: (4.0 * n * 64 * Cc, 4.0 * (4 * n * Cc + n // 64 * Cc), "window_attn"))
+                                                  win_mean.data_ptr(), B, H, W, Cc, heads, shift, precision, stream_ptr()),
+            lambda: (4.0 * n * 64 * Cc, 4.0 * (4 * n * Cc + n // 64 * Cc), ("window_attn", "window_attn_mma3", "window_attn_mma1")[precision]))
 
 
 def local_gate(core_mean: torch.Tensor, w: dict, gate: torch.Tensor, B_: int, Cc: int, r: int) -> None:

@@ -161,9 +161,10 @@ def test_conv3x3_pixel_unshuffle_and_shuffle():
 # ------------------------------------------------------------------------------------------------
 
 
+@pytest.mark.parametrize("prec,tol", [(lib.PREC_FP32_SIMT, TOL), (lib.PREC_BF16X3, 5e-5), (lib.PREC_BF16, 2e-2)])
 @pytest.mark.parametrize("C,heads", [(64, 2), (128, 2), (96, 2), (192, 2), (256, 8)])
 @pytest.mark.parametrize("shift", [0, 4])
-def test_window_attention_core(C, heads, shift):
+def test_window_attention_core(C, heads, shift, prec, tol):
     B, H, W = 2, 16, 24
     qkv = rnd(B, H, W, 3 * C, seed=1)
     table = 0.5 * rnd(225, heads, seed=2)
@@ -183,9 +184,10 @@ def test_window_attention_core(C, heads, shift):
     ref = tokens(O.from_windows(core_w, shift, B, H, W))
     out = out_mat(B * H * W, C)
     wm = torch.full((B_, C), float("nan"), device=DEV)
-    lib.window_attn(V(dev(tokens(qkv))), dev(O.relative_position_bias(table)), V(out), wm, B, H, W, C, heads, shift)
-    assert rel_err(out.cpu(), ref) < TOL
-    assert rel_err(wm.cpu(), core_w.mean(dim=1)) < TOL
+    lib.window_attn(V(dev(tokens(qkv))), dev(O.relative_position_bias(table)), V(out), wm, B, H, W, C, heads, shift,
+                    precision=prec)
+    assert rel_err(out.cpu(), ref) < tol
+    assert rel_err(wm.cpu(), core_w.mean(dim=1)) < tol
     del sd
 
 
@@ -302,5 +304,5 @@ def test_errors_are_reported_not_swallowed():
         lib.gemm(V(a), torch.zeros(16, 64, device=DEV), V(torch.zeros(8, 64, device=DEV)), 64)  # K=6 not %4
     with pytest.raises(RuntimeError, match="head_dim"):
         lib.window_attn(V(torch.zeros(64, 120, device=DEV)), torch.zeros(1, 64, 64, device=DEV),
-                        V(torch.zeros(64, 40, device=DEV)), torch.zeros(40, device=DEV), 1, 8, 8, 40, 1, 0)
+                        V(torch.zeros(64, 40, device=DEV)), torch.zeros(40, device=DEV), 1, 8, 8, 40, 1, 0, precision=1)
     assert math.isfinite(float(a.sum()))
