@@ -213,6 +213,15 @@ MPHSIR_API int mphsir_spectral_fold_fwd(const float* attn, const float* WoutT /*
                              float* Mt /* [B, Cp, ldm] */, int ldm, long long m_batch_stride, int B,
                              int heads, int c, void* stream);
 
+/* Steps 2+3 in one call (what the module uses): reduce the partials (into `scratch` when n_chunks > 1),
+ * normalise + temperature + softmax, fold project_out, and write the per-sample matrix as fp32 "in x out"
+ * Mt [B, Cp, ldm] (may be NULL) and/or as the tensor-core image (may be NULL; see mphsir_pack_bimg).
+ * attn_out [B,heads,c,c] is optional (tests). */
+MPHSIR_API int mphsir_spectral_finish_fwd(const float* partial, int n_chunks, float* scratch, const float* temperature,
+                                          const float* WoutT, float* Mt, int ldm, long long m_batch_stride, void* bimg,
+                                          long long bimg_batch_bytes, float* attn_out, int B, int heads, int c,
+                                          void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * TVSP helpers.
  *  tvsp_query : Q[b,i,j,d] = tp[b,d] * clip_b[floor(i*B/ps), floor(j*512/ps)] with

@@ -4,7 +4,10 @@
 //     applied AFTER the reduction: q^k^ = (q.k)/(|q||k|))
 //   * softmax with temperature (:107-108) and folding of project_out (:113) into one C x C matrix
 //     per sample:  out = W_out (A v)  ==  (W_out blockdiag(A)) v
+#include <cuda_bf16.h>
+
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace mphsir {
 
@@ -253,6 +256,112 @@ __global__ void __launch_bounds__(256) spectral_fold_kernel(const float* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// finish: (reduced Gram, norms) -> normalise, temperature, row softmax -> fold project_out -> write the
+// per-sample matrix both as fp32 "in x out" (SIMT engine) and as the bf16 hi/lo tensor-core image.
+// grid = (B*heads, ceil(C/64)), 256 threads = 64 output columns x 4 groups of 8 input channels.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split2_bf16(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__global__ void __launch_bounds__(256) spectral_finish_kernel(const float* __restrict__ gsum,
+                                                              const float* __restrict__ temperature,
+                                                              const float* __restrict__ WoutT, float* __restrict__ Mt,
+                                                              long long ldm, long long m_batch_stride,
+                                                              uint8_t* __restrict__ bimg, long long bimg_batch_bytes,
+                                                              float* __restrict__ attn_out, int heads, int c) {
+  extern __shared__ float sm[];
+  const int C = heads * c;
+  const int per = c * c + 2 * c;
+  float* A = sm;             // [c][c] (+2c norms while normalising)
+  float* Wt = A + per;       // [c][64]
+  const int bh = blockIdx.x;
+  const int b = bh / heads, h = bh - b * heads;
+  const int o0 = blockIdx.y * 64;
+  for (int e = threadIdx.x; e < per; e += 256) A[e] = __ldg(gsum + (long long)bh * per + e);
+  for (int e = threadIdx.x; e < c * 64; e += 256) {
+    const int i = e >> 6, o = e & 63;
+    Wt[e] = (o0 + o < C) ? __ldg(WoutT + (long long)(h * c + i) * C + o0 + o) : 0.f;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 2 * c; e += 256) A[c * c + e] = fmaxf(sqrtf(A[c * c + e]), 1e-12f);  // F.normalize eps
+  __syncthreads();
+  const float temp = __ldg(temperature + h);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = warp; i < c; i += 8) {
+    const float nq = A[c * c + i];
+    float mx = -INFINITY;
+    for (int j = lane; j < c; j += 32) {
+      const float v = A[i * c + j] / (nq * A[c * c + c + j]) * temp;
+      A[i * c + j] = v;
+      mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    float ssum = 0.f;
+    for (int j = lane; j < c; j += 32) {
+      const float e = expf(A[i * c + j] - mx);
+      A[i * c + j] = e;
+      ssum += e;
+    }
+    ssum = warp_sum(ssum);
+    const float inv = 1.0f / ssum;
+    for (int j = lane; j < c; j += 32) {
+      const float pv = A[i * c + j] * inv;
+      A[i * c + j] = pv;
+      if (attn_out != nullptr && blockIdx.y == 0) attn_out[(long long)bh * c * c + i * c + j] = pv;
+    }
+  }
+  __syncthreads();
+  // fold: M[o][h*c + j] = sum_i Wout[o][h*c + i] * A[i][j]
+  const int o = threadIdx.x & 63;
+  const int Np = (C + 15) / 16 * 16, Ks = (C + 63) / 64;
+  for (int j0 = 8 * (threadIdx.x >> 6); j0 < c; j0 += 32) {
+    float acc[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) acc[jj] = 0.f;
+    for (int i = 0; i < c; ++i) {
+      const float w = Wt[i * 64 + o];
+      const float4 a0 = *reinterpret_cast<const float4*>(&A[i * c + j0]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&A[i * c + j0 + 4]);
+      acc[0] = fmaf(w, a0.x, acc[0]); acc[1] = fmaf(w, a0.y, acc[1]);
+      acc[2] = fmaf(w, a0.z, acc[2]); acc[3] = fmaf(w, a0.w, acc[3]);
+      acc[4] = fmaf(w, a1.x, acc[4]); acc[5] = fmaf(w, a1.y, acc[5]);
+      acc[6] = fmaf(w, a1.z, acc[6]); acc[7] = fmaf(w, a1.w, acc[7]);
+    }
+    if (o0 + o >= C) continue;
+    const int k = h * c + j0;
+    if (Mt != nullptr) {
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) Mt[(long long)b * m_batch_stride + (long long)(k + jj) * ldm + o0 + o] = acc[jj];
+    }
+    if (bimg != nullptr) {
+      uint4 hi, lo;
+      split2_bf16(acc[0], acc[1], hi.x, lo.x);
+      split2_bf16(acc[2], acc[3], hi.y, lo.y);
+      split2_bf16(acc[4], acc[5], hi.z, lo.z);
+      split2_bf16(acc[6], acc[7], hi.w, lo.w);
+      uint8_t* img = bimg + (long long)b * bimg_batch_bytes;
+      const int s_ = k >> 6, ch = (k & 63) >> 3;
+      *reinterpret_cast<uint4*>(img + tc::bimg_offset(0, s_, o0 + o, ch, Np, Ks)) = hi;
+      *reinterpret_cast<uint4*>(img + tc::bimg_offset(1, s_, o0 + o, ch, Np, Ks)) = lo;
+    }
+  }
+  // zero the K tail of the image (C not a multiple of 64) once per output row
+  if (bimg != nullptr && h == heads - 1 && (C & 63) != 0 && o0 + o < C) {
+    uint8_t* img = bimg + (long long)b * bimg_batch_bytes;
+    for (int k = C + 8 * (threadIdx.x >> 6); k < Ks * 64; k += 32) {
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(img + tc::bimg_offset(0, k >> 6, o0 + o, (k & 63) >> 3, Np, Ks)) = z;
+      *reinterpret_cast<uint4*>(img + tc::bimg_offset(1, k >> 6, o0 + o, (k & 63) >> 3, Np, Ks)) = z;
+    }
+  }
+}
+
 }  // namespace mphsir
 
 using namespace mphsir;
@@ -333,4 +442,39 @@ extern "C" int mphsir_spectral_fold_fwd(const float* attn, const float* WoutT, f
   dim3 grid(B * heads, (C + 63) / 64);
   spectral_fold_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(attn, WoutT, Mt, ldm, m_batch_stride, heads, c);
   return check_launch("spectral_fold");
+}
+
+extern "C" int mphsir_spectral_finish_fwd(const float* partial, int n_chunks, float* scratch, const float* temperature,
+                                          const float* WoutT, float* Mt, int ldm, long long m_batch_stride, void* bimg,
+                                          long long bimg_batch_bytes, float* attn_out, int B, int heads, int c,
+                                          void* stream) {
+  MPHSIR_REQUIRE(partial && temperature && WoutT && (Mt || bimg), "spectral_finish: null operand");
+  MPHSIR_REQUIRE(n_chunks > 0 && B > 0 && heads > 0 && c > 0 && c % 8 == 0, "spectral_finish: bad shape (c=%d must be a multiple of 8)", c);
+  MPHSIR_REQUIRE(Mt == nullptr || ldm >= heads * c, "spectral_finish: ldm too small");
+  MPHSIR_REQUIRE(bimg == nullptr || (reinterpret_cast<uintptr_t>(bimg) & 127) == 0, "spectral_finish: image must be 128-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int per = c * c + 2 * c;
+  const int C = heads * c;
+  const float* gsum = partial;
+  if (n_chunks > 1) {
+    MPHSIR_REQUIRE(scratch != nullptr, "spectral_finish: scratch [B*heads*(c*c+2c)] required when n_chunks > 1");
+    dim3 grid((per + 63) / 64, B * heads);
+    gram_reduce_kernel<<<grid, 256, 0, st>>>(partial, n_chunks, per, scratch);
+    gsum = scratch;
+  }
+  const size_t smem = sizeof(float) * ((size_t)per + (size_t)c * 64);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(spectral_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) {
+      set_error("spectral_finish: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return MPHSIR_ERR_CUDA;
+    }
+    configured = true;
+  }
+  MPHSIR_REQUIRE(smem <= 96 * 1024, "spectral_finish: c=%d needs %zu B of shared memory", c, smem);
+  dim3 grid(B * heads, (C + 63) / 64);
+  spectral_finish_kernel<<<grid, 256, smem, st>>>(gsum, temperature, WoutT, Mt, ldm, m_batch_stride,
+                                                  reinterpret_cast<uint8_t*>(bimg), bimg_batch_bytes, attn_out, heads, c);
+  return check_launch("spectral_finish");
 }

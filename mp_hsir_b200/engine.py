@@ -296,18 +296,16 @@ class Engine:
         C = heads * c
         nfl, nch = lib.gram_partial_floats(B, heads, c, HW)
         partial = ws.flat(tag + ".partial", nfl)
-        attn = ws.flat(tag + ".attn", B * heads * c * c)
-        ldm = _ldb(C)
-        Mt = ws.flat(tag + ".Mt", B * _ceil(C, 16) * ldm).view(-1)[: B * _ceil(C, 16) * ldm].view(B, _ceil(C, 16), ldm)
-        lib.gram_partial(q, q_shared, k, k_shared, partial, B, HW, heads, c)
         scratch = ws.flat(tag + ".gsum", B * heads * (c * c + 2 * c))
-        lib.gram_softmax(partial, nch, temp, attn, B, heads, c, scratch=scratch)
-        lib.spectral_fold(attn, out_t, Mt, B, heads, c)
-        img = None
-        if self.prec != lib.PREC_FP32_SIMT:
+        lib.gram_partial(q, q_shared, k, k_shared, partial, B, HW, heads, c)
+        Mt = img = None
+        if self.prec == lib.PREC_FP32_SIMT:
+            ldm = _ldb(C)
+            Mt = ws.flat(tag + ".Mt", B * _ceil(C, 16) * ldm).view(-1)[: B * _ceil(C, 16) * ldm].view(B, _ceil(C, 16), ldm)
+        else:
             nb = lib.bimg_bytes(C, C)
             img = ws.raw(tag + ".img", B * nb)[: B * nb].view(B, nb)
-            lib.pack_bimg(Mt, C, C, transposed=True, img=img)
+        lib.spectral_finish(partial, nch, scratch, temp, out_t, Mt, img, B, heads, c)
         return lib.Weight(Mt, img, C, C)
 
     def _pgsstb(self, w: dict, st: Stage, shift: int, x: View, out: View, res2: Optional[View], B: int, H: int,

@@ -79,6 +79,7 @@ SIGNATURES = {
     "mphsir_gram_partial_fwd": (_I, [_VP, _I, _I, _VP, _I, _I, _VP, _I, _I, _I, _I, _VP]),
     "mphsir_gram_softmax_fwd": (_I, [_VP, _I, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "mphsir_spectral_fold_fwd": (_I, [_VP, _VP, _VP, _I, _LL, _I, _I, _I, _VP]),
+    "mphsir_spectral_finish_fwd": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, _LL, _VP, _LL, _VP, _I, _I, _I, _VP]),
     "mphsir_tvsp_query_fwd": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "mphsir_bilinear_fwd": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "mphsir_text_prompt_fwd": (_I, [_VP, _VP, _VP, _I, _I, _VP]),
@@ -366,6 +367,20 @@ def spectral_fold(attn: torch.Tensor, WoutT: torch.Tensor, Mt: torch.Tensor, B: 
             lambda: load().mphsir_spectral_fold_fwd(attn.data_ptr(), WoutT.data_ptr(), Mt.data_ptr(), Mt.shape[2],
                                                     Mt.shape[1] * Mt.shape[2], B, heads, c, stream_ptr()),
             lambda: (2.0 * B * heads * c * c * heads * c, 4.0 * B * (heads * c) ** 2, "spectral_fold"))
+
+
+def spectral_finish(partial: torch.Tensor, n_chunks: int, scratch: torch.Tensor, temperature: torch.Tensor,
+                    WoutT: torch.Tensor, Mt: Optional[torch.Tensor], img: Optional[torch.Tensor], B: int, heads: int,
+                    c: int, attn_out: Optional[torch.Tensor] = None) -> None:
+    """gram reduce + softmax + project_out fold (+ tensor-core image) in one ABI call."""
+    ldm = Mt.shape[2] if Mt is not None else 0
+    mstride = Mt.shape[1] * Mt.shape[2] if Mt is not None else 0
+    istride = img.stride(0) if img is not None else 0
+    _launch("spectral_finish_fwd",
+            lambda: load().mphsir_spectral_finish_fwd(partial.data_ptr(), n_chunks, scratch.data_ptr(),
+                                                      temperature.data_ptr(), WoutT.data_ptr(), ptr(Mt), ldm, mstride,
+                                                      ptr(img), istride, ptr(attn_out), B, heads, c, stream_ptr()),
+            lambda: (2.0 * B * heads * c * c * heads * c, 4.0 * B * heads * (n_chunks + 1) * c * c, "spectral_finish"))
 
 
 def tvsp_query(clip_b: torch.Tensor, weights: torch.Tensor, learnable: torch.Tensor, Q: View, B: int, T: int,

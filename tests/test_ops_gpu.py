@@ -306,3 +306,34 @@ def test_errors_are_reported_not_swallowed():
         lib.window_attn(V(torch.zeros(64, 120, device=DEV)), torch.zeros(1, 64, 64, device=DEV),
                         V(torch.zeros(64, 40, device=DEV)), torch.zeros(40, device=DEV), 1, 8, 8, 40, 1, 0, precision=1)
     assert math.isfinite(float(a.sum()))
+
+
+@pytest.mark.parametrize("C,heads,HW", [(64, 2, 1024), (128, 2, 4096), (256, 8, 256), (96, 2, 640)])
+def test_spectral_finish_matches_unfused_chain(C, heads, HW):
+    """one-call reduce+softmax+fold(+tensor-core image) == gram_softmax -> spectral_fold -> pack_bimg."""
+    B = 2
+    c = C // heads
+    qkv = rnd(B, HW, 3 * C, seed=1)
+    temp = dev((0.5 + torch.rand(heads, generator=torch.Generator().manual_seed(2))))
+    wout_t = dev(rnd(C, C, seed=3, scale=C ** -0.5))
+    vw = V(dev(qkv.reshape(B * HW, 3 * C)))
+    nfl, nch = lib.gram_partial_floats(B, heads, c, HW)
+    partial = torch.empty(nfl, device=DEV)
+    lib.gram_partial(vw.cols_slice(0, C), False, vw.cols_slice(C, 2 * C), False, partial, B, HW, heads, c)
+    attn = torch.empty(B * heads * c * c, device=DEV)
+    Mt_ref = torch.zeros(B, E._ceil(C, 16), E._ldb(C), device=DEV)
+    lib.gram_softmax(partial, nch, temp, attn, B, heads, c)
+    lib.spectral_fold(attn, wout_t, Mt_ref, B, heads, c)
+    img_ref = lib.pack_bimg(Mt_ref, C, C, transposed=True)
+    Mt = torch.zeros_like(Mt_ref)
+    img = torch.zeros_like(img_ref)
+    attn2 = torch.empty_like(attn)
+    scratch = torch.empty(B * heads * (c * c + 2 * c), device=DEV)
+    lib.spectral_finish(partial, nch, scratch, temp, wout_t, Mt, img, B, heads, c, attn_out=attn2)
+    assert rel_err(attn2.cpu(), attn.cpu()) < 1e-6
+    assert rel_err(Mt[:, :C, :C].cpu(), Mt_ref[:, :C, :C].cpu()) < 1e-6
+    # the images hold [hi part | lo part] in the same layout: hi + lo reconstructs the folded matrix to ~2^-17
+    def recon(t):
+        f = t.view(torch.bfloat16).float().view(B, 2, -1)
+        return (f[:, 0] + f[:, 1]).cpu()
+    assert rel_err(recon(img), recon(img_ref)) < 2e-5  # hi+lo carries 2^-17 relative precision
