@@ -213,6 +213,15 @@ MPHSIR_API int mphsir_spectral_fold_fwd(const float* attn, const float* WoutT /*
                              float* Mt /* [B, Cp, ldm] */, int ldm, long long m_batch_stride, int B,
                              int heads, int c, void* stream);
 
+/* Fused step 0+1 for the tensor-core precisions: depthwise 3x3 of the [q|k|v] 1x1 output X [B*H*W, >=3C] +
+ * Gram partials; only v is written (V [B*H*W, ldv]); q and k never reach HBM.  partial layout as above with
+ * n_chunks = CTAs per sample (mphsir_dwgram_partial_floats).  Supported (C, C/heads): see
+ * mphsir_dwgram_supported; otherwise use dwconv3x3 + gram_partial. */
+MPHSIR_API int mphsir_dwgram_supported(int C, int c);
+MPHSIR_API size_t mphsir_dwgram_partial_floats(int B, int heads, int c, int H, int W, int* n_chunks);
+MPHSIR_API int mphsir_dwgram_fwd(const float* X, int ldx, const float* w9 /* [9, 3C] */, float* V, int ldv,
+                                 float* partial, int B, int H, int W, int C, int heads, int precision, void* stream);
+
 /* Steps 2+3 in one call (what the module uses): reduce the partials (into `scratch` when n_chunks > 1),
  * normalise + temperature + softmax, fold project_out, and write the per-sample matrix as fp32 "in x out"
  * Mt [B, Cp, ldm] (may be NULL) and/or as the tensor-core image (may be NULL; see mphsir_pack_bimg).

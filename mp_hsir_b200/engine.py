@@ -293,11 +293,15 @@ class Engine:
                             B: int, HW: int, heads: int, c: int) -> lib.Weight:
         """Gram statistics -> softmax -> folded per-sample matrix Mt [B, C, ldm] ("in x out")."""
         ws = self.ws
-        C = heads * c
         nfl, nch = lib.gram_partial_floats(B, heads, c, HW)
         partial = ws.flat(tag + ".partial", nfl)
-        scratch = ws.flat(tag + ".gsum", B * heads * (c * c + 2 * c))
         lib.gram_partial(q, q_shared, k, k_shared, partial, B, HW, heads, c)
+        return self._spectral_finish(tag, partial, nch, temp, out_t, B, heads, c)
+
+    def _spectral_finish(self, tag: str, partial, nch: int, temp, out_t, B: int, heads: int, c: int) -> lib.Weight:
+        ws = self.ws
+        C = heads * c
+        scratch = ws.flat(tag + ".gsum", B * heads * (c * c + 2 * c))
         Mt = img = None
         if self.prec == lib.PREC_FP32_SIMT:
             ldm = _ldb(C)
@@ -308,6 +312,24 @@ class Engine:
         lib.spectral_finish(partial, nch, scratch, temp, out_t, Mt, img, B, heads, c)
         return lib.Weight(Mt, img, C, C)
 
+    def _global_spectral(self, tag: str, t3: View, w_dw, temp, out_t, B: int, H: int, W: int, C: int, heads: int):
+        """qkv_dwconv + Gram + softmax + fold (net/MP_HSIR.py:98-113): returns (v operand view, folded Weight).
+        Tensor-core precisions use the fused dwconv+Gram kernel (q, k never reach HBM)."""
+        ws = self.ws
+        N = B * H * W
+        c = C // heads
+        if self.prec != lib.PREC_FP32_SIMT and lib.dwgram_supported(C, c):
+            v = ws.mat(tag + ".v", N, C)
+            nfl, nch = lib.dwgram_partial_floats(B, heads, c, H, W)
+            partial = ws.flat(tag + ".partial", nfl)
+            lib.dwgram(t3, w_dw, v, partial, B, H, W, C, heads, self.prec)
+            return v, self._spectral_finish(tag, partial, nch, temp, out_t, B, heads, c)
+        dw3 = ws.mat(tag + ".dw3", N, 3 * C)
+        lib.dwconv3x3(t3, w_dw, dw3, B, H, W, 3 * C)
+        Mt = self._spectral_attention(tag, dw3.cols_slice(0, C), False, dw3.cols_slice(C, 2 * C), False, temp, out_t,
+                                      B, H * W, heads, c)
+        return dw3.cols_slice(2 * C, 3 * C), Mt
+
     def _pgsstb(self, w: dict, st: Stage, shift: int, x: View, out: View, res2: Optional[View], B: int, H: int,
                 W: int, row_scales=None, taps: Optional[dict] = None):
         ws = self.ws
@@ -317,7 +339,6 @@ class Engine:
         qkv = ws.mat("qkv", N, 3 * C)
         core = ws.mat("core", N, C)
         sa = ws.mat("sa", N, C)
-        dw3 = ws.mat("dw3", N, 3 * C)
         mid = ws.mat("mid", N, C)
         hidden = ws.mat("hidden", N, w["hid_pad"])
         wmean = ws.flat("wmean", B_ * C)
@@ -336,11 +357,9 @@ class Engine:
         # global spectral attention: 1x1 -> dw3x3 -> Gram/softmax/fold -> apply (:98-113)
         t3 = ws.mat("qkv", N, 3 * C)  # qkv is dead: reuse
         self._gemm(sa, w["sqkv_w"], t3, 3 * C)
-        lib.dwconv3x3(t3, w["sdw"], dw3, B, H, W, 3 * C)
-        Mt = self._spectral_attention("spec", dw3.cols_slice(0, C), False, dw3.cols_slice(C, 2 * C), False,
-                                      w["temp"], w["sout_t"], B, H * W, heads, C // heads)
+        v, Mt = self._global_spectral("spec", t3, w["sdw"], w["temp"], w["sout_t"], B, H, W, C, heads)
         # x = shortcut + DropPath(sa*gate + project_out(attn v))   (:715-718)
-        self._gemm(dw3.cols_slice(2 * C, 3 * C), Mt, mid, C, epi=lib.EPI_SPECTRAL, res1=x, gsrc=sa, gate=gate,
+        self._gemm(v, Mt, mid, C, epi=lib.EPI_SPECTRAL, res1=x, gsrc=sa, gate=gate,
                  H=H, W=W, shift=shift, rows_per_batch=H * W, row_scale=s1)
         # x = x + DropPath(fc2(value * gelu(gate)))  with LN2 fused in front (:719, :76-82)
         self._gemm(mid, w["fc1_w"], hidden, 2 * w["hid_pad"], ln=w["ln2"], bias=w["fc1_b"], epi=lib.EPI_GLU)
@@ -411,13 +430,10 @@ class Engine:
         C2, heads = w["C"], w["heads"]
         N = B * H * W
         t3 = ws.mat(name + ".t3", N, 3 * C2)
-        dw3 = ws.mat(name + ".dw3", N, 3 * C2)
         self._gemm(xcat, w["qkv_w"], t3, 3 * C2, ln=w["ln1"])
-        lib.dwconv3x3(t3, w["dw"], dw3, B, H, W, 3 * C2)
-        Mt = self._spectral_attention(name + ".spec", dw3.cols_slice(0, C2), False, dw3.cols_slice(C2, 2 * C2), False,
-                                      w["temp"], w["out_t"], B, H * W, heads, C2 // heads)
+        v, Mt = self._global_spectral(name + ".spec", t3, w["dw"], w["temp"], w["out_t"], B, H, W, C2, heads)
         y1 = ws.mat(name + ".y1", N, C2)
-        self._gemm(dw3.cols_slice(2 * C2, 3 * C2), Mt, y1, C2, epi=lib.EPI_RESIDUAL, res1=xcat, rows_per_batch=H * W)
+        self._gemm(v, Mt, y1, C2, epi=lib.EPI_RESIDUAL, res1=xcat, rows_per_batch=H * W)
         y2 = ws.mat(name + ".y2", N, C2)
         self._gdfn(name + ".ffn", w, y1, y2, w["ln2"], B, H, W, C2)
         self._gemm(y2, w["conv_w"], out, out.cols)

@@ -79,6 +79,9 @@ SIGNATURES = {
     "mphsir_gram_partial_fwd": (_I, [_VP, _I, _I, _VP, _I, _I, _VP, _I, _I, _I, _I, _VP]),
     "mphsir_gram_softmax_fwd": (_I, [_VP, _I, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "mphsir_spectral_fold_fwd": (_I, [_VP, _VP, _VP, _I, _LL, _I, _I, _I, _VP]),
+    "mphsir_dwgram_supported": (_I, [_I, _I]),
+    "mphsir_dwgram_partial_floats": (C.c_size_t, [_I, _I, _I, _I, _I, C.POINTER(_I)]),
+    "mphsir_dwgram_fwd": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "mphsir_spectral_finish_fwd": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, _LL, _VP, _LL, _VP, _I, _I, _I, _VP]),
     "mphsir_tvsp_query_fwd": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "mphsir_bilinear_fwd": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
@@ -367,6 +370,25 @@ def spectral_fold(attn: torch.Tensor, WoutT: torch.Tensor, Mt: torch.Tensor, B: 
             lambda: load().mphsir_spectral_fold_fwd(attn.data_ptr(), WoutT.data_ptr(), Mt.data_ptr(), Mt.shape[2],
                                                     Mt.shape[1] * Mt.shape[2], B, heads, c, stream_ptr()),
             lambda: (2.0 * B * heads * c * c * heads * c, 4.0 * B * (heads * c) ** 2, "spectral_fold"))
+
+
+def dwgram_supported(Cc: int, c: int) -> bool:
+    return bool(load().mphsir_dwgram_supported(Cc, c))
+
+
+def dwgram_partial_floats(B: int, heads: int, c: int, H: int, W: int):
+    n = C.c_int(0)
+    f = load().mphsir_dwgram_partial_floats(B, heads, c, H, W, C.byref(n))
+    return int(f), n.value
+
+
+def dwgram(X: View, w9: torch.Tensor, Vout: View, partial: torch.Tensor, B: int, H: int, W: int, Cc: int, heads: int,
+           precision: int) -> None:
+    n = B * H * W
+    _launch("dwgram_fwd",
+            lambda: load().mphsir_dwgram_fwd(X.ptr, X.ld, w9.data_ptr(), Vout.ptr, Vout.ld, partial.data_ptr(), B, H, W,
+                                             Cc, heads, precision, stream_ptr()),
+            lambda: (2.0 * n * (27 * Cc + Cc * (Cc // heads + 2)), 16.0 * n * Cc, ("", "dwgram3", "dwgram1")[precision]))
 
 
 def spectral_finish(partial: torch.Tensor, n_chunks: int, scratch: torch.Tensor, temperature: torch.Tensor,

@@ -337,3 +337,29 @@ def test_spectral_finish_matches_unfused_chain(C, heads, HW):
         f = t.view(torch.bfloat16).float().view(B, 2, -1)
         return (f[:, 0] + f[:, 1]).cpu()
     assert rel_err(recon(img), recon(img_ref)) < 2e-5  # hi+lo carries 2^-17 relative precision
+
+
+@pytest.mark.parametrize("prec,tol", [(lib.PREC_BF16X3, 5e-5), (lib.PREC_BF16, 2e-2)])
+@pytest.mark.parametrize("C,heads,H,W", [(64, 2, 16, 24), (128, 2, 32, 32), (128, 4, 16, 16), (256, 8, 8, 16), (96, 2, 16, 16)])
+def test_dwgram_fused_matches_dwconv_plus_gram(C, heads, H, W, prec, tol):
+    """fused depthwise conv + tensor-core Gram == oracle dwconv3x3 -> q^T k, sum q^2, sum k^2 (reduced partials)."""
+    B = 2
+    c = C // heads
+    assert lib.dwgram_supported(C, c)
+    x = rnd(B, H, W, 3 * C, seed=1)
+    w = rnd(3 * C, 1, 3, 3, seed=2, scale=1 / 3)
+    ref = O.dwconv3x3(x.double(), w.double())                      # [B,H,W,3C]
+    q, k, v = ref.reshape(B, H * W, 3 * C).split(C, dim=-1)
+    qh = q.view(B, H * W, heads, c).permute(0, 2, 3, 1)             # b h c T
+    kh = k.view(B, H * W, heads, c).permute(0, 2, 3, 1)
+    G = qh @ kh.transpose(-1, -2)                                   # b h c c
+    sq, sk = (qh ** 2).sum(-1), (kh ** 2).sum(-1)
+    vout = out_mat(B * H * W, C)
+    nfl, nch = lib.dwgram_partial_floats(B, heads, c, H, W)
+    partial = torch.full((nfl,), float("nan"), device=DEV)
+    lib.dwgram(V(dev(tokens(x))), dev(E.pack_dw(w)), V(vout), partial, B, H, W, C, heads, prec)
+    got = partial.view(B * heads, nch, c * c + 2 * c).double().sum(1).cpu()
+    assert rel_err(vout.cpu(), v.reshape(B * H * W, C).float()) < TOL       # v path is plain fp32
+    assert rel_err(got[:, : c * c], G.reshape(B * heads, c * c)) < tol
+    assert rel_err(got[:, c * c: c * c + c], sq.reshape(B * heads, c)) < tol
+    assert rel_err(got[:, c * c + c:], sk.reshape(B * heads, c)) < tol
