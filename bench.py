@@ -166,6 +166,9 @@ def main():
     ap.add_argument("--workload", default="cube512", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32_exact", "bf16"],
+                    help="fp32 = tcgen05 with bf16 hi/lo split operands (meets the 1e-4 fp32 parity bound, default); "
+                         "bf16 = bf16 operands (1e-2 bound); fp32_exact = FFMA")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -187,6 +190,8 @@ def main():
 
     model, shape, unit, units, sample_shape, frac = WORKLOADS[args.workload]
     cfg, net = build_net(model, device)
+    net.set_precision(args.precision)
+    precision = args.precision
     # independent cubes per rank (weak scaling): each rank gets its own seed
     x_host = make_input(shape, seed=rank).pin_memory()
     x_dev = x_host.to(device)
@@ -257,12 +262,22 @@ def main():
                              "tflops": round(a["flops"] / (a["ms"] * 1e-3) / 1e12, 2) if a["ms"] else 0,
                              "gbs": round(a["bytes"] / (a["ms"] * 1e-3) / 1e9, 1) if a["ms"] else 0}
                          for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
-            name, a = top
+            # kernel FAMILIES: every tag is one __global__ template; the tcgen05 GEMM engine (all prologue/epilogue
+            # variants of gemm_tc_kernel, incl. the implicit-GEMM convs) is reported as one kernel
+            def family(tag):
+                return "gemm_tc_kernel" if tag.startswith(("gemm_tc", "conv3x3_tc")) else tag
+            fam = {}
+            for k, a in agg.items():
+                f = fam.setdefault(family(k), {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+                for key in f:
+                    f[key] += a[key]
+            name, a = max(fam.items(), key=lambda kv: kv[1]["ms"])
             sec = a["ms"] * 1e-3
-            ridge = pk["tf_sustained"] * 1e12 / (pk["hbm_gbs"] * 1e9)
-            intensity = a["flops"] / max(a["bytes"], 1.0)
-            if intensity > ridge:
-                ach = a["flops"] / sec / 1e12
+            tensor_flops = a["flops"] * (3.0 if (name == "gemm_tc_kernel" and precision == "fp32") else 1.0)
+            t_hbm = a["bytes"] / (pk["hbm_gbs"] * 1e9)
+            t_tensor = tensor_flops / (pk["tf_sustained"] * 1e12)
+            if t_tensor > t_hbm:
+                ach = tensor_flops / sec / 1e12
                 roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                         "frac": ach / pk["tf_sustained"], "traffic": None}
             else:
@@ -270,9 +285,14 @@ def main():
                 roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                         "traffic": None}
             roof.update({"kernel": name, "share_of_step": round(a["ms"] / total_ms, 4), "launches": a["launches"] // passes,
-                         "avg_launch_ms": a["ms"] / a["launches"], "flop_per_byte": round(intensity, 1),
-                         "peak_source": pk["source"] + (" sustained (kernel timed inside a long step)"),
-                         "timing": "CUDA events around each launch on the launching stream, separate instrumented pass"})
+                         "avg_launch_ms": a["ms"] / a["launches"],
+                         "algorithmic_bytes_per_step": a["bytes"] / passes, "algorithmic_flops_per_step": a["flops"] / passes,
+                         "bf16_mma_flops_per_step": tensor_flops / passes,
+                         "roofline_ms_per_step": {"hbm": 1e3 * t_hbm / passes, "tensor": 1e3 * t_tensor / passes},
+                         "peak_source": pk["source"] + " (MEASURED_PEAKS.json; sustained bf16 figure: kernel timed inside a long step)",
+                         "timing": "CUDA events around each launch on the launching stream, separate instrumented pass",
+                         "note": "fp32 mode issues 3 bf16 MMAs per product (hi*hi+hi*lo+lo*hi); bytes = fp32 operands "
+                                 "read/written once (SURVEY 8d materialise-once model)"})
 
     cb = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -286,8 +306,9 @@ def main():
     line = {
         "metric": METRIC[args.workload], "value": total_units / (ms_dev * 1e-3), "unit": unit, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "model": model, "shape_per_gpu": list(shape), "task_id": 0,
+        "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "fp32_exact": "f32", "bf16": "bf16"}[precision], "data": "synthetic",
+        "config": {"workload": args.workload, "model": model, "shape_per_gpu": list(shape), "task_id": 0, "precision": precision,
+                   "precision_detail": {"fp32": "fp32 storage/accumulate; tensor-core products on bf16 hi+lo split operands (hi*hi+hi*lo+lo*hi), parity max|d|/max|ref| 2-3e-5 vs the fp32 reference (bound 1e-4)", "fp32_exact": "FFMA fp32", "bf16": "bf16 operands, fp32 accumulate/storage, parity 7e-3 (bound 1e-2)"}[precision],
                    "weights": "random-init (name-seeded synthetic), reference architecture",
                    "parallelism": f"independent cubes x{world} (no data-path collective)",
                    "l2": "per-step working set (activations, GBs at 512x512) exceeds the 126 MB L2; no explicit flush",
