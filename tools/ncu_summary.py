@@ -39,6 +39,10 @@ def launches(path):
             unit = r.get("Metric Unit", "ns")
             scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit, 1e-3)
             rows.append((short(r["Kernel Name"]), v * scale))
+    # keep exactly one forward step: the launches between two consecutive nchw_to_tokens kernels
+    marks = [i for i, (k, _) in enumerate(rows) if "nchw_to_tokens" in k]
+    if len(marks) >= 2:
+        rows = rows[marks[0]:marks[1]]
     agg = defaultdict(lambda: [0, 0.0])
     for k, us in rows:
         agg[k][0] += 1
