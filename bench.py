@@ -204,12 +204,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from mp_hsir_b200.parallel import max_over_ranks as _max
+
     def max_over_ranks(ms: float) -> float:
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return _max(ms, device)
 
     with torch.no_grad():
         for _ in range(args.warmup):
