@@ -118,6 +118,34 @@ MPHSIR_API int mphsir_pack_bimg(const float* W, int ld, int transposed, long lon
 MPHSIR_API int mphsir_gemm_fwd(const mphsir_gemm_params* p, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Fused gated MLP (tensor-core precisions): Y = X + s_b * (fc2(value * gelu(gate)) + b2) [+ res2] with
+ * [value|gate] = LayerNorm(X) W1^T + b1 — PGSSTB.forward :719 + GatedMlp.forward :76-82 in ONE kernel; the
+ * 2*hidden intermediate stays in TMEM / shared memory.  W1img: image (mphsir_pack_bimg) of the interleaved
+ * fc1 matrix [2*hid_pad, C] ((2j,2j+1) = (value_j, gate_j), as for MPHSIR_EPI_GLU), b1 in the same order;
+ * W2img: image of fc2 [C, hid_pad].  Supported shapes: mphsir_mlp_supported(C, hid_pad).
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* X;
+  int ldx;
+  const float *ln_gamma, *ln_beta;
+  const void* W1img;
+  const float* b1;
+  const void* W2img;
+  const float* b2;
+  const float* res2; /* optional second residual (BaseBlock shortcut) */
+  int ldr2;
+  const float* row_scale; /* DropPath keep/keep_prob per sample or NULL */
+  int rows_per_batch;
+  float* Y;
+  int ldy;
+  int M, C, hid_pad;
+  int precision; /* MPHSIR_PREC_BF16X3 or MPHSIR_PREC_BF16 */
+} mphsir_mlp_params;
+
+MPHSIR_API int mphsir_mlp_supported(int C, int hid_pad);
+MPHSIR_API int mphsir_mlp_fwd(const mphsir_mlp_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Dense 3x3 convolution (zero pad 1, no bias) as an implicit GEMM over token-major input.
  * Replaces OverlapPatchEmbed.proj (:458), Downsample/Upsample bodies incl. PixelUnshuffle /
  * PixelShuffle (:436-437,:446-447), TVSP.conv_last (:581) and `output(x)+inp_img` (:841).

@@ -42,7 +42,7 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
 }
 
 template <int HD, int PARTS>
-__global__ void __launch_bounds__(128) window_attn_mma_kernel(const float* __restrict__ qkv, long long ldqkv,
+__global__ void __launch_bounds__(128, (HD <= 48 ? 6 : 4)) window_attn_mma_kernel(const float* __restrict__ qkv, long long ldqkv,
                                                               const float* __restrict__ bias, float* __restrict__ out,
                                                               long long ldo, float* __restrict__ win_mean, int H, int W,
                                                               int C, int shift) {

@@ -152,6 +152,7 @@ class Engine:
             self.sm_count = lib.device_check(self.device.index or 0)
         self.ws = Workspace(self.device)
         self.prec = PRECISIONS[net.precision]
+        self.fuse_mlp = True
         self.packed: Optional[dict] = None
         self._versions = None
         self._graphs: Dict[tuple, tuple] = {}
@@ -362,9 +363,13 @@ class Engine:
         self._gemm(v, Mt, mid, C, epi=lib.EPI_SPECTRAL, res1=x, gsrc=sa, gate=gate,
                  H=H, W=W, shift=shift, rows_per_batch=H * W, row_scale=s1)
         # x = x + DropPath(fc2(value * gelu(gate)))  with LN2 fused in front (:719, :76-82)
-        self._gemm(mid, w["fc1_w"], hidden, 2 * w["hid_pad"], ln=w["ln2"], bias=w["fc1_b"], epi=lib.EPI_GLU)
-        self._gemm(hidden, w["fc2_w"], out, C, bias=w["fc2_b"], epi=lib.EPI_RESIDUAL, res1=mid, res2=res2,
-                 rows_per_batch=H * W, row_scale=s2)
+        if self.prec != lib.PREC_FP32_SIMT and self.fuse_mlp and lib.mlp_supported(C, w["hid_pad"]):
+            lib.mlp(mid, w["ln2"], w["fc1_w"], w["fc1_b"], w["fc2_w"], w["fc2_b"], out, w["hid_pad"], self.prec,
+                    res2=res2, row_scale=s2, rows_per_batch=H * W)
+        else:
+            self._gemm(mid, w["fc1_w"], hidden, 2 * w["hid_pad"], ln=w["ln2"], bias=w["fc1_b"], epi=lib.EPI_GLU)
+            self._gemm(hidden, w["fc2_w"], out, C, bias=w["fc2_b"], epi=lib.EPI_RESIDUAL, res1=mid, res2=res2,
+                       rows_per_batch=H * W, row_scale=s2)
         if taps is not None:
             taps.update(core=core.torch().clone(), wmean=wmean[: B_ * C].view(B_, C).clone(),
                         gate=gate[: B_ * C].view(B_, C).clone(), sa=sa.torch().clone(), mid=mid.torch().clone(),

@@ -50,6 +50,16 @@ class ConvParams(C.Structure):
     ]
 
 
+class MlpParams(C.Structure):
+    _fields_ = [
+        ("X", C.c_void_p), ("ldx", C.c_int), ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p),
+        ("W1img", C.c_void_p), ("b1", C.c_void_p), ("W2img", C.c_void_p), ("b2", C.c_void_p),
+        ("res2", C.c_void_p), ("ldr2", C.c_int), ("row_scale", C.c_void_p), ("rows_per_batch", C.c_int),
+        ("Y", C.c_void_p), ("ldy", C.c_int), ("M", C.c_int), ("C", C.c_int), ("hid_pad", C.c_int),
+        ("precision", C.c_int),
+    ]
+
+
 class LocalGateParams(C.Structure):
     _fields_ = [("core_mean", C.c_void_p)] + [
         (n, C.c_void_p) for n in ("promptT", "promptb", "downT", "downb", "param", "qT", "kvT", "p2T", "p2b", "upT")
@@ -71,6 +81,8 @@ SIGNATURES = {
     "mphsir_bimg_bytes": (C.c_size_t, [_I, _I]),
     "mphsir_pack_bimg": (_I, [_VP, _I, _I, _LL, _VP, _I, _I, _I, _VP]),
     "mphsir_gemm_fwd": (_I, [C.POINTER(GemmParams), _VP]),
+    "mphsir_mlp_supported": (_I, [_I, _I]),
+    "mphsir_mlp_fwd": (_I, [C.POINTER(MlpParams), _VP]),
     "mphsir_conv3x3_fwd": (_I, [C.POINTER(ConvParams), _VP]),
     "mphsir_window_attn_fwd": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "mphsir_local_gate_fwd": (_I, [C.POINTER(LocalGateParams), _VP]),
@@ -288,6 +300,28 @@ def gemm(A: View, Bt, Y: View, N: int, *, K: Optional[int] = None, ln=None, bias
         return 2.0 * m * n * k, 4.0 * (reads + m * n_out), tag
 
     _launch("gemm_fwd", lambda: load().mphsir_gemm_fwd(C.byref(p), stream_ptr()), cost)
+
+
+def mlp_supported(Cc: int, hid_pad: int) -> bool:
+    return bool(load().mphsir_mlp_supported(Cc, hid_pad))
+
+
+def mlp(X: View, ln, W1: "Weight", b1: torch.Tensor, W2: "Weight", b2: torch.Tensor, Y: View, hid_pad: int,
+        precision: int, res2: Optional[View] = None, row_scale: Optional[torch.Tensor] = None,
+        rows_per_batch: int = 0) -> None:
+    """Fused LN -> fc1 -> value*gelu(gate) -> fc2 -> + residual(s) (one tcgen05 kernel)."""
+    p = MlpParams()
+    p.X, p.ldx = X.ptr, X.ld
+    p.ln_gamma, p.ln_beta = ln[0].data_ptr(), ln[1].data_ptr()
+    p.W1img, p.b1, p.W2img, p.b2 = W1.img.data_ptr(), b1.data_ptr(), W2.img.data_ptr(), b2.data_ptr()
+    if res2 is not None:
+        p.res2, p.ldr2 = res2.ptr, res2.ld
+    p.row_scale, p.rows_per_batch = ptr(row_scale), rows_per_batch
+    p.Y, p.ldy = Y.ptr, Y.ld
+    p.M, p.C, p.hid_pad, p.precision = X.rows, X.cols, hid_pad, precision
+    m, c = X.rows, X.cols
+    _launch("mlp_fwd", lambda: load().mphsir_mlp_fwd(C.byref(p), stream_ptr()),
+            lambda: (2.0 * m * c * 3 * hid_pad, 4.0 * m * c * (3 if res2 is None else 4), ("", "mlp_tc3", "mlp_tc1")[precision]))
 
 
 def conv3x3(X: View, Wt, Y_ptr: int, ldy: int, B: int, H: int, W: int, Cin: int, N: int,

@@ -131,3 +131,25 @@ def test_conv3x3_tc_all_output_modes(prec):
                 lib.CONV_NCHW_RES, R=dev(img), precision=prec)
     ref2 = (O.conv3x3(ref, w2.double()).permute(0, 3, 1, 2) + img.double()).float()
     assert rel_err(out.cpu(), ref2) < TOL[prec]
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("C,hid,M", [(64, 170, 1000), (128, 340, 128), (128, 340, 5000), (64, 170, 40000)])
+def test_fused_mlp_matches_gated_mlp(prec, C, hid, M):
+    """one-kernel LN -> fc1 -> value*gelu(gate) -> fc2 -> x + s*(.) + res2 (net/MP_HSIR.py:719, :76-82)."""
+    hp = E._ceil(hid, 16)
+    assert lib.mlp_supported(C, hp)
+    sd = {"fc1.weight": rnd(2 * hid, C, seed=1, scale=C ** -0.5), "fc1.bias": 0.1 * rnd(2 * hid, seed=2),
+          "fc2.weight": rnd(C, hid, seed=3, scale=hid ** -0.5), "fc2.bias": 0.1 * rnd(C, seed=4)}
+    g, be = 1 + 0.1 * rnd(C, seed=7), 0.1 * rnd(C, seed=8)
+    x, r2 = rnd(M, C, seed=9), rnd(M, C, seed=10)
+    w1, b1 = E.pack_glu_fc1(sd["fc1.weight"], sd["fc1.bias"], hid, hp)
+    w2 = E.pack_linear_t(sd["fc2.weight"], k_pad=hp)
+    W1 = weight(w1[:C, :2 * hp].t().contiguous())
+    W2 = weight(w2[:hp, :C].t().contiguous())
+    y = out_mat(M, C)
+    lib.mlp(V(dev(x)), (dev(g), dev(be)), W1, dev(b1), W2, dev(sd["fc2.bias"]), V(y), hp, prec, res2=V(dev(r2)))
+    torch.cuda.synchronize()
+    ref = (x.double() + O.gated_mlp(O.layer_norm(x.double(), g.double(), be.double()),
+                                    {k: v.double() for k, v in sd.items()}, "") + r2.double()).float()
+    assert rel_err(y.cpu(), ref) < TOL[prec]
