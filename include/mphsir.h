@@ -111,6 +111,10 @@ typedef struct {
 /* Debug: when buf != NULL every subsequent tensor-core GEMM launch writes per-CTA cycle counters of its
  * warp roles into buf[grid][16] (tools/gemm_bench.py --profile).  Pass NULL to switch it off. */
 MPHSIR_API void mphsir_debug_tc_counters(long long* buf);
+/* Debug: 0 disables the 2-CTA cluster / weight-multicast path of the tensor-core GEMM (default 1). */
+MPHSIR_API void mphsir_debug_tc_cluster(int enabled);
+MPHSIR_API void mphsir_debug_mlp_counters(long long* buf); /* same idea for the fused MLP kernel */
+MPHSIR_API void mphsir_debug_mlp_flags(int flags);          /* timing experiments (wrong results!): 1 no gelu, 2 no bias, 4 no split */
 MPHSIR_API size_t mphsir_bimg_bytes(int N, int K);
 MPHSIR_API int mphsir_pack_bimg(const float* W, int ld, int transposed, long long w_batch_stride, void* img,
                                 int batch, int N, int K, void* stream);

@@ -61,7 +61,7 @@ __device__ __forceinline__ void tile_rows(const TcArgs& p, int tile, int& m0, in
   if (p.tiles_per_batch > 0) {
     const int b = tile / p.tiles_per_batch;
     m0 = b * p.rows_per_batch + (tile - b * p.tiles_per_batch) * 128;
-    m_end = (b + 1) * p.rows_per_batch;
+    m_end = min((b + 1) * p.rows_per_batch, p.M);  // dummy tiles of a clustered launch lie beyond M
   } else {
     m0 = tile * 128;
     m_end = p.M;
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       mbar_init(smem_u32(&sm->a_full[i]), kConvThreads / 32);
       mbar_init(smem_u32(&sm->a_empty[i]), 1);
       mbar_init(smem_u32(&sm->b_full[i]), 1);
-      mbar_init(smem_u32(&sm->b_empty[i]), 1);
+      mbar_init(smem_u32(&sm->b_empty[i]), p.cluster);  // every CTA of the cluster must have consumed the block
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&sm->acc_full[i]), 1);
@@ -106,16 +106,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   if (warp == 1) tmem_alloc(smem_u32(&sm->tmem_base), 512);
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();  // the peer's mbarriers exist before any multicast copy / commit targets them
   tc_fence_after();
   const uint32_t tmem_base = sm->tmem_base;
   const int num_tiles = p.num_tiles;
+  const uint32_t crank = p.cluster > 1 ? cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
 
   if (warp == 0) {
     // =============================== B loader ===============================================
     if (lane == 0) {
       uint32_t it = 0;
       long long t_wait = 0, t_all0 = TC_T0();
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x, tit = 0; tit < p.iters; tile += gridDim.x, ++tit) {
+      if (tile >= num_tiles && p.cluster == 1) break;  // clustered CTAs run dummy tiles to stay in lock-step
         const uint8_t* bimg = reinterpret_cast<const uint8_t*>(p.Bimg);
         if (p.tiles_per_batch > 0) bimg += (size_t)(tile / p.tiles_per_batch) * p.b_batch_bytes;
         for (int pass = 0; pass < npass; ++pass) {
@@ -129,9 +133,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               const uint32_t bytes = rows * 128;
               const uint32_t full = smem_u32(&sm->b_full[slot]);
               mbar_expect_tx(full, bytes * parts);
-              for (int part = 0; part < parts; ++part) {
-                const uint8_t* src = bimg + ((size_t)(part * Ks + s) * p.Np + j * BN) * 128;
-                bulk_g2s(smem_u32(b_ring + (size_t)slot * b_slot_bytes + part * BBLK_BYTES), src, bytes, full);
+              if (p.cluster == 1) {
+                for (int part = 0; part < parts; ++part) {
+                  const uint8_t* src = bimg + ((size_t)(part * Ks + s) * p.Np + j * BN) * 128;
+                  bulk_g2s(smem_u32(b_ring + (size_t)slot * b_slot_bytes + part * BBLK_BYTES), src, bytes, full);
+                }
+              } else {
+                // each CTA of the pair fetches half of the rows and multicasts them to both
+                const uint32_t half_bytes = bytes / 2, off = crank * half_bytes;
+                for (int part = 0; part < parts; ++part) {
+                  const uint8_t* src = bimg + ((size_t)(part * Ks + s) * p.Np + j * BN) * 128 + off;
+                  bulk_g2s_mcast(smem_u32(b_ring + (size_t)slot * b_slot_bytes + part * BBLK_BYTES + off), src, half_bytes, full, cmask);
+                }
               }
             }
           }
@@ -147,7 +160,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     if (lane == 0) {
       uint32_t a_it = 0, b_it = 0, acc_it = 0;
       long long t_acc = 0, t_a = 0, t_b = 0, t_issue = 0, t_commit = 0, t_all0 = TC_T0();
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x, tit = 0; tit < p.iters; tile += gridDim.x, ++tit) {
+      if (tile >= num_tiles && p.cluster == 1) break;  // clustered CTAs run dummy tiles to stay in lock-step
         const uint32_t a_base = a_it;
         for (int pass = 0; pass < npass; ++pass, ++acc_it) {
           const int buf = acc_it & 1;
@@ -193,7 +207,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               }
               TC_ACC(t_issue, tw);
               tw = TC_T0();
-              umma_commit(smem_u32(&sm->b_empty[b_slot]));
+              if (p.cluster == 1) umma_commit(smem_u32(&sm->b_empty[b_slot]));
+              else umma_commit_mcast(smem_u32(&sm->b_empty[b_slot]), cmask);
               TC_ACC(t_commit, tw);
             }
             const bool last_use = stationary ? (pass == npass - 1) : true;
@@ -224,7 +239,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int c4 = lane & 7, rsub = lane >> 3;
     uint32_t acc_it = 0;
     long long t_wait = 0, t_tmem = 0, t_all0 = TC_T0();
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x, tit = 0; tit < p.iters; tile += gridDim.x, ++tit) {
+      if (tile >= num_tiles && p.cluster == 1) break;  // clustered CTAs run dummy tiles to stay in lock-step
       int m0, m_end;
       tile_rows(p, tile, m0, m_end);
       const int mrow0 = m0 + quad * 32;
@@ -398,7 +414,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // fallback), landing on the slot's stage_full mbarrier.  It runs as far ahead as the ring allows (4 x 32 KB),
     // so the memory-level parallelism lives in shared memory instead of registers.
     uint32_t st_it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x, tit = 0; tit < p.iters; tile += gridDim.x, ++tit) {
+      if (tile >= num_tiles && p.cluster == 1) break;  // clustered CTAs run dummy tiles to stay in lock-step
       int m0, m_end;
       tile_rows(p, tile, m0, m_end);
       const int conv_passes = stationary ? 1 : npass;
@@ -513,7 +530,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const bool ln_from_stage = has_ln && stationary;  // the whole row is resident in the ring
     long long t_slot = 0, t_ld = 0, t_all0 = TC_T0();
     uint32_t a_it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x, tit = 0; tit < p.iters; tile += gridDim.x, ++tit) {
+      if (tile >= num_tiles && p.cluster == 1) break;  // clustered CTAs run dummy tiles to stay in lock-step
       int m0, m_end;
       tile_rows(p, tile, m0, m_end);
       float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f};
@@ -668,6 +686,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   // teardown: everything issued has completed once the epilogue warps are done with the last tile
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();  // no CTA exits while its peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -724,7 +743,23 @@ static int launch_epi2(const TcArgs& a, size_t smem, int grid, cudaStream_t st) 
     }
     configured = true;
   }
-  gemm_tc_kernel<EPI, LN><<<grid, kThreads, smem, st>>>(a);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = a.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, LN>, a);
+  if (le != cudaSuccess) {
+    set_error("gemm(tc): cudaLaunchKernelEx failed: %s", cudaGetErrorString(le));
+    return MPHSIR_ERR_CUDA;
+  }
   return check_launch("gemm(tc)");
 }
 
@@ -794,6 +829,8 @@ static bool make_a_tensor_map(TcArgs& a, bool conv) {
 }
 
 static long long* g_dbg = nullptr;
+static int g_cluster_enabled = 0;  // measured: multicast halves L2 weight reads but the lock-step pairs cost ~4% in-network
+void set_cluster_enabled(int on) { g_cluster_enabled = on; }
 void set_debug_buffer(long long* p) { g_dbg = p; }
 
 int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
@@ -818,7 +855,11 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
     a.num_tiles = (a.M / a.rows_per_batch) * a.tiles_per_batch;
   }
   make_a_tensor_map(a, conv);
-  const int grid = a.num_tiles < sm_count ? a.num_tiles : sm_count;
+  // CTA pairs share every weight block (one L2 read, multicast into both CTAs) when the weights are not per-sample
+  a.cluster = (a.b_batch_bytes == 0 && a.num_tiles >= 2 && g_cluster_enabled) ? 2 : 1;
+  int grid = a.num_tiles < sm_count ? a.num_tiles : sm_count;
+  if (a.cluster == 2) grid = (grid + 1) & ~1;
+  a.iters = (a.num_tiles + grid - 1) / grid;
   if (conv && a.epi == MPHSIR_EPI_BIAS) a.epi = TC_OUT_TOKENS;
   switch (a.epi) {
     case MPHSIR_EPI_BIAS: return launch_epi<MPHSIR_EPI_BIAS>(a, smem, grid, st);
@@ -841,6 +882,7 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
 using namespace mphsir;
 
 extern "C" MPHSIR_API void mphsir_debug_tc_counters(long long* buf) { tc::set_debug_buffer(buf); }
+extern "C" MPHSIR_API void mphsir_debug_tc_cluster(int enabled) { tc::set_cluster_enabled(enabled); }
 
 extern "C" size_t mphsir_bimg_bytes(int N, int K) {
   const int Np = (N + 15) / 16 * 16, Ks = (K + 63) / 64;

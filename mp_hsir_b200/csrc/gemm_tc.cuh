@@ -37,6 +37,8 @@ struct TcArgs {
   int M, N, Np, ks;
   int parts;   // 1 = bf16x1, 2 = bf16x3 (hi/lo split)
   int na, nb;  // ring depths (set by the launcher)
+  int cluster; // CTAs per cluster (2: weight blocks are fetched once per CTA pair and multicast)
+  int iters;   // tile iterations per CTA (identical for all CTAs so that a cluster stays in lock-step)
   const float* ln_g;
   const float* ln_b;
   const float* bias;
@@ -57,6 +59,7 @@ struct TcArgs {
 
 int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st);
 void set_debug_buffer(long long* p);
+void set_cluster_enabled(int on);
 
 }  // namespace tc
 }  // namespace mphsir

@@ -47,7 +47,12 @@ struct MlpArgs {
   int M, C, N1, Np1, ks1, nj;  // nj = chunks of 128 fc1 columns = k-slabs of fc2
   int parts, nb;
   int num_tiles;
+  long long* dbg;
+  int dbg_flags;  // timing experiments only: 1 = skip gelu, 2 = skip bias shuffles, 4 = skip bf16 split
 };
+
+#define M_T0() (p.dbg ? clock64() : 0)
+#define M_ACC(var, t0) do { if (p.dbg) var += clock64() - (t0); } while (0)
 
 struct MlpSmem {
   uint64_t stage_full[M_NA], a_full[M_NA], a_empty[M_NA];
@@ -57,6 +62,57 @@ struct MlpSmem {
   uint64_t acc2_full, acc2_empty;
   uint32_t tmem_base;
 };
+
+// One GLU work item: 32 fc1 columns (= 16 hidden units) x 32 rows of TMEM lane quadrant `quad`.
+// acc1 (+ b1) -> value * gelu(gate) -> bf16 hi/lo -> chunks 2i, 2i+1 of the K-major swizzled H slab row.
+__device__ __forceinline__ void glu_item(const MlpArgs& p, uint32_t tmem_col_addr, float bias_lane, bool cols_ok, uint8_t* hdst,
+                                         int row, int i, int parts) {
+  uint32_t r[32];
+  tmem_ld32(tmem_col_addr, r);
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float hv[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int cidx = 4 * e + 2 * u;
+      const float val = __uint_as_float(r[cidx]) + __shfl_sync(0xffffffffu, bias_lane, cidx);
+      const float gat = __uint_as_float(r[cidx + 1]) + __shfl_sync(0xffffffffu, bias_lane, cidx + 1);
+      hv[u] = cols_ok ? val * gelu_erf_fast(gat) : 0.f;
+    }
+    split2(hv[0], hv[1], hi[e], lo[e]);
+  }
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const int chunk = 2 * i + cc;
+    const int off = row * 128 + ((chunk ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(hdst + off) = make_uint4(hi[4 * cc], hi[4 * cc + 1], hi[4 * cc + 2], hi[4 * cc + 3]);
+    if (parts == 2)
+      *reinterpret_cast<uint4*>(hdst + M_SLAB + off) = make_uint4(lo[4 * cc], lo[4 * cc + 1], lo[4 * cc + 2], lo[4 * cc + 3]);
+  }
+  (void)p;
+}
+
+// GLU stage of one hidden chunk for one warp: 16 warps (8 epilogue + 8 converter warps) share the 16 items
+// (4 TMEM lane quadrants x 4 column groups) of a chunk; group index `i` is fixed per warp.
+__device__ __forceinline__ void glu_chunk(const MlpArgs& p, MlpSmem* sm, uint8_t* h_ring, int h_slot_bytes, uint32_t tmem_base,
+                                          int j, uint32_t c1_it, uint32_t h_it, int quad, int i, int lane, int parts) {
+  const int buf = c1_it & 1, hs = h_it & 1;
+  const int n = j * 128 + i * 32 + lane;
+  const float bias_lane = n < p.N1 ? __ldg(p.b1 + n) : 0.f;
+  mbar_wait(smem_u32(&sm->acc1_full[buf]), (c1_it >> 1) & 1);
+  mbar_wait(smem_u32(&sm->h_empty[hs]), ((h_it >> 1) & 1) ^ 1);
+  tc_fence_after();
+  glu_item(p, tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128 + i * 32, bias_lane, j * 128 + i * 32 < p.N1,
+           h_ring + (size_t)hs * h_slot_bytes, quad * 32 + lane, i, parts);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) {
+    mbar_arrive(smem_u32(&sm->h_full[hs]));
+    mbar_arrive(smem_u32(&sm->acc1_empty[buf]));
+  }
+}
 
 __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_constant__ MlpArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -87,8 +143,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&sm->acc1_full[i]), 1);
-      mbar_init(smem_u32(&sm->acc1_empty[i]), 8);
-      mbar_init(smem_u32(&sm->h_full[i]), 8);
+      mbar_init(smem_u32(&sm->acc1_empty[i]), 16);  // 8 epilogue + 8 converter warps run the GLU stage
+      mbar_init(smem_u32(&sm->h_full[i]), 16);
       mbar_init(smem_u32(&sm->h_empty[i]), 1);
     }
     mbar_init(smem_u32(&sm->acc2_full), 1);
@@ -133,20 +189,27 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
     // =============================== MMA issuer ================================================
     if (lane == 0) {
       uint32_t a_it = 0, b_it = 0, c1_it = 0, h_it = 0, t_it = 0;
+      long long w_acc1 = 0, w_a = 0, w_b = 0, w_h = 0, w_acc2 = 0, t_all = M_T0();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_it) {
         const uint32_t a_base = a_it;
         auto fc1 = [&](int j) {
           const int buf = c1_it & 1;
+          long long tw = M_T0();
           mbar_wait(smem_u32(&sm->acc1_empty[buf]), ((c1_it >> 1) & 1) ^ 1);
+          M_ACC(w_acc1, tw);
           tc_fence_after();
           const int ncols = min(128, p.Np1 - j * 128);
           const uint32_t idesc = make_idesc(ncols);
           const uint32_t d_addr = tmem_base + buf * 128;
           for (int s = 0; s < Ks1; ++s) {
             const uint32_t a_slot = (a_base + s) % M_NA;
+            tw = M_T0();
             if (j == 0) mbar_wait(smem_u32(&sm->a_full[a_slot]), ((a_base + s) / M_NA) & 1);
+            M_ACC(w_a, tw);
             const int b_slot = b_it % p.nb;
+            tw = M_T0();
             mbar_wait(smem_u32(&sm->b_full[b_slot]), (b_it / p.nb) & 1);
+            M_ACC(w_b, tw);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(a_ring + (size_t)a_slot * M_STAGE);
             const uint32_t b_addr = smem_u32(b_ring + (size_t)b_slot * b_slot_bytes);
@@ -171,10 +234,16 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
         for (int j = 0; j < NJ; ++j) {
           if (j + 1 < NJ) fc1(j + 1);
           const int hs = h_it & 1;
+          long long tw = M_T0();
           mbar_wait(smem_u32(&sm->h_full[hs]), (h_it >> 1) & 1);
+          M_ACC(w_h, tw);
           const int b_slot = b_it % p.nb;
+          tw = M_T0();
           mbar_wait(smem_u32(&sm->b_full[b_slot]), (b_it / p.nb) & 1);
+          M_ACC(w_b, tw);
+          tw = M_T0();
           if (j == 0) mbar_wait(smem_u32(&sm->acc2_empty), (t_it & 1) ^ 1);
+          M_ACC(w_acc2, tw);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(h_ring + (size_t)hs * h_slot_bytes);
           const uint32_t b_addr = smem_u32(b_ring + (size_t)b_slot * b_slot_bytes);
@@ -198,6 +267,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
         umma_commit(smem_u32(&sm->acc2_full));
         a_it += Ks1;
       }
+      if (p.dbg) {
+        long long* d = p.dbg + blockIdx.x * 16;
+        d[0] = clock64() - t_all; d[1] = w_acc1; d[2] = w_a; d[3] = w_b; d[4] = w_h; d[5] = w_acc2;
+      }
     }
   } else if (warp < 10) {
     // =============================== GLU + final epilogue (warps 2..9) =========================
@@ -205,61 +278,16 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
     const int half = (warp - 2) >> 2;
     float* stg = staging + (warp - 2) * M_STG_FLOATS;
     const int c4 = lane & 7, rsub = lane >> 3;
-    const int row = quad * 32 + lane;  // this thread's tile row in the TMEM (row-per-thread) layout
     uint32_t c1_it = 0, h_it = 0, t_it = 0;
+    long long g_glu = 0, g_epi = 0, g_all = M_T0();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_it) {
       const int m0 = tile * 128;
-      // ---- GLU: acc1 -> H slabs ----
-      for (int j = 0; j < NJ; ++j, ++c1_it, ++h_it) {
-        const int buf = c1_it & 1, hs = h_it & 1;
-        // bias of this warp's two 32-column groups (lane holds one value, broadcast by shuffle)
-        float bl[2];
-#pragma unroll
-        for (int ii = 0; ii < 2; ++ii) {
-          const int n = j * 128 + (2 * half + ii) * 32 + lane;
-          bl[ii] = n < p.N1 ? __ldg(p.b1 + n) : 0.f;
-        }
-        mbar_wait(smem_u32(&sm->acc1_full[buf]), (c1_it >> 1) & 1);
-        mbar_wait(smem_u32(&sm->h_empty[hs]), ((h_it >> 1) & 1) ^ 1);
-        tc_fence_after();
-        uint8_t* hdst = h_ring + (size_t)hs * h_slot_bytes;
-#pragma unroll
-        for (int ii = 0; ii < 2; ++ii) {
-          const int i = 2 * half + ii;  // 32-column group inside the 128-column chunk
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128 + i * 32, r);
-          const bool cols_ok = j * 128 + i * 32 < p.N1;  // whole group valid (N1 is a multiple of 32)
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float hv[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int cidx = 4 * e + 2 * u;
-              const float val = __uint_as_float(r[cidx]) + __shfl_sync(0xffffffffu, bl[ii], cidx);
-              const float gat = __uint_as_float(r[cidx + 1]) + __shfl_sync(0xffffffffu, bl[ii], cidx + 1);
-              hv[u] = cols_ok ? val * gelu_erf_fast(gat) : 0.f;
-            }
-            split2(hv[0], hv[1], hi[e], lo[e]);
-          }
-          // hidden units 16*i .. 16*i+15 of this row -> 16-byte chunks 2i, 2i+1 of the K-major swizzled row
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int chunk = 2 * i + cc;
-            const int off = row * 128 + ((chunk ^ (row & 7)) << 4);
-            *reinterpret_cast<uint4*>(hdst + off) = make_uint4(hi[4 * cc], hi[4 * cc + 1], hi[4 * cc + 2], hi[4 * cc + 3]);
-            if (parts == 2)
-              *reinterpret_cast<uint4*>(hdst + M_SLAB + off) = make_uint4(lo[4 * cc], lo[4 * cc + 1], lo[4 * cc + 2], lo[4 * cc + 3]);
-          }
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(smem_u32(&sm->h_full[hs]));
-          mbar_arrive(smem_u32(&sm->acc1_empty[buf]));
-        }
-      }
+      // ---- GLU: acc1 -> H slabs (column group i = half; groups 2, 3 belong to the converter warps) ----
+      long long tg = M_T0();
+      for (int j = 0; j < NJ; ++j, ++c1_it, ++h_it)
+        glu_chunk(p, sm, h_ring, h_slot_bytes, tmem_base, j, c1_it, h_it, quad, half, lane, parts);
+      M_ACC(g_glu, tg);
+      long long te = M_T0();
       // ---- final epilogue: acc2 + b2, residual(s) -> Y (smem-transposed, 128-byte coalesced) ----
       mbar_wait(smem_u32(&sm->acc2_full), t_it & 1);
       tc_fence_after();
@@ -307,9 +335,14 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&sm->acc2_empty));
-      // the transpose buffers alias the H ring: nobody may start the next tile's GLU writes before every
-      // epilogue warp has left its staging area
-      asm volatile("bar.sync 2, 256;" ::: "memory");
+      // the transpose buffers alias the H ring: nobody (epilogue or converter warp) may start the next tile's GLU
+      // writes before every epilogue warp has left its staging area
+      if (tile + (int)gridDim.x < num_tiles) asm volatile("bar.sync 2, 512;" ::: "memory");
+      M_ACC(g_epi, te);
+    }
+    if (p.dbg && warp == 2 && lane == 0) {
+      long long* d = p.dbg + blockIdx.x * 16;
+      d[6] = clock64() - g_all; d[7] = 0; d[8] = 0; d[9] = g_glu; d[10] = g_epi;
     }
   } else if (warp == 18) {
     // =============================== A loader (TMA) ===========================================
@@ -329,7 +362,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
     // =============================== converters (warps 10..17): LN + split, in place ===========
     const int ct = threadIdx.x - 10 * 32;
     const int chunk = ct & 7, rbase = ct >> 3;
-    uint32_t a_it = 0;
+    const int gquad = warp & 3, ggroup = 2 + ((warp - 10) >> 2);  // this warp's GLU item (TMEM quadrant, column group)
+    uint32_t a_it = 0, c1_it = 0, h_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = tile * 128;
       float sm_[4] = {0.f, 0.f, 0.f, 0.f}, sq_[4] = {0.f, 0.f, 0.f, 0.f};
@@ -407,6 +441,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
         if (lane == 0) mbar_arrive(smem_u32(&sm->a_full[st]));
       }
       (void)m0;
+      // ---- then help with the GLU stage of this tile (H slots double as the epilogue warps' staging: wait until
+      //      they have finished the previous tile's final epilogue) ----
+      if (tile != (int)blockIdx.x) asm volatile("bar.sync 2, 512;" ::: "memory");
+      for (int j = 0; j < NJ; ++j, ++c1_it, ++h_it)
+        glu_chunk(p, sm, h_ring, h_slot_bytes, tmem_base, j, c1_it, h_it, gquad, ggroup, lane, parts);
     }
   }
 
@@ -417,6 +456,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
     tmem_dealloc(tmem_base, 512);
   }
 }
+
+long long* g_mlp_dbg = nullptr;
+int g_mlp_flags = 0;
 
 static PFN_cuTensorMapEncodeTiled mlp_encode_fn() {
   static PFN_cuTensorMapEncodeTiled fn = nullptr;
@@ -434,6 +476,9 @@ static PFN_cuTensorMapEncodeTiled mlp_encode_fn() {
 
 using namespace mphsir;
 
+extern "C" MPHSIR_API void mphsir_debug_mlp_counters(long long* buf) { tc::g_mlp_dbg = buf; }
+extern "C" MPHSIR_API void mphsir_debug_mlp_flags(int f) { tc::g_mlp_flags = f; }
+
 extern "C" int mphsir_mlp_supported(int C, int hid_pad) {
   return (C == 64 || C == 128) && hid_pad % 16 == 0 && hid_pad > 0;
 }
@@ -448,6 +493,8 @@ extern "C" int mphsir_mlp_fwd(const mphsir_mlp_params* q, void* stream) {
   if (q->row_scale) MPHSIR_REQUIRE(q->rows_per_batch > 0, "mlp: row_scale needs rows_per_batch");
   if (q->res2) MPHSIR_REQUIRE(q->ldr2 % 4 == 0, "mlp: res2 misaligned");
   tc::MlpArgs a{};
+  a.dbg = tc::g_mlp_dbg;
+  a.dbg_flags = tc::g_mlp_flags;
   a.X = q->X; a.ldx = q->ldx; a.ln_g = q->ln_gamma; a.ln_b = q->ln_beta;
   a.W1img = q->W1img; a.b1 = q->b1; a.W2img = q->W2img; a.b2 = q->b2;
   a.res2 = q->res2; a.ldr2 = q->ldr2; a.row_scale = q->row_scale; a.rows_per_batch = q->rows_per_batch;

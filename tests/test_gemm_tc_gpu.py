@@ -134,7 +134,7 @@ def test_conv3x3_tc_all_output_modes(prec):
 
 
 @pytest.mark.parametrize("prec", PRECS)
-@pytest.mark.parametrize("C,hid,M", [(64, 170, 1000), (128, 340, 128), (128, 340, 5000), (64, 170, 40000)])
+@pytest.mark.parametrize("C,hid,M", [(64, 170, 1000), (128, 340, 128), (128, 340, 5000), (64, 170, 40000), (128, 340, 150000)])
 def test_fused_mlp_matches_gated_mlp(prec, C, hid, M):
     """one-kernel LN -> fc1 -> value*gelu(gate) -> fc2 -> x + s*(.) + res2 (net/MP_HSIR.py:719, :76-82)."""
     hp = E._ceil(hid, 16)
