@@ -72,7 +72,11 @@ enum {
   MPHSIR_EPI_BIAS = 0,     /* Y = acc + bias                                                     */
   MPHSIR_EPI_RESIDUAL = 1, /* Y = res1 + scale_b*(acc + bias) [+ res2]                           */
   MPHSIR_EPI_GLU = 2,      /* packed cols (2j,2j+1)=(value_j,gate_j): Y[:,j] = v*gelu_erf(g)     */
-  MPHSIR_EPI_SPECTRAL = 3  /* Y = res1 + scale_b*(gsrc*gate[window(row)] + acc)   (:715-718)     */
+  MPHSIR_EPI_SPECTRAL = 3, /* Y = res1 + scale_b*(gsrc*gate[window(row)] + acc)   (:715-718)     */
+  /* attention proj with the global-spectral qkv 1x1 folded behind it (one GEMM over the window-attention
+   * output, weight rows [W_proj ; W_sqkv*W_proj]):  cols n <  n_split: Y[m,n] = res1 + scale_b*(acc+bias)*gate[window(row),n]
+   * (the shortcut plus the locally gated spatial branch, :715-718 / :153);  cols n >= n_split: Y2[m,n-n_split] = acc+bias */
+  MPHSIR_EPI_PROJ = 4
 };
 
 typedef struct {
@@ -102,6 +106,9 @@ typedef struct {
   int precision;       /* MPHSIR_PREC_*: FP32_SIMT uses Bt; the tensor-core modes use Bimg             */
   const void* Bimg;    /* packed bf16 hi/lo weight image (mphsir_pack_bimg) of the logical [N,K] matrix */
   long long bimg_batch_bytes; /* bytes between per-sample images; 0 = shared                          */
+  float* Y2;           /* PROJ: second output [M, ldy2] for columns >= n_split                           */
+  int ldy2;
+  int n_split;         /* PROJ: multiple of 32; gate is [B*nW, n_split]                                  */
 } mphsir_gemm_params;
 
 /* Tensor-core weight image: logical W[N,K] fp32 (row n at W + n*ld, or W + k*ld + n when

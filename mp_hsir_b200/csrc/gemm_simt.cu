@@ -48,6 +48,8 @@ struct GemmArgs {
   const float* gate;
   int H, W, shift;
   const float* row_scale;
+  float* Y2;  // EPI_PROJ: second output (columns >= n_split)
+  int ldy2, n_split;
   int Cin;
   const float* R;
 };
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const GemmArgs p) {
     float scale = 1.f;
     if (p.row_scale != nullptr) scale = __ldg(p.row_scale + m / p.rows_per_batch);
     int ib = 0, iy = 0, ix = 0;
-    if (p.epi == MPHSIR_EPI_SPECTRAL || p.epi >= OUT_UNSHUFFLE) {
+    if (p.epi == MPHSIR_EPI_SPECTRAL || p.epi == MPHSIR_EPI_PROJ || p.epi >= OUT_UNSHUFFLE) {
       ib = m / hw;
       const int rem = m - ib * hw;
       iy = rem / p.W;
@@ -294,6 +296,22 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const GemmArgs p) {
           o.z = r1.z + scale * (sa.z * gt.z + v.z);
           o.w = r1.w + scale * (sa.w * gt.w + v.w);
           *reinterpret_cast<float4*>(p.Y + (long long)m * p.ldy + n) = o;
+          break;
+        }
+        case MPHSIR_EPI_PROJ: {
+          if (n >= p.n_split) {
+            *reinterpret_cast<float4*>(p.Y2 + (long long)m * p.ldy2 + (n - p.n_split)) = v;
+            break;
+          }
+          int ys = iy - p.shift, xs = ix - p.shift;
+          if (ys < 0) ys += p.H;
+          if (xs < 0) xs += p.W;
+          const int win = ib * (hw >> 6) + (ys >> 3) * (p.W >> 3) + (xs >> 3);
+          const float4 gt = ldg4(p.gate + (long long)win * p.n_split + n);
+          const float4 r1 = ldg4(p.res1 + (long long)m * p.ldr1 + n);
+          *reinterpret_cast<float4*>(p.Y + (long long)m * p.ldy + n) =
+              make_float4(r1.x + scale * v.x * gt.x, r1.y + scale * v.y * gt.y, r1.z + scale * v.z * gt.z,
+                          r1.w + scale * v.w * gt.w);
           break;
         }
         case OUT_UNSHUFFLE: {
@@ -366,15 +384,19 @@ extern "C" int mphsir_gemm_fwd(const mphsir_gemm_params* p, void* stream) {
   MPHSIR_REQUIRE(p->ldb % 64 == 0 && p->ldb >= ((p->N + 63) / 64) * 64, "gemm: ldb=%d must be a multiple of 64 covering N=%d", p->ldb, p->N);
   MPHSIR_REQUIRE(aligned16(p->A) && aligned16(p->Bt) && aligned16(p->Y), "gemm: operands must be 16-byte aligned");
   MPHSIR_REQUIRE((p->ln_gamma == nullptr) == (p->ln_beta == nullptr), "gemm: ln_gamma/ln_beta must both be set");
-  MPHSIR_REQUIRE(p->epi >= MPHSIR_EPI_BIAS && p->epi <= MPHSIR_EPI_SPECTRAL, "gemm: unknown epilogue %d", p->epi);
-  const bool per_sample = p->b_batch_stride != 0 || p->row_scale != nullptr || p->epi == MPHSIR_EPI_SPECTRAL;
+  MPHSIR_REQUIRE(p->epi >= MPHSIR_EPI_BIAS && p->epi <= MPHSIR_EPI_PROJ, "gemm: unknown epilogue %d", p->epi);
+  const bool per_sample = p->b_batch_stride != 0 || p->row_scale != nullptr || p->epi == MPHSIR_EPI_SPECTRAL || p->epi == MPHSIR_EPI_PROJ;
   if (per_sample)
     MPHSIR_REQUIRE(p->rows_per_batch > 0 && p->M % p->rows_per_batch == 0, "gemm: rows_per_batch=%d must divide M=%d", p->rows_per_batch, p->M);
-  if (p->epi == MPHSIR_EPI_RESIDUAL || p->epi == MPHSIR_EPI_SPECTRAL)
+  if (p->epi == MPHSIR_EPI_RESIDUAL || p->epi == MPHSIR_EPI_SPECTRAL || p->epi == MPHSIR_EPI_PROJ)
     MPHSIR_REQUIRE(p->res1 != nullptr && p->ldr1 % 4 == 0 && aligned16(p->res1), "gemm: residual epilogue needs aligned res1");
   if (p->res2) MPHSIR_REQUIRE(p->ldr2 % 4 == 0 && aligned16(p->res2), "gemm: res2 misaligned");
-  if (p->epi == MPHSIR_EPI_SPECTRAL) {
-    MPHSIR_REQUIRE(p->gsrc && p->gate && p->ldg % 4 == 0, "gemm: spectral epilogue needs gsrc/gate");
+  if (p->epi == MPHSIR_EPI_PROJ) {
+    MPHSIR_REQUIRE(p->gate && p->Y2 && aligned16(p->Y2) && p->ldy2 % 4 == 0, "gemm: proj epilogue needs gate and an aligned Y2");
+    MPHSIR_REQUIRE(p->n_split > 0 && p->n_split % 32 == 0 && p->n_split < p->N, "gemm: proj epilogue needs 0 < n_split=%d < N, a multiple of 32", p->n_split);
+  }
+  if (p->epi == MPHSIR_EPI_SPECTRAL || p->epi == MPHSIR_EPI_PROJ) {
+    MPHSIR_REQUIRE(p->epi == MPHSIR_EPI_PROJ || (p->gsrc && p->gate && p->ldg % 4 == 0), "gemm: spectral epilogue needs gsrc/gate");
     MPHSIR_REQUIRE(p->H > 0 && p->W > 0 && p->H % 8 == 0 && p->W % 8 == 0 && p->H * p->W == p->rows_per_batch, "gemm: spectral epilogue needs H,W multiples of 8 with H*W == rows_per_batch");
     MPHSIR_REQUIRE(p->shift == 0 || p->shift == 4, "gemm: shift must be 0 or 4");
   }
@@ -388,7 +410,7 @@ extern "C" int mphsir_gemm_fwd(const mphsir_gemm_params* p, void* stream) {
   a.ln_g = p->ln_gamma; a.ln_b = p->ln_beta; a.bias = p->bias; a.epi = p->epi;
   a.res1 = p->res1; a.ldr1 = p->ldr1; a.res2 = p->res2; a.ldr2 = p->ldr2;
   a.gsrc = p->gsrc; a.ldg = p->ldg; a.gate = p->gate; a.H = p->H; a.W = p->W; a.shift = p->shift;
-  a.row_scale = p->row_scale;
+  a.row_scale = p->row_scale; a.Y2 = p->Y2; a.ldy2 = p->ldy2; a.n_split = p->n_split;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return p->ln_gamma ? launch<MODE_LN>(a, st, "gemm(ln)") : launch<MODE_PLAIN>(a, st, "gemm");
 }
@@ -400,15 +422,19 @@ static int gemm_tc_dispatch(const mphsir_gemm_params* p, cudaStream_t st) {
   MPHSIR_REQUIRE(p->N % 4 == 0 && p->ldy % 4 == 0, "gemm(tc): N=%d ldy=%d must be multiples of 4", p->N, p->ldy);
   MPHSIR_REQUIRE(aligned16(p->A) && aligned16(p->Y) && (reinterpret_cast<uintptr_t>(p->Bimg) & 127) == 0, "gemm(tc): operands misaligned");
   MPHSIR_REQUIRE((p->ln_gamma == nullptr) == (p->ln_beta == nullptr), "gemm(tc): ln_gamma/ln_beta must both be set");
-  MPHSIR_REQUIRE(p->epi >= MPHSIR_EPI_BIAS && p->epi <= MPHSIR_EPI_SPECTRAL, "gemm(tc): unknown epilogue %d", p->epi);
-  const bool per_sample = p->bimg_batch_bytes != 0 || p->row_scale != nullptr || p->epi == MPHSIR_EPI_SPECTRAL;
+  MPHSIR_REQUIRE(p->epi >= MPHSIR_EPI_BIAS && p->epi <= MPHSIR_EPI_PROJ, "gemm(tc): unknown epilogue %d", p->epi);
+  const bool per_sample = p->bimg_batch_bytes != 0 || p->row_scale != nullptr || p->epi == MPHSIR_EPI_SPECTRAL || p->epi == MPHSIR_EPI_PROJ;
   if (per_sample)
     MPHSIR_REQUIRE(p->rows_per_batch > 0 && p->M % p->rows_per_batch == 0, "gemm(tc): rows_per_batch=%d must divide M=%d", p->rows_per_batch, p->M);
-  if (p->epi == MPHSIR_EPI_RESIDUAL || p->epi == MPHSIR_EPI_SPECTRAL)
+  if (p->epi == MPHSIR_EPI_RESIDUAL || p->epi == MPHSIR_EPI_SPECTRAL || p->epi == MPHSIR_EPI_PROJ)
     MPHSIR_REQUIRE(p->res1 != nullptr && p->ldr1 % 4 == 0 && aligned16(p->res1), "gemm(tc): residual epilogue needs aligned res1");
   if (p->res2) MPHSIR_REQUIRE(p->ldr2 % 4 == 0 && aligned16(p->res2), "gemm(tc): res2 misaligned");
-  if (p->epi == MPHSIR_EPI_SPECTRAL) {
-    MPHSIR_REQUIRE(p->gsrc && p->gate && p->ldg % 4 == 0, "gemm(tc): spectral epilogue needs gsrc/gate");
+  if (p->epi == MPHSIR_EPI_PROJ) {
+    MPHSIR_REQUIRE(p->gate && p->Y2 && aligned16(p->Y2) && p->ldy2 % 4 == 0, "gemm(tc): proj epilogue needs gate and an aligned Y2");
+    MPHSIR_REQUIRE(p->n_split > 0 && p->n_split % 32 == 0 && p->n_split < p->N, "gemm(tc): proj epilogue needs 0 < n_split=%d < N, a multiple of 32", p->n_split);
+  }
+  if (p->epi == MPHSIR_EPI_SPECTRAL || p->epi == MPHSIR_EPI_PROJ) {
+    MPHSIR_REQUIRE(p->epi == MPHSIR_EPI_PROJ || (p->gsrc && p->gate && p->ldg % 4 == 0), "gemm(tc): spectral epilogue needs gsrc/gate");
     MPHSIR_REQUIRE(p->H > 0 && p->W > 0 && p->H % 8 == 0 && p->W % 8 == 0 && p->H * p->W == p->rows_per_batch, "gemm(tc): spectral epilogue needs H,W multiples of 8 with H*W == rows_per_batch");
     MPHSIR_REQUIRE(p->shift == 0 || p->shift == 4, "gemm(tc): shift must be 0 or 4");
   }
@@ -422,7 +448,7 @@ static int gemm_tc_dispatch(const mphsir_gemm_params* p, cudaStream_t st) {
   a.ln_g = p->ln_gamma; a.ln_b = p->ln_beta; a.bias = p->bias; a.epi = p->epi;
   a.res1 = p->res1; a.ldr1 = p->ldr1; a.res2 = p->res2; a.ldr2 = p->ldr2;
   a.gsrc = p->gsrc; a.ldg = p->ldg; a.gate = p->gate; a.H = p->H; a.W = p->W; a.shift = p->shift;
-  a.row_scale = p->row_scale;
+  a.row_scale = p->row_scale; a.Y2 = p->Y2; a.ldy2 = p->ldy2; a.n_split = p->n_split;
   return tc::launch_gemm_tc(a, false, st);
 }
 

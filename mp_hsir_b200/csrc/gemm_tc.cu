@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const int m = mrow0 + it * 4 + rsub;
         if (!DIRECT && m < m_end) {
           if (p.row_scale != nullptr) scl[it] = __ldg(p.row_scale + m / p.rows_per_batch);
-          if (EPI == MPHSIR_EPI_SPECTRAL) {
+          if (EPI == MPHSIR_EPI_SPECTRAL || EPI == MPHSIR_EPI_PROJ) {
             const int hw = p.H * p.W;
             const int b = m / hw;
             const int rem = m - b * hw;
@@ -327,6 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           // ---- staged path ----
           const int n = n0 + 4 * c4;          // this thread's 4 output columns (packed order)
           const bool col_ok = n < p.N;
+          const bool left = n0 < p.n_split;  // EPI_PROJ: warp-uniform side of the column split (n_split % 32 == 0)
           const float4 bias4 = bias_nxt;
           if (p.bias != nullptr && c0 + 64 < ncols_pass && n + 64 < p.N) bias_nxt = ldg4(p.bias + n + 64);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -354,6 +355,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 if (EPI == MPHSIR_EPI_SPECTRAL) {
                   x2[i] = ldg4(p.gsrc + (size_t)m * p.ldg + n);
                   x3[i] = ldg4(p.gate + (size_t)win[it] * p.N + n);
+                }
+                if (EPI == MPHSIR_EPI_PROJ && left) {
+                  x1[i] = ldg4(p.res1 + (size_t)m * p.ldr1 + n);
+                  x3[i] = ldg4(p.gate + (size_t)win[it] * p.n_split + n);
                 }
               }
             }
@@ -385,6 +390,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 o.z = x1[i].z + sc * (x2[i].z * x3[i].z + v.z);
                 o.w = x1[i].w + sc * (x2[i].w * x3[i].w + v.w);
                 *reinterpret_cast<float4*>(p.Y + (size_t)m * p.ldy + n) = o;
+              } else if (EPI == MPHSIR_EPI_PROJ) {
+                if (left) {
+                  const float sc = scl[it];
+                  float4 o;
+                  o.x = x1[i].x + sc * (v.x * x3[i].x);
+                  o.y = x1[i].y + sc * (v.y * x3[i].y);
+                  o.z = x1[i].z + sc * (v.z * x3[i].z);
+                  o.w = x1[i].w + sc * (v.w * x3[i].w);
+                  *reinterpret_cast<float4*>(p.Y + (size_t)m * p.ldy + n) = o;
+                } else {
+                  *reinterpret_cast<float4*>(p.Y2 + (size_t)m * p.ldy2 + (n - p.n_split)) = v;
+                }
               } else if (EPI == TC_OUT_SHUFFLE) {
                 const int hw = p.H * p.W;
                 const int b = m / hw;
@@ -866,6 +883,7 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
     case MPHSIR_EPI_RESIDUAL: return launch_epi<MPHSIR_EPI_RESIDUAL>(a, smem, grid, st);
     case MPHSIR_EPI_GLU: return launch_epi<MPHSIR_EPI_GLU>(a, smem, grid, st);
     case MPHSIR_EPI_SPECTRAL: return launch_epi<MPHSIR_EPI_SPECTRAL>(a, smem, grid, st);
+    case MPHSIR_EPI_PROJ: return launch_epi<MPHSIR_EPI_PROJ>(a, smem, grid, st);
     case TC_OUT_TOKENS: return launch_epi<TC_OUT_TOKENS>(a, smem, grid, st);
     case TC_OUT_UNSHUFFLE: return launch_epi<TC_OUT_UNSHUFFLE>(a, smem, grid, st);
     case TC_OUT_SHUFFLE: return launch_epi<TC_OUT_SHUFFLE>(a, smem, grid, st);

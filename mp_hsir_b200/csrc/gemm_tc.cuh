@@ -52,6 +52,8 @@ struct TcArgs {
   const float* gate;
   int H, W, shift;
   const float* row_scale;
+  float* Y2;  // EPI_PROJ: second output (columns >= n_split)
+  int ldy2, n_split;
   int Cin;
   const float* R;
   long long* dbg;  // optional [grid][16] cycle counters (tools/gemm_bench.py --profile); NULL in production

@@ -11,8 +11,11 @@
 //   A   = softmax_j(q_i k_j r^-0.5) ; o_i = sum_j A_ij v_j     (:146-149, outer-product attention)
 //   g   = upT^T (p2T^T o + p2b)                (:151-152)
 //
-// One CTA (128 threads) handles WPB = 8 windows so each weight element is fetched once per 8 windows;
-// every weight is read "in x out" so that thread o reads W[k][o] coalesced.
+// One CTA (160 threads) handles WPB = 8 windows so each weight element is fetched once per 8 windows;
+// every weight is read "in x out" so that thread o reads W[k][o] coalesced.  The kernel is a chain of
+// tiny dependent products, i.e. latency-bound: the r-sized weights are staged into shared memory in one
+// coalesced burst up front (overlapping the core-mean load) and the C-long logit loop keeps 16 weight
+// loads in flight, so no phase waits on a serial chain of L2 round trips.
 #include "common.cuh"
 
 namespace mphsir {
@@ -34,6 +37,11 @@ __global__ void __launch_bounds__(LG_THREADS) local_gate_kernel(const mphsir_loc
   float* o = kv + WPB * 2 * RMAX;
   float* u = o + WPB * RMAX;
   float* red = u + WPB * RMAX;    // [WPB][8]
+  float* s_param = red + WPB * 8;       // [128][r]
+  float* s_qT = s_param + PLEN * r;     // [r][r]
+  float* s_kvT = s_qT + r * r;          // [r][2r]
+  float* s_p2T = s_kvT + 2 * r * r;     // [r][r]
+  float* s_upT = s_p2T + r * r;         // [r][C]
   const int tid = threadIdx.x;
   const int w0 = blockIdx.x * WPB;
   const int nw = min(WPB, p.B_ - w0);
@@ -42,6 +50,13 @@ __global__ void __launch_bounds__(LG_THREADS) local_gate_kernel(const mphsir_loc
     const int w = e / C, c = e - w * C;
     cm[e] = (w < nw) ? __ldg(p.core_mean + (long long)(w0 + w) * C + c) : 0.f;
   }
+  for (int e = tid; e < PLEN * r; e += LG_THREADS) s_param[e] = __ldg(p.param + e);
+  for (int e = tid; e < r * r; e += LG_THREADS) {
+    s_qT[e] = __ldg(p.qT + e);
+    s_p2T[e] = __ldg(p.p2T + e);
+  }
+  for (int e = tid; e < 2 * r * r; e += LG_THREADS) s_kvT[e] = __ldg(p.kvT + e);
+  for (int e = tid; e < r * C; e += LG_THREADS) s_upT[e] = __ldg(p.upT + e);
   __syncthreads();
   // prompt logits (threads 0..127 == prompt index) and the low-rank projection (threads 128..128+r-1);
   // proj is pre-folded into promptT/downT, so both read the core mean directly.
@@ -56,11 +71,14 @@ __global__ void __launch_bounds__(LG_THREADS) local_gate_kernel(const mphsir_loc
 #pragma unroll
     for (int w = 0; w < WPB; ++w) logit[w] = b0;
     if (active) {
-#pragma unroll 4
-      for (int k = 0; k < C; ++k) {
-        const float wv = __ldg(wsrc + k * ldw + j);
+      for (int k0 = 0; k0 < C; k0 += 16) {  // C % 16 == 0 (checked on the host)
+        float wv[16];
 #pragma unroll
-        for (int w = 0; w < WPB; ++w) logit[w] = fmaf(cm[w * C + k], wv, logit[w]);
+        for (int kk = 0; kk < 16; ++kk) wv[kk] = __ldg(wsrc + (k0 + kk) * ldw + j);
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk)
+#pragma unroll
+          for (int w = 0; w < WPB; ++w) logit[w] = fmaf(cm[w * C + k0 + kk], wv[kk], logit[w]);
       }
     }
     if (!is_prompt && active) {
@@ -100,7 +118,7 @@ __global__ void __launch_bounds__(LG_THREADS) local_gate_kernel(const mphsir_loc
   for (int e = tid; e < WPB * r; e += LG_THREADS) {
     const int w = e / r, i = e - w * r;
     float a = 0.f;
-    for (int k = 0; k < PLEN; ++k) a = fmaf(pw[w * PLEN + k], __ldg(p.param + k * r + i), a);
+    for (int k = 0; k < PLEN; ++k) a = fmaf(pw[w * PLEN + k], s_param[k * r + i], a);
     sp[w * RMAX + i] = a;
   }
   __syncthreads();
@@ -108,11 +126,11 @@ __global__ void __launch_bounds__(LG_THREADS) local_gate_kernel(const mphsir_loc
     const int w = e / (3 * r), j = e - w * 3 * r;
     float a = 0.f;
     if (j < r) {
-      for (int k = 0; k < r; ++k) a = fmaf(sp[w * RMAX + k], __ldg(p.qT + k * r + j), a);
+      for (int k = 0; k < r; ++k) a = fmaf(sp[w * RMAX + k], s_qT[k * r + j], a);
       q[w * RMAX + j] = a;
     } else {
       const int jj = j - r;
-      for (int k = 0; k < r; ++k) a = fmaf(dn[w * RMAX + k], __ldg(p.kvT + k * 2 * r + jj), a);
+      for (int k = 0; k < r; ++k) a = fmaf(dn[w * RMAX + k], s_kvT[k * 2 * r + jj], a);
       kv[w * 2 * RMAX + jj] = a;
     }
   }
@@ -135,7 +153,7 @@ __global__ void __launch_bounds__(LG_THREADS) local_gate_kernel(const mphsir_loc
   for (int e = tid; e < WPB * r; e += LG_THREADS) {
     const int w = e / r, i = e - w * r;
     float a = __ldg(p.p2b + i);
-    for (int k = 0; k < r; ++k) a = fmaf(o[w * RMAX + k], __ldg(p.p2T + k * r + i), a);
+    for (int k = 0; k < r; ++k) a = fmaf(o[w * RMAX + k], s_p2T[k * r + i], a);
     u[w * RMAX + i] = a;
   }
   __syncthreads();
@@ -144,7 +162,7 @@ __global__ void __launch_bounds__(LG_THREADS) local_gate_kernel(const mphsir_loc
 #pragma unroll
     for (int w = 0; w < WPB; ++w) a[w] = 0.f;
     for (int k = 0; k < r; ++k) {
-      const float wv = __ldg(p.upT + k * C + c);
+      const float wv = s_upT[k * C + c];
 #pragma unroll
       for (int w = 0; w < WPB; ++w) a[w] = fmaf(u[w * RMAX + k], wv, a[w]);
     }
@@ -162,7 +180,18 @@ extern "C" int mphsir_local_gate_fwd(const mphsir_local_gate_params* p, void* st
   MPHSIR_REQUIRE(p && p->core_mean && p->gate, "local_gate: null operand");
   MPHSIR_REQUIRE(p->promptT && p->promptb && p->downT && p->downb && p->param && p->qT && p->kvT && p->p2T && p->p2b && p->upT, "local_gate: null weight");
   MPHSIR_REQUIRE(p->B_ > 0 && p->C > 0 && p->r > 0 && p->r <= RMAX, "local_gate: bad shape B_=%d C=%d r=%d (r<=%d)", p->B_, p->C, p->r, RMAX);
-  const size_t smem = sizeof(float) * WPB * (p->C + PLEN + 7 * RMAX + 8);
+  MPHSIR_REQUIRE(p->C % 16 == 0, "local_gate: C=%d must be a multiple of 16", p->C);
+  const size_t smem = sizeof(float) * (WPB * (p->C + PLEN + 7 * RMAX + 8) + PLEN * p->r + 4 * p->r * p->r + p->r * p->C);
+  MPHSIR_REQUIRE(smem <= 200 * 1024, "local_gate: C=%d r=%d needs %zu B of shared memory", p->C, p->r, smem);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(local_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+      set_error("local_gate: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return MPHSIR_ERR_CUDA;
+    }
+    configured = true;
+  }
   local_gate_kernel<<<(p->B_ + WPB - 1) / WPB, LG_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*p);
   return check_launch("local_gate");
 }

@@ -83,24 +83,39 @@ __global__ void __launch_bounds__(128, (HD <= 48 ? 6 : 4)) window_attn_mma_kerne
 
   // ---- gather + split q (pre-scaled), k, v -----------------------------------------------------------
   const float scale = rsqrtf((float)HD);
-  for (int idx = tid; idx < 64 * HD4; idx += 128) {
-    const int t = idx / HD4, d4 = idx - t * HD4;
-    const float* base = qkv + (long long)rows[t] * ldqkv + head * HD + d4 * 4;
-    float4 q = ldg4(base);
-    const float4 k = ldg4(base + C);
-    const float4 v = ldg4(base + 2 * C);
-    q.x *= scale; q.y *= scale; q.z *= scale; q.w *= scale;
-    const int off = t * LD + d4 * 4;
-    uint2 hi, lo;
-    split_pair(q.x, q.y, hi.x, lo.x); split_pair(q.z, q.w, hi.y, lo.y);
-    *reinterpret_cast<uint2*>(Qs + off) = hi;
-    if (PARTS == 2) *reinterpret_cast<uint2*>(Qs + ARR + off) = lo;
-    split_pair(k.x, k.y, hi.x, lo.x); split_pair(k.z, k.w, hi.y, lo.y);
-    *reinterpret_cast<uint2*>(Ks_ + off) = hi;
-    if (PARTS == 2) *reinterpret_cast<uint2*>(Ks_ + ARR + off) = lo;
-    split_pair(v.x, v.y, hi.x, lo.x); split_pair(v.z, v.w, hi.y, lo.y);
-    *reinterpret_cast<uint2*>(Vs + off) = hi;
-    if (PARTS == 2) *reinterpret_cast<uint2*>(Vs + ARR + off) = lo;
+  // all loads of a batch are issued before the first conversion, so one CTA keeps GB x 3 x 16 B per thread in
+  // flight instead of paying one global round trip per 4 channels (the gather was the top stall in ncu)
+  constexpr int ITERS = HD / 8;                       // (64 tokens x HD/4 quads) / 128 threads
+  constexpr int GB = (ITERS % 4 == 0) ? 4 : 3;        // HD 32/64 -> 4, HD 48/96 -> 3
+#pragma unroll
+  for (int it0 = 0; it0 < ITERS; it0 += GB) {
+    float4 q[GB], k[GB], v[GB];
+#pragma unroll
+    for (int u = 0; u < GB; ++u) {
+      const int idx = tid + (it0 + u) * 128;
+      const int t = idx / HD4, d4 = idx - t * HD4;
+      const float* base = qkv + (long long)rows[t] * ldqkv + head * HD + d4 * 4;
+      q[u] = ldg4(base);
+      k[u] = ldg4(base + C);
+      v[u] = ldg4(base + 2 * C);
+    }
+#pragma unroll
+    for (int u = 0; u < GB; ++u) {
+      const int idx = tid + (it0 + u) * 128;
+      const int t = idx / HD4, d4 = idx - t * HD4;
+      q[u].x *= scale; q[u].y *= scale; q[u].z *= scale; q[u].w *= scale;
+      const int off = t * LD + d4 * 4;
+      uint2 hi, lo;
+      split_pair(q[u].x, q[u].y, hi.x, lo.x); split_pair(q[u].z, q[u].w, hi.y, lo.y);
+      *reinterpret_cast<uint2*>(Qs + off) = hi;
+      if (PARTS == 2) *reinterpret_cast<uint2*>(Qs + ARR + off) = lo;
+      split_pair(k[u].x, k[u].y, hi.x, lo.x); split_pair(k[u].z, k[u].w, hi.y, lo.y);
+      *reinterpret_cast<uint2*>(Ks_ + off) = hi;
+      if (PARTS == 2) *reinterpret_cast<uint2*>(Ks_ + ARR + off) = lo;
+      split_pair(v[u].x, v[u].y, hi.x, lo.x); split_pair(v[u].z, v[u].w, hi.y, lo.y);
+      *reinterpret_cast<uint2*>(Vs + off) = hi;
+      if (PARTS == 2) *reinterpret_cast<uint2*>(Vs + ARR + off) = lo;
+    }
   }
   __syncthreads();
 

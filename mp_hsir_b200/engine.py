@@ -112,6 +112,7 @@ class Workspace:
     def __init__(self, device):
         self.device = device
         self.bufs: Dict[str, torch.Tensor] = {}
+        self.generation = 0  # bumped whenever a buffer is (re)allocated: captured graphs hold raw pointers
 
     def mat(self, name: str, rows: int, cols: int) -> View:
         n = rows * cols
@@ -119,6 +120,7 @@ class Workspace:
         if t is None or t.numel() < n:
             t = torch.empty(max(n, 1), device=self.device, dtype=torch.float32)
             self.bufs[name] = t
+            self.generation += 1
         return View(t.data_ptr(), cols, rows, cols, t)
 
     def flat(self, name: str, n: int) -> torch.Tensor:
@@ -126,6 +128,7 @@ class Workspace:
         if t is None or t.numel() < n:
             t = torch.empty(max(n, 1), device=self.device, dtype=torch.float32)
             self.bufs[name] = t
+            self.generation += 1
         return t
 
     def raw(self, name: str, nbytes: int) -> torch.Tensor:
@@ -133,6 +136,7 @@ class Workspace:
         if t is None or t.numel() < nbytes:
             t = torch.empty(max(nbytes, 128), device=self.device, dtype=torch.uint8)
             self.bufs[name] = t
+            self.generation += 1
         return t
 
     def bytes(self) -> int:
@@ -153,6 +157,7 @@ class Engine:
         self.ws = Workspace(self.device)
         self.prec = PRECISIONS[net.precision]
         self.fuse_mlp = True
+        self.fold_proj = True
         self.packed: Optional[dict] = None
         self._versions = None
         self._graphs: Dict[tuple, tuple] = {}
@@ -219,6 +224,12 @@ class Engine:
                 # done in fp64 so the fold itself adds no rounding beyond the final fp32 cast
                 pw64, pb64 = a.proj.weight.detach().double().to(self.device), a.proj.bias.detach().double().to(self.device)
                 lp64, ld64 = l.linear_prompt.weight.detach().double().to(self.device), l.linear_down.weight.detach().double().to(self.device)
+                if tc and st.dim % 32 == 0:
+                    # fold proj in front of the global-spectral qkv 1x1 as well (:216 then :101): one GEMM over the
+                    # window-attention output with rows [W_p ; W_sqkv W_p], bias [b_p ; W_sqkv b_p]  (MPHSIR_EPI_PROJ)
+                    sq64 = g.qkv.weight.detach().double().to(self.device).reshape(3 * st.dim, st.dim)
+                    d["projf_w"] = W(pack_linear_t(torch.cat([pw64, sq64 @ pw64], 0).float()), 4 * st.dim, st.dim)
+                    d["projf_b"] = torch.cat([pb64, sq64 @ pb64]).float().contiguous()
                 d["gate"] = {
                     "promptT": (lp64 @ pw64).t().float().contiguous(),
                     "promptb": (lp64 @ pb64).float().contiguous(),
@@ -341,7 +352,6 @@ class Engine:
         core = ws.mat("core", N, C)
         sa = ws.mat("sa", N, C)
         mid = ws.mat("mid", N, C)
-        hidden = ws.mat("hidden", N, w["hid_pad"])
         wmean = ws.flat("wmean", B_ * C)
         gate = ws.flat("gate", B_ * C)
         s1 = None if row_scales is None else row_scales[0]
@@ -353,20 +363,30 @@ class Engine:
         lib.window_attn(qkv, w["rpb"], core, wmean, B, H, W, C, heads, shift, precision=self.prec)
         # local spectral gate (:132-152)
         lib.local_gate(wmean, w["gate"], gate, B_, C, st.rank)
-        # attention output projection (:216) in image order
-        self._gemm(core, w["proj_w"], sa, C, bias=w["proj_b"])
-        # global spectral attention: 1x1 -> dw3x3 -> Gram/softmax/fold -> apply (:98-113)
         t3 = ws.mat("qkv", N, 3 * C)  # qkv is dead: reuse
-        self._gemm(sa, w["sqkv_w"], t3, 3 * C)
-        v, Mt = self._global_spectral("spec", t3, w["sdw"], w["temp"], w["sout_t"], B, H, W, C, heads)
-        # x = shortcut + DropPath(sa*gate + project_out(attn v))   (:715-718)
-        self._gemm(v, Mt, mid, C, epi=lib.EPI_SPECTRAL, res1=x, gsrc=sa, gate=gate,
-                 H=H, W=W, shift=shift, rows_per_batch=H * W, row_scale=s1)
+        if "projf_w" in w and self.fold_proj and taps is None:
+            # proj (:216) and the global-spectral qkv 1x1 (:101) as ONE GEMM over core; its left C columns leave as
+            # u = shortcut + DropPath(sa*gate) (:715-718, :153), so sa itself is never materialised
+            self._gemm(core, w["projf_w"], sa, 4 * C, bias=w["projf_b"], epi=lib.EPI_PROJ, res1=x, gate=gate, Y2=t3,
+                       n_split=C, H=H, W=W, shift=shift, rows_per_batch=H * W, row_scale=s1)
+            v, Mt = self._global_spectral("spec", t3, w["sdw"], w["temp"], w["sout_t"], B, H, W, C, heads)
+            # mid = u + DropPath(project_out(attn v))
+            self._gemm(v, Mt, mid, C, epi=lib.EPI_RESIDUAL, res1=sa, rows_per_batch=H * W, row_scale=s1)
+        else:
+            # attention output projection (:216) in image order
+            self._gemm(core, w["proj_w"], sa, C, bias=w["proj_b"])
+            # global spectral attention: 1x1 -> dw3x3 -> Gram/softmax/fold -> apply (:98-113)
+            self._gemm(sa, w["sqkv_w"], t3, 3 * C)
+            v, Mt = self._global_spectral("spec", t3, w["sdw"], w["temp"], w["sout_t"], B, H, W, C, heads)
+            # x = shortcut + DropPath(sa*gate + project_out(attn v))   (:715-718)
+            self._gemm(v, Mt, mid, C, epi=lib.EPI_SPECTRAL, res1=x, gsrc=sa, gate=gate,
+                       H=H, W=W, shift=shift, rows_per_batch=H * W, row_scale=s1)
         # x = x + DropPath(fc2(value * gelu(gate)))  with LN2 fused in front (:719, :76-82)
         if self.prec != lib.PREC_FP32_SIMT and self.fuse_mlp and lib.mlp_supported(C, w["hid_pad"]):
             lib.mlp(mid, w["ln2"], w["fc1_w"], w["fc1_b"], w["fc2_w"], w["fc2_b"], out, w["hid_pad"], self.prec,
                     res2=res2, row_scale=s2, rows_per_batch=H * W)
         else:
+            hidden = ws.mat("hidden", N, w["hid_pad"])
             self._gemm(mid, w["fc1_w"], hidden, 2 * w["hid_pad"], ln=w["ln2"], bias=w["fc1_b"], epi=lib.EPI_GLU)
             self._gemm(hidden, w["fc2_w"], out, C, bias=w["fc2_b"], epi=lib.EPI_RESIDUAL, res1=mid, res2=res2,
                        rows_per_batch=H * W, row_scale=s2)
@@ -471,9 +491,43 @@ class Engine:
         x = inp.detach().to(torch.float32).contiguous()
         with torch.cuda.device(self.device):
             weights = self.task_weights(task_id)
-            out = torch.empty_like(x)
-            self._run(x, weights, out)
+            if self.net.use_cuda_graph and lib.PROFILER is None:
+                out = self._run_graphed(x, weights)
+            else:
+                out = torch.empty_like(x)
+                self._run(x, weights, out)
         return out.to(inp.dtype)
+
+    def _run_graphed(self, x: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+        """Replay the whole forward as one CUDA graph per input shape (every launch goes through the
+        C ABI on torch's capture stream; all buffers are workspace-owned, so pointers are stable).
+        A workspace re-allocation (a larger shape came along) drops every captured graph."""
+        key = tuple(x.shape)
+        ent = self._graphs.get(key)
+        if ent is None or ent[0] != self.ws.generation:
+            sx, sw, so = torch.empty_like(x), torch.empty_like(weights), torch.empty_like(x)
+            sx.copy_(x)
+            sw.copy_(weights)
+            self._run(sx, sw, so)  # eager: sizes the workspace, sets kernel attributes
+            torch.cuda.current_stream().synchronize()
+            gen = self.ws.generation
+            for k in [k for k, e in self._graphs.items() if e[0] != gen]:
+                del self._graphs[k]
+            g = torch.cuda.CUDAGraph()
+            n0 = lib.LAUNCHES
+            with torch.cuda.graph(g):
+                self._run(sx, sw, so)
+            if self.ws.generation != gen:
+                raise RuntimeError("workspace grew during graph capture")
+            ent = (gen, g, sx, sw, so, lib.LAUNCHES - n0)
+            lib.LAUNCHES = n0  # capture records, it does not launch
+            self._graphs[key] = ent
+        _, g, sx, sw, so, n_kernels = ent
+        sx.copy_(x)
+        sw.copy_(weights)
+        g.replay()
+        lib.LAUNCHES += n_kernels
+        return so.clone()
 
     def _run(self, x: torch.Tensor, weights: torch.Tensor, out: torch.Tensor, taps: Optional[dict] = None):
         cfg, P, ws = self.cfg, self.packed, self.ws

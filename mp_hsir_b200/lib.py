@@ -35,6 +35,7 @@ class GemmParams(C.Structure):
         ("H", C.c_int), ("W", C.c_int), ("shift", C.c_int),
         ("row_scale", C.c_void_p),
         ("precision", C.c_int), ("Bimg", C.c_void_p), ("bimg_batch_bytes", C.c_longlong),
+        ("Y2", C.c_void_p), ("ldy2", C.c_int), ("n_split", C.c_int),
     ]
 
 
@@ -66,7 +67,7 @@ class LocalGateParams(C.Structure):
     ] + [("gate", C.c_void_p), ("B_", C.c_int), ("C", C.c_int), ("r", C.c_int)]
 
 
-EPI_BIAS, EPI_RESIDUAL, EPI_GLU, EPI_SPECTRAL = 0, 1, 2, 3
+EPI_BIAS, EPI_RESIDUAL, EPI_GLU, EPI_SPECTRAL, EPI_PROJ = 0, 1, 2, 3, 4
 PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16 = 0, 1, 2
 CONV_TOKENS, CONV_UNSHUFFLE, CONV_SHUFFLE, CONV_NCHW_RES = 0, 1, 2, 3
 
@@ -261,9 +262,12 @@ def gemm(A: View, Bt, Y: View, N: int, *, K: Optional[int] = None, ln=None, bias
          epi: int = EPI_BIAS, res1: Optional[View] = None, res2: Optional[View] = None,
          gsrc: Optional[View] = None, gate: Optional[torch.Tensor] = None, H: int = 0, W: int = 0,
          shift: int = 0, rows_per_batch: int = 0, b_batch_stride: int = 0, a_row_mod: int = 0,
-         M: Optional[int] = None, row_scale: Optional[torch.Tensor] = None) -> None:
+         M: Optional[int] = None, row_scale: Optional[torch.Tensor] = None, Y2: Optional[View] = None,
+         n_split: int = 0) -> None:
     p = GemmParams()
     p.A, p.lda, p.a_row_mod = A.ptr, A.ld, a_row_mod
+    if Y2 is not None:
+        p.Y2, p.ldy2, p.n_split = Y2.ptr, Y2.ld, n_split
     if isinstance(Bt, Weight):
         wobj = Bt
         if precision == PREC_FP32_SIMT:
@@ -299,7 +303,7 @@ def gemm(A: View, Bt, Y: View, N: int, *, K: Optional[int] = None, ln=None, bias
         m, n, k = p.M, p.N, p.K
         n_out = n // 2 if epi == EPI_GLU else n
         reads = m * k + k * n + sum(m * n for t in (res1, res2, gsrc) if t is not None)
-        tag = ("gemm", "gemm_tc3", "gemm_tc1")[precision] + ("+ln" if ln is not None else "") + ("", "+res", "+glu", "+spectral")[epi]
+        tag = ("gemm", "gemm_tc3", "gemm_tc1")[precision] + ("+ln" if ln is not None else "") + ("", "+res", "+glu", "+spectral", "+proj")[epi]
         return 2.0 * m * n * k, 4.0 * (reads + m * n_out), tag
 
     _launch("gemm_fwd", lambda: load().mphsir_gemm_fwd(C.byref(p), stream_ptr()), cost)

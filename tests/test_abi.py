@@ -60,8 +60,9 @@ def test_struct_layouts_match_header():
 #include <stddef.h>
 #include "mphsir.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(mphsir_gemm_params), offsetof(mphsir_gemm_params, row_scale),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(mphsir_gemm_params), offsetof(mphsir_gemm_params, row_scale),
          offsetof(mphsir_gemm_params, Bimg), offsetof(mphsir_gemm_params, bimg_batch_bytes),
+         offsetof(mphsir_gemm_params, Y2), offsetof(mphsir_gemm_params, n_split),
          sizeof(mphsir_conv3x3_params), offsetof(mphsir_conv3x3_params, Bimg), sizeof(mphsir_local_gate_params));
   return 0;
 }
@@ -73,6 +74,7 @@ int main(void) {
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         got = [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     G, Cv, L = lib.GemmParams, lib.ConvParams, lib.LocalGateParams
-    want = [ctypes.sizeof(G), G.row_scale.offset, G.Bimg.offset, G.bimg_batch_bytes.offset, ctypes.sizeof(Cv),
+    want = [ctypes.sizeof(G), G.row_scale.offset, G.Bimg.offset, G.bimg_batch_bytes.offset, G.Y2.offset,
+            G.n_split.offset, ctypes.sizeof(Cv),
             Cv.Bimg.offset, ctypes.sizeof(L)]
     assert got == want

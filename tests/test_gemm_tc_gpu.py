@@ -92,6 +92,29 @@ def test_gemm_tc_per_sample_weights_shared_operand_and_spectral_epilogue(prec):
     assert rel_err(y.cpu(), ref) < TOL[prec]
 
 
+@pytest.mark.parametrize("prec", [lib.PREC_FP32_SIMT] + PRECS)
+@pytest.mark.parametrize("C,shift", [(64, 4), (96, 0), (256, 4)])
+def test_gemm_proj_epilogue_split_outputs(prec, C, shift):
+    """MPHSIR_EPI_PROJ: left n_split columns -> res1 + s_b * (acc+bias) * gate[window]; the rest -> Y2."""
+    B, H, W = 2, 16, 24
+    hw = H * W
+    a = rnd(B * hw, C, seed=1)
+    w = rnd(4 * C, C, seed=2, scale=C ** -0.5)
+    bias, r1 = rnd(4 * C, seed=3), rnd(B * hw, C, seed=4)
+    gate = rnd(B * hw // 64, C, seed=5)
+    scale = torch.tensor([1.0, 0.5])
+    y, y2 = out_mat(B * hw, C), out_mat(B * hw, 3 * C)
+    wobj = Weight(E.pack_linear_t(dev(w)), None if prec == lib.PREC_FP32_SIMT else lib.pack_bimg(dev(w), 4 * C, C), 4 * C, C)
+    lib.gemm(V(dev(a)), wobj, V(y), 4 * C, bias=dev(bias), epi=lib.EPI_PROJ, res1=V(dev(r1)), gate=dev(gate), Y2=V(y2),
+             n_split=C, H=H, W=W, shift=shift, rows_per_batch=hw, row_scale=dev(scale), precision=prec)
+    full = mm64(a, w) + bias
+    g_img = O.from_windows(gate[:, None, :].expand(-1, 64, -1), shift, B, H, W).reshape(B * hw, C)
+    s_row = scale.repeat_interleave(hw)[:, None]
+    tol = 2e-6 if prec == lib.PREC_FP32_SIMT else TOL[prec]
+    assert rel_err(y.cpu(), r1 + s_row * full[:, :C] * g_img) < tol
+    assert rel_err(y2.cpu(), full[:, C:]) < tol
+
+
 @pytest.mark.parametrize("prec", PRECS)
 def test_conv3x3_tc_all_output_modes(prec):
     B, H, W, C = 2, 16, 24, 64

@@ -132,3 +132,30 @@ def test_train_mode_raises_loudly_until_backward_exists():
             net(x, torch.tensor([[1]]).cuda())
     finally:
         net.eval()
+
+
+def test_cuda_graph_replay_matches_eager_across_shapes_and_tasks():
+    """use_cuda_graph replays one captured graph per input shape; results are bit-identical to the
+    eager launches, task ids are data (not baked), and a larger shape re-captures after the
+    workspace grows."""
+    net = net_for("natural")
+    xs = [synthetic_input((2, 31, 32, 32), seed=11).cuda(), synthetic_input((1, 31, 64, 64), seed=12).cuda()]
+    tids = [torch.tensor([0, 3]).cuda(), torch.tensor([5]).cuda()]
+    with torch.no_grad():
+        eager = [net(x, t) for x, t in zip(xs, tids)]
+        eager_t = net(xs[0], torch.tensor([2, 2]).cuda())
+        net.use_cuda_graph = True
+        try:
+            before = lib.LAUNCHES
+            g0 = net(xs[0], tids[0])          # capture at 32x32
+            g1 = net(xs[1], tids[1])          # workspace grows -> 32x32 graph dropped, 64x64 captured
+            g0b = net(xs[0], tids[0])         # re-capture
+            g0c = net(xs[0], torch.tensor([2, 2]).cuda())  # replay with other task ids
+            g1b = net(xs[1], tids[1])         # replay
+            assert lib.LAUNCHES - before > 5 * 200
+        finally:
+            net.use_cuda_graph = False
+    torch.cuda.synchronize()
+    assert torch.equal(g0, eager[0]) and torch.equal(g0b, eager[0])
+    assert torch.equal(g1, eager[1]) and torch.equal(g1b, eager[1])
+    assert torch.equal(g0c, eager_t) and not torch.equal(g0c, g0)
