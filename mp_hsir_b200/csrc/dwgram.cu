@@ -198,8 +198,21 @@ __global__ void __launch_bounds__(256) dwgram_kernel(const float* __restrict__ X
   }
 }
 
-static int ctas_per_sample(int B, int tiles) {
-  int n = 296 / (B > 0 ? B : 1);
+// TMA-fed variant (dwgram_tma.cu): 64/128-channel head groups on images of at least 16x16 pixels
+int launch_tma(int cfg, bool x3, const float* X, int ldx, const float* w9, float* V, int ldv, float* partial, int B, int H,
+               int W, int ctas, cudaStream_t st);
+static bool g_use_tma = true;
+static bool tma_eligible(int cfg, int H, int W) { return g_use_tma && cfg >= 1 && cfg <= 4 && H >= 16 && W >= 16; }
+
+// CTAs per sample: the direct kernel runs 2 CTAs per SM, the TMA kernel is persistent with one CTA per SM
+static int ctas_per_sample(int B, int tiles, bool tma) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  int n = (tma ? sms : 2 * sms) / (B > 0 ? B : 1);
   if (n < 1) n = 1;
   if (n > tiles) n = tiles;
   return n;
@@ -219,7 +232,7 @@ static int launch(const float* X, int ldx, const float* w9, float* V, int ldv, f
     configured = true;
   }
   const int tiles_x = W / 8, tiles = tiles_x * (H / 8);
-  dim3 grid(ctas_per_sample(B, tiles), B);
+  dim3 grid(ctas_per_sample(B, tiles, false), B);
   dwgram_kernel<CG, CH, NG, PARTS><<<grid, 256, smem, st>>>(X, ldx, w9, V, ldv, partial, H, W, tiles_x, tiles);
   return check_launch("dwgram");
 }
@@ -241,8 +254,12 @@ static int dwgram_config(int C, int c) {
 
 extern "C" int mphsir_dwgram_supported(int C, int c) { return dwgram_config(C, c) != 0; }
 
+static int dwgram_config(int C, int c);
+
+extern "C" void mphsir_debug_dwgram_tma(int enabled) { dwg::g_use_tma = enabled != 0; }
+
 extern "C" size_t mphsir_dwgram_partial_floats(int B, int heads, int c, int H, int W, int* n_chunks) {
-  const int n = dwg::ctas_per_sample(B, (H / 8) * (W / 8));
+  const int n = dwg::ctas_per_sample(B, (H / 8) * (W / 8), dwg::tma_eligible(dwgram_config(heads * c, c), H, W));
   if (n_chunks) *n_chunks = n;
   return (size_t)B * heads * n * ((size_t)c * c + 2 * c);
 }
@@ -260,6 +277,8 @@ extern "C" int mphsir_dwgram_fwd(const float* X, int ldx, const float* w9, float
   MPHSIR_REQUIRE(cfg != 0, "dwgram: unsupported (C=%d, c=%d); use dwconv3x3 + gram_partial", C, C / heads);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool x3 = precision == MPHSIR_PREC_BF16X3;
+  if (dwg::tma_eligible(cfg, H, W))
+    return dwg::launch_tma(cfg, x3, X, ldx, w9, V, ldv, partial, B, H, W, dwg::ctas_per_sample(B, (H / 8) * (W / 8), true), st);
 #define DWG(CG, CH, NG) (x3 ? dwg::launch<CG, CH, NG, 2>(X, ldx, w9, V, ldv, partial, B, H, W, st) \
                             : dwg::launch<CG, CH, NG, 1>(X, ldx, w9, V, ldv, partial, B, H, W, st))
   switch (cfg) {

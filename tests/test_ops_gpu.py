@@ -340,7 +340,8 @@ def test_spectral_finish_matches_unfused_chain(C, heads, HW):
 
 
 @pytest.mark.parametrize("prec,tol", [(lib.PREC_BF16X3, 5e-5), (lib.PREC_BF16, 2e-2)])
-@pytest.mark.parametrize("C,heads,H,W", [(64, 2, 16, 24), (128, 2, 32, 32), (128, 4, 16, 16), (256, 8, 8, 16), (96, 2, 16, 16)])
+@pytest.mark.parametrize("C,heads,H,W", [(64, 2, 16, 24), (128, 2, 32, 32), (128, 4, 16, 16), (256, 8, 8, 16), (96, 2, 16, 16),
+                                         (64, 2, 40, 48), (128, 2, 48, 40), (128, 4, 64, 64), (256, 8, 16, 32), (128, 2, 8, 32)])
 def test_dwgram_fused_matches_dwconv_plus_gram(C, heads, H, W, prec, tol):
     """fused depthwise conv + tensor-core Gram == oracle dwconv3x3 -> q^T k, sum q^2, sum k^2 (reduced partials)."""
     B = 2
