@@ -221,6 +221,10 @@ typedef struct {
 } mphsir_local_gate_params;
 
 MPHSIR_API int mphsir_local_gate_fwd(const mphsir_local_gate_params* p, void* stream);
+/* Two-step form: the caller first computes logits[B_, ldl] = core_mean x [promptT | downT] + [promptb | downb]
+ * (128 prompt logits, then the r low-rank projections; one mphsir_gemm_fwd call) and this kernel finishes
+ * :136-152 with one warp per window.  core_mean, promptT/b and downT/b of *p are ignored. */
+MPHSIR_API int mphsir_local_gate_tail_fwd(const float* logits, int ldl, const mphsir_local_gate_params* p, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Depthwise 3x3 conv (zero pad 1, no bias) on token-major data, optional GDFN gate.

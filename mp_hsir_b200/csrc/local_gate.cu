@@ -17,6 +17,7 @@
 // coalesced burst up front (overlapping the core-mean load) and the C-long logit loop keeps 16 weight
 // loads in flight, so no phase waits on a serial chain of L2 round trips.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace mphsir {
 
@@ -172,6 +173,131 @@ __global__ void __launch_bounds__(LG_THREADS) local_gate_kernel(const mphsir_loc
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two-step variant used by the engine: the C-long products (prompt logits and the low-rank projection,
+// [B_, 128 + r] = core_mean [B_, C] x [promptT | downT] + [promptb | downb]) run as ONE GEMM on the tensor-core
+// engine, and this kernel does the r-sized remainder with one warp per window.  The fused kernel above spends
+// its time in C/16 dependent global round trips per CTA (the weights of a block are HBM-cold: they are used
+// once per forward), which no amount of unrolling hides; here the small weights arrive in shared memory through
+// one batch of bulk copies that overlaps the logits load, and every later step is shuffles + shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int LT_WARPS = 8;
+
+__global__ void __launch_bounds__(LT_WARPS * 32) local_gate_tail_kernel(const float* __restrict__ logits, int ldl,
+                                                                        const mphsir_local_gate_params p, int rp) {
+  extern __shared__ __align__(128) float sm[];
+  const int C = p.C, r = p.r;
+  float* s_param = sm;                  // [128][r]
+  float* s_qT = s_param + PLEN * r;     // [r][r]
+  float* s_kvT = s_qT + r * r;          // [r][2r]
+  float* s_p2T = s_kvT + 2 * r * r;     // [r][r]
+  float* s_upT = s_p2T + r * r;         // [r][C]
+  float* s_p2b = s_upT + r * C;         // [r] (padded to 4)
+  float* s_pw = s_p2b + ((r + 3) & ~3); // [LT_WARPS][128]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_pw + LT_WARPS * PLEN);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar_a = tc::smem_u32(bar);
+  if (tid == 0) {
+    tc::mbar_init(bar_a, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t b_param = PLEN * r * 4, b_rr = r * r * 4, b_up = r * C * 4, b_b = r * 4;
+    tc::mbar_expect_tx(bar_a, b_param + 4 * b_rr + b_up + b_b);
+    tc::bulk_g2s(tc::smem_u32(s_param), p.param, b_param, bar_a);
+    tc::bulk_g2s(tc::smem_u32(s_qT), p.qT, b_rr, bar_a);
+    tc::bulk_g2s(tc::smem_u32(s_kvT), p.kvT, 2 * b_rr, bar_a);
+    tc::bulk_g2s(tc::smem_u32(s_p2T), p.p2T, b_rr, bar_a);
+    tc::bulk_g2s(tc::smem_u32(s_upT), p.upT, b_up, bar_a);
+    tc::bulk_g2s(tc::smem_u32(s_p2b), p.p2b, b_b, bar_a);
+  }
+  __syncthreads();  // the barrier is initialised before anyone polls it
+  const int i = lane & (rp - 1);   // index inside the rank (rp = r rounded up to a power of two, <= 32)
+  const int part = lane / rp;      // 32/rp lanes share one index and split the 128-long sum
+  const int parts = 32 / rp;
+  const bool iv = i < r;
+  float* pw = s_pw + warp * PLEN;
+  const float rs = rsqrtf((float)r);
+  bool weights_ready = false;
+  for (int win = blockIdx.x * LT_WARPS + warp; win < p.B_; win += gridDim.x * LT_WARPS) {
+    const float* lrow = logits + (long long)win * ldl;
+    const float4 lg = ldg4(lrow + 4 * lane);
+    const float dn = iv ? __ldg(lrow + PLEN + i) : 0.f;
+    // softmax over the 128 prompt logits (:136)
+    const float mx = warp_max(fmaxf(fmaxf(lg.x, lg.y), fmaxf(lg.z, lg.w)));
+    float4 e = make_float4(expf(lg.x - mx), expf(lg.y - mx), expf(lg.z - mx), expf(lg.w - mx));
+    const float inv = 1.0f / warp_sum((e.x + e.y) + (e.z + e.w));
+    e.x *= inv; e.y *= inv; e.z *= inv; e.w *= inv;
+    __syncwarp();
+    *reinterpret_cast<float4*>(pw + 4 * lane) = e;
+    __syncwarp();
+    if (!weights_ready) {
+      tc::mbar_wait(bar_a, 0);
+      weights_ready = true;
+    }
+    // sp = pw @ param (:139-140): lanes (i, part) sum a 128/parts slice, then fold the parts
+    float sp = 0.f;
+    {
+      const int klen = PLEN / parts, k0 = part * klen;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      if (iv) {
+        for (int k = k0; k < k0 + klen; k += 4) {
+          a0 = fmaf(pw[k], s_param[k * r + i], a0);
+          a1 = fmaf(pw[k + 1], s_param[(k + 1) * r + i], a1);
+          a2 = fmaf(pw[k + 2], s_param[(k + 2) * r + i], a2);
+          a3 = fmaf(pw[k + 3], s_param[(k + 3) * r + i], a3);
+        }
+      }
+      sp = (a0 + a1) + (a2 + a3);
+      for (int off = rp; off < 32; off <<= 1) sp += __shfl_xor_sync(0xffffffffu, sp, off);
+    }
+    // q = qT^T sp ; [k;v] = kvT^T dn (:142-144) -- every lane of an index group holds the same values
+    float q = 0.f, kk = 0.f, vv = 0.f;
+    for (int k = 0; k < r; ++k) {
+      const float spk = __shfl_sync(0xffffffffu, sp, k);
+      const float dnk = __shfl_sync(0xffffffffu, dn, k);
+      if (iv) {
+        q = fmaf(spk, s_qT[k * r + i], q);
+        kk = fmaf(dnk, s_kvT[k * 2 * r + i], kk);
+        vv = fmaf(dnk, s_kvT[k * 2 * r + r + i], vv);
+      }
+    }
+    // outer-product attention (:146-149): A_ij = softmax_j(q_i k_j r^-0.5), o_i = sum_j A_ij v_j
+    const float qi = q * rs;
+    float mxl = -INFINITY;
+    for (int j = 0; j < r; ++j) mxl = fmaxf(mxl, qi * __shfl_sync(0xffffffffu, kk, j));
+    float den = 0.f, num = 0.f;
+    for (int j = 0; j < r; ++j) {
+      const float wgt = expf(qi * __shfl_sync(0xffffffffu, kk, j) - mxl);
+      den += wgt;
+      num = fmaf(wgt, __shfl_sync(0xffffffffu, vv, j), num);
+    }
+    const float o = iv ? num / den : 0.f;
+    // u = p2T^T o + p2b (:151)
+    float u = iv ? s_p2b[i] : 0.f;
+    for (int k = 0; k < r; ++k) {
+      const float ok = __shfl_sync(0xffffffffu, o, k);
+      if (iv) u = fmaf(ok, s_p2T[k * r + i], u);
+    }
+    // g = upT^T u (:152): lane -> channels lane, lane+32, ... in groups of 4
+    for (int c0 = 0; c0 < C; c0 += 128) {
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k = 0; k < r; ++k) {
+        const float uk = __shfl_sync(0xffffffffu, u, k);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int c = c0 + 32 * m + lane;
+          if (c < C) a[m] = fmaf(uk, s_upT[k * C + c], a[m]);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int c = c0 + 32 * m + lane;
+        if (c < C) p.gate[(long long)win * C + c] = a[m];
+      }
+    }
+  }
+  if (!weights_ready) tc::mbar_wait(bar_a, 0);  // never leave with bulk copies in flight
+}
+
 }  // namespace mphsir
 
 using namespace mphsir;
@@ -194,4 +320,35 @@ extern "C" int mphsir_local_gate_fwd(const mphsir_local_gate_params* p, void* st
   }
   local_gate_kernel<<<(p->B_ + WPB - 1) / WPB, LG_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*p);
   return check_launch("local_gate");
+}
+
+extern "C" int mphsir_local_gate_tail_fwd(const float* logits, int ldl, const mphsir_local_gate_params* p, void* stream) {
+  MPHSIR_REQUIRE(logits && p && p->gate, "local_gate_tail: null operand");
+  MPHSIR_REQUIRE(p->param && p->qT && p->kvT && p->p2T && p->p2b && p->upT, "local_gate_tail: null weight");
+  MPHSIR_REQUIRE(p->B_ > 0 && p->C > 0 && p->r >= 4 && p->r <= RMAX && p->r % 4 == 0, "local_gate_tail: bad shape B_=%d C=%d r=%d (r multiple of 4, <= %d)", p->B_, p->C, p->r, RMAX);
+  MPHSIR_REQUIRE(p->C % 4 == 0 && ldl >= PLEN + p->r && ldl % 4 == 0, "local_gate_tail: C=%d, ldl=%d must be multiples of 4 with ldl >= 128 + r", p->C, ldl);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(p->param) | reinterpret_cast<uintptr_t>(p->qT) |
+                       reinterpret_cast<uintptr_t>(p->kvT) | reinterpret_cast<uintptr_t>(p->p2T) | reinterpret_cast<uintptr_t>(p->p2b) |
+                       reinterpret_cast<uintptr_t>(p->upT);
+  MPHSIR_REQUIRE((al & 15) == 0, "local_gate_tail: logits and weights must be 16-byte aligned");
+  int rp = 4;
+  while (rp < p->r) rp <<= 1;
+  const int r = p->r;
+  const size_t smem = sizeof(float) * ((size_t)PLEN * r + 4 * r * r + (size_t)r * p->C + ((r + 3) & ~3) + LT_WARPS * PLEN) + 16;
+  MPHSIR_REQUIRE(smem <= 160 * 1024, "local_gate_tail: C=%d r=%d needs %zu B of shared memory", p->C, r, smem);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(local_gate_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) {
+      set_error("local_gate_tail: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return MPHSIR_ERR_CUDA;
+    }
+    configured = true;
+  }
+  // one window per warp while the grid still fits the machine in one wave (the kernel is a latency chain;
+  // re-staging ~20 KB of weights per CTA out of L2 is cheap next to a second trip through that chain)
+  int grid = (p->B_ + LT_WARPS - 1) / LT_WARPS;
+  if (grid > 8 * 148) grid = 8 * 148;
+  local_gate_tail_kernel<<<grid, LT_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(logits, ldl, *p, rp);
+  return check_launch("local_gate_tail");
 }

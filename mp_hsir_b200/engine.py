@@ -158,6 +158,7 @@ class Engine:
         self.prec = PRECISIONS[net.precision]
         self.fuse_mlp = True
         self.fold_proj = True
+        self.split_gate = True
         self.packed: Optional[dict] = None
         self._versions = None
         self._graphs: Dict[tuple, tuple] = {}
@@ -230,6 +231,9 @@ class Engine:
                     sq64 = g.qkv.weight.detach().double().to(self.device).reshape(3 * st.dim, st.dim)
                     d["projf_w"] = W(pack_linear_t(torch.cat([pw64, sq64 @ pw64], 0).float()), 4 * st.dim, st.dim)
                     d["projf_b"] = torch.cat([pb64, sq64 @ pb64]).float().contiguous()
+                # prompt logits and low-rank projection of the window mean as one GEMM: rows [W_prompt W_p ; W_down W_p]
+                d["gate_cat_w"] = W(pack_linear_t(torch.cat([lp64 @ pw64, ld64 @ pw64], 0).float()), PROMPT_LEN + r, st.dim)
+                d["gate_cat_b"] = torch.cat([lp64 @ pb64, ld64 @ pb64]).float().contiguous()
                 d["gate"] = {
                     "promptT": (lp64 @ pw64).t().float().contiguous(),
                     "promptb": (lp64 @ pb64).float().contiguous(),
@@ -362,7 +366,12 @@ class Engine:
         # shifted-window attention core + per-window mean (:671-683, :198-215)
         lib.window_attn(qkv, w["rpb"], core, wmean, B, H, W, C, heads, shift, precision=self.prec)
         # local spectral gate (:132-152)
-        lib.local_gate(wmean, w["gate"], gate, B_, C, st.rank)
+        if self.split_gate and st.rank % 4 == 0:
+            logits = ws.mat("gate_logits", B_, _ceil(PROMPT_LEN + st.rank, 16))
+            self._gemm(View(wmean.data_ptr(), C, B_, C, wmean), w["gate_cat_w"], logits, PROMPT_LEN + st.rank, bias=w["gate_cat_b"])
+            lib.local_gate_tail(logits, w["gate"], gate, B_, C, st.rank)
+        else:
+            lib.local_gate(wmean, w["gate"], gate, B_, C, st.rank)
         t3 = ws.mat("qkv", N, 3 * C)  # qkv is dead: reuse
         if "projf_w" in w and self.fold_proj and taps is None:
             # proj (:216) and the global-spectral qkv 1x1 (:101) as ONE GEMM over core; its left C columns leave as

@@ -91,6 +91,7 @@ SIGNATURES = {
     "mphsir_conv3x3_fwd": (_I, [C.POINTER(ConvParams), _VP]),
     "mphsir_window_attn_fwd": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "mphsir_local_gate_fwd": (_I, [C.POINTER(LocalGateParams), _VP]),
+    "mphsir_local_gate_tail_fwd": (_I, [_VP, _I, C.POINTER(LocalGateParams), _VP]),
     "mphsir_dwconv3x3_fwd": (_I, [_VP, _I, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "mphsir_gram_partial_floats": (C.c_size_t, [_I, _I, _I, _I, C.POINTER(_I)]),
     "mphsir_gram_partial_fwd": (_I, [_VP, _I, _I, _VP, _I, _I, _VP, _I, _I, _I, _I, _VP]),
@@ -371,6 +372,16 @@ def local_gate(core_mean: torch.Tensor, w: dict, gate: torch.Tensor, B_: int, Cc
     p.gate, p.B_, p.C, p.r = gate.data_ptr(), B_, Cc, r
     _launch("local_gate_fwd", lambda: load().mphsir_local_gate_fwd(C.byref(p), stream_ptr()),
             lambda: (2.0 * B_ * (Cc * 128 + 2 * Cc * r + 128 * r), 8.0 * B_ * Cc, "local_gate"))
+
+
+def local_gate_tail(logits: View, w: dict, gate: torch.Tensor, B_: int, Cc: int, r: int) -> None:
+    """r-sized remainder of the local spectral gate; `logits` [B_, 128 + r] comes from one GEMM."""
+    p = LocalGateParams()
+    for n in ("param", "qT", "kvT", "p2T", "p2b", "upT"):
+        setattr(p, n, w[n].data_ptr())
+    p.gate, p.B_, p.C, p.r = gate.data_ptr(), B_, Cc, r
+    _launch("local_gate_tail_fwd", lambda: load().mphsir_local_gate_tail_fwd(logits.ptr, logits.ld, C.byref(p), stream_ptr()),
+            lambda: (2.0 * B_ * (128 * r + 5 * r * r + Cc * r), 4.0 * B_ * (Cc + 128 + r), "local_gate_tail"))
 
 
 def dwconv3x3(X: View, w9: torch.Tensor, Y: View, B: int, H: int, W: int, Cc: int, gate_half: int = 0) -> None:

@@ -213,6 +213,14 @@ def test_local_gate(C, r):
     gate = torch.full((B_, C), float("nan"), device=DEV)
     lib.local_gate(dev(core_mean), w, gate, B_, C, r)
     assert rel_err(gate.cpu(), ref) < TOL
+    # two-step form: [prompt logits | low-rank projection] supplied by the caller (one GEMM in the engine)
+    ldl = (128 + r + 15) // 16 * 16
+    logits = torch.zeros(B_, ldl)
+    logits[:, :128] = (core_mean.double() @ w["promptT"].cpu().double() + w["promptb"].cpu().double()).float()
+    logits[:, 128:128 + r] = (core_mean.double() @ w["downT"].cpu().double() + w["downb"].cpu().double()).float()
+    gate2 = torch.full((B_, C), float("nan"), device=DEV)
+    lib.local_gate_tail(V(dev(logits)), w, gate2, B_, C, r)
+    assert rel_err(gate2.cpu(), ref) < TOL
 
 
 # ------------------------------------------------------------------------------------------------

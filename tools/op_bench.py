@@ -70,3 +70,8 @@ for (B, H, W, C, heads) in SHAPES + SMALL:
              "qT": rnd(r, r), "kvT": rnd(r, 2 * r), "p2T": rnd(r, r), "p2b": rnd(r), "upT": rnd(r, C)}
         cm, gate = rnd(B_, C), torch.empty(B_, C, device=dev)
         timeit(f"gate B_{B_} C{C} r{r}", lambda: lib.local_gate(cm, w, gate, B_, C, r), 8.0 * B_ * C)
+        logits = rnd(B_, 144)
+        timeit(f"gate_tail B_{B_} C{C} r{r}", lambda: lib.local_gate_tail(View.of(logits), w, gate, B_, C, r), 4.0 * B_ * (C + 144))
+        wcat = lib.Weight(None, lib.pack_bimg(rnd(128 + r, C), 128 + r, C), 128 + r, C)
+        bias = rnd(128 + r)
+        timeit(f"gate_gemm B_{B_} C{C} N{128 + r}", lambda: lib.gemm(View.of(cm), wcat, View.of(logits), 128 + r, bias=bias, precision=P3), 4.0 * B_ * (C + 144))
