@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
   if (warp == 0) {
     // =============================== B loader ===============================================
-    if (lane == 0) {
+    {  // warp-uniform loop, one elected lane issues the bulk copies
       uint32_t it = 0;
       long long t_wait = 0, t_all0 = TC_T0();
       for (int tile = blockIdx.x, tit = 0; tit < p.iters; tile += gridDim.x, ++tit) {
@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               const int rows = min(BN, p.Np - j * BN);
               const uint32_t bytes = rows * 128;
               const uint32_t full = smem_u32(&sm->b_full[slot]);
+              if (elect_one()) {
               mbar_expect_tx(full, bytes * parts);
               if (p.cluster == 1) {
                 for (int part = 0; part < parts; ++part) {
@@ -146,18 +147,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                   bulk_g2s_mcast(smem_u32(b_ring + (size_t)slot * b_slot_bytes + part * BBLK_BYTES + off), src, half_bytes, full, cmask);
                 }
               }
+              }
+              __syncwarp();
             }
           }
         }
       }
-      if (p.dbg) {
+      if (p.dbg && lane == 0) {
         p.dbg[blockIdx.x * 16 + 0] = clock64() - t_all0;
         p.dbg[blockIdx.x * 16 + 1] = t_wait;
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =============================================
-    if (lane == 0) {
+    // The whole warp walks the loop nest (waits are warp-uniform); one elected lane issues the MMAs and commits.
+    {
       uint32_t a_it = 0, b_it = 0, acc_it = 0;
       long long t_acc = 0, t_a = 0, t_b = 0, t_issue = 0, t_commit = 0, t_all0 = TC_T0();
       for (int tile = blockIdx.x, tit = 0; tit < p.iters; tile += gridDim.x, ++tit) {
@@ -193,33 +197,35 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               const uint32_t idesc = make_idesc(ncols);
               const uint32_t d_addr = tmem_base + buf * PASS_COLS + (j - TPP * pass) * BN;
               tw = TC_T0();
+              // descriptors of consecutive k16 steps differ by 32 bytes (+2 in the 16-byte address field)
+              const uint64_t ah0 = make_desc(a_addr), bh0 = make_desc(b_addr);
+              const uint64_t al0 = make_desc(a_addr + SLAB_BYTES), bl0 = make_desc(b_addr + BBLK_BYTES);
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t ah = make_desc(a_addr + k * 32);
-                const uint64_t bh = make_desc(b_addr + k * 32);
-                umma_bf16(d_addr, ah, bh, idesc, (s | k) != 0);
-                if (parts == 2) {
-                  const uint64_t al = make_desc(a_addr + SLAB_BYTES + k * 32);
-                  const uint64_t bl = make_desc(b_addr + BBLK_BYTES + k * 32);
-                  umma_bf16(d_addr, ah, bl, idesc, 1);
-                  umma_bf16(d_addr, al, bh, idesc, 1);
+                for (int k = 0; k < 4; ++k) {
+                  umma_bf16(d_addr, ah0 + 2 * k, bh0 + 2 * k, idesc, (s | k) != 0);
+                  if (parts == 2) {
+                    umma_bf16(d_addr, ah0 + 2 * k, bl0 + 2 * k, idesc, 1);
+                    umma_bf16(d_addr, al0 + 2 * k, bh0 + 2 * k, idesc, 1);
+                  }
                 }
+                if (p.cluster == 1) umma_commit(smem_u32(&sm->b_empty[b_slot]));
+                else umma_commit_mcast(smem_u32(&sm->b_empty[b_slot]), cmask);
               }
+              __syncwarp();
               TC_ACC(t_issue, tw);
-              tw = TC_T0();
-              if (p.cluster == 1) umma_commit(smem_u32(&sm->b_empty[b_slot]));
-              else umma_commit_mcast(smem_u32(&sm->b_empty[b_slot]), cmask);
-              TC_ACC(t_commit, tw);
             }
             const bool last_use = stationary ? (pass == npass - 1) : true;
-            if (last_use) umma_commit(smem_u32(&sm->a_empty[a_slot]));
+            if (last_use && elect_one()) umma_commit(smem_u32(&sm->a_empty[a_slot]));
+            __syncwarp();
             if (!stationary) ++a_it;
           }
-          umma_commit(smem_u32(&sm->acc_full[buf]));
+          if (elect_one()) umma_commit(smem_u32(&sm->acc_full[buf]));
+          __syncwarp();
         }
         if (stationary) a_it += Ks;
       }
-      if (p.dbg) {
+      if (p.dbg && lane == 0) {
         p.dbg[blockIdx.x * 16 + 2] = clock64() - t_all0;
         p.dbg[blockIdx.x * 16 + 3] = t_acc;
         p.dbg[blockIdx.x * 16 + 4] = t_a;

@@ -160,18 +160,21 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
 
   if (warp == 0) {
     // =============================== B loader: W1 / W2 blocks =================================
-    if (lane == 0) {
+    {  // warp-uniform loop, one elected lane issues the bulk copies
       uint32_t it = 0;
       auto load_block = [&](const uint8_t* img, int ks_total, int np_rows, int slab, int row0, int rows) {
         const int slot = it % p.nb;
         mbar_wait(smem_u32(&sm->b_empty[slot]), ((it / p.nb) & 1) ^ 1);
         const uint32_t bytes = rows * 128;
         const uint32_t full = smem_u32(&sm->b_full[slot]);
-        mbar_expect_tx(full, bytes * parts);
-        for (int part = 0; part < parts; ++part) {
-          const uint8_t* src = img + ((size_t)(part * ks_total + slab) * np_rows + row0) * 128;
-          bulk_g2s(smem_u32(b_ring + (size_t)slot * b_slot_bytes + part * M_SLAB), src, bytes, full);
+        if (elect_one()) {
+          mbar_expect_tx(full, bytes * parts);
+          for (int part = 0; part < parts; ++part) {
+            const uint8_t* src = img + ((size_t)(part * ks_total + slab) * np_rows + row0) * 128;
+            bulk_g2s(smem_u32(b_ring + (size_t)slot * b_slot_bytes + part * M_SLAB), src, bytes, full);
+          }
         }
+        __syncwarp();
         ++it;
       };
       const uint8_t* w1 = reinterpret_cast<const uint8_t*>(p.W1img);
@@ -187,7 +190,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ================================================
-    if (lane == 0) {
+    // the whole warp walks the loop nest; one elected lane issues the MMAs / commits (see tc::elect_one)
+    {
       uint32_t a_it = 0, b_it = 0, c1_it = 0, h_it = 0, t_it = 0;
       long long w_acc1 = 0, w_a = 0, w_b = 0, w_h = 0, w_acc2 = 0, t_all = M_T0();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_it) {
@@ -213,21 +217,25 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
             tc_fence_after();
             const uint32_t a_addr = smem_u32(a_ring + (size_t)a_slot * M_STAGE);
             const uint32_t b_addr = smem_u32(b_ring + (size_t)b_slot * b_slot_bytes);
+            const uint64_t ah0 = make_desc(a_addr), bh0 = make_desc(b_addr);
+            const uint64_t al0 = make_desc(a_addr + M_SLAB), bl0 = make_desc(b_addr + M_SLAB);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ah = make_desc(a_addr + k * 32), bh = make_desc(b_addr + k * 32);
-              umma_bf16(d_addr, ah, bh, idesc, (s | k) != 0);
-              if (parts == 2) {
-                const uint64_t al = make_desc(a_addr + M_SLAB + k * 32), bl = make_desc(b_addr + M_SLAB + k * 32);
-                umma_bf16(d_addr, ah, bl, idesc, 1);
-                umma_bf16(d_addr, al, bh, idesc, 1);
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(d_addr, ah0 + 2 * k, bh0 + 2 * k, idesc, (s | k) != 0);
+                if (parts == 2) {
+                  umma_bf16(d_addr, ah0 + 2 * k, bl0 + 2 * k, idesc, 1);
+                  umma_bf16(d_addr, al0 + 2 * k, bh0 + 2 * k, idesc, 1);
+                }
               }
+              umma_commit(smem_u32(&sm->b_empty[b_slot]));
+              if (j == NJ - 1) umma_commit(smem_u32(&sm->a_empty[a_slot]));  // last reader of this X slab
             }
-            umma_commit(smem_u32(&sm->b_empty[b_slot]));
+            __syncwarp();
             ++b_it;
-            if (j == NJ - 1) umma_commit(smem_u32(&sm->a_empty[a_slot]));  // last reader of this X slab
           }
-          umma_commit(smem_u32(&sm->acc1_full[buf]));
+          if (elect_one()) umma_commit(smem_u32(&sm->acc1_full[buf]));
+          __syncwarp();
           ++c1_it;
         };
         fc1(0);
@@ -249,25 +257,29 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
           const uint32_t b_addr = smem_u32(b_ring + (size_t)b_slot * b_slot_bytes);
           const uint32_t idesc = make_idesc(C);
           const uint32_t d_addr = tmem_base + ACC2_COL;
+          const uint64_t ah0 = make_desc(a_addr), bh0 = make_desc(b_addr);
+          const uint64_t al0 = make_desc(a_addr + M_SLAB), bl0 = make_desc(b_addr + M_SLAB);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ah = make_desc(a_addr + k * 32), bh = make_desc(b_addr + k * 32);
-            umma_bf16(d_addr, ah, bh, idesc, (j | k) != 0);
-            if (parts == 2) {
-              const uint64_t al = make_desc(a_addr + M_SLAB + k * 32), bl = make_desc(b_addr + M_SLAB + k * 32);
-              umma_bf16(d_addr, ah, bl, idesc, 1);
-              umma_bf16(d_addr, al, bh, idesc, 1);
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16(d_addr, ah0 + 2 * k, bh0 + 2 * k, idesc, (j | k) != 0);
+              if (parts == 2) {
+                umma_bf16(d_addr, ah0 + 2 * k, bl0 + 2 * k, idesc, 1);
+                umma_bf16(d_addr, al0 + 2 * k, bh0 + 2 * k, idesc, 1);
+              }
             }
+            umma_commit(smem_u32(&sm->b_empty[b_slot]));
+            umma_commit(smem_u32(&sm->h_empty[hs]));
           }
-          umma_commit(smem_u32(&sm->b_empty[b_slot]));
-          umma_commit(smem_u32(&sm->h_empty[hs]));
+          __syncwarp();
           ++b_it;
           ++h_it;
         }
-        umma_commit(smem_u32(&sm->acc2_full));
+        if (elect_one()) umma_commit(smem_u32(&sm->acc2_full));
+        __syncwarp();
         a_it += Ks1;
       }
-      if (p.dbg) {
+      if (p.dbg && lane == 0) {
         long long* d = p.dbg + blockIdx.x * 16;
         d[0] = clock64() - t_all; d[1] = w_acc1; d[2] = w_a; d[3] = w_b; d[4] = w_h; d[5] = w_acc2;
       }

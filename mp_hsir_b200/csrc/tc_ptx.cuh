@@ -119,6 +119,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 version 1):
 // rows are 128 B (64 bf16), 8-row groups are 1024 B apart (SBO); LBO is unused for swizzled K-major.
+// One elected lane of a fully converged warp.  The warp runs the surrounding loop uniformly and only the
+// tcgen05.mma / commit issue sits under this predicate: ptxas then keeps descriptors in uniform registers and
+// emits a bare UTCHMMA, where an `if (lane == 0)` region makes it wrap every MMA in an ELECT/BRA.U.ANY loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;

@@ -14,6 +14,9 @@ shapes = [  # name, K, N, epi, ln, extra
     ("qkv    K128 N384 ln", 128, 384, lib.EPI_BIAS, True),
     ("fc1    K128 N704 ln glu", 128, 704, lib.EPI_GLU, True),
     ("fc2    K352 N128 res", 352, 128, lib.EPI_RESIDUAL, False),
+    ("projf  K128 N512 proj", 128, 512, lib.EPI_PROJ, False),
+    ("apply  K128 N128 res", 128, 128, lib.EPI_RESIDUAL, False),
+    ("projf64 K64 N256 proj", 64, 256, lib.EPI_PROJ, False),
     ("proj64 K64 N64", 64, 64, lib.EPI_BIAS, False),
     ("qkv64  K64 N192 ln", 64, 192, lib.EPI_BIAS, True),
 ]
@@ -27,8 +30,20 @@ for name, K, N, epi, ln in shapes:
     bias = torch.randn(N, device=dev)
     g, b = torch.ones(K, device=dev), torch.zeros(K, device=dev)
     res = torch.randn(M, N, device=dev) if epi == lib.EPI_RESIDUAL else None
+    proj = epi == lib.EPI_PROJ
+    if proj:
+        Cc = N // 4
+        res = torch.randn(M, Cc, device=dev)
+        y = torch.empty(M, Cc, device=dev)
+        y2 = torch.empty(M, 3 * Cc, device=dev)
+        gate = torch.randn(M // 64, Cc, device=dev)
+        side = int(M ** 0.5)
     for prec, pn in ((lib.PREC_BF16X3, "x3"), (lib.PREC_BF16, "x1")):
         def run():
+            if proj:
+                lib.gemm(View.of(a), W, View.of(y), N, bias=bias, epi=epi, res1=View.of(res), gate=gate, Y2=View.of(y2),
+                         n_split=Cc, H=side, W=side, shift=4, rows_per_batch=M, precision=prec)
+                return
             lib.gemm(View.of(a), W, View.of(y), N, bias=bias, ln=(g, b) if ln else None, epi=epi,
                      res1=View.of(res) if res is not None else None, precision=prec)
         for _ in range(3):
@@ -51,5 +66,5 @@ for name, K, N, epi, ln in shapes:
             names = ["Bload.total", "Bload.wait_empty", "MMA.total", "MMA.wait_acc", "MMA.wait_A", "MMA.wait_B", "EPI.total",
                      "EPI.wait_full", "EPI.tmem_ld", "CV.total", "CV.bar", "CV.wait_tma", "MMA.issue", "MMA.commit", "-"]
             print("      " + "  ".join(f"{n}={v/1e3:.0f}k" for n, v in zip(names, d)))
-        byts = 4.0 * (M * K + M * n_out + (M * N if res is not None else 0))
+        byts = 4.0 * (M * K + M * n_out + (res.numel() if res is not None else 0))
         print(f"{name:28s} {pn}  {ms*1e3:8.1f} us  {byts/ms/1e6:7.1f} GB/s  {2.0*M*N*K/ms/1e9:7.1f} TFLOP/s")
