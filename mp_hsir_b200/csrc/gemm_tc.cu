@@ -54,6 +54,7 @@ struct Smem {
   uint64_t a_full[MAX_RING], a_empty[MAX_RING], b_full[MAX_RING], b_empty[MAX_RING];
   uint64_t acc_full[2], acc_empty[2];
   uint64_t stage_full[MAX_RING];  // TMA landed the fp32 slab (a_full: converted to bf16; a_empty: MMAs done)
+  uint64_t res_full[2 * 8];       // tepi: residual box landed in slot k of epilogue warp w (index 2*w + k)
   uint32_t tmem_base;
 };
 
@@ -65,6 +66,165 @@ __device__ __forceinline__ void tile_rows(const TcArgs& p, int tile, int& m0, in
   } else {
     m0 = tile * 128;
     m_end = p.M;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA epilogue (BIAS / RESIDUAL / PROJ): the register-staged epilogue below is bound by the latency of its own
+// residual loads and by store issue (ncu / role counters: 2.2k clk per 32x32 chunk for BIAS, 5.9k with a residual,
+// i.e. 4 TB/s resp. 1.5 TB/s of output at best).  Here every epilogue warp owns two 4 KB boxes [32 rows x 32 cols],
+// 128-byte swizzled: the residual of chunk i+1 is TMA-loaded into one box while chunk i is combined IN PLACE in the
+// other (row-per-thread straight out of tcgen05.ld, conflict-free through the swizzle) and leaves by a TMA store.
+// No global load ever stalls a warp, stores cost one instruction per chunk, and row/column tails are clipped by the
+// tensor maps (3-D: columns, rows inside the sample, sample).
+// ------------------------------------------------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t* eslots, uint32_t tmem_base, int num_tiles,
+                                             int npass, int warp, int lane) {
+  constexpr bool RES = EPI == MPHSIR_EPI_RESIDUAL, PROJ = EPI == MPHSIR_EPI_PROJ;
+  const int quad = warp & 3, half = (warp - 2) >> 2, ew = warp - 2;
+  uint8_t* const slot_base = eslots + (size_t)ew * 8192;          // box k at slot_base + 4096 * k
+  const uint32_t slot_a0 = smem_u32(slot_base);
+  const uint32_t rbar0 = smem_u32(&sm->res_full[2 * ew]);          // barrier k at rbar0 + 8 * k
+  uint32_t rph = 0u;                                                // bit k: phase of barrier k
+
+  auto ncols_of = [&](int pass) { return min(PASS_COLS, p.Np - pass * PASS_COLS); };
+  // next chunk of this warp after (tile, tit, pass, c0); false when the CTA's work is finished
+  auto advance = [&](int& tile, int& tit, int& pass, int& c0) -> bool {
+    c0 += 64;
+    for (;;) {
+      if (c0 < ncols_of(pass)) return true;
+      ++pass;
+      c0 = half * 32;
+      if (pass >= npass) {
+        pass = 0;
+        tile += gridDim.x;
+        ++tit;
+        if (tit >= p.iters || tile >= num_tiles) return false;
+      }
+    }
+  };
+  auto needs_res = [&](int pass, int c0) { return RES || (PROJ && pass * PASS_COLS + c0 < p.n_split); };
+  auto tile_coord = [&](int tile, int& b, int& row0) {
+    if (p.tiles_per_batch > 0) {
+      b = tile / p.tiles_per_batch;
+      row0 = (tile - b * p.tiles_per_batch) * 128 + quad * 32;
+    } else {
+      b = 0;
+      row0 = tile * 128 + quad * 32;
+    }
+  };
+  auto issue_res = [&](int tile, int pass, int c0, int slot) {  // lane 0 only
+    int b, row0;
+    tile_coord(tile, b, row0);
+    mbar_expect_tx(rbar0 + 8 * slot, 4096);
+    tma_load_3d(slot_a0 + 4096 * slot, &p.tmR, pass * PASS_COLS + c0, row0, b, rbar0 + 8 * slot);
+  };
+
+  uint32_t ck = 0;  // chunks processed by this warp (slot = ck & 1)
+  {
+    int t = blockIdx.x, ti = 0, ps = 0, c = half * 32 - 64;
+    if (num_tiles > (int)blockIdx.x && p.iters > 0 && advance(t, ti, ps, c) && needs_res(ps, c) && lane == 0) issue_res(t, ps, c, 0);
+  }
+  uint32_t acc_it = 0;
+  long long t_wait = 0, t_tmem = 0, t_all0 = TC_T0();
+  for (int tile = blockIdx.x, tit = 0; tit < p.iters && tile < num_tiles; tile += gridDim.x, ++tit) {
+    int m0, m_end;
+    tile_rows(p, tile, m0, m_end);
+    const int mm = min(m0 + quad * 32 + lane, m_end - 1);  // this thread's row (clamped: tails are clipped by TMA)
+    const float scl = p.row_scale != nullptr ? __ldg(p.row_scale + mm / p.rows_per_batch) : 1.f;
+    const float* grow = nullptr;
+    if (PROJ) {
+      const int hw = p.H * p.W;
+      const int b = mm / hw, rem = mm - b * hw;
+      const int y = rem / p.W, x = rem - y * p.W;
+      int ys = y - p.shift, xs = x - p.shift;
+      if (ys < 0) ys += p.H;
+      if (xs < 0) xs += p.W;
+      grow = p.gate + (size_t)(b * (hw >> 6) + (ys >> 3) * (p.W >> 3) + (xs >> 3)) * p.n_split;
+    }
+    int tb, trow0;
+    tile_coord(tile, tb, trow0);
+    for (int pass = 0; pass < npass; ++pass, ++acc_it) {
+      const int buf = acc_it & 1;
+      long long tw = TC_T0();
+      mbar_wait(smem_u32(&sm->acc_full[buf]), (acc_it >> 1) & 1);
+      TC_ACC(t_wait, tw);
+      tc_fence_after();
+      const int ncols_pass = ncols_of(pass);
+      for (int c0 = half * 32; c0 < ncols_pass; c0 += 64, ++ck) {
+        const int s = ck & 1;
+        const int n0 = pass * PASS_COLS + c0;
+        const bool with_res = needs_res(pass, c0);
+        const bool left = PROJ && n0 < p.n_split;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * PASS_COLS + c0;
+        uint32_t r[16];
+        tw = TC_T0();
+        tmem_ld16_nowait(taddr, r);
+        // the box written two chunks ago has been read out by its store; fetch the residual of the next chunk
+        if (lane == 0) {
+          if (ck > 0) bulk_wait_group_read<0>();
+          int t2 = tile, ti2 = tit, ps2 = pass, c2 = c0;
+          if (advance(t2, ti2, ps2, c2) && needs_res(ps2, c2)) issue_res(t2, ps2, c2, s ^ 1);
+        }
+        if (with_res) {
+          mbar_wait(rbar0 + 8 * s, (rph >> s) & 1u);
+          rph ^= 1u << s;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float4 bias4[4], g4[4];
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const int n = n0 + 16 * h + 4 * qq;
+            bias4[qq] = (p.bias != nullptr && n < p.N) ? ldg4(p.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (PROJ) g4[qq] = (left && n < p.n_split) ? ldg4(grow + n) : make_float4(1.f, 1.f, 1.f, 1.f);
+          }
+          tmem_ld_wait();
+          TC_ACC(t_tmem, tw);
+          float4 v[4];
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq)
+            v[qq] = make_float4(__uint_as_float(r[4 * qq]) + bias4[qq].x, __uint_as_float(r[4 * qq + 1]) + bias4[qq].y,
+                                __uint_as_float(r[4 * qq + 2]) + bias4[qq].z, __uint_as_float(r[4 * qq + 3]) + bias4[qq].w);
+          if (h == 0) tmem_ld16_nowait(taddr + 16, r);  // second half in flight while the first is combined
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const int q = 4 * h + qq;
+            float4* cell = reinterpret_cast<float4*>(slot_base + 4096 * s + lane * 128 + ((q ^ (lane & 7)) << 4));
+            float4 o = v[qq];
+            if (with_res) {
+              const float4 x = *cell;
+              if (PROJ) {
+                o.x = x.x + scl * (v[qq].x * g4[qq].x); o.y = x.y + scl * (v[qq].y * g4[qq].y);
+                o.z = x.z + scl * (v[qq].z * g4[qq].z); o.w = x.w + scl * (v[qq].w * g4[qq].w);
+              } else {
+                o.x = x.x + scl * v[qq].x; o.y = x.y + scl * v[qq].y;
+                o.z = x.z + scl * v[qq].z; o.w = x.w + scl * v[qq].w;
+              }
+            }
+            *cell = o;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (PROJ && !left) tma_store_3d(&p.tmY2, slot_a0 + 4096 * s, n0 - p.n_split, trow0, tb);
+          else tma_store_3d(&p.tmY, slot_a0 + 4096 * s, n0, trow0, tb);
+          bulk_commit_group();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[buf]));
+    }
+  }
+  if (lane == 0) bulk_wait_group_read<0>();  // shared memory stays allocated until the last store has read its box
+  if (p.dbg && warp == 2 && lane == 0) {
+    p.dbg[blockIdx.x * 16 + 6] = clock64() - t_all0;
+    p.dbg[blockIdx.x * 16 + 7] = t_wait;
+    p.dbg[blockIdx.x * 16 + 8] = t_tmem;
   }
 }
 
@@ -101,6 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       mbar_init(smem_u32(&sm->acc_empty[i]), kEpiWarps);
     }
     for (int i = 0; i < MAX_RING; ++i) mbar_init(smem_u32(&sm->stage_full[i]), 1);
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(smem_u32(&sm->res_full[i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&sm->tmem_base), 512);
@@ -239,6 +400,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant alternate 32-column chunks.
     // Staged path: the warp's 32x32 fp32 block goes TMEM -> registers (row per thread) -> padded smem ->
     // registers in a (4 rows x 8 float4) mapping, so every global access is a full 128-byte line segment.
+    constexpr bool TEPI_OK = (EPI == MPHSIR_EPI_BIAS || EPI == MPHSIR_EPI_RESIDUAL || EPI == MPHSIR_EPI_PROJ);
+    if (TEPI_OK && p.tepi) {
+      epilogue_tma<EPI>(p, sm, reinterpret_cast<uint8_t*>(staging), tmem_base, num_tiles, npass, warp, lane);
+    } else {
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     float* stg = staging + (warp - 2) * STG_FLOATS;
@@ -430,6 +595,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       p.dbg[blockIdx.x * 16 + 6] = clock64() - t_all0;
       p.dbg[blockIdx.x * 16 + 7] = t_wait;
       p.dbg[blockIdx.x * 16 + 8] = t_tmem;
+    }
     }
   } else if (warp == kLoaderWarp) {
     // =============================== A loader (TMA bulk copies, warp 18) ====================
@@ -751,8 +917,9 @@ __global__ void __launch_bounds__(256) pack_bimg_kernel(const float* __restrict_
   }
 }
 
-static size_t smem_bytes(int na, int nb, int parts) {
-  return 1024 + (size_t)na * STAGE_BYTES + (size_t)nb * BBLK_BYTES * parts + (size_t)kEpiWarps * STG_FLOATS * sizeof(float);
+static size_t smem_bytes(int na, int nb, int parts, int tepi) {
+  return 1024 + (size_t)na * STAGE_BYTES + (size_t)nb * BBLK_BYTES * parts +
+         (size_t)kEpiWarps * STG_FLOATS * sizeof(float) * (tepi ? 2 : 1);
 }
 
 template <int EPI, bool LN>
@@ -851,7 +1018,22 @@ static bool make_a_tensor_map(TcArgs& a, bool conv) {
   return true;
 }
 
+// 3-D map [cols, rows per sample, samples] of a token-major fp32 matrix, box [32 cols x 32 rows], 128-byte swizzle
+static bool make_epi_map(CUtensorMap* tm, const float* base, long long ld, int cols, int rows_per_batch, int batches) {
+  PFN_cuTensorMapEncodeTiled enc = get_encode_fn();
+  if (enc == nullptr || base == nullptr) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 3) != 0) return false;
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows_per_batch, (cuuint64_t)batches};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 4, (cuuint64_t)rows_per_batch * ld * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static long long* g_dbg = nullptr;
+static int g_tepi_enabled = 1;
+void set_tepi_enabled(int on) { g_tepi_enabled = on; }
 static int g_cluster_enabled = 0;  // measured: multicast halves L2 weight reads but the lock-step pairs cost ~4% in-network
 void set_cluster_enabled(int on) { g_cluster_enabled = on; }
 void set_debug_buffer(long long* p) { g_dbg = p; }
@@ -867,9 +1049,22 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
   // shared-memory plan (225 KB of 227): 1 KB barriers + A ring (32 KB slots: fp32 TMA landing zone, converted in
   // place to bf16 hi|lo) + B ring (128-row blocks) + 32 KB epilogue staging
   //   bf16x3: A 3 x 32 KB + B 3 x 32 KB        bf16x1: A 4 x 32 KB + B 4 x 16 KB
-  a.na = a.parts == 2 ? 3 : 4;
-  a.nb = a.parts == 2 ? 3 : 4;
-  const size_t smem = smem_bytes(a.na, a.nb, a.parts);
+  // TMA epilogue: plain GEMMs with a BIAS / RESIDUAL (single residual) / PROJ epilogue
+  a.tepi = 0;
+  if (g_tepi_enabled && !conv && !g_cluster_enabled &&
+      (a.epi == MPHSIR_EPI_BIAS || (a.epi == MPHSIR_EPI_RESIDUAL && a.res2 == nullptr) || a.epi == MPHSIR_EPI_PROJ)) {
+    const bool per_sample = a.tiles_per_batch > 0;
+    const int rpb = per_sample ? a.rows_per_batch : a.M, nb_ = per_sample ? a.M / a.rows_per_batch : 1;
+    const int ycols = a.epi == MPHSIR_EPI_PROJ ? a.n_split : a.N;
+    bool ok = make_epi_map(&a.tmY, a.Y, a.ldy, ycols, rpb, nb_);
+    if (ok && a.epi == MPHSIR_EPI_PROJ) ok = make_epi_map(&a.tmY2, a.Y2, a.ldy2, a.N - a.n_split, rpb, nb_);
+    if (ok && a.epi != MPHSIR_EPI_BIAS) ok = make_epi_map(&a.tmR, a.res1, a.ldr1, ycols, rpb, nb_);
+    a.tepi = ok ? 1 : 0;
+  }
+  //   with the TMA epilogue (64 KB of boxes):  bf16x3: A 3 x 32 KB + B 2 x 32 KB   bf16x1: A 3 x 32 KB + B 4 x 16 KB
+  a.na = a.parts == 2 ? 3 : (a.tepi ? 3 : 4);
+  a.nb = a.parts == 2 ? (a.tepi ? 2 : 3) : 4;
+  const size_t smem = smem_bytes(a.na, a.nb, a.parts, a.tepi);
   a.a_mode = A_ROWCOPY;
   a.seg = 64;
   if (conv) {
@@ -907,6 +1102,7 @@ using namespace mphsir;
 
 extern "C" MPHSIR_API void mphsir_debug_tc_counters(long long* buf) { tc::set_debug_buffer(buf); }
 extern "C" MPHSIR_API void mphsir_debug_tc_cluster(int enabled) { tc::set_cluster_enabled(enabled); }
+extern "C" MPHSIR_API void mphsir_debug_tc_tma_epilogue(int enabled) { tc::set_tepi_enabled(enabled); }
 
 extern "C" size_t mphsir_bimg_bytes(int N, int K) {
   const int Np = (N + 15) / 16 * 16, Ks = (K + 63) / 64;

@@ -20,6 +20,10 @@ enum { A_ROWCOPY = 0, A_TMAP2D = 1, A_TMAP4D = 2 };  // how the A loader warp fe
 
 struct TcArgs {
   alignas(64) CUtensorMap tmA;  // TMA descriptor of the fp32 A operand (2-D [M,K] or 4-D [B,H,W,C])
+  alignas(64) CUtensorMap tmY;  // TMA epilogue (tepi): output boxes [32 rows x 32 cols] of Y, 3-D [cols, rows/batch, batch]
+  alignas(64) CUtensorMap tmY2; //   EPI_PROJ: second output (columns >= n_split)
+  alignas(64) CUtensorMap tmR;  //   residual res1 (loaded into the box the result is stored from)
+  int tepi;                     // 1: TMA-fed / TMA-drained epilogue (BIAS, RESIDUAL, PROJ), 0: register-staged epilogue
   int a_mode;                   // A_*
   int seg;                      // floats per TMA box row (64 for GEMMs, gcd(Cin,64) for convs)
   int box_rows;                 // conv: pixels per TMA box (= rows of a tile: min(128, H*W))
@@ -62,6 +66,7 @@ struct TcArgs {
 int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st);
 void set_debug_buffer(long long* p);
 void set_cluster_enabled(int on);
+void set_tepi_enabled(int on);
 
 }  // namespace tc
 }  // namespace mphsir

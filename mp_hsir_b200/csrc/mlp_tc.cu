@@ -76,9 +76,13 @@ __device__ __forceinline__ void glu_item(const MlpArgs& p, uint32_t tmem_col_add
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int cidx = 4 * e + 2 * u;
-      const float val = __uint_as_float(r[cidx]) + __shfl_sync(0xffffffffu, bias_lane, cidx);
-      const float gat = __uint_as_float(r[cidx + 1]) + __shfl_sync(0xffffffffu, bias_lane, cidx + 1);
-      hv[u] = cols_ok ? val * gelu_erf_fast(gat) : 0.f;
+      // columns beyond N1 may hold stale TMEM bits: mask the INPUTS (a select), never branch around the gelu --
+      // a branch per output serialises the 16 independent erf chains of the item (ncu: 4.2k clk per item)
+      float val = __uint_as_float(r[cidx]) + __shfl_sync(0xffffffffu, bias_lane, cidx);
+      float gat = __uint_as_float(r[cidx + 1]) + __shfl_sync(0xffffffffu, bias_lane, cidx + 1);
+      val = cols_ok ? val : 0.f;
+      gat = cols_ok ? gat : 0.f;
+      hv[u] = val * gelu_erf_fast(gat);
     }
     split2(hv[0], hv[1], hi[e], lo[e]);
   }

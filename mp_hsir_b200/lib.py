@@ -83,6 +83,7 @@ SIGNATURES = {
     "mphsir_debug_mlp_counters": (None, [_VP]),
     "mphsir_debug_mlp_flags": (None, [_I]),
     "mphsir_debug_dwgram_tma": (None, [_I]),
+    "mphsir_debug_tc_tma_epilogue": (None, [_I]),
     "mphsir_bimg_bytes": (C.c_size_t, [_I, _I]),
     "mphsir_pack_bimg": (_I, [_VP, _I, _I, _LL, _VP, _I, _I, _I, _VP]),
     "mphsir_gemm_fwd": (_I, [C.POINTER(GemmParams), _VP]),
