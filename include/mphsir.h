@@ -292,6 +292,133 @@ MPHSIR_API int mphsir_bilinear_fwd(const float* X, int ldx, float* Y, int ldy, i
 MPHSIR_API int mphsir_text_prompt_fwd(const float* weights /* [B,T] */, const float* clip /* [T,512] */,
                            float* clip_b, int B, int T, void* stream);
 
+
+/* =======================================================================================
+ * Training path: backward of MP_HSIR_Net.forward (what autograd derives from net/MP_HSIR.py
+ * for train.py:50-67), clamp+L1 loss and AdamW (train.py:69).  Data-gradient GEMMs / convs reuse
+ * mphsir_gemm_fwd / mphsir_conv3x3_fwd / mphsir_dwconv3x3_fwd with transposed (flipped) weights;
+ * the entry points below are the operations that have no forward twin.  Gradient buffers are
+ * caller-owned, pre-zeroed where the text says "+=" (fp32 atomics accumulate into them).
+ * ===================================================================================== */
+
+/* output-row maps: how a packed activation column o lands in the reference parameter layout */
+enum {
+  MPHSIR_MAP_IDENTITY = 0,   /* row o, valid o < a                                                        */
+  MPHSIR_MAP_INTERLEAVE = 1, /* packed (2j,2j+1) = (first-half_j, second-half_j): row (o&1)*a + j, j < a  */
+  MPHSIR_MAP_HALVES = 2      /* halves at [0,a) and [b,b+a): rows o / a + (o-b)                            */
+};
+
+/* Weight gradient on the tensor cores: dW[map(o)*so + i*si + tap*st] += sum_m dY[m,o] * X[src(m), i].
+ *   plain          : src(m) = m                                  (nn.Linear / 1x1 conv weights)
+ *   rows_per_batch : one output matrix per sample, dw_batch_stride floats apart (dU^T v of the spectral attention)
+ *   taps = 9       : src(m) = pixel shifted by (dy,dx), zero outside the image (dense 3x3 conv weights [O,I,3,3]:
+ *                    so = 9*I, si = 9, st = 1)
+ *   x_row_mod > 0  : X has x_row_mod rows shared by every sample (TVSP visual prompt)
+ * O, I multiples of 4; i >= i_valid (0 = I) is padding.  precision: MPHSIR_PREC_BF16X3 or MPHSIR_PREC_BF16. */
+typedef struct {
+  const float* dY;
+  int lddy;
+  const float* X;
+  int ldx;
+  float* dW;
+  long long M;
+  int O, I;
+  int rows_per_batch;
+  long long dw_batch_stride;
+  int x_row_mod;
+  int H, W, taps;
+  long long so, si, st;
+  int map_mode, map_a, map_b;
+  int i_valid;
+  int precision;
+} mphsir_wgrad_params;
+MPHSIR_API int mphsir_wgrad(const mphsir_wgrad_params* p, void* stream);
+
+/* bias gradients: out[map(c)] += sum_m X[m,c] */
+MPHSIR_API int mphsir_colsum(const float* X, int ldx, float* out, long long M, int C, int map_mode, int map_a, int map_b,
+                             void* stream);
+
+/* LayerNorm (nn.LayerNorm :618-619 / WithBias_LayerNorm :354-357) materialised for training: Y = LN(X), stats[m] =
+ * (mean, rstd).  Backward: dX = add + dLN(G) (add may be NULL), dgamma/dbeta += . */
+MPHSIR_API int mphsir_layernorm_fwd(const float* X, int ldx, const float* gamma, const float* beta, float* Y, int ldy,
+                                    float* stats, long long M, int C, void* stream);
+MPHSIR_API int mphsir_layernorm_bwd(const float* X, int ldx, const float* stats, const float* gamma, const float* G, int ldg,
+                                    const float* add, int lda, float* dX, int lddx, float* dgamma, float* dbeta, long long M,
+                                    int C, void* stream);
+
+/* GatedMlp gate backward (:77-79) on the packed fc1 output H[:, (2j,2j+1)] = (value_j, gate_j): in place,
+ * H <- dH, dHid <- hidden = value*gelu(gate) (the fc2 weight-gradient operand). */
+MPHSIR_API int mphsir_glu_bwd(float* H, int ldh, float* dHid, int ldd, long long M, int hid_pad, void* stream);
+/* GDFN gate (:388-389,:262-263) un-fused from the depthwise conv for training: T = [a | b] halves of hid_pad columns,
+ * Y = gelu(a)*b; backward dT = [dY*b*gelu'(a) | dY*gelu(a)] (dT may alias T). */
+MPHSIR_API int mphsir_gdfn_gate_fwd(const float* T, int ldt, float* Y, int ldy, long long M, int hid_pad, void* stream);
+MPHSIR_API int mphsir_gdfn_gate_bwd(const float* T, int ldt, const float* dY, int ldy, float* dT, int lddt, long long M,
+                                    int hid_pad, void* stream);
+
+/* Y = alpha * row_scale[m / rows_per_batch] * X[m (mod x_row_mod)] + beta * Y  (DropPath :718-719, gradient sums) */
+MPHSIR_API int mphsir_axpby(const float* X, int ldx, float* Y, int ldy, long long M, int C, float alpha, float beta,
+                            const float* row_scale, int rows_per_batch, int x_row_mod, void* stream);
+/* Y[n,:] = sum_b X[b*rows + n, :] */
+MPHSIR_API int mphsir_batch_sum(const float* X, int ldx, float* Y, int ldy, int B, long long rows, int C, void* stream);
+
+/* Window attention core backward (Spatial_Attention.forward :195-215 + roll/partition :671-696).  dqkv [B*H*W, >=3C]
+ * image order like qkv; dbias_partial [groups, heads, 64, 64] (groups from mphsir_window_attn_bwd_groups) is reduced
+ * with mphsir_colsum and scattered to the [225, heads] table gradient by mphsir_rpb_table_bwd (+=). */
+MPHSIR_API int mphsir_window_attn_bwd_groups(int B, int H, int W, int heads);
+MPHSIR_API int mphsir_window_attn_bwd(const float* qkv, int ldqkv, const float* bias, const float* dO, int ldo, float* dqkv,
+                                      int lddq, float* dbias_partial, int groups, int B, int H, int W, int C, int heads,
+                                      int shift, void* stream);
+MPHSIR_API int mphsir_rpb_table_bwd(const float* dbias /* [heads,64,64] */, float* dtable /* [225,heads] */, int heads,
+                                    void* stream);
+
+/* Local spectral branch backward (PG_Spectral_Attention.forward :135-153), windows = shifted 8x8 windows:
+ *   window_reduce  : out[win,c] = scale * sum_{t in win} A[t,c] * (Bm ? Bm[t,c] : 1)     (window mean; dgate = sum dU*sa)
+ *   local_gate_bwd : per-window chain backward -> record rows (layout in local_gate_bwd.cu); weights in the
+ *                    reference's own [out,in] layouts
+ *   gate_apply_bwd : dSA = dU * gate[win] + dMean[win]/64 */
+MPHSIR_API int mphsir_window_reduce(const float* A, int lda, const float* Bm, int ldb, float* out, int B, int H, int W, int C,
+                                    int shift, float scale, void* stream);
+typedef struct {
+  const float *param /* [128,r] */, *q /* [r,r] */, *kv /* [2r,r] */, *proj /* [r,r] */, *proj_bias /* [r] */, *up /* [C,r] */;
+} mphsir_local_gate_bwd_weights;
+MPHSIR_API int mphsir_local_gate_bwd_record_ld(int r);
+MPHSIR_API int mphsir_local_gate_bwd(const float* LL /* [B_, >=128+r]: W_prompt m | W_down m */, int ldl, const float* dG,
+                                     const mphsir_local_gate_bwd_weights* w, float* record, int ldr, int B_, int C, int r,
+                                     void* stream);
+MPHSIR_API int mphsir_gate_apply_bwd(const float* dU, int ldu, const float* gate, const float* dMean, float* dSA, int lds,
+                                     int B, int H, int W, int C, int shift, void* stream);
+
+/* Global spectral attention backward, small-matrix part (:101-113): from P_b = dU_b^T v_b [B,C,C] (mphsir_wgrad per-sample),
+ * the reduced Gram statistics gsum [B*heads, c*c+2c] of the forward and Wout [C,C] ([out,in]) produce dWout (+=),
+ * dTemperature (+=) and Wb [B, 2C, ldwb] "in x out" with [dq | dk] = [q | k] Wb. */
+MPHSIR_API int mphsir_spectral_bwd(const float* P, long long p_batch_stride, const float* Wout, const float* gsum,
+                                   const float* temperature, float* Wb, int ldwb, long long wb_batch_stride, float* dWout,
+                                   float* dTemperature, int B, int heads, int c, void* stream);
+
+/* depthwise 3x3 weight gradient in the reference layout [C,1,3,3]: dW[map(c)*9 + tap] +=
+ * (the data gradient is mphsir_dwconv3x3_fwd with flipped taps) */
+MPHSIR_API int mphsir_dwconv3x3_wgrad(const float* X, int ldx, const float* dY, int ldy, float* dW, int B, int H, int W, int C,
+                                      int map_mode, int map_a, int map_b, void* stream);
+
+/* PixelUnshuffle(2)/PixelShuffle(2) (:437,:447) on token-major data, reference channel order c*4+2i+j.
+ * unshuffle: in [B*H*W, C] -> out [B*H/2*W/2, 4C];  shuffle: in [B*H*W, 4C] -> out [B*2H*2W, C] */
+MPHSIR_API int mphsir_pixel_unshuffle(const float* in, int ldi, float* out, int ldo, int B, int H, int W, int C, void* stream);
+MPHSIR_API int mphsir_pixel_shuffle(const float* in, int ldi, float* out, int ldo, int B, int H, int W, int C, void* stream);
+MPHSIR_API int mphsir_tokens_to_nchw(const float* in, int ld, float* out, int B, int C, int HW, void* stream);
+
+/* bilinear resize backward (dX pre-zeroed, +=) and TVSP query backward (dLearnable [T,D] +=) */
+MPHSIR_API int mphsir_bilinear_bwd(const float* dY, int ldy, float* dX, int ldx, int B, int h, int w, int H, int W, int C,
+                                   void* stream);
+MPHSIR_API int mphsir_tvsp_query_bwd(const float* dQ, int ldq, const float* clip_b, const float* weights, float* dLearnable,
+                                     int B, int T, int D, int ps, void* stream);
+
+/* loss[0] += mean|clamp(out,0,1) - clean| (train.py:58-61), dOut = d loss / d out * grad_scale */
+MPHSIR_API int mphsir_l1_clamp_loss(const float* out, const float* clean, float* dOut, float* loss, long long numel,
+                                    float grad_scale, void* stream);
+/* torch.optim.AdamW step (train.py:69) over one flat fp32 range; g is multiplied by grad_scale first */
+MPHSIR_API int mphsir_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                                 float eps, float weight_decay, int step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

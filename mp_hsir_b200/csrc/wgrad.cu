@@ -1,0 +1,282 @@
+// Weight gradients on the tensor cores:  dW[o, i] += sum_m dY[m, o] * X[src(m), i]
+//
+// The contraction runs over tokens, i.e. over the *slow* axis of both token-major operands, so neither operand
+// is K-major: tiles of 64 tokens are converted to bf16 (hi, or hi+lo for the fp32-grade mode) into shared
+// memory as [token][channel] and read by ldmatrix.trans as the A (dY, 128 channels) and B (X, 64 channels)
+// fragments of mma.sync.m16n8k16 — the same scheme as the forward Gram kernel (dwgram.cu).  Each CTA owns one
+// 128x64 tile of dW and a strided subset of the token chunks; partial sums leave through fp32 atomics into
+// the (pre-zeroed) gradient buffer, addressed through the output map so that packed / padded / interleaved
+// activation layouts land directly in the reference parameter layout.
+//
+// Modes: plain; per-sample (grid.z = sample: the d(out)^T v products of the spectral attention backward);
+// conv taps (grid.z = tap: X rows shifted by (dy,dx) with zero padding = dense 3x3 conv weight gradient);
+// x_row_mod (X shared by all samples: TVSP visual prompt).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace mphsir {
+namespace wg {
+
+constexpr int TO = 128, TI = 64, KT = 64;
+constexpr int LDA = TO + 8, LDB = TI + 8;
+
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
+  const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+  const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+  hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+}
+
+__device__ __forceinline__ int map_index(int o, int mode, int a, int b) {
+  if (mode == MPHSIR_MAP_IDENTITY) return o < a ? o : -1;
+  if (mode == MPHSIR_MAP_INTERLEAVE) {
+    const int j = o >> 1;
+    return j < a ? (o & 1) * a + j : -1;
+  }
+  if (o < b) return o < a ? o : -1;
+  return (o - b) < a ? a + (o - b) : -1;
+}
+
+struct Args {
+  const float* dY;
+  long long lddy;
+  const float* X;
+  long long ldx;
+  float* dW;
+  long long M;
+  int O, I;
+  int rows_per_batch;  // > 0: grid.z = sample
+  long long dw_batch_stride;
+  int x_row_mod;
+  int H, W, taps;  // taps == 9: grid.z = tap
+  long long so, si, st;
+  int map_mode, map_a, map_b;
+  int i_valid;
+  int tiles_i;
+};
+
+template <int PARTS>
+__global__ void __launch_bounds__(256, 2) wgrad_kernel(const Args p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __nv_bfloat16* As = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // [PARTS][KT][LDA]
+  __nv_bfloat16* Bs = As + PARTS * KT * LDA;                       // [PARTS][KT][LDB]
+  constexpr int A_ARR = KT * LDA, B_ARR = KT * LDB;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile_o = blockIdx.y / p.tiles_i, tile_i = blockIdx.y - tile_o * p.tiles_i;
+  const int o0 = tile_o * TO, i0 = tile_i * TI;
+
+  long long m_begin = 0, m_end = p.M;
+  int tap = 0, dy = 0, dx = 0;
+  float* dW = p.dW;
+  if (p.taps == 9) {
+    tap = blockIdx.z;
+    dy = tap / 3 - 1;
+    dx = tap - (tap / 3) * 3 - 1;
+  } else if (p.rows_per_batch > 0) {
+    m_begin = (long long)blockIdx.z * p.rows_per_batch;
+    m_end = m_begin + p.rows_per_batch;
+    dW += (long long)blockIdx.z * p.dw_batch_stride;
+  }
+  const long long n_chunks = (m_end - m_begin + KT - 1) / KT;
+
+  float acc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+
+  float4 ra[8], rb[4];
+  auto load_chunk = [&](long long chunk) {
+    const long long mc = m_begin + chunk * KT;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int u = tid + 256 * r;
+      const int t = u >> 5, oq = u & 31;
+      const long long m = mc + t;
+      const int o = o0 + 4 * oq;
+      ra[r] = (m < m_end && o < p.O) ? ldg4(p.dY + m * p.lddy + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int u = tid + 256 * r;
+      const int t = u >> 4, iq = u & 15;
+      long long m = mc + t;
+      const int i = i0 + 4 * iq;
+      bool ok = (m < m_end && i < p.I);
+      if (ok && p.taps == 9) {
+        const int x = (int)(m % p.W), y = (int)((m / p.W) % p.H);
+        ok = (unsigned)(y + dy) < (unsigned)p.H && (unsigned)(x + dx) < (unsigned)p.W;
+        m += (long long)dy * p.W + dx;
+      }
+      if (ok && p.x_row_mod > 0) m %= p.x_row_mod;
+      rb[r] = ok ? ldg4(p.X + m * p.ldx + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto store_chunk = [&]() {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int u = tid + 256 * r;
+      const int t = u >> 5, oq = u & 31;
+      uint2 hi, lo;
+      split4(ra[r], hi, lo);
+      *reinterpret_cast<uint2*>(As + t * LDA + 4 * oq) = hi;
+      if (PARTS == 2) *reinterpret_cast<uint2*>(As + A_ARR + t * LDA + 4 * oq) = lo;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int u = tid + 256 * r;
+      const int t = u >> 4, iq = u & 15;
+      uint2 hi, lo;
+      split4(rb[r], hi, lo);
+      *reinterpret_cast<uint2*>(Bs + t * LDB + 4 * iq) = hi;
+      if (PARTS == 2) *reinterpret_cast<uint2*>(Bs + B_ARR + t * LDB + 4 * iq) = lo;
+    }
+  };
+
+  const uint32_t a_base = (uint32_t)__cvta_generic_to_shared(As);
+  const uint32_t b_base = (uint32_t)__cvta_generic_to_shared(Bs);
+  const int m0 = warp * 16;
+
+  long long chunk = blockIdx.x;
+  if (chunk < n_chunks) load_chunk(chunk);
+  for (; chunk < n_chunks; chunk += gridDim.x) {
+    __syncthreads();  // the previous chunk's fragments have been consumed
+    store_chunk();
+    __syncthreads();
+    if (chunk + gridDim.x < n_chunks) load_chunk(chunk + gridDim.x);
+#pragma unroll
+    for (int ks = 0; ks < KT / 16; ++ks) {
+      uint32_t ah[4], al[4];
+      const uint32_t a_off = (uint32_t)(((16 * ks + (lane & 7) + ((lane >> 4) & 1) * 8) * LDA + m0 + ((lane >> 3) & 1) * 8) * 2);
+      ldsm_x4_trans(a_base + a_off, ah);
+      if (PARTS == 2) ldsm_x4_trans(a_base + A_ARR * 2 + a_off, al);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        const uint32_t b_off = (uint32_t)(((16 * ks + (lane & 7) + ((lane >> 3) & 1) * 8) * LDB + 8 * (2 * np + (lane >> 4))) * 2);
+        uint32_t bh[4], bl[4];
+        ldsm_x4_trans(b_base + b_off, bh);
+        mma_bf16(acc[2 * np], ah, bh[0], bh[1]);
+        mma_bf16(acc[2 * np + 1], ah, bh[2], bh[3]);
+        if (PARTS == 2) {
+          ldsm_x4_trans(b_base + B_ARR * 2 + b_off, bl);
+          mma_bf16(acc[2 * np], ah, bl[0], bl[1]);
+          mma_bf16(acc[2 * np + 1], ah, bl[2], bl[3]);
+          mma_bf16(acc[2 * np], al, bh[0], bh[1]);
+          mma_bf16(acc[2 * np + 1], al, bh[2], bh[3]);
+        }
+      }
+    }
+  }
+
+  // ---- scatter-add the tile through the output map --------------------------------------------
+  const int g = lane >> 2, qd = lane & 3;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int o = o0 + m0 + g + 8 * half;
+    if (o >= p.O) continue;
+    const int ro = map_index(o, p.map_mode, p.map_a, p.map_b);
+    if (ro < 0) continue;
+    float* row = dW + (long long)ro * p.so + (long long)tap * p.st;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int i = i0 + 8 * nt + 2 * qd;
+      if (i < p.i_valid) atomicAdd(row + (long long)i * p.si, acc[nt][2 * half]);
+      if (i + 1 < p.i_valid) atomicAdd(row + (long long)(i + 1) * p.si, acc[nt][2 * half + 1]);
+    }
+  }
+}
+
+static int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+template <int PARTS>
+static int launch(const Args& a, int z, cudaStream_t st) {
+  const size_t smem = (size_t)PARTS * KT * (LDA + LDB) * 2;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("wgrad: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+      return MPHSIR_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int tiles = ((a.O + TO - 1) / TO) * a.tiles_i;
+  const long long rows = a.rows_per_batch > 0 && a.taps != 9 ? a.rows_per_batch : a.M;
+  const long long n_chunks = (rows + KT - 1) / KT;
+  long long splits = (2LL * sm_count() + (long long)tiles * z - 1) / ((long long)tiles * z);
+  if (splits > (n_chunks + 3) / 4) splits = (n_chunks + 3) / 4;  // >= 4 chunks per CTA: bounds the atomic traffic
+  if (splits < 1) splits = 1;
+  dim3 grid((unsigned)splits, (unsigned)tiles, (unsigned)z);
+  wgrad_kernel<PARTS><<<grid, 256, smem, st>>>(a);
+  return check_launch("wgrad");
+}
+
+}  // namespace wg
+}  // namespace mphsir
+
+using namespace mphsir;
+
+extern "C" int mphsir_wgrad(const mphsir_wgrad_params* p, void* stream) {
+  MPHSIR_REQUIRE(p && p->dY && p->X && p->dW, "wgrad: null operand");
+  MPHSIR_REQUIRE(p->M > 0 && p->O > 0 && p->I > 0 && p->O % 4 == 0 && p->I % 4 == 0, "wgrad: O and I must be positive multiples of 4");
+  MPHSIR_REQUIRE(p->lddy % 4 == 0 && p->ldx % 4 == 0 && p->lddy >= p->O && p->ldx >= p->I, "wgrad: leading dimensions must be multiples of 4");
+  MPHSIR_REQUIRE(((reinterpret_cast<uintptr_t>(p->dY) | reinterpret_cast<uintptr_t>(p->X)) & 15) == 0, "wgrad: operands must be 16-byte aligned");
+  MPHSIR_REQUIRE(p->precision == MPHSIR_PREC_BF16X3 || p->precision == MPHSIR_PREC_BF16, "wgrad: precision must be a tensor-core mode");
+  MPHSIR_REQUIRE(p->taps == 0 || p->taps == 9, "wgrad: taps must be 0 or 9");
+  wg::Args a;
+  a.dY = p->dY;
+  a.lddy = p->lddy;
+  a.X = p->X;
+  a.ldx = p->ldx;
+  a.dW = p->dW;
+  a.M = p->M;
+  a.O = p->O;
+  a.I = p->I;
+  a.rows_per_batch = p->rows_per_batch;
+  a.dw_batch_stride = p->dw_batch_stride;
+  a.x_row_mod = p->x_row_mod;
+  a.H = p->H;
+  a.W = p->W;
+  a.taps = p->taps;
+  a.so = p->so;
+  a.si = p->si;
+  a.st = p->st;
+  a.map_mode = p->map_mode;
+  a.map_a = p->map_a;
+  a.map_b = p->map_b;
+  a.i_valid = p->i_valid > 0 ? p->i_valid : p->I;
+  a.tiles_i = (p->I + wg::TI - 1) / wg::TI;
+  int z = 1;
+  if (p->taps == 9) {
+    MPHSIR_REQUIRE(p->H > 0 && p->W > 0 && p->M % ((long long)p->H * p->W) == 0, "wgrad: conv mode needs H, W with M = B*H*W");
+    MPHSIR_REQUIRE(p->x_row_mod == 0, "wgrad: conv mode does not take a shared X");
+    z = 9;
+  } else if (p->rows_per_batch > 0) {
+    MPHSIR_REQUIRE(p->M % p->rows_per_batch == 0, "wgrad: M must be a multiple of rows_per_batch");
+    z = (int)(p->M / p->rows_per_batch);
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return p->precision == MPHSIR_PREC_BF16X3 ? wg::launch<2>(a, z, st) : wg::launch<1>(a, z, st);
+}

@@ -67,12 +67,29 @@ class LocalGateParams(C.Structure):
     ] + [("gate", C.c_void_p), ("B_", C.c_int), ("C", C.c_int), ("r", C.c_int)]
 
 
+class WgradParams(C.Structure):
+    _fields_ = [
+        ("dY", C.c_void_p), ("lddy", C.c_int), ("X", C.c_void_p), ("ldx", C.c_int), ("dW", C.c_void_p),
+        ("M", C.c_longlong), ("O", C.c_int), ("I", C.c_int),
+        ("rows_per_batch", C.c_int), ("dw_batch_stride", C.c_longlong), ("x_row_mod", C.c_int),
+        ("H", C.c_int), ("W", C.c_int), ("taps", C.c_int),
+        ("so", C.c_longlong), ("si", C.c_longlong), ("st", C.c_longlong),
+        ("map_mode", C.c_int), ("map_a", C.c_int), ("map_b", C.c_int),
+        ("i_valid", C.c_int), ("precision", C.c_int),
+    ]
+
+
+class LocalGateBwdWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("param", "q", "kv", "proj", "proj_bias", "up")]
+
+
 EPI_BIAS, EPI_RESIDUAL, EPI_GLU, EPI_SPECTRAL, EPI_PROJ = 0, 1, 2, 3, 4
 PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16 = 0, 1, 2
 CONV_TOKENS, CONV_UNSHUFFLE, CONV_SHUFFLE, CONV_NCHW_RES = 0, 1, 2, 3
+MAP_IDENTITY, MAP_INTERLEAVE, MAP_HALVES = 0, 1, 2
 
 # symbol -> (restype, argtypes); also the list tests/test_abi.py checks against include/mphsir.h
-_VP, _I, _LL = C.c_void_p, C.c_int, C.c_longlong
+_VP, _I, _LL, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 SIGNATURES = {
     "mphsir_version": (_I, []),
     "mphsir_last_error": (C.c_char_p, []),
@@ -105,6 +122,32 @@ SIGNATURES = {
     "mphsir_tvsp_query_fwd": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "mphsir_bilinear_fwd": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "mphsir_text_prompt_fwd": (_I, [_VP, _VP, _VP, _I, _I, _VP]),
+    # ---- training path ----
+    "mphsir_wgrad": (_I, [C.POINTER(WgradParams), _VP]),
+    "mphsir_colsum": (_I, [_VP, _I, _VP, _LL, _I, _I, _I, _I, _VP]),
+    "mphsir_layernorm_fwd": (_I, [_VP, _I, _VP, _VP, _VP, _I, _VP, _LL, _I, _VP]),
+    "mphsir_layernorm_bwd": (_I, [_VP, _I, _VP, _VP, _VP, _I, _VP, _I, _VP, _I, _VP, _VP, _LL, _I, _VP]),
+    "mphsir_glu_bwd": (_I, [_VP, _I, _VP, _I, _LL, _I, _VP]),
+    "mphsir_gdfn_gate_fwd": (_I, [_VP, _I, _VP, _I, _LL, _I, _VP]),
+    "mphsir_gdfn_gate_bwd": (_I, [_VP, _I, _VP, _I, _VP, _I, _LL, _I, _VP]),
+    "mphsir_axpby": (_I, [_VP, _I, _VP, _I, _LL, _I, _F, _F, _VP, _I, _I, _VP]),
+    "mphsir_batch_sum": (_I, [_VP, _I, _VP, _I, _I, _LL, _I, _VP]),
+    "mphsir_window_attn_bwd_groups": (_I, [_I, _I, _I, _I]),
+    "mphsir_window_attn_bwd": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
+    "mphsir_rpb_table_bwd": (_I, [_VP, _VP, _I, _VP]),
+    "mphsir_window_reduce": (_I, [_VP, _I, _VP, _I, _VP, _I, _I, _I, _I, _I, _F, _VP]),
+    "mphsir_local_gate_bwd_record_ld": (_I, [_I]),
+    "mphsir_local_gate_bwd": (_I, [_VP, _I, _VP, C.POINTER(LocalGateBwdWeights), _VP, _I, _I, _I, _I, _VP]),
+    "mphsir_gate_apply_bwd": (_I, [_VP, _I, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
+    "mphsir_spectral_bwd": (_I, [_VP, _LL, _VP, _VP, _VP, _VP, _I, _LL, _VP, _VP, _I, _I, _I, _VP]),
+    "mphsir_dwconv3x3_wgrad": (_I, [_VP, _I, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
+    "mphsir_pixel_unshuffle": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _VP]),
+    "mphsir_pixel_shuffle": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _VP]),
+    "mphsir_tokens_to_nchw": (_I, [_VP, _I, _VP, _I, _I, _I, _VP]),
+    "mphsir_bilinear_bwd": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
+    "mphsir_tvsp_query_bwd": (_I, [_VP, _I, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
+    "mphsir_l1_clamp_loss": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _VP]),
+    "mphsir_adamw_step": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _I, _F, _VP]),
 }
 
 
@@ -478,3 +521,182 @@ def text_prompt(weights: torch.Tensor, clip: torch.Tensor, clip_b: torch.Tensor,
             lambda: load().mphsir_text_prompt_fwd(weights.data_ptr(), clip.data_ptr(), clip_b.data_ptr(), B, T,
                                                   stream_ptr()),
             lambda: (0.0, 4.0 * B * 512, "text_prompt"))
+
+
+# ------------------------------------------------------------------------------------------
+# training path (include/mphsir.h, "Training path")
+# ------------------------------------------------------------------------------------------
+
+
+def wgrad(dY: View, X: View, dW: torch.Tensor, precision: int, *, M: Optional[int] = None, so: Optional[int] = None,
+          si: int = 1, st: int = 0, map_mode: int = MAP_IDENTITY, map_a: Optional[int] = None, map_b: int = 0,
+          i_valid: int = 0, rows_per_batch: int = 0, dw_batch_stride: int = 0, x_row_mod: int = 0, taps: int = 0,
+          H: int = 0, W: int = 0, dw_offset: int = 0) -> None:
+    """dW[map(o)*so + i*si + tap*st] += sum_m dY[m,o] * X[src(m), i]  (dW: flat fp32 gradient storage)."""
+    p = WgradParams()
+    p.dY, p.lddy, p.X, p.ldx = dY.ptr, dY.ld, X.ptr, X.ld
+    p.dW = dW.data_ptr() + 4 * dw_offset
+    p.M, p.O, p.I = (dY.rows if M is None else M), dY.cols, X.cols
+    p.rows_per_batch, p.dw_batch_stride, p.x_row_mod = rows_per_batch, dw_batch_stride, x_row_mod
+    p.H, p.W, p.taps = H, W, taps
+    iv = i_valid if i_valid > 0 else X.cols
+    p.so, p.si, p.st = (iv * si if so is None else so), si, st
+    p.map_mode, p.map_a, p.map_b = map_mode, (dY.cols if map_a is None else map_a), map_b
+    p.i_valid, p.precision = iv, precision
+    m, o, i = p.M, p.O, p.I
+    _launch("wgrad", lambda: load().mphsir_wgrad(C.byref(p), stream_ptr()),
+            lambda: (2.0 * m * o * i * max(taps, 1), 4.0 * m * (o + i) * max(taps, 1), ("", "wgrad3", "wgrad1")[precision]))
+
+
+def colsum(X: View, out: torch.Tensor, map_mode: int = MAP_IDENTITY, map_a: Optional[int] = None, map_b: int = 0,
+           M: Optional[int] = None) -> None:
+    m = X.rows if M is None else M
+    _launch("colsum", lambda: load().mphsir_colsum(X.ptr, X.ld, out.data_ptr(), m, X.cols, map_mode,
+                                                   X.cols if map_a is None else map_a, map_b, stream_ptr()),
+            lambda: (0.0, 4.0 * m * X.cols, "colsum"))
+
+
+def layernorm_fwd(X: View, ln, Y: View, stats: Optional[torch.Tensor]) -> None:
+    _launch("layernorm_fwd", lambda: load().mphsir_layernorm_fwd(X.ptr, X.ld, ln[0].data_ptr(), ln[1].data_ptr(), Y.ptr, Y.ld,
+                                                                 ptr(stats), X.rows, X.cols, stream_ptr()),
+            lambda: (0.0, 8.0 * X.rows * X.cols, "layernorm_fwd"))
+
+
+def layernorm_bwd(X: View, stats: torch.Tensor, gamma: torch.Tensor, G: View, add: Optional[View], dX: View,
+                  dgamma: torch.Tensor, dbeta: torch.Tensor) -> None:
+    _launch("layernorm_bwd",
+            lambda: load().mphsir_layernorm_bwd(X.ptr, X.ld, stats.data_ptr(), gamma.data_ptr(), G.ptr, G.ld,
+                                                add.ptr if add is not None else None, add.ld if add is not None else 0,
+                                                dX.ptr, dX.ld, dgamma.data_ptr(), dbeta.data_ptr(), X.rows, X.cols, stream_ptr()),
+            lambda: (0.0, 4.0 * X.rows * X.cols * (3 if add is None else 4), "layernorm_bwd"))
+
+
+def glu_bwd(H: View, dHid: View, hid_pad: int) -> None:
+    _launch("glu_bwd", lambda: load().mphsir_glu_bwd(H.ptr, H.ld, dHid.ptr, dHid.ld, H.rows, hid_pad, stream_ptr()),
+            lambda: (0.0, 4.0 * H.rows * 6 * hid_pad, "glu_bwd"))
+
+
+def gdfn_gate_fwd(T: View, Y: View, hid_pad: int) -> None:
+    _launch("gdfn_gate_fwd", lambda: load().mphsir_gdfn_gate_fwd(T.ptr, T.ld, Y.ptr, Y.ld, T.rows, hid_pad, stream_ptr()),
+            lambda: (0.0, 4.0 * T.rows * 3 * hid_pad, "gdfn_gate_fwd"))
+
+
+def gdfn_gate_bwd(T: View, dY: View, dT: View, hid_pad: int) -> None:
+    _launch("gdfn_gate_bwd", lambda: load().mphsir_gdfn_gate_bwd(T.ptr, T.ld, dY.ptr, dY.ld, dT.ptr, dT.ld, T.rows, hid_pad,
+                                                                 stream_ptr()),
+            lambda: (0.0, 4.0 * T.rows * 5 * hid_pad, "gdfn_gate_bwd"))
+
+
+def axpby(X: View, Y: View, alpha: float = 1.0, beta: float = 0.0, row_scale: Optional[torch.Tensor] = None,
+          rows_per_batch: int = 0, x_row_mod: int = 0, M: Optional[int] = None) -> None:
+    m = Y.rows if M is None else M
+    _launch("axpby", lambda: load().mphsir_axpby(X.ptr, X.ld, Y.ptr, Y.ld, m, Y.cols, alpha, beta, ptr(row_scale),
+                                                 rows_per_batch, x_row_mod, stream_ptr()),
+            lambda: (0.0, 4.0 * m * Y.cols * (2 if beta == 0.0 else 3), "axpby"))
+
+
+def batch_sum(X: View, Y: View, B: int) -> None:
+    _launch("batch_sum", lambda: load().mphsir_batch_sum(X.ptr, X.ld, Y.ptr, Y.ld, B, Y.rows, Y.cols, stream_ptr()),
+            lambda: (0.0, 4.0 * (B + 1) * Y.rows * Y.cols, "batch_sum"))
+
+
+def window_attn_bwd_groups(B: int, H: int, W: int, heads: int) -> int:
+    return int(load().mphsir_window_attn_bwd_groups(B, H, W, heads))
+
+
+def window_attn_bwd(qkv: View, bias: torch.Tensor, dO: View, dqkv: View, partial: torch.Tensor, groups: int, B: int,
+                    H: int, W: int, Cc: int, heads: int, shift: int) -> None:
+    n = B * H * W
+    _launch("window_attn_bwd",
+            lambda: load().mphsir_window_attn_bwd(qkv.ptr, qkv.ld, bias.data_ptr(), dO.ptr, dO.ld, dqkv.ptr, dqkv.ld,
+                                                  partial.data_ptr(), groups, B, H, W, Cc, heads, shift, stream_ptr()),
+            lambda: (10.0 * n * 64 * Cc, 4.0 * 10 * n * Cc, "window_attn_bwd"))
+
+
+def rpb_table_bwd(dbias: torch.Tensor, dtable: torch.Tensor, heads: int) -> None:
+    _launch("rpb_table_bwd", lambda: load().mphsir_rpb_table_bwd(dbias.data_ptr(), dtable.data_ptr(), heads, stream_ptr()))
+
+
+def window_reduce(A: View, Bm: Optional[View], out: torch.Tensor, B: int, H: int, W: int, Cc: int, shift: int,
+                  scale: float) -> None:
+    _launch("window_reduce",
+            lambda: load().mphsir_window_reduce(A.ptr, A.ld, Bm.ptr if Bm is not None else None, Bm.ld if Bm is not None else 0,
+                                                out.data_ptr(), B, H, W, Cc, shift, scale, stream_ptr()),
+            lambda: (0.0, 4.0 * B * H * W * Cc * (1 if Bm is None else 2), "window_reduce"))
+
+
+def local_gate_bwd_record_ld(r: int) -> int:
+    return int(load().mphsir_local_gate_bwd_record_ld(r))
+
+
+def local_gate_bwd(LL: View, dG: torch.Tensor, w: dict, record: View, B_: int, Cc: int, r: int) -> None:
+    ws = LocalGateBwdWeights()
+    for n in ("param", "q", "kv", "proj", "proj_bias", "up"):
+        setattr(ws, n, w[n].data_ptr())
+    _launch("local_gate_bwd", lambda: load().mphsir_local_gate_bwd(LL.ptr, LL.ld, dG.data_ptr(), C.byref(ws), record.ptr,
+                                                                   record.ld, B_, Cc, r, stream_ptr()))
+
+
+def gate_apply_bwd(dU: View, gate: torch.Tensor, dMean: torch.Tensor, dSA: View, B: int, H: int, W: int, Cc: int,
+                   shift: int) -> None:
+    _launch("gate_apply_bwd", lambda: load().mphsir_gate_apply_bwd(dU.ptr, dU.ld, gate.data_ptr(), dMean.data_ptr(), dSA.ptr,
+                                                                   dSA.ld, B, H, W, Cc, shift, stream_ptr()),
+            lambda: (0.0, 8.0 * B * H * W * Cc, "gate_apply_bwd"))
+
+
+def spectral_bwd(P: torch.Tensor, Wout: torch.Tensor, gsum: torch.Tensor, temperature: torch.Tensor, Wb: torch.Tensor,
+                 dWout: torch.Tensor, dTemp: torch.Tensor, B: int, heads: int, c: int) -> None:
+    """P [B,C,C]; Wb [B,2C,ldwb]."""
+    Cc = heads * c
+    _launch("spectral_bwd",
+            lambda: load().mphsir_spectral_bwd(P.data_ptr(), Cc * Cc, Wout.data_ptr(), gsum.data_ptr(), temperature.data_ptr(),
+                                               Wb.data_ptr(), Wb.shape[2], Wb.shape[1] * Wb.shape[2], dWout.data_ptr(),
+                                               dTemp.data_ptr(), B, heads, c, stream_ptr()),
+            lambda: (4.0 * B * heads * c * c * Cc, 4.0 * B * (Cc * Cc + 4 * Cc * Cc), "spectral_bwd"))
+
+
+def dwconv3x3_wgrad(X: View, dY: View, dW: torch.Tensor, B: int, H: int, W: int, Cc: int, map_mode: int = MAP_IDENTITY,
+                    map_a: Optional[int] = None, map_b: int = 0) -> None:
+    """dW: gradient of the reference depthwise weight [C,1,3,3] (+=)."""
+    _launch("dwconv3x3_wgrad", lambda: load().mphsir_dwconv3x3_wgrad(X.ptr, X.ld, dY.ptr, dY.ld, dW.data_ptr(), B, H, W, Cc,
+                                                                     map_mode, Cc if map_a is None else map_a, map_b,
+                                                                     stream_ptr()),
+            lambda: (18.0 * B * H * W * Cc, 8.0 * B * H * W * Cc, "dwconv3x3_wgrad"))
+
+
+def pixel_unshuffle(X: View, Y: View, B: int, H: int, W: int, Cc: int) -> None:
+    _launch("pixel_unshuffle", lambda: load().mphsir_pixel_unshuffle(X.ptr, X.ld, Y.ptr, Y.ld, B, H, W, Cc, stream_ptr()),
+            lambda: (0.0, 8.0 * B * H * W * Cc, "pixel_shuffle"))
+
+
+def pixel_shuffle(X: View, Y: View, B: int, H: int, W: int, Cc: int) -> None:
+    _launch("pixel_shuffle", lambda: load().mphsir_pixel_shuffle(X.ptr, X.ld, Y.ptr, Y.ld, B, H, W, Cc, stream_ptr()),
+            lambda: (0.0, 32.0 * B * H * W * Cc, "pixel_shuffle"))
+
+
+def tokens_to_nchw(X: View, out: torch.Tensor, B: int, Cc: int, HW: int) -> None:
+    _launch("tokens_to_nchw", lambda: load().mphsir_tokens_to_nchw(X.ptr, X.ld, out.data_ptr(), B, Cc, HW, stream_ptr()),
+            lambda: (0.0, 8.0 * B * Cc * HW, "tokens_to_nchw"))
+
+
+def bilinear_bwd(dY: View, dX: View, B: int, h: int, w: int, H: int, W: int, Cc: int) -> None:
+    _launch("bilinear_bwd", lambda: load().mphsir_bilinear_bwd(dY.ptr, dY.ld, dX.ptr, dX.ld, B, h, w, H, W, Cc, stream_ptr()))
+
+
+def tvsp_query_bwd(dQ: View, clip_b: torch.Tensor, weights: torch.Tensor, dLearn: torch.Tensor, B: int, T: int, D: int,
+                   ps: int) -> None:
+    _launch("tvsp_query_bwd", lambda: load().mphsir_tvsp_query_bwd(dQ.ptr, dQ.ld, clip_b.data_ptr(), weights.data_ptr(),
+                                                                   dLearn.data_ptr(), B, T, D, ps, stream_ptr()))
+
+
+def l1_clamp_loss(out: torch.Tensor, clean: torch.Tensor, dOut: torch.Tensor, loss: torch.Tensor, grad_scale: float = 1.0) -> None:
+    _launch("l1_clamp_loss", lambda: load().mphsir_l1_clamp_loss(out.data_ptr(), clean.data_ptr(), dOut.data_ptr(),
+                                                                 loss.data_ptr(), out.numel(), grad_scale, stream_ptr()),
+            lambda: (0.0, 12.0 * out.numel(), "l1_clamp_loss"))
+
+
+def adamw_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr: float, beta1: float, beta2: float,
+               eps: float, weight_decay: float, step: int, grad_scale: float = 1.0) -> None:
+    _launch("adamw_step", lambda: load().mphsir_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
+                                                           lr, beta1, beta2, eps, weight_decay, step, grad_scale, stream_ptr()),
+            lambda: (0.0, 28.0 * p.numel(), "adamw"))

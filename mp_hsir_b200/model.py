@@ -259,6 +259,15 @@ class MP_HSIR_Net(nn.Module):
             self._engine = Engine(self)
         return self._engine
 
+    def trainer(self, **optimizer_kwargs):
+        """Training executor (mp_hsir_b200/train_engine.py): forward + clamp/L1 loss + hand-written backward + AdamW,
+        i.e. PromptIRModel.training_step / configure_optimizers of the reference (train.py:50-69).  The parameters are
+        re-homed into one flat buffer; ``param.grad`` are views of the flat gradient buffer."""
+        from .train_engine import TrainEngine
+        if not isinstance(self._engine, TrainEngine):
+            self._engine = TrainEngine(self, **optimizer_kwargs)
+        return self._engine
+
     def set_precision(self, precision: str) -> "MP_HSIR_Net":
         if precision not in ("fp32", "fp32_exact", "bf16"):
             raise ValueError(precision)
@@ -289,6 +298,6 @@ class MP_HSIR_Net(nn.Module):
                 "there is no CPU fallback (move the module and inputs to cuda)")
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError(
-                "round 1 implements the forward pass only; run under torch.no_grad() / .eval() "
-                "(backward kernels are the next SURVEY.md §8 row)")
+                "autograd cannot see through libmphsir.so: train with net.trainer().train_step(degraded, clean, task_id) "
+                "(hand-written backward + AdamW), or run the forward under torch.no_grad() / .eval()")
         return self.engine().forward(inp_img, task_id)

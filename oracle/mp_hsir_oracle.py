@@ -263,7 +263,7 @@ def base_block(x: torch.Tensor, sd: SD, st: Stage, keep=None) -> torch.Tensor:
     """BaseBlock: x + blocks(x); shift 0 on even, 4 on odd blocks (net/MP_HSIR.py:746-761)."""
     y = x
     for i in range(st.depth):
-        k = None if keep is None else keep[(st.name, i)]
+        k = None if keep is None else keep.get((st.name, i))  # blocks with rate 0 hold nn.Identity (:620)
         y = pgsstb(y, sd, f"{st.name}.blocks.{i}.", st.heads, SHIFT if i % 2 else 0, k)
     return y + x
 

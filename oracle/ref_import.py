@@ -22,6 +22,9 @@ import torch
 REF_ROOT = os.environ.get("MPHSIR_REFERENCE", "/root/reference")
 
 
+KEEP_QUEUE = None  # optional list of [B] DropPath multipliers consumed by the stub in forward-call order
+
+
 def available() -> bool:
     return os.path.isfile(os.path.join(REF_ROOT, "net", "MP_HSIR.py"))
 
@@ -37,6 +40,9 @@ class _DropPath(torch.nn.Module):
         if self.drop_prob == 0.0 or not self.training:
             return x
         keep = 1.0 - self.drop_prob
+        if KEEP_QUEUE is not None:
+            # gradient fixtures: consume pre-drawn multipliers (mask/keep_prob, [B]) in call order
+            return x * KEEP_QUEUE.pop(0).view((x.shape[0],) + (1,) * (x.dim() - 1)).to(x.dtype)
         mask = x.new_empty((x.shape[0],) + (1,) * (x.dim() - 1)).bernoulli_(keep)
         return x * mask / keep
 
