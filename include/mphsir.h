@@ -415,9 +415,10 @@ MPHSIR_API int mphsir_tvsp_query_bwd(const float* dQ, int ldq, const float* clip
 /* loss[0] += mean|clamp(out,0,1) - clean| (train.py:58-61), dOut = d loss / d out * grad_scale */
 MPHSIR_API int mphsir_l1_clamp_loss(const float* out, const float* clean, float* dOut, float* loss, long long numel,
                                     float grad_scale, void* stream);
-/* torch.optim.AdamW step (train.py:69) over one flat fp32 range; g is multiplied by grad_scale first */
+/* torch.optim.AdamW step (train.py:69) over one flat fp32 range; g is multiplied by grad_scale first.  dyn (device, may
+ * be NULL) = {lr, 1-beta1^step, 1-beta2^step} overrides lr/step so that a captured CUDA graph can be replayed every step. */
 MPHSIR_API int mphsir_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                                 float eps, float weight_decay, int step, float grad_scale, void* stream);
+                                 float eps, float weight_decay, int step, float grad_scale, const float* dyn, void* stream);
 
 #ifdef __cplusplus
 }

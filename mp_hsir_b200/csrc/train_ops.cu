@@ -580,7 +580,13 @@ __global__ void __launch_bounds__(256) l1_clamp_loss_kernel(const float* __restr
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, long long n, float lr, float beta1, float beta2,
-                                                    float eps, float wd, float bc1, float bc2, float grad_scale) {
+                                                    float eps, float wd, float bc1, float bc2, float grad_scale,
+                                                    const float* __restrict__ dyn) {
+  if (dyn != nullptr) {  // CUDA-graph replays: step-dependent scalars live in device memory
+    lr = __ldg(dyn);
+    bc1 = __ldg(dyn + 1);
+    bc2 = __ldg(dyn + 2);
+  }
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
@@ -776,11 +782,11 @@ extern "C" int mphsir_l1_clamp_loss(const float* out, const float* clean, float*
 }
 
 extern "C" int mphsir_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                                 float eps, float weight_decay, int step, float grad_scale, void* stream) {
+                                 float eps, float weight_decay, int step, float grad_scale, const float* dyn, void* stream) {
   MPHSIR_REQUIRE(p && g && m && v && n > 0 && step > 0, "adamw_step: bad arguments");
   MPHSIR_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                    reinterpret_cast<uintptr_t>(v)) & 15) == 0, "adamw_step: buffers must be 16-byte aligned");
   const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
-  adamw_kernel<<<grid_for(n / 4 + 4), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale);
+  adamw_kernel<<<grid_for(n / 4 + 4), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale, dyn);
   return check_launch("adamw_step");
 }

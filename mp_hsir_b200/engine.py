@@ -198,7 +198,9 @@ class Engine:
         P["up2_1"] = W(pack_conv3x3(f32(net.up2_1.body[0].weight), shuffle=True), 4 * cfg.dim, 18 * cfg.dim)
         P["reduce_chan_level2"] = W(pack_linear_t(f32(net.reduce_chan_level2.weight)), 2 * cfg.dim, 4 * cfg.dim)
         P["output"] = W(pack_conv3x3(f32(net.output.weight)), cfg.out_channel, 18 * cfg.dim)
-        P["clip"] = f32(net.text_prompt.clip_prompt).contiguous()
+        if getattr(self, "_clip_dev", None) is None:  # a constant, moved once (the module keeps it on the host)
+            self._clip_dev = f32(net.text_prompt.clip_prompt).contiguous()
+        P["clip"] = self._clip_dev
 
         for st in cfg.stages():
             hid = cfg.hidden(st.dim)

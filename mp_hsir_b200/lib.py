@@ -147,7 +147,7 @@ SIGNATURES = {
     "mphsir_bilinear_bwd": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "mphsir_tvsp_query_bwd": (_I, [_VP, _I, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "mphsir_l1_clamp_loss": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _VP]),
-    "mphsir_adamw_step": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _I, _F, _VP]),
+    "mphsir_adamw_step": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _I, _F, _VP, _VP]),
 }
 
 
@@ -696,7 +696,8 @@ def l1_clamp_loss(out: torch.Tensor, clean: torch.Tensor, dOut: torch.Tensor, lo
 
 
 def adamw_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr: float, beta1: float, beta2: float,
-               eps: float, weight_decay: float, step: int, grad_scale: float = 1.0) -> None:
+               eps: float, weight_decay: float, step: int, grad_scale: float = 1.0, dyn: Optional[torch.Tensor] = None) -> None:
     _launch("adamw_step", lambda: load().mphsir_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
-                                                           lr, beta1, beta2, eps, weight_decay, step, grad_scale, stream_ptr()),
+                                                           lr, beta1, beta2, eps, weight_decay, step, grad_scale, ptr(dyn),
+                                                           stream_ptr()),
             lambda: (0.0, 28.0 * p.numel(), "adamw"))

@@ -106,8 +106,13 @@ class TrainEngine(Engine):
                     d[k + ".d"] = self._dgrad_of(d[k])
                 d["sdw.f"] = _flip_dw(d["sdw"])
                 l = blk.local_spectral_attn
-                cat = torch.cat([f32(l.linear_prompt.weight), f32(l.linear_down.weight)], 0)   # [128+r, C]
-                d["ll_w"] = self._W(pack_linear_t(cat), PROMPT_LEN + st.rank, st.dim)
+                # [W_prompt ; W_down ; 0] with the row count padded to a multiple of 8 (the GEMM engine's K granularity
+                # when this matrix is used transposed for dL/dm)
+                nlp = _ceil(PROMPT_LEN + st.rank, 8)
+                cat = f32(l.linear_prompt.weight).new_zeros(nlp, st.dim)
+                cat[:PROMPT_LEN] = f32(l.linear_prompt.weight)
+                cat[PROMPT_LEN:PROMPT_LEN + st.rank] = f32(l.linear_down.weight)
+                d["ll_w"] = self._W(pack_linear_t(cat), nlp, st.dim)
                 d["ll_w.d"] = self._dgrad_of(d["ll_w"])
                 d["gate_raw"] = {
                     "param": f32(l.prompt_param).reshape(PROMPT_LEN, st.rank).contiguous(),
@@ -280,7 +285,7 @@ class TrainEngine(Engine):
         msa = ws.flat("b.msa", B_ * C)
         lib.window_reduce(sa, None, msa, B, H, W, C, shift, 1.0 / 64.0)
         msa_v, dg_v = View(msa.data_ptr(), C, B_, C, msa), View(dg.data_ptr(), C, B_, C, dg)
-        nl = PROMPT_LEN + r
+        nl = _ceil(PROMPT_LEN + r, 8)   # record columns [128+r, nl) hit zero weight rows
         LL = ws.mat("b.LL", B_, _ceil(nl, 16))
         self._gemm(msa_v, w["ll_w"], LL, nl)
         ldr = lib.local_gate_bwd_record_ld(r)
@@ -637,9 +642,19 @@ class TrainEngine(Engine):
                 keep[(st.name, i)] = m.contiguous()
         return keep
 
+    def _fwd_bwd(self, x, cl, weights, out, d_out, keep):
+        """launch sequence of forward + clamp/L1 + backward on pre-allocated buffers (CUDA-graph capturable)."""
+        self.flat_g.zero_()
+        if keep == "sample":
+            keep = self.drop_path_scales(x.shape[0])
+        F = self.forward_train(x, weights, out, keep)
+        self.loss_buf.zero_()
+        lib.l1_clamp_loss(out, cl, d_out, self.loss_buf)
+        self.backward(F, d_out)
+
     @torch.no_grad()
     def loss_and_grad(self, inp: torch.Tensor, clean: torch.Tensor, task_id: torch.Tensor, keep=None):
-        """forward + clamp/L1 loss + backward.  Returns (restored, loss tensor[1]); gradients land in flat_g (+=)."""
+        """forward + clamp/L1 loss + backward.  Returns (restored, loss tensor[1]); gradients overwrite flat_g."""
         B, _, H, W = inp.shape
         if H % 32 or W % 32:
             raise ValueError(f"H and W must be multiples of 32, got {H}x{W}")
@@ -647,13 +662,8 @@ class TrainEngine(Engine):
         x = inp.detach().to(torch.float32).contiguous()
         cl = clean.detach().to(torch.float32).contiguous()
         with torch.cuda.device(self.device):
-            weights = self.task_weights(task_id)
-            out = torch.empty_like(x)
-            F = self.forward_train(x, weights, out, keep)
-            d_out = torch.empty_like(x)
-            self.loss_buf.zero_()
-            lib.l1_clamp_loss(out, cl, d_out, self.loss_buf)
-            self.backward(F, d_out)
+            out, d_out = torch.empty_like(x), torch.empty_like(x)
+            self._fwd_bwd(x, cl, self.task_weights(task_id), out, d_out, keep)
         return out, self.loss_buf
 
     @torch.no_grad()
@@ -662,16 +672,101 @@ class TrainEngine(Engine):
         with torch.cuda.device(self.device):
             lib.adamw_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps,
                            self.weight_decay, self.step_count, grad_scale)
-        # parameters changed in place behind torch's back: re-pack the weight images
-        self.invalidate()
+        # parameters changed in place behind torch's back: re-pack the weight images (captured steps stay valid)
+        Engine.invalidate(self)
 
-    def train_step(self, inp, clean, task_id, keep="sample", world_size: int = 1, all_reduce=None) -> torch.Tensor:
-        """One optimisation step (train.py:50-69): returns the loss tensor [1] (device)."""
-        if keep == "sample":
-            keep = self.drop_path_scales(inp.shape[0])
+    def train_step(self, inp, clean, task_id, keep="sample", world_size: int = 1, all_reduce=None,
+                   cuda_graph: bool = False) -> torch.Tensor:
+        """One optimisation step (train.py:50-69): returns the loss tensor [1] (device).  With ``cuda_graph`` the launch
+        sequence (~1.8k kernels) is captured once per input shape and replayed: weight re-packing, forward, loss,
+        backward and AdamW become three graph launches around the (eager) gradient all-reduce."""
+        if cuda_graph and lib.PROFILER is None:
+            return self._train_step_graphed(inp, clean, task_id, keep, world_size, all_reduce)
         self.zero_grad()
         _, loss = self.loss_and_grad(inp, clean, task_id, keep)
         if all_reduce is not None:
             all_reduce(self.flat_g)  # DDP: sum over ranks, the mean is folded into grad_scale
         self.optimizer_step(grad_scale=1.0 / world_size)
         return loss
+
+    # -- CUDA-graph replay of the step ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def _train_step_graphed(self, inp, clean, task_id, keep, world_size, all_reduce):
+        if keep not in (None, "sample"):
+            raise ValueError("cuda_graph=True supports keep=None or 'sample' (masks are drawn inside the graph)")
+        key = (tuple(inp.shape), keep, world_size)
+        graphs = self.__dict__.setdefault("_train_graphs", {})
+        ent = graphs.get(key)
+        if ent is None:
+            # first call at this shape: eager step (sizes the workspace, sets kernel attributes); mark for capture
+            graphs[key] = "warm"
+            return self.train_step(inp, clean, task_id, keep, world_size, all_reduce, cuda_graph=False)
+        with torch.cuda.device(self.device):
+            if ent == "warm":
+                ent = graphs[key] = self._capture_step(inp, clean, task_id, keep, world_size)
+            g_pack, g_main, g_opt, sx, sc, sw, dyn = ent[:7]
+            sx.copy_(inp, non_blocking=True)
+            sc.copy_(clean, non_blocking=True)
+            sw.copy_(self.task_weights(task_id), non_blocking=True)
+            g_main.replay()
+            if all_reduce is not None:
+                all_reduce(self.flat_g)
+            self.step_count += 1
+            dyn[0:1].fill_(self.lr)  # stream-ordered scalars: an lr schedule just changes self.lr
+            dyn[3:4].fill_(float(self.step_count - 1))
+            g_opt.replay()           # bumps the device step counter, bias corrections, AdamW
+            g_pack.replay()          # weight images for the next forward
+            lib.LAUNCHES += ent[7]
+        return self.loss_buf
+
+    def _capture_step(self, inp, clean, task_id, keep, world_size):
+        gen = self.ws.generation
+        sx = torch.empty_like(inp, dtype=torch.float32).contiguous()
+        sc = torch.empty_like(sx)
+        sw = torch.empty_like(self.task_weights(task_id))
+        out, d_out = torch.empty_like(sx), torch.empty_like(sx)
+        dyn = torch.zeros(4, device=self.device, dtype=torch.float32)          # {lr, 1-b1^t, 1-b2^t, t}
+        dyn[3] = float(self.step_count)
+        sx.copy_(inp)
+        sc.copy_(clean)
+        sw.copy_(self.task_weights(task_id))
+        torch.cuda.current_stream().synchronize()
+        n0 = lib.LAUNCHES
+        pool = torch.cuda.graph_pool_handle()
+        # 1. weight (re-)packing from the flat parameter buffer: the packed tensors live in the graph's pool, so their
+        #    addresses are what the forward/backward graph records
+        g_pack = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_pack, pool=pool):
+            self.packed = self._pack()
+            self._pack_train()
+        self._versions = self._param_versions()
+        self._train_packed_version = self.packed
+        self._graph_packed = self.packed
+        n_pack = lib.LAUNCHES - n0
+        g_pack.replay()
+        # 2. zero_grad + DropPath masks + forward + loss + backward
+        g_main = torch.cuda.CUDAGraph()
+        n1 = lib.LAUNCHES
+        with torch.cuda.graph(g_main, pool=pool):
+            self._fwd_bwd(sx, sc, sw, out, d_out, keep)
+        n_main = lib.LAUNCHES - n1
+        if self.ws.generation != gen:
+            raise RuntimeError("workspace grew during graph capture")
+        # 3. AdamW reading {lr, bias corrections} from device memory
+        g_opt = torch.cuda.CUDAGraph()
+        n2 = lib.LAUNCHES
+        with torch.cuda.graph(g_opt, pool=pool):
+            dyn[3:4].add_(1.0)
+            dyn[1:2].copy_(1.0 - torch.pow(self.betas[0], dyn[3:4]))
+            dyn[2:3].copy_(1.0 - torch.pow(self.betas[1], dyn[3:4]))
+            lib.adamw_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps,
+                           self.weight_decay, 1, 1.0 / world_size, dyn=dyn)
+        n_opt = lib.LAUNCHES - n2
+        lib.LAUNCHES = n0  # capture records, it does not launch
+        return (g_pack, g_main, g_opt, sx, sc, sw, dyn, n_pack + n_main + n_opt)
+
+    def invalidate(self):
+        # a captured step owns its packed weights and refreshes them itself (g_pack); anything else (load_state_dict,
+        # manual edits) drops the graphs
+        super().invalidate()
+        self.__dict__.pop("_train_graphs", None)
