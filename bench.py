@@ -210,7 +210,8 @@ def run_train(args):
     with torch.no_grad():
         net.output.weight.mul_(0.05)  # random-init output conv scaled so restored values sit in the clamp's live range
     tr = net.trainer(lr=2e-4)
-    all_reduce = (lambda g: dist.all_reduce(g)) if world > 1 else None
+    from mp_hsir_b200.parallel import all_reduce_gradients
+    all_reduce = all_reduce_gradients if world > 1 else None
     # every rank trains on its own shard of the global batch (DDP batch sharding, train.py:118)
     noisy_h, clean_h, tid_h = (t.pin_memory() for t in make_train_batch(shape, rank, cfg.task_classes))
     noisy_d, clean_d, tid_d = noisy_h.to(device), clean_h.to(device), tid_h.to(device)
@@ -259,6 +260,12 @@ def run_train(args):
     ms_e2e = _max(f0.elapsed_time(f1), device)
     losses.append(float(loss_h))
     clocks = sampler.stop() if sampler else None
+    graph_ms = None
+    if use_graph:
+        tr.time_graphs = True
+        step(noisy_d, clean_d, tid_d)
+        tr.time_graphs = False
+        graph_ms = {k: round(v, 3) for k, v in (tr.graph_ms or {}).items()}
 
     roof, breakdown = None, None
     if rank == 0 and not args.no_roofline:
@@ -322,7 +329,7 @@ def run_train(args):
                    "weights": "random-init (name-seeded synthetic), reference architecture, output conv x0.05",
                    "parallelism": f"dp{world} (batch-sharded, {nparam * 4 / 1e6:.1f} MB gradient all-reduce)" if world > 1 else "dp1",
                    "l2": "per-step working set (saved activations, GBs) exceeds the 126 MB L2; no explicit flush",
-                   "cuda_graph": use_graph, "losses_first_last": [losses[0], losses[-1]], "workspace_bytes": tr.ws.bytes()},
+                   "cuda_graph": use_graph, "graph_ms": graph_ms, "losses_first_last": [losses[0], losses[-1]], "workspace_bytes": tr.ws.bytes()},
         "e2e": {"value": total_units / (ms_e2e * 1e-3), "unit": unit, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": (noisy_h.numel() + clean_h.numel()) * 4 + tid_h.numel() * 8, "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cb, "kernels": breakdown,

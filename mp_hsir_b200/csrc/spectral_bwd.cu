@@ -17,24 +17,31 @@
 namespace mphsir {
 namespace spb {
 
+// TM = c/16: every thread owns a TM x TM micro-tile of the c x c head matrices (c in {32,48,64,96})
+template <int TM>
 __global__ void __launch_bounds__(256) spectral_bwd_kernel(const float* __restrict__ P, long long p_batch_stride,
                                                            const float* __restrict__ Wout, const float* __restrict__ gsum,
                                                            const float* __restrict__ temperature, float* __restrict__ Wb,
                                                            long long wb_batch_stride, int ldwb, float* __restrict__ dWout,
-                                                           float* __restrict__ dTemp, int heads, int c) {
+                                                           float* __restrict__ dTemp, int heads) {
+  constexpr int c = 16 * TM;
+  constexpr int LDm = c + 1;
+  constexpr int KC = 32;  // rows of Wout / P staged per step
   extern __shared__ float sm[];
   const int C = heads * c;
-  const int LDm = c + 1;
   float* A = sm;                 // [c][LDm]
-  float* D = A + c * LDm;        // dA -> dS -> dGh/(|q||k|)
+  float* D = A + c * LDm;        // dA -> dGh
   float* Gh = D + c * LDm;       // normalised Gram
-  float* nq = Gh + c * LDm;      // [c] 1/|q_i|
+  float* Ws = Gh + c * LDm;      // [KC][LDm] staged Wout[o, hc + i]
+  float* Ps = Ws + KC * LDm;     // [KC][LDm] staged P_b[o, hc + j]
+  float* nq = Ps + KC * LDm;     // [c] 1/|q_i|
   float* nk = nq + c;            // [c] 1/|k_j|
   float* sq = nk + c;            // [c] s_i
   float* sk = sq + c;            // [c] s'_j
   __shared__ float red[8];
   const int b = blockIdx.x / heads, h = blockIdx.x - b * heads;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ti = tid >> 4, tj = tid & 15;
   const float* gs = gsum + (long long)blockIdx.x * (c * c + 2 * c);
   const float* Pb = P + (long long)b * p_batch_stride;
   const float T = __ldg(temperature + h);
@@ -48,10 +55,41 @@ __global__ void __launch_bounds__(256) spectral_bwd_kernel(const float* __restri
   for (int e = tid; e < c * c; e += 256) {
     const int i = e / c, j = e - i * c;
     Gh[i * LDm + j] = __ldg(gs + e) * nq[i] * nk[j];
-    // dA_ij = sum_o Wout[o, hc+i] * P_b[o, hc+j]
-    float s = 0.f;
-    for (int o = 0; o < C; ++o) s = fmaf(__ldg(Wout + (long long)o * C + hc + i), __ldg(Pb + (long long)o * C + hc + j), s);
-    D[i * LDm + j] = s;
+  }
+  // ---- dA_ij = sum_o Wout[o, hc+i] * P_b[o, hc+j]: staged mini-GEMM, micro-tile rows ti*TM.., cols tj*TM.. --------
+  {
+    float acc[TM][TM];
+#pragma unroll
+    for (int a = 0; a < TM; ++a)
+#pragma unroll
+      for (int e = 0; e < TM; ++e) acc[a][e] = 0.f;
+    for (int o0 = 0; o0 < C; o0 += KC) {
+      __syncthreads();
+      for (int e = tid; e < KC * c; e += 256) {
+        const int r = e / c, col = e - r * c;
+        const bool ok = o0 + r < C;
+        Ws[r * LDm + col] = ok ? __ldg(Wout + (long long)(o0 + r) * C + hc + col) : 0.f;
+        Ps[r * LDm + col] = ok ? __ldg(Pb + (long long)(o0 + r) * C + hc + col) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int r = 0; r < KC; ++r) {
+        float wv[TM], pv[TM];
+#pragma unroll
+        for (int a = 0; a < TM; ++a) {
+          wv[a] = Ws[r * LDm + ti * TM + a];
+          pv[a] = Ps[r * LDm + tj * TM + a];
+        }
+#pragma unroll
+        for (int a = 0; a < TM; ++a)
+#pragma unroll
+          for (int e = 0; e < TM; ++e) acc[a][e] = fmaf(wv[a], pv[e], acc[a][e]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < TM; ++a)
+#pragma unroll
+      for (int e = 0; e < TM; ++e) D[(ti * TM + a) * LDm + tj * TM + e] = acc[a][e];
   }
   __syncthreads();
   // A = softmax_j(Gh*T); dS = A o (dA - rowsum(A o dA)); dT partial   (warp per row)
@@ -80,7 +118,7 @@ __global__ void __launch_bounds__(256) spectral_bwd_kernel(const float* __restri
       dT = fmaf(ds, Gh[i * LDm + j], dT);
       const float dgh = ds * T;
       si = fmaf(dgh, Gh[i * LDm + j], si);
-      D[i * LDm + j] = dgh;  // dGh for now
+      D[i * LDm + j] = dgh;
     }
     si = warp_sum(si);
     if (lane == 0) sq[i] = si;
@@ -124,13 +162,49 @@ __global__ void __launch_bounds__(256) spectral_bwd_kernel(const float* __restri
     }
     wb[(long long)(C + hc + j) * ldwb + col] = val;
   }
-  // ---- dWout[o, hc+i] += sum_j P_b[o, hc+j] A_ij -----------------------------------------------
-  for (int e = tid; e < C * c; e += 256) {
-    const int o = e / c, i = e - o * c;
-    float s = 0.f;
-    for (int j = 0; j < c; ++j) s = fmaf(__ldg(Pb + (long long)o * C + hc + j), A[i * LDm + j], s);
-    atomicAdd(dWout + (long long)o * C + hc + i, s);
+  // ---- dWout[o, hc+i] += sum_j P_b[o, hc+j] A_ij : KC rows of P staged per step, thread -> (row r, c/8 values of i) ----
+  constexpr int IPT = c / 8;
+  const int r = tid >> 3, ib = (tid & 7) * IPT;
+  for (int o0 = 0; o0 < C; o0 += KC) {
+    __syncthreads();
+    for (int e = tid; e < KC * c; e += 256) {
+      const int rr = e / c, col = e - rr * c;
+      Ps[rr * LDm + col] = (o0 + rr < C) ? __ldg(Pb + (long long)(o0 + rr) * C + hc + col) : 0.f;
+    }
+    __syncthreads();
+    float acc[IPT];
+#pragma unroll
+    for (int e = 0; e < IPT; ++e) acc[e] = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < c; ++j) {
+      const float pv = Ps[r * LDm + j];
+#pragma unroll
+      for (int e = 0; e < IPT; ++e) acc[e] = fmaf(pv, A[(ib + e) * LDm + j], acc[e]);
+    }
+    if (o0 + r < C) {
+#pragma unroll
+      for (int e = 0; e < IPT; ++e) atomicAdd(dWout + (long long)(o0 + r) * C + hc + ib + e, acc[e]);
+    }
   }
+}
+
+template <int TM>
+static int launch(const float* P, long long p_batch_stride, const float* Wout, const float* gsum, const float* temperature,
+                  float* Wb, int ldwb, long long wb_batch_stride, float* dWout, float* dTemp, int B, int heads, cudaStream_t st) {
+  constexpr int c = 16 * TM;
+  const size_t smem = sizeof(float) * ((3 * c + 2 * 32) * (c + 1) + 4 * c);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(spectral_bwd_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("spectral_bwd: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+      return MPHSIR_ERR_CUDA;
+    }
+    configured = true;
+  }
+  spectral_bwd_kernel<TM><<<B * heads, 256, smem, st>>>(P, p_batch_stride, Wout, gsum, temperature, Wb, wb_batch_stride, ldwb,
+                                                        dWout, dTemp, heads);
+  return check_launch("spectral_bwd");
 }
 
 }  // namespace spb
@@ -142,18 +216,18 @@ extern "C" int mphsir_spectral_bwd(const float* P, long long p_batch_stride, con
                                    const float* temperature, float* Wb, int ldwb, long long wb_batch_stride, float* dWout,
                                    float* dTemperature, int B, int heads, int c, void* stream) {
   MPHSIR_REQUIRE(P && Wout && gsum && temperature && Wb && dWout && dTemperature, "spectral_bwd: null operand");
-  MPHSIR_REQUIRE(B > 0 && heads > 0 && c > 0 && c <= 128 && ldwb >= 2 * heads * c, "spectral_bwd: bad shape");
-  const size_t smem = sizeof(float) * (3 * c * (c + 1) + 4 * c);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(spb::spectral_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("spectral_bwd: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
-      return MPHSIR_ERR_CUDA;
-    }
-    configured = smem;
+  MPHSIR_REQUIRE(B > 0 && heads > 0 && c > 0 && ldwb >= 2 * heads * c, "spectral_bwd: bad shape");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define SPB_CASE(TM) \
+  case 16 * TM: return spb::launch<TM>(P, p_batch_stride, Wout, gsum, temperature, Wb, ldwb, wb_batch_stride, dWout, dTemperature, B, heads, st)
+  switch (c) {
+    SPB_CASE(2);
+    SPB_CASE(3);
+    SPB_CASE(4);
+    SPB_CASE(6);
+    default:
+      set_error("spectral_bwd: channels per head %d not supported (32, 48, 64, 96)", c);
+      return MPHSIR_ERR_INVALID;
   }
-  spb::spectral_bwd_kernel<<<B * heads, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      P, p_batch_stride, Wout, gsum, temperature, Wb, wb_batch_stride, ldwb, dWout, dTemperature, heads, c);
-  return check_launch("spectral_bwd");
+#undef SPB_CASE
 }

@@ -30,8 +30,10 @@ __device__ __forceinline__ float gelu_grad(float x) {
 // ------------------------------------------------------------------------------------------------
 // LayerNorm over the channel axis (nn.LayerNorm / WithBias_LayerNorm, net/MP_HSIR.py:618-619, :354-357)
 // ------------------------------------------------------------------------------------------------
-constexpr int LN_MAXV = 8;  // float4 chunks per lane -> C <= 1024
+constexpr int LN_MAXV_LIMIT = 8;  // float4 chunks per lane -> C <= 1024
 
+// LN_MAXV = ceil(C / 128): 1..3 for every width of the network (64..384); keeps xhat / g*gamma of a row in registers
+template <int LN_MAXV>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ X, long long ldx,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* __restrict__ Y, long long ldy, float* __restrict__ stats,
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 }
 
 // dX = add + rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat));  dgamma += sum g*xhat;  dbeta += sum g
+template <int LN_MAXV>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ X, long long ldx,
                                                             const float* __restrict__ stats, const float* __restrict__ gamma,
                                                             const float* __restrict__ G, long long ldg,
@@ -291,23 +294,39 @@ __device__ __forceinline__ int map_index(int o, int mode, int a, int b) {
 
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, long long ldx, float* __restrict__ out,
                                                      long long M, int C, int rows_per_cta, int mode, int ma, int mb) {
-  // block = 32 column lanes x 8 row lanes; grid.x = row chunks, grid.y = 32-column groups
-  __shared__ float red[8][33];
+  // block = 32 column quads (128 columns) x 8 row lanes; grid.x = row chunks, grid.y = 128-column groups
+  __shared__ float4 red[8][32];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int c = blockIdx.y * 32 + cx;
+  const int c = blockIdx.y * 128 + cx * 4;
   const long long m0 = (long long)blockIdx.x * rows_per_cta;
   const long long m1 = min(M, m0 + rows_per_cta);
-  float s = 0.f;
-  if (c < C)
-    for (long long m = m0 + ry; m < m1; m += 8) s += __ldg(X + m * ldx + c);
-  red[ry][cx] = s;
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+  if (c < C) {
+    long long m = m0 + ry;
+    for (; m + 8 < m1; m += 16) {
+      const float4 a = ldg4(X + m * ldx + c), b = ldg4(X + (m + 8) * ldx + c);
+      s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+      s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
+    }
+    if (m < m1) {
+      const float4 a = ldg4(X + m * ldx + c);
+      s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+    }
+  }
+  red[ry][cx] = make_float4(s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w);
   __syncthreads();
   if (ry == 0 && c < C) {
-    float t = 0.f;
+    float4 t = red[0][cx];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) t += red[r][cx];
-    const int dst = map_index(c, mode, ma, mb);
-    if (dst >= 0) atomicAdd(out + dst, t);
+    for (int r = 1; r < 8; ++r) {
+      t.x += red[r][cx].x; t.y += red[r][cx].y; t.z += red[r][cx].z; t.w += red[r][cx].w;
+    }
+    const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int dst = (c + e < C) ? map_index(c + e, mode, ma, mb) : -1;
+      if (dst >= 0) atomicAdd(out + dst, tv[e]);
+    }
   }
 }
 
@@ -383,36 +402,54 @@ __global__ void __launch_bounds__(256) gate_apply_bwd_kernel(const float* __rest
 
 // ------------------------------------------------------------------------------------------------
 // depthwise 3x3 weight gradient: dW[map(c), tap] += sum_{b,y,x} dY[b,y,x,c] * X[b,y+dy,x+dx,c]   (zero pad)
-// block = 64 channel quads x 4 pixel lanes; grid.x = pixel chunks, grid.y = 256-channel groups
+// Thread = (channel quad, image row): it walks the row with a sliding 3x3 window of X in registers (3 new float4 of X
+// + 1 of dY per pixel for 36 FMAs).  block = 64 quads x 4 row lanes, each lane takes rows_per_lane rows;
+// grid.x = row groups over B*H, grid.y = 256-channel groups.  Partial sums: shared-memory reduce, then atomics.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dwconv3x3_wgrad_kernel(const float* __restrict__ X, long long ldx,
                                                               const float* __restrict__ dY, long long ldy,
                                                               float* __restrict__ dW, int B, int H, int W, int C,
-                                                              int pix_per_cta, int mode, int ma, int mb) {
+                                                              int rows_per_lane, int mode, int ma, int mb) {
   __shared__ float4 red[4][64];
   const int q = threadIdx.x & 63, pl = threadIdx.x >> 6;
   const int c = blockIdx.y * 256 + q * 4;
-  const long long total = (long long)B * H * W;
-  const long long p0 = (long long)blockIdx.x * pix_per_cta, p1 = min(total, p0 + pix_per_cta);
+  const long long total_rows = (long long)B * H;
+  const long long r0 = ((long long)blockIdx.x * 4 + pl) * rows_per_lane;
   float4 acc[9];
 #pragma unroll
   for (int t = 0; t < 9; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c < C) {
-    for (long long p = p0 + pl; p < p1; p += 4) {
-      const int x = (int)(p % W), y = (int)((p / W) % H);
-      const float4 d = ldg4(dY + p * ldy + c);
+    for (long long row = r0; row < min(total_rows, r0 + rows_per_lane); ++row) {
+      const int y = (int)(row % H);
+      const float* xr = X + row * W * ldx + c;   // (b, y, 0)
+      const float* dr = dY + row * W * ldy + c;
+      const bool up = y > 0, dn = y + 1 < H;
+      // window columns: l = x-1, m = x, r = x+1 for rows y-1 (0), y (1), y+1 (2)
+      float4 wl[3] = {zero, zero, zero}, wm[3], wr[3];
+      wm[0] = up ? ldg4(xr - (long long)W * ldx) : zero;
+      wm[1] = ldg4(xr);
+      wm[2] = dn ? ldg4(xr + (long long)W * ldx) : zero;
+      for (int x = 0; x < W; ++x) {
+        if (x + 1 < W) {
+          const float* p = xr + (long long)(x + 1) * ldx;
+          wr[0] = up ? ldg4(p - (long long)W * ldx) : zero;
+          wr[1] = ldg4(p);
+          wr[2] = dn ? ldg4(p + (long long)W * ldx) : zero;
+        } else {
+          wr[0] = wr[1] = wr[2] = zero;
+        }
+        const float4 d = ldg4(dr + (long long)x * ldy);
 #pragma unroll
-      for (int dy = -1; dy <= 1; ++dy) {
-        if (y + dy < 0 || y + dy >= H) continue;
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-          if (x + dx < 0 || x + dx >= W) continue;
-          const float4 v = ldg4(X + (p + (long long)dy * W + dx) * ldx + c);
-          float4& a = acc[(dy + 1) * 3 + dx + 1];
-          a.x = fmaf(d.x, v.x, a.x);
-          a.y = fmaf(d.y, v.y, a.y);
-          a.z = fmaf(d.z, v.z, a.z);
-          a.w = fmaf(d.w, v.w, a.w);
+        for (int ky = 0; ky < 3; ++ky) {
+          float4& a0 = acc[ky * 3 + 0];
+          float4& a1 = acc[ky * 3 + 1];
+          float4& a2 = acc[ky * 3 + 2];
+          a0.x = fmaf(d.x, wl[ky].x, a0.x); a0.y = fmaf(d.y, wl[ky].y, a0.y); a0.z = fmaf(d.z, wl[ky].z, a0.z); a0.w = fmaf(d.w, wl[ky].w, a0.w);
+          a1.x = fmaf(d.x, wm[ky].x, a1.x); a1.y = fmaf(d.y, wm[ky].y, a1.y); a1.z = fmaf(d.z, wm[ky].z, a1.z); a1.w = fmaf(d.w, wm[ky].w, a1.w);
+          a2.x = fmaf(d.x, wr[ky].x, a2.x); a2.y = fmaf(d.y, wr[ky].y, a2.y); a2.z = fmaf(d.z, wr[ky].z, a2.z); a2.w = fmaf(d.w, wr[ky].w, a2.w);
+          wl[ky] = wm[ky];
+          wm[ky] = wr[ky];
         }
       }
     }
@@ -643,8 +680,14 @@ using namespace mphsir::trn;
 extern "C" int mphsir_layernorm_fwd(const float* X, int ldx, const float* gamma, const float* beta, float* Y, int ldy,
                                     float* stats, long long M, int C, void* stream) {
   MPHSIR_REQUIRE(X && gamma && beta && Y && M > 0, "layernorm_fwd: null operand");
-  MPHSIR_REQUIRE(C > 0 && C % 4 == 0 && C <= 128 * LN_MAXV && ldx % 4 == 0 && ldy % 4 == 0, "layernorm_fwd: C must be a multiple of 4, <= 1024");
-  layernorm_fwd_kernel<<<grid_for(M, 8), 256, 0, ST(stream)>>>(X, ldx, gamma, beta, Y, ldy, stats, M, C);
+  MPHSIR_REQUIRE(C > 0 && C % 4 == 0 && C <= 128 * LN_MAXV_LIMIT && ldx % 4 == 0 && ldy % 4 == 0, "layernorm_fwd: C must be a multiple of 4, <= 1024");
+  const int grid = grid_for(M, 8, 32);
+  switch ((C + 127) / 128) {
+    case 1: layernorm_fwd_kernel<1><<<grid, 256, 0, ST(stream)>>>(X, ldx, gamma, beta, Y, ldy, stats, M, C); break;
+    case 2: layernorm_fwd_kernel<2><<<grid, 256, 0, ST(stream)>>>(X, ldx, gamma, beta, Y, ldy, stats, M, C); break;
+    case 3: layernorm_fwd_kernel<3><<<grid, 256, 0, ST(stream)>>>(X, ldx, gamma, beta, Y, ldy, stats, M, C); break;
+    default: layernorm_fwd_kernel<LN_MAXV_LIMIT><<<grid, 256, 0, ST(stream)>>>(X, ldx, gamma, beta, Y, ldy, stats, M, C); break;
+  }
   return check_launch("layernorm_fwd");
 }
 
@@ -652,10 +695,19 @@ extern "C" int mphsir_layernorm_bwd(const float* X, int ldx, const float* stats,
                                     const float* add, int lda, float* dX, int lddx, float* dgamma, float* dbeta, long long M,
                                     int C, void* stream) {
   MPHSIR_REQUIRE(X && stats && gamma && G && dX && dgamma && dbeta && M > 0, "layernorm_bwd: null operand");
-  MPHSIR_REQUIRE(C > 0 && C % 4 == 0 && C <= 128 * LN_MAXV && ldx % 4 == 0 && ldg % 4 == 0 && lddx % 4 == 0 && lda % 4 == 0,
+  MPHSIR_REQUIRE(C > 0 && C % 4 == 0 && C <= 128 * LN_MAXV_LIMIT && ldx % 4 == 0 && ldg % 4 == 0 && lddx % 4 == 0 && lda % 4 == 0,
                  "layernorm_bwd: C must be a multiple of 4, <= 1024");
-  layernorm_bwd_kernel<<<grid_for(M, 64, 2), 256, sizeof(float) * 2 * C, ST(stream)>>>(X, ldx, stats, gamma, G, ldg, add, lda, dX,
-                                                                                     lddx, dgamma, dbeta, M, C);
+  // >= 16 rows per warp keeps the dgamma / dbeta flush (shared + global atomics per CTA) small next to the row traffic
+  const int grid = grid_for(M, 8 * 16, 8);
+  const size_t smem = sizeof(float) * 2 * C;
+#define LNB(V) layernorm_bwd_kernel<V><<<grid, 256, smem, ST(stream)>>>(X, ldx, stats, gamma, G, ldg, add, lda, dX, lddx, dgamma, dbeta, M, C)
+  switch ((C + 127) / 128) {
+    case 1: LNB(1); break;
+    case 2: LNB(2); break;
+    case 3: LNB(3); break;
+    default: LNB(LN_MAXV_LIMIT); break;
+  }
+#undef LNB
   return check_launch("layernorm_bwd");
 }
 
@@ -695,8 +747,8 @@ extern "C" int mphsir_batch_sum(const float* X, int ldx, float* Y, int ldy, int 
 
 extern "C" int mphsir_colsum(const float* X, int ldx, float* out, long long M, int C, int map_mode, int map_a, int map_b,
                              void* stream) {
-  MPHSIR_REQUIRE(X && out && M > 0 && C > 0, "colsum: bad arguments");
-  const int groups = (C + 31) / 32;
+  MPHSIR_REQUIRE(X && out && M > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0, "colsum: C and ldx must be multiples of 4");
+  const int groups = (C + 127) / 128;
   long long chunks = (2LL * sm_count() + groups - 1) / groups;
   if (chunks > (M + 63) / 64) chunks = (M + 63) / 64;
   if (chunks < 1) chunks = 1;
@@ -728,13 +780,13 @@ extern "C" int mphsir_dwconv3x3_wgrad(const float* X, int ldx, const float* dY, 
   MPHSIR_REQUIRE(X && dY && dW && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0,
                  "dwconv3x3_wgrad: bad arguments");
   const int groups = (C + 255) / 256;
-  const long long total = (long long)B * H * W;
-  long long chunks = (4LL * sm_count() + groups - 1) / groups;
-  if (chunks > (total + 63) / 64) chunks = (total + 63) / 64;
-  if (chunks < 1) chunks = 1;
-  const int ppc = (int)((total + chunks - 1) / chunks);
-  dim3 grid((unsigned)((total + ppc - 1) / ppc), groups);
-  dwconv3x3_wgrad_kernel<<<grid, 256, 0, ST(stream)>>>(X, ldx, dY, ldy, dW, B, H, W, C, ppc, map_mode, map_a, map_b);
+  const long long rows = (long long)B * H;
+  // enough CTAs for ~4 per SM, but at least 2 rows per lane so the reduction + atomics amortise
+  long long ctas = (4LL * sm_count() + groups - 1) / groups;
+  long long rpl = (rows + ctas * 4 - 1) / (ctas * 4);
+  if (rpl < 2) rpl = 2;
+  dim3 grid((unsigned)((rows + rpl * 4 - 1) / (rpl * 4)), groups);
+  dwconv3x3_wgrad_kernel<<<grid, 256, 0, ST(stream)>>>(X, ldx, dY, ldy, dW, B, H, W, C, (int)rpl, map_mode, map_a, map_b);
   return check_launch("dwconv3x3_wgrad");
 }
 

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(const Args p) {
   constexpr int A_ARR = KT * LDA, B_ARR = KT * LDB;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile_o = blockIdx.y / p.tiles_i, tile_i = blockIdx.y - tile_o * p.tiles_i;
+  const int tile_o = blockIdx.x / p.tiles_i, tile_i = blockIdx.x - tile_o * p.tiles_i;
   const int o0 = tile_o * TO, i0 = tile_i * TI;
 
   long long m_begin = 0, m_end = p.M;
@@ -151,13 +151,13 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(const Args p) {
   const uint32_t b_base = (uint32_t)__cvta_generic_to_shared(Bs);
   const int m0 = warp * 16;
 
-  long long chunk = blockIdx.x;
+  long long chunk = blockIdx.y;
   if (chunk < n_chunks) load_chunk(chunk);
-  for (; chunk < n_chunks; chunk += gridDim.x) {
+  for (; chunk < n_chunks; chunk += gridDim.y) {
     __syncthreads();  // the previous chunk's fragments have been consumed
     store_chunk();
     __syncthreads();
-    if (chunk + gridDim.x < n_chunks) load_chunk(chunk + gridDim.x);
+    if (chunk + gridDim.y < n_chunks) load_chunk(chunk + gridDim.y);
 #pragma unroll
     for (int ks = 0; ks < KT / 16; ++ks) {
       uint32_t ah[4], al[4];
@@ -228,7 +228,9 @@ static int launch(const Args& a, int z, cudaStream_t st) {
   long long splits = (2LL * sm_count() + (long long)tiles * z - 1) / ((long long)tiles * z);
   if (splits > (n_chunks + 3) / 4) splits = (n_chunks + 3) / 4;  // >= 4 chunks per CTA: bounds the atomic traffic
   if (splits < 1) splits = 1;
-  dim3 grid((unsigned)splits, (unsigned)tiles, (unsigned)z);
+  // blockIdx.x = tile (fastest): CTAs resident together walk the same token chunks, so each operand tile is read
+  // from HBM once and re-used by the other tiles through L2
+  dim3 grid((unsigned)tiles, (unsigned)splits, (unsigned)z);
   wgrad_kernel<PARTS><<<grid, 256, smem, st>>>(a);
   return check_launch("wgrad");
 }

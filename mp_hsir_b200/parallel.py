@@ -1,6 +1,7 @@
-"""Multi-GPU plumbing for the hot path: the forward shards over independent cubes / patches (one process per
-GPU, no data-path collective — SURVEY.md §8e), so all that is needed is unit assignment and the
-max-over-ranks reduction of device timings.  Backend-agnostic (nccl on GPUs, gloo in the CPU tests)."""
+"""Multi-GPU plumbing for the hot path.  Inference shards over independent cubes / patches (one process per GPU,
+no data-path collective — SURVEY.md §8e): unit assignment + max-over-ranks reduction of device timings.  Training is
+DDP batch sharding (train.py:118): ONE all-reduce of the flat gradient buffer per step, the mean folded into AdamW.
+Backend-agnostic (nccl on GPUs, gloo in the CPU tests)."""
 from __future__ import annotations
 
 from typing import List, Tuple
@@ -40,3 +41,17 @@ def gather_psnr(local: List[float], device=None) -> float:
     s = sum_over_ranks(sum(local), device)
     n = sum_over_ranks(len(local), device)
     return s / max(n, 1.0)
+
+
+def world_size() -> int:
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
+def all_reduce_gradients(flat_grad: torch.Tensor) -> float:
+    """DDP gradient averaging for the trainer's flat gradient buffer: SUM over ranks in place (one collective over
+    NVLink for the 617 tensors), returning the factor 1/world that AdamW applies to the summed gradient
+    (``TrainEngine.train_step(..., world_size=w, all_reduce=all_reduce_gradients)``)."""
+    w = world_size()
+    if w > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+    return 1.0 / w

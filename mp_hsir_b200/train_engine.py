@@ -46,6 +46,8 @@ class TrainEngine(Engine):
         self._flatten_parameters()
         self.loss_buf = torch.zeros(1, device=self.device, dtype=torch.float32)
         self._train_packed_version = None
+        self.time_graphs = False   # bench: CUDA events around the three graphs of the captured step -> self.graph_ms
+        self.graph_ms = None
 
     # -- flat parameter / gradient storage -----------------------------------------------------------
     def _flatten_parameters(self):
@@ -708,14 +710,28 @@ class TrainEngine(Engine):
             sx.copy_(inp, non_blocking=True)
             sc.copy_(clean, non_blocking=True)
             sw.copy_(self.task_weights(task_id), non_blocking=True)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if self.time_graphs else None
+            if ev:
+                ev[0].record()
             g_main.replay()
+            if ev:
+                ev[1].record()
             if all_reduce is not None:
                 all_reduce(self.flat_g)
             self.step_count += 1
             dyn[0:1].fill_(self.lr)  # stream-ordered scalars: an lr schedule just changes self.lr
             dyn[3:4].fill_(float(self.step_count - 1))
+            if ev:
+                ev[2].record()
             g_opt.replay()           # bumps the device step counter, bias corrections, AdamW
+            if ev:
+                ev[3].record()
             g_pack.replay()          # weight images for the next forward
+            if ev:
+                ev[4].record()
+                torch.cuda.synchronize()
+                self.graph_ms = {"fwd_bwd": ev[0].elapsed_time(ev[1]), "all_reduce": ev[1].elapsed_time(ev[2]),
+                                 "adamw": ev[2].elapsed_time(ev[3]), "repack": ev[3].elapsed_time(ev[4])}
             lib.LAUNCHES += ent[7]
         return self.loss_buf
 

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from mp_hsir_b200.parallel import gather_psnr, max_over_ranks, shard_range
+from mp_hsir_b200.parallel import all_reduce_gradients, gather_psnr, max_over_ranks, shard_range
 
 
 def _free_port():
@@ -22,8 +22,11 @@ def _worker(rank, world, port, out):
         lo, hi = shard_range(7, rank, world)
         slowest = max_over_ranks(10.0 + 5.0 * rank)
         mean = gather_psnr([30.0 + u for u in range(lo, hi)])
+        # DDP step of the trainer: every rank holds the gradient of ITS batch shard in one flat buffer
+        flat = torch.full((1000,), float(rank + 1))
+        scale = all_reduce_gradients(flat)
         dist.barrier()
-        out.put((rank, lo, hi, slowest, mean))
+        out.put((rank, lo, hi, slowest, mean, float((flat * scale).mean()), float(flat.min()), float(flat.max())))
     finally:
         dist.destroy_process_group()
 
@@ -42,6 +45,7 @@ def test_two_rank_sharding_and_reductions():
     assert [(r[1], r[2]) for r in res] == [(0, 4), (4, 7)]            # 7 cubes over 2 ranks, disjoint + complete
     assert all(abs(r[3] - 15.0) < 1e-12 for r in res)                  # max over ranks
     assert all(abs(r[4] - (30.0 + 3.0)) < 1e-12 for r in res)          # mean over all 7 cubes
+    assert all(r[5] == 1.5 and r[6] == r[7] == 3.0 for r in res)       # summed gradient, mean = sum / world on every rank
 
 
 def test_shard_range_covers_everything():
