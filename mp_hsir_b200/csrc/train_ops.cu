@@ -781,8 +781,10 @@ extern "C" int mphsir_dwconv3x3_wgrad(const float* X, int ldx, const float* dY, 
                  "dwconv3x3_wgrad: bad arguments");
   const int groups = (C + 255) / 256;
   const long long rows = (long long)B * H;
-  // enough CTAs for ~4 per SM, but at least 2 rows per lane so the reduction + atomics amortise
-  long long ctas = (4LL * sm_count() + groups - 1) / groups;
+  // one full wave (2 CTAs of 256 threads per SM at 122 registers), at least 2 rows per lane so the reduction +
+  // atomics amortise
+  long long ctas = (2LL * sm_count()) / groups;
+  if (ctas < 1) ctas = 1;
   long long rpl = (rows + ctas * 4 - 1) / (ctas * 4);
   if (rpl < 2) rpl = 2;
   dim3 grid((unsigned)((rows + rpl * 4 - 1) / (rpl * 4)), groups);

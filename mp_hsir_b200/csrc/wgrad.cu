@@ -24,10 +24,11 @@ constexpr int LDA = TO + 8, LDB = TI + 8;
 __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr));
+               : "r"(addr)
+               : "memory");
 }
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -100,50 +101,52 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(const Args p) {
     for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
 
   float4 ra[8], rb[4];
+  // per-thread constants of the chunk loads: A unit (row ta + 8r, quad oq), B unit (row tb + 16r, quad iq)
+  const int ta = tid >> 5, oq = tid & 31, tb = tid >> 4, iq = tid & 15;
+  const bool a_col_ok = o0 + 4 * oq < p.O, b_col_ok = i0 + 4 * iq < p.I;
+  const float* a_col = p.dY + o0 + 4 * oq;
+  const float* b_col = p.X + i0 + 4 * iq;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   auto load_chunk = [&](long long chunk) {
     const long long mc = m_begin + chunk * KT;
+    const float* ap = a_col + (mc + ta) * p.lddy;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int u = tid + 256 * r;
-      const int t = u >> 5, oq = u & 31;
-      const long long m = mc + t;
-      const int o = o0 + 4 * oq;
-      ra[r] = (m < m_end && o < p.O) ? ldg4(p.dY + m * p.lddy + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    for (int r = 0; r < 8; ++r)
+      ra[r] = (a_col_ok && mc + ta + 8 * r < m_end) ? ldg4(ap + (long long)(8 * r) * p.lddy) : zero4;
+    if (p.taps == 9 || p.x_row_mod > 0) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int u = tid + 256 * r;
-      const int t = u >> 4, iq = u & 15;
-      long long m = mc + t;
-      const int i = i0 + 4 * iq;
-      bool ok = (m < m_end && i < p.I);
-      if (ok && p.taps == 9) {
-        const int x = (int)(m % p.W), y = (int)((m / p.W) % p.H);
-        ok = (unsigned)(y + dy) < (unsigned)p.H && (unsigned)(x + dx) < (unsigned)p.W;
-        m += (long long)dy * p.W + dx;
+      for (int r = 0; r < 4; ++r) {
+        long long m = mc + tb + 16 * r;
+        bool ok = b_col_ok && m < m_end;
+        if (ok && p.taps == 9) {
+          const int x = (int)(m % p.W), y = (int)((m / p.W) % p.H);
+          ok = (unsigned)(y + dy) < (unsigned)p.H && (unsigned)(x + dx) < (unsigned)p.W;
+          m += (long long)dy * p.W + dx;
+        }
+        if (ok && p.x_row_mod > 0) m %= p.x_row_mod;
+        rb[r] = ok ? ldg4(b_col + m * p.ldx) : zero4;
       }
-      if (ok && p.x_row_mod > 0) m %= p.x_row_mod;
-      rb[r] = ok ? ldg4(p.X + m * p.ldx + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      const float* bp = b_col + (mc + tb) * p.ldx;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        rb[r] = (b_col_ok && mc + tb + 16 * r < m_end) ? ldg4(bp + (long long)(16 * r) * p.ldx) : zero4;
     }
   };
   auto store_chunk = [&]() {
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      const int u = tid + 256 * r;
-      const int t = u >> 5, oq = u & 31;
       uint2 hi, lo;
       split4(ra[r], hi, lo);
-      *reinterpret_cast<uint2*>(As + t * LDA + 4 * oq) = hi;
-      if (PARTS == 2) *reinterpret_cast<uint2*>(As + A_ARR + t * LDA + 4 * oq) = lo;
+      *reinterpret_cast<uint2*>(As + (ta + 8 * r) * LDA + 4 * oq) = hi;
+      if (PARTS == 2) *reinterpret_cast<uint2*>(As + A_ARR + (ta + 8 * r) * LDA + 4 * oq) = lo;
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const int u = tid + 256 * r;
-      const int t = u >> 4, iq = u & 15;
       uint2 hi, lo;
       split4(rb[r], hi, lo);
-      *reinterpret_cast<uint2*>(Bs + t * LDB + 4 * iq) = hi;
-      if (PARTS == 2) *reinterpret_cast<uint2*>(Bs + B_ARR + t * LDB + 4 * iq) = lo;
+      *reinterpret_cast<uint2*>(Bs + (tb + 16 * r) * LDB + 4 * iq) = hi;
+      if (PARTS == 2) *reinterpret_cast<uint2*>(Bs + B_ARR + (tb + 16 * r) * LDB + 4 * iq) = lo;
     }
   };
 
@@ -160,23 +163,30 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(const Args p) {
     if (chunk + gridDim.y < n_chunks) load_chunk(chunk + gridDim.y);
 #pragma unroll
     for (int ks = 0; ks < KT / 16; ++ks) {
-      uint32_t ah[4], al[4];
+      // every fragment of this k-step first (ldmatrix latency overlaps), then 8 (24) independent MMAs
+      uint32_t ah[4], al[4], bh[4][4], bl[4][4];
       const uint32_t a_off = (uint32_t)(((16 * ks + (lane & 7) + ((lane >> 4) & 1) * 8) * LDA + m0 + ((lane >> 3) & 1) * 8) * 2);
+      const uint32_t b_row = (uint32_t)((16 * ks + (lane & 7) + ((lane >> 3) & 1) * 8) * LDB + 8 * (lane >> 4));
       ldsm_x4_trans(a_base + a_off, ah);
-      if (PARTS == 2) ldsm_x4_trans(a_base + A_ARR * 2 + a_off, al);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) ldsm_x4_trans(b_base + (b_row + 16 * np) * 2, bh[np]);
+      if (PARTS == 2) {
+        ldsm_x4_trans(a_base + A_ARR * 2 + a_off, al);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) ldsm_x4_trans(b_base + B_ARR * 2 + (b_row + 16 * np) * 2, bl[np]);
+      }
 #pragma unroll
       for (int np = 0; np < 4; ++np) {
-        const uint32_t b_off = (uint32_t)(((16 * ks + (lane & 7) + ((lane >> 3) & 1) * 8) * LDB + 8 * (2 * np + (lane >> 4))) * 2);
-        uint32_t bh[4], bl[4];
-        ldsm_x4_trans(b_base + b_off, bh);
-        mma_bf16(acc[2 * np], ah, bh[0], bh[1]);
-        mma_bf16(acc[2 * np + 1], ah, bh[2], bh[3]);
-        if (PARTS == 2) {
-          ldsm_x4_trans(b_base + B_ARR * 2 + b_off, bl);
-          mma_bf16(acc[2 * np], ah, bl[0], bl[1]);
-          mma_bf16(acc[2 * np + 1], ah, bl[2], bl[3]);
-          mma_bf16(acc[2 * np], al, bh[0], bh[1]);
-          mma_bf16(acc[2 * np + 1], al, bh[2], bh[3]);
+        mma_bf16(acc[2 * np], ah, bh[np][0], bh[np][1]);
+        mma_bf16(acc[2 * np + 1], ah, bh[np][2], bh[np][3]);
+      }
+      if (PARTS == 2) {
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          mma_bf16(acc[2 * np], ah, bl[np][0], bl[np][1]);
+          mma_bf16(acc[2 * np + 1], ah, bl[np][2], bl[np][3]);
+          mma_bf16(acc[2 * np], al, bh[np][0], bh[np][1]);
+          mma_bf16(acc[2 * np + 1], al, bh[np][2], bh[np][3]);
         }
       }
     }
@@ -225,7 +235,7 @@ static int launch(const Args& a, int z, cudaStream_t st) {
   const int tiles = ((a.O + TO - 1) / TO) * a.tiles_i;
   const long long rows = a.rows_per_batch > 0 && a.taps != 9 ? a.rows_per_batch : a.M;
   const long long n_chunks = (rows + KT - 1) / KT;
-  long long splits = (2LL * sm_count() + (long long)tiles * z - 1) / ((long long)tiles * z);
+  long long splits = (2LL * sm_count()) / ((long long)tiles * z);  // floor: one full wave of 2 CTAs per SM, no tail wave
   if (splits > (n_chunks + 3) / 4) splits = (n_chunks + 3) / 4;  // >= 4 chunks per CTA: bounds the atomic traffic
   if (splits < 1) splits = 1;
   // blockIdx.x = tile (fastest): CTAs resident together walk the same token chunks, so each operand tile is read

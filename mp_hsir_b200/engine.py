@@ -157,6 +157,7 @@ class Engine:
         self.ws = Workspace(self.device)
         self.prec = PRECISIONS[net.precision]
         self.fuse_mlp = True
+        self.fold_weights = True   # fp64 weight folds (proj into the gate / spectral-qkv matrices); the trainer turns it off
         self.fold_proj = True
         self.split_gate = True
         self.packed: Optional[dict] = None
@@ -225,6 +226,28 @@ class Engine:
                 r = st.rank
                 # fold Spatial_Attention.proj into the two matrices that consume its (window-mean) output;
                 # done in fp64 so the fold itself adds no rounding beyond the final fp32 cast
+                d["gate"] = {
+                    "param": f32(l.prompt_param).reshape(PROMPT_LEN, r).contiguous(),
+                    "qT": f32(l.q.weight).t().contiguous(),
+                    "kvT": f32(l.kv.weight).t().contiguous(),
+                    "p2T": f32(l.proj.weight).t().contiguous(),
+                    "p2b": f32(l.proj.bias).contiguous(),
+                    "upT": f32(l.linear_up.weight).t().contiguous(),
+                }
+                if not self.fold_weights:
+                    # training: weights change every step, so the fp64 folds below are not worth re-doing; the local gate is
+                    # computed from the window mean of the *projected* attention output with the plain matrices instead
+                    nlp = _ceil(PROMPT_LEN + r, 8)
+                    cat = f32(l.linear_prompt.weight).new_zeros(nlp, st.dim)
+                    cat[:PROMPT_LEN] = f32(l.linear_prompt.weight)
+                    cat[PROMPT_LEN:PROMPT_LEN + r] = f32(l.linear_down.weight)
+                    d["ll_w"] = W(pack_linear_t(cat), nlp, st.dim)
+                    fc1_w, d["fc1_b"] = pack_glu_fc1(f32(blk.mlp.fc1.weight), f32(blk.mlp.fc1.bias), hid, hid_pad)
+                    d["fc1_w"] = W(fc1_w, 2 * hid_pad, st.dim)
+                    d["fc2_w"] = W(pack_linear_t(f32(blk.mlp.fc2.weight), k_pad=hid_pad), st.dim, hid_pad)
+                    d["fc2_b"] = f32(blk.mlp.fc2.bias).contiguous()
+                    blocks.append(d)
+                    continue
                 pw64, pb64 = a.proj.weight.detach().double().to(self.device), a.proj.bias.detach().double().to(self.device)
                 lp64, ld64 = l.linear_prompt.weight.detach().double().to(self.device), l.linear_down.weight.detach().double().to(self.device)
                 if tc and st.dim % 32 == 0:
@@ -236,18 +259,12 @@ class Engine:
                 # prompt logits and low-rank projection of the window mean as one GEMM: rows [W_prompt W_p ; W_down W_p]
                 d["gate_cat_w"] = W(pack_linear_t(torch.cat([lp64 @ pw64, ld64 @ pw64], 0).float()), PROMPT_LEN + r, st.dim)
                 d["gate_cat_b"] = torch.cat([lp64 @ pb64, ld64 @ pb64]).float().contiguous()
-                d["gate"] = {
+                d["gate"].update({
                     "promptT": (lp64 @ pw64).t().float().contiguous(),
                     "promptb": (lp64 @ pb64).float().contiguous(),
                     "downT": (ld64 @ pw64).t().float().contiguous(),
                     "downb": (ld64 @ pb64).float().contiguous(),
-                    "param": f32(l.prompt_param).reshape(PROMPT_LEN, r).contiguous(),
-                    "qT": f32(l.q.weight).t().contiguous(),
-                    "kvT": f32(l.kv.weight).t().contiguous(),
-                    "p2T": f32(l.proj.weight).t().contiguous(),
-                    "p2b": f32(l.proj.bias).contiguous(),
-                    "upT": f32(l.linear_up.weight).t().contiguous(),
-                }
+                })
                 fc1_w, d["fc1_b"] = pack_glu_fc1(f32(blk.mlp.fc1.weight), f32(blk.mlp.fc1.bias), hid, hid_pad)
                 d["fc1_w"] = W(fc1_w, 2 * hid_pad, st.dim)
                 d["fc2_w"] = W(pack_linear_t(f32(blk.mlp.fc2.weight), k_pad=hid_pad), st.dim, hid_pad)
@@ -368,7 +385,9 @@ class Engine:
         # shifted-window attention core + per-window mean (:671-683, :198-215)
         lib.window_attn(qkv, w["rpb"], core, wmean, B, H, W, C, heads, shift, precision=self.prec)
         # local spectral gate (:132-152)
-        if self.split_gate and st.rank % 4 == 0:
+        if "gate_cat_w" not in w:
+            pass  # un-folded weights (trainer): the gate is computed below from the window mean of sa
+        elif self.split_gate and st.rank % 4 == 0:
             logits = ws.mat("gate_logits", B_, _ceil(PROMPT_LEN + st.rank, 16))
             self._gemm(View(wmean.data_ptr(), C, B_, C, wmean), w["gate_cat_w"], logits, PROMPT_LEN + st.rank, bias=w["gate_cat_b"])
             lib.local_gate_tail(logits, w["gate"], gate, B_, C, st.rank)
@@ -386,6 +405,8 @@ class Engine:
         else:
             # attention output projection (:216) in image order
             self._gemm(core, w["proj_w"], sa, C, bias=w["proj_b"])
+            if "gate_cat_w" not in w:
+                self._gate_from_sa(w, st, sa, gate, B, H, W, shift)
             # global spectral attention: 1x1 -> dw3x3 -> Gram/softmax/fold -> apply (:98-113)
             self._gemm(sa, w["sqkv_w"], t3, 3 * C)
             v, Mt = self._global_spectral("spec", t3, w["sdw"], w["temp"], w["sout_t"], B, H, W, C, heads)
@@ -405,6 +426,16 @@ class Engine:
             taps.update(core=core.torch().clone(), wmean=wmean[: B_ * C].view(B_, C).clone(),
                         gate=gate[: B_ * C].view(B_, C).clone(), sa=sa.torch().clone(), mid=mid.torch().clone(),
                         out=out.torch().clone())
+
+    def _gate_from_sa(self, w: dict, st: Stage, sa: View, gate, B: int, H: int, W: int, shift: int, msa=None, LL=None):
+        """local spectral gate from the window mean of the projected attention output (:135-152), plain weights"""
+        C, B_ = st.dim, B * H * W // 64
+        msa = self.ws.flat("gate_msa", B_ * C) if msa is None else msa
+        lib.window_reduce(sa, None, msa, B, H, W, C, shift, 1.0 / 64.0)
+        nl = w["ll_w"].n
+        LL = self.ws.mat("gate_LL", B_, _ceil(nl, 16)) if LL is None else LL
+        self._gemm(View(msa.data_ptr(), C, B_, C, msa), w["ll_w"], LL, nl)
+        lib.local_gate_tail(LL, w["gate"], gate, B_, C, st.rank)
 
     def _stage(self, name: str, x_in: View, out: View, B: int, H: int, W: int):
         st = {s.name: s for s in self.cfg.stages()}[name]

@@ -41,6 +41,7 @@ class TrainEngine(Engine):
         super().__init__(net)
         if self.prec == lib.PREC_FP32_SIMT:
             raise ValueError("training runs on the tensor-core engine: precision must be 'fp32' (bf16x3) or 'bf16'")
+        self.fold_weights = False
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.step_count = 0
         self._flatten_parameters()
@@ -108,13 +109,8 @@ class TrainEngine(Engine):
                     d[k + ".d"] = self._dgrad_of(d[k])
                 d["sdw.f"] = _flip_dw(d["sdw"])
                 l = blk.local_spectral_attn
-                # [W_prompt ; W_down ; 0] with the row count padded to a multiple of 8 (the GEMM engine's K granularity
-                # when this matrix is used transposed for dL/dm)
-                nlp = _ceil(PROMPT_LEN + st.rank, 8)
-                cat = f32(l.linear_prompt.weight).new_zeros(nlp, st.dim)
-                cat[:PROMPT_LEN] = f32(l.linear_prompt.weight)
-                cat[PROMPT_LEN:PROMPT_LEN + st.rank] = f32(l.linear_down.weight)
-                d["ll_w"] = self._W(pack_linear_t(cat), nlp, st.dim)
+                # ll_w = [W_prompt ; W_down ; 0], rows padded to a multiple of 8 (the GEMM engine's K granularity when the
+                # matrix is used transposed for dL/dm) — packed by Engine._pack (fold_weights = False)
                 d["ll_w.d"] = self._dgrad_of(d["ll_w"])
                 d["gate_raw"] = {
                     "param": f32(l.prompt_param).reshape(PROMPT_LEN, st.rank).contiguous(),
@@ -217,12 +213,9 @@ class TrainEngine(Engine):
         sa = S["sa"] = ws.mat(pre + "sa", N, C)
         self._gemm(core, w["proj_w"], sa, C, bias=w["proj_b"])
         gate = S["gate"] = ws.flat(pre + "gate", B_ * C)
-        if st.rank % 4 == 0:
-            logits = ws.mat("gate_logits", B_, _ceil(PROMPT_LEN + st.rank, 16))
-            self._gemm(View(wmean.data_ptr(), C, B_, C, wmean), w["gate_cat_w"], logits, PROMPT_LEN + st.rank, bias=w["gate_cat_b"])
-            lib.local_gate_tail(logits, w["gate"], gate, B_, C, st.rank)
-        else:
-            lib.local_gate(wmean, w["gate"], gate, B_, C, st.rank)
+        S["msa"] = ws.flat(pre + "msa", B_ * C)
+        S["LL"] = ws.mat(pre + "LL", B_, _ceil(w["ll_w"].n, 16))
+        self._gate_from_sa(w, st, sa, gate, B, H, W, shift, S["msa"], S["LL"])
         t3 = S["t3"] = ws.mat(pre + "t3", N, 3 * C)
         self._gemm(sa, w["sqkv_w"], t3, 3 * C)
         dw3 = S["dw3"] = ws.mat(pre + "dw3", N, 3 * C)
@@ -284,12 +277,9 @@ class TrainEngine(Engine):
         # ---- local spectral gate (:135-153)
         dg = ws.flat("b.dg", B_ * C)
         lib.window_reduce(du, sa, dg, B, H, W, C, shift, 1.0)
-        msa = ws.flat("b.msa", B_ * C)
-        lib.window_reduce(sa, None, msa, B, H, W, C, shift, 1.0 / 64.0)
+        msa, LL = S["msa"], S["LL"]     # window mean of sa and [W_prompt m | W_down m], kept by the forward
         msa_v, dg_v = View(msa.data_ptr(), C, B_, C, msa), View(dg.data_ptr(), C, B_, C, dg)
-        nl = _ceil(PROMPT_LEN + r, 8)   # record columns [128+r, nl) hit zero weight rows
-        LL = ws.mat("b.LL", B_, _ceil(nl, 16))
-        self._gemm(msa_v, w["ll_w"], LL, nl)
+        nl = w["ll_w"].n                # record columns [128+r, nl) hit zero weight rows
         ldr = lib.local_gate_bwd_record_ld(r)
         rec = ws.mat("b.rec", B_, ldr)
         lib.local_gate_bwd(LL, dg, w["gate_raw"], rec, B_, C, r)

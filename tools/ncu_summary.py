@@ -41,7 +41,7 @@ def launches(path):
             rows.append((short(r["Kernel Name"]), v * scale))
     # keep exactly one forward step: the launches between two consecutive nchw_to_tokens kernels
     marks = [i for i, (k, _) in enumerate(rows) if "nchw_to_tokens" in k]
-    if len(marks) >= 2:
+    if len(marks) >= 2 and "all" not in sys.argv[3:]:
         rows = rows[marks[0]:marks[1]]
     agg = defaultdict(lambda: [0, 0.0])
     for k, us in rows:
