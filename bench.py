@@ -57,6 +57,19 @@ def peaks():
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_traffic(workload: str, family: str):
+    """DRAM bytes per launch of a kernel family from the committed ncu capture of this workload (profiles/traffic_<workload>.json,
+    written by tools/ncu_traffic.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over one step)."""
+    p = os.path.join(ROOT, "profiles", f"traffic_{workload}.json")
+    try:
+        with open(p) as f:
+            fam = json.load(f)["families"].get(family)
+        return None if fam is None else {"bytes_per_launch": fam["dram_bytes_per_launch"], "launches": fam["launches"],
+                                         "source": os.path.relpath(p, ROOT)}
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
 
@@ -301,6 +314,11 @@ def run_train(args):
         else:
             ach = a["bytes"] / sec / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None}
+        tr_ = ncu_traffic(args.workload, name) if precision == "bf16" else None
+        if tr_ is not None:
+            roof["traffic"] = tr_["bytes_per_launch"]
+            roof["traffic_source"] = f"{tr_['source']}: ncu dram read+write bytes / launch over the {tr_['launches']} launches of one step"
+            roof["algorithmic_bytes_per_launch"] = a["bytes"] / a["launches"]
         roof.update({"kernel": name, "share_of_step": round(a["ms"] / total_ms, 4), "launches": a["launches"],
                      "avg_launch_ms": a["ms"] / a["launches"], "algorithmic_bytes_per_step": a["bytes"],
                      "algorithmic_flops_per_step": a["flops"],
@@ -510,6 +528,11 @@ def main():
                 ach = a["bytes"] / sec / 1e9
                 roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                         "traffic": None}
+            tr_ = ncu_traffic(args.workload, name) if precision == "fp32" else None
+            if tr_ is not None:
+                roof["traffic"] = tr_["bytes_per_launch"]
+                roof["traffic_source"] = f"{tr_['source']}: ncu dram read+write bytes / launch over the {tr_['launches']} launches of one step"
+                roof["algorithmic_bytes_per_launch"] = a["bytes"] / a["launches"]
             roof.update({"kernel": name, "share_of_step": round(a["ms"] / total_ms, 4), "launches": a["launches"] // passes,
                          "avg_launch_ms": a["ms"] / a["launches"],
                          "algorithmic_bytes_per_step": a["bytes"] / passes, "algorithmic_flops_per_step": a["flops"] / passes,

@@ -367,7 +367,8 @@ MPHSIR_API int mphsir_batch_sum(const float* X, int ldx, float* Y, int ldy, int 
 MPHSIR_API int mphsir_window_attn_bwd_groups(int B, int H, int W, int heads);
 MPHSIR_API int mphsir_window_attn_bwd(const float* qkv, int ldqkv, const float* bias, const float* dO, int ldo, float* dqkv,
                                       int lddq, float* dbias_partial, int groups, int B, int H, int W, int C, int heads,
-                                      int shift, void* stream);
+                                      int shift, int precision /* MPHSIR_PREC_*: FFMA, or mma.sync with bf16x3 / bf16 operands */,
+                                      void* stream);
 MPHSIR_API int mphsir_rpb_table_bwd(const float* dbias /* [heads,64,64] */, float* dtable /* [225,heads] */, int heads,
                                     void* stream);
 

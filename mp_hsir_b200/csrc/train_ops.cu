@@ -346,33 +346,50 @@ __device__ __forceinline__ long long window_token(int win, int t, int H, int W, 
 }
 
 // out[win, c] = scale * sum_{t in win} A[t, c] * (Bm ? Bm[t, c] : 1)
+// CTA = (window, 128-channel group): 32 channel quads x 8 token lanes, 8 independent loads per thread, smem reduce
 __global__ void __launch_bounds__(256) window_reduce_kernel(const float* __restrict__ A, long long lda,
                                                             const float* __restrict__ Bm, long long ldb,
                                                             float* __restrict__ out, int n_win, int H, int W, int C,
                                                             int shift, float scale) {
-  const int c4n = C >> 2;
-  const long long total = (long long)n_win * c4n;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int win = (int)(idx / c4n);
-    const int c = (int)(idx - (long long)win * c4n) * 4;
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t = 0; t < 64; ++t) {
-      const long long n = window_token(win, t, H, W, shift);
-      float4 a = ldg4(A + n * lda + c);
-      if (Bm != nullptr) {
-        const float4 b = ldg4(Bm + n * ldb + c);
-        a.x *= b.x;
-        a.y *= b.y;
-        a.z *= b.z;
-        a.w *= b.w;
+  __shared__ float4 red[8][32];
+  const int q = threadIdx.x & 31, tl = threadIdx.x >> 5;
+  const int win = blockIdx.x;
+  const int c = blockIdx.y * 128 + q * 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+    float4 a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = ldg4(A + window_token(win, tl * 8 + i, H, W, shift) * lda + c);
+    if (Bm != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = ldg4(Bm + window_token(win, tl * 8 + i, H, W, shift) * ldb + c);
+        a[i].x *= b.x;
+        a[i].y *= b.y;
+        a[i].z *= b.z;
+        a[i].w *= b.w;
       }
-      s.x += a.x;
-      s.y += a.y;
-      s.z += a.z;
-      s.w += a.w;
     }
-    *reinterpret_cast<float4*>(out + (long long)win * C + c) = make_float4(s.x * scale, s.y * scale, s.z * scale, s.w * scale);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s.x += a[i].x;
+      s.y += a[i].y;
+      s.z += a[i].z;
+      s.w += a[i].w;
+    }
+  }
+  red[tl][q] = s;
+  __syncthreads();
+  if (tl == 0 && c < C) {
+    float4 t = red[0][q];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) {
+      t.x += red[r][q].x;
+      t.y += red[r][q].y;
+      t.z += red[r][q].z;
+      t.w += red[r][q].w;
+    }
+    *reinterpret_cast<float4*>(out + (long long)win * C + c) = make_float4(t.x * scale, t.y * scale, t.z * scale, t.w * scale);
   }
 }
 
@@ -426,20 +443,29 @@ __global__ void __launch_bounds__(256) dwconv3x3_wgrad_kernel(const float* __res
       const float* dr = dY + row * W * ldy + c;
       const bool up = y > 0, dn = y + 1 < H;
       // window columns: l = x-1, m = x, r = x+1 for rows y-1 (0), y (1), y+1 (2)
-      float4 wl[3] = {zero, zero, zero}, wm[3], wr[3];
+      float4 wl[3] = {zero, zero, zero}, wm[3], wr[3], d;
       wm[0] = up ? ldg4(xr - (long long)W * ldx) : zero;
       wm[1] = ldg4(xr);
       wm[2] = dn ? ldg4(xr + (long long)W * ldx) : zero;
+      // column x+1 and dY[x] are always one iteration ahead of the FMAs that consume them
+      {
+        const float* p = xr + ldx;
+        const bool in = 1 < W;
+        wr[0] = (in && up) ? ldg4(p - (long long)W * ldx) : zero;
+        wr[1] = in ? ldg4(p) : zero;
+        wr[2] = (in && dn) ? ldg4(p + (long long)W * ldx) : zero;
+        d = ldg4(dr);
+      }
       for (int x = 0; x < W; ++x) {
-        if (x + 1 < W) {
-          const float* p = xr + (long long)(x + 1) * ldx;
-          wr[0] = up ? ldg4(p - (long long)W * ldx) : zero;
-          wr[1] = ldg4(p);
-          wr[2] = dn ? ldg4(p + (long long)W * ldx) : zero;
-        } else {
-          wr[0] = wr[1] = wr[2] = zero;
+        float4 nr[3], nd;
+        {
+          const bool in = x + 2 < W;
+          const float* p = xr + (long long)(x + 2) * ldx;
+          nr[0] = (in && up) ? ldg4(p - (long long)W * ldx) : zero;
+          nr[1] = in ? ldg4(p) : zero;
+          nr[2] = (in && dn) ? ldg4(p + (long long)W * ldx) : zero;
+          nd = (x + 1 < W) ? ldg4(dr + (long long)(x + 1) * ldy) : zero;
         }
-        const float4 d = ldg4(dr + (long long)x * ldy);
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
           float4& a0 = acc[ky * 3 + 0];
@@ -450,7 +476,9 @@ __global__ void __launch_bounds__(256) dwconv3x3_wgrad_kernel(const float* __res
           a2.x = fmaf(d.x, wr[ky].x, a2.x); a2.y = fmaf(d.y, wr[ky].y, a2.y); a2.z = fmaf(d.z, wr[ky].z, a2.z); a2.w = fmaf(d.w, wr[ky].w, a2.w);
           wl[ky] = wm[ky];
           wm[ky] = wr[ky];
+          wr[ky] = nr[ky];
         }
+        d = nd;
       }
     }
   }
@@ -763,7 +791,8 @@ extern "C" int mphsir_window_reduce(const float* A, int lda, const float* Bm, in
   MPHSIR_REQUIRE(A && out && B > 0 && H % 8 == 0 && W % 8 == 0 && C % 4 == 0 && lda % 4 == 0 && (Bm == nullptr || ldb % 4 == 0),
                  "window_reduce: bad arguments");
   const int n_win = B * (H / 8) * (W / 8);
-  window_reduce_kernel<<<grid_for((long long)n_win * (C / 4), 256, 32), 256, 0, ST(stream)>>>(A, lda, Bm, ldb, out, n_win, H, W, C, shift, scale);
+  dim3 grid(n_win, (C + 127) / 128);
+  window_reduce_kernel<<<grid, 256, 0, ST(stream)>>>(A, lda, Bm, ldb, out, n_win, H, W, C, shift, scale);
   return check_launch("window_reduce");
 }
 

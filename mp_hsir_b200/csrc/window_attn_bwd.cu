@@ -265,6 +265,11 @@ static int launch(const float* qkv, int ldqkv, const float* bias, const float* d
 }
 
 }  // namespace wab
+namespace wabm {
+int launch_window_attn_bwd_mma(const float* qkv, int ldqkv, const float* bias, const float* dO, int ldo, float* dqkv, int lddq,
+                               float* partial, int groups, int B, int H, int W, int C, int heads, int shift, int parts,
+                               cudaStream_t st);
+}
 }  // namespace mphsir
 
 using namespace mphsir;
@@ -274,19 +279,22 @@ extern "C" int mphsir_window_attn_bwd_groups(int B, int H, int W, int heads) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int n_win = B * (H / 8) * (W / 8);
-  int g = (2 * sms + heads - 1) / heads;
+  int g = (4 * sms) / heads;  // one wave of the 128-thread tensor-core kernel at 4 CTAs per SM (2 waves of the FFMA kernel)
   if (g > n_win) g = n_win;
   return g < 1 ? 1 : g;
 }
 
 extern "C" int mphsir_window_attn_bwd(const float* qkv, int ldqkv, const float* bias, const float* dO, int ldo, float* dqkv,
                                       int lddq, float* dbias_partial, int groups, int B, int H, int W, int C, int heads,
-                                      int shift, void* stream) {
+                                      int shift, int precision, void* stream) {
   MPHSIR_REQUIRE(qkv && bias && dO && dqkv && dbias_partial, "window_attn_bwd: null operand");
   MPHSIR_REQUIRE(B > 0 && H % 8 == 0 && W % 8 == 0 && heads > 0 && C % heads == 0 && groups > 0, "window_attn_bwd: bad shape");
   MPHSIR_REQUIRE(shift == 0 || shift == 4, "window_attn_bwd: shift must be 0 or 4");
   MPHSIR_REQUIRE(ldqkv % 4 == 0 && ldo % 4 == 0 && ldqkv >= 3 * C && lddq >= 3 * C && ldo >= C, "window_attn_bwd: bad leading dimension");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (precision == MPHSIR_PREC_BF16X3 || precision == MPHSIR_PREC_BF16)
+    return wabm::launch_window_attn_bwd_mma(qkv, ldqkv, bias, dO, ldo, dqkv, lddq, dbias_partial, groups, B, H, W, C, heads, shift,
+                                            precision == MPHSIR_PREC_BF16X3 ? 2 : 1, st);
   const int hd = C / heads;
   switch (hd) {
     case 32: return wab::launch<32>(qkv, ldqkv, bias, dO, ldo, dqkv, lddq, dbias_partial, groups, B, H, W, C, heads, shift, st);

@@ -133,7 +133,7 @@ SIGNATURES = {
     "mphsir_axpby": (_I, [_VP, _I, _VP, _I, _LL, _I, _F, _F, _VP, _I, _I, _VP]),
     "mphsir_batch_sum": (_I, [_VP, _I, _VP, _I, _I, _LL, _I, _VP]),
     "mphsir_window_attn_bwd_groups": (_I, [_I, _I, _I, _I]),
-    "mphsir_window_attn_bwd": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
+    "mphsir_window_attn_bwd": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "mphsir_rpb_table_bwd": (_I, [_VP, _VP, _I, _VP]),
     "mphsir_window_reduce": (_I, [_VP, _I, _VP, _I, _VP, _I, _I, _I, _I, _I, _F, _VP]),
     "mphsir_local_gate_bwd_record_ld": (_I, [_I]),
@@ -605,12 +605,12 @@ def window_attn_bwd_groups(B: int, H: int, W: int, heads: int) -> int:
 
 
 def window_attn_bwd(qkv: View, bias: torch.Tensor, dO: View, dqkv: View, partial: torch.Tensor, groups: int, B: int,
-                    H: int, W: int, Cc: int, heads: int, shift: int) -> None:
+                    H: int, W: int, Cc: int, heads: int, shift: int, precision: int = 0) -> None:
     n = B * H * W
     _launch("window_attn_bwd",
             lambda: load().mphsir_window_attn_bwd(qkv.ptr, qkv.ld, bias.data_ptr(), dO.ptr, dO.ld, dqkv.ptr, dqkv.ld,
-                                                  partial.data_ptr(), groups, B, H, W, Cc, heads, shift, stream_ptr()),
-            lambda: (10.0 * n * 64 * Cc, 4.0 * 10 * n * Cc, "window_attn_bwd"))
+                                                  partial.data_ptr(), groups, B, H, W, Cc, heads, shift, precision, stream_ptr()),
+            lambda: (10.0 * n * 64 * Cc, 4.0 * 7 * n * Cc, ("window_attn_bwd", "window_attn_bwd_mma3", "window_attn_bwd_mma1")[precision]))
 
 
 def rpb_table_bwd(dbias: torch.Tensor, dtable: torch.Tensor, heads: int) -> None:

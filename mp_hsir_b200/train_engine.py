@@ -309,7 +309,7 @@ class TrainEngine(Engine):
         dqkv = ws.mat("b.dqkv", N, 3 * C)
         groups = lib.window_attn_bwd_groups(B, H, W, heads)
         partial = ws.flat("b.wabp", groups * heads * 4096)
-        lib.window_attn_bwd(S["qkv"], w["rpb"], dcore, dqkv, partial, groups, B, H, W, C, heads, shift)
+        lib.window_attn_bwd(S["qkv"], w["rpb"], dcore, dqkv, partial, groups, B, H, W, C, heads, shift, precision=self.prec)
         dbias = ws.flat("b.dbias", heads * 4096)[: heads * 4096]
         dbias.zero_()
         lib.colsum(View(partial.data_ptr(), heads * 4096, groups, heads * 4096, partial), dbias)

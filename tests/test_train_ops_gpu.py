@@ -158,9 +158,10 @@ def test_axpby_batch_sum():
     assert rel(out, x.view(B, rows, C).sum(0)) < 1e-6
 
 
+@pytest.mark.parametrize("prec,tol", [(lib.PREC_FP32_SIMT, 1e-5), (lib.PREC_BF16X3, 5e-5), (lib.PREC_BF16, 2e-2)])
 @pytest.mark.parametrize("C,heads,shift,H,W", [(64, 2, 0, 16, 16), (64, 2, 4, 16, 24), (128, 4, 4, 16, 16), (96, 2, 4, 16, 16),
                                                (192, 2, 4, 8, 16)])
-def test_window_attn_bwd(C, heads, shift, H, W):
+def test_window_attn_bwd(C, heads, shift, H, W, prec, tol):
     B = 2
     hd = C // heads
     qkv = rnd(B, H, W, 3 * C, seed=26, scale=0.7).requires_grad_(True)
@@ -184,13 +185,13 @@ def test_window_attn_bwd(C, heads, shift, H, W):
     dq = torch.empty(B * H * W, 3 * C, device=DEV)
     groups = lib.window_attn_bwd_groups(B, H, W, heads)
     partial = torch.empty(groups * heads * 4096, device=DEV)
-    lib.window_attn_bwd(V(qd), rpb, V(dev(dO.view(-1, C))), V(dq), partial, groups, B, H, W, C, heads, shift)
-    assert rel(dq, qkv.grad.view(-1, 3 * C)) < 1e-5
+    lib.window_attn_bwd(V(qd), rpb, V(dev(dO.view(-1, C))), V(dq), partial, groups, B, H, W, C, heads, shift, precision=prec)
+    assert rel(dq, qkv.grad.view(-1, 3 * C)) < tol
     dbias = torch.zeros(heads * 4096, device=DEV)
     lib.colsum(View(partial.data_ptr(), heads * 4096, groups, heads * 4096, partial), dbias)
     dtab = torch.zeros(225 * heads, device=DEV)
     lib.rpb_table_bwd(dbias, dtab, heads)
-    assert rel(dtab.view(225, heads), table.grad) < 1e-5
+    assert rel(dtab.view(225, heads), table.grad) < tol
 
 
 @pytest.mark.parametrize("C,r,shift", [(64, 8, 0), (128, 16, 4), (192, 12, 4)])
