@@ -333,6 +333,8 @@ typedef struct {
   int precision;
 } mphsir_wgrad_params;
 MPHSIR_API int mphsir_wgrad(const mphsir_wgrad_params* p, void* stream);
+/* Debug: force the weight-gradient engine: 0 = mma.sync (wgrad.cu), 1 = tcgen05 (wgrad_tc.cu), -1 = per-shape choice (default). */
+MPHSIR_API void mphsir_debug_wgrad_tc(int enabled);
 
 /* bias gradients: out[map(c)] += sum_m X[m,c] */
 MPHSIR_API int mphsir_colsum(const float* X, int ldx, float* out, long long M, int C, int map_mode, int map_a, int map_b,

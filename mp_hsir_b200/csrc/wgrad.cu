@@ -246,9 +246,15 @@ static int launch(const Args& a, int z, cudaStream_t st) {
 }
 
 }  // namespace wg
+namespace wgt {
+int launch_wgrad_tc(const mphsir_wgrad_params* p, int z, cudaStream_t st);
+}
+static int g_wgrad_tc = -1;  // -1: per-shape choice (default), 0: always mma.sync, 1: always tcgen05
 }  // namespace mphsir
 
 using namespace mphsir;
+
+extern "C" void mphsir_debug_wgrad_tc(int enabled) { g_wgrad_tc = enabled; }
 
 extern "C" int mphsir_wgrad(const mphsir_wgrad_params* p, void* stream) {
   MPHSIR_REQUIRE(p && p->dY && p->X && p->dW, "wgrad: null operand");
@@ -290,5 +296,12 @@ extern "C" int mphsir_wgrad(const mphsir_wgrad_params* p, void* stream) {
     z = (int)(p->M / p->rows_per_batch);
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // Engine choice (tools/wgrad_bench.py on B200): the tcgen05 kernel (128x128 tile, transposing converters off the MMA
+  // path, coalesced scatter-add epilogue) wins on the nine-tap conv gradients (2-3x) and whenever both channel counts
+  // fill its tile (C >= 128 stages: 1.2-1.5x); on narrow layers (64-wide level-1 blocks, the r-sized local-gate
+  // matrices) the mma.sync kernel (128x64 tile, no TMEM / barrier setup per CTA) is as fast or faster.
+  bool use_tc = g_wgrad_tc == 1;
+  if (g_wgrad_tc < 0) use_tc = p->taps == 9 || (p->O >= 128 && p->I >= 128 && p->rows_per_batch == 0);
+  if (use_tc && p->M < (1LL << 31)) return wgt::launch_wgrad_tc(p, z, st);
   return p->precision == MPHSIR_PREC_BF16X3 ? wg::launch<2>(a, z, st) : wg::launch<1>(a, z, st);
 }

@@ -124,6 +124,7 @@ SIGNATURES = {
     "mphsir_text_prompt_fwd": (_I, [_VP, _VP, _VP, _I, _I, _VP]),
     # ---- training path ----
     "mphsir_wgrad": (_I, [C.POINTER(WgradParams), _VP]),
+    "mphsir_debug_wgrad_tc": (None, [_I]),
     "mphsir_colsum": (_I, [_VP, _I, _VP, _LL, _I, _I, _I, _I, _VP]),
     "mphsir_layernorm_fwd": (_I, [_VP, _I, _VP, _VP, _VP, _I, _VP, _LL, _I, _VP]),
     "mphsir_layernorm_bwd": (_I, [_VP, _I, _VP, _VP, _VP, _I, _VP, _I, _VP, _I, _VP, _VP, _LL, _I, _VP]),

@@ -31,6 +31,14 @@ def rnd(*shape, seed=0, scale=1.0):
     return scale * torch.randn(*shape, generator=g)
 
 
+@pytest.fixture(params=[1, 0], ids=["wgrad_tcgen05", "wgrad_mma_sync"], autouse=True)
+def wgrad_engine(request):
+    """every test of this file runs with both weight-gradient kernels"""
+    lib.load().mphsir_debug_wgrad_tc(request.param)
+    yield request.param
+    lib.load().mphsir_debug_wgrad_tc(-1)
+
+
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("prec,tol", [(lib.PREC_BF16X3, 2e-5), (lib.PREC_BF16, 8e-3)])
 @pytest.mark.parametrize("M,O_,I", [(1000, 192, 64), (4096, 352, 128), (130, 8, 16), (777, 136, 24)])
