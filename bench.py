@@ -203,7 +203,9 @@ def cpu_train_baseline(model: str, sample_shape, steps: int = 1, warmup: int = 0
                       f"{sample_shape[0]} {list(sample_shape[1:])} patches fp32, {t:.2f} s per step, torch CPU {cores} threads"}, t
 
 
-def run_train(args):
+def run_train(args, embedded: bool = False):
+    """train64 workload.  embedded: called from the default (cube512) run, which owns the process group and prints the
+    line itself; then `args.workload` is still cube512 and the training precision is the training default (bf16)."""
     import torch.distributed as dist
     from mp_hsir_b200 import lib
     from mp_hsir_b200.parallel import max_over_ranks as _max
@@ -211,12 +213,13 @@ def run_train(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
+    if world > 1 and not embedded:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
-    model, shape, unit, units, sample_shape, _ = WORKLOADS[args.workload]
-    precision = args.precision
+    workload = "train64"
+    model, shape, unit, units, sample_shape, _ = WORKLOADS[workload]
+    precision = "bf16" if embedded else args.precision
     cfg, net = build_net(model, device)
     net.set_precision(precision)
     net.train()
@@ -281,12 +284,18 @@ def run_train(args):
         graph_ms = {k: round(v, 3) for k, v in (tr.graph_ms or {}).items()}
 
     roof, breakdown = None, None
-    if rank == 0 and not args.no_roofline:
-        pk = peaks()
-        lib.PROFILER = lib.Profiler()
+    agg = None
+    if not args.no_roofline:
+        # the instrumented step contains the gradient all-reduce: EVERY rank takes it (rank 0 with per-launch events)
+        if rank == 0:
+            lib.PROFILER = lib.Profiler()
         step(noisy_d, clean_d, tid_d)
-        agg = lib.PROFILER.summary()
-        lib.PROFILER = None
+        if rank == 0:
+            agg = lib.PROFILER.summary()
+            lib.PROFILER = None
+        barrier()
+    if agg is not None:
+        pk = peaks()
         total_ms = sum(a["ms"] for a in agg.values())
         breakdown = {k: {"ms_per_step": round(a["ms"], 3), "share": round(a["ms"] / total_ms, 4), "launches_per_step": a["launches"],
                          "tflops": round(a["flops"] / (a["ms"] * 1e-3) / 1e12, 2) if a["ms"] else 0,
@@ -314,7 +323,7 @@ def run_train(args):
         else:
             ach = a["bytes"] / sec / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None}
-        tr_ = ncu_traffic(args.workload, name) if precision == "bf16" else None
+        tr_ = ncu_traffic(workload, name) if precision == "bf16" else None
         if tr_ is not None:
             roof["traffic"] = tr_["bytes_per_launch"]
             roof["traffic_source"] = f"{tr_['source']}: ncu dram read+write bytes / launch over the {tr_['launches']} launches of one step"
@@ -325,21 +334,24 @@ def run_train(args):
                      "roofline_ms_per_step": {"hbm": 1e3 * t_hbm, "tensor": 1e3 * t_tensor},
                      "peak_source": pk["source"] + " (MEASURED_PEAKS.json; sustained bf16 figure: kernel timed inside a long step)",
                      "timing": "CUDA events around each launch on the launching stream, separate instrumented step"})
-    cb = None
-    if rank == 0 and not args.no_cpu_baseline:
-        cb, _ = cpu_train_baseline(model, sample_shape)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        if not embedded:
+            dist.destroy_process_group()
+    nparam, ws_total = tr.flat_p.numel(), tr.ws.bytes()
+    del tr, net
+    torch.cuda.empty_cache()
     if rank != 0:
-        return
+        return None
+    cb = None
+    if not args.no_cpu_baseline and not embedded:
+        cb, _ = cpu_train_baseline(model, sample_shape)
     total_units = units * world * args.steps
-    nparam = tr.flat_p.numel()
     line = {
-        "metric": METRIC[args.workload], "value": total_units / (ms_dev * 1e-3), "unit": unit, "n_gpus": world,
+        "metric": METRIC[workload], "value": total_units / (ms_dev * 1e-3), "unit": unit, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "bf16": "bf16"}[precision], "data": "synthetic",
-        "config": {"workload": args.workload, "model": model, "shape_per_gpu": list(shape), "global_batch": shape[0] * world,
+        "config": {"workload": workload, "model": model, "shape_per_gpu": list(shape), "global_batch": shape[0] * world,
                    "precision": precision,
                    "step": "forward + L1(clamp(out,0,1), clean) + hand-written backward + AdamW(lr 2e-4, wd 1e-2)"
                            + (" + NCCL all-reduce (sum, mean folded into AdamW) of the flat gradient buffer" if world > 1 else ""),
@@ -347,12 +359,15 @@ def run_train(args):
                    "weights": "random-init (name-seeded synthetic), reference architecture, output conv x0.05",
                    "parallelism": f"dp{world} (batch-sharded, {nparam * 4 / 1e6:.1f} MB gradient all-reduce)" if world > 1 else "dp1",
                    "l2": "per-step working set (saved activations, GBs) exceeds the 126 MB L2; no explicit flush",
-                   "cuda_graph": use_graph, "graph_ms": graph_ms, "losses_first_last": [losses[0], losses[-1]], "workspace_bytes": tr.ws.bytes()},
+                   "cuda_graph": use_graph, "graph_ms": graph_ms, "losses_first_last": [losses[0], losses[-1]], "workspace_bytes": ws_total},
         "e2e": {"value": total_units / (ms_e2e * 1e-3), "unit": unit, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": (noisy_h.numel() + clean_h.numel()) * 4 + tid_h.numel() * 8, "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cb, "kernels": breakdown,
     }
+    if embedded:
+        return line
     print(json.dumps(line))
+    return line
 
 
 def run_reference(args):
@@ -371,6 +386,11 @@ def run_reference(args):
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if args.workload == "cube512" and not args.no_train:
+        tm, ts, tu, tn, tss, _ = WORKLOADS["train64"]
+        tcb, tt = cpu_train_baseline(tm, tss, steps=1, warmup=0)
+        line["train"] = {"impl": "reference", "metric": METRIC["train64"], "value": tcb["value"], "unit": tu,
+                         "ms_per_step": 1e3 * tt / tss[0] * tn, "cpu_baseline": tcb}
     print(json.dumps(line))
 
 
@@ -383,6 +403,7 @@ def main():
     ap.add_argument("--workload", default="cube512", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="cube512 only: skip the embedded train64 measurement")
     ap.add_argument("--precision", default=None, choices=["fp32", "fp32_exact", "bf16"],
                     help="fp32 = tcgen05 with bf16 hi/lo split operands (meets the 1e-4 fp32 parity bound, default); "
                          "bf16 = bf16 operands (1e-2 bound); fp32_exact = FFMA")
@@ -543,14 +564,24 @@ def main():
                          "note": "fp32 mode issues 3 bf16 MMAs per product (hi*hi+hi*lo+lo*hi); bytes = fp32 operands "
                                  "read/written once (SURVEY 8d materialise-once model)"})
 
-    cb = None
-    if rank == 0 and not args.no_cpu_baseline:
-        cb, _ = cpu_baseline(model, sample_shape, frac, unit)
+    # BASELINE.json's metric has two halves: "HSI cubes/s (31x512x512 infer) & train patches/s".  The default run reports
+    # the second half as a sub-object of the same line (same contract fields, its own roofline / e2e / cpu_baseline).
+    train_line = None
+    if args.workload == "cube512" and not args.no_train:
+        ws_bytes = net.engine().ws.bytes()
+        del net, y
+        torch.cuda.empty_cache()
+        train_line = run_train(args, embedded=True)
+    else:
+        ws_bytes = net.engine().ws.bytes()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return
+    cb = None
+    if not args.no_cpu_baseline:
+        cb, _ = cpu_baseline(model, sample_shape, frac, unit)
     total_units = units * world * args.steps
     line = {
         "metric": METRIC[args.workload], "value": total_units / (ms_dev * 1e-3), "unit": unit, "n_gpus": world,
@@ -563,11 +594,17 @@ def main():
                    "l2": ("256 MB buffer written between timed steps (per-step CUDA events)" if flush else
                           "per-step working set (activations, GBs at 512x512) exceeds the 126 MB L2; no explicit flush"),
                    "cuda_graph": use_graph, "output_check": {"finite": finite, "mean_abs_change_over_mean_abs_input": rel_change},
-                   "workspace_bytes": net.engine().ws.bytes()},
+                   "workspace_bytes": ws_bytes},
         "e2e": {"value": total_units / (ms_e2e * 1e-3), "unit": unit, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": x_host.numel() * 4 + tid_host.numel() * 8, "d2h_bytes_per_step": out_host.numel() * 4},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cb, "kernels": breakdown,
     }
+    if train_line is not None:
+        train_line.pop("kernels", None)
+        if not args.no_cpu_baseline:
+            tm, _, _, _, tss, _ = WORKLOADS["train64"]
+            train_line["cpu_baseline"], _ = cpu_train_baseline(tm, tss)
+        line["train"] = train_line
     print(json.dumps(line))
 
 

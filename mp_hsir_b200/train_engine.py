@@ -697,6 +697,12 @@ class TrainEngine(Engine):
             if ent == "warm":
                 ent = graphs[key] = self._capture_step(inp, clean, task_id, keep, world_size)
             g_pack, g_main, g_opt, sx, sc, sw, dyn = ent[:7]
+            if self.packed is not ent[8]:
+                # an eager step (or anything else that invalidated the packed weights) ran since the last replay: refresh the
+                # graph's own weight images from the flat parameters and make them current again
+                g_pack.replay()
+                self.packed = self._train_packed_version = ent[8]
+                self._versions = self._param_versions()
             sx.copy_(inp, non_blocking=True)
             sc.copy_(clean, non_blocking=True)
             sw.copy_(self.task_weights(task_id), non_blocking=True)
@@ -747,7 +753,6 @@ class TrainEngine(Engine):
             self._pack_train()
         self._versions = self._param_versions()
         self._train_packed_version = self.packed
-        self._graph_packed = self.packed
         n_pack = lib.LAUNCHES - n0
         g_pack.replay()
         # 2. zero_grad + DropPath masks + forward + loss + backward
@@ -769,7 +774,7 @@ class TrainEngine(Engine):
                            self.weight_decay, 1, 1.0 / world_size, dyn=dyn)
         n_opt = lib.LAUNCHES - n2
         lib.LAUNCHES = n0  # capture records, it does not launch
-        return (g_pack, g_main, g_opt, sx, sc, sw, dyn, n_pack + n_main + n_opt)
+        return (g_pack, g_main, g_opt, sx, sc, sw, dyn, n_pack + n_main + n_opt, self.packed)
 
     def invalidate(self):
         # a captured step owns its packed weights and refreshes them itself (g_pack); anything else (load_state_dict,
