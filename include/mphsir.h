@@ -331,6 +331,8 @@ typedef struct {
   int map_mode, map_a, map_b;
   int i_valid;
   int precision;
+  float* dbias; /* optional: dbias[map(o)] += sum_m dY[m,o] (the bias gradient of the same layer, exact fp32 sums taken from the
+                   dY tiles on their way through registers); plain mode only */
 } mphsir_wgrad_params;
 MPHSIR_API int mphsir_wgrad(const mphsir_wgrad_params* p, void* stream);
 /* Debug: force the weight-gradient engine: 0 = mma.sync (wgrad.cu), 1 = tcgen05 (wgrad_tc.cu), -1 = per-shape choice (default). */

@@ -67,6 +67,7 @@ struct Args {
   int map_mode, map_a, map_b;
   int i_valid;
   int tiles_i;
+  float* dbias;
 };
 
 template <int PARTS>
@@ -133,7 +134,18 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(const Args p) {
         rb[r] = (b_col_ok && mc + tb + 16 * r < m_end) ? ldg4(bp + (long long)(16 * r) * p.ldx) : zero4;
     }
   };
+  const bool want_bias = p.dbias != nullptr && tile_i == 0 && blockIdx.z == 0;
+  float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
   auto store_chunk = [&]() {
+    if (want_bias) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        bsum.x += ra[r].x;
+        bsum.y += ra[r].y;
+        bsum.z += ra[r].z;
+        bsum.w += ra[r].w;
+      }
+    }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       uint2 hi, lo;
@@ -189,6 +201,21 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(const Args p) {
           mma_bf16(acc[2 * np + 1], al, bh[np][2], bh[np][3]);
         }
       }
+    }
+  }
+
+  // ---- bias gradient: column sums of this CTA's dY chunks (rows ta + 8r of every chunk, 4 columns per thread) ----
+  if (want_bias) {
+    __syncthreads();  // the last chunk's fragments have been read: the A tile area is free
+    float* red = reinterpret_cast<float*>(smem_raw);  // [8][128]
+    *reinterpret_cast<float4*>(red + ta * 128 + 4 * oq) = bsum;
+    __syncthreads();
+    if (tid < 128 && o0 + tid < p.O) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) sacc += red[r * 128 + tid];
+      const int ro = map_index(o0 + tid, p.map_mode, p.map_a, p.map_b);
+      if (ro >= 0) atomicAdd(p.dbias + ro, sacc);
     }
   }
 
@@ -286,6 +313,8 @@ extern "C" int mphsir_wgrad(const mphsir_wgrad_params* p, void* stream) {
   a.map_b = p->map_b;
   a.i_valid = p->i_valid > 0 ? p->i_valid : p->I;
   a.tiles_i = (p->I + wg::TI - 1) / wg::TI;
+  a.dbias = p->dbias;
+  MPHSIR_REQUIRE(p->dbias == nullptr || (p->taps == 0 && p->rows_per_batch == 0), "wgrad: dbias is available in plain mode only");
   int z = 1;
   if (p->taps == 9) {
     MPHSIR_REQUIRE(p->H > 0 && p->W > 0 && p->M % ((long long)p->H * p->W) == 0, "wgrad: conv mode needs H, W with M = B*H*W");

@@ -54,6 +54,7 @@ struct Args {
   int map_mode, map_a, map_b;
   int i_valid;
   int tiles_i;
+  float* dbias;
 };
 
 struct Bars {
@@ -194,17 +195,48 @@ __global__ void __launch_bounds__(kThreads, (PARTS == 1 ? 2 : 1)) wgrad_tc_kerne
       }
     };
 
+    const bool want_bias = p.dbias != nullptr && tile_i == 0 && blockIdx.z == 0;
+    float4 bsum = zero4;
     if (my_chunks > 0) load_chunk(blockIdx.y);
     for (int it = 0; it < my_chunks; ++it) {
       const int s = it & 1;
       mbar_wait(smem_u32(&bars->empty[s]), ((it >> 1) & 1) ^ 1);  // the MMAs that read this stage two chunks ago are done
       uint8_t* a_dst = img + s * STAGE_BYTES;
+      if (want_bias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          bsum.x += ra[j].x;
+          bsum.y += ra[j].y;
+          bsum.z += ra[j].z;
+          bsum.w += ra[j].w;
+        }
+      }
       store_unit(ra, a_dst);
       if (b_store) store_unit(rb, a_dst + PARTS * IMG_BYTES);
       fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars->full[s]));
       if (it + 1 < my_chunks) load_chunk(blockIdx.y + (it + 1) * gridDim.y);
+    }
+
+    // bias gradient: the 8 token groups of a channel quad sit in lanes l, l^4, l^8, ... of one warp
+    if (want_bias) {
+#pragma unroll
+      for (int sh = 4; sh < 32; sh <<= 1) {
+        bsum.x += __shfl_xor_sync(0xffffffffu, bsum.x, sh);
+        bsum.y += __shfl_xor_sync(0xffffffffu, bsum.y, sh);
+        bsum.z += __shfl_xor_sync(0xffffffffu, bsum.z, sh);
+        bsum.w += __shfl_xor_sync(0xffffffffu, bsum.w, sh);
+      }
+      if (tg == 0) {
+        const float bv[4] = {bsum.x, bsum.y, bsum.z, bsum.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int o = o0 + 4 * cq + e;
+          const int ro = o < p.O ? map_index(o, p.map_mode, p.map_a, p.map_b) : -1;
+          if (ro >= 0) atomicAdd(p.dbias + ro, bv[e]);
+        }
+      }
     }
 
     // =============================== epilogue (warps 1-4: TMEM lane quadrant = warp % 4) ===============
@@ -302,6 +334,7 @@ int launch_wgrad_tc(const mphsir_wgrad_params* p, int z, cudaStream_t st) {
   a.map_b = p->map_b;
   a.i_valid = p->i_valid > 0 ? p->i_valid : p->I;
   a.tiles_i = (p->I + TI - 1) / TI;
+  a.dbias = p->dbias;
   return p->precision == MPHSIR_PREC_BF16X3 ? launch<2>(a, z, st) : launch<1>(a, z, st);
 }
 

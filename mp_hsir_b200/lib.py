@@ -75,7 +75,7 @@ class WgradParams(C.Structure):
         ("H", C.c_int), ("W", C.c_int), ("taps", C.c_int),
         ("so", C.c_longlong), ("si", C.c_longlong), ("st", C.c_longlong),
         ("map_mode", C.c_int), ("map_a", C.c_int), ("map_b", C.c_int),
-        ("i_valid", C.c_int), ("precision", C.c_int),
+        ("i_valid", C.c_int), ("precision", C.c_int), ("dbias", C.c_void_p),
     ]
 
 
@@ -532,8 +532,9 @@ def text_prompt(weights: torch.Tensor, clip: torch.Tensor, clip_b: torch.Tensor,
 def wgrad(dY: View, X: View, dW: torch.Tensor, precision: int, *, M: Optional[int] = None, so: Optional[int] = None,
           si: int = 1, st: int = 0, map_mode: int = MAP_IDENTITY, map_a: Optional[int] = None, map_b: int = 0,
           i_valid: int = 0, rows_per_batch: int = 0, dw_batch_stride: int = 0, x_row_mod: int = 0, taps: int = 0,
-          H: int = 0, W: int = 0, dw_offset: int = 0) -> None:
-    """dW[map(o)*so + i*si + tap*st] += sum_m dY[m,o] * X[src(m), i]  (dW: flat fp32 gradient storage)."""
+          H: int = 0, W: int = 0, dw_offset: int = 0, dbias: Optional[torch.Tensor] = None) -> None:
+    """dW[map(o)*so + i*si + tap*st] += sum_m dY[m,o] * X[src(m), i]  (dW: flat fp32 gradient storage);
+    dbias[map(o)] += sum_m dY[m,o] when given (plain mode)."""
     p = WgradParams()
     p.dY, p.lddy, p.X, p.ldx = dY.ptr, dY.ld, X.ptr, X.ld
     p.dW = dW.data_ptr() + 4 * dw_offset
@@ -544,6 +545,7 @@ def wgrad(dY: View, X: View, dW: torch.Tensor, precision: int, *, M: Optional[in
     p.so, p.si, p.st = (iv * si if so is None else so), si, st
     p.map_mode, p.map_a, p.map_b = map_mode, (dY.cols if map_a is None else map_a), map_b
     p.i_valid, p.precision = iv, precision
+    p.dbias = ptr(dbias)
     m, o, i = p.M, p.O, p.I
     _launch("wgrad", lambda: load().mphsir_wgrad(C.byref(p), stream_ptr()),
             lambda: (2.0 * m * o * i * max(taps, 1), 4.0 * m * (o + i) * max(taps, 1), ("", "wgrad3", "wgrad1")[precision]))

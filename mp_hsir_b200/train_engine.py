@@ -254,10 +254,9 @@ class TrainEngine(Engine):
         dhid = ws.mat("b.dhid", N, hp)
         self._gemm(dm, w["fc2_w.d"], dhid, hp)
         lib.glu_bwd(h, dhid, hp)                      # h <- d(fc1 out), dhid <- hidden
-        self._wgrad(dm, dhid, pn + "mlp.fc2.weight", i_valid=hid)
-        lib.colsum(dm, g[pn + "mlp.fc2.bias"])
-        self._wgrad(h, y2, pn + "mlp.fc1.weight", map_mode=MAP_INTERLEAVE, map_a=hid)
-        lib.colsum(h, g[pn + "mlp.fc1.bias"], MAP_INTERLEAVE, hid)
+        # bias gradients ride on the weight-gradient launches (column sums of the dY tiles, exact fp32)
+        self._wgrad(dm, dhid, pn + "mlp.fc2.weight", i_valid=hid, dbias=g[pn + "mlp.fc2.bias"])
+        self._wgrad(h, y2, pn + "mlp.fc1.weight", map_mode=MAP_INTERLEAVE, map_a=hid, dbias=g[pn + "mlp.fc1.bias"])
         gln = ws.mat("b.gln", N, C)
         self._gemm(h, w["fc1_w.d"], gln, C)
         d_mid = ws.mat("b.dmid", N, C)
@@ -293,8 +292,7 @@ class TrainEngine(Engine):
         self._wgrad(rec.cols_slice(o_w, o_w + 128), rec.cols_slice(o_dsp, o_dsp + r), lp + "prompt_param")
         self._wgrad(rec.cols_slice(o_dq, o_dq + r), rec.cols_slice(o_sp, o_sp + r), lp + "q.weight")
         self._wgrad(rec.cols_slice(o_dkv, o_dkv + 2 * r), rec.cols_slice(o_low, o_low + r), lp + "kv.weight")
-        self._wgrad(rec.cols_slice(o_du, o_du + r), rec.cols_slice(o_o, o_o + r), lp + "proj.weight")
-        lib.colsum(rec.cols_slice(o_du, o_du + r), g[lp + "proj.bias"])
+        self._wgrad(rec.cols_slice(o_du, o_du + r), rec.cols_slice(o_o, o_o + r), lp + "proj.weight", dbias=g[lp + "proj.bias"])
         self._wgrad(dg_v, rec.cols_slice(o_u, o_u + r), lp + "linear_up.weight")
         dsa0 = ws.mat("b.dsa0", N, C)
         lib.gate_apply_bwd(du, S["gate"], dmean, dsa0, B, H, W, C, shift)
@@ -302,8 +300,7 @@ class TrainEngine(Engine):
         self._gemm(dt3, w["sqkv_w.d"], dsa, C, epi=lib.EPI_RESIDUAL, res1=dsa0)
         # ---- sa = proj(core) + b;  core = window attention(qkv);  qkv = LN1(x) Wqkv + b              (:195-216, :667)
         ap = pn + "attn."
-        self._wgrad(dsa, S["core"], ap + "proj.weight")
-        lib.colsum(dsa, g[ap + "proj.bias"])
+        self._wgrad(dsa, S["core"], ap + "proj.weight", dbias=g[ap + "proj.bias"])
         dcore = ws.mat("b.dcore", N, C)
         self._gemm(dsa, w["proj_w.d"], dcore, C)
         dqkv = ws.mat("b.dqkv", N, 3 * C)
@@ -314,8 +311,7 @@ class TrainEngine(Engine):
         dbias.zero_()
         lib.colsum(View(partial.data_ptr(), heads * 4096, groups, heads * 4096, partial), dbias)
         lib.rpb_table_bwd(dbias, g[ap + "relative_position_bias_table"], heads)
-        self._wgrad(dqkv, S["y1"], ap + "qkv.weight")
-        lib.colsum(dqkv, g[ap + "qkv.bias"])
+        self._wgrad(dqkv, S["y1"], ap + "qkv.weight", dbias=g[ap + "qkv.bias"])
         gln1 = ws.mat("b.gln", N, C)
         self._gemm(dqkv, w["qkv_w.d"], gln1, C)
         lib.layernorm_bwd(x, S["st1"], w["ln1"][0], gln1, d_mid, dx, g[pn + "norm1.weight"], g[pn + "norm1.bias"])

@@ -60,8 +60,9 @@ def test_struct_layouts_match_header():
 #include <stddef.h>
 #include "mphsir.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu ", sizeof(mphsir_wgrad_params), offsetof(mphsir_wgrad_params, dw_batch_stride),
-         offsetof(mphsir_wgrad_params, so), offsetof(mphsir_wgrad_params, precision), sizeof(mphsir_local_gate_bwd_weights));
+  printf("%zu %zu %zu %zu %zu %zu ", sizeof(mphsir_wgrad_params), offsetof(mphsir_wgrad_params, dw_batch_stride),
+         offsetof(mphsir_wgrad_params, so), offsetof(mphsir_wgrad_params, precision), offsetof(mphsir_wgrad_params, dbias),
+         sizeof(mphsir_local_gate_bwd_weights));
   printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(mphsir_gemm_params), offsetof(mphsir_gemm_params, row_scale),
          offsetof(mphsir_gemm_params, Bimg), offsetof(mphsir_gemm_params, bimg_batch_bytes),
          offsetof(mphsir_gemm_params, Y2), offsetof(mphsir_gemm_params, n_split),
@@ -77,7 +78,8 @@ int main(void) {
         got = [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     G, Cv, L = lib.GemmParams, lib.ConvParams, lib.LocalGateParams
     Wg = lib.WgradParams
-    want = [ctypes.sizeof(Wg), Wg.dw_batch_stride.offset, Wg.so.offset, Wg.precision.offset, ctypes.sizeof(lib.LocalGateBwdWeights)]
+    want = [ctypes.sizeof(Wg), Wg.dw_batch_stride.offset, Wg.so.offset, Wg.precision.offset, Wg.dbias.offset,
+            ctypes.sizeof(lib.LocalGateBwdWeights)]
     want += [ctypes.sizeof(G), G.row_scale.offset, G.Bimg.offset, G.bimg_batch_bytes.offset, G.Y2.offset,
             G.n_split.offset, ctypes.sizeof(Cv),
             Cv.Bimg.offset, ctypes.sizeof(L)]

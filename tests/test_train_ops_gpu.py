@@ -72,11 +72,20 @@ def test_wgrad_maps_and_padding():
     dW3 = torch.zeros(C * hid, device=DEV)
     lib.wgrad(V(dev(dYc)), V(dev(Hd)), dW3, lib.PREC_BF16X3, i_valid=hid)
     assert rel(dW3.view(C, hid), (dYc.double().t() @ Hd.double())[:, :hid]) < 2e-5
-    # bias gradient with the same maps
+    # bias gradient with the same maps: stand-alone column sums, and riding on the weight-gradient launch
     db = torch.zeros(2 * hid, device=DEV)
     lib.colsum(V(dev(dH)), db, lib.MAP_INTERLEAVE, hid)
     s = dH.double().sum(0)
     assert rel(db, torch.cat([s[0:2 * hid:2], s[1:2 * hid:2]])) < 1e-5
+    db2, dW4 = torch.zeros(2 * hid, device=DEV), torch.zeros(2 * hid * C, device=DEV)
+    lib.wgrad(V(dev(dH)), V(dev(X)), dW4, lib.PREC_BF16X3, map_mode=lib.MAP_INTERLEAVE, map_a=hid, dbias=db2)
+    assert rel(db2, torch.cat([s[0:2 * hid:2], s[1:2 * hid:2]])) < 1e-5 and rel(dW4.view(2 * hid, C), ref) < 2e-5
+    # wide layer (several 128-row tiles, two input-channel tiles): every column is summed exactly once
+    M2, O2, I2 = 3000, 384, 192
+    dY2, X2 = rnd(M2, O2, seed=60), rnd(M2, I2, seed=61)
+    db3, dW5 = torch.zeros(O2, device=DEV), torch.zeros(O2 * I2, device=DEV)
+    lib.wgrad(V(dev(dY2)), V(dev(X2)), dW5, lib.PREC_BF16X3, dbias=db3)
+    assert rel(db3, dY2.double().sum(0)) < 1e-5 and rel(dW5.view(O2, I2), dY2.double().t() @ X2.double()) < 2e-5
 
 
 def test_wgrad_batched_and_shared():
