@@ -163,6 +163,22 @@ class TrainEngine(Engine):
         nfl, nch = lib.gram_partial_floats(B, heads, c, HW)
         partial = ws.flat(tag + ".partial", nfl)
         lib.gram_partial(q, q_shared, k, k_shared, partial, B, HW, heads, c)
+        return self._spectral_finish_train(tag, partial, nch, temp, out_t, B, heads, c)
+
+    def _dwgram_fwd(self, tag: str, t3: View, w_dw, temp, out_t, B, H, W, C, heads):
+        """fused depthwise conv + Gram (forward kernel of the inference path): only v is written; q and k are recomputed by
+        one depthwise conv in the backward.  Returns (v, spectral state)."""
+        ws = self.ws
+        c = C // heads
+        v = ws.mat(tag + ".v", B * H * W, C)
+        nfl, nch = lib.dwgram_partial_floats(B, heads, c, H, W)
+        partial = ws.flat(tag + ".partial", nfl)
+        lib.dwgram(t3, w_dw, v, partial, B, H, W, C, heads, self.prec)
+        return v, self._spectral_finish_train(tag, partial, nch, temp, out_t, B, heads, c)
+
+    def _spectral_finish_train(self, tag: str, partial, nch: int, temp, out_t, B, heads, c):
+        ws = self.ws
+        C = heads * c
         gsum = ws.flat(tag + ".gsum", B * heads * (c * c + 2 * c))
         ldm = _ldb(C)
         Mt = ws.flat(tag + ".Mt", B * _ceil(C, 16) * ldm)[: B * _ceil(C, 16) * ldm].view(B, _ceil(C, 16), ldm)
@@ -218,12 +234,17 @@ class TrainEngine(Engine):
         self._gate_from_sa(w, st, sa, gate, B, H, W, shift, S["msa"], S["LL"])
         t3 = S["t3"] = ws.mat(pre + "t3", N, 3 * C)
         self._gemm(sa, w["sqkv_w"], t3, 3 * C)
-        dw3 = S["dw3"] = ws.mat(pre + "dw3", N, 3 * C)
-        lib.dwconv3x3(t3, w["sdw"], dw3, B, H, W, 3 * C)
-        S["spec"] = self._spectral_fwd(pre + "spec", dw3.cols_slice(0, C), False, dw3.cols_slice(C, 2 * C), False, w["temp"],
-                                       w["sout_t"], B, H * W, heads, C // heads)
+        if lib.dwgram_supported(C, C // heads):
+            S["dw3"] = None  # q, k recomputed in the backward
+            v, S["spec"] = self._dwgram_fwd(pre + "spec", t3, w["sdw"], w["temp"], w["sout_t"], B, H, W, C, heads)
+        else:
+            dw3 = S["dw3"] = ws.mat(pre + "dw3", N, 3 * C)
+            lib.dwconv3x3(t3, w["sdw"], dw3, B, H, W, 3 * C)
+            S["spec"] = self._spectral_fwd(pre + "spec", dw3.cols_slice(0, C), False, dw3.cols_slice(C, 2 * C), False, w["temp"],
+                                           w["sout_t"], B, H * W, heads, C // heads)
+            v = dw3.cols_slice(2 * C, 3 * C)
         mid = S["mid"] = ws.mat(pre + "mid", N, C)
-        self._gemm(dw3.cols_slice(2 * C, 3 * C), S["spec"]["w"], mid, C, epi=lib.EPI_SPECTRAL, res1=x, gsrc=sa, gate=gate,
+        self._gemm(v, S["spec"]["w"], mid, C, epi=lib.EPI_SPECTRAL, res1=x, gsrc=sa, gate=gate,
                    H=H, W=W, shift=shift, rows_per_batch=H * W, row_scale=s1)
         if lib.mlp_supported(C, w["hid_pad"]):
             lib.mlp(mid, w["ln2"], w["fc1_w"], w["fc1_b"], w["fc2_w"], w["fc2_b"], out, w["hid_pad"], self.prec,
@@ -264,6 +285,9 @@ class TrainEngine(Engine):
         # ---- mid = x + s1 * (sa * gate[win] + project_out(A v))                                     (:715-718)
         du = self._scaled("b.du", d_mid, S["s1"], HW)
         dw3, t3 = S["dw3"], S["t3"]
+        if dw3 is None:  # forward ran the fused dwconv+Gram kernel: q, k, v = dwconv3x3(t3) again
+            dw3 = ws.mat("b.dw3", N, 3 * C)
+            lib.dwconv3x3(t3, w["sdw"], dw3, B, H, W, 3 * C)
         ddw3 = ws.mat("b.ddw3", N, 3 * C)
         sp = pn + "gobal_spectral_attn."
         self._spectral_bwd("b.spec", S["spec"], du, dw3.cols_slice(0, 2 * C), dw3.cols_slice(2 * C, 3 * C), 0, w["sout"],
@@ -387,12 +411,17 @@ class TrainEngine(Engine):
         lib.layernorm_fwd(xcat, w["ln1"], y, S["st"])
         t3 = S["t3"] = ws.mat(name + ".t3", N, 3 * C2)
         self._gemm(y, w["qkv_w"], t3, 3 * C2)
-        dw3 = S["dw3"] = ws.mat(name + ".dw3", N, 3 * C2)
-        lib.dwconv3x3(t3, w["dw"], dw3, B, H, W, 3 * C2)
-        S["spec"] = self._spectral_fwd(name + ".spec", dw3.cols_slice(0, C2), False, dw3.cols_slice(C2, 2 * C2), False,
-                                       w["temp"], w["out_t"], B, H * W, heads, C2 // heads)
+        if lib.dwgram_supported(C2, C2 // heads):
+            S["dw3"] = None
+            v, S["spec"] = self._dwgram_fwd(name + ".spec", t3, w["dw"], w["temp"], w["out_t"], B, H, W, C2, heads)
+        else:
+            dw3 = S["dw3"] = ws.mat(name + ".dw3", N, 3 * C2)
+            lib.dwconv3x3(t3, w["dw"], dw3, B, H, W, 3 * C2)
+            S["spec"] = self._spectral_fwd(name + ".spec", dw3.cols_slice(0, C2), False, dw3.cols_slice(C2, 2 * C2), False,
+                                           w["temp"], w["out_t"], B, H * W, heads, C2 // heads)
+            v = dw3.cols_slice(2 * C2, 3 * C2)
         y1 = S["y1"] = ws.mat(name + ".y1", N, C2)
-        self._gemm(dw3.cols_slice(2 * C2, 3 * C2), S["spec"]["w"], y1, C2, epi=lib.EPI_RESIDUAL, res1=xcat, rows_per_batch=H * W)
+        self._gemm(v, S["spec"]["w"], y1, C2, epi=lib.EPI_RESIDUAL, res1=xcat, rows_per_batch=H * W)
         y2 = S["y2"] = ws.mat(name + ".y2", N, C2)
         S["ffn"] = self._gdfn_fwd(name + ".ffn", w, y1, y2, w["ln2"], B, H, W, C2)
         self._gemm(y2, w["conv_w"], out, out.cols)
@@ -409,6 +438,9 @@ class TrainEngine(Engine):
         dy1 = ws.mat("b.u.dy1", N, C2)
         self._gdfn_bwd(tb + "ffn.", tb + "norm2.body.", w, S["ffn"], w["ln2"], dy2, dy1, B, H, W, C2)
         dw3, t3 = S["dw3"], S["t3"]
+        if dw3 is None:
+            dw3 = ws.mat("b.u.dw3", N, 3 * C2)
+            lib.dwconv3x3(t3, w["dw"], dw3, B, H, W, 3 * C2)
         ddw3 = ws.mat("b.u.ddw3", N, 3 * C2)
         self._spectral_bwd("b.spec", S["spec"], dy1, dw3.cols_slice(0, 2 * C2), dw3.cols_slice(2 * C2, 3 * C2), 0, w["out"],
                            w["temp"], g[tb + "attn.project_out.weight"], g[tb + "attn.temperature"], B, HW, heads, C2 // heads,
