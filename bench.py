@@ -162,14 +162,32 @@ def cpu_baseline(model: str, sample_shape, frac: float, unit: str, steps: int = 
 
 
 def make_train_batch(shape, seed, T):
-    """clean patches + Gaussian degradation sigma ~ U(30,70)/255 per sample (utils/dataset_utils.py:112,293-298 of the
-    reference: the array-only recipe), task ids [B,1] like the training collate (utils/dataset_utils.py:140)."""
+    """clean patches + ONE random degradation per sample, drawn like ImageTransformDataset.__getitem__ of the reference
+    (utils/dataset_utils.py:128-146) from the array-only recipes of its de_dict (:112): Gaussian noise sigma ~ U(30,70)/255,
+    non-iid Gaussian noise with a per-band sigma from {10,30,50,70}/255, random pixel mask (ratio 0.7/0.8/0.9,
+    degradation_utils.py:227-233) and band loss (ratio 0.1/0.2/0.3).  The task id [B,1] is the degradation id, as in the
+    training collate (utils/dataset_utils.py:140)."""
     from mp_hsir_b200.synth import synthetic_input
     g = torch.Generator().manual_seed(1000 + seed)
+    B, C, H, W = shape
     clean = synthetic_input(shape, seed=seed)
-    sigma = (30.0 + 40.0 * torch.rand(shape[0], 1, 1, 1, generator=g)) / 255.0
-    noisy = clean + sigma * torch.randn(shape, generator=g)
-    tid = torch.randint(0, T, (shape[0], 1), generator=g)
+    noisy = clean.clone()
+    tid = torch.randint(0, min(T, 4), (B, 1), generator=g)
+    for b in range(B):
+        k = int(tid[b, 0])
+        if k == 0:      # gaussianN
+            sigma = (30.0 + 40.0 * torch.rand(1, generator=g)) / 255.0
+            noisy[b] += sigma * torch.randn(C, H, W, generator=g)
+        elif k == 1:    # non-iid noise (the array-only part of complexN)
+            sig = torch.tensor([10.0, 30.0, 50.0, 70.0])[torch.randint(0, 4, (C,), generator=g)] / 255.0
+            noisy[b] += sig.view(C, 1, 1) * torch.randn(C, H, W, generator=g)
+        elif k == 2:    # inpaint: random mask
+            ratio = (0.7, 0.8, 0.9)[int(torch.randint(0, 3, (1,), generator=g))]
+            noisy[b] *= (torch.rand(C, H, W, generator=g) > ratio).float()
+        else:           # bandmiss
+            ratio = (0.1, 0.2, 0.3)[int(torch.randint(0, 3, (1,), generator=g))]
+            lost = torch.randperm(C, generator=g)[: max(1, int(round(ratio * C)))]
+            noisy[b, lost] = 0.0
     return noisy.contiguous(), clean.contiguous(), tid
 
 
@@ -355,7 +373,8 @@ def run_train(args, embedded: bool = False):
                    "precision": precision,
                    "step": "forward + L1(clamp(out,0,1), clean) + hand-written backward + AdamW(lr 2e-4, wd 1e-2)"
                            + (" + NCCL all-reduce (sum, mean folded into AdamW) of the flat gradient buffer" if world > 1 else ""),
-                   "task_id": "randint(0,T,(B,1))", "degradation": "Gaussian sigma~U(30,70)/255 per sample",
+                   "task_id": "degradation id per sample, [B,1]",
+                   "degradation": "one per sample of {Gaussian sigma~U(30,70)/255, non-iid per-band sigma {10,30,50,70}/255, random mask 0.7-0.9, band loss 0.1-0.3}",
                    "weights": "random-init (name-seeded synthetic), reference architecture, output conv x0.05",
                    "parallelism": f"dp{world} (batch-sharded, {nparam * 4 / 1e6:.1f} MB gradient all-reduce)" if world > 1 else "dp1",
                    "l2": "per-step working set (saved activations, GBs) exceeds the 126 MB L2; no explicit flush",

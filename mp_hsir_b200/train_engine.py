@@ -25,8 +25,8 @@ import torch
 
 from . import lib
 from .config import PROMPT_LEN, SHIFT, Stage
-from .engine import Engine, _ceil, _ldb, pack_conv3x3, pack_dw, pack_linear_t
-from .lib import MAP_HALVES, MAP_IDENTITY, MAP_INTERLEAVE, View
+from .engine import Engine, _ceil, _ldb, pack_conv3x3
+from .lib import MAP_HALVES, MAP_INTERLEAVE, View
 
 DEAD_PARAMS = ("text_linear", "clip_linear")  # defined, never used by TVSP.forward (net/MP_HSIR.py:572-583)
 

@@ -1,6 +1,4 @@
 """GPU: every backward / training kernel of the C ABI against PyTorch-CPU autograd of the oracle's op."""
-import math
-
 import pytest
 import torch
 import torch.nn.functional as F

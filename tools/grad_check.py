@@ -1,7 +1,6 @@
 """Print per-parameter gradient errors of the CUDA backward vs the oracle's autograd (debug aid, GPU box)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch
 from tests.test_train_model_gpu import run_backward, grad_errors
 from tests.train_helpers import oracle_grads
 from tests.conftest import rel_err
