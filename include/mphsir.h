@@ -335,6 +335,9 @@ typedef struct {
                    dY tiles on their way through registers); plain mode only */
 } mphsir_wgrad_params;
 MPHSIR_API int mphsir_wgrad(const mphsir_wgrad_params* p, void* stream);
+/* Up to 8 small plain-mode problems (no taps / per-sample / shared X, one precision) in ONE launch of the mma.sync kernel:
+ * the seven r-sized weight gradients of the local spectral gate. */
+MPHSIR_API int mphsir_wgrad_multi(const mphsir_wgrad_params* list, int count, void* stream);
 /* Debug: force the weight-gradient engine: 0 = mma.sync (wgrad.cu), 1 = tcgen05 (wgrad_tc.cu), -1 = per-shape choice (default). */
 MPHSIR_API void mphsir_debug_wgrad_tc(int enabled);
 

@@ -70,28 +70,28 @@ struct Args {
   float* dbias;
 };
 
+// bx: dW tile, by / gy: token split index / count, bz: sample or conv tap
 template <int PARTS>
-__global__ void __launch_bounds__(256, 2) wgrad_kernel(const Args p) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+__device__ __forceinline__ void wgrad_body(const Args& p, const int bx, const int by, const int bz, const int gy, uint8_t* smem_raw) {
   __nv_bfloat16* As = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // [PARTS][KT][LDA]
   __nv_bfloat16* Bs = As + PARTS * KT * LDA;                       // [PARTS][KT][LDB]
   constexpr int A_ARR = KT * LDA, B_ARR = KT * LDB;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile_o = blockIdx.x / p.tiles_i, tile_i = blockIdx.x - tile_o * p.tiles_i;
+  const int tile_o = bx / p.tiles_i, tile_i = bx - tile_o * p.tiles_i;
   const int o0 = tile_o * TO, i0 = tile_i * TI;
 
   long long m_begin = 0, m_end = p.M;
   int tap = 0, dy = 0, dx = 0;
   float* dW = p.dW;
   if (p.taps == 9) {
-    tap = blockIdx.z;
+    tap = bz;
     dy = tap / 3 - 1;
     dx = tap - (tap / 3) * 3 - 1;
   } else if (p.rows_per_batch > 0) {
-    m_begin = (long long)blockIdx.z * p.rows_per_batch;
+    m_begin = (long long)bz * p.rows_per_batch;
     m_end = m_begin + p.rows_per_batch;
-    dW += (long long)blockIdx.z * p.dw_batch_stride;
+    dW += (long long)bz * p.dw_batch_stride;
   }
   const long long n_chunks = (m_end - m_begin + KT - 1) / KT;
 
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(const Args p) {
         rb[r] = (b_col_ok && mc + tb + 16 * r < m_end) ? ldg4(bp + (long long)(16 * r) * p.ldx) : zero4;
     }
   };
-  const bool want_bias = p.dbias != nullptr && tile_i == 0 && blockIdx.z == 0;
+  const bool want_bias = p.dbias != nullptr && tile_i == 0 && bz == 0;
   float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
   auto store_chunk = [&]() {
     if (want_bias) {
@@ -166,13 +166,13 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(const Args p) {
   const uint32_t b_base = (uint32_t)__cvta_generic_to_shared(Bs);
   const int m0 = warp * 16;
 
-  long long chunk = blockIdx.y;
+  long long chunk = by;
   if (chunk < n_chunks) load_chunk(chunk);
-  for (; chunk < n_chunks; chunk += gridDim.y) {
+  for (; chunk < n_chunks; chunk += gy) {
     __syncthreads();  // the previous chunk's fragments have been consumed
     store_chunk();
     __syncthreads();
-    if (chunk + gridDim.y < n_chunks) load_chunk(chunk + gridDim.y);
+    if (chunk + gy < n_chunks) load_chunk(chunk + gy);
 #pragma unroll
     for (int ks = 0; ks < KT / 16; ++ks) {
       // every fragment of this k-step first (ldmatrix latency overlaps), then 8 (24) independent MMAs
@@ -237,6 +237,27 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(const Args p) {
   }
 }
 
+template <int PARTS>
+__global__ void __launch_bounds__(256, 2) wgrad_kernel(const Args p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  wgrad_body<PARTS>(p, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.y, smem_raw);
+}
+
+// several small plain-mode problems in one launch (grid.z = problem): the r-sized matrices of the local spectral gate
+constexpr int MAX_MULTI = 8;
+struct ArgsList {
+  Args a[MAX_MULTI];
+  int tiles[MAX_MULTI], splits[MAX_MULTI];
+};
+
+template <int PARTS>
+__global__ void __launch_bounds__(256, 2) wgrad_multi_kernel(const ArgsList l) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int z = blockIdx.z;
+  if ((int)blockIdx.x >= l.tiles[z] || (int)blockIdx.y >= l.splits[z]) return;
+  wgrad_body<PARTS>(l.a[z], blockIdx.x, blockIdx.y, 0, l.splits[z], smem_raw);
+}
+
 static int sm_count() {
   static int sms = 0;
   if (sms == 0) {
@@ -283,14 +304,56 @@ using namespace mphsir;
 
 extern "C" void mphsir_debug_wgrad_tc(int enabled) { g_wgrad_tc = enabled; }
 
-extern "C" int mphsir_wgrad(const mphsir_wgrad_params* p, void* stream) {
+static int fill_args(const mphsir_wgrad_params* p, wg::Args& a);
+
+extern "C" int mphsir_wgrad_multi(const mphsir_wgrad_params* list, int count, void* stream) {
+  MPHSIR_REQUIRE(list && count > 0 && count <= wg::MAX_MULTI, "wgrad_multi: 1..%d problems", wg::MAX_MULTI);
+  wg::ArgsList l;
+  int max_tiles = 0, max_splits = 0;
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  for (int i = 0; i < count; ++i) {
+    MPHSIR_REQUIRE(list[i].taps == 0 && list[i].rows_per_batch == 0 && list[i].x_row_mod == 0, "wgrad_multi: plain-mode problems only");
+    MPHSIR_REQUIRE(list[i].precision == list[0].precision, "wgrad_multi: one precision per launch");
+    const int rc = fill_args(&list[i], l.a[i]);
+    if (rc != MPHSIR_OK) return rc;
+    l.tiles[i] = ((l.a[i].O + wg::TO - 1) / wg::TO) * l.a[i].tiles_i;
+    const long long n_chunks = (l.a[i].M + wg::KT - 1) / wg::KT;
+    long long splits = (2LL * sms) / ((long long)l.tiles[i] * count);
+    if (splits > (n_chunks + 3) / 4) splits = (n_chunks + 3) / 4;
+    if (splits < 1) splits = 1;
+    l.splits[i] = (int)splits;
+    max_tiles = l.tiles[i] > max_tiles ? l.tiles[i] : max_tiles;
+    max_splits = l.splits[i] > max_splits ? l.splits[i] : max_splits;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(max_tiles, max_splits, count);
+  if (list[0].precision == MPHSIR_PREC_BF16X3) {
+    const size_t smem = (size_t)2 * wg::KT * (wg::LDA + wg::LDB) * 2;
+    static bool configured = false;
+    if (!configured) {
+      if (cudaFuncSetAttribute(wg::wgrad_multi_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        set_error("wgrad_multi: cudaFuncSetAttribute failed");
+        return MPHSIR_ERR_CUDA;
+      }
+      configured = true;
+    }
+    wg::wgrad_multi_kernel<2><<<grid, 256, smem, st>>>(l);
+  } else {
+    const size_t smem = (size_t)wg::KT * (wg::LDA + wg::LDB) * 2;
+    wg::wgrad_multi_kernel<1><<<grid, 256, smem, st>>>(l);
+  }
+  return check_launch("wgrad_multi");
+}
+
+static int fill_args(const mphsir_wgrad_params* p, wg::Args& a) {
   MPHSIR_REQUIRE(p && p->dY && p->X && p->dW, "wgrad: null operand");
   MPHSIR_REQUIRE(p->M > 0 && p->O > 0 && p->I > 0 && p->O % 4 == 0 && p->I % 4 == 0, "wgrad: O and I must be positive multiples of 4");
   MPHSIR_REQUIRE(p->lddy % 4 == 0 && p->ldx % 4 == 0 && p->lddy >= p->O && p->ldx >= p->I, "wgrad: leading dimensions must be multiples of 4");
   MPHSIR_REQUIRE(((reinterpret_cast<uintptr_t>(p->dY) | reinterpret_cast<uintptr_t>(p->X)) & 15) == 0, "wgrad: operands must be 16-byte aligned");
   MPHSIR_REQUIRE(p->precision == MPHSIR_PREC_BF16X3 || p->precision == MPHSIR_PREC_BF16, "wgrad: precision must be a tensor-core mode");
   MPHSIR_REQUIRE(p->taps == 0 || p->taps == 9, "wgrad: taps must be 0 or 9");
-  wg::Args a;
   a.dY = p->dY;
   a.lddy = p->lddy;
   a.X = p->X;
@@ -315,6 +378,15 @@ extern "C" int mphsir_wgrad(const mphsir_wgrad_params* p, void* stream) {
   a.tiles_i = (p->I + wg::TI - 1) / wg::TI;
   a.dbias = p->dbias;
   MPHSIR_REQUIRE(p->dbias == nullptr || (p->taps == 0 && p->rows_per_batch == 0), "wgrad: dbias is available in plain mode only");
+  return MPHSIR_OK;
+}
+
+extern "C" int mphsir_wgrad(const mphsir_wgrad_params* p, void* stream) {
+  wg::Args a;
+  {
+    const int rc = fill_args(p, a);
+    if (rc != MPHSIR_OK) return rc;
+  }
   int z = 1;
   if (p->taps == 9) {
     MPHSIR_REQUIRE(p->H > 0 && p->W > 0 && p->M % ((long long)p->H * p->W) == 0, "wgrad: conv mode needs H, W with M = B*H*W");

@@ -190,6 +190,19 @@ class Engine:
             """fp32 "in x out" matrix -> Weight (adds the tensor-core image when that engine is selected)."""
             return lib.Weight(bt, lib.pack_bimg(bt, n, k, transposed=True) if tc else None, n, k)
 
+        def L(param: torch.Tensor, n: int, k: int, k_gemm: Optional[int] = None) -> lib.Weight:
+            """plain nn.Linear / 1x1-conv weight [out=n, in=k].  Inference: "in x out" fp32 matrix + image.  Trainer (weights
+            change every step): the image is packed straight from the parameter — no intermediate tensors, one launch —
+            and the `src` field lets the data-gradient image be packed from the same storage transposed."""
+            w2 = f32(param).reshape(n, k)
+            if self.fold_weights or not tc:
+                return W(pack_linear_t(w2, k_pad=k_gemm), n, k if k_gemm is None else k_gemm)
+            kg = k if k_gemm is None else k_gemm
+            assert (k + 63) // 64 == (kg + 63) // 64, "padded K must stay inside the last 64-wide k-slab"
+            wobj = lib.Weight(None, lib.pack_bimg(w2, n, k, transposed=False), n, kg)
+            wobj.src = w2
+            return wobj
+
         cin_p = _ceil(cfg.in_channel, 16)
         P["cin_p"] = cin_p
         P["patch_embed"] = W(pack_conv3x3(f32(net.patch_embed.proj.weight), cin_pad=cin_p), cfg.dim, 9 * cin_p)
@@ -197,7 +210,7 @@ class Engine:
         P["down2_3"] = W(pack_conv3x3(f32(net.down2_3.body[0].weight)), cfg.dim, 18 * cfg.dim)
         P["up3_2"] = W(pack_conv3x3(f32(net.up3_2.body[0].weight), shuffle=True), 8 * cfg.dim, 36 * cfg.dim)
         P["up2_1"] = W(pack_conv3x3(f32(net.up2_1.body[0].weight), shuffle=True), 4 * cfg.dim, 18 * cfg.dim)
-        P["reduce_chan_level2"] = W(pack_linear_t(f32(net.reduce_chan_level2.weight)), 2 * cfg.dim, 4 * cfg.dim)
+        P["reduce_chan_level2"] = L(net.reduce_chan_level2.weight, 2 * cfg.dim, 4 * cfg.dim)
         P["output"] = W(pack_conv3x3(f32(net.output.weight)), cfg.out_channel, 18 * cfg.dim)
         if getattr(self, "_clip_dev", None) is None:  # a constant, moved once (the module keeps it on the host)
             self._clip_dev = f32(net.text_prompt.clip_prompt).contiguous()
@@ -212,14 +225,14 @@ class Engine:
                 d["ln1"] = (f32(blk.norm1.weight).contiguous(), f32(blk.norm1.bias).contiguous())
                 d["ln2"] = (f32(blk.norm2.weight).contiguous(), f32(blk.norm2.bias).contiguous())
                 a = blk.attn
-                d["qkv_w"] = W(pack_linear_t(f32(a.qkv.weight)), 3 * st.dim, st.dim)
+                d["qkv_w"] = L(a.qkv.weight, 3 * st.dim, st.dim)
                 d["qkv_b"] = f32(a.qkv.bias).contiguous()
-                d["proj_w"] = W(pack_linear_t(f32(a.proj.weight)), st.dim, st.dim)
+                d["proj_w"] = L(a.proj.weight, st.dim, st.dim)
                 d["proj_b"] = f32(a.proj.bias).contiguous()
                 d["rpb"] = rel_pos_bias(f32(a.relative_position_bias_table), a.relative_position_index.to(self.device))
                 g = blk.gobal_spectral_attn
                 d["temp"] = f32(g.temperature).reshape(-1).contiguous()
-                d["sqkv_w"] = W(pack_linear_t(f32(g.qkv.weight)), 3 * st.dim, st.dim)
+                d["sqkv_w"] = L(g.qkv.weight, 3 * st.dim, st.dim)
                 d["sdw"] = pack_dw(f32(g.qkv_dwconv.weight))
                 d["sout_t"] = f32(g.project_out.weight).reshape(st.dim, st.dim).t().contiguous()
                 l = blk.local_spectral_attn
@@ -244,7 +257,7 @@ class Engine:
                     d["ll_w"] = W(pack_linear_t(cat), nlp, st.dim)
                     fc1_w, d["fc1_b"] = pack_glu_fc1(f32(blk.mlp.fc1.weight), f32(blk.mlp.fc1.bias), hid, hid_pad)
                     d["fc1_w"] = W(fc1_w, 2 * hid_pad, st.dim)
-                    d["fc2_w"] = W(pack_linear_t(f32(blk.mlp.fc2.weight), k_pad=hid_pad), st.dim, hid_pad)
+                    d["fc2_w"] = L(blk.mlp.fc2.weight, st.dim, hid, k_gemm=hid_pad)
                     d["fc2_b"] = f32(blk.mlp.fc2.bias).contiguous()
                     blocks.append(d)
                     continue
@@ -286,9 +299,9 @@ class Engine:
             d["learnable"] = f32(m.text_prompt_learnable).reshape(cfg.task_classes, D).contiguous()
             d["visual"] = f32(m.visual_prompt)[0].permute(1, 2, 0).reshape(ps * ps, D).contiguous()
             d["ln11"], d["ln12"], d["ln2"] = ln(ct.norm11), ln(ct.norm12), ln(ct.norm2)
-            d["q_w"] = W(pack_linear_t(f32(ct.attn.q.weight)), D, D)
+            d["q_w"] = L(ct.attn.q.weight, D, D)
             d["q_dw"] = pack_dw(f32(ct.attn.q_dwconv.weight))
-            d["kv_w"] = W(pack_linear_t(f32(ct.attn.kv.weight)), 2 * D, D)
+            d["kv_w"] = L(ct.attn.kv.weight, 2 * D, D)
             d["kv_dw"] = pack_dw(f32(ct.attn.kv_dwconv.weight))
             d["temp"] = f32(ct.attn.temperature).reshape(-1).contiguous()
             d["out_t"] = f32(ct.attn.project_out.weight).reshape(D, D).t().contiguous()
@@ -306,14 +319,14 @@ class Engine:
             hid_pad = _ceil(hid, 16)
             d = {"C": C2, "heads": m.heads, "hid_pad": hid_pad}
             d["ln1"], d["ln2"] = ln(tb.norm1), ln(tb.norm2)
-            d["qkv_w"] = W(pack_linear_t(f32(tb.attn.qkv.weight)), 3 * C2, C2)
+            d["qkv_w"] = L(tb.attn.qkv.weight, 3 * C2, C2)
             d["dw"] = pack_dw(f32(tb.attn.qkv_dwconv.weight))
             d["temp"] = f32(tb.attn.temperature).reshape(-1).contiguous()
             d["out_t"] = f32(tb.attn.project_out.weight).reshape(C2, C2).t().contiguous()
             pin_w, d["ffn_dw"], pout_w = pack_gdfn(
                 f32(tb.ffn.project_in.weight), f32(tb.ffn.dwconv.weight), f32(tb.ffn.project_out.weight), hid, hid_pad)
             d["pin_w"], d["pout_w"] = W(pin_w, 2 * hid_pad, C2), W(pout_w, C2, hid_pad)
-            d["conv_w"] = W(pack_linear_t(f32(m.conv.weight)), C2 // 2, C2)
+            d["conv_w"] = L(m.conv.weight, C2 // 2, C2)
             P[name] = d
         return P
 

@@ -125,6 +125,7 @@ SIGNATURES = {
     # ---- training path ----
     "mphsir_wgrad": (_I, [C.POINTER(WgradParams), _VP]),
     "mphsir_debug_wgrad_tc": (None, [_I]),
+    "mphsir_wgrad_multi": (_I, [C.POINTER(WgradParams), _I, _VP]),
     "mphsir_colsum": (_I, [_VP, _I, _VP, _LL, _I, _I, _I, _I, _VP]),
     "mphsir_layernorm_fwd": (_I, [_VP, _I, _VP, _VP, _VP, _I, _VP, _LL, _I, _VP]),
     "mphsir_layernorm_bwd": (_I, [_VP, _I, _VP, _VP, _VP, _I, _VP, _I, _VP, _I, _VP, _VP, _LL, _I, _VP]),
@@ -278,10 +279,11 @@ class Weight:
     bf16 hi/lo tensor-core image of the logical [N, K] matrix (tcgen05 engine).  Either may be None.
     3-D `bt` / batched `img` ([B, bytes]) hold per-sample matrices."""
 
-    __slots__ = ("bt", "img", "n", "k")
+    __slots__ = ("bt", "img", "n", "k", "src")
 
     def __init__(self, bt: Optional[torch.Tensor], img: Optional[torch.Tensor], n: int, k: int):
         self.bt, self.img, self.n, self.k = bt, img, n, k
+        self.src = None  # trainer: the [n, k_valid] parameter view the image was packed from (engine.py: L())
 
 
 def bimg_bytes(n: int, k: int) -> int:
@@ -529,12 +531,10 @@ def text_prompt(weights: torch.Tensor, clip: torch.Tensor, clip_b: torch.Tensor,
 # ------------------------------------------------------------------------------------------
 
 
-def wgrad(dY: View, X: View, dW: torch.Tensor, precision: int, *, M: Optional[int] = None, so: Optional[int] = None,
-          si: int = 1, st: int = 0, map_mode: int = MAP_IDENTITY, map_a: Optional[int] = None, map_b: int = 0,
-          i_valid: int = 0, rows_per_batch: int = 0, dw_batch_stride: int = 0, x_row_mod: int = 0, taps: int = 0,
-          H: int = 0, W: int = 0, dw_offset: int = 0, dbias: Optional[torch.Tensor] = None) -> None:
-    """dW[map(o)*so + i*si + tap*st] += sum_m dY[m,o] * X[src(m), i]  (dW: flat fp32 gradient storage);
-    dbias[map(o)] += sum_m dY[m,o] when given (plain mode)."""
+def _wgrad_params(dY: View, X: View, dW: torch.Tensor, precision: int, *, M: Optional[int] = None, so: Optional[int] = None,
+                  si: int = 1, st: int = 0, map_mode: int = MAP_IDENTITY, map_a: Optional[int] = None, map_b: int = 0,
+                  i_valid: int = 0, rows_per_batch: int = 0, dw_batch_stride: int = 0, x_row_mod: int = 0, taps: int = 0,
+                  H: int = 0, W: int = 0, dw_offset: int = 0, dbias: Optional[torch.Tensor] = None) -> WgradParams:
     p = WgradParams()
     p.dY, p.lddy, p.X, p.ldx = dY.ptr, dY.ld, X.ptr, X.ld
     p.dW = dW.data_ptr() + 4 * dw_offset
@@ -546,9 +546,28 @@ def wgrad(dY: View, X: View, dW: torch.Tensor, precision: int, *, M: Optional[in
     p.map_mode, p.map_a, p.map_b = map_mode, (dY.cols if map_a is None else map_a), map_b
     p.i_valid, p.precision = iv, precision
     p.dbias = ptr(dbias)
-    m, o, i = p.M, p.O, p.I
+    return p
+
+
+def wgrad(dY: View, X: View, dW: torch.Tensor, precision: int, **kw) -> None:
+    """dW[map(o)*so + i*si + tap*st] += sum_m dY[m,o] * X[src(m), i]  (dW: flat fp32 gradient storage);
+    dbias[map(o)] += sum_m dY[m,o] when given (plain mode).  Keywords: see _wgrad_params."""
+    p = _wgrad_params(dY, X, dW, precision, **kw)
+    m, o, i, taps = p.M, p.O, p.I, p.taps
     _launch("wgrad", lambda: load().mphsir_wgrad(C.byref(p), stream_ptr()),
             lambda: (2.0 * m * o * i * max(taps, 1), 4.0 * m * (o + i) * max(taps, 1), ("", "wgrad3", "wgrad1")[precision]))
+
+
+def wgrad_multi(problems, precision: int) -> None:
+    """several small plain-mode weight gradients in one launch; problems: [(dY, X, dW, kwargs), ...] (at most 8)."""
+    arr = (WgradParams * len(problems))()
+    fl = by = 0.0
+    for j, (dY, X, dW, kw) in enumerate(problems):
+        arr[j] = _wgrad_params(dY, X, dW, precision, **kw)
+        fl += 2.0 * arr[j].M * arr[j].O * arr[j].I
+        by += 4.0 * arr[j].M * (arr[j].O + arr[j].I)
+    _launch("wgrad_multi", lambda: load().mphsir_wgrad_multi(arr, len(problems), stream_ptr()),
+            lambda: (fl, by, ("", "wgrad_multi3", "wgrad_multi1")[precision]))
 
 
 def colsum(X: View, out: torch.Tensor, map_mode: int = MAP_IDENTITY, map_a: Optional[int] = None, map_b: int = 0,

@@ -82,6 +82,12 @@ class TrainEngine(Engine):
     def _dgrad_of(self, w: lib.Weight) -> lib.Weight:
         """data-gradient weight of a forward GEMM weight: dX[M,K_f] = dY[M,N_f] @ W  (packed column order kept)."""
         n_f, k_f = w.n, w.k
+        if w.src is not None:
+            # packed straight from the parameter [n_f, k_valid]: the data-gradient image is the same storage read transposed
+            # (logical [N = k_valid, K = n_f]); the GEMM's N = k_f may be the 16-padded k_valid, which the image rows cover
+            kv = w.src.shape[1]
+            assert _ceil(kv, 16) == _ceil(k_f, 16)
+            return lib.Weight(None, lib.pack_bimg(w.src, kv, n_f, transposed=True), k_f, n_f)
         out = w.bt.new_zeros(_ceil(n_f, 16), _ldb(k_f))
         out[:n_f, :k_f] = w.bt[:k_f, :n_f].t()
         return self._W(out.contiguous(), k_f, n_f)
@@ -311,13 +317,17 @@ class TrainEngine(Engine):
         lp = pn + "local_spectral_attn."
         o_w, o_dsp, o_dq, o_sp, o_dkv, o_low, o_du, o_o, o_u = (128 + r, 256 + r, 256 + 2 * r, 256 + 3 * r, 256 + 4 * r,
                                                                  256 + 6 * r, 256 + 7 * r, 256 + 8 * r, 256 + 9 * r)
-        self._wgrad(rec.cols_slice(0, 128), msa_v, lp + "linear_prompt.weight")
-        self._wgrad(rec.cols_slice(128, 128 + r), msa_v, lp + "linear_down.weight")
-        self._wgrad(rec.cols_slice(o_w, o_w + 128), rec.cols_slice(o_dsp, o_dsp + r), lp + "prompt_param")
-        self._wgrad(rec.cols_slice(o_dq, o_dq + r), rec.cols_slice(o_sp, o_sp + r), lp + "q.weight")
-        self._wgrad(rec.cols_slice(o_dkv, o_dkv + 2 * r), rec.cols_slice(o_low, o_low + r), lp + "kv.weight")
-        self._wgrad(rec.cols_slice(o_du, o_du + r), rec.cols_slice(o_o, o_o + r), lp + "proj.weight", dbias=g[lp + "proj.bias"])
-        self._wgrad(dg_v, rec.cols_slice(o_u, o_u + r), lp + "linear_up.weight")
+        # the seven r-sized weight gradients (+ proj.bias) are token-contractions of record columns: one launch
+        R = rec.cols_slice
+        lib.wgrad_multi([
+            (R(0, 128), msa_v, g[lp + "linear_prompt.weight"], {}),
+            (R(128, 128 + r), msa_v, g[lp + "linear_down.weight"], {}),
+            (R(o_w, o_w + 128), R(o_dsp, o_dsp + r), g[lp + "prompt_param"], {}),
+            (R(o_dq, o_dq + r), R(o_sp, o_sp + r), g[lp + "q.weight"], {}),
+            (R(o_dkv, o_dkv + 2 * r), R(o_low, o_low + r), g[lp + "kv.weight"], {}),
+            (R(o_du, o_du + r), R(o_o, o_o + r), g[lp + "proj.weight"], {"dbias": g[lp + "proj.bias"]}),
+            (dg_v, R(o_u, o_u + r), g[lp + "linear_up.weight"], {}),
+        ], self.prec)
         dsa0 = ws.mat("b.dsa0", N, C)
         lib.gate_apply_bwd(du, S["gate"], dmean, dsa0, B, H, W, C, shift)
         dsa = ws.mat("b.dsa", N, C)

@@ -86,6 +86,26 @@ def test_wgrad_maps_and_padding():
     assert rel(db3, dY2.double().sum(0)) < 1e-5 and rel(dW5.view(O2, I2), dY2.double().t() @ X2.double()) < 2e-5
 
 
+def test_wgrad_multi_problem_launch():
+    M = 700
+    shapes = [(128, 64), (8, 64), (128, 8), (8, 8), (16, 8), (64, 8), (136, 24)]
+    probs, refs, outs = [], [], []
+    db = torch.zeros(8, device=DEV)
+    for j, (O_, I) in enumerate(shapes):
+        dY, X = rnd(M, O_, seed=70 + j), rnd(M, I, seed=90 + j)
+        out = torch.zeros(O_ * I, device=DEV)
+        kw = {"dbias": db} if j == 3 else {}
+        probs.append((V(dev(dY)), V(dev(X)), out, kw))
+        refs.append(dY.double().t() @ X.double())
+        outs.append(out)
+        if j == 3:
+            bias_ref = dY.double().sum(0)
+    lib.wgrad_multi(probs, lib.PREC_BF16X3)
+    for (O_, I), out, ref in zip(shapes, outs, refs):
+        assert rel(out.view(O_, I), ref) < 2e-5, (O_, I)
+    assert rel(db, bias_ref) < 1e-5
+
+
 def test_wgrad_batched_and_shared():
     B, HW, C = 3, 320, 64
     dU, v = rnd(B * HW, C, seed=7), rnd(B * HW, C, seed=8)
