@@ -128,6 +128,15 @@ MPHSIR_API size_t mphsir_bimg_bytes(int N, int K);
 MPHSIR_API int mphsir_pack_bimg(const float* W, int ld, int transposed, long long w_batch_stride, void* img,
                                 int batch, int N, int K, void* stream);
 
+/* The same for many (un-batched) matrices in one launch per 64 items: the trainer re-packs every weight after each
+ * optimizer step. */
+typedef struct {
+  const float* W;
+  void* img;
+  int ld, transposed, N, K;
+} mphsir_pack_item;
+MPHSIR_API int mphsir_pack_bimg_multi(const mphsir_pack_item* items, int count, void* stream);
+
 MPHSIR_API int mphsir_gemm_fwd(const mphsir_gemm_params* p, void* stream);
 
 /* ---------------------------------------------------------------------------------------

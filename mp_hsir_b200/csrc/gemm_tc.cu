@@ -1109,6 +1109,72 @@ extern "C" size_t mphsir_bimg_bytes(int N, int K) {
   return (size_t)2 * Ks * Np * 128;
 }
 
+// many weight images in one launch (blockIdx.y = item): the trainer re-packs ~300 matrices after every optimizer step
+namespace mphsir {
+namespace tc {
+constexpr int PACK_MULTI_MAX = 64;
+struct PackItem {
+  const float* W;
+  uint16_t* img;
+  int ld, transposed, N, K;
+};
+struct PackList {
+  PackItem it[PACK_MULTI_MAX];
+};
+__global__ void __launch_bounds__(256) pack_bimg_multi_kernel(const PackList l) {
+  const PackItem& q = l.it[blockIdx.y];
+  const int Np = (q.N + 15) / 16 * 16, Ks = (q.K + 63) / 64;
+  const long long total = (long long)Ks * Np * 8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx & 7);
+    const long long rn = idx >> 3;
+    const int n = (int)(rn % Np);
+    const int s = (int)(rn / Np);
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = s * 64 + c * 8 + 2 * e + h;
+        v[h] = (n < q.N && k < q.K) ? __ldg(q.W + (q.transposed ? (long long)k * q.ld + n : (long long)n * q.ld + k)) : 0.f;
+      }
+      split2(v[0], v[1], hi[e], lo[e]);
+    }
+    uint8_t* out = reinterpret_cast<uint8_t*>(q.img);
+    *reinterpret_cast<uint4*>(out + bimg_offset(0, s, n, c, Np, Ks)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(out + bimg_offset(1, s, n, c, Np, Ks)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+}  // namespace tc
+}  // namespace mphsir
+
+extern "C" int mphsir_pack_bimg_multi(const mphsir_pack_item* items, int count, void* stream) {
+  MPHSIR_REQUIRE(items && count > 0, "pack_bimg_multi: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int i0 = 0; i0 < count; i0 += tc::PACK_MULTI_MAX) {
+    const int n = count - i0 < tc::PACK_MULTI_MAX ? count - i0 : tc::PACK_MULTI_MAX;
+    tc::PackList l;
+    long long max_total = 0;
+    for (int j = 0; j < n; ++j) {
+      const mphsir_pack_item& q = items[i0 + j];
+      MPHSIR_REQUIRE(q.W && q.img && q.N > 0 && q.K > 0 && q.ld > 0, "pack_bimg_multi: bad item %d", i0 + j);
+      MPHSIR_REQUIRE((reinterpret_cast<uintptr_t>(q.img) & 127) == 0, "pack_bimg_multi: image %d must be 128-byte aligned", i0 + j);
+      l.it[j] = tc::PackItem{q.W, reinterpret_cast<uint16_t*>(q.img), q.ld, q.transposed, q.N, q.K};
+      const long long total = (long long)((q.K + 63) / 64) * ((q.N + 15) / 16 * 16) * 8;
+      max_total = total > max_total ? total : max_total;
+    }
+    long long gx = (max_total + 255) / 256;
+    if (gx > 48) gx = 48;  // 64 items x 48 CTAs: a few waves; the grid-stride loop covers the larger matrices
+    dim3 grid((unsigned)gx, (unsigned)n);
+    tc::pack_bimg_multi_kernel<<<grid, 256, 0, st>>>(l);
+    const int rc = check_launch("pack_bimg_multi");
+    if (rc != MPHSIR_OK) return rc;
+  }
+  return MPHSIR_OK;
+}
+
 extern "C" int mphsir_pack_bimg(const float* W, int ld, int transposed, long long w_batch_stride, void* img,
                                 int batch, int N, int K, void* stream) {
   MPHSIR_REQUIRE(W && img && batch > 0 && N > 0 && K > 0 && ld > 0, "pack_bimg: bad arguments");

@@ -79,6 +79,10 @@ class WgradParams(C.Structure):
     ]
 
 
+class PackItem(C.Structure):
+    _fields_ = [("W", C.c_void_p), ("img", C.c_void_p), ("ld", C.c_int), ("transposed", C.c_int), ("N", C.c_int), ("K", C.c_int)]
+
+
 class LocalGateBwdWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("param", "q", "kv", "proj", "proj_bias", "up")]
 
@@ -103,6 +107,7 @@ SIGNATURES = {
     "mphsir_debug_tc_tma_epilogue": (None, [_I]),
     "mphsir_bimg_bytes": (C.c_size_t, [_I, _I]),
     "mphsir_pack_bimg": (_I, [_VP, _I, _I, _LL, _VP, _I, _I, _I, _VP]),
+    "mphsir_pack_bimg_multi": (_I, [C.POINTER(PackItem), _I, _VP]),
     "mphsir_gemm_fwd": (_I, [C.POINTER(GemmParams), _VP]),
     "mphsir_mlp_supported": (_I, [_I, _I]),
     "mphsir_mlp_fwd": (_I, [C.POINTER(MlpParams), _VP]),
@@ -300,11 +305,33 @@ def pack_bimg(w: torch.Tensor, n: int, k: int, transposed: bool = False, img: Op
     if img is None:
         img = torch.empty(batch, nbytes, device=w.device, dtype=torch.uint8)
     assert img.numel() >= batch * nbytes and img.data_ptr() % 128 == 0
+    if PACK_QUEUE is not None and batch == 1:
+        # deferred: flush_packs() issues one launch per 64 matrices (sources and images are kept alive by the queue)
+        PACK_QUEUE.append((w3, img, w3.stride(1), int(transposed), n, k))
+        return img
     _launch("pack_bimg", lambda: load().mphsir_pack_bimg(w3.data_ptr(), w3.stride(1), int(transposed),
                                                          w3.stride(0) if batch > 1 else 0, img.data_ptr(), batch, n, k,
                                                          stream_ptr()),
             lambda: (0.0, 4.0 * batch * n * k + batch * nbytes, "pack_bimg"))
     return img
+
+
+PACK_QUEUE: Optional[list] = None  # set to [] to defer pack_bimg calls; flush_packs() launches them in bulk
+
+
+def flush_packs() -> None:
+    """launch every deferred weight-image pack (mphsir_pack_bimg_multi) and leave deferred mode"""
+    global PACK_QUEUE
+    q, PACK_QUEUE = PACK_QUEUE, None
+    if not q:
+        return
+    arr = (PackItem * len(q))()
+    nbytes = 0.0
+    for j, (w3, img, ld, tr, n, k) in enumerate(q):
+        arr[j] = PackItem(w3.data_ptr(), img.data_ptr(), ld, tr, n, k)
+        nbytes += 4.0 * n * k + img.numel()
+    _launch("pack_bimg_multi", lambda: load().mphsir_pack_bimg_multi(arr, len(q), stream_ptr()), lambda: (0.0, nbytes, "pack_bimg"))
+    del q
 
 
 def gemm(A: View, Bt, Y: View, N: int, *, K: Optional[int] = None, ln=None, bias=None, precision: int = 0,

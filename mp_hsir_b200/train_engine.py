@@ -99,11 +99,22 @@ class TrainEngine(Engine):
         cp = _ceil(cout if cout_pad is None else cout_pad, 16)
         return self._W(pack_conv3x3(wt, cin_pad=cp), weight.shape[1], 9 * cp)
 
-    def _ensure_packed(self):
-        super()._ensure_packed()
-        if self._train_packed_version is not self.packed:
+    def _pack_all(self):
+        """forward + data-gradient weight images; the ~300 image packs are deferred and issued as a handful of launches"""
+        lib.PACK_QUEUE = []
+        try:
+            self.packed = self._pack()
             self._pack_train()
-            self._train_packed_version = self.packed
+        finally:
+            lib.flush_packs()
+        self._train_packed_version = self.packed
+
+    def _ensure_packed(self):
+        v = self._param_versions()
+        if self.packed is None or v != self._versions or self._train_packed_version is not self.packed:
+            self._pack_all()
+            self._versions = v
+            self._graphs.clear()
 
     @torch.no_grad()
     def _pack_train(self):
@@ -787,10 +798,8 @@ class TrainEngine(Engine):
         #    addresses are what the forward/backward graph records
         g_pack = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g_pack, pool=pool):
-            self.packed = self._pack()
-            self._pack_train()
+            self._pack_all()
         self._versions = self._param_versions()
-        self._train_packed_version = self.packed
         n_pack = lib.LAUNCHES - n0
         g_pack.replay()
         # 2. zero_grad + DropPath masks + forward + loss + backward
