@@ -207,3 +207,17 @@ def test_checkpoint_resume_continues_training(tmp_path):
     w1 = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
     w2 = torch.cat([p.detach().reshape(-1) for p in net2.parameters()])
     assert float((w1 - w2).abs().max()) < 1e-6
+
+
+def test_train_step_at_a_non_square_resolution():
+    """64x96 patches: no bilinear resize at level 1 rows but one along the columns, 12 x 8 windows, batch 3"""
+    cfg, net = build("bf16")
+    with torch.no_grad():
+        net.output.weight.mul_(0.05)
+    B = 3
+    clean = synthetic_input((B, 31, 64, 96), seed=9).to(DEV)
+    noisy = clean + 0.1 * torch.randn(clean.shape, device=DEV, generator=torch.Generator(DEV).manual_seed(3))
+    tid = torch.tensor([[0], [2], [5]], device=DEV)
+    tr = net.trainer(lr=2e-4)
+    losses = [float(tr.train_step(noisy, clean, tid, cuda_graph=(i >= 2))) for i in range(8)]
+    assert all(l == l for l in losses) and losses[-1] < losses[0], losses
