@@ -13,9 +13,15 @@ Layout choices
   * the 8 parameters the reference never uses (``prompt{1,2}.{text,clip}_linear``, net/MP_HSIR.py:552,555;
     ``grad is None`` there, so torch's AdamW skips them) sit outside the flat range and stay untouched.
   * activations needed by the backward are kept per block in named workspace buffers (180 GB HBM: a batch
-    of 32 64x64 patches keeps < 12 GB); the fused MLP recomputes its hidden tile in the backward instead.
+    of 32 64x64 patches keeps ~16 GB).  Two things are recomputed instead of stored because their forward
+    kernels are fused: the MLP's hidden tile (LN2 + fc1 GEMM again) and the depthwise-conv outputs q, k of the
+    global spectral attention (the forward runs the fused dwconv+Gram kernel that writes only v).
   * data gradients of linear / conv layers run on the forward's tcgen05 GEMM engine with transposed
-    (flipped) weight images; weight gradients on ``mphsir_wgrad`` (mma.sync over the token axis).
+    (flipped) weight images; weight gradients (and the bias gradients riding on them) on ``mphsir_wgrad``:
+    a tcgen05 kernel for convs / wide layers, an mma.sync kernel for narrow ones, one multi-problem launch
+    for the r-sized local-gate matrices.
+  * after every optimizer step the weight images are re-packed from the flat parameter buffer: plain linear
+    layers straight from the parameter storage, all images through a handful of multi-matrix launches.
 """
 from __future__ import annotations
 
