@@ -221,3 +221,27 @@ def test_train_step_at_a_non_square_resolution():
     tr = net.trainer(lr=2e-4)
     losses = [float(tr.train_step(noisy, clean, tid, cuda_graph=(i >= 2))) for i in range(8)]
     assert all(l == l for l in losses) and losses[-1] < losses[0], losses
+
+
+def test_backward_batch_of_one_with_1d_task_id():
+    """B = 1 and an eval-style 1-D task id (Text_Prompt's one-hot branch, net/MP_HSIR.py:525) through the backward"""
+    from tests.helpers import synthetic_state_dict
+    cfg, net = build("fp32")
+    x = synthetic_input((1, 31, 32, 64), seed=12)
+    tid = torch.tensor([4])
+    R = objective_weights(x.shape, seed=13)
+    sd = {k: v.clone().requires_grad_(True) for k, v in synthetic_state_dict("natural").items()}
+    out_ref = O.forward(sd, cfg, x, tid, synthetic_clip_prompt(cfg.task_classes))
+    (out_ref * R).sum().backward()
+    tr = net.trainer()
+    tr._ensure_packed()
+    tr.zero_grad()
+    out = torch.empty(x.shape, device=DEV)
+    with torch.no_grad():
+        F = tr.forward_train(x.to(DEV), tr.task_weights(tid.to(DEV)), out, None)
+        tr.backward(F, R.to(DEV).contiguous())
+    torch.cuda.synchronize()
+    assert rel_err(out.cpu(), out_ref.detach()) < 1e-4
+    errs = grad_errors(net, {k: v.grad for k, v in sd.items()})
+    bad = sorted(((e, n) for n, e in errs.items() if not e < 2e-3), reverse=True)
+    assert len(errs) == 617 and not bad, f"{len(bad)} off, worst {bad[:8]}"
