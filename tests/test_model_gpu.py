@@ -159,3 +159,36 @@ def test_cuda_graph_replay_matches_eager_across_shapes_and_tasks():
     assert torch.equal(g0, eager[0]) and torch.equal(g0b, eager[0])
     assert torch.equal(g1, eager[1]) and torch.equal(g1b, eager[1])
     assert torch.equal(g0c, eager_t) and not torch.equal(g0c, g0)
+
+
+def test_host_pipeline_matches_direct_forward():
+    """HostPipeline.restore_stream (copies overlapped on side streams, double-buffered inputs) == net(x.cuda()).cpu()"""
+    from mp_hsir_b200 import MP_HSIR_Net
+    from mp_hsir_b200.config import NetConfig
+    from mp_hsir_b200.pipeline import HostPipeline
+    from mp_hsir_b200.synth import fill_state_dict_, synthetic_input
+    cfg = NetConfig.natural()
+    net = MP_HSIR_Net(cfg.in_channel, cfg.out_channel, cfg.dim, task_classes=cfg.task_classes)
+    fill_state_dict_(net, seed=0)
+    net = net.to("cuda:0").eval()
+    xs = [synthetic_input((1, 31, 64, 96), seed=20 + i).pin_memory() for i in range(5)]
+    tids = [torch.tensor([i % 6]).pin_memory() for i in range(5)]
+    outs = [torch.empty_like(x).pin_memory() for x in xs]
+    HostPipeline(net).restore_stream(zip(xs, tids), outs)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        for x, t, o in zip(xs, tids, outs):
+            assert torch.equal(net(x.cuda(), t.cuda()).cpu(), o)
+
+
+def test_device_prefetcher_delivers_every_item_intact():
+    from mp_hsir_b200.pipeline import DevicePrefetcher
+    items = [(torch.full((1 << 20,), float(i)).pin_memory(), torch.tensor([[i]]).pin_memory()) for i in range(7)]
+    got = []
+    for xd, td in DevicePrefetcher(items, "cuda:0"):
+        for _ in range(20):                      # keep the consumer stream busy so copies really run ahead
+            xd = xd * 1.0
+        got.append((xd.sum(), td.clone()))
+    torch.cuda.synchronize()
+    assert [float(s) for s, _ in got] == [float(i) * (1 << 20) for i in range(7)]
+    assert [int(t) for _, t in got] == list(range(7))
