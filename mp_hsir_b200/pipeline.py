@@ -73,51 +73,3 @@ class HostPipeline:
             y.record_stream(self.d2h)
             i += 1
 
-
-class DevicePrefetcher:
-    """Iterate over tuples of pinned host tensors as device tensors, copying item i+1 on a copy stream while the consumer
-    works on item i (the usual training-loop prefetcher for ``trainer.train_step``; two sets of device buffers).  The
-    consumer's stream waits for the copy; a buffer set is overwritten only after the consumer's work enqueued up to the
-    next ``__next__`` call has finished with it."""
-
-    def __init__(self, items: Iterable[Sequence[torch.Tensor]], device):
-        self.it = iter(items)
-        self.device = torch.device(device)
-        self.stream = torch.cuda.Stream(device=self.device)
-        self.bufs = [None, None]
-        self.free = [None, None]
-        self.slot = 0
-        self.staged = self._stage()
-
-    def _stage(self):
-        item = next(self.it, None)
-        if item is None:
-            return None
-        s = self.slot
-        self.slot ^= 1
-        if self.bufs[s] is None or any(tuple(b.shape) != tuple(t.shape) or b.dtype != t.dtype for b, t in zip(self.bufs[s], item)):
-            self.bufs[s] = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in item]
-        with torch.cuda.stream(self.stream):
-            if self.free[s] is not None:
-                self.stream.wait_event(self.free[s])
-            for b, t in zip(self.bufs[s], item):
-                b.copy_(t, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(self.stream)
-        return s, ev
-
-    def __iter__(self):
-        return self
-
-    def __next__(self):
-        if self.staged is None:
-            raise StopIteration
-        s, ev = self.staged
-        cur = torch.cuda.current_stream(self.device)
-        # everything the consumer enqueued so far (its work on the OTHER buffer set) precedes the overwrite of that set
-        done = torch.cuda.Event()
-        done.record(cur)
-        self.free[s ^ 1] = done
-        self.staged = self._stage()
-        cur.wait_event(ev)
-        return self.bufs[s]

@@ -180,15 +180,3 @@ def test_host_pipeline_matches_direct_forward():
         for x, t, o in zip(xs, tids, outs):
             assert torch.equal(net(x.cuda(), t.cuda()).cpu(), o)
 
-
-def test_device_prefetcher_delivers_every_item_intact():
-    from mp_hsir_b200.pipeline import DevicePrefetcher
-    items = [(torch.full((1 << 20,), float(i)).pin_memory(), torch.tensor([[i]]).pin_memory()) for i in range(7)]
-    got = []
-    for xd, td in DevicePrefetcher(items, "cuda:0"):
-        for _ in range(20):                      # keep the consumer stream busy so copies really run ahead
-            xd = xd * 1.0
-        got.append((xd.sum(), td.clone()))
-    torch.cuda.synchronize()
-    assert [float(s) for s, _ in got] == [float(i) * (1 << 20) for i in range(7)]
-    assert [int(t) for _, t in got] == list(range(7))
