@@ -827,7 +827,8 @@ class TrainEngine(Engine):
                            self.weight_decay, 1, 1.0 / world_size, dyn=dyn)
         n_opt = lib.LAUNCHES - n2
         lib.LAUNCHES = n0  # capture records, it does not launch
-        return (g_pack, g_main, g_opt, sx, sc, sw, dyn, n_pack + n_main + n_opt, self.packed)
+        # `out` / `d_out` are written by every replay of g_main: they must live as long as the graph does
+        return (g_pack, g_main, g_opt, sx, sc, sw, dyn, n_pack + n_main + n_opt, self.packed, out, d_out)
 
     def invalidate(self):
         # a captured step owns its packed weights and refreshes them itself (g_pack); anything else (load_state_dict,

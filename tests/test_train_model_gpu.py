@@ -245,3 +245,22 @@ def test_backward_batch_of_one_with_1d_task_id():
     errs = grad_errors(net, {k: v.grad for k, v in sd.items()})
     bad = sorted(((e, n) for n, e in errs.items() if not e < 2e-3), reverse=True)
     assert len(errs) == 617 and not bad, f"{len(bad)} off, worst {bad[:8]}"
+
+
+def test_captured_step_owns_every_buffer_it_writes():
+    """regression: the restored batch / its gradient are written by every replay of the forward+backward graph, so they
+    must stay allocated for the graph's lifetime — tensors a user allocates after the capture must never be clobbered"""
+    B = 2
+    clean = synthetic_input((B, 31, 32, 32), seed=14).to(DEV)
+    noisy = clean + 0.1 * torch.randn(clean.shape, device=DEV, generator=torch.Generator(DEV).manual_seed(4))
+    tid = torch.tensor([[0], [1]], device=DEV)
+    cfg, net = build("bf16")
+    tr = net.trainer(lr=2e-4)
+    for _ in range(2):                                   # eager warm-up step, then capture + first replay
+        tr.train_step(noisy, clean, tid, keep=None, cuda_graph=True)
+    torch.cuda.synchronize()
+    sentinels = [torch.full_like(noisy, 7.0) for _ in range(8)]   # same size class as the graph's output buffers
+    for _ in range(3):
+        tr.train_step(noisy, clean, tid, keep=None, cuda_graph=True)
+    torch.cuda.synchronize()
+    assert all(bool((s == 7.0).all()) for s in sentinels)
