@@ -402,6 +402,9 @@ MPHSIR_API int mphsir_local_gate_bwd_record_ld(int r);
 MPHSIR_API int mphsir_local_gate_bwd(const float* LL /* [B_, >=128+r]: W_prompt m | W_down m */, int ldl, const float* dG,
                                      const mphsir_local_gate_bwd_weights* w, float* record, int ldr, int B_, int C, int r,
                                      void* stream);
+/* forward twin used by the trainer: U = X + row_scale_b * SA * gate[win] (shortcut + locally gated spatial branch, :153,:715-718) */
+MPHSIR_API int mphsir_gate_apply_fwd(const float* X, int ldx, const float* SA, int lds, const float* gate, const float* row_scale,
+                                     float* U, int ldu, int B, int H, int W, int C, int shift, void* stream);
 MPHSIR_API int mphsir_gate_apply_bwd(const float* dU, int ldu, const float* gate, const float* dMean, float* dSA, int lds,
                                      int B, int H, int W, int C, int shift, void* stream);
 

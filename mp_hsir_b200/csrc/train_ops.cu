@@ -417,6 +417,32 @@ __global__ void __launch_bounds__(256) gate_apply_bwd_kernel(const float* __rest
   }
 }
 
+// U[n, c] = X[n, c] + s_b * SA[n, c] * gate[win(n), c]: the shortcut plus the locally gated spatial branch (:153, :715-718)
+// as a stand-alone pass, so that the spectral-apply GEMM of the training forward can use its TMA-drained residual epilogue
+__global__ void __launch_bounds__(256) gate_apply_fwd_kernel(const float* __restrict__ X, long long ldx,
+                                                             const float* __restrict__ SA, long long lds,
+                                                             const float* __restrict__ gate, const float* __restrict__ row_scale,
+                                                             float* __restrict__ U, long long ldu, int B, int H, int W, int C,
+                                                             int shift) {
+  const int c4n = C >> 2;
+  const long long total = (long long)B * H * W * c4n;
+  const int nWx = W >> 3, nW = (H >> 3) * nWx;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long n = idx / c4n;
+    const int c = (int)(idx - n * c4n) * 4;
+    const int x = (int)(n % W), y = (int)((n / W) % H), b = (int)(n / ((long long)W * H));
+    int ys = y - shift, xs = x - shift;
+    if (ys < 0) ys += H;
+    if (xs < 0) xs += W;
+    const long long win = (long long)b * nW + (ys >> 3) * nWx + (xs >> 3);
+    const float s = row_scale != nullptr ? __ldg(row_scale + b) : 1.0f;
+    const float4 xv = ldg4(X + n * ldx + c), a = ldg4(SA + n * lds + c), g = ldg4(gate + win * C + c);
+    *reinterpret_cast<float4*>(U + n * ldu + c) =
+        make_float4(fmaf(s * a.x, g.x, xv.x), fmaf(s * a.y, g.y, xv.y), fmaf(s * a.z, g.z, xv.z), fmaf(s * a.w, g.w, xv.w));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // depthwise 3x3 weight gradient: dW[map(c), tap] += sum_{b,y,x} dY[b,y,x,c] * X[b,y+dy,x+dx,c]   (zero pad)
 // Thread = (channel quad, image row): it walks the row with a sliding 3x3 window of X in registers (3 new float4 of X
@@ -802,6 +828,15 @@ extern "C" int mphsir_gate_apply_bwd(const float* dU, int ldu, const float* gate
                  "gate_apply_bwd: bad arguments");
   gate_apply_bwd_kernel<<<grid_for((long long)B * H * W * (C / 4)), 256, 0, ST(stream)>>>(dU, ldu, gate, dMean, dSA, lds, B, H, W, C, shift);
   return check_launch("gate_apply_bwd");
+}
+
+extern "C" int mphsir_gate_apply_fwd(const float* X, int ldx, const float* SA, int lds, const float* gate, const float* row_scale,
+                                     float* U, int ldu, int B, int H, int W, int C, int shift, void* stream) {
+  MPHSIR_REQUIRE(X && SA && gate && U && B > 0 && H % 8 == 0 && W % 8 == 0 && C % 4 == 0 && ldx % 4 == 0 && lds % 4 == 0 && ldu % 4 == 0,
+                 "gate_apply_fwd: bad arguments");
+  gate_apply_fwd_kernel<<<grid_for((long long)B * H * W * (C / 4)), 256, 0, ST(stream)>>>(X, ldx, SA, lds, gate, row_scale, U, ldu, B, H, W,
+                                                                                          C, shift);
+  return check_launch("gate_apply_fwd");
 }
 
 extern "C" int mphsir_dwconv3x3_wgrad(const float* X, int ldx, const float* dY, int ldy, float* dW, int B, int H, int W, int C,

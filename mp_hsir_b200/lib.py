@@ -146,6 +146,7 @@ SIGNATURES = {
     "mphsir_local_gate_bwd_record_ld": (_I, [_I]),
     "mphsir_local_gate_bwd": (_I, [_VP, _I, _VP, C.POINTER(LocalGateBwdWeights), _VP, _I, _I, _I, _I, _VP]),
     "mphsir_gate_apply_bwd": (_I, [_VP, _I, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
+    "mphsir_gate_apply_fwd": (_I, [_VP, _I, _VP, _I, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "mphsir_spectral_bwd": (_I, [_VP, _LL, _VP, _VP, _VP, _VP, _I, _LL, _VP, _VP, _I, _I, _I, _VP]),
     "mphsir_dwconv3x3_wgrad": (_I, [_VP, _I, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "mphsir_pixel_unshuffle": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _VP]),
@@ -684,6 +685,13 @@ def local_gate_bwd(LL: View, dG: torch.Tensor, w: dict, record: View, B_: int, C
         setattr(ws, n, w[n].data_ptr())
     _launch("local_gate_bwd", lambda: load().mphsir_local_gate_bwd(LL.ptr, LL.ld, dG.data_ptr(), C.byref(ws), record.ptr,
                                                                    record.ld, B_, Cc, r, stream_ptr()))
+
+
+def gate_apply_fwd(X: View, SA: View, gate: torch.Tensor, row_scale: Optional[torch.Tensor], U: View, B: int, H: int, W: int,
+                   Cc: int, shift: int) -> None:
+    _launch("gate_apply_fwd", lambda: load().mphsir_gate_apply_fwd(X.ptr, X.ld, SA.ptr, SA.ld, gate.data_ptr(), ptr(row_scale), U.ptr,
+                                                                   U.ld, B, H, W, Cc, shift, stream_ptr()),
+            lambda: (0.0, 12.0 * B * H * W * Cc, "gate_apply_fwd"))
 
 
 def gate_apply_bwd(dU: View, gate: torch.Tensor, dMean: torch.Tensor, dSA: View, B: int, H: int, W: int, Cc: int,
