@@ -76,6 +76,10 @@ def main():
     out = net(x, torch.tensor(TASK))
     assert not queue, "DropPath call order mismatch"
     ref_import.KEEP_QUEUE = None
+    # the training objective itself (train.py:58-61) on the same forward: value only (its gradient is mostly clamped away on
+    # random weights, which is why the gradient fixture uses the linear objective below)
+    clean = synthetic_input(SHAPE, seed=1)
+    loss_l1 = float(torch.nn.L1Loss()(torch.clamp(out.detach(), 0, 1), clean))
     R = objective_weights(SHAPE)
     (out * R).sum().backward()
     rec = {}
@@ -86,8 +90,8 @@ def main():
         g = p.grad.double()
         rec[n] = {"shape": list(p.shape), "norm": float(g.norm()), "dot": float((g * probe(n, p.shape).double()).sum())}
     with open(os.path.join(GOLDEN, "nat_b2_32_grads.json"), "w") as f:
-        json.dump({"shape": list(SHAPE), "task_id": TASK, "out_absmax": float(out.abs().max()),
-                   "out_sum": float(out.double().sum()), "grads": rec}, f, indent=0)
+        json.dump({"shape": list(SHAPE), "task_id": TASK, "out_absmax": float(out.detach().abs().max()),
+                   "out_sum": float(out.detach().double().sum()), "loss_l1_clamp": loss_l1, "grads": rec}, f, indent=0)
     none = [n for n, v in rec.items() if v is None]
     print("params", len(rec), "without grad", none)
 
