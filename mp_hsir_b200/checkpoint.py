@@ -29,9 +29,24 @@ def save_reference_checkpoint(path: str, net: torch.nn.Module, epoch: int = 0, g
     torch.save(ckpt, path)
 
 
-def load_reference_checkpoint(path_or_ckpt, net: torch.nn.Module, trainer=None, map_location="cpu") -> dict:
-    """Returns {'loaded': [...], 'skipped': [...]} (keys without the 'net.' prefix)."""
-    ckpt = torch.load(path_or_ckpt, map_location=map_location, weights_only=False) if isinstance(path_or_ckpt, str) else path_or_ckpt
+def _load_file(path: str, map_location, trust_pickle: bool):
+    """Tensors-only unpickling first (a checkpoint is user-supplied data); Lightning checkpoints that carry arbitrary Python
+    objects (hyper-parameter namespaces, callbacks) need full unpickling, which executes code from the file: opt-in only."""
+    try:
+        return torch.load(path, map_location=map_location, weights_only=True)
+    except Exception as e:  # noqa: BLE001 - torch raises pickle.UnpicklingError / RuntimeError depending on the payload
+        if not trust_pickle:
+            raise RuntimeError(f"{path} cannot be read with weights_only=True ({type(e).__name__}: {e}); pass "
+                               "trust_pickle=True only for a checkpoint from a source you trust") from e
+        return torch.load(path, map_location=map_location, weights_only=False)
+
+
+def load_reference_checkpoint(path_or_ckpt, net: torch.nn.Module, trainer=None, map_location="cpu",
+                              trust_pickle: bool = False) -> dict:
+    """Returns {'loaded': [...], 'skipped': [...], 'optimizer_restored': bool} (keys without the 'net.' prefix).
+    `optimizer_restored` is False when a trainer was passed but the file holds no matching AdamW state (a plain
+    reference checkpoint, or one written for another architecture: layout checked through `param_offsets`)."""
+    ckpt = _load_file(path_or_ckpt, map_location, trust_pickle) if isinstance(path_or_ckpt, str) else path_or_ckpt
     sd = ckpt["state_dict"] if "state_dict" in ckpt else ckpt
     own = net.state_dict()
     loaded, skipped, filtered = [], [], {}
@@ -48,8 +63,16 @@ def load_reference_checkpoint(path_or_ckpt, net: torch.nn.Module, trainer=None, 
     if hasattr(net, "invalidate_packed_weights"):
         net.invalidate_packed_weights()
     st: Optional[dict] = ckpt.get("mp_hsir_b200_trainer") if isinstance(ckpt, dict) else None
-    if trainer is not None and st is not None and st["exp_avg"].numel() == trainer.flat_m.numel():
-        trainer.flat_m.copy_(st["exp_avg"])
-        trainer.flat_v.copy_(st["exp_avg_sq"])
-        trainer.step_count, trainer.lr = int(st["step_count"]), float(st["lr"])
-    return {"loaded": loaded, "skipped": skipped}
+    restored = False
+    if trainer is not None and st is not None:
+        same_layout = (st["exp_avg"].numel() == trainer.flat_m.numel()
+                       and dict(st.get("param_offsets", {})) == dict(trainer.param_offsets))
+        if same_layout:
+            trainer.flat_m.copy_(st["exp_avg"])
+            trainer.flat_v.copy_(st["exp_avg_sq"])
+            trainer.step_count, trainer.lr = int(st["step_count"]), float(st["lr"])
+            restored = True
+        else:
+            import warnings
+            warnings.warn("checkpoint holds AdamW state for another parameter layout: moments and step count NOT restored")
+    return {"loaded": loaded, "skipped": skipped, "optimizer_restored": restored}

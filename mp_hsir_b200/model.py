@@ -262,7 +262,8 @@ class MP_HSIR_Net(nn.Module):
     def trainer(self, **optimizer_kwargs):
         """Training executor (mp_hsir_b200/train_engine.py): forward + clamp/L1 loss + hand-written backward + AdamW,
         i.e. PromptIRModel.training_step / configure_optimizers of the reference (train.py:50-69).  The parameters are
-        re-homed into one flat buffer; ``param.grad`` are views of the flat gradient buffer."""
+        re-homed into one flat buffer; ``param.grad`` are views of the flat gradient buffer (until the module is first called
+        under autograd — ``net(x, t)`` in train mode — which hands ``param.grad`` back to torch, see autograd.py)."""
         from .train_engine import TrainEngine
         if not isinstance(self._engine, TrainEngine):
             self._engine = TrainEngine(self, **optimizer_kwargs)
@@ -297,7 +298,9 @@ class MP_HSIR_Net(nn.Module):
                 "mp_hsir_b200.MP_HSIR_Net computes only on a CUDA sm_100a device via libmphsir.so; "
                 "there is no CPU fallback (move the module and inputs to cuda)")
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "autograd cannot see through libmphsir.so: train with net.trainer().train_step(degraded, clean, task_id) "
-                "(hand-written backward + AdamW), or run the forward under torch.no_grad() / .eval()")
+            # train mode with gradients being recorded (train.py:58 -> loss.backward()): one autograd.Function over the whole network,
+            # forward = the training launch sequence, backward = the hand-written backward kernels (autograd.py).
+            # net.trainer().train_step(degraded, clean, task_id) is the fast path for the same step.
+            from . import autograd as _ag
+            return _ag.apply(self, inp_img, task_id)
         return self.engine().forward(inp_img, task_id)

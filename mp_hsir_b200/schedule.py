@@ -14,6 +14,19 @@ import math
 def warmup_cosine_lr(epoch: int, base_lr: float, warmup_epochs: int, max_epochs: int, warmup_start_lr: float = 0.0,
                      eta_min: float = 0.0) -> float:
     """lr used during 0-based ``epoch`` (== scheduler.last_epoch after ``epoch`` calls of ``scheduler.step()``)."""
+    if warmup_epochs == 0:
+        # max_epochs < 10 with train.py's int(0.1 * epochs): the reference's chainable recursion (utils/schedulers.py:
+        # 303-326) returns warmup_start_lr at epoch 0 and never passes through its `last_epoch == warmup_epochs` reset,
+        # so the cosine factor is applied to (lr - eta_min) starting from warmup_start_lr — the lr stays within
+        # eta_min of 0 for the whole run.  Reproduced literally, quirk included.
+        lr = warmup_start_lr
+        for e in range(1, epoch + 1):
+            if (e - 1 - max_epochs) % (2 * max_epochs) == 0:
+                lr = lr + (base_lr - eta_min) * (1.0 - math.cos(math.pi / max_epochs)) / 2.0
+            else:
+                lr = ((1.0 + math.cos(math.pi * e / max_epochs)) / (1.0 + math.cos(math.pi * (e - 1) / max_epochs))
+                      * (lr - eta_min) + eta_min)
+        return lr
     if epoch < warmup_epochs:
         if warmup_epochs <= 1:
             return warmup_start_lr

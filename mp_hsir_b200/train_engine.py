@@ -574,6 +574,7 @@ class TrainEngine(Engine):
         """MP_HSIR_Net.forward (net/MP_HSIR.py:810-844) keeping what the backward needs.  keep: {(stage, i): [2,B]}
         DropPath multipliers (mask/keep_prob, :718-719) or None."""
         cfg, P, ws = self.cfg, self.packed, self.ws
+        self._tvsp_valid.clear()   # the prompt columns of the fusion buffers are rewritten below (inference-time cache)
         B, _, H, W = x.shape
         d = cfg.dim
         N1, N2, N3 = B * H * W, B * H * W // 4, B * H * W // 16
@@ -678,6 +679,44 @@ class TrainEngine(Engine):
         self._stage_bwd("encoder_level1", F["enc1"], d_e1, d_x1, B, H, W)
         self._conv_wgrad(d_x1, F["tok"], "patch_embed.proj.weight", d, cfg.in_channel, H, W)
 
+    # -- torch.autograd entry points (mp_hsir_b200/autograd.py) --------------------------------------------------
+    autograd_serial = 0
+    drop_path_generator: Optional[torch.Generator] = None   # tests: seeded DropPath draws
+    _grads_attached = True   # _flatten_parameters points param.grad at views of flat_g (the train_step fast path)
+
+    def release_param_grads(self):
+        """hand ``param.grad`` back to torch: in autograd mode AccumulateGrad owns it (a grad that aliased the flat gradient
+        buffer would be added to itself)"""
+        if self._grads_attached:
+            for p in self.net.parameters():
+                p.grad = None
+            self._grads_attached = False
+
+    @torch.no_grad()
+    def autograd_forward(self, inp: torch.Tensor, task_id: torch.Tensor):
+        B, _, H, W = inp.shape
+        if H % 32 or W % 32:
+            raise ValueError(f"H and W must be multiples of 32, got {H}x{W}")
+        self._ensure_packed()
+        x = inp.detach().to(torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            out = torch.empty_like(x)
+            keep = self.drop_path_scales(B, self.drop_path_generator) if self.net.training else None
+            F = self.forward_train(x, self.task_weights(task_id), out, keep)
+        TrainEngine.autograd_serial = self.autograd_serial = self.autograd_serial + 1
+        return out.to(inp.dtype), F
+
+    @torch.no_grad()
+    def autograd_backward(self, F: dict, d_out: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """-> {parameter name: gradient tensor} (views of ONE fresh copy of the flat gradient buffer, so that they neither
+        alias each other's future contents nor the next backward's)"""
+        with torch.cuda.device(self.device):
+            self.flat_g.zero_()
+            self.backward(F, d_out.detach().to(torch.float32).contiguous())
+            snap = self.flat_g.clone()
+        params = dict(self.net.named_parameters())
+        return {n: snap[o:o + params[n].numel()].view(params[n].shape) for n, o in self.param_offsets.items()}
+
     # -- public steps --------------------------------------------------------------------------------------------
     def drop_path_scales(self, B: int, generator: Optional[torch.Generator] = None) -> dict:
         """Per-sample DropPath multipliers mask/keep_prob for every block, one draw per call like timm's DropPath
@@ -737,7 +776,7 @@ class TrainEngine(Engine):
         if all_reduce is not None:
             all_reduce(self.flat_g)  # DDP: sum over ranks, the mean is folded into grad_scale
         self.optimizer_step(grad_scale=1.0 / world_size)
-        return loss
+        return loss.clone()   # loss_buf itself is overwritten by the next step
 
     # -- CUDA-graph replay of the step ---------------------------------------------------------------------------
     @torch.no_grad()
@@ -747,6 +786,11 @@ class TrainEngine(Engine):
         key = (tuple(inp.shape), keep, world_size)
         graphs = self.__dict__.setdefault("_train_graphs", {})
         ent = graphs.get(key)
+        if ent is not None and ent != "warm" and ent[11] != self.ws.generation:
+            # a named workspace buffer was re-allocated since the capture (a larger batch, or an inference forward at a
+            # larger shape on this engine): every captured step holds raw pointers into the old blocks -> drop them all
+            graphs.clear()
+            ent = None
         if ent is None:
             # first call at this shape: eager step (sizes the workspace, sets kernel attributes); mark for capture
             graphs[key] = "warm"
@@ -787,7 +831,7 @@ class TrainEngine(Engine):
                 self.graph_ms = {"fwd_bwd": ev[0].elapsed_time(ev[1]), "all_reduce": ev[1].elapsed_time(ev[2]),
                                  "adamw": ev[2].elapsed_time(ev[3]), "repack": ev[3].elapsed_time(ev[4])}
             lib.LAUNCHES += ent[7]
-        return self.loss_buf
+        return self.loss_buf.clone()   # loss_buf itself is overwritten by the next step
 
     def _capture_step(self, inp, clean, task_id, keep, world_size):
         gen = self.ws.generation
@@ -831,7 +875,7 @@ class TrainEngine(Engine):
         n_opt = lib.LAUNCHES - n2
         lib.LAUNCHES = n0  # capture records, it does not launch
         # `out` / `d_out` are written by every replay of g_main: they must live as long as the graph does
-        return (g_pack, g_main, g_opt, sx, sc, sw, dyn, n_pack + n_main + n_opt, self.packed, out, d_out)
+        return (g_pack, g_main, g_opt, sx, sc, sw, dyn, n_pack + n_main + n_opt, self.packed, out, d_out, gen)
 
     def invalidate(self):
         # a captured step owns its packed weights and refreshes them itself (g_pack); anything else (load_state_dict,

@@ -8,7 +8,7 @@ spec = importlib.util.spec_from_file_location("ref_schedulers", "/root/reference
 mod = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(mod)
 out = {}
-for name, (lr, epochs) in {"train_default": (2e-4, 500), "short": (1e-3, 30)}.items():
+for name, (lr, epochs) in {"train_default": (2e-4, 500), "short": (1e-3, 30), "no_warmup_5": (2e-4, 5), "no_warmup_9": (2e-4, 9)}.items():
     p = torch.nn.Parameter(torch.zeros(1))
     opt = torch.optim.AdamW([p], lr=lr)
     sch = mod.LinearWarmupCosineAnnealingLR(optimizer=opt, warmup_epochs=int(0.1 * epochs), max_epochs=epochs, eta_min=1e-6)

@@ -1,8 +1,9 @@
-"""Import the UNMODIFIED reference model from /root/reference (authoring container only).
+"""Import the UNMODIFIED reference model: from /root/reference in the authoring container, else from the verbatim
+copy ``oracle/build_ref.py`` placed under the git-ignored ``oracle/_ref/`` (which travels to the GPU box).
 
-TEST INFRASTRUCTURE.  `/root/reference` does not exist on the GPU box, so nothing that runs
-there may call this; it is used by ``oracle/make_golden.py`` to generate the committed
-fixtures and by the optional ``tests/test_reference_live.py`` (skipped when the tree is absent).
+TEST INFRASTRUCTURE.  Used by ``oracle/make_golden*.py`` to generate the committed fixtures, by
+``tests/test_reference_live.py`` (skipped when neither tree is present) and by ``bench.py --impl reference`` /
+``cpu_baseline`` (the reference timed on the host cores).  Never on the product path.
 
 Two imports of net/MP_HSIR.py are not installable here and are stubbed through
 ``sys.modules`` before the import:
@@ -19,7 +20,19 @@ import types
 
 import torch
 
-REF_ROOT = os.environ.get("MPHSIR_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _ref_root() -> str:
+    env = os.environ.get("MPHSIR_REFERENCE")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/net/MP_HSIR.py"):
+        return "/root/reference"
+    return os.path.join(_HERE, "_ref")
+
+
+REF_ROOT = _ref_root()
 
 
 KEEP_QUEUE = None  # optional list of [B] DropPath multipliers consumed by the stub in forward-call order

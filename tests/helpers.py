@@ -4,7 +4,7 @@ import functools
 import torch
 
 from mp_hsir_b200.config import NetConfig
-from mp_hsir_b200.synth import synth_tensor, synthetic_clip_prompt, synthetic_input
+from mp_hsir_b200.synth import synth_tensor, synthetic_clip_prompt, synthetic_input, synthetic_scene
 from tests.conftest import GOLDEN  # noqa: F401
 
 import json
@@ -36,3 +36,31 @@ def case_inputs(meta):
 
 def clip_for(cfg: NetConfig):
     return synthetic_clip_prompt(cfg.task_classes)
+
+
+def big_case_inputs(meta):
+    """(input, clean-or-None, task ids) of a BASELINE-shape case (oracle/make_golden.py BIG_CASES)."""
+    recipe = meta["recipe"]
+    tid = torch.tensor(meta["task_id"])
+    if recipe[0] == "rand":
+        return synthetic_input(tuple(recipe[1]), seed=meta["seed"]), None, tid
+    noisy, clean = synthetic_scene(recipe[1], recipe[2], seed=meta["seed"])
+    return noisy, clean, tid
+
+
+def psnr_per_band(y, clean) -> float:
+    """utils/val_utils.py:49-69 of the reference: per-band PSNR (data_range 1) on clip(.,0,1), mean over bands and batch."""
+    y, c = y.clamp(0, 1).double(), clean.clamp(0, 1).double()
+    mse = ((y - c) ** 2).mean(dim=(-1, -2))
+    return float((10.0 * torch.log10(1.0 / mse)).mean())
+
+
+def big_case_errors(y: torch.Tensor, g: dict, meta: dict):
+    """parity of a full-size output against the stored strided subsample + all-pixel band sums of the reference:
+    (max|d|/max|ref| on the subsample, max band-mean error / max|ref|)."""
+    s = meta["stride"]
+    sub = y[:, :, ::s, ::s].double().cpu()
+    e_sub = float((sub - g["sub"].double()).abs().max() / meta["out_absmax"])
+    hw = y.shape[-1] * y.shape[-2]
+    e_mean = float((y.double().sum(dim=(-1, -2)).cpu() - g["band_sums"].double()).abs().max() / hw / meta["out_absmax"])
+    return e_sub, e_mean

@@ -51,5 +51,26 @@ def test_reference_arm_prints_one_contract_line():
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in j, key
-    assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port" and j["vs_baseline"] is None
+    assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] in ("reference", "port") and j["vs_baseline"] is None
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
+    # same config as our arm: the full workload shape, no extrapolation from a smaller sample
+    assert j["config"]["sample_shape"] == j["config"]["shape_per_gpu"] == [16, 31, 64, 64]
+
+
+def test_golden_check_accepts_the_reference_and_rejects_a_perturbed_output():
+    """bench.golden_check (the in-run output check) on the config-2 fixture: the oracle's output passes at the fp32
+    bound, a 1e-3 perturbation fails."""
+    import pytest
+    from mp_hsir_b200.config import NetConfig
+    from mp_hsir_b200.synth import synthetic_clip_prompt
+    from oracle import mp_hsir_oracle as O
+    from tests.helpers import synthetic_state_dict
+    x, clean, tid = bench.make_input((16, 31, 64, 64), 0, "patch16")
+    assert tid.tolist() == [i % 6 for i in range(16)] and clean is None
+    cfg = NetConfig.natural()
+    with torch.no_grad():
+        y = O.forward(synthetic_state_dict("natural"), cfg, x, tid, synthetic_clip_prompt(cfg.task_classes))
+    res = bench.golden_check("patch16", y, None, "fp32")
+    assert res["max_abs_err_over_max_abs_ref"] < 2e-5
+    with pytest.raises(SystemExit):
+        bench.golden_check("patch16", y + 1e-3 * y.abs().max(), None, "fp32")

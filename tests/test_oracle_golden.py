@@ -4,7 +4,7 @@ import torch
 
 from oracle import mp_hsir_oracle as O
 from tests.conftest import load_golden, rel_err
-from tests.helpers import case_inputs, cfg_of, clip_for, synthetic_state_dict
+from tests.helpers import big_case_errors, big_case_inputs, case_inputs, cfg_of, clip_for, synthetic_state_dict
 
 # reference fp32 thread-count jitter is 2.4e-6 abs; the restatement only
 # re-associates sums, so 2e-5 relative is a comfortable but meaningful bound.
@@ -24,6 +24,18 @@ def test_oracle_matches_reference_output(name, cases):
     ref = load_golden(name)["out"]
     assert y.shape == ref.shape
     assert rel_err(y, ref) < TOL
+
+
+def test_oracle_matches_reference_at_config2_shape(cases):
+    """BASELINE config 2 (16x31x64x64, task ids arange(16)%6): the oracle against the reference's strided subsample and
+    band sums (the 512x512 / RS 256x256 fixtures are checked on the GPU box only: minutes of CPU time here)."""
+    meta = cases["nat_b16_64"]
+    cfg = cfg_of(meta["model"])
+    x, _, tid = big_case_inputs(meta)
+    with torch.no_grad():
+        y = O.forward(synthetic_state_dict(meta["model"]), cfg, x, tid, clip_for(cfg))
+    e_sub, e_mean = big_case_errors(y, load_golden("nat_b16_64"), meta)
+    assert e_sub < TOL and e_mean < TOL
 
 
 def test_oracle_intermediates_match_reference_hooks(cases):

@@ -264,3 +264,108 @@ def test_captured_step_owns_every_buffer_it_writes():
         tr.train_step(noisy, clean, tid, keep=None, cuda_graph=True)
     torch.cuda.synchronize()
     assert all(bool((s == 7.0).all()) for s in sentinels)
+
+
+def _train_py_step(net, opt, x, clean, tid):
+    """PromptIRModel.training_step + the optimiser step Lightning wraps around it (train.py:50-69), verbatim."""
+    restored = net(x, tid)                                   # train.py:58
+    restored = torch.clamp(restored, 0, 1)                   # train.py:59
+    loss = torch.nn.functional.l1_loss(restored, clean)      # train.py:61 (nn.L1Loss)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    return loss.detach()
+
+
+def test_module_drops_into_train_py_autograd_loop():
+    """The drop-in module under autograd — net(x, t) in train mode, loss.backward(), torch.optim.AdamW(net.parameters()) —
+    against net.trainer().train_step (hand-written backward + fused AdamW) on the same batches with the same DropPath
+    draws: losses to 1e-6, first-step gradients to 1e-5 relative L2 per tensor (the two paths run the SAME kernels; the
+    weight-gradient atomics make the summation order vary), parameters after two steps equal except where |g| ~ 0
+    (AdamW's first updates are lr * sign(g))."""
+    steps, lr = 2, 2e-4
+    xs = [synthetic_input((2, 31, 32, 32), seed=40 + i).to(DEV) for i in range(steps)]
+    cs = [synthetic_input((2, 31, 32, 32), seed=50 + i).to(DEV) for i in range(steps)]
+    tid = torch.tensor([[1], [4]]).to(DEV)
+
+    cfg, net_a = build("fp32")
+    with torch.no_grad():
+        net_a.output.weight.mul_(0.05)
+    opt = torch.optim.AdamW(net_a.parameters(), lr=lr)       # train.py:69 — created BEFORE the first forward, like Lightning
+    cfg, net_b = build("fp32")
+    with torch.no_grad():
+        net_b.output.weight.mul_(0.05)
+    tr = net_b.trainer(lr=lr)
+    gen_b = torch.Generator(device=DEV).manual_seed(123)
+
+    losses_a, losses_b, grad_errs = [], [], {}
+    for i, (x, c) in enumerate(zip(xs, cs)):
+        if i == 0:
+            net_a.trainer().drop_path_generator = torch.Generator(device=DEV).manual_seed(123)
+        losses_a.append(float(_train_py_step(net_a, opt, x, c, tid)))
+        keep = tr.drop_path_scales(x.shape[0], gen_b)
+        if i == 0:
+            # gradients of the first step, before either optimiser has moved anything
+            tr.zero_grad()
+            _, l = tr.loss_and_grad(x, c, tid, keep=keep)
+            for n, p in net_a.named_parameters():
+                if p.grad is not None:
+                    g = tr.g[n].view(p.shape)
+                    grad_errs[n] = float((p.grad - g).norm() / g.norm().clamp_min(1e-30))
+            losses_b.append(float(l))
+            tr.optimizer_step()
+        else:
+            losses_b.append(float(tr.train_step(x, c, tid, keep=keep)))
+    torch.cuda.synchronize()
+    assert all(abs(a - b) <= 1e-6 for a, b in zip(losses_a, losses_b)), (losses_a, losses_b)
+    assert len(grad_errs) == 617 and max(grad_errs.values()) < 1e-5, sorted(grad_errs.items(), key=lambda kv: -kv[1])[:5]
+    dead = [n for n, p in net_a.named_parameters() if p.grad is None]
+    assert sorted(dead) == sorted(n for n, _ in net_a.named_parameters() if "text_linear" in n or "clip_linear" in n)
+    pa, pb = dict(net_a.named_parameters()), dict(net_b.named_parameters())
+    diffs = [float((pa[n] - pb[n]).abs().max()) for n in pa]
+    assert max(diffs) <= 2.2 * lr * steps, max(diffs)
+    assert sum(d < 2e-6 for d in diffs) / len(diffs) > 0.8, sorted(diffs)[-20:]
+    y = net_a(xs[0], tid)
+    assert y.requires_grad and y.grad_fn is not None
+
+
+def test_second_forward_invalidates_the_first_graph():
+    cfg, net = build("fp32")
+    x = synthetic_input((1, 31, 32, 32), seed=1).to(DEV)
+    tid = torch.tensor([0]).to(DEV)
+    y1 = net(x, tid)
+    y2 = net(x, tid)
+    with pytest.raises(RuntimeError, match="LATEST forward"):
+        y1.sum().backward()
+    y2.sum().backward()
+    assert net.output.weight.grad is not None and torch.isfinite(net.output.weight.grad).all()
+
+
+def test_captured_steps_survive_a_larger_inference_forward():
+    """ADVICE r1: a forward at a larger shape re-allocates named workspace buffers the captured training step points into;
+    the captured graphs must be dropped and re-captured, not replayed on freed memory."""
+    cfg, net = build("fp32")
+    with torch.no_grad():
+        net.output.weight.mul_(0.05)
+    tr = net.trainer(lr=2e-4)
+    x = synthetic_input((2, 31, 32, 32), seed=60).to(DEV)
+    c = synthetic_input((2, 31, 32, 32), seed=61).to(DEV)
+    tid = torch.tensor([[0], [2]]).to(DEV)
+    for _ in range(3):                        # eager warm-up, capture, replay
+        tr.train_step(x, c, tid, keep=None, cuda_graph=True)
+    gen0 = tr.ws.generation
+    net.eval()
+    with torch.no_grad():
+        big = tr.forward(synthetic_input((1, 31, 64, 96), seed=62).to(DEV), torch.tensor([1]).to(DEV))
+    net.train()
+    assert tr.ws.generation != gen0 and torch.isfinite(big).all()
+    l_graph = float(tr.train_step(x, c, tid, keep=None, cuda_graph=True))      # must not replay the stale graph
+    # same state, eager, on a twin
+    cfg, net2 = build("fp32")
+    with torch.no_grad():
+        net2.output.weight.mul_(0.05)
+    tr2 = net2.trainer(lr=2e-4)
+    for _ in range(3):
+        tr2.train_step(x, c, tid, keep=None)
+    l_eager = float(tr2.train_step(x, c, tid, keep=None))
+    assert abs(l_graph - l_eager) <= 1e-5, (l_graph, l_eager)
