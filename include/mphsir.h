@@ -211,6 +211,14 @@ MPHSIR_API int mphsir_window_attn_fwd(const float* qkv, int ldqkv, const float* 
                            float* win_mean, int B, int H, int W, int C, int heads, int shift,
                            int precision /* MPHSIR_PREC_*: SIMT fp32, or tensor cores with bf16x3 / bf16 operands */,
                            void* stream);
+/* Row band of a scene sharded over GPUs (mp_hsir_b200/sharded.py): the [H, W] image handed to the kernel is rows
+ * [y0, y0 + H) (cyclic) of a scene of mask_H rows, and the Swin mask of calculate_mask (:643-658) is evaluated in
+ * the shifted coordinates of the SCENE: local shifted row ys is scene row (ys + mask_y0) mod mask_H.  The roll wraps
+ * inside the band (those windows belong to the halo and are recomputed by the neighbour rank).
+ * mphsir_window_attn_fwd == mask_H = H, mask_y0 = 0.  Tensor-core precisions only. */
+MPHSIR_API int mphsir_window_attn_band_fwd(const float* qkv, int ldqkv, const float* bias, float* out, int ldo,
+                           float* win_mean, int B, int H, int W, int C, int heads, int shift, int precision,
+                           int mask_H, int mask_y0, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Local spectral branch (low-rank spectral-prompt gate), one fused kernel per window:
@@ -275,6 +283,15 @@ MPHSIR_API int mphsir_dwgram_supported(int C, int c);
 MPHSIR_API size_t mphsir_dwgram_partial_floats(int B, int heads, int c, int H, int W, int* n_chunks);
 MPHSIR_API int mphsir_dwgram_fwd(const float* X, int ldx, const float* w9 /* [9, 3C] */, float* V, int ldv,
                                  float* partial, int B, int H, int W, int C, int heads, int precision, void* stream);
+/* Row band of a sharded scene: conv and V cover all H rows handed in (own rows + halo), but only 8x8 tiles whose first
+ * row lies in [gram_y0, gram_y1) (multiples of 8) enter the Gram statistics — each rank contributes its OWN rows to the
+ * reduction over the whole scene (net/MP_HSIR.py:104-110).  mphsir_dwgram_fwd == [0, H). */
+MPHSIR_API int mphsir_dwgram_band_fwd(const float* X, int ldx, const float* w9 /* [9, 3C] */, float* V, int ldv,
+                                      float* partial, int B, int H, int W, int C, int heads, int precision,
+                                      int gram_y0, int gram_y1, void* stream);
+/* Step 2a alone: reduced[B*heads, c*c+2c] = sum over chunks of partial — the per-rank statistics a sharded scene
+ * sums across GPUs before mphsir_spectral_finish_fwd(n_chunks = 1). */
+MPHSIR_API int mphsir_gram_reduce(const float* partial, int n_chunks, float* reduced, int B, int heads, int c, void* stream);
 
 /* Steps 2+3 in one call (what the module uses): reduce the partials (into `scratch` when n_chunks > 1),
  * normalise + temperature + softmax, fold project_out, and write the per-sample matrix as fp32 "in x out"

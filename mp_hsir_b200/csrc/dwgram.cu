@@ -68,7 +68,9 @@ template <int CG, int CH, int NG, int PARTS>
 __global__ void __launch_bounds__(256) dwgram_kernel(const float* __restrict__ X, long long ldx,
                                                      const float* __restrict__ w9, float* __restrict__ V, long long ldv,
                                                      float* __restrict__ partial, int H, int W, int tiles_x,
-                                                     int tiles_per_sample) {
+                                                     int tiles_per_sample, int gy0, int gy1) {
+  // gy0, gy1: only tiles whose first row lies in [gy0, gy1) contribute to the Gram statistics (row-sharded scenes: the
+  // depthwise conv and V are computed on the halo rows too, the statistics on the rank's own rows only)
   constexpr int C = CG * NG;
   constexpr int LD = CG + 8;           // bf16 elements per smem row
   constexpr int ARR = 64 * LD;
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(256) dwgram_kernel(const float* __restrict__ X
 
   for (int tile = blockIdx.x; tile < tiles_per_sample; tile += gridDim.x) {
     const int ty0 = (tile / tiles_x) * 8, tx0 = (tile - (tile / tiles_x) * tiles_x) * 8;
+    const bool in_gram = ty0 >= gy0 && ty0 < gy1;
 #pragma unroll
     for (int gi = 0; gi < NG; ++gi) {
       // ---- phase A: depthwise conv of this group's q, k, v channels for the 8x8 tile ----------------
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(256) dwgram_kernel(const float* __restrict__ X
       }
       __syncthreads();
       // ---- phase B: Gram of every head of the group on the tensor cores + squared norms ---------------
-      if (warp < UNITS) {
+      if (warp < UNITS && in_gram) {
         const int m0 = warp * 16;                  // first q channel of this unit (inside the group)
         const int n_base = (m0 / CH) * CH;         // first k channel of the same head
 #pragma unroll
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(256) dwgram_kernel(const float* __restrict__ X
           }
         }
       }
-      if (tid < 2 * CG) {
+      if (tid < 2 * CG && in_gram) {
         const __nv_bfloat16* src = (tid < CG ? Qs + tid : Ks + (tid - CG));
         float s = 0.f;
 #pragma unroll 8
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(256) dwgram_kernel(const float* __restrict__ X
 
 // TMA-fed variant (dwgram_tma.cu): 64/128-channel head groups on images of at least 16x16 pixels
 int launch_tma(int cfg, bool x3, const float* X, int ldx, const float* w9, float* V, int ldv, float* partial, int B, int H,
-               int W, int ctas, cudaStream_t st);
+               int W, int ctas, int gy0, int gy1, cudaStream_t st);
 static bool g_use_tma = true;
 static bool tma_eligible(int cfg, int H, int W) { return g_use_tma && cfg >= 1 && cfg <= 4 && H >= 16 && W >= 16; }
 
@@ -220,7 +223,7 @@ static int ctas_per_sample(int B, int tiles, bool tma) {
 
 template <int CG, int CH, int NG, int PARTS>
 static int launch(const float* X, int ldx, const float* w9, float* V, int ldv, float* partial, int B, int H, int W,
-                  cudaStream_t st) {
+                  int gy0, int gy1, cudaStream_t st) {
   const size_t smem = (size_t)2 * PARTS * 64 * (CG + 8) * 2;
   static bool configured = false;
   if (!configured) {
@@ -233,7 +236,7 @@ static int launch(const float* X, int ldx, const float* w9, float* V, int ldv, f
   }
   const int tiles_x = W / 8, tiles = tiles_x * (H / 8);
   dim3 grid(ctas_per_sample(B, tiles, false), B);
-  dwgram_kernel<CG, CH, NG, PARTS><<<grid, 256, smem, st>>>(X, ldx, w9, V, ldv, partial, H, W, tiles_x, tiles);
+  dwgram_kernel<CG, CH, NG, PARTS><<<grid, 256, smem, st>>>(X, ldx, w9, V, ldv, partial, H, W, tiles_x, tiles, gy0, gy1);
   return check_launch("dwgram");
 }
 
@@ -264,8 +267,8 @@ extern "C" size_t mphsir_dwgram_partial_floats(int B, int heads, int c, int H, i
   return (size_t)B * heads * n * ((size_t)c * c + 2 * c);
 }
 
-extern "C" int mphsir_dwgram_fwd(const float* X, int ldx, const float* w9, float* V, int ldv, float* partial, int B,
-                                 int H, int W, int C, int heads, int precision, void* stream) {
+extern "C" int mphsir_dwgram_band_fwd(const float* X, int ldx, const float* w9, float* V, int ldv, float* partial, int B,
+                                      int H, int W, int C, int heads, int precision, int gram_y0, int gram_y1, void* stream) {
   MPHSIR_REQUIRE(X && w9 && V && partial, "dwgram: null operand");
   MPHSIR_REQUIRE(B > 0 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0, "dwgram: H=%d W=%d must be multiples of 8", H, W);
   MPHSIR_REQUIRE(heads > 0 && C % heads == 0, "dwgram: C=%d not divisible by heads=%d", C, heads);
@@ -273,14 +276,16 @@ extern "C" int mphsir_dwgram_fwd(const float* X, int ldx, const float* w9, float
   MPHSIR_REQUIRE(((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(V) | reinterpret_cast<uintptr_t>(w9) |
                    reinterpret_cast<uintptr_t>(partial)) & 15) == 0, "dwgram: operands must be 16-byte aligned");
   MPHSIR_REQUIRE(precision == MPHSIR_PREC_BF16X3 || precision == MPHSIR_PREC_BF16, "dwgram: tensor-core precisions only (use dwconv3x3 + gram_partial for fp32 SIMT)");
+  MPHSIR_REQUIRE(gram_y0 % 8 == 0 && gram_y1 % 8 == 0 && 0 <= gram_y0 && gram_y0 <= gram_y1, "dwgram: Gram row range [%d,%d) must be tile aligned", gram_y0, gram_y1);
   const int cfg = dwgram_config(C, C / heads);
   MPHSIR_REQUIRE(cfg != 0, "dwgram: unsupported (C=%d, c=%d); use dwconv3x3 + gram_partial", C, C / heads);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool x3 = precision == MPHSIR_PREC_BF16X3;
   if (dwg::tma_eligible(cfg, H, W))
-    return dwg::launch_tma(cfg, x3, X, ldx, w9, V, ldv, partial, B, H, W, dwg::ctas_per_sample(B, (H / 8) * (W / 8), true), st);
-#define DWG(CG, CH, NG) (x3 ? dwg::launch<CG, CH, NG, 2>(X, ldx, w9, V, ldv, partial, B, H, W, st) \
-                            : dwg::launch<CG, CH, NG, 1>(X, ldx, w9, V, ldv, partial, B, H, W, st))
+    return dwg::launch_tma(cfg, x3, X, ldx, w9, V, ldv, partial, B, H, W, dwg::ctas_per_sample(B, (H / 8) * (W / 8), true),
+                           gram_y0, gram_y1, st);
+#define DWG(CG, CH, NG) (x3 ? dwg::launch<CG, CH, NG, 2>(X, ldx, w9, V, ldv, partial, B, H, W, gram_y0, gram_y1, st) \
+                            : dwg::launch<CG, CH, NG, 1>(X, ldx, w9, V, ldv, partial, B, H, W, gram_y0, gram_y1, st))
   switch (cfg) {
     case 1: return DWG(64, 32, 1);
     case 2: return DWG(128, 64, 1);
@@ -289,4 +294,9 @@ extern "C" int mphsir_dwgram_fwd(const float* X, int ldx, const float* w9, float
     default: return DWG(96, 48, 1);
   }
 #undef DWG
+}
+
+extern "C" int mphsir_dwgram_fwd(const float* X, int ldx, const float* w9, float* V, int ldv, float* partial, int B,
+                                 int H, int W, int C, int heads, int precision, void* stream) {
+  return mphsir_dwgram_band_fwd(X, ldx, w9, V, ldv, partial, B, H, W, C, heads, precision, 0, H, stream);
 }

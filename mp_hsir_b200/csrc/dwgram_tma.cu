@@ -98,7 +98,8 @@ template <int CG, int CH, int NG, int PARTS>
 __global__ void __launch_bounds__(TMA_THREADS, 1) dwgram_tma_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                     const float* __restrict__ w9, float* __restrict__ V,
                                                                     long long ldv, float* __restrict__ partial, int H, int W,
-                                                                    int tiles_x, int tiles_per_sample) {
+                                                                    int tiles_x, int tiles_per_sample, int gy0, int gy1) {
+  // gy0, gy1: only tiles whose first row lies in [gy0, gy1) enter the Gram statistics (see dwgram.cu)
   using P = TmaPlan<CG, PARTS>;
   constexpr int C = CG * NG;
   constexpr int NST = P::NST, LD = P::LD, ARR = P::ARR;
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) dwgram_tma_kernel(const __grid
   uint32_t it = 0;
   for (int tile = blockIdx.x; tile < tiles_per_sample; tile += gridDim.x) {
     const int ty0 = (tile / tiles_x) * 8, tx0 = (tile - (tile / tiles_x) * tiles_x) * 8;
+    const bool in_gram = ty0 >= gy0 && ty0 < gy1;
 #pragma unroll
     for (int gi = 0; gi < NG; ++gi) {
 #pragma unroll
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) dwgram_tma_kernel(const __grid
         if (op == 2) {
           // ---- Gram of every head of the group (q, k tiles are complete) ------------------------------
           consumer_bar();
-          if (warp < UNITS) {
+          if (warp < UNITS && in_gram) {
             const int m0 = warp * 16;
             const int n_base = (m0 / CH) * CH;
 #pragma unroll
@@ -228,8 +230,10 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) dwgram_tma_kernel(const __grid
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
               const float4 x = r[rr][o];
-              n4.x = fmaf(x.x, x.x, n4.x); n4.y = fmaf(x.y, x.y, n4.y);
-              n4.z = fmaf(x.z, x.z, n4.z); n4.w = fmaf(x.w, x.w, n4.w);
+              if (in_gram) {
+                n4.x = fmaf(x.x, x.x, n4.x); n4.y = fmaf(x.y, x.y, n4.y);
+                n4.z = fmaf(x.z, x.z, n4.z); n4.w = fmaf(x.w, x.w, n4.w);
+              }
               const int p = (by + rr) * 8 + bx + o;  // pixel index inside the tile
               uint2 hi, lo;
               t_split_pair(x.x, x.y, hi.x, lo.x);
@@ -293,7 +297,7 @@ static PFN_cuTensorMapEncodeTiled dwg_encode_fn() {
 
 template <int CG, int CH, int NG, int PARTS>
 static int launch_tma_t(const float* X, int ldx, const float* w9, float* V, int ldv, float* partial, int B, int H, int W,
-                        int ctas, cudaStream_t st) {
+                        int ctas, int gy0, int gy1, cudaStream_t st) {
   constexpr int C = CG * NG;
   PFN_cuTensorMapEncodeTiled enc = dwg_encode_fn();
   if (enc == nullptr) {
@@ -322,15 +326,15 @@ static int launch_tma_t(const float* X, int ldx, const float* w9, float* V, int 
   }
   const int tiles_x = W / 8, tiles = tiles_x * (H / 8);
   dim3 grid(ctas, B);
-  dwgram_tma_kernel<CG, CH, NG, PARTS><<<grid, TMA_THREADS, smem, st>>>(tm, w9, V, ldv, partial, H, W, tiles_x, tiles);
+  dwgram_tma_kernel<CG, CH, NG, PARTS><<<grid, TMA_THREADS, smem, st>>>(tm, w9, V, ldv, partial, H, W, tiles_x, tiles, gy0, gy1);
   return check_launch("dwgram(tma)");
 }
 
 // cfg numbering of dwgram.cu: 1 (64,32,1)  2 (128,64,1)  3 (128,32,1)  4 (128,32,2)
 int launch_tma(int cfg, bool x3, const float* X, int ldx, const float* w9, float* V, int ldv, float* partial, int B, int H,
-               int W, int ctas, cudaStream_t st) {
-#define DWT(CG, CH, NG) (x3 ? launch_tma_t<CG, CH, NG, 2>(X, ldx, w9, V, ldv, partial, B, H, W, ctas, st) \
-                            : launch_tma_t<CG, CH, NG, 1>(X, ldx, w9, V, ldv, partial, B, H, W, ctas, st))
+               int W, int ctas, int gy0, int gy1, cudaStream_t st) {
+#define DWT(CG, CH, NG) (x3 ? launch_tma_t<CG, CH, NG, 2>(X, ldx, w9, V, ldv, partial, B, H, W, ctas, gy0, gy1, st) \
+                            : launch_tma_t<CG, CH, NG, 1>(X, ldx, w9, V, ldv, partial, B, H, W, ctas, gy0, gy1, st))
   switch (cfg) {
     case 1: return DWT(64, 32, 1);
     case 2: return DWT(128, 64, 1);

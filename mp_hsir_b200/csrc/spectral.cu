@@ -444,6 +444,14 @@ extern "C" int mphsir_spectral_fold_fwd(const float* attn, const float* WoutT, f
   return check_launch("spectral_fold");
 }
 
+extern "C" int mphsir_gram_reduce(const float* partial, int n_chunks, float* reduced, int B, int heads, int c, void* stream) {
+  MPHSIR_REQUIRE(partial && reduced && n_chunks > 0 && B > 0 && heads > 0 && c > 0, "gram_reduce: bad arguments");
+  const int per = c * c + 2 * c;
+  dim3 grid((per + 63) / 64, B * heads);
+  gram_reduce_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partial, n_chunks, per, reduced);
+  return check_launch("gram_reduce");
+}
+
 extern "C" int mphsir_spectral_finish_fwd(const float* partial, int n_chunks, float* scratch, const float* temperature,
                                           const float* WoutT, float* Mt, int ldm, long long m_batch_stride, void* bimg,
                                           long long bimg_batch_bytes, float* attn_out, int B, int heads, int c,

@@ -192,27 +192,29 @@ static int launch_wa(const float* qkv, int ldqkv, const float* bias, float* out,
 
 namespace wa {
 int launch_window_attn_mma(const float* qkv, int ldqkv, const float* bias, float* out, int ldo, float* win_mean, int B,
-                           int H, int W, int C, int heads, int shift, int parts, cudaStream_t st);
+                           int H, int W, int C, int heads, int shift, int parts, int mask_H, int mask_y0, cudaStream_t st);
 }
 
 }  // namespace mphsir
 
 using namespace mphsir;
 
-extern "C" int mphsir_window_attn_fwd(const float* qkv, int ldqkv, const float* bias, float* out, int ldo,
-                                      float* win_mean, int B, int H, int W, int C, int heads, int shift,
-                                      int precision, void* stream) {
+extern "C" int mphsir_window_attn_band_fwd(const float* qkv, int ldqkv, const float* bias, float* out, int ldo,
+                                           float* win_mean, int B, int H, int W, int C, int heads, int shift,
+                                           int precision, int mask_H, int mask_y0, void* stream) {
   MPHSIR_REQUIRE(qkv && bias && out && win_mean, "window_attn: null operand");
   MPHSIR_REQUIRE(B > 0 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0, "window_attn: H=%d W=%d must be multiples of 8", H, W);
   MPHSIR_REQUIRE(heads > 0 && C % heads == 0, "window_attn: C=%d not divisible by heads=%d", C, heads);
   MPHSIR_REQUIRE(shift == 0 || shift == 4, "window_attn: shift must be 0 or 4");
   MPHSIR_REQUIRE(ldqkv >= 3 * C && ldqkv % 4 == 0 && ldo >= C, "window_attn: bad leading dimensions");
   MPHSIR_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "window_attn: qkv/bias must be 16-byte aligned");
+  MPHSIR_REQUIRE(mask_H >= 8 && mask_y0 >= 0 && mask_y0 < mask_H, "window_attn: bad mask geometry (mask_H=%d mask_y0=%d)", mask_H, mask_y0);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   MPHSIR_REQUIRE(precision >= MPHSIR_PREC_FP32_SIMT && precision <= MPHSIR_PREC_BF16, "window_attn: unknown precision %d", precision);
   if (precision != MPHSIR_PREC_FP32_SIMT)
     return wa::launch_window_attn_mma(qkv, ldqkv, bias, out, ldo, win_mean, B, H, W, C, heads, shift,
-                                      precision == MPHSIR_PREC_BF16X3 ? 2 : 1, st);
+                                      precision == MPHSIR_PREC_BF16X3 ? 2 : 1, mask_H, mask_y0, st);
+  MPHSIR_REQUIRE(mask_H == H && mask_y0 == 0, "window_attn: row bands of a sharded scene run on the tensor-core precisions only");
   switch (C / heads) {
     case 32: return launch_wa<32>(qkv, ldqkv, bias, out, ldo, win_mean, B, H, W, C, heads, shift, st);
     case 48: return launch_wa<48>(qkv, ldqkv, bias, out, ldo, win_mean, B, H, W, C, heads, shift, st);
@@ -221,4 +223,10 @@ extern "C" int mphsir_window_attn_fwd(const float* qkv, int ldqkv, const float* 
     default:
       MPHSIR_REQUIRE(false, "window_attn: head_dim %d not in {32,48,64,96}", C / heads);
   }
+}
+
+extern "C" int mphsir_window_attn_fwd(const float* qkv, int ldqkv, const float* bias, float* out, int ldo,
+                                      float* win_mean, int B, int H, int W, int C, int heads, int shift,
+                                      int precision, void* stream) {
+  return mphsir_window_attn_band_fwd(qkv, ldqkv, bias, out, ldo, win_mean, B, H, W, C, heads, shift, precision, H, 0, stream);
 }

@@ -45,7 +45,10 @@ template <int HD, int PARTS>
 __global__ void __launch_bounds__(128, (HD <= 48 ? 6 : 4)) window_attn_mma_kernel(const float* __restrict__ qkv, long long ldqkv,
                                                               const float* __restrict__ bias, float* __restrict__ out,
                                                               long long ldo, float* __restrict__ win_mean, int H, int W,
-                                                              int C, int shift) {
+                                                              int C, int shift, int mask_H, int mask_y0) {
+  // mask_H, mask_y0: the Swin mask (net/MP_HSIR.py:643-658) is a function of the row in the shifted coordinates of the WHOLE
+  // image; for a row band of a sharded scene local shifted row ys is row (ys + mask_y0) mod mask_H of the scene (the plain
+  // call passes mask_H = H, mask_y0 = 0)
   constexpr int LD = HD + 8;            // bf16 elements per smem row (16-byte pad: conflict-free ldmatrix)
   constexpr int ARR = 64 * LD;          // elements per operand array
   constexpr int KS = HD / 16;           // k-steps of q k^T
@@ -75,7 +78,9 @@ __global__ void __launch_bounds__(128, (HD <= 48 ? 6 : 4)) window_attn_mma_kerne
     if (y >= H) y -= H;
     if (x >= W) x -= W;
     rows[tid] = (b * H + y) * W + x;
-    const int rh = (ys >= H - 8) + (ys >= H - 4);
+    int ysg = ys + mask_y0;
+    if (ysg >= mask_H) ysg -= mask_H;
+    const int rh = (ysg >= mask_H - 8) + (ysg >= mask_H - 4);
     const int rw = (xs >= W - 8) + (xs >= W - 4);
     label[tid] = shift ? 3 * rh + rw : 0;
   }
@@ -244,7 +249,7 @@ __global__ void __launch_bounds__(128, (HD <= 48 ? 6 : 4)) window_attn_mma_kerne
 
 template <int HD, int PARTS>
 static int launch(const float* qkv, int ldqkv, const float* bias, float* out, int ldo, float* win_mean, int B, int H,
-                  int W, int C, int heads, int shift, cudaStream_t st) {
+                  int W, int C, int heads, int shift, int mask_H, int mask_y0, cudaStream_t st) {
   const size_t smem = (size_t)3 * PARTS * 64 * (HD + 8) * 2 + 2 * 64 * sizeof(int);
   static bool configured = false;
   if (!configured) {
@@ -256,16 +261,16 @@ static int launch(const float* qkv, int ldqkv, const float* bias, float* out, in
     configured = true;
   }
   dim3 grid(B * (H / 8) * (W / 8), heads);
-  window_attn_mma_kernel<HD, PARTS><<<grid, 128, smem, st>>>(qkv, ldqkv, bias, out, ldo, win_mean, H, W, C, shift);
+  window_attn_mma_kernel<HD, PARTS><<<grid, 128, smem, st>>>(qkv, ldqkv, bias, out, ldo, win_mean, H, W, C, shift, mask_H, mask_y0);
   return check_launch("window_attn(mma)");
 }
 
 int launch_window_attn_mma(const float* qkv, int ldqkv, const float* bias, float* out, int ldo, float* win_mean, int B,
-                           int H, int W, int C, int heads, int shift, int parts, cudaStream_t st) {
+                           int H, int W, int C, int heads, int shift, int parts, int mask_H, int mask_y0, cudaStream_t st) {
 #define WA_CASE(HD)                                                                                          \
   case HD:                                                                                                   \
-    return parts == 2 ? launch<HD, 2>(qkv, ldqkv, bias, out, ldo, win_mean, B, H, W, C, heads, shift, st)   \
-                      : launch<HD, 1>(qkv, ldqkv, bias, out, ldo, win_mean, B, H, W, C, heads, shift, st);
+    return parts == 2 ? launch<HD, 2>(qkv, ldqkv, bias, out, ldo, win_mean, B, H, W, C, heads, shift, mask_H, mask_y0, st)   \
+                      : launch<HD, 1>(qkv, ldqkv, bias, out, ldo, win_mean, B, H, W, C, heads, shift, mask_H, mask_y0, st);
   switch (C / heads) {
     WA_CASE(32)
     WA_CASE(48)

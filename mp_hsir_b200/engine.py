@@ -109,16 +109,19 @@ class Workspace:
     """Named, grow-only fp32 device buffers; a forward at a fixed shape allocates nothing after the
     first call (CUDA-graph friendly)."""
 
-    def __init__(self, device):
+    def __init__(self, device, zero_new: bool = False):
         self.device = device
         self.bufs: Dict[str, torch.Tensor] = {}
         self.generation = 0  # bumped whenever a buffer is (re)allocated: captured graphs hold raw pointers
+        # sharded scenes compute on row sub-ranges of their buffers and copy halos in from neighbours; rows nobody has
+        # written yet must at least be finite
+        self._new = torch.zeros if zero_new else torch.empty
 
     def mat(self, name: str, rows: int, cols: int) -> View:
         n = rows * cols
         t = self.bufs.get(name)
         if t is None or t.numel() < n:
-            t = torch.empty(max(n, 1), device=self.device, dtype=torch.float32)
+            t = self._new(max(n, 1), device=self.device, dtype=torch.float32)
             self.bufs[name] = t
             self.generation += 1
         return View(t.data_ptr(), cols, rows, cols, t)
@@ -126,7 +129,7 @@ class Workspace:
     def flat(self, name: str, n: int) -> torch.Tensor:
         t = self.bufs.get(name)
         if t is None or t.numel() < n:
-            t = torch.empty(max(n, 1), device=self.device, dtype=torch.float32)
+            t = self._new(max(n, 1), device=self.device, dtype=torch.float32)
             self.bufs[name] = t
             self.generation += 1
         return t
@@ -169,6 +172,9 @@ class Engine:
         self.cache_prompts = True
         self._tvsp_valid: Dict[str, tuple] = {}
         self._pack_serial = 0
+        # row band of a scene sharded over GPUs (mp_hsir_b200/sharded.py sets it per resolution level): the image the block
+        # kernels see is the band plus an 8-row halo on either side
+        self.band = None
 
     # -- weights -------------------------------------------------------------------------------
     def invalidate(self):
@@ -398,6 +404,8 @@ class Engine:
         ws = self.ws
         N = B * H * W
         c = C // heads
+        if self.band is not None:
+            return self._global_spectral_band(tag, t3, w_dw, temp, out_t, H, W, C, heads)
         if self.prec != lib.PREC_FP32_SIMT and lib.dwgram_supported(C, c):
             v = ws.mat(tag + ".v", N, C)
             nfl, nch = lib.dwgram_partial_floats(B, heads, c, H, W)
@@ -409,6 +417,36 @@ class Engine:
         Mt = self._spectral_attention(tag, dw3.cols_slice(0, C), False, dw3.cols_slice(C, 2 * C), False, temp, out_t,
                                       B, H * W, heads, c)
         return dw3.cols_slice(2 * C, 3 * C), Mt
+
+    def _global_spectral_band(self, tag: str, t3: View, w_dw, temp, out_t, H: int, W: int, C: int, heads: int):
+        """`_global_spectral` on a row band: depthwise conv + V on the rows [a, b) this rank may touch (own rows + halo; at
+        the scene's top / bottom the view ends at the scene edge, so the kernels' zero padding IS the conv padding), Gram
+        statistics on the rank's OWN rows only, summed over the ranks (ONE small all-reduce per block: heads*(c*c+2c)
+        floats), then the softmax / fold on every rank (net/MP_HSIR.py:104-113 reduce over the whole scene)."""
+        ws, bd = self.ws, self.band
+        c = C // heads
+        a, b = bd.a, bd.b
+        v = ws.mat(tag + ".v", H * W, C)
+        t3v, vv = t3.rows_slice(a * W, b * W), v.rows_slice(a * W, b * W)
+        own0 = bd.halo - a
+        if lib.dwgram_supported(C, c):
+            nfl, nch = lib.dwgram_partial_floats(1, heads, c, b - a, W)
+            partial = ws.flat(tag + ".partial", nfl)
+            lib.dwgram(t3v, w_dw, vv, partial, 1, b - a, W, C, heads, self.prec, gram_rows=(own0, own0 + bd.Hb))
+            vout = v
+        else:
+            dw3 = ws.mat(tag + ".dw3", H * W, 3 * C)
+            lib.dwconv3x3(t3v, w_dw, dw3.rows_slice(a * W, b * W), 1, b - a, W, 3 * C)
+            own = dw3.rows_slice(bd.halo * W, (bd.halo + bd.Hb) * W)
+            nfl, nch = lib.gram_partial_floats(1, heads, c, bd.Hb * W)
+            partial = ws.flat(tag + ".partial", nfl)
+            lib.gram_partial(own.cols_slice(0, C), False, own.cols_slice(C, 2 * C), False, partial, 1, bd.Hb * W, heads, c)
+            vout = dw3.cols_slice(2 * C, 3 * C)
+        per = heads * (c * c + 2 * c)
+        gsum = ws.flat(tag + ".gsum_rank", per)
+        lib.gram_reduce(partial, nch, gsum, 1, heads, c)
+        bd.comm.all_reduce(gsum[:per])
+        return vout, self._spectral_finish(tag, gsum, 1, temp, out_t, 1, heads, c)
 
     def _pgsstb(self, w: dict, st: Stage, shift: int, x: View, out: View, res2: Optional[View], B: int, H: int,
                 W: int, row_scales=None, taps: Optional[dict] = None):
@@ -424,11 +462,17 @@ class Engine:
         gate = ws.flat("gate", B_ * C)
         s1 = None if row_scales is None else row_scales[0]
         s2 = None if row_scales is None else row_scales[1]
+        mask_H, mask_y0 = None, 0
+        if self.band is not None:
+            # row band: refresh the 8-row halos of the block input from the neighbour ranks (cyclic: the roll of :672 wraps
+            # between the last and the first band); everything below is then local except the Gram all-reduce
+            self.band.exchange(x)
+            mask_H, mask_y0 = self.band.Hg, self.band.y0
 
         # LN1 + qkv projection (net/MP_HSIR.py:667, :195)
         self._gemm(x, w["qkv_w"], qkv, 3 * C, ln=w["ln1"], bias=w["qkv_b"])
         # shifted-window attention core + per-window mean (:671-683, :198-215)
-        lib.window_attn(qkv, w["rpb"], core, wmean, B, H, W, C, heads, shift, precision=self.prec)
+        lib.window_attn(qkv, w["rpb"], core, wmean, B, H, W, C, heads, shift, precision=self.prec, mask_H=mask_H, mask_y0=mask_y0)
         # local spectral gate (:132-152)
         if "gate_cat_w" not in w:
             pass  # un-folded weights (trainer): the gate is computed below from the window mean of sa
@@ -502,7 +546,11 @@ class Engine:
         hin = self.ws.mat(tag + ".hin", N, 2 * hp)
         hg = self.ws.mat(tag + ".hg", N, hp)
         self._gemm(x, w["pin_w"], hin, 2 * hp, ln=ln)
-        lib.dwconv3x3(hin, w["ffn_dw"], hg, B, H, W, 2 * hp, gate_half=hp)
+        if self.band is not None:   # the rows this rank may touch; the view ends at the scene edge on the outer ranks
+            a, b = self.band.a, self.band.b
+            lib.dwconv3x3(hin.rows_slice(a * W, b * W), w["ffn_dw"], hg.rows_slice(a * W, b * W), 1, b - a, W, 2 * hp, gate_half=hp)
+        else:
+            lib.dwconv3x3(hin, w["ffn_dw"], hg, B, H, W, 2 * hp, gate_half=hp)
         self._gemm(hg, w["pout_w"], out, D, epi=lib.EPI_RESIDUAL, res1=x)
 
     def _tvsp_key(self, task_key, B: int, Hs: int, Ws: int, out: View):

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Optional
+from typing import Optional, Tuple
 
 import torch
 
@@ -113,6 +113,9 @@ SIGNATURES = {
     "mphsir_mlp_fwd": (_I, [C.POINTER(MlpParams), _VP]),
     "mphsir_conv3x3_fwd": (_I, [C.POINTER(ConvParams), _VP]),
     "mphsir_window_attn_fwd": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
+    "mphsir_window_attn_band_fwd": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP]),
+    "mphsir_dwgram_band_fwd": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _VP]),
+    "mphsir_gram_reduce": (_I, [_VP, _I, _VP, _I, _I, _I, _VP]),
     "mphsir_local_gate_fwd": (_I, [C.POINTER(LocalGateParams), _VP]),
     "mphsir_local_gate_tail_fwd": (_I, [_VP, _I, C.POINTER(LocalGateParams), _VP]),
     "mphsir_dwconv3x3_fwd": (_I, [_VP, _I, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
@@ -431,11 +434,14 @@ def conv3x3(X: View, Wt, Y_ptr: int, ldy: int, B: int, H: int, W: int, Cin: int,
 
 
 def window_attn(qkv: View, bias: torch.Tensor, out: View, win_mean: torch.Tensor, B: int, H: int, W: int,
-                Cc: int, heads: int, shift: int, precision: int = 0) -> None:
+                Cc: int, heads: int, shift: int, precision: int = 0, mask_H: Optional[int] = None, mask_y0: int = 0) -> None:
+    """mask_H / mask_y0: row band of a sharded scene (mphsir_window_attn_band_fwd); default = the whole image."""
     n = B * H * W
+    mH = H if mask_H is None else mask_H
     _launch("window_attn_fwd",
-            lambda: load().mphsir_window_attn_fwd(qkv.ptr, qkv.ld, bias.data_ptr(), out.ptr, out.ld,
-                                                  win_mean.data_ptr(), B, H, W, Cc, heads, shift, precision, stream_ptr()),
+            lambda: load().mphsir_window_attn_band_fwd(qkv.ptr, qkv.ld, bias.data_ptr(), out.ptr, out.ld,
+                                                       win_mean.data_ptr(), B, H, W, Cc, heads, shift, precision, mH, mask_y0,
+                                                       stream_ptr()),
             lambda: (4.0 * n * 64 * Cc, 4.0 * (4 * n * Cc + n // 64 * Cc), ("window_attn", "window_attn_mma3", "window_attn_mma1")[precision]))
 
 
@@ -511,12 +517,22 @@ def dwgram_partial_floats(B: int, heads: int, c: int, H: int, W: int):
 
 
 def dwgram(X: View, w9: torch.Tensor, Vout: View, partial: torch.Tensor, B: int, H: int, W: int, Cc: int, heads: int,
-           precision: int) -> None:
+           precision: int, gram_rows: Optional[Tuple[int, int]] = None) -> None:
+    """gram_rows: (y0, y1) tile-aligned row range whose tiles enter the Gram statistics (row band of a sharded scene);
+    default = every row."""
     n = B * H * W
+    gy0, gy1 = (0, H) if gram_rows is None else gram_rows
     _launch("dwgram_fwd",
-            lambda: load().mphsir_dwgram_fwd(X.ptr, X.ld, w9.data_ptr(), Vout.ptr, Vout.ld, partial.data_ptr(), B, H, W,
-                                             Cc, heads, precision, stream_ptr()),
+            lambda: load().mphsir_dwgram_band_fwd(X.ptr, X.ld, w9.data_ptr(), Vout.ptr, Vout.ld, partial.data_ptr(), B, H, W,
+                                                  Cc, heads, precision, gy0, gy1, stream_ptr()),
             lambda: (2.0 * n * (27 * Cc + Cc * (Cc // heads + 2)), 16.0 * n * Cc, ("", "dwgram3", "dwgram1")[precision]))
+
+
+def gram_reduce(partial: torch.Tensor, n_chunks: int, reduced: torch.Tensor, B: int, heads: int, c: int) -> None:
+    """reduced[B*heads, c*c+2c] = sum over the n_chunks partials (the per-rank statistics of a sharded scene)"""
+    _launch("gram_reduce", lambda: load().mphsir_gram_reduce(partial.data_ptr(), n_chunks, reduced.data_ptr(), B, heads, c,
+                                                             stream_ptr()),
+            lambda: (0.0, 4.0 * B * heads * (n_chunks + 1) * (c * c + 2 * c), "gram_reduce"))
 
 
 def spectral_finish(partial: torch.Tensor, n_chunks: int, scratch: torch.Tensor, temperature: torch.Tensor,
