@@ -475,6 +475,168 @@ def run_train(args, embedded: bool = False):
     return line
 
 
+def inference_roofline(agg, passes: int, precision: str, workload: str):
+    """dominant kernel family of an instrumented forward -> (roofline object, per-kernel breakdown)"""
+    pk = peaks()
+    total_ms = sum(a["ms"] for a in agg.values())
+    top = max(agg.items(), key=lambda kv: kv[1]["ms"])
+    breakdown = {k: {"ms_per_step": round(a["ms"] / passes, 3), "share": round(a["ms"] / total_ms, 4),
+                     "launches_per_step": a["launches"] // passes,
+                     "tflops": round(a["flops"] / (a["ms"] * 1e-3) / 1e12, 2) if a["ms"] else 0,
+                     "gbs": round(a["bytes"] / (a["ms"] * 1e-3) / 1e9, 1) if a["ms"] else 0}
+                 for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+    # kernel FAMILIES: every tag is one __global__ template; the tcgen05 GEMM engine (all prologue/epilogue
+    # variants of gemm_tc_kernel, incl. the implicit-GEMM convs) is reported as one kernel
+    def family(tag):
+        return "gemm_tc_kernel" if tag.startswith(("gemm_tc", "conv3x3_tc")) else tag
+    fam = {}
+    for k, a in agg.items():
+        f = fam.setdefault(family(k), {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        for key in f:
+            f[key] += a[key]
+    name, a = max(fam.items(), key=lambda kv: kv[1]["ms"])
+    sec = a["ms"] * 1e-3
+    tensor_flops = a["flops"] * (3.0 if (name == "gemm_tc_kernel" and precision == "fp32") else 1.0)
+    t_hbm = a["bytes"] / (pk["hbm_gbs"] * 1e9)
+    t_tensor = tensor_flops / (pk["tf_sustained"] * 1e12)
+    if t_tensor > t_hbm:
+        ach = tensor_flops / sec / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["tf_sustained"], "traffic": None}
+    else:
+        ach = a["bytes"] / sec / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                "traffic": None}
+    tr_ = ncu_traffic(workload, name) if precision == "fp32" else None
+    if tr_ is not None:
+        roof["traffic"] = tr_["bytes_per_launch"]
+        roof["traffic_source"] = f"{tr_['source']}: ncu dram read+write bytes / launch over the {tr_['launches']} launches of one step"
+        roof["algorithmic_bytes_per_launch"] = a["bytes"] / a["launches"]
+    roof.update({"kernel": name, "share_of_step": round(a["ms"] / total_ms, 4), "launches": a["launches"] // passes,
+                 "avg_launch_ms": a["ms"] / a["launches"],
+                 "algorithmic_bytes_per_step": a["bytes"] / passes, "algorithmic_flops_per_step": a["flops"] / passes,
+                 "bf16_mma_flops_per_step": tensor_flops / passes,
+                 "roofline_ms_per_step": {"hbm": 1e3 * t_hbm / passes, "tensor": 1e3 * t_tensor / passes},
+                 "peak_source": pk["source"] + " (MEASURED_PEAKS.json; sustained bf16 figure: kernel timed inside a long step)",
+                 "timing": "CUDA events around each launch on the launching stream, separate instrumented pass",
+                 "note": "fp32 mode issues 3 bf16 MMAs per product (hi*hi+hi*lo+lo*hi); bytes = fp32 operands "
+                         "read/written once (SURVEY 8d materialise-once model)"})
+    return roof, breakdown
+
+
+def run_sharded(args):
+    """`--workload cube512 --shard rows`: ONE 31x512x512 scene per step, its rows split over all ranks (BASELINE config 3 as
+    specified; mp_hsir_b200/sharded.py) — strong scaling: value = 1 / (time per scene).  Collectives on the data path:
+    neighbour halo send/recv before every block / conv, one all-reduce of the Gram statistics per block."""
+    import torch.distributed as dist
+    from mp_hsir_b200 import lib
+    from mp_hsir_b200.parallel import max_over_ranks as _max
+    from mp_hsir_b200.sharded import NcclComm, ShardedEngine, ThreadComm, _ThreadWorld, band_rows
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    model, shape, unit, units, _, _ = WORKLOADS[args.workload]
+    precision = args.precision
+    cfg, net = build_net(model, device)
+    net.set_precision(precision)
+    comm = NcclComm() if world > 1 else ThreadComm(_ThreadWorld(1), 0)
+    eng = ShardedEngine(net, comm)
+    H = shape[2]
+    x_full, clean, tid_host = make_input(shape, 0, args.workload)        # every rank derives the SAME scene from the seed
+    r0, r1 = band_rows(H, rank, world)
+    x_host = x_full[:, :, r0:r1].contiguous().pin_memory()
+    x_dev = x_host.to(device)
+    out_host = torch.empty_like(x_host).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            y = eng.forward_band(x_dev, tid_host, H)
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+            time.sleep(0.3)
+        n0 = lib.LAUNCHES
+        c0 = (comm.halo_exchanges, comm.all_reduces)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            y = eng.forward_band(x_dev, tid_host, H)
+        e1.record()
+        barrier()
+        launches = lib.LAUNCHES - n0
+        comm_per_step = ((comm.halo_exchanges - c0[0]) // args.steps, (comm.all_reduces - c0[1]) // args.steps)
+        ms_dev = _max(e0.elapsed_time(e1), device)
+        # parity: assemble the scene on rank 0 and hold it against the unmodified reference's output
+        if world > 1:
+            parts = [torch.empty_like(y) for _ in range(world)] if rank == 0 else None
+            dist.gather(y, parts, dst=0)
+            y_full = torch.cat(parts, dim=2) if rank == 0 else None
+        else:
+            y_full = y
+        parity = golden_check(args.workload, y_full, clean, precision) if rank == 0 else None
+        # e2e: every rank's band comes from pinned host memory and goes back to it, inside the timed region
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        f0.record()
+        for _ in range(args.steps):
+            out_host.copy_(eng.forward_band(x_host.to(device, non_blocking=True), tid_host, H), non_blocking=True)
+        f1.record()
+        barrier()
+        ms_e2e = _max(f0.elapsed_time(f1), device)
+        clocks = sampler.stop() if sampler else None
+        roof = breakdown = None
+        if not args.no_roofline:
+            # the instrumented pass contains collectives: every rank takes it, rank 0 with per-launch events
+            if rank == 0:
+                lib.PROFILER = lib.Profiler()
+            eng.forward_band(x_dev, tid_host, H)
+            if rank == 0:
+                agg = lib.PROFILER.summary()
+                lib.PROFILER = None
+                roof, breakdown = inference_roofline(agg, 1, precision, args.workload)
+                roof["traffic"] = None   # the committed ncu traffic capture is of the unsharded launch shapes
+            barrier()
+    ws_bytes = eng.ws.bytes()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    cb = None
+    if not args.no_cpu_baseline:
+        cb, _ = cpu_baseline(model, shape, float(units), unit, workload=args.workload)
+    line = {
+        "metric": METRIC[args.workload], "value": args.steps / (ms_dev * 1e-3), "unit": unit, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": {"fp32": "f32", "bf16": "bf16"}[precision], "data": "synthetic",
+        "config": {"workload": args.workload, "shard": "rows", "model": model, "scene": list(shape),
+                   "rows_per_gpu": (r1 - r0), "halo_rows": 8, "task_id": tid_host.tolist(), "precision": precision,
+                   "parallelism": f"ONE scene per step, rows split over {world} GPU(s): {comm_per_step[0]} neighbour halo exchanges "
+                                  f"(send/recv, 8 rows each way) + {comm_per_step[1]} all-reduces of the Gram statistics "
+                                  f"(<= 9.2 KB) per scene; exact (equals the single-GPU forward up to summation order)",
+                   "collectives": comm.name,
+                   "weights": "random-init (name-seeded synthetic), reference architecture",
+                   "l2": "per-step working set exceeds the 126 MB L2 (GBs of activations); no explicit flush",
+                   "cuda_graph": False, "output_check": parity, "workspace_bytes_per_gpu": ws_bytes},
+        "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": unit, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": x_full.numel() * 4 + tid_host.numel() * 8, "d2h_bytes_per_step": x_full.numel() * 4},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cb, "kernels": breakdown,
+    }
+    print(json.dumps(line))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -515,6 +677,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="cube512 only: skip the embedded train64 measurement")
+    ap.add_argument("--shard", default="cubes", choices=["cubes", "rows"],
+                    help="cube512 with N GPUs: 'cubes' = one independent cube per GPU per step (weak scaling, default); "
+                         "'rows' = ONE scene per step, its rows split over the GPUs with halo exchange + Gram all-reduce "
+                         "(strong scaling, BASELINE config 3 as specified)")
     ap.add_argument("--reference-budget-s", type=float, default=120.0,
                     help="--impl reference: stop timing further steps once this many seconds of timed work are spent")
     ap.add_argument("--precision", default=None, choices=["fp32", "fp32_exact", "bf16"],
@@ -533,6 +699,10 @@ def main():
         return run_reference(args)
     if args.workload == "train64":
         return run_train(args)
+    if args.shard == "rows":
+        if args.workload != "cube512" or args.precision == "fp32_exact":
+            raise SystemExit("--shard rows applies to --workload cube512 with a tensor-core precision")
+        return run_sharded(args)
 
     import torch.distributed as dist
     from mp_hsir_b200 import lib
@@ -642,56 +812,12 @@ def main():
         # ---- roofline: instrumented pass (outside the timed region) -----------------------------
         roof, breakdown = None, None
         if rank == 0 and not args.no_roofline:
-            pk = peaks()
             lib.PROFILER = lib.Profiler()
             for _ in range(min(args.steps, 3)):
                 net(x_dev, tid_dev)
             agg = lib.PROFILER.summary()
             lib.PROFILER = None
-            passes = min(args.steps, 3)
-            total_ms = sum(a["ms"] for a in agg.values())
-            top = max(agg.items(), key=lambda kv: kv[1]["ms"])
-            breakdown = {k: {"ms_per_step": round(a["ms"] / passes, 3), "share": round(a["ms"] / total_ms, 4),
-                             "launches_per_step": a["launches"] // passes,
-                             "tflops": round(a["flops"] / (a["ms"] * 1e-3) / 1e12, 2) if a["ms"] else 0,
-                             "gbs": round(a["bytes"] / (a["ms"] * 1e-3) / 1e9, 1) if a["ms"] else 0}
-                         for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
-            # kernel FAMILIES: every tag is one __global__ template; the tcgen05 GEMM engine (all prologue/epilogue
-            # variants of gemm_tc_kernel, incl. the implicit-GEMM convs) is reported as one kernel
-            def family(tag):
-                return "gemm_tc_kernel" if tag.startswith(("gemm_tc", "conv3x3_tc")) else tag
-            fam = {}
-            for k, a in agg.items():
-                f = fam.setdefault(family(k), {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
-                for key in f:
-                    f[key] += a[key]
-            name, a = max(fam.items(), key=lambda kv: kv[1]["ms"])
-            sec = a["ms"] * 1e-3
-            tensor_flops = a["flops"] * (3.0 if (name == "gemm_tc_kernel" and precision == "fp32") else 1.0)
-            t_hbm = a["bytes"] / (pk["hbm_gbs"] * 1e9)
-            t_tensor = tensor_flops / (pk["tf_sustained"] * 1e12)
-            if t_tensor > t_hbm:
-                ach = tensor_flops / sec / 1e12
-                roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                        "frac": ach / pk["tf_sustained"], "traffic": None}
-            else:
-                ach = a["bytes"] / sec / 1e9
-                roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                        "traffic": None}
-            tr_ = ncu_traffic(args.workload, name) if precision == "fp32" else None
-            if tr_ is not None:
-                roof["traffic"] = tr_["bytes_per_launch"]
-                roof["traffic_source"] = f"{tr_['source']}: ncu dram read+write bytes / launch over the {tr_['launches']} launches of one step"
-                roof["algorithmic_bytes_per_launch"] = a["bytes"] / a["launches"]
-            roof.update({"kernel": name, "share_of_step": round(a["ms"] / total_ms, 4), "launches": a["launches"] // passes,
-                         "avg_launch_ms": a["ms"] / a["launches"],
-                         "algorithmic_bytes_per_step": a["bytes"] / passes, "algorithmic_flops_per_step": a["flops"] / passes,
-                         "bf16_mma_flops_per_step": tensor_flops / passes,
-                         "roofline_ms_per_step": {"hbm": 1e3 * t_hbm / passes, "tensor": 1e3 * t_tensor / passes},
-                         "peak_source": pk["source"] + " (MEASURED_PEAKS.json; sustained bf16 figure: kernel timed inside a long step)",
-                         "timing": "CUDA events around each launch on the launching stream, separate instrumented pass",
-                         "note": "fp32 mode issues 3 bf16 MMAs per product (hi*hi+hi*lo+lo*hi); bytes = fp32 operands "
-                                 "read/written once (SURVEY 8d materialise-once model)"})
+            roof, breakdown = inference_roofline(agg, min(args.steps, 3), precision, args.workload)
 
     # BASELINE.json's metric has two halves: "HSI cubes/s (31x512x512 infer) & train patches/s".  The default run reports
     # the second half as a sub-object of the same line (same contract fields, its own roofline / e2e / cpu_baseline).

@@ -161,11 +161,17 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t*
         uint32_t r[16];
         tw = TC_T0();
         tmem_ld16_nowait(taddr, r);
-        // the box written two chunks ago has been read out by its store; fetch the residual of the next chunk
+        // This chunk overwrites box s, last stored from two chunks ago: ONE store (the previous chunk's, from box s^1) may
+        // still be reading.  Only when the next chunk needs its residual TMA-loaded into box s^1 must that store have
+        // finished too — waiting for it unconditionally serialised every chunk behind the previous chunk's store.
         if (lane == 0) {
-          if (ck > 0) bulk_wait_group_read<0>();
           int t2 = tile, ti2 = tit, ps2 = pass, c2 = c0;
-          if (advance(t2, ti2, ps2, c2) && needs_res(ps2, c2)) issue_res(t2, ps2, c2, s ^ 1);
+          const bool next_res = advance(t2, ti2, ps2, c2) && needs_res(ps2, c2);
+          if (ck > 0) {
+            if (next_res) bulk_wait_group_read<0>();
+            else bulk_wait_group_read<1>();
+          }
+          if (next_res) issue_res(t2, ps2, c2, s ^ 1);
         }
         if (with_res) {
           mbar_wait(rbar0 + 8 * s, (rph >> s) & 1u);
@@ -730,7 +736,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           // the whole row (K <= 128) is resident in the staging slabs: statistics straight from smem
           for (int s = 0; s < Ks; ++s) {
             const int st = (a_it + s) % p.na;
+            const long long tws = TC_T0();
             mbar_wait(smem_u32(&sm->stage_full[st]), ((a_it + s) / p.na) & 1);
+            TC_ACC(t_ld, tws);
             const int k = s * 64 + chunk * 8;
             if (k < p.Ka) {
 #pragma unroll

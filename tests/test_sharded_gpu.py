@@ -28,11 +28,13 @@ def net_for(model, precision="fp32"):
     return _NETS[(model, precision)]
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 4e-3)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 1e-2)])
 @pytest.mark.parametrize("world", [1, 2, 4])
 def test_virtual_ranks_match_single_gpu(world, precision, tol):
     """128x96 scene, task 2: world = 1 exercises the geometry alone (the halos are the band's own cyclic rows), 2 the
-    prev == next case, 4 has inner ranks.  fp32 mode: same kernels, only the Gram summation order differs."""
+    prev == next case, 4 has inner ranks.  fp32 mode: same kernels, only the Gram summation order differs; bf16 mode rounds
+    every GEMM operand to 8 bits, so a last-bit change of a Gram sum moves the result like the precision mode itself
+    (bound = the mode's north_star bound)."""
     net = net_for("natural", precision)
     x = synthetic_input((1, 31, 128, 96), seed=31).cuda()
     tid = torch.tensor([2]).cuda()
