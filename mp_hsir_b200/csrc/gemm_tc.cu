@@ -83,7 +83,10 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t*
                                              int npass, int warp, int lane) {
   constexpr bool RES = EPI == MPHSIR_EPI_RESIDUAL, PROJ = EPI == MPHSIR_EPI_PROJ;
   const int quad = warp & 3, half = (warp - 2) >> 2, ew = warp - 2;
-  uint8_t* const slot_base = eslots + (size_t)ew * 8192;          // box k at slot_base + 4096 * k
+  // p.ebox boxes of 4 KB per warp: 2 (default), or 1 for BIAS epilogues of K > 64 GEMMs — the 32 KB saved buy a fourth
+  // A-ring slot, i.e. a whole K = 128 tile of load/convert lookahead (role counters: the converters starved on TMA
+  // latency with one slab of lookahead while the epilogue warps idled half of the time)
+  uint8_t* const slot_base = eslots + (size_t)ew * 4096 * p.ebox;   // box k at slot_base + 4096 * k
   const uint32_t slot_a0 = smem_u32(slot_base);
   const uint32_t rbar0 = smem_u32(&sm->res_full[2 * ew]);          // barrier k at rbar0 + 8 * k
   uint32_t rph = 0u;                                                // bit k: phase of barrier k
@@ -153,7 +156,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t*
       tc_fence_after();
       const int ncols_pass = ncols_of(pass);
       for (int c0 = half * 32; c0 < ncols_pass; c0 += 64, ++ck) {
-        const int s = ck & 1;
+        const int s = p.ebox == 2 ? (ck & 1) : 0;
         const int n0 = pass * PASS_COLS + c0;
         const bool with_res = needs_res(pass, c0);
         const bool left = PROJ && n0 < p.n_split;
@@ -168,7 +171,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t*
           int t2 = tile, ti2 = tit, ps2 = pass, c2 = c0;
           const bool next_res = advance(t2, ti2, ps2, c2) && needs_res(ps2, c2);
           if (ck > 0) {
-            if (next_res) bulk_wait_group_read<0>();
+            if (next_res || p.ebox == 1) bulk_wait_group_read<0>();
             else bulk_wait_group_read<1>();
           }
           if (next_res) issue_res(t2, ps2, c2, s ^ 1);
@@ -925,9 +928,9 @@ __global__ void __launch_bounds__(256) pack_bimg_kernel(const float* __restrict_
   }
 }
 
-static size_t smem_bytes(int na, int nb, int parts, int tepi) {
+static size_t smem_bytes(int na, int nb, int parts, int tepi, int ebox) {
   return 1024 + (size_t)na * STAGE_BYTES + (size_t)nb * BBLK_BYTES * parts +
-         (size_t)kEpiWarps * STG_FLOATS * sizeof(float) * (tepi ? 2 : 1);
+         (size_t)kEpiWarps * STG_FLOATS * sizeof(float) * (tepi ? ebox : 1);
 }
 
 template <int EPI, bool LN>
@@ -1042,6 +1045,8 @@ static bool make_epi_map(CUtensorMap* tm, const float* base, long long ld, int c
 static long long* g_dbg = nullptr;
 static int g_tepi_enabled = 1;
 void set_tepi_enabled(int on) { g_tepi_enabled = on; }
+static int g_ebox1_enabled = 1;
+void set_ebox1_enabled(int on) { g_ebox1_enabled = on; }
 static int g_cluster_enabled = 0;  // measured: multicast halves L2 weight reads but the lock-step pairs cost ~4% in-network
 void set_cluster_enabled(int on) { g_cluster_enabled = on; }
 void set_debug_buffer(long long* p) { g_dbg = p; }
@@ -1072,7 +1077,12 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
   //   with the TMA epilogue (64 KB of boxes):  bf16x3: A 3 x 32 KB + B 2 x 32 KB   bf16x1: A 3 x 32 KB + B 4 x 16 KB
   a.na = a.parts == 2 ? 3 : (a.tepi ? 3 : 4);
   a.nb = a.parts == 2 ? (a.tepi ? 2 : 3) : 4;
-  const size_t smem = smem_bytes(a.na, a.nb, a.parts, a.tepi);
+  a.ebox = 2;
+  if (a.tepi && a.epi == MPHSIR_EPI_BIAS && a.ks == 2 && g_ebox1_enabled) {
+    a.ebox = 1;   // one store box per epilogue warp -> A ring of 4 slots = two whole K = 128 tiles
+    a.na = 4;
+  }
+  const size_t smem = smem_bytes(a.na, a.nb, a.parts, a.tepi, a.ebox);
   a.a_mode = A_ROWCOPY;
   a.seg = 64;
   if (conv) {
@@ -1111,6 +1121,7 @@ using namespace mphsir;
 extern "C" MPHSIR_API void mphsir_debug_tc_counters(long long* buf) { tc::set_debug_buffer(buf); }
 extern "C" MPHSIR_API void mphsir_debug_tc_cluster(int enabled) { tc::set_cluster_enabled(enabled); }
 extern "C" MPHSIR_API void mphsir_debug_tc_tma_epilogue(int enabled) { tc::set_tepi_enabled(enabled); }
+extern "C" MPHSIR_API void mphsir_debug_tc_ebox1(int enabled) { tc::set_ebox1_enabled(enabled); }
 
 extern "C" size_t mphsir_bimg_bytes(int N, int K) {
   const int Np = (N + 15) / 16 * 16, Ks = (K + 63) / 64;

@@ -24,6 +24,7 @@ struct TcArgs {
   alignas(64) CUtensorMap tmY2; //   EPI_PROJ: second output (columns >= n_split)
   alignas(64) CUtensorMap tmR;  //   residual res1 (loaded into the box the result is stored from)
   int tepi;                     // 1: TMA-fed / TMA-drained epilogue (BIAS, RESIDUAL, PROJ), 0: register-staged epilogue
+  int ebox;                     // tepi: 4 KB boxes per epilogue warp (2, or 1 when the smem buys a deeper A ring)
   int a_mode;                   // A_*
   int seg;                      // floats per TMA box row (64 for GEMMs, gcd(Cin,64) for convs)
   int box_rows;                 // conv: pixels per TMA box (= rows of a tile: min(128, H*W))
@@ -67,6 +68,7 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st);
 void set_debug_buffer(long long* p);
 void set_cluster_enabled(int on);
 void set_tepi_enabled(int on);
+void set_ebox1_enabled(int on);
 
 }  // namespace tc
 }  // namespace mphsir
