@@ -458,6 +458,26 @@ MPHSIR_API int mphsir_l1_clamp_loss(const float* out, const float* clean, float*
 MPHSIR_API int mphsir_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                                  float eps, float weight_decay, int step, float grad_scale, const float* dyn, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Around the hot path: evaluation metrics and training-time degradations on the device.
+ *
+ * mphsir_psnr_ssim: utils/val_utils.py:49-69 (compute_psnr_ssim) per NCHW plane, on clip(.,0,1), data_range 1.
+ *   sums[2*p]   = sum over the plane of (x-y)^2                         -> PSNR_p = 10 log10(H*W / sums[2p])
+ *   sums[2*p+1] = sum of the SSIM index over the (H-6)*(W-6) whole 7x7 windows (skimage defaults: uniform window,
+ *                 sample covariance, K1 0.01, K2 0.03; border crop 3)    -> SSIM_p = sums[2p+1] / ((H-6)(W-6))
+ *   fp64 accumulation; sums [2*planes] is zeroed by the call.
+ * mphsir_plane_nonzero: nonzero[p] = 1 if plane p has any non-zero element (compute_psnr_ssim2, :88: band-miss eval).
+ * mphsir_degrade: out = clean * keep[b,c] * (u > mask_ratio[b]) + sigma[b,c] * n, u ~ U[0,1), n ~ N(0,1) drawn from
+ *   Philox4x32-10 keyed by `seed`, counter = element pair index (utils/degradation_utils.py:25-39, :227-233, :275-284;
+ *   one degradation per sample as utils/dataset_utils.py:128-146 — the per-sample / per-band parameters are drawn by
+ *   the host and passed as the three small arrays).
+ * ------------------------------------------------------------------------------------- */
+MPHSIR_API int mphsir_psnr_ssim(const float* restored, const float* clean, int planes, int H, int W, double* sums, void* stream);
+MPHSIR_API int mphsir_plane_nonzero(const float* X, int planes, long long hw, int* nonzero, void* stream);
+MPHSIR_API int mphsir_degrade(const float* clean, float* out, int B, int C, long long hw, const float* sigma /* [B*C] */,
+                              const float* keep /* [B*C] */, const float* mask_ratio /* [B] */, unsigned long long seed,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

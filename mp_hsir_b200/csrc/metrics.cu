@@ -1,0 +1,211 @@
+// Evaluation metrics and training-time degradations on the device: what wraps the hot path in
+// test.py / train.py once the model itself runs at tens of cubes per second.
+//
+//  * psnr_ssim_kernel — utils/val_utils.py:49-69 (compute_psnr_ssim): per band, on clip(.,0,1), data_range 1:
+//      PSNR  = 10 log10(1 / mean((x-y)^2))                     (skimage.metrics.peak_signal_noise_ratio)
+//      SSIM  = mean over the (H-6)x(W-6) windows that fit the image of
+//              ((2 ux uy + C1)(2 vxy + C2)) / ((ux^2 + uy^2 + C1)(vx + vy + C2)),   C1 = 0.01^2, C2 = 0.03^2,
+//              7x7 uniform window, sample covariance (x 49/48)   (skimage.metrics.structural_similarity defaults:
+//              win_size 7, use_sample_covariance, the 3-pixel border of the filtered image is cropped, so only whole
+//              windows contribute and the filter's border mode never matters)
+//    One pass over the two NCHW planes: a CTA stages a (32+6) x (128+6) tile of both images in shared memory, every
+//    thread slides a 7-row ring of horizontal 7-sums (x, y, xx, yy, xy) down one window column.  Sums in fp64 (the
+//    variance terms cancel against C2 = 9e-4).  Output: per plane { sum (x-y)^2, sum of window SSIMs }.  HBM-bound:
+//    8 bytes per pixel.
+//  * degrade_kernel — the array-only degradations train.py draws per sample (utils/dataset_utils.py:128-146 ->
+//    utils/degradation_utils.py:25-39 Gaussian / non-iid noise, :227-233 random mask, :275-284 band loss) as ONE
+//    elementwise pass:  out = clean * keep[b,c] * (u > mask_ratio[b]) + sigma[b,c] * n,  u ~ U[0,1), n ~ N(0,1) from a
+//    counter-based Philox4x32-10 stream keyed by (seed, element index) — reproducible, no state, any launch shape.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace mphsir {
+namespace metrics {
+
+constexpr int TW = 128, TH = 32, WIN = 7;
+constexpr int SW = TW + WIN - 1, SH = TH + WIN - 1;
+
+__global__ void __launch_bounds__(TW) psnr_ssim_kernel(const float* __restrict__ X, const float* __restrict__ Y, int H, int W,
+                                                       double* __restrict__ sums) {
+  __shared__ float sx[SH][SW + 1];
+  __shared__ float sy[SH][SW + 1];
+  const int plane = blockIdx.z;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const float* xp = X + (size_t)plane * H * W;
+  const float* yp = Y + (size_t)plane * H * W;
+  const int t = threadIdx.x;
+
+  double sse = 0.0;
+  for (int idx = t; idx < SH * SW; idx += TW) {
+    const int r = idx / SW, c = idx - r * SW;
+    const int gy = y0 + r, gx = x0 + c;
+    float a = 0.f, b = 0.f;
+    if (gy < H && gx < W) {
+      a = fminf(fmaxf(__ldg(xp + (size_t)gy * W + gx), 0.f), 1.f);   // np.clip(., 0, 1), val_utils.py:51-52
+      b = fminf(fmaxf(__ldg(yp + (size_t)gy * W + gx), 0.f), 1.f);
+      if (r < TH && c < TW) {  // the tile's own pixels: every pixel of the image is owned by exactly one tile
+        const double d = (double)a - (double)b;
+        sse += d * d;
+      }
+    }
+    sx[r][c] = a;
+    sy[r][c] = b;
+  }
+  __syncthreads();
+
+  // window column x0 + t: top-left corners (y0 + r, x0 + t), r = 0..TH-1, valid while the window fits the image
+  double ssim = 0.0;
+  if (x0 + t + WIN <= W) {
+    double ring[WIN][5];
+    double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+    const double C1 = 0.01 * 0.01, C2 = 0.03 * 0.03, NP = 49.0, COVN = 49.0 / 48.0;
+#pragma unroll
+    for (int r = 0; r < SH; ++r) {
+      double h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;
+#pragma unroll
+      for (int j = 0; j < WIN; ++j) {
+        const double a = sx[r][t + j], b = sy[r][t + j];
+        h0 += a; h1 += b; h2 += a * a; h3 += b * b; h4 += a * b;
+      }
+      v0 += h0; v1 += h1; v2 += h2; v3 += h3; v4 += h4;
+      if (r >= WIN) {
+        v0 -= ring[r % WIN][0]; v1 -= ring[r % WIN][1]; v2 -= ring[r % WIN][2]; v3 -= ring[r % WIN][3]; v4 -= ring[r % WIN][4];
+      }
+      ring[r % WIN][0] = h0; ring[r % WIN][1] = h1; ring[r % WIN][2] = h2; ring[r % WIN][3] = h3; ring[r % WIN][4] = h4;
+      if (r >= WIN - 1) {
+        const int top = y0 + r - (WIN - 1);
+        if (top + WIN <= H) {
+          const double ux = v0 / NP, uy = v1 / NP;
+          const double vx = COVN * (v2 / NP - ux * ux), vy = COVN * (v3 / NP - uy * uy), vxy = COVN * (v4 / NP - ux * uy);
+          ssim += ((2.0 * ux * uy + C1) * (2.0 * vxy + C2)) / ((ux * ux + uy * uy + C1) * (vx + vy + C2));
+        }
+      }
+    }
+  }
+  // CTA reduction -> one atomic per CTA and quantity
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sse += __shfl_xor_sync(0xffffffffu, sse, o);
+    ssim += __shfl_xor_sync(0xffffffffu, ssim, o);
+  }
+  __shared__ double red[2][TW / 32];
+  if ((t & 31) == 0) {
+    red[0][t >> 5] = sse;
+    red[1][t >> 5] = ssim;
+  }
+  __syncthreads();
+  if (t == 0) {
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int w = 0; w < TW / 32; ++w) {
+      a += red[0][w];
+      b += red[1][w];
+    }
+    atomicAdd(sums + 2 * plane, a);
+    atomicAdd(sums + 2 * plane + 1, b);
+  }
+}
+
+// per plane: 1.0 if every element is exactly zero (compute_psnr_ssim2, val_utils.py:88: bands the degradation removed)
+__global__ void __launch_bounds__(256) plane_all_zero_kernel(const float* __restrict__ X, long long hw, int* __restrict__ nonzero) {
+  const float* p = X + (size_t)blockIdx.y * hw;
+  int any = 0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < hw; i += (long long)gridDim.x * 256) any |= (__ldg(p + i) != 0.f);
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0 && any) atomicOr(nonzero + blockIdx.y, 1);
+}
+
+// ---- Philox4x32-10 (Salmon et al., SC'11): counter = element index / 4, key = seed ---------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// element e of the [B, C, HW] batch: stream block q = e / 2 yields (u0, u1, u2, u3); element parity picks the pair:
+//   mask uniform  u = (w0 >> 8) * 2^-24                      in [0, 1)
+//   normal        n = sqrt(-2 ln((w1 >> 8) + 1) * 2^-24)) * cos(2 pi (w0' ...))   (Box-Muller on two further words)
+// Layout per block of 4 words serving 2 elements: element 2q uses (w0: mask, w1+w2: Box-Muller cos branch),
+// element 2q+1 uses (w3: mask, w1+w2: Box-Muller sin branch).
+__global__ void __launch_bounds__(256) degrade_kernel(const float* __restrict__ clean, float* __restrict__ out, long long total,
+                                                      long long hw, int C, const float* __restrict__ sigma /* [B*C] */,
+                                                      const float* __restrict__ keep /* [B*C] */,
+                                                      const float* __restrict__ mask_ratio /* [B] */, uint32_t seed_lo,
+                                                      uint32_t seed_hi) {
+  const long long pairs = (total + 1) / 2;
+  for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < pairs; q += (long long)gridDim.x * 256) {
+    uint32_t w[4];
+    philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), 0u, 0u, seed_lo, seed_hi, w);
+    const float u1 = ((float)(w[1] >> 8) + 1.0f) * (1.0f / 16777216.0f);   // (0, 1]
+    const float u2 = (float)(w[2] >> 8) * (1.0f / 16777216.0f);            // [0, 1)
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long e = 2 * q + h;
+      if (e >= total) break;
+      const long long bc = e / hw;
+      const int b = (int)(bc / C);
+      const float um = (float)((h == 0 ? w[0] : w[3]) >> 8) * (1.0f / 16777216.0f);
+      const float n = rad * (h == 0 ? cs : sn);
+      const float m = um > __ldg(mask_ratio + b) ? 1.f : 0.f;   // np.random.rand(C,H,W) > mask_ratio (degradation_utils.py:230)
+      out[e] = __ldg(clean + e) * __ldg(keep + bc) * m + __ldg(sigma + bc) * n;
+    }
+  }
+}
+
+}  // namespace metrics
+}  // namespace mphsir
+
+using namespace mphsir;
+
+extern "C" int mphsir_psnr_ssim(const float* restored, const float* clean, int planes, int H, int W, double* sums, void* stream) {
+  MPHSIR_REQUIRE(restored && clean && sums && planes > 0, "psnr_ssim: null operand");
+  MPHSIR_REQUIRE(H >= 7 && W >= 7, "psnr_ssim: the 7x7 SSIM window needs H, W >= 7 (got %dx%d)", H, W);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(sums, 0, sizeof(double) * 2 * planes, st) != cudaSuccess) {
+    set_error("psnr_ssim: cudaMemsetAsync failed");
+    return MPHSIR_ERR_CUDA;
+  }
+  for (int p0 = 0; p0 < planes; p0 += 65535) {
+    const int n = planes - p0 < 65535 ? planes - p0 : 65535;
+    dim3 grid((W + metrics::TW - 1) / metrics::TW, (H + metrics::TH - 1) / metrics::TH, n);
+    metrics::psnr_ssim_kernel<<<grid, metrics::TW, 0, st>>>(restored + (size_t)p0 * H * W, clean + (size_t)p0 * H * W, H, W, sums + 2 * p0);
+  }
+  return check_launch("psnr_ssim");
+}
+
+extern "C" int mphsir_plane_nonzero(const float* X, int planes, long long hw, int* nonzero, void* stream) {
+  MPHSIR_REQUIRE(X && nonzero && planes > 0 && planes <= 65535 && hw > 0, "plane_nonzero: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(nonzero, 0, sizeof(int) * planes, st) != cudaSuccess) {
+    set_error("plane_nonzero: cudaMemsetAsync failed");
+    return MPHSIR_ERR_CUDA;
+  }
+  long long gx = (hw + 255) / 256;
+  if (gx > 64) gx = 64;
+  metrics::plane_all_zero_kernel<<<dim3((unsigned)gx, planes), 256, 0, st>>>(X, hw, nonzero);
+  return check_launch("plane_nonzero");
+}
+
+extern "C" int mphsir_degrade(const float* clean, float* out, int B, int C, long long hw, const float* sigma, const float* keep,
+                              const float* mask_ratio, unsigned long long seed, void* stream) {
+  MPHSIR_REQUIRE(clean && out && sigma && keep && mask_ratio && B > 0 && C > 0 && hw > 0, "degrade: bad arguments");
+  const long long total = (long long)B * C * hw;
+  long long blocks = ((total + 1) / 2 + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  metrics::degrade_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      clean, out, total, hw, C, sigma, keep, mask_ratio, (uint32_t)seed, (uint32_t)(seed >> 32));
+  return check_launch("degrade");
+}

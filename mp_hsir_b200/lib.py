@@ -159,6 +159,9 @@ SIGNATURES = {
     "mphsir_bilinear_bwd": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "mphsir_tvsp_query_bwd": (_I, [_VP, _I, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "mphsir_l1_clamp_loss": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _VP]),
+    "mphsir_psnr_ssim": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),
+    "mphsir_plane_nonzero": (_I, [_VP, _I, _LL, _VP, _VP]),
+    "mphsir_degrade": (_I, [_VP, _VP, _I, _I, _LL, _VP, _VP, _VP, C.c_ulonglong, _VP]),
     "mphsir_adamw_step": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _I, _F, _VP, _VP]),
 }
 
@@ -775,3 +778,35 @@ def adamw_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tenso
                                                            lr, beta1, beta2, eps, weight_decay, step, grad_scale, ptr(dyn),
                                                            stream_ptr()),
             lambda: (0.0, 28.0 * p.numel(), "adamw"))
+
+
+def psnr_ssim_sums(restored: torch.Tensor, clean: torch.Tensor) -> torch.Tensor:
+    """[B,C,H,W] fp32 pair -> float64 [B*C, 2] {sum of squared error, sum of the 7x7-window SSIM index} per band plane"""
+    assert restored.shape == clean.shape and restored.dim() == 4 and restored.is_cuda and clean.is_cuda
+    r, c = restored.detach().float().contiguous(), clean.detach().float().contiguous()
+    B, Cc, H, W = r.shape
+    sums = torch.empty(B * Cc, 2, dtype=torch.float64, device=r.device)
+    _launch("psnr_ssim", lambda: load().mphsir_psnr_ssim(r.data_ptr(), c.data_ptr(), B * Cc, H, W, sums.data_ptr(), stream_ptr()),
+            lambda: (0.0, 8.0 * r.numel(), "psnr_ssim"))
+    return sums
+
+
+def plane_nonzero(x: torch.Tensor) -> torch.Tensor:
+    """[B,C,H,W] -> int32 [B*C]: 1 where the band plane has any non-zero element"""
+    xx = x.detach().float().contiguous()
+    B, Cc, H, W = xx.shape
+    out = torch.empty(B * Cc, dtype=torch.int32, device=xx.device)
+    _launch("plane_nonzero", lambda: load().mphsir_plane_nonzero(xx.data_ptr(), B * Cc, H * W, out.data_ptr(), stream_ptr()),
+            lambda: (0.0, 4.0 * xx.numel(), "plane_nonzero"))
+    return out
+
+
+def degrade(clean: torch.Tensor, out: torch.Tensor, sigma: torch.Tensor, keep: torch.Tensor, mask_ratio: torch.Tensor,
+            seed: int) -> None:
+    """out = clean * keep[b,c] * (u > mask_ratio[b]) + sigma[b,c] * n  (Philox4x32-10 stream keyed by `seed`)"""
+    B, Cc, H, W = clean.shape
+    assert clean.is_contiguous() and out.is_contiguous() and out.shape == clean.shape and clean.dtype == torch.float32
+    assert sigma.numel() == B * Cc and keep.numel() == B * Cc and mask_ratio.numel() == B
+    _launch("degrade", lambda: load().mphsir_degrade(clean.data_ptr(), out.data_ptr(), B, Cc, H * W, sigma.data_ptr(), keep.data_ptr(),
+                                                     mask_ratio.data_ptr(), seed & 0xFFFFFFFFFFFFFFFF, stream_ptr()),
+            lambda: (0.0, 8.0 * clean.numel(), "degrade"))

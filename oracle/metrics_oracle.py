@@ -1,0 +1,94 @@
+"""CPU restatements of what mp_hsir_b200/csrc/metrics.cu computes.  TEST INFRASTRUCTURE (imported by tests/ only).
+
+* ``psnr_ssim`` — utils/val_utils.py:49-69 of the reference.  The arithmetic lives in scikit-image (a dependency of the
+  reference, ``requirements.txt``: scikit-image 0.21; NOT installed here, so this restatement is "parity unpinned"
+  against skimage itself): ``peak_signal_noise_ratio(x, y, data_range=1)`` = 10 log10(1 / mean((x-y)^2)) and
+  ``structural_similarity(x, y, data_range=1)`` with its defaults — win_size 7, uniform_filter means, sample covariance
+  (cov_norm = 49/48), K1 = 0.01, K2 = 0.03, and the mean taken over the filtered image cropped by (win_size-1)//2 = 3 —
+  restated step by step below with scipy.ndimage.uniform_filter (the function skimage itself calls), in float64.
+* ``philox4x32_10`` / ``degrade`` — the counter-based random stream (Salmon et al., "Parallel random numbers: as easy as
+  1, 2, 3", SC'11; constants of Random123) and the elementwise degradation formula of the kernel.
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy.ndimage import uniform_filter
+
+
+def psnr_ssim(recovered: np.ndarray, clean: np.ndarray):
+    """[B,C,H,W] -> (psnr [B,C], ssim [B,C]) per band plane, float64."""
+    x = np.clip(recovered.astype(np.float64), 0, 1)
+    y = np.clip(clean.astype(np.float64), 0, 1)
+    B, C = x.shape[:2]
+    psnr = np.zeros((B, C))
+    ssim = np.zeros((B, C))
+    K1, K2, win, R = 0.01, 0.03, 7, 1.0
+    NP = win * win
+    cov_norm = NP / (NP - 1.0)
+    C1, C2 = (K1 * R) ** 2, (K2 * R) ** 2
+    pad = (win - 1) // 2
+    for b in range(B):
+        for c in range(C):
+            a, t = x[b, c], y[b, c]
+            psnr[b, c] = 10.0 * np.log10(R * R / np.mean((a - t) ** 2))
+            ux, uy = uniform_filter(a, size=win), uniform_filter(t, size=win)
+            uxx, uyy, uxy = uniform_filter(a * a, size=win), uniform_filter(t * t, size=win), uniform_filter(a * t, size=win)
+            vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+            S = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux ** 2 + uy ** 2 + C1) * (vx + vy + C2))
+            ssim[b, c] = S[pad:-pad, pad:-pad].mean()
+    return psnr, ssim
+
+
+def compute_psnr_ssim(recovered: np.ndarray, clean: np.ndarray):
+    """utils/val_utils.py:49-69: mean over bands, then over the batch."""
+    p, s = psnr_ssim(recovered, clean)
+    return p.mean(axis=1).mean(), s.mean(axis=1).mean(), recovered.shape[0]
+
+
+def compute_psnr_ssim2(recovered: np.ndarray, clean: np.ndarray, degrad: np.ndarray):
+    """utils/val_utils.py:71-105: only bands whose degraded plane is all zero; samples without one are skipped."""
+    p, s = psnr_ssim(recovered, clean)
+    ps, ss, count = 0.0, 0.0, 0
+    for b in range(recovered.shape[0]):
+        sel = [c for c in range(recovered.shape[1]) if np.all(degrad[b, c] == 0)]
+        if sel:
+            ps += p[b, sel].mean()
+            ss += s[b, sel].mean()
+            count += 1
+    return (ps / count, ss / count, count) if count else (0, 0, 0)
+
+
+def philox4x32_10(counter: np.ndarray, seed: int) -> np.ndarray:
+    """counter: uint64 array [n] -> uint32 [n, 4]; counter words (lo, hi, 0, 0), key (seed lo, seed hi)."""
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    mask = np.uint64(0xFFFFFFFF)
+    c0 = counter & mask
+    c1 = counter >> np.uint64(32)
+    c2 = np.zeros_like(c0)
+    c3 = np.zeros_like(c0)
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    return np.stack([c0, c1, c2, c3], axis=1).astype(np.uint32)
+
+
+def degrade(clean: np.ndarray, sigma: np.ndarray, keep: np.ndarray, mask_ratio: np.ndarray, seed: int):
+    """-> (degraded float64 [B,C,H,W], mask uniforms, normals): out = clean*keep*(u > ratio) + sigma*n"""
+    B, C, H, W = clean.shape
+    total = clean.size
+    pairs = (total + 1) // 2
+    w = philox4x32_10(np.arange(pairs, dtype=np.uint64), seed).astype(np.float64)
+    f = lambda v: np.floor(v / 256.0)                      # noqa: E731  (w >> 8)
+    u1 = (f(w[:, 1]) + 1.0) / 16777216.0
+    u2 = f(w[:, 2]) / 16777216.0
+    rad = np.sqrt(-2.0 * np.log(u1))
+    n = np.stack([rad * np.cos(2 * np.pi * u2), rad * np.sin(2 * np.pi * u2)], axis=1).reshape(-1)[:total]
+    um = np.stack([f(w[:, 0]), f(w[:, 3])], axis=1).reshape(-1)[:total] / 16777216.0
+    n, um = n.reshape(B, C, H, W), um.reshape(B, C, H, W)
+    m = (um.astype(np.float32) > mask_ratio.astype(np.float32).reshape(B, 1, 1, 1)).astype(np.float64)
+    out = clean.astype(np.float64) * keep.reshape(B, C, 1, 1) * m + sigma.reshape(B, C, 1, 1).astype(np.float64) * n
+    return out, um, n

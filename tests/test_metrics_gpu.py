@@ -1,0 +1,74 @@
+"""GPU: device PSNR/SSIM (utils/val_utils.py:49-105) and device degradations against the CPU restatements."""
+import numpy as np
+import pytest
+import torch
+
+from mp_hsir_b200 import lib
+from mp_hsir_b200 import metrics as GM
+from mp_hsir_b200.degrade import degrade, degrade_batch, draw_parameters
+from mp_hsir_b200.synth import synthetic_input, synthetic_scene
+from oracle import metrics_oracle as M
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 40, 50), (1, 31, 64, 64), (1, 3, 7, 7), (1, 2, 135, 263)])
+def test_psnr_ssim_matches_oracle(shape):
+    clean = synthetic_input(shape, seed=3)
+    rec = clean + 0.08 * torch.randn(shape, generator=torch.Generator().manual_seed(1)) - 0.01   # leaves [0,1]: clip is live
+    p, s, n = GM.compute_psnr_ssim(rec.cuda(), clean.cuda())
+    pr, sr, nr = M.compute_psnr_ssim(rec.numpy(), clean.numpy())
+    assert n == nr == shape[0]
+    assert abs(p - pr) < 1e-9 * max(1.0, abs(pr)) and abs(s - sr) < 1e-9, (p, pr, s, sr)
+
+
+def test_psnr_ssim_on_the_scene_shape_and_band_miss_variant():
+    noisy, clean = synthetic_scene(31, 512, seed=0)
+    p, s, _ = GM.compute_psnr_ssim(noisy.cuda(), clean.cuda())
+    pr, sr, _ = M.compute_psnr_ssim(noisy.numpy(), clean.numpy())
+    assert abs(p - pr) < 1e-8 and abs(s - sr) < 1e-9
+    deg = clean.clone()
+    deg[0, [2, 17, 30]] = 0
+    p2, s2, n2 = GM.compute_psnr_ssim2(noisy.cuda(), clean.cuda(), deg.cuda())
+    pr2, sr2, nr2 = M.compute_psnr_ssim2(noisy.numpy(), clean.numpy(), deg.numpy())
+    assert n2 == nr2 == 1 and abs(p2 - pr2) < 1e-8 and abs(s2 - sr2) < 1e-9
+    assert GM.compute_psnr_ssim2(noisy.cuda(), clean.cuda(), clean.cuda() + 1.0) == (0, 0, 0)   # nothing lost: nothing counted
+
+
+def test_degrade_matches_oracle_stream():
+    B, C, H, W = 3, 7, 24, 40
+    clean = synthetic_input((B, C, H, W), seed=9)
+    g = torch.Generator().manual_seed(5)
+    sigma = 0.3 * torch.rand(B, C, generator=g)
+    keep = (torch.rand(B, C, generator=g) > 0.3).float()
+    ratio = torch.tensor([-1.0, 0.7, 0.9])
+    out = degrade(clean.cuda(), sigma, keep, ratio, seed=0x1234567890ABCDEF).cpu().numpy()
+    ref, um, n = M.degrade(clean.numpy(), sigma.numpy(), keep.numpy(), ratio.numpy(), seed=0x1234567890ABCDEF)
+    # the mask decisions are integer arithmetic (bit exact); the normals go through fp32 log / sincospi
+    assert np.array_equal(out == 0, ref == 0) or np.mean((out == 0) != (ref == 0)) < 1e-6
+    assert np.max(np.abs(out - ref)) < 2e-6
+    # another seed, another stream
+    out2 = degrade(clean.cuda(), sigma, keep, ratio, seed=1).cpu().numpy()
+    assert np.mean(out2 != out) > 0.5
+
+
+def test_degrade_batch_follows_the_recipes():
+    clean = synthetic_input((32, 31, 64, 64), seed=2).cuda()
+    before = lib.LAUNCHES
+    noisy, tid = degrade_batch(clean, seed=77, generator=torch.Generator().manual_seed(3))
+    assert lib.LAUNCHES - before == 1 and tid.shape == (32, 1)
+    d = (noisy - clean).cpu()
+    c = clean.cpu()
+    for b in range(32):
+        k = int(tid[b, 0])
+        if k == 0:
+            assert 28 / 255 < float(d[b].std()) < 72 / 255
+        elif k == 1:
+            sd = d[b].std(dim=(1, 2)) * 255
+            assert all(min(abs(float(v) - t) for t in (10, 30, 50, 70)) < 3 for v in sd)
+        elif k == 2:
+            kept = noisy[b].cpu() != 0
+            assert 0.05 < float(kept.float().mean()) < 0.35 and torch.equal(noisy[b].cpu()[kept], c[b][kept])
+        else:
+            lost = noisy[b].abs().sum(dim=(1, 2)).cpu() == 0
+            assert int(lost.sum()) in (3, 6, 9) and torch.equal(noisy[b].cpu()[~lost], c[b][~lost])
