@@ -69,6 +69,31 @@ def test_backward_matches_oracle(precision, out_tol, grad_tol, median_tol):
     assert len(dead) == 8 and all(n not in tr.g for n in dead)
 
 
+def test_bf16_gradients_are_no_worse_than_the_reference_autocast():
+    """Yardstick for the bf16 training mode: the UNMODIFIED reference under torch.autocast(bfloat16) — what its own
+    `precision="16-mixed"` trainer computes (train.py:118) — is itself 2e-2 (median) / 0.27 (worst tensor) away from its fp32
+    gradients on this case (tests/golden/nat_b2_32_grads_bf16_yardstick.json, oracle/make_golden_bf16_yardstick.py).  The
+    CUDA trainer's bf16 mode must not be worse: distribution-wise (median, 90th percentile, maximum) and per tensor (within
+    a factor of the reference's own error for that tensor, with the reference's 90th percentile as the floor)."""
+    import json
+    import os
+    import statistics
+    from tests.conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "nat_b2_32_grads_bf16_yardstick.json")) as f:
+        yard = json.load(f)
+    _, ref_grads = oracle_grads()
+    net, tr, _ = run_backward("bf16")
+    errs = grad_errors(net, ref_grads)
+    ours = sorted(errs.values())
+    summ = yard["summary"]
+    med, p90, mx = statistics.median(ours), ours[int(0.9 * len(ours))], ours[-1]
+    print(f"bf16 gradient rel-L2: ours median {med:.3e} p90 {p90:.3e} max {mx:.3e} | reference autocast median "
+          f"{summ['median']:.3e} p90 {summ['p90']:.3e} max {summ['max']:.3e}")
+    assert med <= 1.25 * summ["median"] and p90 <= 1.25 * summ["p90"] and mx <= 1.25 * summ["max"]
+    worse = {n: (e, yard["rel_l2"][n]) for n, e in errs.items() if e > max(4.0 * yard["rel_l2"][n], summ["p90"])}
+    assert not worse, sorted(worse.items(), key=lambda kv: -kv[1][0])[:8]
+
+
 def test_backward_is_additive_and_zero_grad_resets():
     net, tr, _ = run_backward("fp32")
     g1 = tr.flat_g.clone()
