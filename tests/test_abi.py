@@ -84,3 +84,17 @@ int main(void) {
             G.n_split.offset, ctypes.sizeof(Cv),
             Cv.Bimg.offset, ctypes.sizeof(L)]
     assert got == want
+
+
+def test_integration_md_struct_is_the_current_layout():
+    """INTEGRATION.md shows maintainers a ctypes mirror of mphsir_gemm_params: it must be the struct the library reads
+    (round 1 shipped a stale one)."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"class GemmParams\(ctypes.Structure\):.*?\n    _fields_ = \[(.*?)\]\n\n", text, flags=re.S)
+    assert m, "GemmParams snippet not found in INTEGRATION.md"
+    ns = {"ctypes": ctypes}
+    exec("class GemmParams(ctypes.Structure):\n    _fields_ = [" + m.group(1) + "]", ns)
+    doc = ns["GemmParams"]
+    ours = lib.GemmParams
+    assert [(n, t) for n, t in doc._fields_] == [(n, t) for n, t in ours._fields_]
+    assert ctypes.sizeof(doc) == ctypes.sizeof(ours)
