@@ -542,7 +542,7 @@ def run_sharded(args):
     import torch.distributed as dist
     from mp_hsir_b200 import lib
     from mp_hsir_b200.parallel import max_over_ranks as _max
-    from mp_hsir_b200.sharded import NcclComm, ShardedEngine, ThreadComm, _ThreadWorld, band_rows
+    from mp_hsir_b200.sharded import NcclComm, PeerComm, ShardedEngine, ThreadComm, _ThreadWorld, band_rows
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -555,7 +555,12 @@ def run_sharded(args):
     precision = args.precision
     cfg, net = build_net(model, device)
     net.set_precision(precision)
-    comm = NcclComm() if world > 1 else ThreadComm(_ThreadWorld(1), 0)
+    if world == 1:
+        comm = ThreadComm(_ThreadWorld(1), 0)
+    elif args.comm == "peer":
+        comm = PeerComm(device)          # fails loudly if the GPUs cannot map each other's memory; --comm nccl is the alternative
+    else:
+        comm = NcclComm()
     eng = ShardedEngine(net, comm)
     eng.use_cuda_graph = args.cuda_graph == "on"
     H = shape[2]
@@ -627,6 +632,8 @@ def run_sharded(args):
     ws_bytes = eng.ws.bytes()
     if world > 1:
         dist.barrier()
+        if hasattr(comm, "close"):
+            comm.close()
         dist.destroy_process_group()
     if rank != 0:
         return
@@ -697,6 +704,9 @@ def main():
                     help="cube512 with N GPUs: 'cubes' = one independent cube per GPU per step (weak scaling, default); "
                          "'rows' = ONE scene per step, its rows split over the GPUs with halo exchange + Gram all-reduce "
                          "(strong scaling, BASELINE config 3 as specified)")
+    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
+                    help="--shard rows: 'peer' = libmphsir one-kernel halo exchange / all-reduce over NVLink peer memory (CUDA IPC "
+                         "windows), 'nccl' = torch.distributed send/recv + all_reduce")
     ap.add_argument("--reference-budget-s", type=float, default=120.0,
                     help="--impl reference: stop timing further steps once this many seconds of timed work are spent")
     ap.add_argument("--precision", default=None, choices=["fp32", "fp32_exact", "bf16"],

@@ -478,6 +478,30 @@ MPHSIR_API int mphsir_degrade(const float* clean, float* out, int B, int C, long
                               const float* keep /* [B*C] */, const float* mask_ratio /* [B] */, unsigned long long seed,
                               void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Collectives of the row-sharded scene over NVLink peer memory (mp_hsir_b200/csrc/peer.cu; one process per GPU of one
+ * node).  Every rank allocates one WINDOW of mphsir_peer_window_bytes(halo_cap, ar_cap) bytes (256-byte aligned, zeroed
+ * once), exports it through CUDA IPC and maps every peer's window; `windows[q]` is rank q's window as mapped in THIS
+ * process.  All ranks must issue the same sequence of these calls (sequence numbers live in the windows, so CUDA-graph
+ * replays stay in step).  Each call is ONE kernel: push to the peers' windows, publish flags, wait for the peers' flags,
+ * consume.  halo_exchange: halo_top <- previous rank's own_last rows, halo_bottom <- next rank's own_first rows (cyclic),
+ * n floats per direction (multiple of 4, <= halo_cap).  all_reduce: data[0..n) <- sum over ranks in rank order (the
+ * same bits on every rank), n <= ar_cap.
+ * ------------------------------------------------------------------------------------- */
+MPHSIR_API size_t mphsir_peer_window_bytes(long long halo_cap, long long ar_cap);
+/* window life cycle (the one place the library owns device memory: an IPC handle names a whole cudaMalloc allocation):
+ * alloc + zero on the current device, export a 64-byte CUDA IPC handle, open a peer's handle (lazy P2P enable), close, free */
+MPHSIR_API int mphsir_peer_window_alloc(size_t bytes, void** window);
+MPHSIR_API int mphsir_peer_window_free(void* window);
+MPHSIR_API int mphsir_peer_export(void* window, unsigned char* handle64);
+MPHSIR_API int mphsir_peer_open(const unsigned char* handle64, void** mapped);
+MPHSIR_API int mphsir_peer_close(void* mapped);
+MPHSIR_API int mphsir_peer_halo_exchange(void* const* windows, int rank, int world, long long halo_cap, long long ar_cap,
+                                         const float* own_first, const float* own_last, float* halo_top, float* halo_bottom,
+                                         long long n, void* stream);
+MPHSIR_API int mphsir_peer_all_reduce(void* const* windows, int rank, int world, long long halo_cap, long long ar_cap,
+                                      float* data, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,7 +48,10 @@ __device__ __forceinline__ void t_split_pair(float a, float b, uint32_t& hi, uin
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void consumer_bar() {
+  __syncwarp();  // bar.sync is .aligned: reconverge after the lane-0 mbarrier arrives
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+}
 
 constexpr int TMA_CONSUMERS = 256;
 constexpr int TMA_THREADS = TMA_CONSUMERS + 32;

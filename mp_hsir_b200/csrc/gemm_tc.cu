@@ -848,6 +848,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           const int slot = st;
           // in-place conversion: every converter thread has read its fp32 cells; now the slot may be overwritten
           long long tw2 = TC_T0();
+          __syncwarp();  // bar.sync is .aligned: converged again after the lane-0 arrive of the previous slab
           asm volatile("bar.sync 1, %0;" ::"n"(kConvThreads) : "memory");
           TC_ACC(t_slot, tw2);
           uint8_t* dst = a_ring + (size_t)slot * a_slot_bytes;

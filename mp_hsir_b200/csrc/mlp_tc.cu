@@ -116,6 +116,7 @@ __device__ __forceinline__ void glu_chunk(const MlpArgs& p, MlpSmem* sm, uint8_t
     mbar_arrive(smem_u32(&sm->h_full[hs]));
     mbar_arrive(smem_u32(&sm->acc1_empty[buf]));
   }
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_constant__ MlpArgs p) {
@@ -351,6 +352,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&sm->acc2_empty));
+      __syncwarp();  // bar.sync is .aligned: the warp must be converged again after the lane-0 branch (synccheck)
       // the transpose buffers alias the H ring: nobody (epilogue or converter warp) may start the next tile's GLU
       // writes before every epilogue warp has left its staging area
       if (tile + (int)gridDim.x < num_tiles) asm volatile("bar.sync 2, 512;" ::: "memory");
@@ -431,6 +433,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
           g0 = ldg4(p.ln_g + k); g1 = ldg4(p.ln_g + k + 4);
           e0 = ldg4(p.ln_b + k); e1 = ldg4(p.ln_b + k + 4);
         }
+        __syncwarp();
         asm volatile("bar.sync 1, 256;" ::: "memory");  // every converter has read its cells of the slot
         uint8_t* dst = a_ring + (size_t)st * M_STAGE;
 #pragma unroll
@@ -459,6 +462,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
       (void)m0;
       // ---- then help with the GLU stage of this tile (H slots double as the epilogue warps' staging: wait until
       //      they have finished the previous tile's final epilogue) ----
+      __syncwarp();  // converged again after the lane-0 arrive of the last slab (bar.sync is .aligned)
       if (tile != (int)blockIdx.x) asm volatile("bar.sync 2, 512;" ::: "memory");
       for (int j = 0; j < NJ; ++j, ++c1_it, ++h_it)
         glu_chunk(p, sm, h_ring, h_slot_bytes, tmem_base, j, c1_it, h_it, gquad, ggroup, lane, parts);

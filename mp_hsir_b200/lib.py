@@ -159,6 +159,14 @@ SIGNATURES = {
     "mphsir_bilinear_bwd": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "mphsir_tvsp_query_bwd": (_I, [_VP, _I, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "mphsir_l1_clamp_loss": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _VP]),
+    "mphsir_peer_window_bytes": (C.c_size_t, [_LL, _LL]),
+    "mphsir_peer_window_alloc": (_I, [C.c_size_t, C.POINTER(_VP)]),
+    "mphsir_peer_window_free": (_I, [_VP]),
+    "mphsir_peer_export": (_I, [_VP, C.c_char_p]),
+    "mphsir_peer_open": (_I, [C.c_char_p, C.POINTER(_VP)]),
+    "mphsir_peer_close": (_I, [_VP]),
+    "mphsir_peer_halo_exchange": (_I, [C.POINTER(_VP), _I, _I, _LL, _LL, _VP, _VP, _VP, _VP, _LL, _VP]),
+    "mphsir_peer_all_reduce": (_I, [C.POINTER(_VP), _I, _I, _LL, _LL, _VP, _LL, _VP]),
     "mphsir_psnr_ssim": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),
     "mphsir_plane_nonzero": (_I, [_VP, _I, _LL, _VP, _VP]),
     "mphsir_degrade": (_I, [_VP, _VP, _I, _I, _LL, _VP, _VP, _VP, C.c_ulonglong, _VP]),

@@ -114,6 +114,77 @@ class NcclComm:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
 
 
+class PeerComm:
+    """one process per GPU of ONE node: both collectives are single libmphsir kernels over NVLink peer memory
+    (mp_hsir_b200/csrc/peer.cu) — every rank's window (mailboxes, gather slots, flags) is exported through CUDA IPC and mapped
+    by all peers; torch.distributed is used once, to swap the 64-byte handles.  CUDA-graph capturable (the sequence numbers
+    live in device memory)."""
+
+    name = "libmphsir peer-memory kernels over NVLink (CUDA IPC windows): 1 kernel per halo exchange / all-reduce"
+
+    def __init__(self, device, halo_cap: int = 1 << 20, ar_cap: int = 1 << 15, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise ValueError("PeerComm serves the GPUs of one node (<= 8 ranks)")
+        self.device = torch.device(device)
+        self.halo_cap, self.ar_cap = int(halo_cap), int(ar_cap)
+        self.halo_exchanges = self.all_reduces = 0
+        L = lib.load()
+        with torch.cuda.device(self.device):
+            win = C.c_void_p()
+            lib._check(L.mphsir_peer_window_alloc(L.mphsir_peer_window_bytes(self.halo_cap, self.ar_cap), C.byref(win)), "peer_window_alloc")
+            lib.LAUNCHES -= 1
+            self._own = win.value
+            handle = C.create_string_buffer(64)
+            lib._check(L.mphsir_peer_export(self._own, handle), "peer_export")
+            lib.LAUNCHES -= 1
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self._mapped = []
+            table = (C.c_void_p * self.world)()
+            for q in range(self.world):
+                if q == self.rank:
+                    table[q] = self._own
+                    continue
+                m = C.c_void_p()
+                lib._check(L.mphsir_peer_open(handles[q], C.byref(m)), f"peer_open(rank {q})")
+                lib.LAUNCHES -= 1
+                self._mapped.append(m.value)
+                table[q] = m.value
+            self._table = table
+            dist.barrier(group=group)        # every window is mapped everywhere before the first kernel touches one
+
+    def halo(self, base: torch.Tensor, top: int, own_first: int, own_last: int, bottom: int, n: int) -> None:
+        self.halo_exchanges += 1
+        p0 = base.data_ptr()
+        L = lib.load()
+        lib._launch("peer_halo_exchange",
+                    lambda: L.mphsir_peer_halo_exchange(self._table, self.rank, self.world, self.halo_cap, self.ar_cap,
+                                                        p0 + 4 * own_first, p0 + 4 * own_last, p0 + 4 * top, p0 + 4 * bottom, n,
+                                                        lib.stream_ptr()),
+                    lambda: (0.0, 16.0 * n, "peer_halo_exchange"))
+
+    def all_reduce(self, t: torch.Tensor) -> None:
+        self.all_reduces += 1
+        L = lib.load()
+        lib._launch("peer_all_reduce",
+                    lambda: L.mphsir_peer_all_reduce(self._table, self.rank, self.world, self.halo_cap, self.ar_cap, t.data_ptr(),
+                                                     t.numel(), lib.stream_ptr()),
+                    lambda: (0.0, 4.0 * t.numel() * (2 * self.world + 1), "peer_all_reduce"))
+
+    def close(self) -> None:
+        L = lib.load()
+        torch.cuda.synchronize(self.device)
+        for m in self._mapped:
+            L.mphsir_peer_close(m)
+        self._mapped = []
+        if self._own:
+            L.mphsir_peer_window_free(self._own)
+            self._own = None
+
+
 class _ThreadWorld:
     def __init__(self, world: int):
         self.world = world

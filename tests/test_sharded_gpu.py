@@ -84,50 +84,97 @@ def test_full_scene_cube512_eight_bands_matches_reference(cases):
     assert abs(psnr_per_band(y.cpu(), clean) - meta["psnr_ref_vs_clean"]) <= 0.01
 
 
-def _nccl_worker(rank, world, port, out):
+def _dist_worker(rank, world, port, out, kind):
     import torch.distributed as dist
-    from mp_hsir_b200.sharded import NcclComm, ShardedEngine, band_rows
+    from mp_hsir_b200.sharded import NcclComm, PeerComm, ShardedEngine, band_rows
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
+        comm = PeerComm(dev) if kind == "peer" else NcclComm()
+        # ---- the collectives alone, many rounds (sequence numbers, parity double-buffering), eager and graph replay ----
+        rounds, n = 40, 8 * 96 * 64
+        buf = torch.zeros(4 * n, device=dev)
+        own_first, own_last, top, bottom = n, 2 * n, 0, 3 * n
+        vec = torch.zeros(2176, device=dev)
+        ok = True
+
+        def one_round(i):
+            buf[own_first:own_first + n] = 1000.0 * rank + i
+            buf[own_last:own_last + n] = 1000.0 * rank + i + 0.5
+            vec.fill_(float(rank + 1) * (i + 1))
+            comm.halo(buf, top, own_first, own_last, bottom, n)
+            comm.all_reduce(vec)
+
+        prev, nxt = (rank - 1) % world, (rank + 1) % world
+        for i in range(rounds):
+            one_round(i)
+            ok &= bool((buf[top:top + n] == 1000.0 * prev + i + 0.5).all()) and bool((buf[bottom:bottom + n] == 1000.0 * nxt + i).all())
+            ok &= bool((vec == (i + 1) * world * (world + 1) / 2).all())
+        if kind == "peer":
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                comm.halo(buf, top, own_first, own_last, bottom, n)
+                comm.all_reduce(vec)
+            for i in range(10):
+                buf[own_first:own_first + n] = -1.0 - rank - 10 * i
+                buf[own_last:own_last + n] = -1.5 - rank - 10 * i
+                vec.fill_(float(rank + 1))
+                g.replay()
+                ok &= bool((buf[top:top + n] == -1.5 - prev - 10 * i).all()) and bool((buf[bottom:bottom + n] == -1.0 - nxt - 10 * i).all())
+                ok &= bool((vec == world * (world + 1) / 2).all())
+        # ---- the sharded forward ----
         cfg = cfg_of("natural")
         net = MP_HSIR_Net(cfg.in_channel, cfg.out_channel, cfg.dim, task_classes=cfg.task_classes)
         fill_state_dict_(net, seed=0)
-        net = net.to(f"cuda:{rank}").eval()
-        x = synthetic_input((1, 31, 128, 96), seed=31).to(f"cuda:{rank}")
-        tid = torch.tensor([2]).to(f"cuda:{rank}")
-        eng = ShardedEngine(net, NcclComm())
+        net = net.to(dev).eval()
+        x = synthetic_input((1, 31, 128, 96), seed=31).to(dev)
+        tid = torch.tensor([2]).to(dev)
+        eng = ShardedEngine(net, comm)
         r0, r1 = band_rows(128, rank, world)
         with torch.no_grad():
+            h0, a0 = comm.halo_exchanges, comm.all_reduces
             band = eng.forward_band(x[:, :, r0:r1].contiguous(), tid, 128)
+            per_scene = (comm.halo_exchanges - h0, comm.all_reduces - a0)
             band2 = eng.forward_band(x[:, :, r0:r1].contiguous(), tid, 128)   # cached prompts, warm workspace
+            eng.use_cuda_graph = True
+            for _ in range(4):                                                 # 2 eager, capture, replay
+                band3 = eng.forward_band(x[:, :, r0:r1].contiguous(), tid, 128)
             ref = net(x, tid)
         torch.cuda.synchronize()
         err = float((band - ref[:, :, r0:r1]).abs().max() / ref.abs().max())
-        out.put((rank, err, bool(torch.equal(band, band2)), eng.comm.halo_exchanges, eng.comm.all_reduces))
+        out.put((rank, ok, err, bool(torch.equal(band, band2)), bool(torch.equal(band, band3)), per_scene))
         dist.barrier()
+        if hasattr(comm, "close"):
+            comm.close()
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_two_gpus_over_nccl_match_single_gpu():
+@pytest.mark.parametrize("kind", ["nccl", "peer"])
+def test_two_gpus_match_single_gpu(kind):
+    """real multi-process path on 2 GPUs with both transports: the collectives alone over many rounds (and, for the
+    peer-memory kernels, under CUDA-graph replay), then the sharded forward eager / repeated / graph-replayed"""
     import torch.multiprocessing as mp
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    world = 2
+    world = min(torch.cuda.device_count(), 4) if kind == "peer" else 2
+    world = 2 if world == 3 else world          # 128 rows: 2 or 4 bands of whole level-3 windows
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, out)) for r in range(world)]
+    procs = [ctx.Process(target=_dist_worker, args=(r, world, port, out, kind)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(out.get(timeout=600) for _ in range(world))
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    for rank, err, same, halos, reds in res:
-        print(f"rank {rank}: max|d|/max|ref| = {err:.3e}, halo exchanges {halos}, all-reduces {reds}")
-        assert err < 2e-5 and same
-        assert reds == 2 * 24                       # 22 PGSSTB + 2 PromptFusion Gram all-reduces per forward
+    for rank, ok, err, same, same_graph, per_scene in res:
+        print(f"[{kind}] rank {rank}/{world}: collectives ok {ok}, max|d|/max|ref| = {err:.3e}, per scene {per_scene[0]} halo exchanges + "
+              f"{per_scene[1]} all-reduces")
+        assert ok and err < 2e-5 and same and same_graph
+        assert per_scene[1] == 24                    # 22 PGSSTB + 2 PromptFusion Gram all-reduces per forward
