@@ -4,15 +4,18 @@
 cd "${GRAFT_REPO_ROOT:-.}"
 O=gpurun_out
 NMAX=${1:-2}
+COMMS=${2:-"peer nccl"}
 for n in 1 2 4 8; do
   [ $n -gt $NMAX ] && break
+  for c in $COMMS; do
+  [ $n -eq 1 ] && [ $c != peer ] && continue
   for g in off on; do
-    tag=r02_rows_n${n}_graph_${g}
+    tag=r02_rows_n${n}_${c}_graph_${g}
     if [ $n -eq 1 ]; then
       timeout 300 python bench.py --shard rows --steps 20 --warmup 4 --no-cpu-baseline --cuda-graph $g > $O/$tag.json 2> $O/$tag.err
     else
       timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600 + n)) \
-        bench.py --gpus $n --shard rows --steps 20 --warmup 4 --no-cpu-baseline --cuda-graph $g > $O/$tag.json 2> $O/$tag.err
+        bench.py --gpus $n --shard rows --comm $c --steps 20 --warmup 4 --no-cpu-baseline --cuda-graph $g > $O/$tag.json 2> $O/$tag.err
     fi
     echo "$tag rc=$? $(python - <<PY
 import json
@@ -24,5 +27,6 @@ except Exception as e:
 PY
 )"
     tail -2 $O/$tag.err | cut -c1-300
+  done
   done
 done
