@@ -562,7 +562,11 @@ def run_sharded(args):
     else:
         comm = NcclComm()
     eng = ShardedEngine(net, comm)
-    eng.use_cuda_graph = args.cuda_graph == "on"
+    # graph replay needs collectives that are plain kernels on the capture stream (the peer-memory ones); capturing torch's
+    # NCCL send/recv batches hung on this stack (NCCL 2.28.9, measured once, never again)
+    if args.cuda_graph == "on" and isinstance(comm, NcclComm):
+        raise SystemExit("--cuda-graph on with --shard rows needs --comm peer (NCCL calls are not captured)")
+    eng.use_cuda_graph = args.cuda_graph != "off" and not isinstance(comm, NcclComm)   # auto = on: at 4-8 GPUs eager launches bound the band
     H = shape[2]
     x_full, clean, tid_host = make_input(shape, 0, args.workload)        # every rank derives the SAME scene from the seed
     r0, r1 = band_rows(H, rank, world)

@@ -20,9 +20,11 @@ forward up to the summation order of one small all-reduce per block:
     level 1, <= 18.8k for the remote-sensing model) -> softmax / fold on every rank.  24 per forward.
   * TVSP depends on (task ids, shape) only: every rank computes the full-resolution prompt once (cached) and keeps its rows.
 
-Communication back-ends: ``NcclComm`` (one process per GPU, torch.distributed) and ``ThreadComm`` (G virtual ranks as
-threads on ONE GPU — the same code path with device-local copies; used by the single-GPU parity tests and as a
-debugging aid).  Host plumbing only: all arithmetic is libmphsir launches.
+Communication back-ends: ``PeerComm`` (one process per GPU of one node; each collective is ONE libmphsir kernel over NVLink
+peer memory — CUDA IPC windows, device-side sequence numbers, CUDA-graph capturable; mp_hsir_b200/csrc/peer.cu),
+``NcclComm`` (torch.distributed send/recv + all_reduce) and ``ThreadComm`` (G virtual ranks as threads on ONE GPU — the same
+code path with device-local copies; used by the single-GPU parity tests and as a debugging aid).  Host plumbing only: all
+arithmetic is libmphsir launches.
 """
 from __future__ import annotations
 

@@ -1,11 +1,13 @@
 #!/bin/bash
 # Strong scaling of ONE 31x512x512 scene split into row bands (bench.py --shard rows) at 1..N GPUs of this box, eager and
-# CUDA-graph replay, each run under its own timeout (a hung collective must not hold the box).  Usage: gpu_scale_rows.sh N
+# CUDA-graph replay, each run under its own timeout (a hung collective must not hold the box).
+# Usage: gpu_scale_rows.sh NMAX ["peer nccl"] ["1 2 4 8"]
 cd "${GRAFT_REPO_ROOT:-.}"
 O=gpurun_out
 NMAX=${1:-2}
 COMMS=${2:-"peer nccl"}
-for n in 1 2 4 8; do
+NLIST=${3:-"1 2 4 8"}
+for n in $NLIST; do
   [ $n -gt $NMAX ] && break
   for c in $COMMS; do
   [ $n -eq 1 ] && [ $c != peer ] && continue
