@@ -535,7 +535,7 @@ def inference_roofline(agg, passes: int, precision: str, workload: str):
     return roof, breakdown
 
 
-def run_sharded(args):
+def run_sharded(args, embedded: bool = False):
     """`--workload cube512 --shard rows`: ONE 31x512x512 scene per step, its rows split over all ranks (BASELINE config 3 as
     specified; mp_hsir_b200/sharded.py) — strong scaling: value = 1 / (time per scene).  Collectives on the data path:
     neighbour halo send/recv before every block / conv, one all-reduce of the Gram statistics per block."""
@@ -549,7 +549,7 @@ def run_sharded(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
-    if world > 1:
+    if world > 1 and not embedded:
         dist.init_process_group("nccl", device_id=device)
     model, shape, unit, units, _, _ = WORKLOADS[args.workload]
     precision = args.precision
@@ -633,16 +633,19 @@ def run_sharded(args):
                 roof, breakdown = inference_roofline(agg, 1, precision, args.workload)
                 roof["traffic"] = None   # the committed ncu traffic capture is of the unsharded launch shapes
             barrier()
-    ws_bytes = eng.ws.bytes()
+    ws_bytes, used_graph = eng.ws.bytes(), eng.use_cuda_graph
     if world > 1:
         dist.barrier()
         if hasattr(comm, "close"):
             comm.close()
-        dist.destroy_process_group()
+        if not embedded:
+            dist.destroy_process_group()
+    del eng, net
+    torch.cuda.empty_cache()
     if rank != 0:
-        return
+        return None
     cb = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and not embedded:
         cb, _ = cpu_baseline(model, shape, float(units), unit, workload=args.workload)
     line = {
         "metric": METRIC[args.workload], "value": args.steps / (ms_dev * 1e-3), "unit": unit, "n_gpus": world,
@@ -656,12 +659,17 @@ def run_sharded(args):
                    "collectives": comm.name,
                    "weights": "random-init (name-seeded synthetic), reference architecture",
                    "l2": "per-step working set exceeds the 126 MB L2 (GBs of activations); no explicit flush",
-                   "cuda_graph": eng.use_cuda_graph, "output_check": parity, "workspace_bytes_per_gpu": ws_bytes},
+                   "cuda_graph": used_graph, "output_check": parity, "workspace_bytes_per_gpu": ws_bytes},
         "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": unit, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": x_full.numel() * 4 + tid_host.numel() * 8, "d2h_bytes_per_step": x_full.numel() * 4},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cb, "kernels": breakdown,
     }
+    if embedded:
+        line.pop("kernels", None)
+        line.pop("cpu_baseline", None)
+        return line
     print(json.dumps(line))
+    return line
 
 
 def run_reference(args):
@@ -704,6 +712,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="cube512 only: skip the embedded train64 measurement")
+    ap.add_argument("--no-rows", action="store_true", help="N > 1, cube512: skip the embedded one-scene-over-all-GPUs measurement")
     ap.add_argument("--shard", default="cubes", choices=["cubes", "rows"],
                     help="cube512 with N GPUs: 'cubes' = one independent cube per GPU per step (weak scaling, default); "
                          "'rows' = ONE scene per step, its rows split over the GPUs with halo exchange + Gram all-reduce "
@@ -849,9 +858,17 @@ def main():
             lib.PROFILER = None
             roof, breakdown = inference_roofline(agg, min(args.steps, 3), precision, args.workload)
 
-    # BASELINE.json's metric has two halves: "HSI cubes/s (31x512x512 infer) & train patches/s".  The default run reports
-    # the second half as a sub-object of the same line (same contract fields, its own roofline / e2e / cpu_baseline).
     ws_bytes = net.engine().ws.bytes()
+    # N > 1: the same GPUs then restore ONE scene together (BASELINE config 3 as specified: rows split with halos, strong
+    # scaling) — reported as the "scene_sharded" sub-object of the line, like "train"
+    rows_line = None
+    if world > 1 and args.workload == "cube512" and not args.no_rows and args.precision != "fp32_exact":
+        del net
+        torch.cuda.empty_cache()
+        try:
+            rows_line = run_sharded(args, embedded=True)
+        except Exception as e:  # noqa: BLE001 - the weak-scaling line must not be lost to a transport problem
+            rows_line = {"error": f"{type(e).__name__}: {e}"}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -877,6 +894,8 @@ def main():
                 "h2d_bytes_per_step": x_host.numel() * 4 + tid_host.numel() * 8, "d2h_bytes_per_step": out_host.numel() * 4},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cb, "kernels": breakdown,
     }
+    if rows_line is not None:
+        line["scene_sharded"] = rows_line
     if train_line is not None:
         train_line.pop("kernels", None)
         if not args.no_cpu_baseline:

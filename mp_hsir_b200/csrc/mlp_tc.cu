@@ -4,10 +4,14 @@
 // The 2*hidden intermediate never leaves the SM.  Per 128-row tile the hidden dimension is walked in chunks of
 // 64 units (= 128 interleaved (value, gate) fc1 columns = one 64-k slab of fc2):
 //     MMA  : acc1[j&1] (TMEM, 128 cols)  = LN(X) . W1_j^T                (K = C, bf16 hi/lo split operands)
-//     GLU  : 8 epilogue warps drain acc1 with tcgen05.ld, add b1, value*gelu(gate), split to bf16 hi/lo and write
-//            the [128 x 64] tile straight into a 128-byte-swizzled K-major shared-memory slab H_j (the TMEM
-//            row-per-thread layout is already the slab's row layout, so no transpose is needed)
-//     MMA  : acc2 (TMEM, C cols)        += H_j . W2_j^T                  (K = 64)
+//     GLU  : 16 warps drain acc1 with tcgen05.ld, add b1, value*gelu(gate), split to bf16 hi/lo and write the
+//            [128 x 64] tile H_j back into TENSOR MEMORY with tcgen05.st (two bf16 per 32-bit column: the row-per-lane
+//            layout of the accumulator is the layout of a TMEM A operand, so no transpose and no shared memory)
+//     MMA  : acc2 (TMEM, C cols)        += H_j . W2_j^T                  (K = 64, A from TMEM, B from shared memory)
+// (ncu / role counters: with both operands in shared memory the N = 128 MMAs are bound by its 128 B/clk — 8 KB of operand
+// reads per 64-clk instruction — and the MMA thread spent 75 % of the kernel blocked on issue; H in TMEM removes a third
+// of the operand reads, the H stores, and frees 64 KB for a deeper weight ring.  debug flag 8 selects the old
+// shared-memory H path.)
 // with fc1 of chunk j+1 issued before fc2 of chunk j so the tensor pipe never waits for the GLU warps.
 // X slabs arrive by TMA (2-D tensor map) and are LayerNorm-ed / split in place by 8 converter warps exactly as in
 // gemm_tc.cu; W1 / W2 blocks stream through a cp.async.bulk ring.  HBM traffic per token: read C (+C residual),
@@ -49,6 +53,7 @@ struct MlpArgs {
   int num_tiles;
   long long* dbg;
   int dbg_flags;  // timing experiments only: 1 = skip gelu, 2 = skip bias shuffles, 4 = skip bf16 split
+  int h_tmem;     // 1: the GLU output H lives in tensor memory (A operand of fc2 from TMEM); 0: shared-memory H ring
 };
 
 #define M_T0() (p.dbg ? clock64() : 0)
@@ -66,7 +71,7 @@ struct MlpSmem {
 // One GLU work item: 32 fc1 columns (= 16 hidden units) x 32 rows of TMEM lane quadrant `quad`.
 // acc1 (+ b1) -> value * gelu(gate) -> bf16 hi/lo -> chunks 2i, 2i+1 of the K-major swizzled H slab row.
 __device__ __forceinline__ void glu_item(const MlpArgs& p, uint32_t tmem_col_addr, float bias_lane, bool cols_ok, uint8_t* hdst,
-                                         int row, int i, int parts) {
+                                         int row, int i, int parts, uint32_t h_taddr) {
   uint32_t r[32];
   tmem_ld32(tmem_col_addr, r);
   uint32_t hi[8], lo[8];
@@ -85,6 +90,13 @@ __device__ __forceinline__ void glu_item(const MlpArgs& p, uint32_t tmem_col_add
       hv[u] = val * gelu_erf_fast(gat);
     }
     split2(hv[0], hv[1], hi[e], lo[e]);
+  }
+  if (p.h_tmem) {
+    // hidden units 16 i .. 16 i + 15 of this row = columns 8 i .. 8 i + 7 of the hi part (lo part 32 columns further)
+    tmem_st8(h_taddr + 8 * i, hi);
+    if (parts == 2) tmem_st8(h_taddr + 32 + 8 * i, lo);
+    tmem_st_wait();
+    return;
   }
 #pragma unroll
   for (int cc = 0; cc < 2; ++cc) {
@@ -108,8 +120,9 @@ __device__ __forceinline__ void glu_chunk(const MlpArgs& p, MlpSmem* sm, uint8_t
   mbar_wait(smem_u32(&sm->h_empty[hs]), ((h_it >> 1) & 1) ^ 1);
   tc_fence_after();
   glu_item(p, tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128 + i * 32, bias_lane, j * 128 + i * 32 < p.N1,
-           h_ring + (size_t)hs * h_slot_bytes, quad * 32 + lane, i, parts);
-  fence_proxy_async();
+           h_ring + (size_t)hs * h_slot_bytes, quad * 32 + lane, i, parts,
+           tmem_base + ((uint32_t)(quad * 32) << 16) + 384 + hs * 64);
+  if (!p.h_tmem) fence_proxy_async();
   tc_fence_before();
   __syncwarp();
   if (lane == 0) {
@@ -127,9 +140,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
   const int b_slot_bytes = M_SLAB * parts;
   uint8_t* a_ring = smem_raw + 1024;
   uint8_t* h_ring = a_ring + (size_t)M_NA * M_STAGE;
-  uint8_t* b_ring = h_ring + 2 * (size_t)h_slot_bytes;
-  // the final-epilogue transpose buffers (8 x 4 KB) alias H slot 0: when acc2_full fires every MMA that read the
-  // H slabs of this tile has completed, and the next tile's first GLU write waits for this warp's own epilogue
+  // H in tensor memory: no H ring, the final-epilogue transpose buffers (8 x 4 KB) own their 32 KB.
+  // H in shared memory: they alias H slot 0 — when acc2_full fires every MMA that read the H slabs of this tile has
+  // completed, and the next tile's first GLU write waits for this warp's own epilogue (bar.sync 2 below)
+  uint8_t* b_ring = h_ring + (p.h_tmem ? (size_t)8 * M_STG_FLOATS * 4 : 2 * (size_t)h_slot_bytes);
   float* staging = reinterpret_cast<float*>(h_ring);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -264,13 +278,25 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
           const uint32_t d_addr = tmem_base + ACC2_COL;
           const uint64_t ah0 = make_desc(a_addr), bh0 = make_desc(b_addr);
           const uint64_t al0 = make_desc(a_addr + M_SLAB), bl0 = make_desc(b_addr + M_SLAB);
+          const uint32_t th0 = tmem_base + 384 + hs * 64, tl0 = th0 + 32;   // H hi / lo parts in tensor memory
           if (elect_one()) {
+            if (p.h_tmem) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_bf16(d_addr, ah0 + 2 * k, bh0 + 2 * k, idesc, (j | k) != 0);
-              if (parts == 2) {
-                umma_bf16(d_addr, ah0 + 2 * k, bl0 + 2 * k, idesc, 1);
-                umma_bf16(d_addr, al0 + 2 * k, bh0 + 2 * k, idesc, 1);
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16_tmem_a(d_addr, th0 + 8 * k, bh0 + 2 * k, idesc, (j | k) != 0);
+                if (parts == 2) {
+                  umma_bf16_tmem_a(d_addr, th0 + 8 * k, bl0 + 2 * k, idesc, 1);
+                  umma_bf16_tmem_a(d_addr, tl0 + 8 * k, bh0 + 2 * k, idesc, 1);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(d_addr, ah0 + 2 * k, bh0 + 2 * k, idesc, (j | k) != 0);
+                if (parts == 2) {
+                  umma_bf16(d_addr, ah0 + 2 * k, bl0 + 2 * k, idesc, 1);
+                  umma_bf16(d_addr, al0 + 2 * k, bh0 + 2 * k, idesc, 1);
+                }
               }
             }
             umma_commit(smem_u32(&sm->b_empty[b_slot]));
@@ -355,7 +381,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
       __syncwarp();  // bar.sync is .aligned: the warp must be converged again after the lane-0 branch (synccheck)
       // the transpose buffers alias the H ring: nobody (epilogue or converter warp) may start the next tile's GLU
       // writes before every epilogue warp has left its staging area
-      if (tile + (int)gridDim.x < num_tiles) asm volatile("bar.sync 2, 512;" ::: "memory");
+      if (!p.h_tmem && tile + (int)gridDim.x < num_tiles) asm volatile("bar.sync 2, 512;" ::: "memory");
       M_ACC(g_epi, te);
     }
     if (p.dbg && warp == 2 && lane == 0) {
@@ -463,7 +489,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
       // ---- then help with the GLU stage of this tile (H slots double as the epilogue warps' staging: wait until
       //      they have finished the previous tile's final epilogue) ----
       __syncwarp();  // converged again after the lane-0 arrive of the last slab (bar.sync is .aligned)
-      if (tile != (int)blockIdx.x) asm volatile("bar.sync 2, 512;" ::: "memory");
+      if (!p.h_tmem && tile != (int)blockIdx.x) asm volatile("bar.sync 2, 512;" ::: "memory");
       for (int j = 0; j < NJ; ++j, ++c1_it, ++h_it)
         glu_chunk(p, sm, h_ring, h_slot_bytes, tmem_base, j, c1_it, h_it, gquad, ggroup, lane, parts);
     }
@@ -521,7 +547,10 @@ extern "C" int mphsir_mlp_fwd(const mphsir_mlp_params* q, void* stream) {
   a.Y = q->Y; a.ldy = q->ldy; a.M = q->M; a.C = q->C;
   a.N1 = 2 * q->hid_pad; a.Np1 = (a.N1 + 15) / 16 * 16; a.ks1 = q->C / 64; a.nj = (a.N1 + 127) / 128;
   a.parts = q->precision == MPHSIR_PREC_BF16X3 ? 2 : 1;
-  a.nb = a.parts == 2 ? 3 : 8;  // 1 + 64 + 64 + 96 = 225 KB (bf16x3); 1 + 64 + 32 + 128 = 225 KB (bf16)
+  a.h_tmem = (tc::g_mlp_flags & 8) ? 0 : 1;
+  // shared memory (<= 225 KB): 1 KB barriers + A ring 64 KB + {H in TMEM: 32 KB staging | 2 H slots} + weight ring
+  //   H in TMEM : bf16x3 4 x 32 KB, bf16 8 x 16 KB        H in smem : bf16x3 3 x 32 KB (H 64 KB), bf16 8 x 16 KB (H 32 KB)
+  a.nb = a.parts == 2 ? (a.h_tmem ? 4 : 3) : 8;
   a.num_tiles = (q->M + 127) / 128;
   PFN_cuTensorMapEncodeTiled enc = tc::mlp_encode_fn();
   MPHSIR_REQUIRE(enc != nullptr, "mlp: cuTensorMapEncodeTiled unavailable");
@@ -545,7 +574,8 @@ extern "C" int mphsir_mlp_fwd(const mphsir_mlp_params* q, void* stream) {
     }
     configured = true;
   }
-  const size_t smem = 1024 + (size_t)tc::M_NA * tc::M_STAGE + 2 * (size_t)tc::M_SLAB * a.parts + (size_t)a.nb * tc::M_SLAB * a.parts;
+  const size_t smem = 1024 + (size_t)tc::M_NA * tc::M_STAGE + (a.h_tmem ? (size_t)8 * tc::M_STG_FLOATS * 4 : 2 * (size_t)tc::M_SLAB * a.parts) +
+                      (size_t)a.nb * tc::M_SLAB * a.parts;
   const int grid = a.num_tiles < sm_count ? a.num_tiles : sm_count;
   tc::mlp_tc_kernel<<<grid, tc::kMlpThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   return check_launch("mlp(tc)");
