@@ -243,6 +243,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   // NCHW / pixel-unshuffle stores are already coalesced (or hopeless) in the row-per-thread TMEM mapping
   constexpr bool DIRECT = (EPI == TC_OUT_NCHW_RES || EPI == TC_OUT_UNSHUFFLE);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  pdl_launch_dependents();
   Smem* sm = reinterpret_cast<Smem*>(smem_raw);
   const int parts = p.parts;                       // 1 (bf16x1) or 2 (bf16x3)
   const int a_slot_bytes = STAGE_BYTES;
@@ -278,6 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   __syncthreads();
   if (p.cluster > 1) cluster_sync_all();  // the peer's mbarriers exist before any multicast copy / commit targets them
   tc_fence_after();
+  pdl_wait();  // everything above overlapped the predecessor's tail; from here on its results are read / its inputs overwritten
   const uint32_t tmem_base = sm->tmem_base;
   const int num_tiles = p.num_tiles;
   const uint32_t crank = p.cluster > 1 ? cluster_ctarank() : 0;
@@ -950,13 +952,15 @@ static int launch_epi2(const TcArgs& a, size_t smem, int grid, cudaStream_t st) 
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = a.cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, LN>, a);
   if (le != cudaSuccess) {
     set_error("gemm(tc): cudaLaunchKernelEx failed: %s", cudaGetErrorString(le));
@@ -1043,6 +1047,9 @@ static bool make_epi_map(CUtensorMap* tm, const float* base, long long ld, int c
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static int g_pdl = 1;
+int pdl_enabled() { return g_pdl; }
+void set_pdl_enabled(int on) { g_pdl = on; }
 static long long* g_dbg = nullptr;
 static int g_tepi_enabled = 1;
 void set_tepi_enabled(int on) { g_tepi_enabled = on; }
@@ -1123,6 +1130,7 @@ extern "C" MPHSIR_API void mphsir_debug_tc_counters(long long* buf) { tc::set_de
 extern "C" MPHSIR_API void mphsir_debug_tc_cluster(int enabled) { tc::set_cluster_enabled(enabled); }
 extern "C" MPHSIR_API void mphsir_debug_tc_tma_epilogue(int enabled) { tc::set_tepi_enabled(enabled); }
 extern "C" MPHSIR_API void mphsir_debug_tc_ebox1(int enabled) { tc::set_ebox1_enabled(enabled); }
+extern "C" MPHSIR_API void mphsir_debug_pdl(int enabled) { tc::set_pdl_enabled(enabled); }
 
 extern "C" size_t mphsir_bimg_bytes(int N, int K) {
   const int Np = (N + 15) / 16 * 16, Ks = (K + 63) / 64;

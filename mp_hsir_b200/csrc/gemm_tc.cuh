@@ -69,6 +69,8 @@ void set_debug_buffer(long long* p);
 void set_cluster_enabled(int on);
 void set_tepi_enabled(int on);
 void set_ebox1_enabled(int on);
+int pdl_enabled();           // programmatic dependent launch of the persistent tcgen05 kernels (tc_ptx.cuh: pdl_*)
+void set_pdl_enabled(int on);
 
 }  // namespace tc
 }  // namespace mphsir

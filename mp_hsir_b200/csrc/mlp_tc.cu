@@ -134,6 +134,7 @@ __device__ __forceinline__ void glu_chunk(const MlpArgs& p, MlpSmem* sm, uint8_t
 
 __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_constant__ MlpArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  pdl_launch_dependents();
   MlpSmem* sm = reinterpret_cast<MlpSmem*>(smem_raw);
   const int parts = p.parts;
   const int h_slot_bytes = M_SLAB * parts;
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // prologue above overlaps the predecessor's tail (programmatic dependent launch)
   const uint32_t tmem_base = sm->tmem_base;
   const uint32_t ACC2_COL = 256;
 
@@ -577,6 +579,20 @@ extern "C" int mphsir_mlp_fwd(const mphsir_mlp_params* q, void* stream) {
   const size_t smem = 1024 + (size_t)tc::M_NA * tc::M_STAGE + (a.h_tmem ? (size_t)8 * tc::M_STG_FLOATS * 4 : 2 * (size_t)tc::M_SLAB * a.parts) +
                       (size_t)a.nb * tc::M_SLAB * a.parts;
   const int grid = a.num_tiles < sm_count ? a.num_tiles : sm_count;
-  tc::mlp_tc_kernel<<<grid, tc::kMlpThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(tc::kMlpThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tc::pdl_enabled() ? 1 : 0;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, tc::mlp_tc_kernel, a);
+  if (le != cudaSuccess) {
+    set_error("mlp(tc): cudaLaunchKernelEx failed: %s", cudaGetErrorString(le));
+    return MPHSIR_ERR_CUDA;
+  }
   return check_launch("mlp(tc)");
 }

@@ -182,6 +182,14 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Programmatic dependent launch (launch attribute cudaLaunchAttributeProgrammaticStreamSerialization): a kernel lets its
+// successor in the stream be scheduled as soon as all of ITS CTAs are resident (pdl_launch_dependents at the top) and blocks
+// before its first global-memory access until the predecessor grid has completed and flushed (pdl_wait).  What overlaps is
+// the successor's launch latency and prologue (barrier init, TMEM allocation, descriptor fetches) with the predecessor's
+// tail; without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;

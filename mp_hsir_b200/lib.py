@@ -106,6 +106,7 @@ SIGNATURES = {
     "mphsir_debug_dwgram_tma": (None, [_I]),
     "mphsir_debug_tc_tma_epilogue": (None, [_I]),
     "mphsir_debug_tc_ebox1": (None, [_I]),
+    "mphsir_debug_pdl": (None, [_I]),
     "mphsir_bimg_bytes": (C.c_size_t, [_I, _I]),
     "mphsir_pack_bimg": (_I, [_VP, _I, _I, _LL, _VP, _I, _I, _I, _VP]),
     "mphsir_pack_bimg_multi": (_I, [C.POINTER(PackItem), _I, _VP]),
