@@ -720,7 +720,7 @@ def main():
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
                     help="--shard rows: 'peer' = libmphsir one-kernel halo exchange / all-reduce over NVLink peer memory (CUDA IPC "
                          "windows), 'nccl' = torch.distributed send/recv + all_reduce")
-    ap.add_argument("--no-pdl", action="store_true", help="plain stream-ordered launches (A/B switch for programmatic dependent launch)")
+    ap.add_argument("--pdl", action="store_true", help="programmatic dependent launch of the tcgen05 kernels (A/B switch; measured: no gain)")
     ap.add_argument("--reference-budget-s", type=float, default=120.0,
                     help="--impl reference: stop timing further steps once this many seconds of timed work are spent")
     ap.add_argument("--precision", default=None, choices=["fp32", "fp32_exact", "bf16"],
@@ -737,9 +737,9 @@ def main():
         args.precision = "bf16" if args.workload == "train64" else "fp32"
     if args.impl == "reference":
         return run_reference(args)
-    if args.no_pdl:
+    if args.pdl:
         from mp_hsir_b200 import lib as _lib
-        _lib.load().mphsir_debug_pdl(0)
+        _lib.load().mphsir_debug_pdl(1)
     if args.workload == "train64":
         return run_train(args)
     if args.shard == "rows":

@@ -1047,7 +1047,8 @@ static bool make_epi_map(CUtensorMap* tm, const float* base, long long ld, int c
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static int g_pdl = 1;
+static int g_pdl = 0;  // measured on B200: no gain (cube512 14.69 vs 14.78 ms, train64 / patch16 unchanged) — one CTA per SM at 225 KB
+                       // of shared memory leaves the successor nothing to overlap but its launch latency; off by default
 int pdl_enabled() { return g_pdl; }
 void set_pdl_enabled(int on) { g_pdl = on; }
 static long long* g_dbg = nullptr;

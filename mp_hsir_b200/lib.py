@@ -191,6 +191,8 @@ def load() -> C.CDLL:
         fn.argtypes = args
     if lib.mphsir_version() < 100:
         raise RuntimeError("libmphsir.so is older than this Python package; rebuild it")
+    if os.environ.get("MPHSIR_PDL") in ("0", "1"):     # A/B switch: programmatic dependent launch of the tcgen05 kernels
+        lib.mphsir_debug_pdl(int(os.environ["MPHSIR_PDL"]))
     _lib = lib
     return lib
 
