@@ -1,0 +1,474 @@
+// Shifted-window attention core on tcgen05 (sm_100a), TMA-fed, flash-style: softmax(q k^T + bias + mask) v for every
+// 8x8 window and head (Spatial_Attention.forward, net/MP_HSIR.py:198-215) with the roll / partition / reverse of
+// PGSSTB.forward (:671-696) folded into the TMA coordinates and the store addresses.
+//
+// A tile is TWO windows of one head: 128 query rows = the M of one tcgen05.mma ("pack two windows per MMA").
+//   producer (1 thread) : 24 TMA boxes [4 x 4 pixels x hd] of the fp32 q | k | v columns of the LN+QKV GEMM output — a
+//                         window is four such boxes, none of which straddles the cyclic wrap of the shifted grid
+//   converters (8 warps): fp32 -> bf16 hi (+ lo) operand images, 128-byte-swizzled K-major: Q [128 x hd] (pre-scaled),
+//                         K [128 x hd], and V TRANSPOSED, Vt [hd x 128 keys] (lane = channel, 8 keys per 16-byte store)
+//   MMA (1 thread)      : S = Q K^T            (M 128, N 128, K hd; the two windows' blocks sit on the diagonal)
+//   softmax (4 warps)   : tcgen05.ld of the row's OWN window's 64 logits, + relative-position bias + closed-form Swin
+//                         mask, softmax in registers, P -> bf16 hi/lo -> tcgen05.st back into TENSOR MEMORY in the layout of
+//                         a TMEM A operand (the other window's 64 key columns stay zero: written once at kernel start)
+//   MMA                 : O = P Vt^T           (A = P from tensor memory, B = Vt from shared memory; M 128, N hd, K 128)
+//   epilogue (same warps): tcgen05.ld O, store the fp32 row in image order, per-window token mean (:135) by a register
+//                         butterfly over the warp + one shared-memory hand-off between the two warps of a window
+// Probabilities and logits never touch shared or global memory.  All hand-offs are mbarriers; landing zone, operand
+// images, S / P / O are single-buffered, which already lets the TMA loads and the conversion of tile i+1 run under the
+// MMAs, softmax and stores of tile i.  HBM traffic: read 3 hd, write hd floats per token and head (the minimum).
+// Precision: bf16x3 (hi*hi + hi*lo + lo*hi) or bf16, as the mma.sync kernel it replaces (window_attn_mma.cu, kept for
+// head dims 48 / 96 of the remote-sensing model).
+#include <cuda_bf16.h>
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace mphsir {
+namespace watc {
+
+using namespace tc;
+
+constexpr int kThreads = 448;  // warp 0: TMA producer, 1: MMA, 2-5: softmax + epilogue, 6-13: converters
+constexpr int kSoftWarp0 = 2, kConvWarp0 = 6, kConvThreads = 256;
+constexpr int S_COL = 0, PH_COL = 128, PL_COL = 192, O_COL = 256;
+
+template <int HD>
+struct Plan {
+  static constexpr int LAND_OP = 128 * HD * 4;  // one operand (q, k or v) of both windows, fp32
+  static constexpr int QK_PART = 128 * 128;     // [128 rows][128 B] (row pitch 128 B for HD = 32 as well)
+  static constexpr int VT_SLAB = HD * 128;      // [HD rows][64 keys]
+  static constexpr int VT_PART = 2 * VT_SLAB;
+  static size_t smem(int parts) { return 1024 + 3 * (size_t)LAND_OP + 2 * (size_t)parts * QK_PART + (size_t)parts * VT_PART + 2 * 4 * HD * 4; }
+};
+
+struct Bars {
+  uint64_t land_full, land_empty, qk_full, qk_empty, v_full, v_empty, s_full, s_empty, p_full, p_empty, o_full, o_empty;
+  uint32_t tmem_base;
+};
+
+struct Args {
+  alignas(64) CUtensorMap tm;  // qkv as [B][H][W][3C] fp32, box [1][4][4][HD]
+  const float* bias;           // [heads][64][64]
+  float* out;
+  long long ldo;
+  float* win_mean;             // [B*nW][C]
+  int B, H, W, C, heads, shift, parts, mask_H, mask_y0;
+  int n_windows, n_tiles;
+};
+
+// token m of a tile (two windows of 64 tokens, row-major 8x8) -> float offset of its pixel inside one operand's landing zone
+template <int HD>
+__device__ __forceinline__ int land_pixel(int m) {
+  const int win = m >> 6, t = m & 63, r = t >> 3, c = t & 7;
+  const int box = win * 4 + (r >> 2) * 2 + (c >> 2);
+  return (box * 16 + (r & 3) * 4 + (c & 3)) * HD;
+}
+
+template <int HD>
+__global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __grid_constant__ Args p) {
+  using P = Plan<HD>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Bars* bar = reinterpret_cast<Bars*>(smem_raw);
+  uint8_t* land = smem_raw + 1024;
+  uint8_t* q_img = land + 3 * P::LAND_OP;
+  uint8_t* k_img = q_img + p.parts * P::QK_PART;
+  uint8_t* vt_img = k_img + p.parts * P::QK_PART;
+  float* psum = reinterpret_cast<float*>(vt_img + p.parts * P::VT_PART);  // [2 (tile parity)][4 quadrants][HD]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int parts = p.parts;
+  const int nWx = p.W >> 3, nW = (p.H >> 3) * nWx;
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar->land_full), 1);
+    mbar_init(smem_u32(&bar->land_empty), kConvThreads / 32);
+    mbar_init(smem_u32(&bar->qk_full), kConvThreads / 32);
+    mbar_init(smem_u32(&bar->qk_empty), 1);
+    mbar_init(smem_u32(&bar->v_full), kConvThreads / 32);
+    mbar_init(smem_u32(&bar->v_empty), 1);
+    mbar_init(smem_u32(&bar->s_full), 1);
+    mbar_init(smem_u32(&bar->s_empty), 4);
+    mbar_init(smem_u32(&bar->p_full), 4);
+    mbar_init(smem_u32(&bar->p_empty), 1);
+    mbar_init(smem_u32(&bar->o_full), 1);
+    mbar_init(smem_u32(&bar->o_empty), 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&bar->tmem_base), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bar->tmem_base;
+
+  if (warp == 0) {
+    // =============================== TMA producer ============================================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const int pair = tile / p.heads, h = tile - pair * p.heads;
+        mbar_wait(smem_u32(&bar->land_empty), (it & 1) ^ 1);
+        const int nwin = (2 * pair + 1 < p.n_windows) ? 2 : 1;
+        const uint32_t full = smem_u32(&bar->land_full);
+        mbar_expect_tx(full, (uint32_t)(3 * nwin * 64 * HD * 4));
+        for (int win = 0; win < nwin; ++win) {
+          const int w = 2 * pair + win;
+          const int b = w / nW, wrem = w - b * nW;
+          const int wi = wrem / nWx, wj = wrem - wi * nWx;
+#pragma unroll
+          for (int op = 0; op < 3; ++op)
+#pragma unroll
+            for (int bx = 0; bx < 4; ++bx) {
+              int y = wi * 8 + (bx >> 1) * 4 + p.shift, x = wj * 8 + (bx & 1) * 4 + p.shift;  // roll(-s): shifted[ys] = img[(ys+s) % H]
+              if (y >= p.H) y -= p.H;
+              if (x >= p.W) x -= p.W;
+              tma_load_4d(smem_u32(land + op * P::LAND_OP + ((win * 4 + bx) * 16) * HD * 4), &p.tm, op * p.C + h * HD, x, y, b, full);
+            }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ==============================================================
+    uint32_t it = 0;
+    const uint32_t idesc_s = make_idesc(128), idesc_o = make_idesc(HD);
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      // ---- S = Q K^T ----
+      mbar_wait(smem_u32(&bar->qk_full), it & 1);
+      mbar_wait(smem_u32(&bar->s_empty), (it & 1) ^ 1);
+      tc_fence_after();
+      {
+        const uint64_t qh = make_desc(smem_u32(q_img)), kh = make_desc(smem_u32(k_img));
+        const uint64_t ql = make_desc(smem_u32(q_img + P::QK_PART)), kl = make_desc(smem_u32(k_img + P::QK_PART));
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < HD / 16; ++ks) {
+            umma_bf16(tmem_base + S_COL, qh + 2 * ks, kh + 2 * ks, idesc_s, ks != 0);
+            if (parts == 2) {
+              umma_bf16(tmem_base + S_COL, qh + 2 * ks, kl + 2 * ks, idesc_s, 1);
+              umma_bf16(tmem_base + S_COL, ql + 2 * ks, kh + 2 * ks, idesc_s, 1);
+            }
+          }
+          umma_commit(smem_u32(&bar->s_full));
+          umma_commit(smem_u32(&bar->qk_empty));
+        }
+        __syncwarp();
+      }
+      // ---- O = P Vt^T : A from tensor memory ----
+      mbar_wait(smem_u32(&bar->v_full), it & 1);
+      mbar_wait(smem_u32(&bar->p_full), it & 1);
+      mbar_wait(smem_u32(&bar->o_empty), (it & 1) ^ 1);
+      tc_fence_after();
+      {
+        const uint32_t vt = smem_u32(vt_img);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {  // 16 keys per step
+            const uint64_t vh = make_desc(vt + (kk >> 2) * P::VT_SLAB) + 2 * (kk & 3);
+            const uint64_t vl = make_desc(vt + P::VT_PART + (kk >> 2) * P::VT_SLAB) + 2 * (kk & 3);
+            umma_bf16_tmem_a(tmem_base + O_COL, tmem_base + PH_COL + 8 * kk, vh, idesc_o, kk != 0);
+            if (parts == 2) {
+              umma_bf16_tmem_a(tmem_base + O_COL, tmem_base + PH_COL + 8 * kk, vl, idesc_o, 1);
+              umma_bf16_tmem_a(tmem_base + O_COL, tmem_base + PL_COL + 8 * kk, vh, idesc_o, 1);
+            }
+          }
+          umma_commit(smem_u32(&bar->o_full));
+          umma_commit(smem_u32(&bar->v_empty));
+          umma_commit(smem_u32(&bar->p_empty));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < kConvWarp0) {
+    // =============================== softmax + epilogue (warps 2..5) =========================================
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may touch
+    const int m = quad * 32 + lane;            // query row of the tile
+    const int win = m >> 6, t = m & 63, r = t >> 3, c = t & 7;
+    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+    {  // the OTHER window's key columns of P are never written again: zero them once
+      const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        tmem_st8(trow + PH_COL + 32 * (win ^ 1) + 8 * g, z);
+        tmem_st8(trow + PL_COL + 32 * (win ^ 1) + 8 * g, z);
+      }
+      tmem_st_wait();
+    }
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int pair = tile / p.heads, h = tile - pair * p.heads;
+      const int w = 2 * pair + win;
+      const bool valid = w < p.n_windows;
+      const int wc = valid ? w : 2 * pair;
+      const int b = wc / nW, wrem = wc - b * nW;
+      const int wi = wrem / nWx, wj = wrem - wi * nWx;
+      // Swin mask (:643-658) in closed form: only the last window row / column of the SCENE's shifted grid is split
+      int ysg = wi * 8 + p.mask_y0;
+      if (ysg >= p.mask_H) ysg -= p.mask_H;
+      const bool lastrow = p.shift != 0 && ysg >= p.mask_H - 8;
+      const bool lastcol = p.shift != 0 && wj == nWx - 1;
+      const bool rq_low = r < 4, cq_low = c < 4;
+      const float* brow = p.bias + ((long long)h * 64 + t) * 64;
+
+      mbar_wait(smem_u32(&bar->s_full), it & 1);
+      tc_fence_after();
+      float s[64];
+      {
+        uint32_t raw[32];
+        tmem_ld32(trow + S_COL + 64 * win, raw);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(raw[j]);
+        tmem_ld32(trow + S_COL + 64 * win + 32, raw);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s[32 + j] = __uint_as_float(raw[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar->s_empty));  // S is in registers: the next tile's Q K^T may overwrite it
+      __syncwarp();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j4 = 0; j4 < 16; ++j4) {
+        const float4 b4 = ldg4(brow + 4 * j4);
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int kj = 4 * j4 + e;
+          const bool masked = (lastrow && (rq_low != (kj < 32))) || (lastcol && (cq_low != ((kj & 7) < 4)));
+          s[kj] += bb[e] + (masked ? -100.f : 0.f);
+          mx = fmaxf(mx, s[kj]);
+        }
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        s[j] = __expf(s[j] - mx);
+        sum += s[j];
+      }
+      const float inv = 1.0f / sum;
+      // P = softmax row -> bf16 hi/lo pairs -> tensor memory (A operand of O = P V)
+      mbar_wait(smem_u32(&bar->p_empty), (it & 1) ^ 1);
+      tc_fence_after();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split2(s[16 * g + 2 * e] * inv, s[16 * g + 2 * e + 1] * inv, hi[e], lo[e]);
+        tmem_st8(trow + PH_COL + 32 * win + 8 * g, hi);
+        if (parts == 2) tmem_st8(trow + PL_COL + 32 * win + 8 * g, lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar->p_full));
+      __syncwarp();
+
+      // ---- epilogue: O row -> image order, window mean ----
+      mbar_wait(smem_u32(&bar->o_full), it & 1);
+      tc_fence_after();
+      float o[HD];
+      {
+        uint32_t raw[32];
+#pragma unroll
+        for (int c0 = 0; c0 < HD; c0 += 32) {
+          tmem_ld32(trow + O_COL + c0, raw);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[c0 + j] = __uint_as_float(raw[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar->o_empty));
+      __syncwarp();
+      if (valid) {
+        int y = wi * 8 + r + p.shift, x = wj * 8 + c + p.shift;
+        if (y >= p.H) y -= p.H;
+        if (x >= p.W) x -= p.W;
+        float* dst = p.out + ((long long)(b * p.H + y) * p.W + x) * p.ldo + h * HD;
+#pragma unroll
+        for (int j4 = 0; j4 < HD / 4; ++j4)
+          *reinterpret_cast<float4*>(dst + 4 * j4) = make_float4(o[4 * j4], o[4 * j4 + 1], o[4 * j4 + 2], o[4 * j4 + 3]);
+      }
+      // column sums over the warp's 32 rows: butterfly that halves the column set at every step; afterwards lane l holds
+      // HD/32 consecutive columns starting at col0(l)
+      int col0 = 0;
+#pragma unroll
+      for (int st = 0; st < 5; ++st) {
+        const int off = 16 >> st, half = HD >> (st + 1);
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+          const float send = upper ? o[i] : o[i + half];
+          const float keep = upper ? o[i + half] : o[i];
+          o[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+        col0 += upper ? half : 0;
+      }
+      float* ps = psum + ((it & 1) * 4 + quad) * HD;
+#pragma unroll
+      for (int i = 0; i < HD / 32; ++i) ps[col0 + i] = o[i];
+      asm volatile("bar.sync 3, 128;" ::: "memory");  // the four softmax warps (converged: every path above ends in __syncwarp / shuffles)
+      const int et = threadIdx.x - kSoftWarp0 * 32;   // 0..127
+      if (et < 2 * HD) {
+        const int ew = et / HD, col = et - ew * HD;
+        const int wg = 2 * pair + ew;
+        if (wg < p.n_windows) {
+          const float* p0 = psum + ((it & 1) * 4 + 2 * ew) * HD;
+          p.win_mean[(long long)wg * p.C + h * HD + col] = (p0[col] + p0[HD + col]) * (1.0f / 64.0f);
+        }
+      }
+    }
+  } else {
+    // =============================== converters (warps 6..13) ================================================
+    const int ct = threadIdx.x - kConvWarp0 * 32;  // 0..255
+    const float scale = rsqrtf((float)HD);
+    const float* lq = reinterpret_cast<const float*>(land);
+    const float* lk = reinterpret_cast<const float*>(land + P::LAND_OP);
+    const float* lv = reinterpret_cast<const float*>(land + 2 * P::LAND_OP);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int pair = tile / p.heads;
+      const bool two = 2 * pair + 1 < p.n_windows;
+      mbar_wait(smem_u32(&bar->land_full), it & 1);
+      // ---- Q (pre-scaled), K: row m, 16-byte chunk ch of the K-major image ----
+      mbar_wait(smem_u32(&bar->qk_empty), (it & 1) ^ 1);
+      constexpr int CH = HD / 8;
+#pragma unroll
+      for (int i = 0; i < 128 * CH / kConvThreads; ++i) {
+        const int item = ct + kConvThreads * i;
+        const int m = item / CH, ch = item - m * CH;
+        const bool ok = two || m < 64;
+        const int lo_ = land_pixel<HD>(m) + ch * 8;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+        if (ok) {
+          a0 = *reinterpret_cast<const float4*>(lq + lo_);
+          a1 = *reinterpret_cast<const float4*>(lq + lo_ + 4);
+          b0 = *reinterpret_cast<const float4*>(lk + lo_);
+          b1 = *reinterpret_cast<const float4*>(lk + lo_ + 4);
+        }
+        const int off = m * 128 + ((ch ^ (m & 7)) << 4);
+        uint4 hi, lo;
+        split2(a0.x * scale, a0.y * scale, hi.x, lo.x);
+        split2(a0.z * scale, a0.w * scale, hi.y, lo.y);
+        split2(a1.x * scale, a1.y * scale, hi.z, lo.z);
+        split2(a1.z * scale, a1.w * scale, hi.w, lo.w);
+        *reinterpret_cast<uint4*>(q_img + off) = hi;
+        if (parts == 2) *reinterpret_cast<uint4*>(q_img + P::QK_PART + off) = lo;
+        split2(b0.x, b0.y, hi.x, lo.x);
+        split2(b0.z, b0.w, hi.y, lo.y);
+        split2(b1.x, b1.y, hi.z, lo.z);
+        split2(b1.z, b1.w, hi.w, lo.w);
+        *reinterpret_cast<uint4*>(k_img + off) = hi;
+        if (parts == 2) *reinterpret_cast<uint4*>(k_img + P::QK_PART + off) = lo;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar->qk_full));
+      __syncwarp();
+      // ---- V transposed: row = channel d, K = key; one item = 8 keys (one row of a window) of one channel ----
+      mbar_wait(smem_u32(&bar->v_empty), (it & 1) ^ 1);
+#pragma unroll
+      for (int i = 0; i < HD * 16 / kConvThreads; ++i) {
+        const int item = ct + kConvThreads * i;
+        const int kg = item / HD, d = item - kg * HD;   // lanes = consecutive channels: conflict-free scalar reads
+        const int m0 = kg * 8;                          // keys m0 .. m0+7 = window (kg >> 3), row (kg & 7), columns 0..7
+        const bool ok = two || m0 < 64;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = ok ? lv[land_pixel<HD>(m0 + e) + d] : 0.f;
+        uint4 hi, lo;
+        split2(v[0], v[1], hi.x, lo.x);
+        split2(v[2], v[3], hi.y, lo.y);
+        split2(v[4], v[5], hi.z, lo.z);
+        split2(v[6], v[7], hi.w, lo.w);
+        const int off = (kg >> 3) * P::VT_SLAB + d * 128 + (((kg & 7) ^ (d & 7)) << 4);
+        *reinterpret_cast<uint4*>(vt_img + off) = hi;
+        if (parts == 2) *reinterpret_cast<uint4*>(vt_img + P::VT_PART + off) = lo;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&bar->v_full));
+        mbar_arrive(smem_u32(&bar->land_empty));  // every read of the landing zone is done: the next tile may land
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static PFN_cuTensorMapEncodeTiled encode_fn() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(ptr);
+  }
+  return fn;
+}
+
+template <int HD>
+static int launch_t(const float* qkv, int ldqkv, const float* bias, float* out, int ldo, float* win_mean, int B, int H, int W,
+                    int C, int heads, int shift, int parts, int mask_H, int mask_y0, cudaStream_t st) {
+  PFN_cuTensorMapEncodeTiled enc = encode_fn();
+  if (enc == nullptr) {
+    set_error("window_attn(tc): cuTensorMapEncodeTiled unavailable");
+    return MPHSIR_ERR_CUDA;
+  }
+  Args a{};
+  cuuint64_t gdim[4] = {(cuuint64_t)3 * C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)ldqkv * 4, (cuuint64_t)W * ldqkv * 4, (cuuint64_t)H * W * ldqkv * 4};
+  cuuint32_t box[4] = {(cuuint32_t)HD, 4, 4, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (enc(&a.tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(qkv), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+    set_error("window_attn(tc): cuTensorMapEncodeTiled failed (C=%d H=%d W=%d ld=%d)", C, H, W, ldqkv);
+    return MPHSIR_ERR_CUDA;
+  }
+  a.bias = bias; a.out = out; a.ldo = ldo; a.win_mean = win_mean;
+  a.B = B; a.H = H; a.W = W; a.C = C; a.heads = heads; a.shift = shift; a.parts = parts; a.mask_H = mask_H; a.mask_y0 = mask_y0;
+  a.n_windows = B * (H / 8) * (W / 8);
+  a.n_tiles = ((a.n_windows + 1) / 2) * heads;
+  static int sm_count = 0;
+  static bool configured = false;
+  if (!configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(window_attn_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Plan<HD>::smem(2));
+    if (e != cudaSuccess) {
+      set_error("window_attn(tc): cudaFuncSetAttribute(%zu B): %s", Plan<HD>::smem(2), cudaGetErrorString(e));
+      return MPHSIR_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int grid = a.n_tiles < sm_count ? a.n_tiles : sm_count;
+  window_attn_tc_kernel<HD><<<grid, kThreads, Plan<HD>::smem(parts), st>>>(a);
+  return check_launch("window_attn(tc)");
+}
+
+static bool g_enabled = true;
+void set_enabled(int on) { g_enabled = on != 0; }
+
+// head dims 32 / 64 (every stage of the natural-scene model), qkv rows 16-byte aligned
+bool supported(int hd, int ldqkv, int ldo, const float* qkv) {
+  return g_enabled && (hd == 32 || hd == 64) && ldqkv % 4 == 0 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0;
+}
+
+int launch(const float* qkv, int ldqkv, const float* bias, float* out, int ldo, float* win_mean, int B, int H, int W, int C, int heads,
+           int shift, int parts, int mask_H, int mask_y0, cudaStream_t st) {
+  if (C / heads == 32)
+    return launch_t<32>(qkv, ldqkv, bias, out, ldo, win_mean, B, H, W, C, heads, shift, parts, mask_H, mask_y0, st);
+  return launch_t<64>(qkv, ldqkv, bias, out, ldo, win_mean, B, H, W, C, heads, shift, parts, mask_H, mask_y0, st);
+}
+
+}  // namespace watc
+}  // namespace mphsir
+
+extern "C" MPHSIR_API void mphsir_debug_window_attn_tc(int enabled) { mphsir::watc::set_enabled(enabled); }

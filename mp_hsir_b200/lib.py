@@ -104,6 +104,7 @@ SIGNATURES = {
     "mphsir_debug_mlp_counters": (None, [_VP]),
     "mphsir_debug_mlp_flags": (None, [_I]),
     "mphsir_debug_dwgram_tma": (None, [_I]),
+    "mphsir_debug_window_attn_tc": (None, [_I]),
     "mphsir_debug_tc_tma_epilogue": (None, [_I]),
     "mphsir_debug_tc_ebox1": (None, [_I]),
     "mphsir_debug_pdl": (None, [_I]),
@@ -191,6 +192,8 @@ def load() -> C.CDLL:
         fn.argtypes = args
     if lib.mphsir_version() < 100:
         raise RuntimeError("libmphsir.so is older than this Python package; rebuild it")
+    if os.environ.get("MPHSIR_WATC") in ("0", "1"):    # A/B switch: tcgen05 window attention vs the mma.sync kernel
+        lib.mphsir_debug_window_attn_tc(int(os.environ["MPHSIR_WATC"]))
     if os.environ.get("MPHSIR_PDL") in ("0", "1"):     # A/B switch: programmatic dependent launch of the tcgen05 kernels
         lib.mphsir_debug_pdl(int(os.environ["MPHSIR_PDL"]))
     _lib = lib

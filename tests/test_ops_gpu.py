@@ -191,6 +191,32 @@ def test_window_attention_core(C, heads, shift, prec, tol):
     del sd
 
 
+@pytest.mark.parametrize("prec", [lib.PREC_BF16X3, lib.PREC_BF16])
+@pytest.mark.parametrize("C,heads,B,H,W", [(128, 2, 1, 24, 24), (64, 2, 3, 8, 8), (128, 4, 1, 40, 16), (256, 8, 2, 16, 16)])
+def test_window_attention_tcgen05_equals_mma_sync_kernel(C, heads, B, H, W, prec):
+    """the TMA-fed tcgen05 kernel (two windows per 128-row tile; an ODD number of windows leaves half a tile empty) against
+    the mma.sync kernel it replaces, incl. the scene-coordinate mask of a row band (mask_H / mask_y0)"""
+    qkv = dev(rnd(B * H * W, 3 * C, seed=5))
+    bias = dev(0.5 * rnd(heads, 64, 64, seed=6))
+    B_ = B * H * W // 64
+    res = {}
+    for shift, mask_H, mask_y0 in ((0, None, 0), (4, None, 0), (4, 2 * H, H), (4, 4 * H, 0)):
+        for tc_on in (0, 1):
+            lib.load().mphsir_debug_window_attn_tc(tc_on)
+            out = out_mat(B * H * W, C)
+            wm = torch.full((B_, C), float("nan"), device=DEV)
+            try:
+                lib.window_attn(V(qkv), bias, V(out), wm, B, H, W, C, heads, shift, precision=prec, mask_H=mask_H, mask_y0=mask_y0)
+                torch.cuda.synchronize()
+            finally:
+                lib.load().mphsir_debug_window_attn_tc(1)
+            res[tc_on] = (out.cpu(), wm.cpu())
+        tol = 2e-5 if prec == lib.PREC_BF16X3 else 2e-2
+        assert torch.isfinite(res[1][0]).all() and torch.isfinite(res[1][1]).all()
+        assert rel_err(res[1][0], res[0][0]) < tol, (shift, mask_H, mask_y0)
+        assert rel_err(res[1][1], res[0][1]) < tol
+
+
 @pytest.mark.parametrize("C,r", [(64, 8), (128, 16), (256, 8), (96, 12), (192, 24)])
 def test_local_gate(C, r):
     B_ = 37
