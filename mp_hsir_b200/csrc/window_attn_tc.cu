@@ -14,9 +14,11 @@
 //   MMA                 : O = P Vt^T           (A = P from tensor memory, B = Vt from shared memory; M 128, N hd, K 128)
 //   epilogue (same warps): tcgen05.ld O, store the fp32 row in image order, per-window token mean (:135) by a register
 //                         butterfly over the warp + one shared-memory hand-off between the two warps of a window
-// Probabilities and logits never touch shared or global memory.  All hand-offs are mbarriers; landing zone, operand
-// images, S / P / O are single-buffered, which already lets the TMA loads and the conversion of tile i+1 run under the
-// MMAs, softmax and stores of tile i.  HBM traffic: read 3 hd, write hd floats per token and head (the minimum).
+// Probabilities and logits never touch shared or global memory.  All hand-offs are mbarriers.  Every role runs one tile
+// ahead of the next: S / P / O are double-buffered in tensor memory (P overwrites the S columns it was computed from, as
+// in FlashAttention-4), the q|k and the v landing zones are released separately, the MMA thread issues Q K^T of tile
+// i+1 before P V of tile i, and the softmax warps do softmax(i+1) before the epilogue of tile i.  HBM traffic: read 3 hd,
+// write hd floats per token and head (the minimum).
 // Precision: bf16x3 (hi*hi + hi*lo + lo*hi) or bf16, as the mma.sync kernel it replaces (window_attn_mma.cu, kept for
 // head dims 48 / 96 of the remote-sensing model).
 #include <cuda_bf16.h>
@@ -32,7 +34,8 @@ using namespace tc;
 
 constexpr int kThreads = 448;  // warp 0: TMA producer, 1: MMA, 2-5: softmax + epilogue, 6-13: converters
 constexpr int kSoftWarp0 = 2, kConvWarp0 = 6, kConvThreads = 256;
-constexpr int S_COL = 0, PH_COL = 128, PL_COL = 192, O_COL = 256;
+// tensor memory: buffer u of S / P at columns 128 u (S fp32 [128]; then P hi [0,64) | P lo [64,128) in place), O at 256 + 64 u
+constexpr int SP_COL = 0, PL_OFF = 64, O_COL = 256;
 
 template <int HD>
 struct Plan {
@@ -44,7 +47,9 @@ struct Plan {
 };
 
 struct Bars {
-  uint64_t land_full, land_empty, qk_full, qk_empty, v_full, v_empty, s_full, s_empty, p_full, p_empty, o_full, o_empty;
+  uint64_t lqk_full, lqk_empty, lv_full, lv_empty;   // landing zones (TMA -> converters)
+  uint64_t qk_full, qk_empty, v_full, v_empty;       // operand images (converters -> MMA)
+  uint64_t s_full[2], sp_empty[2], p_full[2], o_full[2], o_empty[2];   // tensor-memory buffers
   uint32_t tmem_base;
 };
 
@@ -81,18 +86,21 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
   const int nWx = p.W >> 3, nW = (p.H >> 3) * nWx;
 
   if (threadIdx.x == 0) {
-    mbar_init(smem_u32(&bar->land_full), 1);
-    mbar_init(smem_u32(&bar->land_empty), kConvThreads / 32);
+    mbar_init(smem_u32(&bar->lqk_full), 1);
+    mbar_init(smem_u32(&bar->lqk_empty), kConvThreads / 32);
+    mbar_init(smem_u32(&bar->lv_full), 1);
+    mbar_init(smem_u32(&bar->lv_empty), kConvThreads / 32);
     mbar_init(smem_u32(&bar->qk_full), kConvThreads / 32);
     mbar_init(smem_u32(&bar->qk_empty), 1);
     mbar_init(smem_u32(&bar->v_full), kConvThreads / 32);
     mbar_init(smem_u32(&bar->v_empty), 1);
-    mbar_init(smem_u32(&bar->s_full), 1);
-    mbar_init(smem_u32(&bar->s_empty), 4);
-    mbar_init(smem_u32(&bar->p_full), 4);
-    mbar_init(smem_u32(&bar->p_empty), 1);
-    mbar_init(smem_u32(&bar->o_full), 1);
-    mbar_init(smem_u32(&bar->o_empty), 4);
+    for (int u = 0; u < 2; ++u) {
+      mbar_init(smem_u32(&bar->s_full[u]), 1);
+      mbar_init(smem_u32(&bar->sp_empty[u]), 1);
+      mbar_init(smem_u32(&bar->p_full[u]), 4);
+      mbar_init(smem_u32(&bar->o_full[u]), 1);
+      mbar_init(smem_u32(&bar->o_empty[u]), 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&bar->tmem_base), 512);
@@ -107,214 +115,237 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
         const int pair = tile / p.heads, h = tile - pair * p.heads;
-        mbar_wait(smem_u32(&bar->land_empty), (it & 1) ^ 1);
         const int nwin = (2 * pair + 1 < p.n_windows) ? 2 : 1;
-        const uint32_t full = smem_u32(&bar->land_full);
-        mbar_expect_tx(full, (uint32_t)(3 * nwin * 64 * HD * 4));
-        for (int win = 0; win < nwin; ++win) {
-          const int w = 2 * pair + win;
-          const int b = w / nW, wrem = w - b * nW;
-          const int wi = wrem / nWx, wj = wrem - wi * nWx;
+        // q | k boxes first (their landing zone is released as soon as Q and K are converted), then the v boxes
+#pragma unroll 1
+        for (int grp = 0; grp < 2; ++grp) {
+          const uint32_t full = smem_u32(grp == 0 ? &bar->lqk_full : &bar->lv_full);
+          mbar_wait(smem_u32(grp == 0 ? &bar->lqk_empty : &bar->lv_empty), (it & 1) ^ 1);
+          mbar_expect_tx(full, (uint32_t)((grp == 0 ? 2 : 1) * nwin * 64 * HD * 4));
+          for (int win = 0; win < nwin; ++win) {
+            const int w = 2 * pair + win;
+            const int b = w / nW, wrem = w - b * nW;
+            const int wi = wrem / nWx, wj = wrem - wi * nWx;
+            for (int op = (grp == 0 ? 0 : 2); op < (grp == 0 ? 2 : 3); ++op)
 #pragma unroll
-          for (int op = 0; op < 3; ++op)
-#pragma unroll
-            for (int bx = 0; bx < 4; ++bx) {
-              int y = wi * 8 + (bx >> 1) * 4 + p.shift, x = wj * 8 + (bx & 1) * 4 + p.shift;  // roll(-s): shifted[ys] = img[(ys+s) % H]
-              if (y >= p.H) y -= p.H;
-              if (x >= p.W) x -= p.W;
-              tma_load_4d(smem_u32(land + op * P::LAND_OP + ((win * 4 + bx) * 16) * HD * 4), &p.tm, op * p.C + h * HD, x, y, b, full);
-            }
+              for (int bx = 0; bx < 4; ++bx) {
+                int y = wi * 8 + (bx >> 1) * 4 + p.shift, x = wj * 8 + (bx & 1) * 4 + p.shift;  // roll(-s): shifted[ys] = img[(ys+s) % H]
+                if (y >= p.H) y -= p.H;
+                if (x >= p.W) x -= p.W;
+                tma_load_4d(smem_u32(land + op * P::LAND_OP + ((win * 4 + bx) * 16) * HD * 4), &p.tm, op * p.C + h * HD, x, y, b, full);
+              }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ==============================================================
-    uint32_t it = 0;
+    // software-pipelined: Q K^T of tile i is issued before P V of tile i-1, so the softmax of tile i-1 runs under it
     const uint32_t idesc_s = make_idesc(128), idesc_o = make_idesc(HD);
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      // ---- S = Q K^T ----
-      mbar_wait(smem_u32(&bar->qk_full), it & 1);
-      mbar_wait(smem_u32(&bar->s_empty), (it & 1) ^ 1);
-      tc_fence_after();
-      {
+    int n_local = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) ++n_local;
+    for (int it = 0; it <= n_local; ++it) {
+      if (it < n_local) {
+        const int u = it & 1;
+        mbar_wait(smem_u32(&bar->qk_full), it & 1);
+        mbar_wait(smem_u32(&bar->sp_empty[u]), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + SP_COL + 128 * u;
         const uint64_t qh = make_desc(smem_u32(q_img)), kh = make_desc(smem_u32(k_img));
         const uint64_t ql = make_desc(smem_u32(q_img + P::QK_PART)), kl = make_desc(smem_u32(k_img + P::QK_PART));
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < HD / 16; ++ks) {
-            umma_bf16(tmem_base + S_COL, qh + 2 * ks, kh + 2 * ks, idesc_s, ks != 0);
+            umma_bf16(d, qh + 2 * ks, kh + 2 * ks, idesc_s, ks != 0);
             if (parts == 2) {
-              umma_bf16(tmem_base + S_COL, qh + 2 * ks, kl + 2 * ks, idesc_s, 1);
-              umma_bf16(tmem_base + S_COL, ql + 2 * ks, kh + 2 * ks, idesc_s, 1);
+              umma_bf16(d, qh + 2 * ks, kl + 2 * ks, idesc_s, 1);
+              umma_bf16(d, ql + 2 * ks, kh + 2 * ks, idesc_s, 1);
             }
           }
-          umma_commit(smem_u32(&bar->s_full));
+          umma_commit(smem_u32(&bar->s_full[u]));
           umma_commit(smem_u32(&bar->qk_empty));
         }
         __syncwarp();
       }
-      // ---- O = P Vt^T : A from tensor memory ----
-      mbar_wait(smem_u32(&bar->v_full), it & 1);
-      mbar_wait(smem_u32(&bar->p_full), it & 1);
-      mbar_wait(smem_u32(&bar->o_empty), (it & 1) ^ 1);
-      tc_fence_after();
-      {
+      if (it >= 1) {
+        const int jt = it - 1, u = jt & 1;
+        mbar_wait(smem_u32(&bar->v_full), jt & 1);
+        mbar_wait(smem_u32(&bar->p_full[u]), (jt >> 1) & 1);
+        mbar_wait(smem_u32(&bar->o_empty[u]), ((jt >> 1) & 1) ^ 1);
+        tc_fence_after();
         const uint32_t vt = smem_u32(vt_img);
+        const uint32_t d = tmem_base + O_COL + 64 * u, ph = tmem_base + SP_COL + 128 * u, pl = ph + PL_OFF;
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {  // 16 keys per step
             const uint64_t vh = make_desc(vt + (kk >> 2) * P::VT_SLAB) + 2 * (kk & 3);
             const uint64_t vl = make_desc(vt + P::VT_PART + (kk >> 2) * P::VT_SLAB) + 2 * (kk & 3);
-            umma_bf16_tmem_a(tmem_base + O_COL, tmem_base + PH_COL + 8 * kk, vh, idesc_o, kk != 0);
+            umma_bf16_tmem_a(d, ph + 8 * kk, vh, idesc_o, kk != 0);
             if (parts == 2) {
-              umma_bf16_tmem_a(tmem_base + O_COL, tmem_base + PH_COL + 8 * kk, vl, idesc_o, 1);
-              umma_bf16_tmem_a(tmem_base + O_COL, tmem_base + PL_COL + 8 * kk, vh, idesc_o, 1);
+              umma_bf16_tmem_a(d, ph + 8 * kk, vl, idesc_o, 1);
+              umma_bf16_tmem_a(d, pl + 8 * kk, vh, idesc_o, 1);
             }
           }
-          umma_commit(smem_u32(&bar->o_full));
+          umma_commit(smem_u32(&bar->o_full[u]));
           umma_commit(smem_u32(&bar->v_empty));
-          umma_commit(smem_u32(&bar->p_empty));
+          umma_commit(smem_u32(&bar->sp_empty[u]));
         }
         __syncwarp();
       }
     }
   } else if (warp < kConvWarp0) {
     // =============================== softmax + epilogue (warps 2..5) =========================================
+    // software-pipelined like the MMA thread: softmax of tile i, then the epilogue of tile i-1 (its P V ran meanwhile)
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may touch
     const int m = quad * 32 + lane;            // query row of the tile
     const int win = m >> 6, t = m & 63, r = t >> 3, c = t & 7;
     const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-    {  // the OTHER window's key columns of P are never written again: zero them once
-      const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        tmem_st8(trow + PH_COL + 32 * (win ^ 1) + 8 * g, z);
-        tmem_st8(trow + PL_COL + 32 * (win ^ 1) + 8 * g, z);
-      }
-      tmem_st_wait();
-    }
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      const int pair = tile / p.heads, h = tile - pair * p.heads;
-      const int w = 2 * pair + win;
-      const bool valid = w < p.n_windows;
-      const int wc = valid ? w : 2 * pair;
-      const int b = wc / nW, wrem = wc - b * nW;
-      const int wi = wrem / nWx, wj = wrem - wi * nWx;
-      // Swin mask (:643-658) in closed form: only the last window row / column of the SCENE's shifted grid is split
-      int ysg = wi * 8 + p.mask_y0;
-      if (ysg >= p.mask_H) ysg -= p.mask_H;
-      const bool lastrow = p.shift != 0 && ysg >= p.mask_H - 8;
-      const bool lastcol = p.shift != 0 && wj == nWx - 1;
-      const bool rq_low = r < 4, cq_low = c < 4;
-      const float* brow = p.bias + ((long long)h * 64 + t) * 64;
+    const bool rq_low = r < 4, cq_low = c < 4;
+    const int et = threadIdx.x - kSoftWarp0 * 32;   // 0..127
+    int n_local = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) ++n_local;
+    // geometry of the previous tile (for its epilogue)
+    bool pv_valid = false;
+    long long pv_row = 0;
+    int pv_h = 0, pv_pair = 0;
+    for (int it = 0; it <= n_local; ++it) {
+      if (it < n_local) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int u = it & 1;
+        const int pair = tile / p.heads, h = tile - pair * p.heads;
+        const int w = 2 * pair + win;
+        const bool valid = w < p.n_windows;
+        const int wc = valid ? w : 2 * pair;
+        const int b = wc / nW, wrem = wc - b * nW;
+        const int wi = wrem / nWx, wj = wrem - wi * nWx;
+        // Swin mask (:643-658) in closed form: only the last window row / column of the SCENE's shifted grid is split
+        int ysg = wi * 8 + p.mask_y0;
+        if (ysg >= p.mask_H) ysg -= p.mask_H;
+        const bool lastrow = p.shift != 0 && ysg >= p.mask_H - 8;
+        const bool lastcol = p.shift != 0 && wj == nWx - 1;
+        const float* brow = p.bias + ((long long)h * 64 + t) * 64;
+        const uint32_t sp = trow + SP_COL + 128 * u;
 
-      mbar_wait(smem_u32(&bar->s_full), it & 1);
-      tc_fence_after();
-      float s[64];
-      {
-        uint32_t raw[32];
-        tmem_ld32(trow + S_COL + 64 * win, raw);
+        mbar_wait(smem_u32(&bar->s_full[u]), (it >> 1) & 1);
+        tc_fence_after();
+        float s[64];
+        {
+          uint32_t raw[32];
+          tmem_ld32(sp + 64 * win, raw);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(raw[j]);
-        tmem_ld32(trow + S_COL + 64 * win + 32, raw);
+          for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(raw[j]);
+          tmem_ld32(sp + 64 * win + 32, raw);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) s[32 + j] = __uint_as_float(raw[j]);
+          for (int j = 0; j < 32; ++j) s[32 + j] = __uint_as_float(raw[j]);
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j4 = 0; j4 < 16; ++j4) {
+          const float4 b4 = ldg4(brow + 4 * j4);
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int kj = 4 * j4 + e;
+            const bool masked = (lastrow && (rq_low != (kj < 32))) || (lastcol && (cq_low != ((kj & 7) < 4)));
+            s[kj] += bb[e] + (masked ? -100.f : 0.f);
+            mx = fmaxf(mx, s[kj]);
+          }
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          s[j] = __expf(s[j] - mx);
+          sum += s[j];
+        }
+        const float inv = 1.0f / sum;
+        // P = softmax row -> bf16 hi/lo pairs -> over the S columns of this row (the A operand of O = P V lives in tensor
+        // memory); the other window's 64 keys get zeros (S holds cross-window products there)
+        const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) split2(s[16 * g + 2 * e] * inv, s[16 * g + 2 * e + 1] * inv, hi[e], lo[e]);
+          tmem_st8(sp + 32 * win + 8 * g, hi);
+          tmem_st8(sp + 32 * (win ^ 1) + 8 * g, z);
+          if (parts == 2) {
+            tmem_st8(sp + PL_OFF + 32 * win + 8 * g, lo);
+            tmem_st8(sp + PL_OFF + 32 * (win ^ 1) + 8 * g, z);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar->p_full[u]));
+        __syncwarp();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar->s_empty));  // S is in registers: the next tile's Q K^T may overwrite it
-      __syncwarp();
-      float mx = -INFINITY;
+      if (it >= 1) {
+        // ---- epilogue of tile it-1: O row -> image order, window mean ----
+        const int jt = it - 1, u = jt & 1;
+        mbar_wait(smem_u32(&bar->o_full[u]), (jt >> 1) & 1);
+        tc_fence_after();
+        float o[HD];
+        {
+          uint32_t raw[32];
 #pragma unroll
-      for (int j4 = 0; j4 < 16; ++j4) {
-        const float4 b4 = ldg4(brow + 4 * j4);
-        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+          for (int c0 = 0; c0 < HD; c0 += 32) {
+            tmem_ld32(trow + O_COL + 64 * u + c0, raw);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int kj = 4 * j4 + e;
-          const bool masked = (lastrow && (rq_low != (kj < 32))) || (lastcol && (cq_low != ((kj & 7) < 4)));
-          s[kj] += bb[e] + (masked ? -100.f : 0.f);
-          mx = fmaxf(mx, s[kj]);
+            for (int j = 0; j < 32; ++j) o[c0 + j] = __uint_as_float(raw[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar->o_empty[u]));
+        __syncwarp();
+        if (pv_valid) {
+          float* dst = p.out + pv_row * p.ldo + pv_h * HD;
+#pragma unroll
+          for (int j4 = 0; j4 < HD / 4; ++j4)
+            *reinterpret_cast<float4*>(dst + 4 * j4) = make_float4(o[4 * j4], o[4 * j4 + 1], o[4 * j4 + 2], o[4 * j4 + 3]);
+        }
+        // column sums over the warp's 32 rows: butterfly that halves the column set at every step; afterwards lane l holds
+        // HD/32 consecutive columns starting at col0(l)
+        int col0 = 0;
+#pragma unroll
+        for (int st = 0; st < 5; ++st) {
+          const int off = 16 >> st, half = HD >> (st + 1);
+          const bool upper = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < half; ++i) {
+            const float send = upper ? o[i] : o[i + half];
+            const float keep = upper ? o[i + half] : o[i];
+            o[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+          col0 += upper ? half : 0;
+        }
+        float* ps = psum + ((jt & 1) * 4 + quad) * HD;
+#pragma unroll
+        for (int i = 0; i < HD / 32; ++i) ps[col0 + i] = o[i];
+        asm volatile("bar.sync 3, 128;" ::: "memory");  // the four softmax warps (converged: the code above ends in full-mask shuffles)
+        if (et < 2 * HD) {
+          const int ew = et / HD, col = et - ew * HD;
+          const int wg = 2 * pv_pair + ew;
+          if (wg < p.n_windows) {
+            const float* p0 = psum + ((jt & 1) * 4 + 2 * ew) * HD;
+            p.win_mean[(long long)wg * p.C + pv_h * HD + col] = (p0[col] + p0[HD + col]) * (1.0f / 64.0f);
+          }
         }
       }
-      float sum = 0.f;
-#pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        s[j] = __expf(s[j] - mx);
-        sum += s[j];
-      }
-      const float inv = 1.0f / sum;
-      // P = softmax row -> bf16 hi/lo pairs -> tensor memory (A operand of O = P V)
-      mbar_wait(smem_u32(&bar->p_empty), (it & 1) ^ 1);
-      tc_fence_after();
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint32_t hi[8], lo[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) split2(s[16 * g + 2 * e] * inv, s[16 * g + 2 * e + 1] * inv, hi[e], lo[e]);
-        tmem_st8(trow + PH_COL + 32 * win + 8 * g, hi);
-        if (parts == 2) tmem_st8(trow + PL_COL + 32 * win + 8 * g, lo);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar->p_full));
-      __syncwarp();
-
-      // ---- epilogue: O row -> image order, window mean ----
-      mbar_wait(smem_u32(&bar->o_full), it & 1);
-      tc_fence_after();
-      float o[HD];
-      {
-        uint32_t raw[32];
-#pragma unroll
-        for (int c0 = 0; c0 < HD; c0 += 32) {
-          tmem_ld32(trow + O_COL + c0, raw);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) o[c0 + j] = __uint_as_float(raw[j]);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar->o_empty));
-      __syncwarp();
-      if (valid) {
+      if (it < n_local) {  // remember this tile's geometry for its epilogue in the next round
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int pair = tile / p.heads, h = tile - pair * p.heads;
+        const int w = 2 * pair + win;
+        pv_valid = w < p.n_windows;
+        const int wc = pv_valid ? w : 2 * pair;
+        const int b = wc / nW, wrem = wc - b * nW;
+        const int wi = wrem / nWx, wj = wrem - wi * nWx;
         int y = wi * 8 + r + p.shift, x = wj * 8 + c + p.shift;
         if (y >= p.H) y -= p.H;
         if (x >= p.W) x -= p.W;
-        float* dst = p.out + ((long long)(b * p.H + y) * p.W + x) * p.ldo + h * HD;
-#pragma unroll
-        for (int j4 = 0; j4 < HD / 4; ++j4)
-          *reinterpret_cast<float4*>(dst + 4 * j4) = make_float4(o[4 * j4], o[4 * j4 + 1], o[4 * j4 + 2], o[4 * j4 + 3]);
-      }
-      // column sums over the warp's 32 rows: butterfly that halves the column set at every step; afterwards lane l holds
-      // HD/32 consecutive columns starting at col0(l)
-      int col0 = 0;
-#pragma unroll
-      for (int st = 0; st < 5; ++st) {
-        const int off = 16 >> st, half = HD >> (st + 1);
-        const bool upper = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < half; ++i) {
-          const float send = upper ? o[i] : o[i + half];
-          const float keep = upper ? o[i + half] : o[i];
-          o[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-        col0 += upper ? half : 0;
-      }
-      float* ps = psum + ((it & 1) * 4 + quad) * HD;
-#pragma unroll
-      for (int i = 0; i < HD / 32; ++i) ps[col0 + i] = o[i];
-      asm volatile("bar.sync 3, 128;" ::: "memory");  // the four softmax warps (converged: every path above ends in __syncwarp / shuffles)
-      const int et = threadIdx.x - kSoftWarp0 * 32;   // 0..127
-      if (et < 2 * HD) {
-        const int ew = et / HD, col = et - ew * HD;
-        const int wg = 2 * pair + ew;
-        if (wg < p.n_windows) {
-          const float* p0 = psum + ((it & 1) * 4 + 2 * ew) * HD;
-          p.win_mean[(long long)wg * p.C + h * HD + col] = (p0[col] + p0[HD + col]) * (1.0f / 64.0f);
-        }
+        pv_row = (long long)(b * p.H + y) * p.W + x;
+        pv_h = h;
+        pv_pair = pair;
       }
     }
   } else {
@@ -328,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int pair = tile / p.heads;
       const bool two = 2 * pair + 1 < p.n_windows;
-      mbar_wait(smem_u32(&bar->land_full), it & 1);
+      mbar_wait(smem_u32(&bar->lqk_full), it & 1);
       // ---- Q (pre-scaled), K: row m, 16-byte chunk ch of the K-major image ----
       mbar_wait(smem_u32(&bar->qk_empty), (it & 1) ^ 1);
       constexpr int CH = HD / 8;
@@ -362,9 +393,13 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar->qk_full));
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&bar->qk_full));
+        mbar_arrive(smem_u32(&bar->lqk_empty));   // q | k landing zone read out: the next tile's q | k may land
+      }
       __syncwarp();
       // ---- V transposed: row = channel d, K = key; one item = 8 keys (one row of a window) of one channel ----
+      mbar_wait(smem_u32(&bar->lv_full), it & 1);
       mbar_wait(smem_u32(&bar->v_empty), (it & 1) ^ 1);
 #pragma unroll
       for (int i = 0; i < HD * 16 / kConvThreads; ++i) {
@@ -388,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(smem_u32(&bar->v_full));
-        mbar_arrive(smem_u32(&bar->land_empty));  // every read of the landing zone is done: the next tile may land
+        mbar_arrive(smem_u32(&bar->lv_empty));
       }
       __syncwarp();
     }
