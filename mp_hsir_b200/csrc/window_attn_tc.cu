@@ -32,8 +32,11 @@ namespace watc {
 
 using namespace tc;
 
-constexpr int kThreads = 448;  // warp 0: TMA producer, 1: MMA, 2-5: softmax + epilogue, 6-13: converters
-constexpr int kSoftWarp0 = 2, kConvWarp0 = 6, kConvThreads = 256;
+// warp 0: TMA producer, 1: MMA, 2-5 / 6-9: two softmax + epilogue groups (even / odd tiles), 10-15: converters.
+// The softmax path is a long dependent chain per row (tcgen05.ld -> bias -> max -> 64 ex2 -> split -> tcgen05.st -> wait for
+// P V -> tcgen05.ld -> stores -> butterfly): one warp per scheduler ran it at IPC 0.17, so two groups alternate tiles.
+constexpr int kThreads = 512;  // 16 warps x 128 registers = the whole register file
+constexpr int kSoftWarp0 = 2, kConvWarp0 = 10, kConvThreads = 192;
 // tensor memory: buffer u of S / P at columns 128 u (S fp32 [128]; then P hi [0,64) | P lo [64,128) in place), O at 256 + 64 u
 constexpr int SP_COL = 0, PL_OFF = 64, O_COL = 256;
 
@@ -43,7 +46,7 @@ struct Plan {
   static constexpr int QK_PART = 128 * 128;     // [128 rows][128 B] (row pitch 128 B for HD = 32 as well)
   static constexpr int VT_SLAB = HD * 128;      // [HD rows][64 keys]
   static constexpr int VT_PART = 2 * VT_SLAB;
-  static size_t smem(int parts) { return 1024 + 3 * (size_t)LAND_OP + 2 * (size_t)parts * QK_PART + (size_t)parts * VT_PART + 2 * 4 * HD * 4; }
+  static size_t smem(int parts) { return 1024 + 3 * (size_t)LAND_OP + 2 * (size_t)parts * QK_PART + (size_t)parts * VT_PART + 2 * 4 * HD * 4; }  // + psum [2 groups][4][HD]
 };
 
 struct Bars {
@@ -194,163 +197,145 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
       }
     }
   } else if (warp < kConvWarp0) {
-    // =============================== softmax + epilogue (warps 2..5) =========================================
-    // software-pipelined like the MMA thread: softmax of tile i, then the epilogue of tile i-1 (its P V ran meanwhile)
+    // =============================== softmax + epilogue (warps 2..9, two groups) =============================
+    const int grp = (warp - kSoftWarp0) >> 2;  // group g owns tiles it = g, g + 2, ... and tensor-memory buffer u = g
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may touch
     const int m = quad * 32 + lane;            // query row of the tile
     const int win = m >> 6, t = m & 63, r = t >> 3, c = t & 7;
     const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
     const bool rq_low = r < 4, cq_low = c < 4;
-    const int et = threadIdx.x - kSoftWarp0 * 32;   // 0..127
+    const int et = threadIdx.x - (kSoftWarp0 + 4 * grp) * 32;   // 0..127 inside the group
+    const int u = grp;
+    const uint32_t sp = trow + SP_COL + 128 * u;
+    float* ps_grp = psum + grp * 4 * HD;
     int n_local = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) ++n_local;
-    // geometry of the previous tile (for its epilogue)
-    bool pv_valid = false;
-    long long pv_row = 0;
-    int pv_h = 0, pv_pair = 0;
-    for (int it = 0; it <= n_local; ++it) {
-      if (it < n_local) {
-        const int tile = blockIdx.x + it * gridDim.x;
-        const int u = it & 1;
-        const int pair = tile / p.heads, h = tile - pair * p.heads;
-        const int w = 2 * pair + win;
-        const bool valid = w < p.n_windows;
-        const int wc = valid ? w : 2 * pair;
-        const int b = wc / nW, wrem = wc - b * nW;
-        const int wi = wrem / nWx, wj = wrem - wi * nWx;
-        // Swin mask (:643-658) in closed form: only the last window row / column of the SCENE's shifted grid is split
-        int ysg = wi * 8 + p.mask_y0;
-        if (ysg >= p.mask_H) ysg -= p.mask_H;
-        const bool lastrow = p.shift != 0 && ysg >= p.mask_H - 8;
-        const bool lastcol = p.shift != 0 && wj == nWx - 1;
-        const float* brow = p.bias + ((long long)h * 64 + t) * 64;
-        const uint32_t sp = trow + SP_COL + 128 * u;
+    for (int it = grp; it < n_local; it += 2) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int pair = tile / p.heads, h = tile - pair * p.heads;
+      const int w = 2 * pair + win;
+      const bool valid = w < p.n_windows;
+      const int wc = valid ? w : 2 * pair;
+      const int b = wc / nW, wrem = wc - b * nW;
+      const int wi = wrem / nWx, wj = wrem - wi * nWx;
+      // Swin mask (:643-658) in closed form: only the last window row / column of the SCENE's shifted grid is split
+      int ysg = wi * 8 + p.mask_y0;
+      if (ysg >= p.mask_H) ysg -= p.mask_H;
+      const bool lastrow = p.shift != 0 && ysg >= p.mask_H - 8;
+      const bool lastcol = p.shift != 0 && wj == nWx - 1;
+      const float* brow = p.bias + ((long long)h * 64 + t) * 64;
 
-        mbar_wait(smem_u32(&bar->s_full[u]), (it >> 1) & 1);
-        tc_fence_after();
-        float s[64];
-        {
-          uint32_t raw[32];
-          tmem_ld32(sp + 64 * win, raw);
+      mbar_wait(smem_u32(&bar->s_full[u]), (it >> 1) & 1);
+      tc_fence_after();
+      float s[64];
+      {
+        uint32_t raw[32];
+        tmem_ld32(sp + 64 * win, raw);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(raw[j]);
-          tmem_ld32(sp + 64 * win + 32, raw);
+        for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(raw[j]);
+        tmem_ld32(sp + 64 * win + 32, raw);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s[32 + j] = __uint_as_float(raw[j]);
-        }
-        float mx = -INFINITY;
-#pragma unroll
-        for (int j4 = 0; j4 < 16; ++j4) {
-          const float4 b4 = ldg4(brow + 4 * j4);
-          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int kj = 4 * j4 + e;
-            const bool masked = (lastrow && (rq_low != (kj < 32))) || (lastcol && (cq_low != ((kj & 7) < 4)));
-            s[kj] += bb[e] + (masked ? -100.f : 0.f);
-            mx = fmaxf(mx, s[kj]);
-          }
-        }
-        float sum = 0.f;
-#pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          s[j] = __expf(s[j] - mx);
-          sum += s[j];
-        }
-        const float inv = 1.0f / sum;
-        // P = softmax row -> bf16 hi/lo pairs -> over the S columns of this row (the A operand of O = P V lives in tensor
-        // memory); the other window's 64 keys get zeros (S holds cross-window products there)
-        const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) split2(s[16 * g + 2 * e] * inv, s[16 * g + 2 * e + 1] * inv, hi[e], lo[e]);
-          tmem_st8(sp + 32 * win + 8 * g, hi);
-          tmem_st8(sp + 32 * (win ^ 1) + 8 * g, z);
-          if (parts == 2) {
-            tmem_st8(sp + PL_OFF + 32 * win + 8 * g, lo);
-            tmem_st8(sp + PL_OFF + 32 * (win ^ 1) + 8 * g, z);
-          }
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bar->p_full[u]));
-        __syncwarp();
+        for (int j = 0; j < 32; ++j) s[32 + j] = __uint_as_float(raw[j]);
       }
-      if (it >= 1) {
-        // ---- epilogue of tile it-1: O row -> image order, window mean ----
-        const int jt = it - 1, u = jt & 1;
-        mbar_wait(smem_u32(&bar->o_full[u]), (jt >> 1) & 1);
-        tc_fence_after();
-        float o[HD];
-        {
-          uint32_t raw[32];
+      float mx = -INFINITY;
 #pragma unroll
-          for (int c0 = 0; c0 < HD; c0 += 32) {
-            tmem_ld32(trow + O_COL + 64 * u + c0, raw);
+      for (int j4 = 0; j4 < 16; ++j4) {
+        const float4 b4 = ldg4(brow + 4 * j4);
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[c0 + j] = __uint_as_float(raw[j]);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bar->o_empty[u]));
-        __syncwarp();
-        if (pv_valid) {
-          float* dst = p.out + pv_row * p.ldo + pv_h * HD;
-#pragma unroll
-          for (int j4 = 0; j4 < HD / 4; ++j4)
-            *reinterpret_cast<float4*>(dst + 4 * j4) = make_float4(o[4 * j4], o[4 * j4 + 1], o[4 * j4 + 2], o[4 * j4 + 3]);
-        }
-        // column sums over the warp's 32 rows: butterfly that halves the column set at every step; afterwards lane l holds
-        // HD/32 consecutive columns starting at col0(l)
-        int col0 = 0;
-#pragma unroll
-        for (int st = 0; st < 5; ++st) {
-          const int off = 16 >> st, half = HD >> (st + 1);
-          const bool upper = (lane & off) != 0;
-#pragma unroll
-          for (int i = 0; i < half; ++i) {
-            const float send = upper ? o[i] : o[i + half];
-            const float keep = upper ? o[i + half] : o[i];
-            o[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-          }
-          col0 += upper ? half : 0;
-        }
-        float* ps = psum + ((jt & 1) * 4 + quad) * HD;
-#pragma unroll
-        for (int i = 0; i < HD / 32; ++i) ps[col0 + i] = o[i];
-        asm volatile("bar.sync 3, 128;" ::: "memory");  // the four softmax warps (converged: the code above ends in full-mask shuffles)
-        if (et < 2 * HD) {
-          const int ew = et / HD, col = et - ew * HD;
-          const int wg = 2 * pv_pair + ew;
-          if (wg < p.n_windows) {
-            const float* p0 = psum + ((jt & 1) * 4 + 2 * ew) * HD;
-            p.win_mean[(long long)wg * p.C + pv_h * HD + col] = (p0[col] + p0[HD + col]) * (1.0f / 64.0f);
-          }
+        for (int e = 0; e < 4; ++e) {
+          const int kj = 4 * j4 + e;
+          const bool masked = (lastrow && (rq_low != (kj < 32))) || (lastcol && (cq_low != ((kj & 7) < 4)));
+          s[kj] += bb[e] + (masked ? -100.f : 0.f);
+          mx = fmaxf(mx, s[kj]);
         }
       }
-      if (it < n_local) {  // remember this tile's geometry for its epilogue in the next round
-        const int tile = blockIdx.x + it * gridDim.x;
-        const int pair = tile / p.heads, h = tile - pair * p.heads;
-        const int w = 2 * pair + win;
-        pv_valid = w < p.n_windows;
-        const int wc = pv_valid ? w : 2 * pair;
-        const int b = wc / nW, wrem = wc - b * nW;
-        const int wi = wrem / nWx, wj = wrem - wi * nWx;
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        s[j] = __expf(s[j] - mx);
+        sum += s[j];
+      }
+      const float inv = 1.0f / sum;
+      // P = softmax row -> bf16 hi/lo pairs -> over the S columns of this row (the A operand of O = P V lives in tensor
+      // memory); the other window's 64 keys get zeros (S holds cross-window products there)
+      const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split2(s[16 * g + 2 * e] * inv, s[16 * g + 2 * e + 1] * inv, hi[e], lo[e]);
+        tmem_st8(sp + 32 * win + 8 * g, hi);
+        tmem_st8(sp + 32 * (win ^ 1) + 8 * g, z);
+        if (parts == 2) {
+          tmem_st8(sp + PL_OFF + 32 * win + 8 * g, lo);
+          tmem_st8(sp + PL_OFF + 32 * (win ^ 1) + 8 * g, z);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar->p_full[u]));
+      __syncwarp();
+
+      // ---- epilogue: O row -> image order, window mean (the other group runs the next tile's softmax meanwhile) ----
+      mbar_wait(smem_u32(&bar->o_full[u]), (it >> 1) & 1);
+      tc_fence_after();
+      float o[HD];
+      {
+        uint32_t raw[32];
+#pragma unroll
+        for (int c0 = 0; c0 < HD; c0 += 32) {
+          tmem_ld32(trow + O_COL + 64 * u + c0, raw);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[c0 + j] = __uint_as_float(raw[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar->o_empty[u]));
+      __syncwarp();
+      if (valid) {
         int y = wi * 8 + r + p.shift, x = wj * 8 + c + p.shift;
         if (y >= p.H) y -= p.H;
         if (x >= p.W) x -= p.W;
-        pv_row = (long long)(b * p.H + y) * p.W + x;
-        pv_h = h;
-        pv_pair = pair;
+        float* dst = p.out + ((long long)(b * p.H + y) * p.W + x) * p.ldo + h * HD;
+#pragma unroll
+        for (int j4 = 0; j4 < HD / 4; ++j4)
+          *reinterpret_cast<float4*>(dst + 4 * j4) = make_float4(o[4 * j4], o[4 * j4 + 1], o[4 * j4 + 2], o[4 * j4 + 3]);
       }
+      // column sums over the warp's 32 rows: butterfly that halves the column set at every step; afterwards lane l holds
+      // HD/32 consecutive columns starting at col0(l)
+      int col0 = 0;
+#pragma unroll
+      for (int st = 0; st < 5; ++st) {
+        const int off = 16 >> st, half = HD >> (st + 1);
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+          const float send = upper ? o[i] : o[i + half];
+          const float keep = upper ? o[i + half] : o[i];
+          o[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+        col0 += upper ? half : 0;
+      }
+      // the group's previous tile read ps_grp before its second barrier, so it may be overwritten now
+#pragma unroll
+      for (int i = 0; i < HD / 32; ++i) ps_grp[quad * HD + col0 + i] = o[i];
+      if (grp == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+      else asm volatile("bar.sync 4, 128;" ::: "memory");
+      if (et < 2 * HD) {
+        const int ew = et / HD, col = et - ew * HD;
+        const int wg = 2 * pair + ew;
+        if (wg < p.n_windows)
+          p.win_mean[(long long)wg * p.C + h * HD + col] = (ps_grp[2 * ew * HD + col] + ps_grp[(2 * ew + 1) * HD + col]) * (1.0f / 64.0f);
+      }
+      if (grp == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+      else asm volatile("bar.sync 4, 128;" ::: "memory");
     }
   } else {
-    // =============================== converters (warps 6..13) ================================================
-    const int ct = threadIdx.x - kConvWarp0 * 32;  // 0..255
+    // =============================== converters (warps 10..15) ===============================================
+    const int ct = threadIdx.x - kConvWarp0 * 32;  // 0..191
     const float scale = rsqrtf((float)HD);
     const float* lq = reinterpret_cast<const float*>(land);
     const float* lk = reinterpret_cast<const float*>(land + P::LAND_OP);
@@ -363,9 +348,8 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
       // ---- Q (pre-scaled), K: row m, 16-byte chunk ch of the K-major image ----
       mbar_wait(smem_u32(&bar->qk_empty), (it & 1) ^ 1);
       constexpr int CH = HD / 8;
-#pragma unroll
-      for (int i = 0; i < 128 * CH / kConvThreads; ++i) {
-        const int item = ct + kConvThreads * i;
+#pragma unroll 2
+      for (int item = ct; item < 128 * CH; item += kConvThreads) {
         const int m = item / CH, ch = item - m * CH;
         const bool ok = two || m < 64;
         const int lo_ = land_pixel<HD>(m) + ch * 8;
@@ -401,9 +385,8 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
       // ---- V transposed: row = channel d, K = key; one item = 8 keys (one row of a window) of one channel ----
       mbar_wait(smem_u32(&bar->lv_full), it & 1);
       mbar_wait(smem_u32(&bar->v_empty), (it & 1) ^ 1);
-#pragma unroll
-      for (int i = 0; i < HD * 16 / kConvThreads; ++i) {
-        const int item = ct + kConvThreads * i;
+#pragma unroll 2
+      for (int item = ct; item < HD * 16; item += kConvThreads) {
         const int kg = item / HD, d = item - kg * HD;   // lanes = consecutive channels: conflict-free scalar reads
         const int m0 = kg * 8;                          // keys m0 .. m0+7 = window (kg >> 3), row (kg & 7), columns 0..7
         const bool ok = two || m0 < 64;
