@@ -50,7 +50,7 @@ struct Plan {
 };
 
 struct Bars {
-  uint64_t slot_full[6], slot_empty[6];              // landing slots (operand, window): TMA -> converters, refilled one by one
+  uint64_t lqk_full, lqk_empty, lv_full, lv_empty;   // landing zones (TMA -> converters)
   uint64_t qk_full, qk_empty, v_full, v_empty;       // operand images (converters -> MMA)
   uint64_t s_full[2], sp_empty[2], p_full[2], o_full[2], o_empty[2];   // tensor-memory buffers
   uint32_t tmem_base;
@@ -89,10 +89,10 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
   const int nWx = p.W >> 3, nW = (p.H >> 3) * nWx;
 
   if (threadIdx.x == 0) {
-    for (int sl = 0; sl < 6; ++sl) {
-      mbar_init(smem_u32(&bar->slot_full[sl]), 1);
-      mbar_init(smem_u32(&bar->slot_empty[sl]), kConvThreads / 32);
-    }
+    mbar_init(smem_u32(&bar->lqk_full), 1);
+    mbar_init(smem_u32(&bar->lqk_empty), kConvThreads / 32);
+    mbar_init(smem_u32(&bar->lv_full), 1);
+    mbar_init(smem_u32(&bar->lv_empty), kConvThreads / 32);
     mbar_init(smem_u32(&bar->qk_full), kConvThreads / 32);
     mbar_init(smem_u32(&bar->qk_empty), 1);
     mbar_init(smem_u32(&bar->v_full), kConvThreads / 32);
@@ -119,81 +119,83 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
         const int pair = tile / p.heads, h = tile - pair * p.heads;
         const int nwin = (2 * pair + 1 < p.n_windows) ? 2 : 1;
-        // six landing slots (operand x window: 64 tokens = four 4x4-pixel boxes each); a slot is refilled as soon as the
-        // converters have read it, so loads stream continuously instead of once per tile
+        // q | k boxes first (their landing zone is released as soon as Q and K are converted), then the v boxes
 #pragma unroll 1
-        for (int sl = 0; sl < 6; ++sl) {
-          const int op = sl >> 1, win = sl & 1;
-          if (win >= nwin) continue;   // second window of an odd tail: the converters zero-fill, nobody waits for this slot
-          const uint32_t full = smem_u32(&bar->slot_full[sl]);
-          mbar_wait(smem_u32(&bar->slot_empty[sl]), (it & 1) ^ 1);
-          mbar_expect_tx(full, (uint32_t)(64 * HD * 4));
-          const int w = 2 * pair + win;
-          const int b = w / nW, wrem = w - b * nW;
-          const int wi = wrem / nWx, wj = wrem - wi * nWx;
+        for (int grp = 0; grp < 2; ++grp) {
+          const uint32_t full = smem_u32(grp == 0 ? &bar->lqk_full : &bar->lv_full);
+          mbar_wait(smem_u32(grp == 0 ? &bar->lqk_empty : &bar->lv_empty), (it & 1) ^ 1);
+          mbar_expect_tx(full, (uint32_t)((grp == 0 ? 2 : 1) * nwin * 64 * HD * 4));
+          for (int win = 0; win < nwin; ++win) {
+            const int w = 2 * pair + win;
+            const int b = w / nW, wrem = w - b * nW;
+            const int wi = wrem / nWx, wj = wrem - wi * nWx;
+            for (int op = (grp == 0 ? 0 : 2); op < (grp == 0 ? 2 : 3); ++op)
 #pragma unroll
-          for (int bx = 0; bx < 4; ++bx) {
-            int y = wi * 8 + (bx >> 1) * 4 + p.shift, x = wj * 8 + (bx & 1) * 4 + p.shift;  // roll(-s): shifted[ys] = img[(ys+s) % H]
-            if (y >= p.H) y -= p.H;
-            if (x >= p.W) x -= p.W;
-            tma_load_4d(smem_u32(land + op * P::LAND_OP + ((win * 4 + bx) * 16) * HD * 4), &p.tm, op * p.C + h * HD, x, y, b, full);
+              for (int bx = 0; bx < 4; ++bx) {
+                int y = wi * 8 + (bx >> 1) * 4 + p.shift, x = wj * 8 + (bx & 1) * 4 + p.shift;  // roll(-s): shifted[ys] = img[(ys+s) % H]
+                if (y >= p.H) y -= p.H;
+                if (x >= p.W) x -= p.W;
+                tma_load_4d(smem_u32(land + op * P::LAND_OP + ((win * 4 + bx) * 16) * HD * 4), &p.tm, op * p.C + h * HD, x, y, b, full);
+              }
           }
         }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ==============================================================
-    // software-pipelined: Q K^T of tile i is issued before P V of tile i-1, so the softmax of tile i-1 runs under it
-    const uint32_t idesc_s = make_idesc(128), idesc_o = make_idesc(HD);
-    int n_local = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) ++n_local;
-    for (int it = 0; it <= n_local; ++it) {
-      if (it < n_local) {
-        const int u = it & 1;
-        mbar_wait(smem_u32(&bar->qk_full), it & 1);
-        mbar_wait(smem_u32(&bar->sp_empty[u]), ((it >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d = tmem_base + SP_COL + 128 * u;
-        const uint64_t qh = make_desc(smem_u32(q_img)), kh = make_desc(smem_u32(k_img));
-        const uint64_t ql = make_desc(smem_u32(q_img + P::QK_PART)), kl = make_desc(smem_u32(k_img + P::QK_PART));
-        if (elect_one()) {
+    // ONE thread, readiness-ordered: Q K^T of the next tile and P V of the oldest pending tile are polled without
+    // blocking and issued whichever is ready first (a fixed order let a late q | k landing hold back a P V that was
+    // ready, and with it the epilogue, the V conversion and the next loads).  At most two tiles are in flight (two
+    // tensor-memory buffers).
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(128), idesc_o = make_idesc(HD);
+      int n_local = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) ++n_local;
+      const uint64_t qh = make_desc(smem_u32(q_img)), kh = make_desc(smem_u32(k_img));
+      const uint64_t ql = make_desc(smem_u32(q_img + P::QK_PART)), kl = make_desc(smem_u32(k_img + P::QK_PART));
+      const uint32_t vt = smem_u32(vt_img);
+      int n1 = 0, n2 = 0;   // tiles whose S / whose O have been issued
+      while (n2 < n_local) {
+        if (n1 < n_local && n1 - n2 < 2) {
+          const int u = n1 & 1;
+          if (mbar_try_wait(smem_u32(&bar->qk_full), n1 & 1) && mbar_try_wait(smem_u32(&bar->sp_empty[u]), ((n1 >> 1) & 1) ^ 1)) {
+            tc_fence_after();
+            const uint32_t d = tmem_base + SP_COL + 128 * u;
 #pragma unroll
-          for (int ks = 0; ks < HD / 16; ++ks) {
-            umma_bf16(d, qh + 2 * ks, kh + 2 * ks, idesc_s, ks != 0);
-            if (parts == 2) {
-              umma_bf16(d, qh + 2 * ks, kl + 2 * ks, idesc_s, 1);
-              umma_bf16(d, ql + 2 * ks, kh + 2 * ks, idesc_s, 1);
+            for (int ks = 0; ks < HD / 16; ++ks) {
+              umma_bf16(d, qh + 2 * ks, kh + 2 * ks, idesc_s, ks != 0);
+              if (parts == 2) {
+                umma_bf16(d, qh + 2 * ks, kl + 2 * ks, idesc_s, 1);
+                umma_bf16(d, ql + 2 * ks, kh + 2 * ks, idesc_s, 1);
+              }
             }
+            umma_commit(smem_u32(&bar->s_full[u]));
+            umma_commit(smem_u32(&bar->qk_empty));
+            ++n1;
           }
-          umma_commit(smem_u32(&bar->s_full[u]));
-          umma_commit(smem_u32(&bar->qk_empty));
         }
-        __syncwarp();
-      }
-      if (it >= 1) {
-        const int jt = it - 1, u = jt & 1;
-        mbar_wait(smem_u32(&bar->v_full), jt & 1);
-        mbar_wait(smem_u32(&bar->p_full[u]), (jt >> 1) & 1);
-        mbar_wait(smem_u32(&bar->o_empty[u]), ((jt >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t vt = smem_u32(vt_img);
-        const uint32_t d = tmem_base + O_COL + 64 * u, ph = tmem_base + SP_COL + 128 * u, pl = ph + PL_OFF;
-        if (elect_one()) {
+        if (n2 < n1) {
+          const int u = n2 & 1;
+          if (mbar_try_wait(smem_u32(&bar->v_full), n2 & 1) && mbar_try_wait(smem_u32(&bar->p_full[u]), (n2 >> 1) & 1) &&
+              mbar_try_wait(smem_u32(&bar->o_empty[u]), ((n2 >> 1) & 1) ^ 1)) {
+            tc_fence_after();
+            const uint32_t d = tmem_base + O_COL + 64 * u, ph = tmem_base + SP_COL + 128 * u, pl = ph + PL_OFF;
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {  // 16 keys per step
-            const uint64_t vh = make_desc(vt + (kk >> 2) * P::VT_SLAB) + 2 * (kk & 3);
-            const uint64_t vl = make_desc(vt + P::VT_PART + (kk >> 2) * P::VT_SLAB) + 2 * (kk & 3);
-            umma_bf16_tmem_a(d, ph + 8 * kk, vh, idesc_o, kk != 0);
-            if (parts == 2) {
-              umma_bf16_tmem_a(d, ph + 8 * kk, vl, idesc_o, 1);
-              umma_bf16_tmem_a(d, pl + 8 * kk, vh, idesc_o, 1);
+            for (int kk = 0; kk < 8; ++kk) {  // 16 keys per step
+              const uint64_t vh = make_desc(vt + (kk >> 2) * P::VT_SLAB) + 2 * (kk & 3);
+              const uint64_t vl = make_desc(vt + P::VT_PART + (kk >> 2) * P::VT_SLAB) + 2 * (kk & 3);
+              umma_bf16_tmem_a(d, ph + 8 * kk, vh, idesc_o, kk != 0);
+              if (parts == 2) {
+                umma_bf16_tmem_a(d, ph + 8 * kk, vl, idesc_o, 1);
+                umma_bf16_tmem_a(d, pl + 8 * kk, vh, idesc_o, 1);
+              }
             }
+            umma_commit(smem_u32(&bar->o_full[u]));
+            umma_commit(smem_u32(&bar->v_empty));
+            umma_commit(smem_u32(&bar->sp_empty[u]));
+            ++n2;
           }
-          umma_commit(smem_u32(&bar->o_full[u]));
-          umma_commit(smem_u32(&bar->v_empty));
-          umma_commit(smem_u32(&bar->sp_empty[u]));
         }
-        __syncwarp();
       }
     }
   } else if (warp < kConvWarp0) {
@@ -337,76 +339,77 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
     // =============================== converters (warps 10..15) ===============================================
     const int ct = threadIdx.x - kConvWarp0 * 32;  // 0..191
     const float scale = rsqrtf((float)HD);
-    constexpr int CH = HD / 8;
+    const float* lq = reinterpret_cast<const float*>(land);
+    const float* lk = reinterpret_cast<const float*>(land + P::LAND_OP);
+    const float* lv = reinterpret_cast<const float*>(land + 2 * P::LAND_OP);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int pair = tile / p.heads;
       const bool two = 2 * pair + 1 < p.n_windows;
-      // ---- Q (pre-scaled) and K: row m, 16-byte chunk ch of the K-major image; slot by slot (operand, window) ----
+      mbar_wait(smem_u32(&bar->lqk_full), it & 1);
+      // ---- Q (pre-scaled), K: row m, 16-byte chunk ch of the K-major image ----
       mbar_wait(smem_u32(&bar->qk_empty), (it & 1) ^ 1);
-#pragma unroll 1
-      for (int sl = 0; sl < 4; ++sl) {
-        const int op = sl >> 1, win = sl & 1;
-        const bool ok = win == 0 || two;
-        if (ok) mbar_wait(smem_u32(&bar->slot_full[sl]), it & 1);
-        const float* lsrc = reinterpret_cast<const float*>(land + op * P::LAND_OP);
-        uint8_t* img = op == 0 ? q_img : k_img;
-        const float sc = op == 0 ? scale : 1.0f;
+      constexpr int CH = HD / 8;
 #pragma unroll 2
-        for (int item = ct; item < 64 * CH; item += kConvThreads) {
-          const int m = win * 64 + item / CH, ch = item % CH;
-          float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-          if (ok) {
-            const int lo_ = land_pixel<HD>(m) + ch * 8;
-            a0 = *reinterpret_cast<const float4*>(lsrc + lo_);
-            a1 = *reinterpret_cast<const float4*>(lsrc + lo_ + 4);
-          }
-          const int off = m * 128 + ((ch ^ (m & 7)) << 4);
-          uint4 hi, lo;
-          split2(a0.x * sc, a0.y * sc, hi.x, lo.x);
-          split2(a0.z * sc, a0.w * sc, hi.y, lo.y);
-          split2(a1.x * sc, a1.y * sc, hi.z, lo.z);
-          split2(a1.z * sc, a1.w * sc, hi.w, lo.w);
-          *reinterpret_cast<uint4*>(img + off) = hi;
-          if (parts == 2) *reinterpret_cast<uint4*>(img + P::QK_PART + off) = lo;
+      for (int item = ct; item < 128 * CH; item += kConvThreads) {
+        const int m = item / CH, ch = item - m * CH;
+        const bool ok = two || m < 64;
+        const int lo_ = land_pixel<HD>(m) + ch * 8;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+        if (ok) {
+          a0 = *reinterpret_cast<const float4*>(lq + lo_);
+          a1 = *reinterpret_cast<const float4*>(lq + lo_ + 4);
+          b0 = *reinterpret_cast<const float4*>(lk + lo_);
+          b1 = *reinterpret_cast<const float4*>(lk + lo_ + 4);
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0 && ok) mbar_arrive(smem_u32(&bar->slot_empty[sl]));   // the producer refills this slot with the next tile
-        __syncwarp();
+        const int off = m * 128 + ((ch ^ (m & 7)) << 4);
+        uint4 hi, lo;
+        split2(a0.x * scale, a0.y * scale, hi.x, lo.x);
+        split2(a0.z * scale, a0.w * scale, hi.y, lo.y);
+        split2(a1.x * scale, a1.y * scale, hi.z, lo.z);
+        split2(a1.z * scale, a1.w * scale, hi.w, lo.w);
+        *reinterpret_cast<uint4*>(q_img + off) = hi;
+        if (parts == 2) *reinterpret_cast<uint4*>(q_img + P::QK_PART + off) = lo;
+        split2(b0.x, b0.y, hi.x, lo.x);
+        split2(b0.z, b0.w, hi.y, lo.y);
+        split2(b1.x, b1.y, hi.z, lo.z);
+        split2(b1.z, b1.w, hi.w, lo.w);
+        *reinterpret_cast<uint4*>(k_img + off) = hi;
+        if (parts == 2) *reinterpret_cast<uint4*>(k_img + P::QK_PART + off) = lo;
       }
-      if (lane == 0) mbar_arrive(smem_u32(&bar->qk_full));
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&bar->qk_full));
+        mbar_arrive(smem_u32(&bar->lqk_empty));   // q | k landing zone read out: the next tile's q | k may land
+      }
       __syncwarp();
       // ---- V transposed: row = channel d, K = key; one item = 8 keys (one row of a window) of one channel ----
+      mbar_wait(smem_u32(&bar->lv_full), it & 1);
       mbar_wait(smem_u32(&bar->v_empty), (it & 1) ^ 1);
-      const float* lv = reinterpret_cast<const float*>(land + 2 * P::LAND_OP);
-#pragma unroll 1
-      for (int win = 0; win < 2; ++win) {
-        const int sl = 4 + win;
-        const bool ok = win == 0 || two;
-        if (ok) mbar_wait(smem_u32(&bar->slot_full[sl]), it & 1);
 #pragma unroll 2
-        for (int item = ct; item < HD * 8; item += kConvThreads) {
-          const int kg = win * 8 + item / HD, d = item % HD;   // lanes = consecutive channels: conflict-free scalar reads
-          const int m0 = kg * 8;                                // keys m0 .. m0+7 = window win, row (kg & 7), columns 0..7
-          float v[8];
+      for (int item = ct; item < HD * 16; item += kConvThreads) {
+        const int kg = item / HD, d = item - kg * HD;   // lanes = consecutive channels: conflict-free scalar reads
+        const int m0 = kg * 8;                          // keys m0 .. m0+7 = window (kg >> 3), row (kg & 7), columns 0..7
+        const bool ok = two || m0 < 64;
+        float v[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = ok ? lv[land_pixel<HD>(m0 + e) + d] : 0.f;
-          uint4 hi, lo;
-          split2(v[0], v[1], hi.x, lo.x);
-          split2(v[2], v[3], hi.y, lo.y);
-          split2(v[4], v[5], hi.z, lo.z);
-          split2(v[6], v[7], hi.w, lo.w);
-          const int off = win * P::VT_SLAB + d * 128 + (((kg & 7) ^ (d & 7)) << 4);
-          *reinterpret_cast<uint4*>(vt_img + off) = hi;
-          if (parts == 2) *reinterpret_cast<uint4*>(vt_img + P::VT_PART + off) = lo;
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0 && ok) mbar_arrive(smem_u32(&bar->slot_empty[sl]));
-        __syncwarp();
+        for (int e = 0; e < 8; ++e) v[e] = ok ? lv[land_pixel<HD>(m0 + e) + d] : 0.f;
+        uint4 hi, lo;
+        split2(v[0], v[1], hi.x, lo.x);
+        split2(v[2], v[3], hi.y, lo.y);
+        split2(v[4], v[5], hi.z, lo.z);
+        split2(v[6], v[7], hi.w, lo.w);
+        const int off = (kg >> 3) * P::VT_SLAB + d * 128 + (((kg & 7) ^ (d & 7)) << 4);
+        *reinterpret_cast<uint4*>(vt_img + off) = hi;
+        if (parts == 2) *reinterpret_cast<uint4*>(vt_img + P::VT_PART + off) = lo;
       }
-      if (lane == 0) mbar_arrive(smem_u32(&bar->v_full));
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&bar->v_full));
+        mbar_arrive(smem_u32(&bar->lv_empty));
+      }
       __syncwarp();
     }
   }
