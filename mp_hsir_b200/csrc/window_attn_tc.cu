@@ -46,12 +46,15 @@ struct Plan {
   static constexpr int QK_PART = 128 * 128;     // [128 rows][128 B] (row pitch 128 B for HD = 32 as well)
   static constexpr int VT_SLAB = HD * 128;      // [HD rows][64 keys]
   static constexpr int VT_PART = 2 * VT_SLAB;
-  static size_t smem(int parts) { return 1024 + 3 * (size_t)LAND_OP + 2 * (size_t)parts * QK_PART + (size_t)parts * VT_PART + 2 * 4 * HD * 4; }  // + psum [2 groups][4][HD]
+  // barriers + landing + Q, K images + TWO Vt images + psum [2 groups][4][HD]: exactly 227 KB for HD = 64 with hi/lo parts
+  static size_t smem(int parts) { return 1024 + 3 * (size_t)LAND_OP + 2 * (size_t)parts * QK_PART + 2 * (size_t)parts * VT_PART + 2 * 4 * HD * 4; }
 };
 
 struct Bars {
   uint64_t lqk_full, lqk_empty, lv_full, lv_empty;   // landing zones (TMA -> converters)
-  uint64_t qk_full, qk_empty, v_full, v_empty;       // operand images (converters -> MMA)
+  uint64_t qk_full, qk_empty, v_full[2], v_empty[2]; // operand images (converters -> MMA); Vt is double-buffered: with one
+                                                     // buffer V(t+1) waited for P V of tile t, which chained every second
+                                                     // tile behind a whole convert -> QK^T -> softmax -> PV round trip
   uint64_t s_full[2], sp_empty[2], p_full[2], o_full[2], o_empty[2];   // tensor-memory buffers
   uint32_t tmem_base;
 };
@@ -64,6 +67,7 @@ struct Args {
   float* win_mean;             // [B*nW][C]
   int B, H, W, C, heads, shift, parts, mask_H, mask_y0;
   int n_windows, n_tiles;
+  int dbg;  // timing experiments only (mphsir_debug_window_attn_tc(1 | flags << 4)): 1 skip conversion math, 2 skip softmax math, 4 skip TMA loads, 8 skip epilogue stores/butterfly
 };
 
 // token m of a tile (two windows of 64 tokens, row-major 8x8) -> float offset of its pixel inside one operand's landing zone
@@ -83,7 +87,7 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
   uint8_t* q_img = land + 3 * P::LAND_OP;
   uint8_t* k_img = q_img + p.parts * P::QK_PART;
   uint8_t* vt_img = k_img + p.parts * P::QK_PART;
-  float* psum = reinterpret_cast<float*>(vt_img + p.parts * P::VT_PART);  // [2 (tile parity)][4 quadrants][HD]
+  float* psum = reinterpret_cast<float*>(vt_img + 2 * p.parts * P::VT_PART);  // [2 groups][4 quadrants][HD]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int parts = p.parts;
   const int nWx = p.W >> 3, nW = (p.H >> 3) * nWx;
@@ -95,9 +99,9 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
     mbar_init(smem_u32(&bar->lv_empty), kConvThreads / 32);
     mbar_init(smem_u32(&bar->qk_full), kConvThreads / 32);
     mbar_init(smem_u32(&bar->qk_empty), 1);
-    mbar_init(smem_u32(&bar->v_full), kConvThreads / 32);
-    mbar_init(smem_u32(&bar->v_empty), 1);
     for (int u = 0; u < 2; ++u) {
+      mbar_init(smem_u32(&bar->v_full[u]), kConvThreads / 32);
+      mbar_init(smem_u32(&bar->v_empty[u]), 1);
       mbar_init(smem_u32(&bar->s_full[u]), 1);
       mbar_init(smem_u32(&bar->sp_empty[u]), 1);
       mbar_init(smem_u32(&bar->p_full[u]), 4);
@@ -124,6 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
         for (int grp = 0; grp < 2; ++grp) {
           const uint32_t full = smem_u32(grp == 0 ? &bar->lqk_full : &bar->lv_full);
           mbar_wait(smem_u32(grp == 0 ? &bar->lqk_empty : &bar->lv_empty), (it & 1) ^ 1);
+          if (p.dbg & 4) { mbar_arrive(full); continue; }
           mbar_expect_tx(full, (uint32_t)((grp == 0 ? 2 : 1) * nwin * 64 * HD * 4));
           for (int win = 0; win < nwin; ++win) {
             const int w = 2 * pair + win;
@@ -176,14 +181,15 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
         }
         if (n2 < n1) {
           const int u = n2 & 1;
-          if (mbar_try_wait(smem_u32(&bar->v_full), n2 & 1) && mbar_try_wait(smem_u32(&bar->p_full[u]), (n2 >> 1) & 1) &&
+          if (mbar_try_wait(smem_u32(&bar->v_full[u]), (n2 >> 1) & 1) && mbar_try_wait(smem_u32(&bar->p_full[u]), (n2 >> 1) & 1) &&
               mbar_try_wait(smem_u32(&bar->o_empty[u]), ((n2 >> 1) & 1) ^ 1)) {
             tc_fence_after();
             const uint32_t d = tmem_base + O_COL + 64 * u, ph = tmem_base + SP_COL + 128 * u, pl = ph + PL_OFF;
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {  // 16 keys per step
-              const uint64_t vh = make_desc(vt + (kk >> 2) * P::VT_SLAB) + 2 * (kk & 3);
-              const uint64_t vl = make_desc(vt + P::VT_PART + (kk >> 2) * P::VT_SLAB) + 2 * (kk & 3);
+              const uint32_t vb = vt + u * parts * P::VT_PART;
+              const uint64_t vh = make_desc(vb + (kk >> 2) * P::VT_SLAB) + 2 * (kk & 3);
+              const uint64_t vl = make_desc(vb + P::VT_PART + (kk >> 2) * P::VT_SLAB) + 2 * (kk & 3);
               umma_bf16_tmem_a(d, ph + 8 * kk, vh, idesc_o, kk != 0);
               if (parts == 2) {
                 umma_bf16_tmem_a(d, ph + 8 * kk, vl, idesc_o, 1);
@@ -191,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
               }
             }
             umma_commit(smem_u32(&bar->o_full[u]));
-            umma_commit(smem_u32(&bar->v_empty));
+            umma_commit(smem_u32(&bar->v_empty[u]));
             umma_commit(smem_u32(&bar->sp_empty[u]));
             ++n2;
           }
@@ -240,6 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
         for (int j = 0; j < 32; ++j) s[32 + j] = __uint_as_float(raw[j]);
       }
       float mx = -INFINITY;
+      if (!(p.dbg & 2))
 #pragma unroll
       for (int j4 = 0; j4 < 16; ++j4) {
         const float4 b4 = ldg4(brow + 4 * j4);
@@ -253,11 +260,13 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
         }
       }
       float sum = 0.f;
+      if (!(p.dbg & 2)) {
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        s[j] = __expf(s[j] - mx);
-        sum += s[j];
-      }
+        for (int j = 0; j < 64; ++j) {
+          s[j] = __expf(s[j] - mx);
+          sum += s[j];
+        }
+      } else sum = 1.f;
       const float inv = 1.0f / sum;
       // P = softmax row -> bf16 hi/lo pairs -> over the S columns of this row (the A operand of O = P V lives in tensor
       // memory); the other window's 64 keys get zeros (S holds cross-window products there)
@@ -297,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar->o_empty[u]));
       __syncwarp();
-      if (valid) {
+      if (valid && !(p.dbg & 8)) {
         int y = wi * 8 + r + p.shift, x = wj * 8 + c + p.shift;
         if (y >= p.H) y -= p.H;
         if (x >= p.W) x -= p.W;
@@ -351,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
       mbar_wait(smem_u32(&bar->qk_empty), (it & 1) ^ 1);
       constexpr int CH = HD / 8;
 #pragma unroll 2
-      for (int item = ct; item < 128 * CH; item += kConvThreads) {
+      for (int item = ct; item < ((p.dbg & 1) ? 0 : 128 * CH); item += kConvThreads) {
         const int m = item / CH, ch = item - m * CH;
         const bool ok = two || m < 64;
         const int lo_ = land_pixel<HD>(m) + ch * 8;
@@ -385,10 +394,12 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
       }
       __syncwarp();
       // ---- V transposed: row = channel d, K = key; one item = 8 keys (one row of a window) of one channel ----
+      const int vu = it & 1;
+      uint8_t* vt_buf = vt_img + vu * parts * P::VT_PART;
       mbar_wait(smem_u32(&bar->lv_full), it & 1);
-      mbar_wait(smem_u32(&bar->v_empty), (it & 1) ^ 1);
+      mbar_wait(smem_u32(&bar->v_empty[vu]), ((it >> 1) & 1) ^ 1);
 #pragma unroll 2
-      for (int item = ct; item < HD * 16; item += kConvThreads) {
+      for (int item = ct; item < ((p.dbg & 1) ? 0 : HD * 16); item += kConvThreads) {
         const int kg = item / HD, d = item - kg * HD;   // lanes = consecutive channels: conflict-free scalar reads
         const int m0 = kg * 8;                          // keys m0 .. m0+7 = window (kg >> 3), row (kg & 7), columns 0..7
         const bool ok = two || m0 < 64;
@@ -401,13 +412,13 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
         split2(v[4], v[5], hi.z, lo.z);
         split2(v[6], v[7], hi.w, lo.w);
         const int off = (kg >> 3) * P::VT_SLAB + d * 128 + (((kg & 7) ^ (d & 7)) << 4);
-        *reinterpret_cast<uint4*>(vt_img + off) = hi;
-        if (parts == 2) *reinterpret_cast<uint4*>(vt_img + P::VT_PART + off) = lo;
+        *reinterpret_cast<uint4*>(vt_buf + off) = hi;
+        if (parts == 2) *reinterpret_cast<uint4*>(vt_buf + P::VT_PART + off) = lo;
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(smem_u32(&bar->v_full));
+        mbar_arrive(smem_u32(&bar->v_full[vu]));
         mbar_arrive(smem_u32(&bar->lv_empty));
       }
       __syncwarp();
@@ -433,6 +444,9 @@ static PFN_cuTensorMapEncodeTiled encode_fn() {
   return fn;
 }
 
+static bool g_enabled = true;
+static int g_dbg = 0;
+
 template <int HD>
 static int launch_t(const float* qkv, int ldqkv, const float* bias, float* out, int ldo, float* win_mean, int B, int H, int W,
                     int C, int heads, int shift, int parts, int mask_H, int mask_y0, cudaStream_t st) {
@@ -455,6 +469,7 @@ static int launch_t(const float* qkv, int ldqkv, const float* bias, float* out, 
   a.B = B; a.H = H; a.W = W; a.C = C; a.heads = heads; a.shift = shift; a.parts = parts; a.mask_H = mask_H; a.mask_y0 = mask_y0;
   a.n_windows = B * (H / 8) * (W / 8);
   a.n_tiles = ((a.n_windows + 1) / 2) * heads;
+  a.dbg = g_dbg;
   static int sm_count = 0;
   static bool configured = false;
   if (!configured) {
@@ -473,8 +488,7 @@ static int launch_t(const float* qkv, int ldqkv, const float* bias, float* out, 
   return check_launch("window_attn(tc)");
 }
 
-static bool g_enabled = true;
-void set_enabled(int on) { g_enabled = on != 0; }
+void set_enabled(int on) { g_enabled = (on & 1) != 0; g_dbg = on >> 4; }
 
 // head dims 32 / 64 (every stage of the natural-scene model), qkv rows 16-byte aligned
 bool supported(int hd, int ldqkv, int ldo, const float* qkv) {

@@ -192,7 +192,7 @@ def load() -> C.CDLL:
         fn.argtypes = args
     if lib.mphsir_version() < 100:
         raise RuntimeError("libmphsir.so is older than this Python package; rebuild it")
-    if os.environ.get("MPHSIR_WATC") in ("0", "1"):    # A/B switch: tcgen05 window attention vs the mma.sync kernel
+    if os.environ.get("MPHSIR_WATC"):                  # A/B switch: tcgen05 window attention (1 | debug flags << 4) vs mma.sync (0)
         lib.mphsir_debug_window_attn_tc(int(os.environ["MPHSIR_WATC"]))
     if os.environ.get("MPHSIR_PDL") in ("0", "1"):     # A/B switch: programmatic dependent launch of the tcgen05 kernels
         lib.mphsir_debug_pdl(int(os.environ["MPHSIR_PDL"]))
