@@ -124,6 +124,7 @@ MPHSIR_API void mphsir_debug_tc_ebox1(int enabled);         /* 0: two store boxe
 MPHSIR_API void mphsir_debug_pdl(int enabled);              /* 1: programmatic dependent launch of the persistent tcgen05 kernels (default 0: measured, no gain) */
 MPHSIR_API void mphsir_debug_tc_tma_epilogue(int enabled);  /* 0: register-staged GEMM epilogue everywhere (default 1: TMA boxes) */
 MPHSIR_API void mphsir_debug_window_attn_tc(int enabled);   /* 0: mma.sync window attention everywhere (default 1: TMA-fed tcgen05 kernel for head dims 32 / 64) */
+MPHSIR_API void mphsir_debug_window_attn_tc_counters(long long* buf);   /* [grid][16] per-CTA role cycle counters of the tcgen05 window attention (NULL: off) */
 MPHSIR_API void mphsir_debug_dwgram_tma(int enabled);       /* 0: use the direct-load dwconv+Gram kernel everywhere (default 1) */
 MPHSIR_API void mphsir_debug_mlp_counters(long long* buf); /* same idea for the fused MLP kernel */
 MPHSIR_API void mphsir_debug_mlp_flags(int flags);          /* timing experiments (wrong results!): 1 no gelu, 2 no bias, 4 no split */

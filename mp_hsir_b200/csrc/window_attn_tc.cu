@@ -67,6 +67,7 @@ struct Args {
   float* win_mean;             // [B*nW][C]
   int B, H, W, C, heads, shift, parts, mask_H, mask_y0;
   int n_windows, n_tiles;
+  long long* cnt;  // optional [grid][16] cycle counters (role totals and waits), NULL in production
   int dbg;  // timing experiments only (mphsir_debug_window_attn_tc(1 | flags << 4)): 1 skip conversion math, 2 skip softmax math, 4 skip TMA loads, 8 skip epilogue stores/butterfly
 };
 
@@ -77,6 +78,10 @@ __device__ __forceinline__ int land_pixel(int m) {
   const int box = win * 4 + (r >> 2) * 2 + (c >> 2);
   return (box * 16 + (r & 3) * 4 + (c & 3)) * HD;
 }
+
+#define W_T0() (p.cnt ? clock64() : 0)
+#define W_ACC(var, t0) do { if (p.cnt) var += clock64() - (t0); } while (0)
+#define W_WAIT(var, barp, par) do { long long _t = W_T0(); mbar_wait(smem_u32(barp), par); W_ACC(var, _t); } while (0)
 
 template <int HD>
 __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __grid_constant__ Args p) {
@@ -120,6 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
     // =============================== TMA producer ============================================================
     if (lane == 0) {
       uint32_t it = 0;
+      long long w_empty = 0, t_all = W_T0();
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
         const int pair = tile / p.heads, h = tile - pair * p.heads;
         const int nwin = (2 * pair + 1 < p.n_windows) ? 2 : 1;
@@ -127,7 +133,7 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
 #pragma unroll 1
         for (int grp = 0; grp < 2; ++grp) {
           const uint32_t full = smem_u32(grp == 0 ? &bar->lqk_full : &bar->lv_full);
-          mbar_wait(smem_u32(grp == 0 ? &bar->lqk_empty : &bar->lv_empty), (it & 1) ^ 1);
+          W_WAIT(w_empty, grp == 0 ? &bar->lqk_empty : &bar->lv_empty, (it & 1) ^ 1);
           if (p.dbg & 4) { mbar_arrive(full); continue; }
           mbar_expect_tx(full, (uint32_t)((grp == 0 ? 2 : 1) * nwin * 64 * HD * 4));
           for (int win = 0; win < nwin; ++win) {
@@ -145,6 +151,7 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
           }
         }
       }
+      if (p.cnt) { p.cnt[blockIdx.x * 16 + 0] = clock64() - t_all; p.cnt[blockIdx.x * 16 + 1] = w_empty; }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ==============================================================
@@ -160,11 +167,13 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
       const uint64_t ql = make_desc(smem_u32(q_img + P::QK_PART)), kl = make_desc(smem_u32(k_img + P::QK_PART));
       const uint32_t vt = smem_u32(vt_img);
       int n1 = 0, n2 = 0;   // tiles whose S / whose O have been issued
+      long long t_all = W_T0(), t_issue = 0;
       while (n2 < n_local) {
         if (n1 < n_local && n1 - n2 < 2) {
           const int u = n1 & 1;
           if (mbar_try_wait(smem_u32(&bar->qk_full), n1 & 1) && mbar_try_wait(smem_u32(&bar->sp_empty[u]), ((n1 >> 1) & 1) ^ 1)) {
             tc_fence_after();
+            const long long ti = W_T0();
             const uint32_t d = tmem_base + SP_COL + 128 * u;
 #pragma unroll
             for (int ks = 0; ks < HD / 16; ++ks) {
@@ -176,6 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
             }
             umma_commit(smem_u32(&bar->s_full[u]));
             umma_commit(smem_u32(&bar->qk_empty));
+            W_ACC(t_issue, ti);
             ++n1;
           }
         }
@@ -184,6 +194,7 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
           if (mbar_try_wait(smem_u32(&bar->v_full[u]), (n2 >> 1) & 1) && mbar_try_wait(smem_u32(&bar->p_full[u]), (n2 >> 1) & 1) &&
               mbar_try_wait(smem_u32(&bar->o_empty[u]), ((n2 >> 1) & 1) ^ 1)) {
             tc_fence_after();
+            const long long ti = W_T0();
             const uint32_t d = tmem_base + O_COL + 64 * u, ph = tmem_base + SP_COL + 128 * u, pl = ph + PL_OFF;
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {  // 16 keys per step
@@ -199,10 +210,12 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
             umma_commit(smem_u32(&bar->o_full[u]));
             umma_commit(smem_u32(&bar->v_empty[u]));
             umma_commit(smem_u32(&bar->sp_empty[u]));
+            W_ACC(t_issue, ti);
             ++n2;
           }
         }
       }
+      if (p.cnt) { p.cnt[blockIdx.x * 16 + 2] = clock64() - t_all; p.cnt[blockIdx.x * 16 + 3] = t_issue; }
     }
   } else if (warp < kConvWarp0) {
     // =============================== softmax + epilogue (warps 2..9, two groups) =============================
@@ -218,6 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
     float* ps_grp = psum + grp * 4 * HD;
     int n_local = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) ++n_local;
+    long long w_s = 0, w_o = 0, t_soft = 0, t_epi = 0, t_all = W_T0();
     for (int it = grp; it < n_local; it += 2) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int pair = tile / p.heads, h = tile - pair * p.heads;
@@ -233,20 +247,9 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
       const bool lastcol = p.shift != 0 && wj == nWx - 1;
       const float* brow = p.bias + ((long long)h * 64 + t) * 64;
 
-      mbar_wait(smem_u32(&bar->s_full[u]), (it >> 1) & 1);
-      tc_fence_after();
+      // bias + mask of this row first: the 16 loads are in flight while the warp waits for S (issued one by one behind
+      // the tcgen05.ld they cost ~600 clk each: the relative-position table misses L1 next to 227 KB of shared memory)
       float s[64];
-      {
-        uint32_t raw[32];
-        tmem_ld32(sp + 64 * win, raw);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(raw[j]);
-        tmem_ld32(sp + 64 * win + 32, raw);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) s[32 + j] = __uint_as_float(raw[j]);
-      }
-      float mx = -INFINITY;
-      if (!(p.dbg & 2))
 #pragma unroll
       for (int j4 = 0; j4 < 16; ++j4) {
         const float4 b4 = ldg4(brow + 4 * j4);
@@ -255,8 +258,22 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
         for (int e = 0; e < 4; ++e) {
           const int kj = 4 * j4 + e;
           const bool masked = (lastrow && (rq_low != (kj < 32))) || (lastcol && (cq_low != ((kj & 7) < 4)));
-          s[kj] += bb[e] + (masked ? -100.f : 0.f);
-          mx = fmaxf(mx, s[kj]);
+          s[kj] = bb[e] + (masked ? -100.f : 0.f);
+        }
+      }
+      W_WAIT(w_s, &bar->s_full[u], (it >> 1) & 1);
+      const long long ts0 = W_T0();
+      tc_fence_after();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t raw[16];
+        tmem_ld16_nowait(sp + 64 * win + c0, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          s[c0 + j] += __uint_as_float(raw[j]);
+          mx = fmaxf(mx, s[c0 + j]);
         }
       }
       float sum = 0.f;
@@ -288,9 +305,11 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar->p_full[u]));
       __syncwarp();
+      W_ACC(t_soft, ts0);
 
       // ---- epilogue: O row -> image order, window mean (the other group runs the next tile's softmax meanwhile) ----
-      mbar_wait(smem_u32(&bar->o_full[u]), (it >> 1) & 1);
+      W_WAIT(w_o, &bar->o_full[u], (it >> 1) & 1);
+      const long long te0 = W_T0();
       tc_fence_after();
       float o[HD];
       {
@@ -343,6 +362,11 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
       }
       if (grp == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
       else asm volatile("bar.sync 4, 128;" ::: "memory");
+      W_ACC(t_epi, te0);
+    }
+    if (p.cnt && et == 0) {
+      long long* c = p.cnt + blockIdx.x * 16 + 4 + 5 * grp;
+      c[0] = clock64() - t_all; c[1] = w_s; c[2] = w_o; c[3] = t_soft; c[4] = t_epi;
     }
   } else {
     // =============================== converters (warps 10..15) ===============================================
@@ -351,40 +375,63 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
     const float* lq = reinterpret_cast<const float*>(land);
     const float* lk = reinterpret_cast<const float*>(land + P::LAND_OP);
     const float* lv = reinterpret_cast<const float*>(land + 2 * P::LAND_OP);
+    constexpr int CH = HD / 8;
+    constexpr int NQK = (128 * CH + kConvThreads - 1) / kConvThreads;  // items per thread: (row m, 16-byte chunk ch) of Q and K
+    constexpr int NV = (HD * 16 + kConvThreads - 1) / kConvThreads;    // items per thread: (channel d, 8 keys of one window row)
+    // the item -> address maps do not depend on the tile: hoisted out of the loop (the index arithmetic was a third of the
+    // converters' instructions)
+    int qk_src[NQK], qk_dst[NQK], v_src[NV], v_dst[NV];
+    uint32_t win1_bits = 0;   // bit i: QK item i belongs to the second window; bit 16 + i: V item i
+#pragma unroll
+    for (int i = 0; i < NQK; ++i) {
+      const int item = ct + kConvThreads * i;
+      const int m = item / CH, ch = item - m * CH;
+      qk_src[i] = item < 128 * CH ? land_pixel<HD>(m) + ch * 8 : -1;
+      qk_dst[i] = m * 128 + ((ch ^ (m & 7)) << 4);
+      win1_bits |= (uint32_t)(m >= 64) << i;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int item = ct + kConvThreads * i;
+      const int kg = item / HD, d = item - kg * HD;   // lanes = consecutive channels: conflict-free scalar reads
+      v_src[i] = item < HD * 16 ? land_pixel<HD>(kg * 8) + d : -1;   // key e of the row: + (e >> 2) * 16 * HD + (e & 3) * HD
+      v_dst[i] = (kg >> 3) * P::VT_SLAB + d * 128 + (((kg & 7) ^ (d & 7)) << 4);
+      win1_bits |= (uint32_t)(kg >= 8) << (16 + i);
+    }
     uint32_t it = 0;
+    long long w_land = 0, w_img = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int pair = tile / p.heads;
       const bool two = 2 * pair + 1 < p.n_windows;
-      mbar_wait(smem_u32(&bar->lqk_full), it & 1);
+      W_WAIT(w_land, &bar->lqk_full, it & 1);
       // ---- Q (pre-scaled), K: row m, 16-byte chunk ch of the K-major image ----
-      mbar_wait(smem_u32(&bar->qk_empty), (it & 1) ^ 1);
-      constexpr int CH = HD / 8;
-#pragma unroll 2
-      for (int item = ct; item < ((p.dbg & 1) ? 0 : 128 * CH); item += kConvThreads) {
-        const int m = item / CH, ch = item - m * CH;
-        const bool ok = two || m < 64;
-        const int lo_ = land_pixel<HD>(m) + ch * 8;
-        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
-        if (ok) {
-          a0 = *reinterpret_cast<const float4*>(lq + lo_);
-          a1 = *reinterpret_cast<const float4*>(lq + lo_ + 4);
-          b0 = *reinterpret_cast<const float4*>(lk + lo_);
-          b1 = *reinterpret_cast<const float4*>(lk + lo_ + 4);
+      W_WAIT(w_img, &bar->qk_empty, (it & 1) ^ 1);
+      if (!(p.dbg & 1)) {
+#pragma unroll
+        for (int i = 0; i < NQK; ++i) {
+          if (qk_src[i] < 0) continue;
+          const bool ok = two || !((win1_bits >> i) & 1u);
+          float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+          if (ok) {
+            a0 = *reinterpret_cast<const float4*>(lq + qk_src[i]);
+            a1 = *reinterpret_cast<const float4*>(lq + qk_src[i] + 4);
+            b0 = *reinterpret_cast<const float4*>(lk + qk_src[i]);
+            b1 = *reinterpret_cast<const float4*>(lk + qk_src[i] + 4);
+          }
+          uint4 hi, lo;
+          split2(a0.x * scale, a0.y * scale, hi.x, lo.x);
+          split2(a0.z * scale, a0.w * scale, hi.y, lo.y);
+          split2(a1.x * scale, a1.y * scale, hi.z, lo.z);
+          split2(a1.z * scale, a1.w * scale, hi.w, lo.w);
+          *reinterpret_cast<uint4*>(q_img + qk_dst[i]) = hi;
+          if (parts == 2) *reinterpret_cast<uint4*>(q_img + P::QK_PART + qk_dst[i]) = lo;
+          split2(b0.x, b0.y, hi.x, lo.x);
+          split2(b0.z, b0.w, hi.y, lo.y);
+          split2(b1.x, b1.y, hi.z, lo.z);
+          split2(b1.z, b1.w, hi.w, lo.w);
+          *reinterpret_cast<uint4*>(k_img + qk_dst[i]) = hi;
+          if (parts == 2) *reinterpret_cast<uint4*>(k_img + P::QK_PART + qk_dst[i]) = lo;
         }
-        const int off = m * 128 + ((ch ^ (m & 7)) << 4);
-        uint4 hi, lo;
-        split2(a0.x * scale, a0.y * scale, hi.x, lo.x);
-        split2(a0.z * scale, a0.w * scale, hi.y, lo.y);
-        split2(a1.x * scale, a1.y * scale, hi.z, lo.z);
-        split2(a1.z * scale, a1.w * scale, hi.w, lo.w);
-        *reinterpret_cast<uint4*>(q_img + off) = hi;
-        if (parts == 2) *reinterpret_cast<uint4*>(q_img + P::QK_PART + off) = lo;
-        split2(b0.x, b0.y, hi.x, lo.x);
-        split2(b0.z, b0.w, hi.y, lo.y);
-        split2(b1.x, b1.y, hi.z, lo.z);
-        split2(b1.z, b1.w, hi.w, lo.w);
-        *reinterpret_cast<uint4*>(k_img + off) = hi;
-        if (parts == 2) *reinterpret_cast<uint4*>(k_img + P::QK_PART + off) = lo;
       }
       fence_proxy_async();
       __syncwarp();
@@ -396,24 +443,24 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
       // ---- V transposed: row = channel d, K = key; one item = 8 keys (one row of a window) of one channel ----
       const int vu = it & 1;
       uint8_t* vt_buf = vt_img + vu * parts * P::VT_PART;
-      mbar_wait(smem_u32(&bar->lv_full), it & 1);
-      mbar_wait(smem_u32(&bar->v_empty[vu]), ((it >> 1) & 1) ^ 1);
-#pragma unroll 2
-      for (int item = ct; item < ((p.dbg & 1) ? 0 : HD * 16); item += kConvThreads) {
-        const int kg = item / HD, d = item - kg * HD;   // lanes = consecutive channels: conflict-free scalar reads
-        const int m0 = kg * 8;                          // keys m0 .. m0+7 = window (kg >> 3), row (kg & 7), columns 0..7
-        const bool ok = two || m0 < 64;
-        float v[8];
+      W_WAIT(w_land, &bar->lv_full, it & 1);
+      W_WAIT(w_img, &bar->v_empty[vu], ((it >> 1) & 1) ^ 1);
+      if (!(p.dbg & 1)) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = ok ? lv[land_pixel<HD>(m0 + e) + d] : 0.f;
-        uint4 hi, lo;
-        split2(v[0], v[1], hi.x, lo.x);
-        split2(v[2], v[3], hi.y, lo.y);
-        split2(v[4], v[5], hi.z, lo.z);
-        split2(v[6], v[7], hi.w, lo.w);
-        const int off = (kg >> 3) * P::VT_SLAB + d * 128 + (((kg & 7) ^ (d & 7)) << 4);
-        *reinterpret_cast<uint4*>(vt_buf + off) = hi;
-        if (parts == 2) *reinterpret_cast<uint4*>(vt_buf + P::VT_PART + off) = lo;
+        for (int i = 0; i < NV; ++i) {
+          if (v_src[i] < 0) continue;
+          const bool ok = two || !((win1_bits >> (16 + i)) & 1u);
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = ok ? lv[v_src[i] + (e >> 2) * 16 * HD + (e & 3) * HD] : 0.f;
+          uint4 hi, lo;
+          split2(v[0], v[1], hi.x, lo.x);
+          split2(v[2], v[3], hi.y, lo.y);
+          split2(v[4], v[5], hi.z, lo.z);
+          split2(v[6], v[7], hi.w, lo.w);
+          *reinterpret_cast<uint4*>(vt_buf + v_dst[i]) = hi;
+          if (parts == 2) *reinterpret_cast<uint4*>(vt_buf + P::VT_PART + v_dst[i]) = lo;
+        }
       }
       fence_proxy_async();
       __syncwarp();
@@ -423,6 +470,7 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
       }
       __syncwarp();
     }
+    if (p.cnt && ct == 0) { p.cnt[blockIdx.x * 16 + 14] = w_land; p.cnt[blockIdx.x * 16 + 15] = w_img; }
   }
 
   tc_fence_before();
@@ -446,6 +494,8 @@ static PFN_cuTensorMapEncodeTiled encode_fn() {
 
 static bool g_enabled = true;
 static int g_dbg = 0;
+static long long* g_cnt = nullptr;
+void set_counters(long long* p) { g_cnt = p; }
 
 template <int HD>
 static int launch_t(const float* qkv, int ldqkv, const float* bias, float* out, int ldo, float* win_mean, int B, int H, int W,
@@ -470,6 +520,7 @@ static int launch_t(const float* qkv, int ldqkv, const float* bias, float* out, 
   a.n_windows = B * (H / 8) * (W / 8);
   a.n_tiles = ((a.n_windows + 1) / 2) * heads;
   a.dbg = g_dbg;
+  a.cnt = g_cnt;
   static int sm_count = 0;
   static bool configured = false;
   if (!configured) {
@@ -506,3 +557,4 @@ int launch(const float* qkv, int ldqkv, const float* bias, float* out, int ldo, 
 }  // namespace mphsir
 
 extern "C" MPHSIR_API void mphsir_debug_window_attn_tc(int enabled) { mphsir::watc::set_enabled(enabled); }
+extern "C" MPHSIR_API void mphsir_debug_window_attn_tc_counters(long long* buf) { mphsir::watc::set_counters(buf); }

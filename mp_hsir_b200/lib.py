@@ -105,6 +105,7 @@ SIGNATURES = {
     "mphsir_debug_mlp_flags": (None, [_I]),
     "mphsir_debug_dwgram_tma": (None, [_I]),
     "mphsir_debug_window_attn_tc": (None, [_I]),
+    "mphsir_debug_window_attn_tc_counters": (None, [_VP]),
     "mphsir_debug_tc_tma_epilogue": (None, [_I]),
     "mphsir_debug_tc_ebox1": (None, [_I]),
     "mphsir_debug_pdl": (None, [_I]),
