@@ -223,6 +223,14 @@ MPHSIR_API int mphsir_window_attn_fwd(const float* qkv, int ldqkv, const float* 
 MPHSIR_API int mphsir_window_attn_band_fwd(const float* qkv, int ldqkv, const float* bias, float* out, int ldo,
                            float* win_mean, int B, int H, int W, int C, int heads, int shift, int precision,
                            int mask_H, int mask_y0, void* stream);
+/* The same operator as a TMA-fed tcgen05 kernel (window_attn_tc.cu: two windows per 128-row MMA tile, S / P / O in tensor
+ * memory, P the TMEM A operand of P V) for head dims 32 and 64 (mphsir_window_attn_tc_supported).  bias_t is the
+ * relative-position bias TRANSPOSED, [heads][key 64][query 64], so that a warp's 32 queries read one line per key. */
+MPHSIR_API int mphsir_window_attn_tc_supported(int head_dim);
+MPHSIR_API int mphsir_window_attn_tc_enabled(void);   /* debug switch state (mphsir_debug_window_attn_tc) */
+MPHSIR_API int mphsir_window_attn_tc_fwd(const float* qkv, int ldqkv, const float* bias_t, float* out, int ldo,
+                           float* win_mean, int B, int H, int W, int C, int heads, int shift, int precision,
+                           int mask_H, int mask_y0, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Local spectral branch (low-rank spectral-prompt gate), one fused kernel per window:

@@ -190,11 +190,6 @@ static int launch_wa(const float* qkv, int ldqkv, const float* bias, float* out,
   return check_launch("window_attn");
 }
 
-namespace watc {  // window_attn_tc.cu: TMA-fed tcgen05 kernel, two windows per 128-row MMA tile (head dims 32 / 64)
-bool supported(int hd, int ldqkv, int ldo, const float* qkv);
-int launch(const float* qkv, int ldqkv, const float* bias, float* out, int ldo, float* win_mean, int B, int H, int W, int C, int heads,
-           int shift, int parts, int mask_H, int mask_y0, cudaStream_t st);
-}
 namespace wa {
 int launch_window_attn_mma(const float* qkv, int ldqkv, const float* bias, float* out, int ldo, float* win_mean, int B,
                            int H, int W, int C, int heads, int shift, int parts, int mask_H, int mask_y0, cudaStream_t st);
@@ -216,12 +211,9 @@ extern "C" int mphsir_window_attn_band_fwd(const float* qkv, int ldqkv, const fl
   MPHSIR_REQUIRE(mask_H >= 8 && mask_y0 >= 0 && mask_y0 < mask_H, "window_attn: bad mask geometry (mask_H=%d mask_y0=%d)", mask_H, mask_y0);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   MPHSIR_REQUIRE(precision >= MPHSIR_PREC_FP32_SIMT && precision <= MPHSIR_PREC_BF16, "window_attn: unknown precision %d", precision);
-  if (precision != MPHSIR_PREC_FP32_SIMT) {
-    const int parts = precision == MPHSIR_PREC_BF16X3 ? 2 : 1;
-    if (watc::supported(C / heads, ldqkv, ldo, qkv) && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
-      return watc::launch(qkv, ldqkv, bias, out, ldo, win_mean, B, H, W, C, heads, shift, parts, mask_H, mask_y0, st);
-    return wa::launch_window_attn_mma(qkv, ldqkv, bias, out, ldo, win_mean, B, H, W, C, heads, shift, parts, mask_H, mask_y0, st);
-  }
+  if (precision != MPHSIR_PREC_FP32_SIMT)
+    return wa::launch_window_attn_mma(qkv, ldqkv, bias, out, ldo, win_mean, B, H, W, C, heads, shift,
+                                      precision == MPHSIR_PREC_BF16X3 ? 2 : 1, mask_H, mask_y0, st);
   MPHSIR_REQUIRE(mask_H == H && mask_y0 == 0, "window_attn: row bands of a sharded scene run on the tensor-core precisions only");
   switch (C / heads) {
     case 32: return launch_wa<32>(qkv, ldqkv, bias, out, ldo, win_mean, B, H, W, C, heads, shift, st);

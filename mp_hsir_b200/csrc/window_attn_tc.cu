@@ -61,7 +61,7 @@ struct Bars {
 
 struct Args {
   alignas(64) CUtensorMap tm;  // qkv as [B][H][W][3C] fp32, box [1][4][4][HD]
-  const float* bias;           // [heads][64][64]
+  const float* bias;           // TRANSPOSED relative-position bias [heads][key 64][query 64]: lanes = consecutive queries read one line per key
   float* out;
   long long ldo;
   float* win_mean;             // [B*nW][C]
@@ -245,21 +245,16 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
       if (ysg >= p.mask_H) ysg -= p.mask_H;
       const bool lastrow = p.shift != 0 && ysg >= p.mask_H - 8;
       const bool lastcol = p.shift != 0 && wj == nWx - 1;
-      const float* brow = p.bias + ((long long)h * 64 + t) * 64;
+      const float* bcol = p.bias + (long long)h * 64 * 64 + t;   // + 64 * key: coalesced over the warp's 32 consecutive queries
 
-      // bias + mask of this row first: the 16 loads are in flight while the warp waits for S (issued one by one behind
-      // the tcgen05.ld they cost ~600 clk each: the relative-position table misses L1 next to 227 KB of shared memory)
+      // bias + mask of this row first: the loads are in flight while the warp waits for S.  The table is read TRANSPOSED
+      // ([key][query]): one 128-byte line per key and warp — row-per-lane float4 loads of the [query][key] table touched
+      // 32 lines per instruction and, with the row-per-lane output stores, saturated the L1/LSU data path (ncu: l1tex 72 %)
       float s[64];
 #pragma unroll
-      for (int j4 = 0; j4 < 16; ++j4) {
-        const float4 b4 = ldg4(brow + 4 * j4);
-        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int kj = 4 * j4 + e;
-          const bool masked = (lastrow && (rq_low != (kj < 32))) || (lastcol && (cq_low != ((kj & 7) < 4)));
-          s[kj] = bb[e] + (masked ? -100.f : 0.f);
-        }
+      for (int kj = 0; kj < 64; ++kj) {
+        const bool masked = (lastrow && (rq_low != (kj < 32))) || (lastcol && (cq_low != ((kj & 7) < 4)));
+        s[kj] = __ldg(bcol + 64 * kj) + (masked ? -100.f : 0.f);
       }
       W_WAIT(w_s, &bar->s_full[u], (it >> 1) & 1);
       const long long ts0 = W_T0();
@@ -543,8 +538,9 @@ void set_enabled(int on) { g_enabled = (on & 1) != 0; g_dbg = on >> 4; }
 
 // head dims 32 / 64 (every stage of the natural-scene model), qkv rows 16-byte aligned
 bool supported(int hd, int ldqkv, int ldo, const float* qkv) {
-  return g_enabled && (hd == 32 || hd == 64) && ldqkv % 4 == 0 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0;
+  return (hd == 32 || hd == 64) && ldqkv % 4 == 0 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0;
 }
+bool enabled() { return g_enabled; }
 
 int launch(const float* qkv, int ldqkv, const float* bias, float* out, int ldo, float* win_mean, int B, int H, int W, int C, int heads,
            int shift, int parts, int mask_H, int mask_y0, cudaStream_t st) {
@@ -557,4 +553,23 @@ int launch(const float* qkv, int ldqkv, const float* bias, float* out, int ldo, 
 }  // namespace mphsir
 
 extern "C" MPHSIR_API void mphsir_debug_window_attn_tc(int enabled) { mphsir::watc::set_enabled(enabled); }
+extern "C" MPHSIR_API int mphsir_window_attn_tc_enabled(void) { return mphsir::watc::enabled() ? 1 : 0; }
+
+extern "C" int mphsir_window_attn_tc_supported(int head_dim) { return head_dim == 32 || head_dim == 64; }
+
+extern "C" int mphsir_window_attn_tc_fwd(const float* qkv, int ldqkv, const float* bias_t, float* out, int ldo, float* win_mean, int B,
+                                         int H, int W, int C, int heads, int shift, int precision, int mask_H, int mask_y0,
+                                         void* stream) {
+  using namespace mphsir;
+  MPHSIR_REQUIRE(qkv && bias_t && out && win_mean, "window_attn(tc): null operand");
+  MPHSIR_REQUIRE(B > 0 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0, "window_attn(tc): H=%d W=%d must be multiples of 8", H, W);
+  MPHSIR_REQUIRE(heads > 0 && C % heads == 0 && (C / heads == 32 || C / heads == 64), "window_attn(tc): head_dim %d not in {32, 64}", heads > 0 ? C / heads : 0);
+  MPHSIR_REQUIRE(shift == 0 || shift == 4, "window_attn(tc): shift must be 0 or 4");
+  MPHSIR_REQUIRE(ldqkv >= 3 * C && ldqkv % 4 == 0 && ldo >= C && ldo % 4 == 0, "window_attn(tc): bad leading dimensions");
+  MPHSIR_REQUIRE(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "window_attn(tc): qkv / out must be 16-byte aligned");
+  MPHSIR_REQUIRE(precision == MPHSIR_PREC_BF16X3 || precision == MPHSIR_PREC_BF16, "window_attn(tc): tensor-core precisions only");
+  MPHSIR_REQUIRE(mask_H >= 8 && mask_y0 >= 0 && mask_y0 < mask_H, "window_attn(tc): bad mask geometry (mask_H=%d mask_y0=%d)", mask_H, mask_y0);
+  return watc::launch(qkv, ldqkv, bias_t, out, ldo, win_mean, B, H, W, C, heads, shift, precision == MPHSIR_PREC_BF16X3 ? 2 : 1, mask_H,
+                      mask_y0, reinterpret_cast<cudaStream_t>(stream));
+}
 extern "C" MPHSIR_API void mphsir_debug_window_attn_tc_counters(long long* buf) { mphsir::watc::set_counters(buf); }

@@ -258,6 +258,8 @@ class Engine:
                 d["proj_w"] = L(a.proj.weight, st.dim, st.dim)
                 d["proj_b"] = f32(a.proj.bias).contiguous()
                 d["rpb"] = rel_pos_bias(f32(a.relative_position_bias_table), a.relative_position_index.to(dev))
+                if self.fold_weights:   # inference: [heads, key, query] copy for the tcgen05 window-attention kernel
+                    d["rpb_t"] = d["rpb"].transpose(1, 2).contiguous()
                 g = blk.gobal_spectral_attn
                 d["temp"] = f32(g.temperature).reshape(-1).contiguous()
                 d["sqkv_w"] = L(g.qkv.weight, 3 * st.dim, st.dim)
@@ -472,7 +474,8 @@ class Engine:
         # LN1 + qkv projection (net/MP_HSIR.py:667, :195)
         self._gemm(x, w["qkv_w"], qkv, 3 * C, ln=w["ln1"], bias=w["qkv_b"])
         # shifted-window attention core + per-window mean (:671-683, :198-215)
-        lib.window_attn(qkv, w["rpb"], core, wmean, B, H, W, C, heads, shift, precision=self.prec, mask_H=mask_H, mask_y0=mask_y0)
+        lib.window_attn(qkv, w["rpb"], core, wmean, B, H, W, C, heads, shift, precision=self.prec, mask_H=mask_H, mask_y0=mask_y0,
+                        bias_t=w.get("rpb_t"))
         # local spectral gate (:132-152)
         if "gate_cat_w" not in w:
             pass  # un-folded weights (trainer): the gate is computed below from the window mean of sa

@@ -118,6 +118,9 @@ SIGNATURES = {
     "mphsir_conv3x3_fwd": (_I, [C.POINTER(ConvParams), _VP]),
     "mphsir_window_attn_fwd": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "mphsir_window_attn_band_fwd": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP]),
+    "mphsir_window_attn_tc_supported": (_I, [_I]),
+    "mphsir_window_attn_tc_enabled": (_I, []),
+    "mphsir_window_attn_tc_fwd": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "mphsir_dwgram_band_fwd": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "mphsir_gram_reduce": (_I, [_VP, _I, _VP, _I, _I, _I, _VP]),
     "mphsir_local_gate_fwd": (_I, [C.POINTER(LocalGateParams), _VP]),
@@ -453,14 +456,24 @@ def conv3x3(X: View, Wt, Y_ptr: int, ldy: int, B: int, H: int, W: int, Cin: int,
 
 
 def window_attn(qkv: View, bias: torch.Tensor, out: View, win_mean: torch.Tensor, B: int, H: int, W: int,
-                Cc: int, heads: int, shift: int, precision: int = 0, mask_H: Optional[int] = None, mask_y0: int = 0) -> None:
-    """mask_H / mask_y0: row band of a sharded scene (mphsir_window_attn_band_fwd); default = the whole image."""
+                Cc: int, heads: int, shift: int, precision: int = 0, mask_H: Optional[int] = None, mask_y0: int = 0,
+                bias_t: Optional[torch.Tensor] = None) -> None:
+    """mask_H / mask_y0: row band of a sharded scene (mphsir_window_attn_band_fwd); default = the whole image.
+    bias_t: the bias transposed to [heads, key, query] — when given (and the head dim is 32 / 64, tensor-core precision) the
+    TMA-fed tcgen05 kernel runs instead of the mma.sync one."""
     n = B * H * W
     mH = H if mask_H is None else mask_H
+    L = load()
+    if bias_t is not None and precision != PREC_FP32_SIMT and L.mphsir_window_attn_tc_supported(Cc // heads) and L.mphsir_window_attn_tc_enabled():
+        _launch("window_attn_tc_fwd",
+                lambda: L.mphsir_window_attn_tc_fwd(qkv.ptr, qkv.ld, bias_t.data_ptr(), out.ptr, out.ld, win_mean.data_ptr(), B, H, W,
+                                                    Cc, heads, shift, precision, mH, mask_y0, stream_ptr()),
+                lambda: (4.0 * n * 64 * Cc, 4.0 * (4 * n * Cc + n // 64 * Cc), ("", "window_attn_tc3", "window_attn_tc1")[precision]))
+        return
     _launch("window_attn_fwd",
-            lambda: load().mphsir_window_attn_band_fwd(qkv.ptr, qkv.ld, bias.data_ptr(), out.ptr, out.ld,
-                                                       win_mean.data_ptr(), B, H, W, Cc, heads, shift, precision, mH, mask_y0,
-                                                       stream_ptr()),
+            lambda: L.mphsir_window_attn_band_fwd(qkv.ptr, qkv.ld, bias.data_ptr(), out.ptr, out.ld,
+                                                  win_mean.data_ptr(), B, H, W, Cc, heads, shift, precision, mH, mask_y0,
+                                                  stream_ptr()),
             lambda: (4.0 * n * 64 * Cc, 4.0 * (4 * n * Cc + n // 64 * Cc), ("window_attn", "window_attn_mma3", "window_attn_mma1")[precision]))
 
 

@@ -206,7 +206,8 @@ def test_window_attention_tcgen05_equals_mma_sync_kernel(C, heads, B, H, W, prec
             out = out_mat(B * H * W, C)
             wm = torch.full((B_, C), float("nan"), device=DEV)
             try:
-                lib.window_attn(V(qkv), bias, V(out), wm, B, H, W, C, heads, shift, precision=prec, mask_H=mask_H, mask_y0=mask_y0)
+                lib.window_attn(V(qkv), bias, V(out), wm, B, H, W, C, heads, shift, precision=prec, mask_H=mask_H, mask_y0=mask_y0,
+                                bias_t=bias.transpose(1, 2).contiguous())
                 torch.cuda.synchronize()
             finally:
                 lib.load().mphsir_debug_window_attn_tc(1)

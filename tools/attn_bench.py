@@ -13,7 +13,8 @@ qkv = torch.randn(H * W, 3 * C, device=dev)
 bias = torch.randn(heads, 64, 64, device=dev)
 out = torch.empty(H * W, C, device=dev)
 wm = torch.empty(H * W // 64, C, device=dev)
-run = lambda: lib.window_attn(View.of(qkv), bias, View.of(out), wm, 1, H, W, C, heads, 4, precision=lib.PREC_BF16X3)
+bias_t = bias.transpose(1, 2).contiguous()
+run = lambda: lib.window_attn(View.of(qkv), bias, View.of(out), wm, 1, H, W, C, heads, 4, precision=lib.PREC_BF16X3, bias_t=bias_t)
 for _ in range(3): run()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
