@@ -258,7 +258,10 @@ class Engine:
                 d["proj_w"] = L(a.proj.weight, st.dim, st.dim)
                 d["proj_b"] = f32(a.proj.bias).contiguous()
                 d["rpb"] = rel_pos_bias(f32(a.relative_position_bias_table), a.relative_position_index.to(dev))
-                if self.fold_weights:   # inference: [heads, key, query] copy for the tcgen05 window-attention kernel
+                if self.fold_weights and st.dim // st.heads == 64:
+                    # inference, head dim 64 (decoder_level1 / refinement: 61 % of the attention tokens): [heads, key, query]
+                    # copy for the TMA-fed tcgen05 kernel (152 vs 160 us per launch at 512x512; at head dim 32 the mma.sync
+                    # kernel is still ahead, 94 vs 104 us, so those stages keep it)
                     d["rpb_t"] = d["rpb"].transpose(1, 2).contiguous()
                 g = blk.gobal_spectral_attn
                 d["temp"] = f32(g.temperature).reshape(-1).contiguous()
