@@ -12,8 +12,8 @@ dev = torch.device("cuda", 0)
 cfg, net = bench.build_net(model, dev)
 if len(sys.argv) > 2:
     net.set_precision(sys.argv[2])
-x = bench.make_input(shape, 0).to(dev)
-tid = torch.zeros(shape[0], dtype=torch.long, device=dev)
+x, _, tid = bench.make_input(shape, 0, workload)
+x, tid = x.to(dev), tid.to(dev)
 
 # wrap lib.gemm / conv3x3 cost lambdas to carry shapes in the tag
 orig_launch = lib._launch
@@ -32,5 +32,5 @@ with torch.no_grad():
     lib.PROFILER = None
 tot = sum(a["ms"] for a in agg.values())
 print(f"total {tot:.2f} ms")
-for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:45]:
+for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:70]:
     print(f"{a['ms']:7.3f} ms x{a['launches']:3d}  {a['bytes']/a['ms']/1e6:7.0f} GB/s {a['flops']/a['ms']/1e9:7.1f} TF  {k}")
