@@ -33,7 +33,7 @@
 namespace mphsir {
 namespace tc {
 
-constexpr int kMlpThreads = 608;  // warp 0: B loader, 1: MMA, 2-9: GLU, 10-13: converters, 14-17: final epilogue, 18: X loader
+constexpr int kMlpThreads = 864;  // warp 0: B loader, 1: MMA (peer CTA: relay), 2-17: GLU, 18-21: converters, 22-25: final epilogue, 26: X loader
 constexpr int M_SLAB = 128 * 128;        // one bf16 part of a 128-row x 64-k weight slab
 constexpr int M_LAND = 128 * 64 * 4;     // fp32 landing slot of one 64-k slab of X: two swizzled [128 x 32] boxes
 constexpr int M_NL = 2;                  // landing slots (one tile at C = 128, two at C = 64)
@@ -70,39 +70,57 @@ struct MlpArgs {
 struct MlpSmem {
   uint64_t land_full[M_NL], land_empty[M_NL];
   uint64_t x_full, x_empty;
-  uint64_t b_full[8], b_empty[8];
+  uint64_t b_full[8], b_peer[8], b_empty[8];
   uint64_t acc1_full[2], h_full[2];
   uint64_t acc2_full, acc2_empty;
   uint64_t res_full, res_empty;
   uint32_t tmem_base;
 };
 
+// value * gelu_erf(gate) with the 0.5 of the Gaussian CDF folded into the Abramowitz-Stegun 7.1.26 coefficients
+// (|erf error| <= 1.5e-7): 13 FP32 + 2 MUFU instructions per hidden unit — the GLU warps are issue-bound.
+__device__ __forceinline__ float glu_unit(float val, float gat) {
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.23164189f, fabsf(gat), 1.0f)));   // 1 / (1 + p |x| / sqrt 2)
+  float pl = fmaf(0.5307027145f, t, -0.7265760135f);
+  pl = fmaf(pl, t, 0.7107068705f);
+  pl = fmaf(pl, t, -0.142248368f);
+  pl = fmaf(pl, t, 0.127414796f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(gat * gat * -0.72134752044f));              // exp(-x^2 / 2)
+  const float half_erf = fmaf(-(pl * t), e, 0.5f);                                               // erf(|x| / sqrt 2) / 2
+  return (val * gat) * (0.5f + copysignf(half_erf, gat));
+}
+
 // One GLU work item: 32 fc1 columns (= 16 hidden units) x 32 rows of TMEM lane quadrant `quad`.
 // acc1 (+ b1) -> value * gelu(gate) -> bf16 hi/lo -> tcgen05.st over the first 16 of the 32 columns just read:
 // hidden units 16 i .. 16 i + 15 of the row = k-step i of fc2 (hi part 8 columns, lo part the next 8).
-__device__ __forceinline__ void glu_item(uint32_t taddr, float bias_lane, bool cols_ok, int parts) {
-  uint32_t r[32];
-  tmem_ld32(taddr, r);
+// `bias` = the item's 32 interleaved fc1 biases (the same address in every lane: broadcast loads), NULL for an item
+// beyond N1 (N1 is a multiple of 32, so an item is valid or not as a whole): its columns hold stale TMEM bits and
+// H must be zero there.
+__device__ __forceinline__ void glu_item(uint32_t taddr, const float* __restrict__ bias, int parts, long long* prof) {
   uint32_t hi[8], lo[8];
+  long long t0 = prof ? clock64() : 0;
+  if (bias != nullptr) {
+    uint32_t r[32];
+    tmem_ld32(taddr, r);
+    if (prof) { const long long t1 = clock64(); prof[0] += t1 - t0; t0 = t1; }
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    float hv[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int cidx = 4 * e + 2 * u;
-      // columns beyond N1 may hold stale TMEM bits: mask the INPUTS (a select), never branch around the gelu --
-      // a branch per output serialises the 16 independent erf chains of the item
-      float val = __uint_as_float(r[cidx]) + __shfl_sync(0xffffffffu, bias_lane, cidx);
-      float gat = __uint_as_float(r[cidx + 1]) + __shfl_sync(0xffffffffu, bias_lane, cidx + 1);
-      val = cols_ok ? val : 0.f;
-      gat = cols_ok ? gat : 0.f;
-      hv[u] = val * gelu_erf_fast(gat);
+    for (int e = 0; e < 8; ++e) {
+      const float4 b = ldg4(bias + 4 * e);
+      const float h0 = glu_unit(__uint_as_float(r[4 * e]) + b.x, __uint_as_float(r[4 * e + 1]) + b.y);
+      const float h1 = glu_unit(__uint_as_float(r[4 * e + 2]) + b.z, __uint_as_float(r[4 * e + 3]) + b.w);
+      split2(h0, h1, hi[e], lo[e]);
     }
-    split2(hv[0], hv[1], hi[e], lo[e]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) hi[e] = lo[e] = 0u;
   }
+  if (prof) { const long long t1 = clock64(); prof[1] += t1 - t0; t0 = t1; }
   tmem_st8(taddr, hi);
   if (parts == 2) tmem_st8(taddr + 8, lo);
   tmem_st_wait();
+  if (prof) prof[2] += clock64() - t0;
 }
 
 __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_constant__ MlpArgs p) {
@@ -110,42 +128,50 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
   pdl_launch_dependents();
   MlpSmem* sm = reinterpret_cast<MlpSmem*>(smem_raw);
   const int parts = p.parts;
-  const int b_slot_bytes = M_SLAB * parts;
+  const int b_slot_bytes = (M_SLAB / 2) * parts;   // this CTA's half (64 rows) of a 128-row x 64-k weight block, hi [+ lo]
   uint8_t* land = smem_raw + 1024;
   uint8_t* resbuf = land + (size_t)M_NL * M_LAND;            // residual tile: C/32 boxes of [128 rows x 32 floats]
   uint8_t* b_ring = resbuf + (size_t)(p.C / 32) * (M_LAND / 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Ks1 = p.ks1, NJ = p.nj, C = p.C;
-  const int num_tiles = p.num_tiles;
+  const int num_pairs = (p.num_tiles + 1) >> 1;   // a CTA pair walks tile pairs (2 q, 2 q + 1); an odd tail tile's twin is all out of bounds
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < M_NL; ++i) {
       mbar_init(smem_u32(&sm->land_full[i]), 1);
       mbar_init(smem_u32(&sm->land_empty[i]), 4);
     }
-    mbar_init(smem_u32(&sm->x_full), 4);
+    mbar_init(smem_u32(&sm->x_full), 8);     // leader: 4 converter warps of each CTA of the pair
     mbar_init(smem_u32(&sm->x_empty), 1);
     for (int i = 0; i < 8; ++i) {
       mbar_init(smem_u32(&sm->b_full[i]), 1);
+      mbar_init(smem_u32(&sm->b_peer[i]), 1);   // leader: the peer CTA's half of the weight block has landed
       mbar_init(smem_u32(&sm->b_empty[i]), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&sm->acc1_full[i]), 1);
-      mbar_init(smem_u32(&sm->h_full[i]), 8);
+      mbar_init(smem_u32(&sm->h_full[i]), 32);  // leader: 16 GLU warps of each CTA
     }
     mbar_init(smem_u32(&sm->acc2_full), 1);
-    mbar_init(smem_u32(&sm->acc2_empty), 4);
+    mbar_init(smem_u32(&sm->acc2_empty), 8); // leader: 4 epilogue warps of each CTA
     mbar_init(smem_u32(&sm->res_full), 1);
     mbar_init(smem_u32(&sm->res_empty), 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(&sm->tmem_base), 512);
+  cluster_sync_all();   // the peer's mbarriers exist before a remote arrive / multicast commit targets them
+  if (warp == 1) tmem_alloc2(smem_u32(&sm->tmem_base), 512);
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   pdl_wait();  // prologue above overlaps the predecessor's tail (programmatic dependent launch)
   const uint32_t tmem_base = sm->tmem_base;
+  const uint32_t crank = cluster_ctarank();
+  const int pair0 = blockIdx.x >> 1, npairs = gridDim.x >> 1;   // this CTA's first tile pair / pairs in flight
+  // barriers the MMA issuer waits on live in the leader CTA; both CTAs arrive there
+  const uint32_t L_x_full = mapa_cluster(smem_u32(&sm->x_full), 0);
+  const uint32_t L_acc2_empty = mapa_cluster(smem_u32(&sm->acc2_empty), 0);
+  const uint32_t L_h_full[2] = {mapa_cluster(smem_u32(&sm->h_full[0]), 0), mapa_cluster(smem_u32(&sm->h_full[1]), 0)};
 
   if (warp == 0) {
     // =============================== B loader: W1 / W2 blocks =================================
@@ -154,13 +180,14 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
       auto load_block = [&](const uint8_t* img, int ks_total, int np_rows, int slab, int row0, int rows) {
         const int slot = it % p.nb;
         mbar_wait(smem_u32(&sm->b_empty[slot]), ((it / p.nb) & 1) ^ 1);
-        const uint32_t bytes = rows * 128;
+        const uint32_t bytes = (rows >> 1) * 128;   // this CTA's half of the block's rows (= of the MMA's N)
+        row0 += (int)crank * (rows >> 1);
         const uint32_t full = smem_u32(&sm->b_full[slot]);
         if (elect_one()) {
           mbar_expect_tx(full, (p.dbg_flags & 16) ? 0 : bytes * parts);
           for (int part = 0; part < parts && !(p.dbg_flags & 16); ++part) {
             const uint8_t* src = img + ((size_t)(part * ks_total + slab) * np_rows + row0) * 128;
-            bulk_g2s(smem_u32(b_ring + (size_t)slot * b_slot_bytes + part * M_SLAB), src, bytes, full);
+            bulk_g2s(smem_u32(b_ring + (size_t)slot * b_slot_bytes + part * (M_SLAB / 2)), src, bytes, full);
           }
         }
         __syncwarp();
@@ -168,7 +195,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
       };
       const uint8_t* w1 = reinterpret_cast<const uint8_t*>(p.W1img);
       const uint8_t* w2 = reinterpret_cast<const uint8_t*>(p.W2img);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int pr = pair0; pr < num_pairs; pr += npairs) {
+      const int tile = 2 * pr + (int)crank; (void)tile;
         for (int s = 0; s < Ks1; ++s) load_block(w1, Ks1, p.Np1, s, 0, min(128, p.Np1));
         for (int j = 0; j < NJ; ++j) {
           if (j + 1 < NJ)
@@ -177,52 +205,73 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
         }
       }
     }
+  } else if (warp == 1 && crank != 0) {
+    // =============================== peer CTA: weight-block relay =============================
+    // only the leader issues MMAs; this warp tells it when the peer's half of a weight block has landed
+    const uint32_t slots_per_pair = (uint32_t)(Ks1 * NJ + NJ);
+    uint32_t b_it = 0;
+    for (int pr = pair0; pr < num_pairs; pr += npairs)
+      for (uint32_t i = 0; i < slots_per_pair; ++i, ++b_it) {
+        const int b_slot = b_it % p.nb;
+        mbar_wait(smem_u32(&sm->b_full[b_slot]), (b_it / p.nb) & 1);
+        // relaxed: the block sits complete in THIS CTA's shared memory (complete_tx fired) and is read there by this SM's
+        // tensor core; nothing travels with the arrive, and a release.cluster fence per block would cap the relay at one
+        // block per ~1.5k clk — more than the MMAs of a block take
+        if (lane == 0) mbar_arrive_remote_relaxed(mapa_cluster(smem_u32(&sm->b_peer[b_slot]), 0));
+        __syncwarp();
+      }
   } else if (warp == 1) {
-    // =============================== MMA issuer ================================================
-    // the whole warp walks the loop nest; one elected lane issues the MMAs / commits (see tc::elect_one)
+    // =============================== MMA issuer (leader CTA of the pair) ========================
+    // M = 256 instructions over both CTAs' tensor / shared memory (cta_group::2): 74 clk per 256 x 128 x 16 against 100 clk
+    // per 128 x 128 x 16 of a single CTA (tools/mma_rate.cu).  The whole warp walks the loop nest; one elected lane issues
+    // the MMAs / commits (see tc::elect_one); every commit is multicast to the same barrier in both CTAs.
     {
       uint32_t b_it = 0, c1_it = 0, t_it = 0;
       long long w_x = 0, w_b = 0, w_h = 0, w_acc2 = 0, t_all = M_T0();
       const bool no_mma = (p.dbg_flags & 4096) != 0;
       const uint32_t xh = tmem_base + XH_COL, xl = tmem_base + XL_COL;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_it) {
+      for (int pr = pair0; pr < num_pairs; pr += npairs, ++t_it) {
         long long tw = M_T0();
-        mbar_wait(smem_u32(&sm->x_full), t_it & 1);   // LN(X) image of this tile is in tensor memory
+        mbar_wait_cluster(smem_u32(&sm->x_full), t_it & 1);   // LN(X) images of both tiles are in tensor memory
         M_ACC(w_x, tw);
         tc_fence_after();
+        auto wait_b = [&](int b_slot) {
+          long long tb = M_T0();
+          mbar_wait(smem_u32(&sm->b_full[b_slot]), (b_it / p.nb) & 1);
+          mbar_wait_cluster(smem_u32(&sm->b_peer[b_slot]), (b_it / p.nb) & 1);
+          M_ACC(w_b, tb);
+        };
         auto fc1 = [&](int j) {
           const int buf = c1_it & 1;
           const int ncols = min(128, p.Np1 - j * 128);
-          const uint32_t idesc = make_idesc(ncols);
+          const uint32_t idesc = make_idesc2(ncols);
           const uint32_t d_addr = tmem_base + buf * 128;
           for (int s = 0; s < Ks1; ++s) {
             const int b_slot = b_it % p.nb;
-            long long tb = M_T0();
-            mbar_wait(smem_u32(&sm->b_full[b_slot]), (b_it / p.nb) & 1);
-            M_ACC(w_b, tb);
+            wait_b(b_slot);
             tc_fence_after();
             const uint32_t b_addr = smem_u32(b_ring + (size_t)b_slot * b_slot_bytes);
-            const uint64_t bh0 = make_desc(b_addr), bl0 = make_desc(b_addr + M_SLAB);
+            const uint64_t bh0 = make_desc(b_addr), bl0 = make_desc(b_addr + M_SLAB / 2);
             if (elect_one()) {
               if (!no_mma) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   const uint32_t kk = 8 * (s * 4 + k);
-                  umma_bf16_tmem_a(d_addr, xh + kk, bh0 + 2 * k, idesc, (s | k) != 0);
+                  umma2_bf16_tmem_a(d_addr, xh + kk, bh0 + 2 * k, idesc, (s | k) != 0);
                   if (parts == 2) {
-                    umma_bf16_tmem_a(d_addr, xh + kk, bl0 + 2 * k, idesc, 1);
-                    umma_bf16_tmem_a(d_addr, xl + kk, bh0 + 2 * k, idesc, 1);
+                    umma2_bf16_tmem_a(d_addr, xh + kk, bl0 + 2 * k, idesc, 1);
+                    umma2_bf16_tmem_a(d_addr, xl + kk, bh0 + 2 * k, idesc, 1);
                   }
                 }
               }
-              umma_commit(smem_u32(&sm->b_empty[b_slot]));
+              umma2_commit(smem_u32(&sm->b_empty[b_slot]));
             }
             __syncwarp();
             ++b_it;
           }
           if (elect_one()) {
-            umma_commit(smem_u32(&sm->acc1_full[buf]));
-            if (j == NJ - 1) umma_commit(smem_u32(&sm->x_empty));  // last reader of this tile's X image
+            umma2_commit(smem_u32(&sm->acc1_full[buf]));
+            if (j == NJ - 1) umma2_commit(smem_u32(&sm->x_empty));  // last reader of this pair's X images
           }
           __syncwarp();
           ++c1_it;
@@ -234,38 +283,36 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
           const uint32_t hit = c1_base + j;
           const int hb = hit & 1;
           tw = M_T0();
-          mbar_wait(smem_u32(&sm->h_full[hb]), (hit >> 1) & 1);
+          mbar_wait_cluster(smem_u32(&sm->h_full[hb]), (hit >> 1) & 1);
           M_ACC(w_h, tw);
           const int b_slot = b_it % p.nb;
+          wait_b(b_slot);
           tw = M_T0();
-          mbar_wait(smem_u32(&sm->b_full[b_slot]), (b_it / p.nb) & 1);
-          M_ACC(w_b, tw);
-          tw = M_T0();
-          if (j == 0) mbar_wait(smem_u32(&sm->acc2_empty), (t_it & 1) ^ 1);
+          if (j == 0) mbar_wait_cluster(smem_u32(&sm->acc2_empty), (t_it & 1) ^ 1);
           M_ACC(w_acc2, tw);
           tc_fence_after();
           const uint32_t b_addr = smem_u32(b_ring + (size_t)b_slot * b_slot_bytes);
-          const uint32_t idesc = make_idesc(C);
+          const uint32_t idesc = make_idesc2(C);
           const uint32_t d_addr = tmem_base + ACC2_COL;
-          const uint64_t bh0 = make_desc(b_addr), bl0 = make_desc(b_addr + M_SLAB);
+          const uint64_t bh0 = make_desc(b_addr), bl0 = make_desc(b_addr + M_SLAB / 2);
           const uint32_t th0 = tmem_base + hb * 128;   // H_j: k-step k at columns 32 k (hi) / 32 k + 8 (lo) of acc1[hb]
           if (elect_one()) {
             if (!no_mma) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                umma_bf16_tmem_a(d_addr, th0 + 32 * k, bh0 + 2 * k, idesc, (j | k) != 0);
+                umma2_bf16_tmem_a(d_addr, th0 + 32 * k, bh0 + 2 * k, idesc, (j | k) != 0);
                 if (parts == 2) {
-                  umma_bf16_tmem_a(d_addr, th0 + 32 * k, bl0 + 2 * k, idesc, 1);
-                  umma_bf16_tmem_a(d_addr, th0 + 32 * k + 8, bh0 + 2 * k, idesc, 1);
+                  umma2_bf16_tmem_a(d_addr, th0 + 32 * k, bl0 + 2 * k, idesc, 1);
+                  umma2_bf16_tmem_a(d_addr, th0 + 32 * k + 8, bh0 + 2 * k, idesc, 1);
                 }
               }
             }
-            umma_commit(smem_u32(&sm->b_empty[b_slot]));
+            umma2_commit(smem_u32(&sm->b_empty[b_slot]));
           }
           __syncwarp();
           ++b_it;
         }
-        if (elect_one()) umma_commit(smem_u32(&sm->acc2_full));
+        if (elect_one()) umma2_commit(smem_u32(&sm->acc2_full));
         __syncwarp();
       }
       if (p.dbg && lane == 0) {
@@ -273,51 +320,45 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
         d[0] = clock64() - t_all; d[1] = 0; d[2] = w_x; d[3] = w_b; d[4] = w_h; d[5] = w_acc2;
       }
     }
-  } else if (warp < 10) {
-    // =============================== GLU (warps 2..9): acc1 -> H, in place ======================
+  } else if (warp < 18) {
+    // =============================== GLU (warps 2..17): acc1 -> H, in place =====================
+    // one item (TMEM lane quadrant x 32-column group) per warp and chunk: four GLU warps per scheduler hide each other's
+    // tcgen05.ld / st latencies
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int grp = (warp - 2) >> 2;
     uint32_t c1_it = 0;
     long long g_wait = 0, g_all = M_T0();
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    long long g_prof[3] = {0, 0, 0};
+    for (int pr = pair0; pr < num_pairs; pr += npairs) {
       for (int j = 0; j < NJ; ++j, ++c1_it) {
         const int buf = c1_it & 1;
-        float bias_lane[2];
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int n = j * 128 + (half + 2 * g) * 32 + lane;
-          bias_lane[g] = n < p.N1 ? __ldg(p.b1 + n) : 0.f;
-        }
+        const int n0 = j * 128 + grp * 32;
         long long tg = M_T0();
         mbar_wait(smem_u32(&sm->acc1_full[buf]), (c1_it >> 1) & 1);
         M_ACC(g_wait, tg);
         tc_fence_after();
-        if (!(p.dbg_flags & 64)) {
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int i = half + 2 * g;
-            glu_item(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128 + i * 32, bias_lane[g], j * 128 + i * 32 < p.N1, parts);
-          }
-        }
+        if (!(p.dbg_flags & 64))
+          glu_item(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128 + grp * 32, n0 < p.N1 ? p.b1 + n0 : nullptr, parts, p.dbg ? g_prof : nullptr);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&sm->h_full[buf]));
+        if (lane == 0) mbar_arrive_remote_relaxed(L_h_full[buf]);
         __syncwarp();
       }
     }
     if (p.dbg && warp == 2 && lane == 0) {
       long long* d = p.dbg + blockIdx.x * 16;
-      d[6] = clock64() - g_all; d[7] = g_wait;
+      d[6] = clock64() - g_all; d[7] = g_wait; d[13] = g_prof[0]; d[14] = g_prof[1]; d[15] = g_prof[2];
     }
-  } else if (warp < 14) {
-    // =============================== converters (warps 10..13): LN + split -> tensor memory =====
+  } else if (warp < 22) {
+    // =============================== converters (warps 18..21): LN + split -> tensor memory =====
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int swz = row & 7;
     uint32_t l_it = 0, t_it = 0;
     long long c_wait = 0, c_all = M_T0();
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_it) {
+    for (int pr = pair0; pr < num_pairs; pr += npairs, ++t_it) {
+      const int tile = 2 * pr + (int)crank; (void)tile;
       // pass 1: row statistics, as soon as the slabs land
       float s1 = 0.f, s2 = 0.f;
       for (int s = 0; s < Ks1; ++s) {
@@ -399,15 +440,15 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&sm->x_full));
+      if (lane == 0) mbar_arrive_remote_relaxed(L_x_full);
       __syncwarp();
     }
-    if (p.dbg && warp == 10 && lane == 0) {
+    if (p.dbg && warp == 18 && lane == 0) {
       long long* d = p.dbg + blockIdx.x * 16;
       d[11] = clock64() - c_all; d[12] = c_wait;
     }
-  } else if (warp < 18) {
-    // =============================== final epilogue (warps 14..17) ==============================
+  } else if (warp < 26) {
+    // =============================== final epilogue (warps 22..25) ==============================
     // The residual tile X[tile] was fetched a second time (an L2 hit) into `resbuf` by TMA while the tile's chunks ran;
     // lane = row combines  x + s * (acc2 + b2) [+ res2]  IN PLACE in the swizzled boxes (conflict-free row-per-lane
     // accesses) and the boxes leave by TMA stores: no global-memory latency anywhere in this role, and acc2 is free again
@@ -417,7 +458,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
     const int swz = row & 7;
     uint32_t t_it = 0;
     long long e_wait = 0, e_ld = 0, e_st = 0, e_pf = 0, e_all = M_T0();
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_it) {
+    for (int pr = pair0; pr < num_pairs; pr += npairs, ++t_it) {
+      const int tile = 2 * pr + (int)crank; (void)tile;
       const int m = tile * 128 + row;
       long long te = M_T0();
       mbar_wait(smem_u32(&sm->res_full), t_it & 1);
@@ -432,7 +474,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
         if (c0 + 32 >= C) {   // acc2 is in registers from here on: fc2 of the next tile may overwrite it
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&sm->acc2_empty));
+          if (lane == 0) mbar_arrive_remote_relaxed(L_acc2_empty);
           __syncwarp();
         }
         uint8_t* box = resbuf + (size_t)(c0 >> 5) * (M_LAND / 2) + row * 128;
@@ -457,7 +499,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
       if (p.dbg_flags & 128) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&sm->acc2_empty));
+        if (lane == 0) mbar_arrive_remote_relaxed(L_acc2_empty);
       }
       t1 = M_T0();
       fence_proxy_async();
@@ -474,15 +516,16 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA exits
     (void)e_pf;
-    if (p.dbg && warp == 14 && lane == 0) {
+    if (p.dbg && warp == 22 && lane == 0) {
       long long* d = p.dbg + blockIdx.x * 16;
-      d[8] = clock64() - e_all; d[9] = e_wait; d[10] = e_ld; d[13] = e_st; d[14] = e_pf;
+      d[8] = clock64() - e_all; d[9] = e_wait; d[10] = e_ld;
     }
   } else {
     // =============================== X loader (TMA) ============================================
     if (lane == 0) {          // landing slots: the operand of fc1
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int pr = pair0; pr < num_pairs; pr += npairs) {
+      const int tile = 2 * pr + (int)crank; (void)tile;
         for (int s = 0; s < Ks1; ++s, ++it) {
           const int st = it % M_NL;
           mbar_wait(smem_u32(&sm->land_empty[st]), ((it / M_NL) & 1) ^ 1);
@@ -497,7 +540,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
       }
     } else if (lane == 1) {   // the same rows again, as the residual the final epilogue combines in place (an L2 hit)
       uint32_t t_it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_it) {
+      for (int pr = pair0; pr < num_pairs; pr += npairs, ++t_it) {
+      const int tile = 2 * pr + (int)crank; (void)tile;
         mbar_wait(smem_u32(&sm->res_empty), (t_it & 1) ^ 1);
         const uint32_t full = smem_u32(&sm->res_full);
         mbar_expect_tx(full, (p.dbg_flags & 256) ? 0 : (uint32_t)(C / 32) * (M_LAND / 2));
@@ -509,10 +553,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tc_kernel(const __grid_con
   }
 
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();   // the leader's MMAs read the peer's shared / tensor memory: neither CTA leaves early
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc2(tmem_base, 512);
   }
 }
 
@@ -562,7 +606,7 @@ extern "C" int mphsir_mlp_fwd(const mphsir_mlp_params* q, void* stream) {
   a.parts = q->precision == MPHSIR_PREC_BF16X3 ? 2 : 1;
   // shared memory (225 KB at C = 128): 1 KB barriers + 2 landing slots x 32 KB + residual tile C/32 x 16 KB + weight ring
   //   bf16x3: 3 (C = 128) / 4 slots x 32 KB (hi + lo),  bf16: 6 / 8 slots x 16 KB
-  a.nb = (a.parts == 2 ? 3 : 6) + (q->C == 64 ? (a.parts == 2 ? 1 : 2) : 0);
+  a.nb = 6;   // weight ring: 6 slots x (64 rows x 128 B) x parts — each CTA of the pair stages half of every block
   a.num_tiles = (q->M + 127) / 128;
   PFN_cuTensorMapEncodeTiled enc = tc::mlp_encode_fn();
   MPHSIR_REQUIRE(enc != nullptr, "mlp: cuTensorMapEncodeTiled unavailable");
@@ -592,18 +636,23 @@ extern "C" int mphsir_mlp_fwd(const mphsir_mlp_params* q, void* stream) {
   MPHSIR_REQUIRE(enc(&a.tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, q->Y, ydim, ystr, ybox, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS, "mlp: output tensor map encode failed");
-  const size_t smem = 1024 + (size_t)tc::M_NL * tc::M_LAND + (size_t)(q->C / 32) * (tc::M_LAND / 2) + (size_t)a.nb * tc::M_SLAB * a.parts;
-  const int grid = a.num_tiles < sm_count ? a.num_tiles : sm_count;
+  const size_t smem = 1024 + (size_t)tc::M_NL * tc::M_LAND + (size_t)(q->C / 32) * (tc::M_LAND / 2) + (size_t)a.nb * (tc::M_SLAB / 2) * a.parts;
+  const int pairs = (a.num_tiles + 1) / 2;
+  const int grid = 2 * (pairs < sm_count / 2 ? pairs : sm_count / 2);   // CTA pairs (clusters of 2 on one TPC)
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(tc::kMlpThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = reinterpret_cast<cudaStream_t>(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = tc::pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = tc::pdl_enabled() ? 2 : 1;
   cudaError_t le = cudaLaunchKernelEx(&cfg, tc::mlp_tc_kernel, a);
   if (le != cudaSuccess) {
     set_error("mlp(tc): cudaLaunchKernelEx failed: %s", cudaGetErrorString(le));

@@ -31,6 +31,6 @@ for C, hid in ((128, 340),):
         dbg = torch.zeros(148, 16, dtype=torch.int64, device=dev)
         lib.load().mphsir_debug_mlp_counters(dbg.data_ptr()); run(); torch.cuda.synchronize(); lib.load().mphsir_debug_mlp_counters(None)
         d = dbg.double().mean(0).tolist()
-        names = ["MMA.total", "-", "MMA.w_x", "MMA.w_b", "MMA.w_h", "MMA.w_acc2", "GLU.total", "GLU.w_acc1", "EPI.total", "EPI.w_acc2", "EPI.tmem_ld", "CVT.total", "CVT.w_x_empty", "EPI.store", "EPI.prefetch"]
+        names = ["MMA.total", "-", "MMA.w_x", "MMA.w_b", "MMA.w_h", "MMA.w_acc2", "GLU.total", "GLU.w_acc1", "EPI.total", "EPI.w_acc2", "EPI.tmem_ld", "CVT.total", "CVT.w_x_empty", "GLU.ld", "GLU.math", "GLU.st"]
         print(f"flags={fl} C={C} hid={hid} {pn}: {ms*1e3:.1f} us  {2.0*M*C*3*hp/ms/1e9:.1f} TF  {12.0*M*C/ms/1e6:.0f} GB/s")
         print("     " + "  ".join(f"{n}={v/1e3:.0f}k" for n, v in zip(names, d)))
