@@ -53,6 +53,7 @@ struct Smem {
   // barriers first (8-byte aligned), rings after (1024-byte aligned, carved dynamically)
   uint64_t a_full[MAX_RING], a_empty[MAX_RING], b_full[MAX_RING], b_empty[MAX_RING];
   uint64_t acc_full[2], acc_empty[2];
+  uint64_t a_peer[MAX_RING], b_peer[MAX_RING];  // CTA pairs: the peer CTA's slab / half weight block is ready (leader side)
   uint64_t stage_full[MAX_RING];  // TMA landed the fp32 slab (a_full: converted to bf16; a_empty: MMAs done)
   uint64_t res_full[2 * 8];       // tepi: residual box landed in slot k of epilogue warp w (index 2*w + k)
   uint32_t tmem_base;
@@ -80,7 +81,7 @@ __device__ __forceinline__ void tile_rows(const TcArgs& p, int tile, int& m0, in
 // ------------------------------------------------------------------------------------------------
 template <int EPI>
 __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t* eslots, uint32_t tmem_base, int num_tiles,
-                                             int npass, int warp, int lane) {
+                                             int npass, int warp, int lane, int crank) {
   constexpr bool RES = EPI == MPHSIR_EPI_RESIDUAL, PROJ = EPI == MPHSIR_EPI_PROJ;
   const int quad = warp & 3, half = (warp - 2) >> 2, ew = warp - 2;
   // p.ebox boxes of 4 KB per warp: 2 (default), or 1 for BIAS epilogues of K > 64 GEMMs — the 32 KB saved buy a fourth
@@ -103,7 +104,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t*
         pass = 0;
         tile += gridDim.x;
         ++tit;
-        if (tit >= p.iters || tile >= num_tiles) return false;
+        if (tit >= p.iters || tile - crank >= num_tiles) return false;
       }
     }
   };
@@ -127,11 +128,11 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t*
   uint32_t ck = 0;  // chunks processed by this warp (slot = ck & 1)
   {
     int t = blockIdx.x, ti = 0, ps = 0, c = half * 32 - 64;
-    if (num_tiles > (int)blockIdx.x && p.iters > 0 && advance(t, ti, ps, c) && needs_res(ps, c) && lane == 0) issue_res(t, ps, c, 0);
+    if (num_tiles > (int)blockIdx.x - crank && p.iters > 0 && advance(t, ti, ps, c) && needs_res(ps, c) && lane == 0) issue_res(t, ps, c, 0);
   }
   uint32_t acc_it = 0;
   long long t_wait = 0, t_tmem = 0, t_all0 = TC_T0();
-  for (int tile = blockIdx.x, tit = 0; tit < p.iters && tile < num_tiles; tile += gridDim.x, ++tit) {
+  for (int tile = blockIdx.x, tit = 0; tit < p.iters && tile - crank < num_tiles; tile += gridDim.x, ++tit) {
     int m0, m_end;
     tile_rows(p, tile, m0, m_end);
     const int mm = min(m0 + quad * 32 + lane, m_end - 1);  // this thread's row (clamped: tails are clipped by TMA)
@@ -226,7 +227,10 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t*
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[buf]));
+      if (lane == 0) {
+        if (p.cluster > 1) mbar_arrive_remote_relaxed(mapa_cluster(smem_u32(&sm->acc_empty[buf]), 0));   // TMEM hand-off to the leader's MMA warp
+        else mbar_arrive(smem_u32(&sm->acc_empty[buf]));
+      }
     }
   }
   if (lane == 0) bulk_wait_group_read<0>();  // shared memory stays allocated until the last store has read its box
@@ -237,7 +241,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t*
   }
 }
 
-template <int EPI, bool LN>
+template <int EPI, bool LN, int CG>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcArgs p) {
   constexpr bool CONV = EPI >= TC_OUT_TOKENS;
   // NCHW / pixel-unshuffle stores are already coalesced (or hopeless) in the row-per-thread TMEM mapping
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   Smem* sm = reinterpret_cast<Smem*>(smem_raw);
   const int parts = p.parts;                       // 1 (bf16x1) or 2 (bf16x3)
   const int a_slot_bytes = STAGE_BYTES;
-  const int b_slot_bytes = BBLK_BYTES * parts;
+  const int b_slot_bytes = (BBLK_BYTES / p.cluster) * parts;
   uint8_t* a_ring = smem_raw + 1024;
   uint8_t* b_ring = a_ring + (size_t)p.na * a_slot_bytes;
   float* staging = reinterpret_cast<float*>(b_ring + (size_t)p.nb * b_slot_bytes);
@@ -264,26 +268,34 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       mbar_init(smem_u32(&sm->a_full[i]), kConvThreads / 32);
       mbar_init(smem_u32(&sm->a_empty[i]), 1);
       mbar_init(smem_u32(&sm->b_full[i]), 1);
-      mbar_init(smem_u32(&sm->b_empty[i]), p.cluster);  // every CTA of the cluster must have consumed the block
+      mbar_init(smem_u32(&sm->b_empty[i]), 1);
+      mbar_init(smem_u32(&sm->a_peer[i]), 1);
+      mbar_init(smem_u32(&sm->b_peer[i]), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&sm->acc_full[i]), 1);
-      mbar_init(smem_u32(&sm->acc_empty[i]), kEpiWarps);
+      mbar_init(smem_u32(&sm->acc_empty[i]), kEpiWarps * p.cluster);  // CTA pairs: both CTAs' epilogue warps arrive at the leader
     }
     for (int i = 0; i < MAX_RING; ++i) mbar_init(smem_u32(&sm->stage_full[i]), 1);
     for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(smem_u32(&sm->res_full[i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(&sm->tmem_base), 512);
-  tc_fence_before();
-  __syncthreads();
-  if (p.cluster > 1) cluster_sync_all();  // the peer's mbarriers exist before any multicast copy / commit targets them
+  if (CG == 2) {
+    cluster_sync_all();  // the peer's mbarriers exist before a remote arrive / multicast commit targets them
+    if (warp == 1) tmem_alloc2(smem_u32(&sm->tmem_base), 512);
+    tc_fence_before();
+    cluster_sync_all();
+  } else {
+    if (warp == 1) tmem_alloc(smem_u32(&sm->tmem_base), 512);
+    tc_fence_before();
+    __syncthreads();
+  }
   tc_fence_after();
   pdl_wait();  // everything above overlapped the predecessor's tail; from here on its results are read / its inputs overwritten
   const uint32_t tmem_base = sm->tmem_base;
   const int num_tiles = p.num_tiles;
-  const uint32_t crank = p.cluster > 1 ? cluster_ctarank() : 0;
-  const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
+  const uint32_t crank = CG == 2 ? cluster_ctarank() : 0;
+  constexpr bool pair = CG == 2;   // CTA pair: M = 256 MMAs (cta_group::2) issued by the leader (rank 0) for both tiles
 
   if (warp == 0) {
     // =============================== B loader ===============================================
@@ -291,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       uint32_t it = 0;
       long long t_wait = 0, t_all0 = TC_T0();
       for (int tile = blockIdx.x, tit = 0; tit < p.iters; tile += gridDim.x, ++tit) {
-      if (tile >= num_tiles && p.cluster == 1) break;  // clustered CTAs run dummy tiles to stay in lock-step
+      if (tile - (int)crank >= num_tiles) break;  // a pair stops together; the peer may run ONE all-out-of-bounds tile (odd tile count)
         const uint8_t* bimg = reinterpret_cast<const uint8_t*>(p.Bimg);
         if (p.tiles_per_batch > 0) bimg += (size_t)(tile / p.tiles_per_batch) * p.b_batch_bytes;
         for (int pass = 0; pass < npass; ++pass) {
@@ -301,24 +313,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               const long long tw = TC_T0();
               mbar_wait(smem_u32(&sm->b_empty[slot]), ((it / p.nb) & 1) ^ 1);
               TC_ACC(t_wait, tw);
-              const int rows = min(BN, p.Np - j * BN);
+              // a CTA pair stages HALF of the block's rows (= of the MMA's N) per CTA
+              const int rows = min(BN, p.Np - j * BN) / p.cluster;
               const uint32_t bytes = rows * 128;
               const uint32_t full = smem_u32(&sm->b_full[slot]);
               if (elect_one()) {
-              mbar_expect_tx(full, bytes * parts);
-              if (p.cluster == 1) {
+                mbar_expect_tx(full, bytes * parts);
                 for (int part = 0; part < parts; ++part) {
-                  const uint8_t* src = bimg + ((size_t)(part * Ks + s) * p.Np + j * BN) * 128;
-                  bulk_g2s(smem_u32(b_ring + (size_t)slot * b_slot_bytes + part * BBLK_BYTES), src, bytes, full);
+                  const uint8_t* src = bimg + ((size_t)(part * Ks + s) * p.Np + j * BN + crank * rows) * 128;
+                  bulk_g2s(smem_u32(b_ring + (size_t)slot * b_slot_bytes + part * (BBLK_BYTES / p.cluster)), src, bytes, full);
                 }
-              } else {
-                // each CTA of the pair fetches half of the rows and multicasts them to both
-                const uint32_t half_bytes = bytes / 2, off = crank * half_bytes;
-                for (int part = 0; part < parts; ++part) {
-                  const uint8_t* src = bimg + ((size_t)(part * Ks + s) * p.Np + j * BN) * 128 + off;
-                  bulk_g2s_mcast(smem_u32(b_ring + (size_t)slot * b_slot_bytes + part * BBLK_BYTES + off), src, half_bytes, full, cmask);
-                }
-              }
               }
               __syncwarp();
             }
@@ -330,6 +334,35 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         p.dbg[blockIdx.x * 16 + 1] = t_wait;
       }
     }
+  } else if (CG == 2 && warp == 1 && crank != 0) {
+    // =============================== peer CTA of a pair: relay ==============================
+    // Only the leader issues MMAs.  This warp walks the leader's wait sequence on THIS CTA's barriers and forwards every
+    // completion (converted A slab, landed half weight block) to the leader's a_peer / b_peer barriers.  Relaxed arrives:
+    // the data stays in this CTA's shared memory and is read there by this SM's tensor core.
+    uint32_t a_it = 0, b_it = 0;
+    for (int tile = blockIdx.x, tit = 0; tit < p.iters; tile += gridDim.x, ++tit) {
+      if (tile - (int)crank >= num_tiles) break;
+      const uint32_t a_base = a_it;
+      for (int pass = 0; pass < npass; ++pass) {
+        for (int s = 0; s < Ks; ++s) {
+          if (!stationary || pass == 0) {
+            const uint32_t ai = stationary ? a_base + s : a_it;
+            const uint32_t a_slot = ai % p.na;
+            mbar_wait(smem_u32(&sm->a_full[a_slot]), (ai / p.na) & 1);
+            if (lane == 0) mbar_arrive_remote_relaxed(mapa_cluster(smem_u32(&sm->a_peer[a_slot]), 0));
+            __syncwarp();
+          }
+          for (int j = TPP * pass; j < min(NT, TPP * pass + TPP); ++j, ++b_it) {
+            const int b_slot = b_it % p.nb;
+            mbar_wait(smem_u32(&sm->b_full[b_slot]), (b_it / p.nb) & 1);
+            if (lane == 0) mbar_arrive_remote_relaxed(mapa_cluster(smem_u32(&sm->b_peer[b_slot]), 0));
+            __syncwarp();
+          }
+          if (!stationary) ++a_it;
+        }
+      }
+      if (stationary) a_it += Ks;
+    }
   } else if (warp == 1) {
     // =============================== MMA issuer =============================================
     // The whole warp walks the loop nest (waits are warp-uniform); one elected lane issues the MMAs and commits.
@@ -337,12 +370,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       uint32_t a_it = 0, b_it = 0, acc_it = 0;
       long long t_acc = 0, t_a = 0, t_b = 0, t_issue = 0, t_commit = 0, t_all0 = TC_T0();
       for (int tile = blockIdx.x, tit = 0; tit < p.iters; tile += gridDim.x, ++tit) {
-      if (tile >= num_tiles && p.cluster == 1) break;  // clustered CTAs run dummy tiles to stay in lock-step
+      if (tile - (int)crank >= num_tiles) break;  // a pair stops together; the peer may run ONE all-out-of-bounds tile (odd tile count)
         const uint32_t a_base = a_it;
         for (int pass = 0; pass < npass; ++pass, ++acc_it) {
           const int buf = acc_it & 1;
           long long tw = TC_T0();
-          mbar_wait(smem_u32(&sm->acc_empty[buf]), ((acc_it >> 1) & 1) ^ 1);
+          if (pair) mbar_wait_cluster(smem_u32(&sm->acc_empty[buf]), ((acc_it >> 1) & 1) ^ 1);
+          else mbar_wait(smem_u32(&sm->acc_empty[buf]), ((acc_it >> 1) & 1) ^ 1);
           TC_ACC(t_acc, tw);
           tc_fence_after();
           for (int s = 0; s < Ks; ++s) {
@@ -350,10 +384,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             tw = TC_T0();
             if (stationary) {
               a_slot = (a_base + s) % p.na;
-              if (pass == 0) mbar_wait(smem_u32(&sm->a_full[a_slot]), ((a_base + s) / p.na) & 1);
+              if (pass == 0) {
+                mbar_wait(smem_u32(&sm->a_full[a_slot]), ((a_base + s) / p.na) & 1);
+                if (pair) mbar_wait_cluster(smem_u32(&sm->a_peer[a_slot]), ((a_base + s) / p.na) & 1);
+              }
             } else {
               a_slot = a_it % p.na;
               mbar_wait(smem_u32(&sm->a_full[a_slot]), (a_it / p.na) & 1);
+              if (pair) mbar_wait_cluster(smem_u32(&sm->a_peer[a_slot]), (a_it / p.na) & 1);
             }
             TC_ACC(t_a, tw);
             tc_fence_after();
@@ -362,37 +400,55 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               const int b_slot = b_it % p.nb;
               tw = TC_T0();
               mbar_wait(smem_u32(&sm->b_full[b_slot]), (b_it / p.nb) & 1);
+              if (pair) mbar_wait_cluster(smem_u32(&sm->b_peer[b_slot]), (b_it / p.nb) & 1);
               TC_ACC(t_b, tw);
               tc_fence_after();
               const uint32_t b_addr = smem_u32(b_ring + (size_t)b_slot * b_slot_bytes);
               const int ncols = min(BN, p.Np - j * BN);
-              const uint32_t idesc = make_idesc(ncols);
+              const uint32_t idesc = pair ? make_idesc2(ncols) : make_idesc(ncols);
               const uint32_t d_addr = tmem_base + buf * PASS_COLS + (j - TPP * pass) * BN;
               tw = TC_T0();
               // descriptors of consecutive k16 steps differ by 32 bytes (+2 in the 16-byte address field)
               const uint64_t ah0 = make_desc(a_addr), bh0 = make_desc(b_addr);
-              const uint64_t al0 = make_desc(a_addr + SLAB_BYTES), bl0 = make_desc(b_addr + BBLK_BYTES);
+              const uint64_t al0 = make_desc(a_addr + SLAB_BYTES), bl0 = make_desc(b_addr + BBLK_BYTES / p.cluster);
               if (elect_one()) {
+                if (pair) {   // M = 256 over both CTAs (109 clk per instruction against 121 clk per M = 128: tools/mma_rate.cu)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  umma_bf16(d_addr, ah0 + 2 * k, bh0 + 2 * k, idesc, (s | k) != 0);
-                  if (parts == 2) {
-                    umma_bf16(d_addr, ah0 + 2 * k, bl0 + 2 * k, idesc, 1);
-                    umma_bf16(d_addr, al0 + 2 * k, bh0 + 2 * k, idesc, 1);
+                  for (int k = 0; k < 4; ++k) {
+                    umma2_bf16(d_addr, ah0 + 2 * k, bh0 + 2 * k, idesc, (s | k) != 0);
+                    if (parts == 2) {
+                      umma2_bf16(d_addr, ah0 + 2 * k, bl0 + 2 * k, idesc, 1);
+                      umma2_bf16(d_addr, al0 + 2 * k, bh0 + 2 * k, idesc, 1);
+                    }
                   }
+                  umma2_commit(smem_u32(&sm->b_empty[b_slot]));
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    umma_bf16(d_addr, ah0 + 2 * k, bh0 + 2 * k, idesc, (s | k) != 0);
+                    if (parts == 2) {
+                      umma_bf16(d_addr, ah0 + 2 * k, bl0 + 2 * k, idesc, 1);
+                      umma_bf16(d_addr, al0 + 2 * k, bh0 + 2 * k, idesc, 1);
+                    }
+                  }
+                  umma_commit(smem_u32(&sm->b_empty[b_slot]));
                 }
-                if (p.cluster == 1) umma_commit(smem_u32(&sm->b_empty[b_slot]));
-                else umma_commit_mcast(smem_u32(&sm->b_empty[b_slot]), cmask);
               }
               __syncwarp();
               TC_ACC(t_issue, tw);
             }
             const bool last_use = stationary ? (pass == npass - 1) : true;
-            if (last_use && elect_one()) umma_commit(smem_u32(&sm->a_empty[a_slot]));
+            if (last_use && elect_one()) {
+              if (pair) umma2_commit(smem_u32(&sm->a_empty[a_slot]));
+              else umma_commit(smem_u32(&sm->a_empty[a_slot]));
+            }
             __syncwarp();
             if (!stationary) ++a_it;
           }
-          if (elect_one()) umma_commit(smem_u32(&sm->acc_full[buf]));
+          if (elect_one()) {
+            if (pair) umma2_commit(smem_u32(&sm->acc_full[buf]));
+            else umma_commit(smem_u32(&sm->acc_full[buf]));
+          }
           __syncwarp();
         }
         if (stationary) a_it += Ks;
@@ -413,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // registers in a (4 rows x 8 float4) mapping, so every global access is a full 128-byte line segment.
     constexpr bool TEPI_OK = (EPI == MPHSIR_EPI_BIAS || EPI == MPHSIR_EPI_RESIDUAL || EPI == MPHSIR_EPI_PROJ);
     if (TEPI_OK && p.tepi) {
-      epilogue_tma<EPI>(p, sm, reinterpret_cast<uint8_t*>(staging), tmem_base, num_tiles, npass, warp, lane);
+      epilogue_tma<EPI>(p, sm, reinterpret_cast<uint8_t*>(staging), tmem_base, num_tiles, npass, warp, lane, (int)crank);
     } else {
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
@@ -422,7 +478,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     uint32_t acc_it = 0;
     long long t_wait = 0, t_tmem = 0, t_all0 = TC_T0();
     for (int tile = blockIdx.x, tit = 0; tit < p.iters; tile += gridDim.x, ++tit) {
-      if (tile >= num_tiles && p.cluster == 1) break;  // clustered CTAs run dummy tiles to stay in lock-step
+      if (tile - (int)crank >= num_tiles) break;  // a pair stops together; the peer may run ONE all-out-of-bounds tile (odd tile count)
       int m0, m_end;
       tile_rows(p, tile, m0, m_end);
       const int mrow0 = m0 + quad * 32;
@@ -599,7 +655,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[buf]));
+        if (lane == 0) {
+          if (pair) mbar_arrive_remote_relaxed(mapa_cluster(smem_u32(&sm->acc_empty[buf]), 0));
+          else mbar_arrive(smem_u32(&sm->acc_empty[buf]));
+        }
       }
     }
     if (p.dbg && warp == 2 && lane == 0) {
@@ -615,7 +674,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // so the memory-level parallelism lives in shared memory instead of registers.
     uint32_t st_it = 0;
     for (int tile = blockIdx.x, tit = 0; tit < p.iters; tile += gridDim.x, ++tit) {
-      if (tile >= num_tiles && p.cluster == 1) break;  // clustered CTAs run dummy tiles to stay in lock-step
+      if (tile - (int)crank >= num_tiles) break;  // a pair stops together; the peer may run ONE all-out-of-bounds tile (odd tile count)
       int m0, m_end;
       tile_rows(p, tile, m0, m_end);
       const int conv_passes = stationary ? 1 : npass;
@@ -731,7 +790,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     long long t_slot = 0, t_ld = 0, t_all0 = TC_T0();
     uint32_t a_it = 0;
     for (int tile = blockIdx.x, tit = 0; tit < p.iters; tile += gridDim.x, ++tit) {
-      if (tile >= num_tiles && p.cluster == 1) break;  // clustered CTAs run dummy tiles to stay in lock-step
+      if (tile - (int)crank >= num_tiles) break;  // a pair stops together; the peer may run ONE all-out-of-bounds tile (odd tile count)
       int m0, m_end;
       tile_rows(p, tile, m0, m_end);
       float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f};
@@ -889,10 +948,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   // teardown: everything issued has completed once the epilogue warps are done with the last tile
   tc_fence_before();
   __syncthreads();
-  if (p.cluster > 1) cluster_sync_all();  // no CTA exits while its peer may still multicast into it
+  if (CG == 2) cluster_sync_all();  // the leader's MMAs read the peer's shared / tensor memory: neither CTA leaves early
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (CG == 2) tmem_dealloc2(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -936,11 +996,11 @@ static size_t smem_bytes(int na, int nb, int parts, int tepi, int ebox) {
          (size_t)kEpiWarps * STG_FLOATS * sizeof(float) * (tepi ? ebox : 1);
 }
 
-template <int EPI, bool LN>
-static int launch_epi2(const TcArgs& a, size_t smem, int grid, cudaStream_t st) {
+template <int EPI, bool LN, int CG>
+static int launch_epi3(const TcArgs& a, size_t smem, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI, LN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return MPHSIR_ERR_CUDA;
@@ -961,12 +1021,18 @@ static int launch_epi2(const TcArgs& a, size_t smem, int grid, cudaStream_t st) 
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, LN>, a);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, LN, CG>, a);
   if (le != cudaSuccess) {
-    set_error("gemm(tc): cudaLaunchKernelEx failed: %s", cudaGetErrorString(le));
+    set_error("gemm(tc): cudaLaunchKernelEx failed: %s (grid %d, cluster %d, smem %zu, tiles %d, iters %d)", cudaGetErrorString(le), grid, a.cluster, smem, a.num_tiles, a.iters);
     return MPHSIR_ERR_CUDA;
   }
   return check_launch("gemm(tc)");
+}
+
+// a kernel that contains cta_group::2 instructions can only be launched in clusters of two: one instantiation per mode
+template <int EPI, bool LN>
+static int launch_epi2(const TcArgs& a, size_t smem, int grid, cudaStream_t st) {
+  return a.cluster == 2 ? launch_epi3<EPI, LN, 2>(a, smem, grid, st) : launch_epi3<EPI, LN, 1>(a, smem, grid, st);
 }
 
 template <int EPI>
@@ -1056,7 +1122,7 @@ static int g_tepi_enabled = 1;
 void set_tepi_enabled(int on) { g_tepi_enabled = on; }
 static int g_ebox1_enabled = 1;
 void set_ebox1_enabled(int on) { g_ebox1_enabled = on; }
-static int g_cluster_enabled = 0;  // measured: multicast halves L2 weight reads but the lock-step pairs cost ~4% in-network
+static int g_cluster_enabled = 1;  // CTA pairs: cta_group::2 MMAs (M = 256), half of every weight block per CTA
 void set_cluster_enabled(int on) { g_cluster_enabled = on; }
 void set_debug_buffer(long long* p) { g_dbg = p; }
 
@@ -1073,7 +1139,7 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
   //   bf16x3: A 3 x 32 KB + B 3 x 32 KB        bf16x1: A 4 x 32 KB + B 4 x 16 KB
   // TMA epilogue: plain GEMMs with a BIAS / RESIDUAL (single residual) / PROJ epilogue
   a.tepi = 0;
-  if (g_tepi_enabled && !conv && !g_cluster_enabled &&
+  if (g_tepi_enabled && !conv &&
       (a.epi == MPHSIR_EPI_BIAS || (a.epi == MPHSIR_EPI_RESIDUAL && a.res2 == nullptr) || a.epi == MPHSIR_EPI_PROJ)) {
     const bool per_sample = a.tiles_per_batch > 0;
     const int rpb = per_sample ? a.rows_per_batch : a.M, nb_ = per_sample ? a.M / a.rows_per_batch : 1;
@@ -1101,9 +1167,21 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
   }
   make_a_tensor_map(a, conv);
   // CTA pairs share every weight block (one L2 read, multicast into both CTAs) when the weights are not per-sample
-  a.cluster = (a.b_batch_bytes == 0 && a.num_tiles >= 2 && g_cluster_enabled) ? 2 : 1;
+  // CTA pairs run tiles (2 q, 2 q + 1) on one M = 256 instruction stream: both tiles must use the same weights
+  // (per-sample weights: an even number of tiles per sample)
+  // Measured (tools/gemm_bench.py, tools/shape_profile.py --no-pair): pairs pay when the tensor pipe bounds the tile — many
+  // weight blocks per A slab (wide 3x3 convs: -16 %, the K = 256 fc1: -3 %); the HBM-side GEMMs (K <= 128) lose 0-8 % to
+  // the lock-step of the two CTAs, so they stay single.
+  const int nt_blocks = (a.Np + BN - 1) / BN;
+  const bool tensor_heavy = nt_blocks >= 2 && a.ks * nt_blocks >= 16;
+  a.cluster = (g_cluster_enabled && tensor_heavy && a.num_tiles >= 2 && a.Np % 16 == 0 &&
+               (a.b_batch_bytes == 0 || a.tiles_per_batch % 2 == 0)) ? 2 : 1;
   int grid = a.num_tiles < sm_count ? a.num_tiles : sm_count;
-  if (a.cluster == 2) grid = (grid + 1) & ~1;
+  if (a.cluster == 2) {
+    grid = (grid + 1) & ~1;
+    if (grid > (sm_count & ~1)) grid = sm_count & ~1;
+    a.nb *= 2;   // half-size weight slots: twice the ring depth in the same shared memory
+  }
   a.iters = (a.num_tiles + grid - 1) / grid;
   if (conv && a.epi == MPHSIR_EPI_BIAS) a.epi = TC_OUT_TOKENS;
   switch (a.epi) {

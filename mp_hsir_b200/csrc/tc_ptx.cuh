@@ -257,6 +257,17 @@ __device__ __forceinline__ void umma2_bf16_tmem_a(uint32_t tmem_d, uint32_t a_ta
       "r"(a_taddr), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// both operands from shared memory (each CTA its own 128 rows of A and HALF of the N rows of B, at the same offsets)
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // completion of all prior MMAs of this thread -> one arrive on the mbarrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma2_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),

@@ -20,6 +20,8 @@ shapes = [  # name, K, N, epi, ln, extra
     ("proj64 K64 N64", 64, 64, lib.EPI_BIAS, False),
     ("qkv64  K64 N192 ln", 64, 192, lib.EPI_BIAS, True),
 ]
+if "--no-pair" in sys.argv:
+    lib.load().mphsir_debug_tc_cluster(0)
 if "--no-ebox1" in sys.argv:
     lib.load().mphsir_debug_tc_ebox1(0)
 for name, K, N, epi, ln in shapes:
