@@ -255,6 +255,9 @@ MPHSIR_API int mphsir_local_gate_fwd(const mphsir_local_gate_params* p, void* st
  * (128 prompt logits, then the r low-rank projections; one mphsir_gemm_fwd call) and this kernel finishes
  * :136-152 with one warp per window.  core_mean, promptT/b and downT/b of *p are ignored. */
 MPHSIR_API int mphsir_local_gate_tail_fwd(const float* logits, int ldl, const mphsir_local_gate_params* p, void* stream);
+/* One-launch form of the same chain (8-32 windows per CTA: fp32 register-tiled C-long products, then the r-sized remainder in
+ * the same warp); needs every field of *p like mphsir_local_gate_fwd, r a multiple of 4.  What the inference engine calls. */
+MPHSIR_API int mphsir_local_gate2_fwd(const mphsir_local_gate_params* p, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Depthwise 3x3 conv (zero pad 1, no bias) on token-major data, optional GDFN gate.

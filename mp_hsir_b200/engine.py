@@ -163,6 +163,7 @@ class Engine:
         self.fold_weights = True   # fp64 weight folds (proj into the gate / spectral-qkv matrices); the trainer turns it off
         self.fold_proj = True
         self.split_gate = True
+        self.fused_gate = True   # one-launch local gate (lib.local_gate2); False: GEMM + tail kernel (split_gate)
         self.packed: Optional[dict] = None
         self._versions = None
         self._graphs: Dict[tuple, tuple] = {}
@@ -482,6 +483,8 @@ class Engine:
         # local spectral gate (:132-152)
         if "gate_cat_w" not in w:
             pass  # un-folded weights (trainer): the gate is computed below from the window mean of sa
+        elif self.fused_gate and st.rank % 4 == 0:
+            lib.local_gate2(wmean, w["gate"], gate, B_, C, st.rank)
         elif self.split_gate and st.rank % 4 == 0:
             logits = ws.mat("gate_logits", B_, _ceil(PROMPT_LEN + st.rank, 16))
             self._gemm(View(wmean.data_ptr(), C, B_, C, wmean), w["gate_cat_w"], logits, PROMPT_LEN + st.rank, bias=w["gate_cat_b"])

@@ -125,6 +125,7 @@ SIGNATURES = {
     "mphsir_gram_reduce": (_I, [_VP, _I, _VP, _I, _I, _I, _VP]),
     "mphsir_local_gate_fwd": (_I, [C.POINTER(LocalGateParams), _VP]),
     "mphsir_local_gate_tail_fwd": (_I, [_VP, _I, C.POINTER(LocalGateParams), _VP]),
+    "mphsir_local_gate2_fwd": (_I, [C.POINTER(LocalGateParams), _VP]),
     "mphsir_dwconv3x3_fwd": (_I, [_VP, _I, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "mphsir_gram_partial_floats": (C.c_size_t, [_I, _I, _I, _I, C.POINTER(_I)]),
     "mphsir_gram_partial_fwd": (_I, [_VP, _I, _I, _VP, _I, _I, _VP, _I, _I, _I, _I, _VP]),
@@ -485,6 +486,17 @@ def local_gate(core_mean: torch.Tensor, w: dict, gate: torch.Tensor, B_: int, Cc
     p.gate, p.B_, p.C, p.r = gate.data_ptr(), B_, Cc, r
     _launch("local_gate_fwd", lambda: load().mphsir_local_gate_fwd(C.byref(p), stream_ptr()),
             lambda: (2.0 * B_ * (Cc * 128 + 2 * Cc * r + 128 * r), 8.0 * B_ * Cc, "local_gate"))
+
+
+def local_gate2(core_mean: torch.Tensor, w: dict, gate: torch.Tensor, B_: int, Cc: int, r: int) -> None:
+    """One-launch local spectral gate (net/MP_HSIR.py:132-152 on the window means; proj folded into promptT / downT)."""
+    p = LocalGateParams()
+    p.core_mean = core_mean.data_ptr()
+    for n in ("promptT", "promptb", "downT", "downb", "param", "qT", "kvT", "p2T", "p2b", "upT"):
+        setattr(p, n, w[n].data_ptr())
+    p.gate, p.B_, p.C, p.r = gate.data_ptr(), B_, Cc, r
+    _launch("local_gate2_fwd", lambda: load().mphsir_local_gate2_fwd(C.byref(p), stream_ptr()),
+            lambda: (2.0 * B_ * (Cc * 128 + 2 * Cc * r + 128 * r), 8.0 * B_ * Cc, "local_gate2"))
 
 
 def local_gate_tail(logits: View, w: dict, gate: torch.Tensor, B_: int, Cc: int, r: int) -> None:

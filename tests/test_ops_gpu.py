@@ -248,6 +248,18 @@ def test_local_gate(C, r):
     gate2 = torch.full((B_, C), float("nan"), device=DEV)
     lib.local_gate_tail(V(dev(logits)), w, gate2, B_, C, r)
     assert rel_err(gate2.cpu(), ref) < TOL
+    # one-launch form (32 windows per CTA): B_ = 37 leaves a partial CTA and a partial warp
+    if r % 4 == 0 and C % 32 == 0:
+        gate3 = torch.full((B_, C), float("nan"), device=DEV)
+        lib.local_gate2(dev(core_mean), w, gate3, B_, C, r)
+        assert rel_err(gate3.cpu(), ref) < TOL
+        # the launcher picks 1, 2 or 4 windows per warp from the window count: cover the other two variants as well
+        for nb in (2401, 4803):
+            cm = rnd(nb, C, seed=12)
+            refb = O.local_spectral_gate(cm @ pw.t() + pb, sd, pfx)
+            gb = torch.full((nb, C), float("nan"), device=DEV)
+            lib.local_gate2(dev(cm), w, gb, nb, C, r)
+            assert rel_err(gb.cpu(), refb) < TOL
 
 
 # ------------------------------------------------------------------------------------------------

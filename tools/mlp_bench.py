@@ -7,8 +7,9 @@ from mp_hsir_b200 import lib, engine as E
 from mp_hsir_b200.lib import View, Weight
 dev = "cuda"
 M = 262144
-FLAGS = [int(a) for a in sys.argv[1:]] or [0]
-for C, hid in ((128, 340),):
+FLAGS = [int(a) for a in sys.argv[1:] if a.isdigit()] or [0]
+PRECS = [(lib.PREC_BF16, "x1")] if "x1" in sys.argv else [(lib.PREC_BF16X3, "x3")]
+for C, hid in (((64, 170),) if "c64" in sys.argv else ((128, 340),)):
     hp = E._ceil(hid, 16)
     x = torch.randn(M, C, device=dev)
     w1 = torch.randn(2 * hp, C, device=dev) * C ** -0.5
@@ -18,7 +19,7 @@ for C, hid in ((128, 340),):
     b1, b2 = torch.randn(2 * hp, device=dev), torch.randn(C, device=dev)
     g, b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
     y = torch.empty(M, C, device=dev)
-    for prec, pn, fl in [(lib.PREC_BF16X3, "x3", f) for f in FLAGS]:
+    for prec, pn, fl in [(pr, pn_, f) for pr, pn_ in PRECS for f in FLAGS]:
         lib.load().mphsir_debug_mlp_flags(fl)
         run = lambda: lib.mlp(View.of(x), (g, b), W1, b1, W2, b2, View.of(y), hp, prec)
         for _ in range(3): run()

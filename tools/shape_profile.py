@@ -13,6 +13,9 @@ if "--no-pair" in sys.argv:
     sys.argv.remove("--no-pair")
     lib.load().mphsir_debug_tc_cluster(0)
 cfg, net = bench.build_net(model, dev)
+if "--no-split-gate" in sys.argv:
+    sys.argv.remove("--no-split-gate")
+    net.engine().split_gate = False
 if len(sys.argv) > 2:
     net.set_precision(sys.argv[2])
 x, _, tid = bench.make_input(shape, 0, workload)
