@@ -118,8 +118,9 @@ typedef struct {
 /* Debug: when buf != NULL every subsequent tensor-core GEMM launch writes per-CTA cycle counters of its
  * warp roles into buf[grid][16] (tools/gemm_bench.py --profile).  Pass NULL to switch it off. */
 MPHSIR_API void mphsir_debug_tc_counters(long long* buf);
-/* Debug: 0 disables the 2-CTA cluster / weight-multicast path of the tensor-core GEMM (default 1). */
+/* Debug: 0 disables the CTA-pair (cta_group::2) instantiation of the tensor-core GEMM (default 1: tensor-heavy shapes use it). */
 MPHSIR_API void mphsir_debug_tc_cluster(int enabled);
+MPHSIR_API void mphsir_debug_tc_psplit(int enabled);           /* 0: never hand the 256-column passes of a row tile to several CTAs (A/B switch; default 1: few-tile GEMMs do) */
 MPHSIR_API void mphsir_debug_tc_ebox1(int enabled);         /* 0: two store boxes per epilogue warp everywhere (default 1: one box + 4-slot A ring for BIAS GEMMs with 64 < K <= 128) */
 MPHSIR_API void mphsir_debug_pdl(int enabled);              /* 1: programmatic dependent launch of the persistent tcgen05 kernels (default 0: measured, no gain) */
 MPHSIR_API void mphsir_debug_tc_tma_epilogue(int enabled);  /* 0: register-staged GEMM epilogue everywhere (default 1: TMA boxes) */

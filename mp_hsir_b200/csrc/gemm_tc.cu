@@ -49,6 +49,13 @@ constexpr int MAX_RING = 8;
 #define TC_T0() (p.dbg ? clock64() : 0)
 #define TC_ACC(var, t0) do { if (p.dbg) var += clock64() - (t0); } while (0)
 
+// Work item `vt` of a launch = (row tile, range of 256-column passes [p0, p1)): vt = tile * psplit + group.
+#define TC_WORK_ITEM(vt)                                               \
+  const int tile = (vt) / p.psplit;                                    \
+  const int p0 = ((vt) - tile * p.psplit) * p.ppg;                     \
+  const int p1 = min(npass, p0 + p.ppg);                               \
+  (void)p0; (void)p1
+
 struct Smem {
   // barriers first (8-byte aligned), rings after (1024-byte aligned, carved dynamically)
   uint64_t a_full[MAX_RING], a_empty[MAX_RING], b_full[MAX_RING], b_empty[MAX_RING];
@@ -94,17 +101,18 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t*
 
   auto ncols_of = [&](int pass) { return min(PASS_COLS, p.Np - pass * PASS_COLS); };
   // next chunk of this warp after (tile, tit, pass, c0); false when the CTA's work is finished
-  auto advance = [&](int& tile, int& tit, int& pass, int& c0) -> bool {
+  auto p0_of = [&](int vt) { return (vt - (vt / p.psplit) * p.psplit) * p.ppg; };
+  auto advance = [&](int& vt, int& tit, int& pass, int& c0) -> bool {
     c0 += 64;
     for (;;) {
       if (c0 < ncols_of(pass)) return true;
       ++pass;
       c0 = half * 32;
-      if (pass >= npass) {
-        pass = 0;
-        tile += gridDim.x;
+      if (pass >= min(npass, p0_of(vt) + p.ppg)) {
+        vt += gridDim.x;
         ++tit;
-        if (tit >= p.iters || tile - crank >= num_tiles) return false;
+        if (tit >= p.iters || vt - crank >= num_tiles) return false;
+        pass = p0_of(vt);
       }
     }
   };
@@ -118,21 +126,22 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t*
       row0 = tile * 128 + quad * 32;
     }
   };
-  auto issue_res = [&](int tile, int pass, int c0, int slot) {  // lane 0 only
+  auto issue_res = [&](int vt, int pass, int c0, int slot) {  // lane 0 only
     int b, row0;
-    tile_coord(tile, b, row0);
+    tile_coord(vt / p.psplit, b, row0);
     mbar_expect_tx(rbar0 + 8 * slot, 4096);
     tma_load_3d(slot_a0 + 4096 * slot, &p.tmR, pass * PASS_COLS + c0, row0, b, rbar0 + 8 * slot);
   };
 
   uint32_t ck = 0;  // chunks processed by this warp (slot = ck & 1)
   {
-    int t = blockIdx.x, ti = 0, ps = 0, c = half * 32 - 64;
+    int t = blockIdx.x, ti = 0, ps = p0_of(blockIdx.x), c = half * 32 - 64;
     if (num_tiles > (int)blockIdx.x - crank && p.iters > 0 && advance(t, ti, ps, c) && needs_res(ps, c) && lane == 0) issue_res(t, ps, c, 0);
   }
   uint32_t acc_it = 0;
   long long t_wait = 0, t_tmem = 0, t_all0 = TC_T0();
-  for (int tile = blockIdx.x, tit = 0; tit < p.iters && tile - crank < num_tiles; tile += gridDim.x, ++tit) {
+  for (int vt = blockIdx.x, tit = 0; tit < p.iters && vt - crank < num_tiles; vt += gridDim.x, ++tit) {
+    TC_WORK_ITEM(vt);
     int m0, m_end;
     tile_rows(p, tile, m0, m_end);
     const int mm = min(m0 + quad * 32 + lane, m_end - 1);  // this thread's row (clamped: tails are clipped by TMA)
@@ -149,7 +158,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t*
     }
     int tb, trow0;
     tile_coord(tile, tb, trow0);
-    for (int pass = 0; pass < npass; ++pass, ++acc_it) {
+    for (int pass = p0; pass < p1; ++pass, ++acc_it) {
       const int buf = acc_it & 1;
       long long tw = TC_T0();
       mbar_wait(smem_u32(&sm->acc_full[buf]), (acc_it >> 1) & 1);
@@ -169,7 +178,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t*
         // still be reading.  Only when the next chunk needs its residual TMA-loaded into box s^1 must that store have
         // finished too — waiting for it unconditionally serialised every chunk behind the previous chunk's store.
         if (lane == 0) {
-          int t2 = tile, ti2 = tit, ps2 = pass, c2 = c0;
+          int t2 = vt, ti2 = tit, ps2 = pass, c2 = c0;
           const bool next_res = advance(t2, ti2, ps2, c2) && needs_res(ps2, c2);
           if (ck > 0) {
             if (next_res || p.ebox == 1) bulk_wait_group_read<0>();
@@ -293,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   tc_fence_after();
   pdl_wait();  // everything above overlapped the predecessor's tail; from here on its results are read / its inputs overwritten
   const uint32_t tmem_base = sm->tmem_base;
-  const int num_tiles = p.num_tiles;
+  const int num_tiles = p.num_tiles * p.psplit;   // work items (row tile x pass group)
   const uint32_t crank = CG == 2 ? cluster_ctarank() : 0;
   constexpr bool pair = CG == 2;   // CTA pair: M = 256 MMAs (cta_group::2) issued by the leader (rank 0) for both tiles
 
@@ -302,11 +311,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     {  // warp-uniform loop, one elected lane issues the bulk copies
       uint32_t it = 0;
       long long t_wait = 0, t_all0 = TC_T0();
-      for (int tile = blockIdx.x, tit = 0; tit < p.iters; tile += gridDim.x, ++tit) {
-      if (tile - (int)crank >= num_tiles) break;  // a pair stops together; the peer may run ONE all-out-of-bounds tile (odd tile count)
+      for (int vt = blockIdx.x, tit = 0; tit < p.iters; vt += gridDim.x, ++tit) {
+      if (vt - (int)crank >= num_tiles) break;  // a pair stops together; the peer may run ONE all-out-of-bounds tile (odd tile count)
+      TC_WORK_ITEM(vt);
         const uint8_t* bimg = reinterpret_cast<const uint8_t*>(p.Bimg);
         if (p.tiles_per_batch > 0) bimg += (size_t)(tile / p.tiles_per_batch) * p.b_batch_bytes;
-        for (int pass = 0; pass < npass; ++pass) {
+        for (int pass = p0; pass < p1; ++pass) {
           for (int s = 0; s < Ks; ++s) {
             for (int j = TPP * pass; j < min(NT, TPP * pass + TPP); ++j, ++it) {
               const int slot = it % p.nb;
@@ -340,12 +350,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // completion (converted A slab, landed half weight block) to the leader's a_peer / b_peer barriers.  Relaxed arrives:
     // the data stays in this CTA's shared memory and is read there by this SM's tensor core.
     uint32_t a_it = 0, b_it = 0;
-    for (int tile = blockIdx.x, tit = 0; tit < p.iters; tile += gridDim.x, ++tit) {
-      if (tile - (int)crank >= num_tiles) break;
+    for (int vt = blockIdx.x, tit = 0; tit < p.iters; vt += gridDim.x, ++tit) {
+      if (vt - (int)crank >= num_tiles) break;
+      TC_WORK_ITEM(vt);
       const uint32_t a_base = a_it;
-      for (int pass = 0; pass < npass; ++pass) {
+      for (int pass = p0; pass < p1; ++pass) {
         for (int s = 0; s < Ks; ++s) {
-          if (!stationary || pass == 0) {
+          if (!stationary || pass == p0) {
             const uint32_t ai = stationary ? a_base + s : a_it;
             const uint32_t a_slot = ai % p.na;
             mbar_wait(smem_u32(&sm->a_full[a_slot]), (ai / p.na) & 1);
@@ -369,10 +380,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     {
       uint32_t a_it = 0, b_it = 0, acc_it = 0;
       long long t_acc = 0, t_a = 0, t_b = 0, t_issue = 0, t_commit = 0, t_all0 = TC_T0();
-      for (int tile = blockIdx.x, tit = 0; tit < p.iters; tile += gridDim.x, ++tit) {
-      if (tile - (int)crank >= num_tiles) break;  // a pair stops together; the peer may run ONE all-out-of-bounds tile (odd tile count)
+      for (int vt = blockIdx.x, tit = 0; tit < p.iters; vt += gridDim.x, ++tit) {
+      if (vt - (int)crank >= num_tiles) break;  // a pair stops together; the peer may run ONE all-out-of-bounds tile (odd tile count)
+      TC_WORK_ITEM(vt);
         const uint32_t a_base = a_it;
-        for (int pass = 0; pass < npass; ++pass, ++acc_it) {
+        for (int pass = p0; pass < p1; ++pass, ++acc_it) {
           const int buf = acc_it & 1;
           long long tw = TC_T0();
           if (pair) mbar_wait_cluster(smem_u32(&sm->acc_empty[buf]), ((acc_it >> 1) & 1) ^ 1);
@@ -384,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             tw = TC_T0();
             if (stationary) {
               a_slot = (a_base + s) % p.na;
-              if (pass == 0) {
+              if (pass == p0) {
                 mbar_wait(smem_u32(&sm->a_full[a_slot]), ((a_base + s) / p.na) & 1);
                 if (pair) mbar_wait_cluster(smem_u32(&sm->a_peer[a_slot]), ((a_base + s) / p.na) & 1);
               }
@@ -437,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               __syncwarp();
               TC_ACC(t_issue, tw);
             }
-            const bool last_use = stationary ? (pass == npass - 1) : true;
+            const bool last_use = stationary ? (pass == p1 - 1) : true;
             if (last_use && elect_one()) {
               if (pair) umma2_commit(smem_u32(&sm->a_empty[a_slot]));
               else umma_commit(smem_u32(&sm->a_empty[a_slot]));
@@ -477,8 +489,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int c4 = lane & 7, rsub = lane >> 3;
     uint32_t acc_it = 0;
     long long t_wait = 0, t_tmem = 0, t_all0 = TC_T0();
-    for (int tile = blockIdx.x, tit = 0; tit < p.iters; tile += gridDim.x, ++tit) {
-      if (tile - (int)crank >= num_tiles) break;  // a pair stops together; the peer may run ONE all-out-of-bounds tile (odd tile count)
+    for (int vt = blockIdx.x, tit = 0; tit < p.iters; vt += gridDim.x, ++tit) {
+      if (vt - (int)crank >= num_tiles) break;  // a pair stops together; the peer may run ONE all-out-of-bounds tile (odd tile count)
+      TC_WORK_ITEM(vt);
       int m0, m_end;
       tile_rows(p, tile, m0, m_end);
       const int mrow0 = m0 + quad * 32;
@@ -518,7 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
       (void)scale_d;
 
-      for (int pass = 0; pass < npass; ++pass, ++acc_it) {
+      for (int pass = p0; pass < p1; ++pass, ++acc_it) {
         const int buf = acc_it & 1;
         long long tw = TC_T0();
         mbar_wait(smem_u32(&sm->acc_full[buf]), (acc_it >> 1) & 1);
@@ -673,11 +686,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // fallback), landing on the slot's stage_full mbarrier.  It runs as far ahead as the ring allows (4 x 32 KB),
     // so the memory-level parallelism lives in shared memory instead of registers.
     uint32_t st_it = 0;
-    for (int tile = blockIdx.x, tit = 0; tit < p.iters; tile += gridDim.x, ++tit) {
-      if (tile - (int)crank >= num_tiles) break;  // a pair stops together; the peer may run ONE all-out-of-bounds tile (odd tile count)
+    for (int vt = blockIdx.x, tit = 0; tit < p.iters; vt += gridDim.x, ++tit) {
+      if (vt - (int)crank >= num_tiles) break;  // a pair stops together; the peer may run ONE all-out-of-bounds tile (odd tile count)
+      TC_WORK_ITEM(vt);
       int m0, m_end;
       tile_rows(p, tile, m0, m_end);
-      const int conv_passes = stationary ? 1 : npass;
+      const int conv_passes = stationary ? 1 : p1 - p0;
       for (int pass = 0; pass < conv_passes; ++pass) {
         for (int s = 0; s < Ks; ++s, ++st_it) {
           const int st = st_it % p.na;
@@ -789,8 +803,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const bool ln_from_stage = has_ln && stationary;  // the whole row is resident in the ring
     long long t_slot = 0, t_ld = 0, t_all0 = TC_T0();
     uint32_t a_it = 0;
-    for (int tile = blockIdx.x, tit = 0; tit < p.iters; tile += gridDim.x, ++tit) {
-      if (tile - (int)crank >= num_tiles) break;  // a pair stops together; the peer may run ONE all-out-of-bounds tile (odd tile count)
+    for (int vt = blockIdx.x, tit = 0; tit < p.iters; vt += gridDim.x, ++tit) {
+      if (vt - (int)crank >= num_tiles) break;  // a pair stops together; the peer may run ONE all-out-of-bounds tile (odd tile count)
+      TC_WORK_ITEM(vt);
       int m0, m_end;
       tile_rows(p, tile, m0, m_end);
       float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f};
@@ -847,7 +862,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           rstd[i] = rsqrtf(fmaxf(sq_[i] / (float)p.Ka - mu * mu, 0.f) + 1e-5f);
         }
       }
-      const int conv_passes = stationary ? 1 : npass;
+      const int conv_passes = stationary ? 1 : p1 - p0;
       for (int pass = 0; pass < conv_passes; ++pass) {
         for (int s = 0; s < Ks; ++s, ++a_it) {
           const int k = s * 64 + chunk * 8;
@@ -1122,6 +1137,8 @@ static int g_tepi_enabled = 1;
 void set_tepi_enabled(int on) { g_tepi_enabled = on; }
 static int g_ebox1_enabled = 1;
 void set_ebox1_enabled(int on) { g_ebox1_enabled = on; }
+static int g_psplit_enabled = 1;
+void set_psplit_enabled(int on) { g_psplit_enabled = on; }
 static int g_cluster_enabled = 1;  // CTA pairs: cta_group::2 MMAs (M = 256), half of every weight block per CTA
 void set_cluster_enabled(int on) { g_cluster_enabled = on; }
 void set_debug_buffer(long long* p) { g_dbg = p; }
@@ -1167,6 +1184,19 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
   }
   make_a_tensor_map(a, conv);
   // CTA pairs share every weight block (one L2 read, multicast into both CTAs) when the weights are not per-sample
+  // few-tile GEMMs (the 16 x 16 latent of a patch batch: 32-64 row tiles for 148 SMs): the 256-column passes of a row tile are
+  // handed to several CTAs (each converts the A slabs it needs itself)
+  a.psplit = 1;
+  {
+    const int npass = (a.Np + PASS_COLS - 1) / PASS_COLS;
+    a.ppg = npass;
+    if (g_psplit_enabled && npass >= 2 && a.num_tiles * 2 <= sm_count) {
+      int want = sm_count / a.num_tiles;
+      if (want > npass) want = npass;
+      a.ppg = (npass + want - 1) / want;
+      a.psplit = (npass + a.ppg - 1) / a.ppg;
+    }
+  }
   // CTA pairs run tiles (2 q, 2 q + 1) on one M = 256 instruction stream: both tiles must use the same weights
   // (per-sample weights: an even number of tiles per sample)
   // Measured (tools/gemm_bench.py, tools/shape_profile.py --no-pair): pairs pay when the tensor pipe bounds the tile — many
@@ -1174,15 +1204,16 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
   // the lock-step of the two CTAs, so they stay single.
   const int nt_blocks = (a.Np + BN - 1) / BN;
   const bool tensor_heavy = nt_blocks >= 2 && a.ks * nt_blocks >= 16;
-  a.cluster = (g_cluster_enabled && tensor_heavy && a.num_tiles >= 2 && a.Np % 16 == 0 &&
+  a.cluster = (g_cluster_enabled && a.psplit == 1 && tensor_heavy && a.num_tiles >= 2 && a.Np % 16 == 0 &&
                (a.b_batch_bytes == 0 || a.tiles_per_batch % 2 == 0)) ? 2 : 1;
-  int grid = a.num_tiles < sm_count ? a.num_tiles : sm_count;
+  const int items = a.num_tiles * a.psplit;
+  int grid = items < sm_count ? items : sm_count;
   if (a.cluster == 2) {
     grid = (grid + 1) & ~1;
     if (grid > (sm_count & ~1)) grid = sm_count & ~1;
     a.nb *= 2;   // half-size weight slots: twice the ring depth in the same shared memory
   }
-  a.iters = (a.num_tiles + grid - 1) / grid;
+  a.iters = (items + grid - 1) / grid;
   if (conv && a.epi == MPHSIR_EPI_BIAS) a.epi = TC_OUT_TOKENS;
   switch (a.epi) {
     case MPHSIR_EPI_BIAS: return launch_epi<MPHSIR_EPI_BIAS>(a, smem, grid, st);
@@ -1207,6 +1238,7 @@ using namespace mphsir;
 
 extern "C" MPHSIR_API void mphsir_debug_tc_counters(long long* buf) { tc::set_debug_buffer(buf); }
 extern "C" MPHSIR_API void mphsir_debug_tc_cluster(int enabled) { tc::set_cluster_enabled(enabled); }
+extern "C" MPHSIR_API void mphsir_debug_tc_psplit(int enabled) { tc::set_psplit_enabled(enabled); }
 extern "C" MPHSIR_API void mphsir_debug_tc_tma_epilogue(int enabled) { tc::set_tepi_enabled(enabled); }
 extern "C" MPHSIR_API void mphsir_debug_tc_ebox1(int enabled) { tc::set_ebox1_enabled(enabled); }
 extern "C" MPHSIR_API void mphsir_debug_pdl(int enabled) { tc::set_pdl_enabled(enabled); }

@@ -43,7 +43,9 @@ struct TcArgs {
   int parts;   // 1 = bf16x1, 2 = bf16x3 (hi/lo split)
   int na, nb;  // ring depths (set by the launcher)
   int cluster; // CTAs per cluster (2: weight blocks are fetched once per CTA pair and multicast)
-  int iters;   // tile iterations per CTA (identical for all CTAs so that a cluster stays in lock-step)
+  int iters;   // work-item iterations per CTA (identical for all CTAs so that a cluster stays in lock-step)
+  int psplit;  // work items per row tile: few-tile GEMMs (M < 128 * SMs / 2) hand the 256-column passes of a tile to `psplit` CTAs
+  int ppg;     // passes per work item
   const float* ln_g;
   const float* ln_b;
   const float* bias;
@@ -67,6 +69,7 @@ struct TcArgs {
 int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st);
 void set_debug_buffer(long long* p);
 void set_cluster_enabled(int on);
+void set_psplit_enabled(int on);
 void set_tepi_enabled(int on);
 void set_ebox1_enabled(int on);
 int pdl_enabled();           // programmatic dependent launch of the persistent tcgen05 kernels (tc_ptx.cuh: pdl_*)

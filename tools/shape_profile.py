@@ -9,6 +9,9 @@ from mp_hsir_b200 import lib
 workload = sys.argv[1] if len(sys.argv) > 1 else "cube512"
 model, shape, unit, units, _, _ = bench.WORKLOADS[workload]
 dev = torch.device("cuda", 0)
+if "--no-psplit" in sys.argv:
+    sys.argv.remove("--no-psplit")
+    lib.load().mphsir_debug_tc_psplit(0)
 if "--no-pair" in sys.argv:
     sys.argv.remove("--no-pair")
     lib.load().mphsir_debug_tc_cluster(0)
