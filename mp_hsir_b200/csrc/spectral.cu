@@ -269,7 +269,7 @@ __device__ __forceinline__ void split2_bf16(float a, float b, uint32_t& hi, uint
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-__global__ void __launch_bounds__(256) spectral_finish_kernel(const float* __restrict__ gsum,
+__global__ void __launch_bounds__(256) spectral_finish_kernel(const float* __restrict__ gsum, int n_chunks,
                                                               const float* __restrict__ temperature,
                                                               const float* __restrict__ WoutT, float* __restrict__ Mt,
                                                               long long ldm, long long m_batch_stride,
@@ -283,7 +283,19 @@ __global__ void __launch_bounds__(256) spectral_finish_kernel(const float* __res
   const int bh = blockIdx.x;
   const int b = bh / heads, h = bh - b * heads;
   const int o0 = blockIdx.y * 64;
-  for (int e = threadIdx.x; e < per; e += 256) A[e] = __ldg(gsum + (long long)bh * per + e);
+  // n_chunks > 1: a handful of partials per (sample, head) are summed here (in chunk order: deterministic) instead of by a
+  // separate reduction launch — both kernels are pure latency at these sizes
+  for (int e = threadIdx.x; e < per; e += 256) {
+    const float* src = gsum + (long long)bh * n_chunks * per + e;
+    float a0 = 0.f, a1 = 0.f;
+    int ch = 0;
+    for (; ch + 1 < n_chunks; ch += 2) {
+      a0 += __ldg(src + (long long)ch * per);
+      a1 += __ldg(src + (long long)(ch + 1) * per);
+    }
+    if (ch < n_chunks) a0 += __ldg(src + (long long)ch * per);
+    A[e] = a0 + a1;
+  }
   for (int e = threadIdx.x; e < c * 64; e += 256) {
     const int i = e >> 6, o = e & 63;
     Wt[e] = (o0 + o < C) ? __ldg(WoutT + (long long)(h * c + i) * C + o0 + o) : 0.f;
@@ -293,27 +305,50 @@ __global__ void __launch_bounds__(256) spectral_finish_kernel(const float* __res
   __syncthreads();
   const float temp = __ldg(temperature + h);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = warp; i < c; i += 8) {
-    const float nq = A[c * c + i];
-    float mx = -INFINITY;
-    for (int j = lane; j < c; j += 32) {
-      const float v = A[i * c + j] / (nq * A[c * c + c + j]) * temp;
-      A[i * c + j] = v;
-      mx = fmaxf(mx, v);
+  // rows i = warp + 8 r of a warp run side by side, four independent reduction chains per step (c <= 128: <= 4 values per lane)
+  for (int ib = warp; ib < c; ib += 32) {
+    float v[4][4], mx[4], ssum[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = ib + 8 * r;
+      mx[r] = -INFINITY;
+      ssum[r] = 0.f;
+      const float nq = i < c ? A[c * c + i] : 1.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = lane + 32 * q;
+        v[r][q] = (i < c && j < c) ? A[i * c + j] / (nq * A[c * c + c + j]) * temp : -INFINITY;
+        mx[r] = fmaxf(mx[r], v[r][q]);
+      }
     }
-    mx = warp_max(mx);
-    float ssum = 0.f;
-    for (int j = lane; j < c; j += 32) {
-      const float e = expf(A[i * c + j] - mx);
-      A[i * c + j] = e;
-      ssum += e;
-    }
-    ssum = warp_sum(ssum);
-    const float inv = 1.0f / ssum;
-    for (int j = lane; j < c; j += 32) {
-      const float pv = A[i * c + j] * inv;
-      A[i * c + j] = pv;
-      if (attn_out != nullptr && blockIdx.y == 0) attn_out[(long long)bh * c * c + i * c + j] = pv;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], o));
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[r][q] = (ib + 8 * r < c && lane + 32 * q < c) ? expf(v[r][q] - mx[r]) : 0.f;
+        ssum[r] += v[r][q];
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) ssum[r] += __shfl_xor_sync(0xffffffffu, ssum[r], o);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = ib + 8 * r;
+      if (i >= c) continue;
+      const float inv = 1.0f / ssum[r];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = lane + 32 * q;
+        if (j >= c) continue;
+        const float pv = v[r][q] * inv;
+        A[i * c + j] = pv;
+        if (attn_out != nullptr && blockIdx.y == 0) attn_out[(long long)bh * c * c + i * c + j] = pv;
+      }
     }
   }
   __syncthreads();
@@ -324,6 +359,7 @@ __global__ void __launch_bounds__(256) spectral_finish_kernel(const float* __res
     float acc[8];
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) acc[jj] = 0.f;
+#pragma unroll 4
     for (int i = 0; i < c; ++i) {
       const float w = Wt[i * 64 + o];
       const float4 a0 = *reinterpret_cast<const float4*>(&A[i * c + j0]);
@@ -463,9 +499,12 @@ extern "C" int mphsir_spectral_finish_fwd(const float* partial, int n_chunks, fl
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int per = c * c + 2 * c;
   const int C = heads * c;
+  MPHSIR_REQUIRE(c <= 128, "spectral_finish: c=%d channels per head (at most 128)", c);
   const float* gsum = partial;
-  if (n_chunks > 1) {
-    MPHSIR_REQUIRE(scratch != nullptr, "spectral_finish: scratch [B*heads*(c*c+2c)] required when n_chunks > 1");
+  int direct_chunks = n_chunks;
+  if (n_chunks > 16) {
+    direct_chunks = 1;
+    MPHSIR_REQUIRE(scratch != nullptr, "spectral_finish: scratch [B*heads*(c*c+2c)] required when n_chunks > 16");
     dim3 grid((per + 63) / 64, B * heads);
     gram_reduce_kernel<<<grid, 256, 0, st>>>(partial, n_chunks, per, scratch);
     gsum = scratch;
@@ -482,7 +521,7 @@ extern "C" int mphsir_spectral_finish_fwd(const float* partial, int n_chunks, fl
   }
   MPHSIR_REQUIRE(smem <= 96 * 1024, "spectral_finish: c=%d needs %zu B of shared memory", c, smem);
   dim3 grid(B * heads, (C + 63) / 64);
-  spectral_finish_kernel<<<grid, 256, smem, st>>>(gsum, temperature, WoutT, Mt, ldm, m_batch_stride,
+  spectral_finish_kernel<<<grid, 256, smem, st>>>(gsum, direct_chunks, temperature, WoutT, Mt, ldm, m_batch_stride,
                                                   reinterpret_cast<uint8_t*>(bimg), bimg_batch_bytes, attn_out, heads, c);
   return check_launch("spectral_finish");
 }
