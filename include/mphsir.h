@@ -120,6 +120,7 @@ typedef struct {
 MPHSIR_API void mphsir_debug_tc_counters(long long* buf);
 /* Debug: 0 disables the CTA-pair (cta_group::2) instantiation of the tensor-core GEMM (default 1: tensor-heavy shapes use it). */
 MPHSIR_API void mphsir_debug_tc_cluster(int enabled);
+MPHSIR_API void mphsir_debug_tc_reverse(int enabled);          /* 0: tensor-core GEMM launches never walk their row tiles backwards (default 1: launches over >= 131072 rows do — their input is then read starting with the part the producer wrote last, which is still in L2) */
 MPHSIR_API void mphsir_debug_tc_psplit(int enabled);           /* 0: never hand the 256-column passes of a row tile to several CTAs (A/B switch; default 1: few-tile GEMMs do) */
 MPHSIR_API void mphsir_debug_tc_ebox1(int enabled);         /* 0: two store boxes per epilogue warp everywhere (default 1: one box + 4-slot A ring for BIAS GEMMs with 64 < K <= 128) */
 MPHSIR_API void mphsir_debug_pdl(int enabled);              /* 1: programmatic dependent launch of the persistent tcgen05 kernels (default 0: measured, no gain) */

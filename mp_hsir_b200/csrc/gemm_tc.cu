@@ -49,10 +49,19 @@ constexpr int MAX_RING = 8;
 #define TC_T0() (p.dbg ? clock64() : 0)
 #define TC_ACC(var, t0) do { if (p.dbg) var += clock64() - (t0); } while (0)
 
+// p.rev: the launch walks its work items from the last to the first.  Activations at 512 x 512 are slightly larger than the
+// L2 (134 MB per 128-channel tensor against 126 MB): a consumer that starts where its producer STOPPED finds the most
+// recently written part still on chip, while two kernels walking in the same direction evict everything just before it is read.
+__device__ __forceinline__ int tc_order(const TcArgs& p, int vt) {
+  const int n = p.num_tiles * p.psplit;
+  return (p.rev && vt < n) ? n - 1 - vt : vt;
+}
+
 // Work item `vt` of a launch = (row tile, range of 256-column passes [p0, p1)): vt = tile * psplit + group.
 #define TC_WORK_ITEM(vt)                                               \
-  const int tile = (vt) / p.psplit;                                    \
-  const int p0 = ((vt) - tile * p.psplit) * p.ppg;                     \
+  const int vtr_ = tc_order(p, (vt));                                  \
+  const int tile = vtr_ / p.psplit;                                    \
+  const int p0 = (vtr_ - tile * p.psplit) * p.ppg;                     \
   const int p1 = min(npass, p0 + p.ppg);                               \
   (void)p0; (void)p1
 
@@ -101,7 +110,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t*
 
   auto ncols_of = [&](int pass) { return min(PASS_COLS, p.Np - pass * PASS_COLS); };
   // next chunk of this warp after (tile, tit, pass, c0); false when the CTA's work is finished
-  auto p0_of = [&](int vt) { return (vt - (vt / p.psplit) * p.psplit) * p.ppg; };
+  auto p0_of = [&](int vt) { const int w = tc_order(p, vt); return (w - (w / p.psplit) * p.psplit) * p.ppg; };
   auto advance = [&](int& vt, int& tit, int& pass, int& c0) -> bool {
     c0 += 64;
     for (;;) {
@@ -128,7 +137,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t*
   };
   auto issue_res = [&](int vt, int pass, int c0, int slot) {  // lane 0 only
     int b, row0;
-    tile_coord(vt / p.psplit, b, row0);
+    tile_coord(tc_order(p, vt) / p.psplit, b, row0);
     mbar_expect_tx(rbar0 + 8 * slot, 4096);
     tma_load_3d(slot_a0 + 4096 * slot, &p.tmR, pass * PASS_COLS + c0, row0, b, rbar0 + 8 * slot);
   };
@@ -1137,6 +1146,8 @@ static int g_tepi_enabled = 1;
 void set_tepi_enabled(int on) { g_tepi_enabled = on; }
 static int g_ebox1_enabled = 1;
 void set_ebox1_enabled(int on) { g_ebox1_enabled = on; }
+static int g_tile_rev = 1;
+void set_tile_rev(int on) { g_tile_rev = on; }
 static int g_psplit_enabled = 1;
 void set_psplit_enabled(int on) { g_psplit_enabled = on; }
 static int g_cluster_enabled = 1;  // CTA pairs: cta_group::2 MMAs (M = 256), half of every weight block per CTA
@@ -1156,6 +1167,8 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
   //   bf16x3: A 3 x 32 KB + B 3 x 32 KB        bf16x1: A 4 x 32 KB + B 4 x 16 KB
   // TMA epilogue: plain GEMMs with a BIAS / RESIDUAL (single residual) / PROJ epilogue
   a.tepi = 0;
+  // measured: 512 x 512 inference -0.9 % per cube, batch-32 training +0.4 %; tensors that fit the L2 anyway gain nothing
+  a.rev = (g_tile_rev && a.M >= 131072) ? 1 : 0;
   if (g_tepi_enabled && !conv &&
       (a.epi == MPHSIR_EPI_BIAS || (a.epi == MPHSIR_EPI_RESIDUAL && a.res2 == nullptr) || a.epi == MPHSIR_EPI_PROJ)) {
     const bool per_sample = a.tiles_per_batch > 0;
@@ -1239,6 +1252,7 @@ using namespace mphsir;
 extern "C" MPHSIR_API void mphsir_debug_tc_counters(long long* buf) { tc::set_debug_buffer(buf); }
 extern "C" MPHSIR_API void mphsir_debug_tc_cluster(int enabled) { tc::set_cluster_enabled(enabled); }
 extern "C" MPHSIR_API void mphsir_debug_tc_psplit(int enabled) { tc::set_psplit_enabled(enabled); }
+extern "C" MPHSIR_API void mphsir_debug_tc_reverse(int enabled) { tc::set_tile_rev(enabled); }
 extern "C" MPHSIR_API void mphsir_debug_tc_tma_epilogue(int enabled) { tc::set_tepi_enabled(enabled); }
 extern "C" MPHSIR_API void mphsir_debug_tc_ebox1(int enabled) { tc::set_ebox1_enabled(enabled); }
 extern "C" MPHSIR_API void mphsir_debug_pdl(int enabled) { tc::set_pdl_enabled(enabled); }

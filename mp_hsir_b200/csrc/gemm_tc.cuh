@@ -46,6 +46,7 @@ struct TcArgs {
   int iters;   // work-item iterations per CTA (identical for all CTAs so that a cluster stays in lock-step)
   int psplit;  // work items per row tile: few-tile GEMMs (M < 128 * SMs / 2) hand the 256-column passes of a tile to `psplit` CTAs
   int ppg;     // passes per work item
+  int rev;     // 1: work items are walked from the last to the first (L2 reuse of the producer's most recent output)
   const float* ln_g;
   const float* ln_b;
   const float* bias;
@@ -70,6 +71,7 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st);
 void set_debug_buffer(long long* p);
 void set_cluster_enabled(int on);
 void set_psplit_enabled(int on);
+void set_tile_rev(int on);
 void set_tepi_enabled(int on);
 void set_ebox1_enabled(int on);
 int pdl_enabled();           // programmatic dependent launch of the persistent tcgen05 kernels (tc_ptx.cuh: pdl_*)

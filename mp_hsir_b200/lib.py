@@ -102,6 +102,7 @@ SIGNATURES = {
     "mphsir_debug_tc_counters": (None, [_VP]),
     "mphsir_debug_tc_cluster": (None, [_I]),
     "mphsir_debug_tc_psplit": (None, [_I]),
+    "mphsir_debug_tc_reverse": (None, [_I]),
     "mphsir_debug_mlp_counters": (None, [_VP]),
     "mphsir_debug_mlp_flags": (None, [_I]),
     "mphsir_debug_dwgram_tma": (None, [_I]),
@@ -204,6 +205,8 @@ def load() -> C.CDLL:
         lib.mphsir_debug_pdl(int(os.environ["MPHSIR_PDL"]))
     if os.environ.get("MPHSIR_PSPLIT") in ("0", "1"):  # A/B switch: few-tile GEMMs hand the passes of a row tile to several CTAs
         lib.mphsir_debug_tc_psplit(int(os.environ["MPHSIR_PSPLIT"]))
+    if os.environ.get("MPHSIR_REV") in ("0", "1"):     # A/B switch: GEMM launches walk their tiles backwards
+        lib.mphsir_debug_tc_reverse(int(os.environ["MPHSIR_REV"]))
     if os.environ.get("MPHSIR_PAIR") in ("0", "1"):    # A/B switch: CTA-pair (cta_group::2) instantiation of the GEMM engine
         lib.mphsir_debug_tc_cluster(int(os.environ["MPHSIR_PAIR"]))
     _lib = lib
