@@ -270,6 +270,7 @@ __device__ __forceinline__ void split2_bf16(float a, float b, uint32_t& hi, uint
 }
 
 __global__ void __launch_bounds__(256) spectral_finish_kernel(const float* __restrict__ gsum, int n_chunks,
+                                                              float* __restrict__ gsum_out,
                                                               const float* __restrict__ temperature,
                                                               const float* __restrict__ WoutT, float* __restrict__ Mt,
                                                               long long ldm, long long m_batch_stride,
@@ -295,6 +296,8 @@ __global__ void __launch_bounds__(256) spectral_finish_kernel(const float* __res
     }
     if (ch < n_chunks) a0 += __ldg(src + (long long)ch * per);
     A[e] = a0 + a1;
+    // the reduced statistics are part of the contract (scratch [B*heads*per]): the training backward reads them
+    if (gsum_out != nullptr && blockIdx.y == 0) gsum_out[(long long)bh * per + e] = a0 + a1;
   }
   for (int e = threadIdx.x; e < c * 64; e += 256) {
     const int i = e >> 6, o = e & 63;
@@ -521,7 +524,7 @@ extern "C" int mphsir_spectral_finish_fwd(const float* partial, int n_chunks, fl
   }
   MPHSIR_REQUIRE(smem <= 96 * 1024, "spectral_finish: c=%d needs %zu B of shared memory", c, smem);
   dim3 grid(B * heads, (C + 63) / 64);
-  spectral_finish_kernel<<<grid, 256, smem, st>>>(gsum, direct_chunks, temperature, WoutT, Mt, ldm, m_batch_stride,
+  spectral_finish_kernel<<<grid, 256, smem, st>>>(gsum, direct_chunks, (n_chunks > 1 && direct_chunks > 1) ? scratch : nullptr, temperature, WoutT, Mt, ldm, m_batch_stride,
                                                   reinterpret_cast<uint8_t*>(bimg), bimg_batch_bytes, attn_out, heads, c);
   return check_launch("spectral_finish");
 }
