@@ -376,8 +376,15 @@ def test_spectral_finish_matches_unfused_chain(C, heads, HW):
     img = torch.zeros_like(img_ref)
     attn2 = torch.empty_like(attn)
     scratch = torch.empty(B * heads * (c * c + 2 * c), device=DEV)
+    scratch.fill_(float("nan"))
     lib.spectral_finish(partial, nch, scratch, temp, wout_t, Mt, img, B, heads, c, attn_out=attn2)
     assert rel_err(attn2.cpu(), attn.cpu()) < 1e-6
+    if nch > 1:
+        # the reduced Gram statistics in `scratch` are part of the contract whichever path summed them (few partials: the
+        # finish kernel itself; many: gram_reduce): the training backward reads them
+        per = c * c + 2 * c
+        want = partial.view(B * heads, nch, per).double().sum(1).float()
+        assert rel_err(scratch.view(B * heads, per).cpu(), want.cpu()) < 1e-6
     assert rel_err(Mt[:, :C, :C].cpu(), Mt_ref[:, :C, :C].cpu()) < 1e-6
     # the images hold [hi part | lo part] in the same layout: hi + lo reconstructs the folded matrix to ~2^-17
     def recon(t):
