@@ -121,6 +121,10 @@ MPHSIR_API void mphsir_debug_tc_counters(long long* buf);
 /* Debug: 0 disables the CTA-pair (cta_group::2) instantiation of the tensor-core GEMM (default 1: tensor-heavy shapes use it). */
 MPHSIR_API void mphsir_debug_tc_cluster(int enabled);
 MPHSIR_API void mphsir_debug_tc_reverse(int enabled);          /* 0: tensor-core GEMM launches never walk their row tiles backwards (default 1: launches over >= 131072 rows do — their input is then read starting with the part the producer wrote last, which is still in L2) */
+/* How mphsir_gemm_fwd (tensor-core precisions) cuts a [M,K] x [K,N] launch into work on a device with `sm_count` SMs — pure host
+ * arithmetic, no device needed: out6 = {CTAs per cluster (2 = cta_group::2 pairs), work items per row tile (256-column pass groups),
+ * passes per work item, grid size, work-item iterations per CTA, 1 if the tiles are walked backwards}. */
+MPHSIR_API int mphsir_gemm_plan(int M, int N, int K, int rows_per_batch, int per_sample_weights, int sm_count, int* out6);
 MPHSIR_API void mphsir_debug_tc_psplit(int enabled);           /* 0: never hand the 256-column passes of a row tile to several CTAs (A/B switch; default 1: few-tile GEMMs do) */
 MPHSIR_API void mphsir_debug_tc_ebox1(int enabled);         /* 0: two store boxes per epilogue warp everywhere (default 1: one box + 4-slot A ring for BIAS GEMMs with 64 < K <= 128) */
 MPHSIR_API void mphsir_debug_pdl(int enabled);              /* 1: programmatic dependent launch of the persistent tcgen05 kernels (default 0: measured, no gain) */
@@ -129,7 +133,7 @@ MPHSIR_API void mphsir_debug_window_attn_tc(int enabled);   /* 0: mma.sync windo
 MPHSIR_API void mphsir_debug_window_attn_tc_counters(long long* buf);   /* [grid][16] per-CTA role cycle counters of the tcgen05 window attention (NULL: off) */
 MPHSIR_API void mphsir_debug_dwgram_tma(int enabled);       /* 0: use the direct-load dwconv+Gram kernel everywhere (default 1) */
 MPHSIR_API void mphsir_debug_mlp_counters(long long* buf); /* same idea for the fused MLP kernel */
-MPHSIR_API void mphsir_debug_mlp_flags(int flags);          /* timing experiments (wrong results!): 1 no gelu, 2 no bias, 4 no split */
+MPHSIR_API void mphsir_debug_mlp_flags(int flags);          /* timing experiments (wrong results!): 16 no weight copies, 32 no conversion, 64 no GLU work, 128 no final epilogue, 256 no X loads, 4096 no MMAs */
 MPHSIR_API size_t mphsir_bimg_bytes(int N, int K);
 MPHSIR_API int mphsir_pack_bimg(const float* W, int ld, int transposed, long long w_batch_stride, void* img,
                                 int batch, int N, int K, void* stream);

@@ -1154,6 +1154,42 @@ static int g_cluster_enabled = 1;  // CTA pairs: cta_group::2 MMAs (M = 256), ha
 void set_cluster_enabled(int on) { g_cluster_enabled = on; }
 void set_debug_buffer(long long* p) { g_dbg = p; }
 
+// How a launch is cut into work: pure host arithmetic (also exported as mphsir_gemm_plan for the CPU tests).
+struct WorkPlan { int cluster, psplit, ppg, grid, iters, rev; };
+static WorkPlan plan_work(int M, int Np, int ks, int num_tiles, int tiles_per_batch, bool per_sample_weights, int sm_count) {
+  WorkPlan w{};
+  // few-tile GEMMs (the 16 x 16 latent of a patch batch: 32-64 row tiles for 148 SMs): the 256-column passes of a row tile are
+  // handed to several CTAs (each converts the A slabs it needs itself)
+  const int npass = (Np + PASS_COLS - 1) / PASS_COLS;
+  w.psplit = 1;
+  w.ppg = npass;
+  if (g_psplit_enabled && npass >= 2 && num_tiles * 2 <= sm_count) {
+    int want = sm_count / num_tiles;
+    if (want > npass) want = npass;
+    w.ppg = (npass + want - 1) / want;
+    w.psplit = (npass + w.ppg - 1) / w.ppg;
+  }
+  // CTA pairs run tiles (2 q, 2 q + 1) on one M = 256 instruction stream: both tiles must use the same weights
+  // (per-sample weights: an even number of tiles per sample).
+  // Measured (tools/gemm_bench.py, tools/shape_profile.py --no-pair): pairs pay when the tensor pipe bounds the tile — many
+  // weight blocks per A slab (wide 3x3 convs: -16 %, the K = 256 fc1: -3 %); the HBM-side GEMMs (K <= 128) lose 0-8 % to
+  // the lock-step of the two CTAs, so they stay single.
+  const int nt_blocks = (Np + BN - 1) / BN;
+  const bool tensor_heavy = nt_blocks >= 2 && ks * nt_blocks >= 16;
+  w.cluster = (g_cluster_enabled && w.psplit == 1 && tensor_heavy && num_tiles >= 2 && Np % 16 == 0 &&
+               (!per_sample_weights || tiles_per_batch % 2 == 0)) ? 2 : 1;
+  const int items = num_tiles * w.psplit;
+  w.grid = items < sm_count ? items : sm_count;
+  if (w.cluster == 2) {
+    w.grid = (w.grid + 1) & ~1;
+    if (w.grid > (sm_count & ~1)) w.grid = sm_count & ~1;
+  }
+  w.iters = (items + w.grid - 1) / w.grid;
+  // measured: 512 x 512 inference -0.9 % per cube, batch-32 training +0.4 %; tensors that fit the L2 anyway gain nothing
+  w.rev = (g_tile_rev && M >= 131072) ? 1 : 0;
+  return w;
+}
+
 int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
   a.dbg = g_dbg;
   static int sm_count = 0;
@@ -1167,8 +1203,6 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
   //   bf16x3: A 3 x 32 KB + B 3 x 32 KB        bf16x1: A 4 x 32 KB + B 4 x 16 KB
   // TMA epilogue: plain GEMMs with a BIAS / RESIDUAL (single residual) / PROJ epilogue
   a.tepi = 0;
-  // measured: 512 x 512 inference -0.9 % per cube, batch-32 training +0.4 %; tensors that fit the L2 anyway gain nothing
-  a.rev = (g_tile_rev && a.M >= 131072) ? 1 : 0;
   if (g_tepi_enabled && !conv &&
       (a.epi == MPHSIR_EPI_BIAS || (a.epi == MPHSIR_EPI_RESIDUAL && a.res2 == nullptr) || a.epi == MPHSIR_EPI_PROJ)) {
     const bool per_sample = a.tiles_per_batch > 0;
@@ -1196,37 +1230,10 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
     a.num_tiles = (a.M / a.rows_per_batch) * a.tiles_per_batch;
   }
   make_a_tensor_map(a, conv);
-  // CTA pairs share every weight block (one L2 read, multicast into both CTAs) when the weights are not per-sample
-  // few-tile GEMMs (the 16 x 16 latent of a patch batch: 32-64 row tiles for 148 SMs): the 256-column passes of a row tile are
-  // handed to several CTAs (each converts the A slabs it needs itself)
-  a.psplit = 1;
-  {
-    const int npass = (a.Np + PASS_COLS - 1) / PASS_COLS;
-    a.ppg = npass;
-    if (g_psplit_enabled && npass >= 2 && a.num_tiles * 2 <= sm_count) {
-      int want = sm_count / a.num_tiles;
-      if (want > npass) want = npass;
-      a.ppg = (npass + want - 1) / want;
-      a.psplit = (npass + a.ppg - 1) / a.ppg;
-    }
-  }
-  // CTA pairs run tiles (2 q, 2 q + 1) on one M = 256 instruction stream: both tiles must use the same weights
-  // (per-sample weights: an even number of tiles per sample)
-  // Measured (tools/gemm_bench.py, tools/shape_profile.py --no-pair): pairs pay when the tensor pipe bounds the tile — many
-  // weight blocks per A slab (wide 3x3 convs: -16 %, the K = 256 fc1: -3 %); the HBM-side GEMMs (K <= 128) lose 0-8 % to
-  // the lock-step of the two CTAs, so they stay single.
-  const int nt_blocks = (a.Np + BN - 1) / BN;
-  const bool tensor_heavy = nt_blocks >= 2 && a.ks * nt_blocks >= 16;
-  a.cluster = (g_cluster_enabled && a.psplit == 1 && tensor_heavy && a.num_tiles >= 2 && a.Np % 16 == 0 &&
-               (a.b_batch_bytes == 0 || a.tiles_per_batch % 2 == 0)) ? 2 : 1;
-  const int items = a.num_tiles * a.psplit;
-  int grid = items < sm_count ? items : sm_count;
-  if (a.cluster == 2) {
-    grid = (grid + 1) & ~1;
-    if (grid > (sm_count & ~1)) grid = sm_count & ~1;
-    a.nb *= 2;   // half-size weight slots: twice the ring depth in the same shared memory
-  }
-  a.iters = (items + grid - 1) / grid;
+  const WorkPlan wp = plan_work(a.M, a.Np, a.ks, a.num_tiles, a.tiles_per_batch, a.b_batch_bytes != 0, sm_count);
+  a.psplit = wp.psplit; a.ppg = wp.ppg; a.cluster = wp.cluster; a.iters = wp.iters; a.rev = wp.rev;
+  const int grid = wp.grid;
+  if (a.cluster == 2) a.nb *= 2;   // half-size weight slots: twice the ring depth in the same shared memory
   if (conv && a.epi == MPHSIR_EPI_BIAS) a.epi = TC_OUT_TOKENS;
   switch (a.epi) {
     case MPHSIR_EPI_BIAS: return launch_epi<MPHSIR_EPI_BIAS>(a, smem, grid, st);
@@ -1244,6 +1251,11 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
   }
 }
 
+GemmPlanOut gemm_plan(int M, int Np, int ks, int num_tiles, int tiles_per_batch, bool per_sample_weights, int sm_count) {
+  const WorkPlan w = plan_work(M, Np, ks, num_tiles, tiles_per_batch, per_sample_weights, sm_count);
+  return GemmPlanOut{w.cluster, w.psplit, w.ppg, w.grid, w.iters, w.rev};
+}
+
 }  // namespace tc
 }  // namespace mphsir
 
@@ -1252,6 +1264,14 @@ using namespace mphsir;
 extern "C" MPHSIR_API void mphsir_debug_tc_counters(long long* buf) { tc::set_debug_buffer(buf); }
 extern "C" MPHSIR_API void mphsir_debug_tc_cluster(int enabled) { tc::set_cluster_enabled(enabled); }
 extern "C" MPHSIR_API void mphsir_debug_tc_psplit(int enabled) { tc::set_psplit_enabled(enabled); }
+extern "C" MPHSIR_API int mphsir_gemm_plan(int M, int N, int K, int rows_per_batch, int per_sample_weights, int sm_count, int* out6) {
+  if (M <= 0 || N <= 0 || K <= 0 || sm_count <= 0 || out6 == nullptr) return MPHSIR_ERR_INVALID;
+  const int tpb = (per_sample_weights && rows_per_batch > 0) ? (rows_per_batch + 127) / 128 : 0;
+  const int tiles = tpb > 0 ? (M / rows_per_batch) * tpb : (M + 127) / 128;
+  const tc::GemmPlanOut w = tc::gemm_plan(M, (N + 15) / 16 * 16, (K + 63) / 64, tiles, tpb, per_sample_weights != 0, sm_count);
+  out6[0] = w.cluster; out6[1] = w.psplit; out6[2] = w.ppg; out6[3] = w.grid; out6[4] = w.iters; out6[5] = w.rev;
+  return MPHSIR_OK;
+}
 extern "C" MPHSIR_API void mphsir_debug_tc_reverse(int enabled) { tc::set_tile_rev(enabled); }
 extern "C" MPHSIR_API void mphsir_debug_tc_tma_epilogue(int enabled) { tc::set_tepi_enabled(enabled); }
 extern "C" MPHSIR_API void mphsir_debug_tc_ebox1(int enabled) { tc::set_ebox1_enabled(enabled); }

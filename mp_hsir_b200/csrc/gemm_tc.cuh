@@ -68,6 +68,8 @@ struct TcArgs {
 };
 
 int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st);
+struct GemmPlanOut { int cluster, psplit, ppg, grid, iters, rev; };
+GemmPlanOut gemm_plan(int M, int Np, int ks, int num_tiles, int tiles_per_batch, bool per_sample_weights, int sm_count);
 void set_debug_buffer(long long* p);
 void set_cluster_enabled(int on);
 void set_psplit_enabled(int on);

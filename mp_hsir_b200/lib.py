@@ -102,6 +102,7 @@ SIGNATURES = {
     "mphsir_debug_tc_counters": (None, [_VP]),
     "mphsir_debug_tc_cluster": (None, [_I]),
     "mphsir_debug_tc_psplit": (None, [_I]),
+    "mphsir_gemm_plan": (_I, [_I, _I, _I, _I, _I, _I, C.POINTER(_I)]),
     "mphsir_debug_tc_reverse": (None, [_I]),
     "mphsir_debug_mlp_counters": (None, [_VP]),
     "mphsir_debug_mlp_flags": (None, [_I]),

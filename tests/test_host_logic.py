@@ -92,3 +92,39 @@ def test_synthetic_weights_are_name_seeded():
     b = synth_tensor("latent.blocks.0.attn.qkv.weight", (768, 256), 0)
     c = synth_tensor("latent.blocks.1.attn.qkv.weight", (768, 256), 0)
     assert torch.equal(a, b) and not torch.equal(a, c)
+
+
+def _gemm_plan(M, N, K, rows_per_batch=0, per_sample=0, sms=148):
+    import ctypes
+    from mp_hsir_b200 import lib
+    out = (ctypes.c_int * 6)()
+    assert lib.load().mphsir_gemm_plan(M, N, K, rows_per_batch, per_sample, sms, out) == 0
+    return dict(zip(("cluster", "psplit", "ppg", "grid", "iters", "rev"), out))
+
+
+@pytest.mark.parametrize("M,N,K", [(262144, 384, 128), (65536, 512, 128), (16384, 768, 256), (4096, 1376, 256), (4096, 256, 688),
+                                   (8192, 1024, 256), (128, 64, 64), (300, 288, 96), (262144, 256, 1152), (4096, 512, 2304)])
+def test_gemm_work_plan_covers_every_pass_exactly_once(M, N, K):
+    """mphsir_gemm_plan (the host arithmetic of the tensor-core GEMM launcher, no device needed): every (row tile, 256-column
+    pass) belongs to exactly one work item, the grid fits the machine, pairs are even, few-tile launches are split."""
+    pl = _gemm_plan(M, N, K)
+    tiles, npass = (M + 127) // 128, ((N + 15) // 16 * 16 + 255) // 256
+    assert pl["cluster"] in (1, 2) and pl["psplit"] >= 1 and pl["ppg"] >= 1
+    # pass groups tile the pass range without gaps or overlap
+    covered = []
+    for g in range(pl["psplit"]):
+        covered += list(range(g * pl["ppg"], min(npass, (g + 1) * pl["ppg"])))
+    assert covered == list(range(npass))
+    items = tiles * pl["psplit"]
+    assert 1 <= pl["grid"] <= 148 and pl["grid"] * pl["iters"] >= items > pl["grid"] * (pl["iters"] - 1) - (pl["cluster"] - 1)
+    if pl["cluster"] == 2:
+        assert pl["grid"] % 2 == 0 and pl["psplit"] == 1 and tiles >= 2
+    if tiles * 2 <= 148 and npass >= 2:
+        assert pl["psplit"] >= 2, "few-tile launches hand the passes of a row tile to several CTAs"
+    assert pl["rev"] == (1 if M >= 131072 else 0)
+
+
+def test_gemm_work_plan_pairs_need_shared_weights_within_a_pair():
+    # per-sample weights: a CTA pair runs tiles (2q, 2q+1) on one instruction stream, so both must lie in the same sample
+    assert _gemm_plan(3 * 384, 256, 1152, rows_per_batch=384, per_sample=1)["cluster"] == 1      # 3 tiles per sample: odd
+    assert _gemm_plan(64 * 512, 256, 1152, rows_per_batch=512, per_sample=1)["cluster"] == 2     # 4 tiles per sample
