@@ -497,6 +497,10 @@ MPHSIR_API int mphsir_plane_nonzero(const float* X, int planes, long long hw, in
 MPHSIR_API int mphsir_degrade(const float* clean, float* out, int B, int C, long long hw, const float* sigma /* [B*C] */,
                               const float* keep /* [B*C] */, const float* mask_ratio /* [B] */, unsigned long long seed,
                               void* stream);
+/* Gaussian blur degradation (utils/degradation_utils.py:91-108): every band of sample b with ksize[b] > 0 (odd, <= 21; device
+ * int array [B]) is convolved with the k x k outer product of the normalised 1-D Gaussian of sigma 0.3((k-1)/2 - 1) + 0.8,
+ * zero padding k/2; planes of samples with ksize[b] == 0 are not touched.  kmax >= every ksize[b] (validated on the host). */
+MPHSIR_API int mphsir_gaussian_blur(const float* in, float* out, const int* ksize, int B, int C, int H, int W, int kmax, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Collectives of the row-sharded scene over NVLink peer memory (mp_hsir_b200/csrc/peer.cu; one process per GPU of one

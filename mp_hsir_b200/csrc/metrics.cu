@@ -165,6 +165,67 @@ __global__ void __launch_bounds__(256) degrade_kernel(const float* __restrict__ 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Gaussian blur degradation (utils/degradation_utils.py:91-108): depthwise conv of every band with the outer product of a
+// normalised 1-D Gaussian, sigma = 0.3 ((k - 1) / 2 - 1) + 0.8, zero padding k / 2.  One CTA per (plane, 32 x 32 tile): the
+// haloed tile is staged in shared memory, a horizontal pass writes a [32 + k - 1][32] strip, a vertical pass the output —
+// the separable form of the reference's k x k kernel (its kernel_2d IS the outer product).  ksize[b] == 0: sample b is not
+// a blur sample and its output plane is left alone (the elementwise degradation kernel wrote it).
+// ---------------------------------------------------------------------------------------------
+constexpr int BLUR_T = 32;       // output tile
+constexpr int BLUR_KMAX = 21;    // largest kernel of the reference's de_dict ('blur': 9, 15, 21 / 7, 11, 15)
+
+__global__ void __launch_bounds__(256) gaussian_blur_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                            const int* __restrict__ ksize, int C, int H, int W, int tiles_x,
+                                                            int tiles_per_plane) {
+  __shared__ float tile[BLUR_T + BLUR_KMAX - 1][BLUR_T + BLUR_KMAX - 1 + 1];
+  __shared__ float hrow[BLUR_T + BLUR_KMAX - 1][BLUR_T + 1];
+  __shared__ float kw[BLUR_KMAX];
+  const int plane = blockIdx.x / tiles_per_plane;
+  const int t = blockIdx.x - plane * tiles_per_plane;
+  const int b = plane / C;
+  const int k = ksize[b];
+  if (k <= 0) return;
+  const int r = k >> 1;
+  const int ty0 = (t / tiles_x) * BLUR_T, tx0 = (t % tiles_x) * BLUR_T;
+  const float* src = in + (long long)plane * H * W;
+  if (threadIdx.x < k) {
+    // kernel_1d = exp(-(x - mean)^2 / (2 sigma^2)) / sum, exactly as the reference builds it (fp32)
+    const float sigma = 0.3f * ((float)(k - 1) * 0.5f - 1.0f) + 0.8f;
+    const float mean = (float)(k - 1) / 2.0f;
+    float sum = 0.f;
+    for (int i = 0; i < k; ++i) {
+      const float d = (float)i - mean;
+      sum += expf(-(d * d) / (2.0f * sigma * sigma));
+    }
+    const float d = (float)threadIdx.x - mean;
+    kw[threadIdx.x] = expf(-(d * d) / (2.0f * sigma * sigma)) / sum;
+  }
+  const int ext = BLUR_T + 2 * r;
+  for (int e = threadIdx.x; e < ext * ext; e += 256) {
+    const int yy = e / ext, xx = e - yy * ext;
+    const int y = ty0 + yy - r, x = tx0 + xx - r;
+    tile[yy][xx] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(src + (long long)y * W + x) : 0.f;   // zero padding
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < ext * BLUR_T; e += 256) {
+    const int yy = e / BLUR_T, xx = e - yy * BLUR_T;
+    float a = 0.f;
+    for (int i = 0; i < k; ++i) a = fmaf(kw[i], tile[yy][xx + i], a);
+    hrow[yy][xx] = a;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < BLUR_T * BLUR_T; e += 256) {
+    const int yy = e / BLUR_T, xx = e - yy * BLUR_T;
+    const int y = ty0 + yy, x = tx0 + xx;
+    if (y >= H || x >= W) continue;
+    float a = 0.f;
+    for (int i = 0; i < k; ++i) a = fmaf(kw[i], hrow[yy + i][xx], a);
+    out[(long long)plane * H * W + (long long)y * W + x] = a;
+  }
+}
+
 }  // namespace metrics
 }  // namespace mphsir
 
@@ -208,4 +269,16 @@ extern "C" int mphsir_degrade(const float* clean, float* out, int B, int C, long
   metrics::degrade_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       clean, out, total, hw, C, sigma, keep, mask_ratio, (uint32_t)seed, (uint32_t)(seed >> 32));
   return check_launch("degrade");
+}
+
+extern "C" int mphsir_gaussian_blur(const float* in, float* out, const int* ksize, int B, int C, int H, int W, int kmax, void* stream) {
+  MPHSIR_REQUIRE(in && out && ksize && B > 0 && C > 0 && H > 0 && W > 0, "gaussian_blur: bad arguments");
+  MPHSIR_REQUIRE(in != out, "gaussian_blur: in place is not supported (every output pixel reads a k x k neighbourhood)");
+  MPHSIR_REQUIRE(kmax >= 0 && kmax <= metrics::BLUR_KMAX, "gaussian_blur: kernel sizes up to %d (got %d)", metrics::BLUR_KMAX, kmax);
+  const int tiles_x = (W + metrics::BLUR_T - 1) / metrics::BLUR_T, tiles_y = (H + metrics::BLUR_T - 1) / metrics::BLUR_T;
+  const long long blocks = (long long)B * C * tiles_x * tiles_y;
+  MPHSIR_REQUIRE(blocks < (1LL << 31), "gaussian_blur: too many tiles");
+  metrics::gaussian_blur_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, out, ksize, C, H, W, tiles_x,
+                                                                                                    tiles_x * tiles_y);
+  return check_launch("gaussian_blur");
 }

@@ -11,6 +11,9 @@ the B*C*H*W random numbers come from a counter-based Philox4x32-10 stream inside
     inpaint   : rand(C,H,W) > ratio, ratio from {0.7, 0.8, 0.9}          (:227-233)
     bandmiss  : int(ratio*C) whole bands zeroed, ratio from {0.1,0.2,0.3} (:275-284)
 
+    blur      : (optional fifth recipe) Gaussian blur, kernel size from {9, 15, 21}, sigma 0.3((k-1)/2 - 1) + 0.8, zero
+                padding (:91-108) — a second launch (``mphsir_gaussian_blur``) over the blur samples only
+
 The task id of a sample is the index of its degradation in the active ``de_type`` list, shape [B,1] (:140).
 """
 from __future__ import annotations
@@ -21,19 +24,25 @@ import torch
 
 from . import lib
 
-RECIPES = ("gaussianN", "complexN", "inpaint", "bandmiss")
-DE_RANGE = {"gaussianN": (30.0, 70.0), "complexN": (10.0, 30.0, 50.0, 70.0), "inpaint": (0.7, 0.8, 0.9), "bandmiss": (0.1, 0.2, 0.3)}
+RECIPES = ("gaussianN", "complexN", "inpaint", "bandmiss")          # the default set (one elementwise launch)
+ALL_RECIPES = RECIPES + ("blur",)                                    # + recipes that need their own kernel
+DE_RANGE = {"gaussianN": (30.0, 70.0), "complexN": (10.0, 30.0, 50.0, 70.0), "inpaint": (0.7, 0.8, 0.9), "bandmiss": (0.1, 0.2, 0.3),
+            "blur": (9, 15, 21)}
 
 
-def draw_parameters(B: int, C: int, de_types: Sequence[str] = RECIPES, generator: Optional[torch.Generator] = None):
+def draw_parameters(B: int, C: int, de_types: Sequence[str] = RECIPES, generator: Optional[torch.Generator] = None,
+                    with_blur: bool = False):
     """Host-side draws of one degradation per sample -> (task_id [B,1] int64, sigma [B,C], keep [B,C], mask_ratio [B]);
-    a few hundred bytes and a dozen vectorised torch calls, the only per-step host work."""
+    a few hundred bytes and a dozen vectorised torch calls, the only per-step host work.  with_blur: a fifth element, the
+    Gaussian-blur kernel size per sample (int32 [B], 0 = not a blur sample)."""
     g = generator
     for k in de_types:
-        if k not in RECIPES:
-            raise ValueError(f"{k!r} is not an array-only recipe ({RECIPES})")
+        if k not in ALL_RECIPES:
+            raise ValueError(f"{k!r} is not an array-only recipe ({ALL_RECIPES})")
+    if "blur" in de_types and not with_blur:
+        raise ValueError("the 'blur' recipe needs with_blur=True (its kernel sizes are a fifth return value)")
     tid = torch.randint(0, len(de_types), (B, 1), generator=g)
-    code = torch.tensor([RECIPES.index(k) for k in de_types])[tid[:, 0]]          # recipe of every sample
+    code = torch.tensor([ALL_RECIPES.index(k) for k in de_types])[tid[:, 0]]      # recipe of every sample
     r = DE_RANGE
     # gaussianN: sigma = U(30, 70) / 255 for the whole cube (degradation_utils.py:26-27)
     sig_g = (r["gaussianN"][0] + (r["gaussianN"][1] - r["gaussianN"][0]) * torch.rand(B, generator=g)) / 255.0
@@ -49,6 +58,11 @@ def draw_parameters(B: int, C: int, de_types: Sequence[str] = RECIPES, generator
     n_lost = (pct * C).floor().to(torch.int64)
     order = torch.rand(B, C, generator=g).argsort(dim=1).argsort(dim=1)          # a random permutation rank per band
     keep = ((order >= n_lost[:, None]) | (code != 3)[:, None]).to(torch.float32)
+    if with_blur:
+        # blur: kernel size from the list (dataset_utils.py:112 'blur': [(9, 15, 21)]); blur samples pass the elementwise kernel unchanged
+        ks = torch.tensor(r["blur"], dtype=torch.int32)[torch.randint(0, len(r["blur"]), (B,), generator=g)]
+        ksize = torch.where(code == 4, ks, torch.zeros(B, dtype=torch.int32))
+        return tid, sigma.contiguous(), keep.contiguous(), ratio.contiguous(), ksize.contiguous()
     return tid, sigma.contiguous(), keep.contiguous(), ratio.contiguous()
 
 
@@ -66,8 +80,27 @@ def degrade(clean: torch.Tensor, sigma: torch.Tensor, keep: torch.Tensor, mask_r
     return out
 
 
+def gaussian_blur(clean: torch.Tensor, ksize: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Gaussian-blur the samples with ksize[b] > 0 (utils/degradation_utils.py:91-108); other samples of `out` keep their content
+    (a fresh `out` starts as a copy of `clean`)."""
+    if not clean.is_cuda:
+        raise RuntimeError("mp_hsir_b200.degrade runs on a CUDA device via libmphsir.so; there is no CPU fallback")
+    c = clean.detach().float().contiguous()
+    if out is None:
+        out = c.clone()
+    kmax = int(ksize.max()) if ksize.numel() else 0
+    if kmax > 0:
+        with torch.cuda.device(c.device):
+            lib.gaussian_blur(c, out, ksize.to(device=c.device, dtype=torch.int32).contiguous(), kmax)
+    return out
+
+
 def degrade_batch(clean: torch.Tensor, seed: int, de_types: Sequence[str] = RECIPES,
                   generator: Optional[torch.Generator] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """(degraded [B,C,H,W], task_id [B,1]) for a clean device batch — what the DataLoader's collate hands train.py:50-58."""
+    if "blur" in de_types:
+        tid, sigma, keep, ratio, ksize = draw_parameters(clean.shape[0], clean.shape[1], de_types, generator, with_blur=True)
+        out = degrade(clean, sigma, keep, ratio, seed)          # blur samples leave this pass as copies of the clean patch
+        return gaussian_blur(clean, ksize, out=out), tid
     tid, sigma, keep, ratio = draw_parameters(clean.shape[0], clean.shape[1], de_types, generator)
     return degrade(clean, sigma, keep, ratio, seed), tid

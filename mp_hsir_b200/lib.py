@@ -180,6 +180,7 @@ SIGNATURES = {
     "mphsir_psnr_ssim": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),
     "mphsir_plane_nonzero": (_I, [_VP, _I, _LL, _VP, _VP]),
     "mphsir_degrade": (_I, [_VP, _VP, _I, _I, _LL, _VP, _VP, _VP, C.c_ulonglong, _VP]),
+    "mphsir_gaussian_blur": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
     "mphsir_adamw_step": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _I, _F, _VP, _VP]),
 }
 
@@ -848,6 +849,17 @@ def plane_nonzero(x: torch.Tensor) -> torch.Tensor:
     _launch("plane_nonzero", lambda: load().mphsir_plane_nonzero(xx.data_ptr(), B * Cc, H * W, out.data_ptr(), stream_ptr()),
             lambda: (0.0, 4.0 * xx.numel(), "plane_nonzero"))
     return out
+
+
+def gaussian_blur(x: torch.Tensor, out: torch.Tensor, ksize: torch.Tensor, kmax: int) -> None:
+    """out[b] = every band of x[b] blurred with the k x k Gaussian of utils/degradation_utils.py:91-108 where ksize[b] > 0;
+    other samples' planes of `out` are left as they are.  ksize: int32 [B] on the device."""
+    B, Cc, H, W = x.shape
+    assert x.is_contiguous() and out.is_contiguous() and out.shape == x.shape and x.dtype == torch.float32
+    assert ksize.dtype == torch.int32 and ksize.numel() == B and ksize.is_cuda
+    _launch("gaussian_blur", lambda: load().mphsir_gaussian_blur(x.data_ptr(), out.data_ptr(), ksize.data_ptr(), B, Cc, H, W, kmax,
+                                                                 stream_ptr()),
+            lambda: (0.0, 8.0 * x.numel(), "gaussian_blur"))
 
 
 def degrade(clean: torch.Tensor, out: torch.Tensor, sigma: torch.Tensor, keep: torch.Tensor, mask_ratio: torch.Tensor,

@@ -92,3 +92,25 @@ def degrade(clean: np.ndarray, sigma: np.ndarray, keep: np.ndarray, mask_ratio: 
     m = (um.astype(np.float32) > mask_ratio.astype(np.float32).reshape(B, 1, 1, 1)).astype(np.float64)
     out = clean.astype(np.float64) * keep.reshape(B, C, 1, 1) * m + sigma.reshape(B, C, 1, 1).astype(np.float64) * n
     return out, um, n
+
+
+def gaussian_blur(clean: np.ndarray, kernel_size: int) -> np.ndarray:
+    """utils/degradation_utils.py:91-108 (_apply_gaussian_blur), restated: depthwise conv of a [C,H,W] cube with the outer
+    product of a normalised 1-D Gaussian (sigma = 0.3 ((k-1)/2 - 1) + 0.8, fp32 like the reference), zero padding k // 2.
+    Written as explicit shifted sums in float64, so it does not share code with either implementation under test."""
+    k = int(kernel_size)
+    sigma = np.float32(0.3) * (np.float32(k - 1) * np.float32(0.5) - np.float32(1.0)) + np.float32(0.8)
+    x = np.arange(k, dtype=np.float32)
+    mean = np.float32(k - 1) / np.float32(2)
+    k1 = np.exp(-((x - mean) ** 2) / (np.float32(2) * sigma ** 2)).astype(np.float32)
+    k1 = (k1 / k1.sum(dtype=np.float32)).astype(np.float32)
+    k2 = (k1[None, :] * k1[:, None]).astype(np.float64)          # kernel_2d of the reference (fp32 product)
+    C, H, W = clean.shape
+    r = k // 2
+    pad = np.zeros((C, H + 2 * r, W + 2 * r), dtype=np.float64)
+    pad[:, r:r + H, r:r + W] = clean
+    out = np.zeros((C, H, W), dtype=np.float64)
+    for dy in range(k):
+        for dx in range(k):
+            out += k2[dy, dx] * pad[:, dy:dy + H, dx:dx + W]     # cross-correlation = F.conv2d
+    return out

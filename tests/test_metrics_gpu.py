@@ -72,3 +72,33 @@ def test_degrade_batch_follows_the_recipes():
         else:
             lost = noisy[b].abs().sum(dim=(1, 2)).cpu() == 0
             assert int(lost.sum()) in (3, 6, 9) and torch.equal(noisy[b].cpu()[~lost], c[b][~lost])
+
+
+@pytest.mark.gpu
+def test_gaussian_blur_matches_oracle():
+    """mphsir_gaussian_blur vs the CPU restatement of utils/degradation_utils.py:91-108: every kernel size of the reference's
+    de_dict, a non-square plane that is not a multiple of the 32 x 32 tile, samples with ksize 0 untouched"""
+    from mp_hsir_b200.degrade import gaussian_blur
+    clean = synthetic_input((6, 5, 72, 50), seed=4)
+    ksize = torch.tensor([9, 0, 15, 21, 7, 11], dtype=torch.int32)
+    out = torch.full_like(clean, 7.0).cuda()
+    gaussian_blur(clean.cuda(), ksize, out=out)
+    out = out.cpu().numpy()
+    for b in range(6):
+        k = int(ksize[b])
+        if k == 0:
+            assert (out[b] == 7.0).all()
+        else:
+            ref = M.gaussian_blur(clean[b].numpy(), k)
+            assert abs(out[b] - ref).max() < 2e-6
+
+
+@pytest.mark.gpu
+def test_degrade_batch_with_blur_recipe():
+    from mp_hsir_b200.degrade import ALL_RECIPES
+    clean = synthetic_input((16, 31, 64, 64), seed=5).cuda()
+    noisy, tid = degrade_batch(clean, seed=9, de_types=ALL_RECIPES, generator=torch.Generator().manual_seed(6))
+    assert 4 in tid.view(-1).tolist()
+    for b in range(16):
+        if int(tid[b, 0]) == 4:   # blurred: smoother than the clean patch, same mean to a few percent
+            assert float(noisy[b].var()) < float(clean[b].var()) and abs(float(noisy[b].mean() - clean[b].mean())) < 0.05

@@ -1,6 +1,7 @@
 """CPU: the oracle restatements behind the metric / degradation kernels (oracle/metrics_oracle.py) against published
 known answers and defining properties."""
 import numpy as np
+import pytest
 import torch
 
 from mp_hsir_b200.degrade import DE_RANGE, RECIPES, draw_parameters
@@ -86,3 +87,38 @@ def test_parameter_draws_follow_the_reference_ranges():
         else:
             lost = int((keep[b] == 0).sum())
             assert lost in {int(p * 31) for p in DE_RANGE["bandmiss"]} and torch.all(sigma[b] == 0) and ratio[b] < 0
+
+
+def test_gaussian_blur_oracle_matches_the_reference_formula():
+    """oracle gaussian_blur (explicit shifted sums) == the reference's own lines (utils/degradation_utils.py:91-108: F.conv2d with
+    the outer-product kernel), re-enacted verbatim here because the module itself imports cv2 / skimage / matplotlib"""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(0)
+    clean = rng.random((5, 40, 36), dtype=np.float32)
+    for kernel_size in (9, 15, 21, 7, 11):
+        sigma = 0.3 * ((kernel_size - 1) * 0.5 - 1) + 0.8
+        x = torch.arange(kernel_size, dtype=torch.float32)
+        mean = (kernel_size - 1) / 2
+        kernel_1d = torch.exp(-((x - mean) ** 2) / (2 * sigma ** 2))
+        kernel_1d = kernel_1d / kernel_1d.sum()
+        kernel_2d = (kernel_1d.unsqueeze(0) * kernel_1d.unsqueeze(1)).unsqueeze(0)
+        inp = torch.from_numpy(clean).float().unsqueeze(0)
+        ref = F.conv2d(inp, kernel_2d.repeat(inp.shape[1], 1, 1, 1), padding=kernel_size // 2, stride=1, groups=inp.shape[1])[0].numpy()
+        got = M.gaussian_blur(clean, kernel_size)
+        assert got.shape == ref.shape and np.abs(got - ref).max() < 2e-6
+        # a blur preserves the mean of the interior and flattens: variance strictly drops
+        assert got.var() < clean.var()
+
+
+def test_blur_parameter_draws():
+    from mp_hsir_b200.degrade import ALL_RECIPES
+    g = torch.Generator().manual_seed(1)
+    tid, sigma, keep, ratio, ksize = draw_parameters(64, 31, ALL_RECIPES, g, with_blur=True)
+    assert ksize.dtype == torch.int32 and set(tid.view(-1).tolist()) == {0, 1, 2, 3, 4}
+    for b in range(64):
+        if ALL_RECIPES[int(tid[b, 0])] == "blur":
+            assert int(ksize[b]) in DE_RANGE["blur"] and torch.all(sigma[b] == 0) and torch.all(keep[b] == 1) and ratio[b] < 0
+        else:
+            assert int(ksize[b]) == 0
+    with pytest.raises(ValueError):
+        draw_parameters(4, 31, ALL_RECIPES, g)
