@@ -497,6 +497,12 @@ MPHSIR_API int mphsir_plane_nonzero(const float* X, int planes, long long hw, in
 MPHSIR_API int mphsir_degrade(const float* clean, float* out, int B, int C, long long hw, const float* sigma /* [B*C] */,
                               const float* keep /* [B*C] */, const float* mask_ratio /* [B] */, unsigned long long seed,
                               void* stream);
+/* The structured half of 'complexN' (utils/degradation_utils.py:296-316), in place after mphsir_degrade, for the samples with
+ * active[b] != 0:  x = x * colmul[b,c,col] + coladd[b,c,col]  (deadline columns: colmul 0, :57-68; stripes: coladd = -offset, :41-55),
+ * then with probability impulse[b,c] a pixel becomes 1 (salt, half of the flips) or 0 (pepper) (:70-84); the per-pixel decisions
+ * come from the Philox4x32-10 stream keyed by `seed` with counter word 2 = 1.  colmul / coladd [B*C*W], impulse [B*C], active [B]. */
+MPHSIR_API int mphsir_degrade_structured(float* x, int B, int C, int H, int W, const float* colmul, const float* coladd,
+                                         const float* impulse, const int* active, unsigned long long seed, void* stream);
 /* Gaussian blur degradation (utils/degradation_utils.py:91-108): every band of sample b with ksize[b] > 0 (odd, <= 21; device
  * int array [B]) is convolved with the k x k outer product of the normalised 1-D Gaussian of sigma 0.3((k-1)/2 - 1) + 0.8,
  * zero padding k/2; planes of samples with ksize[b] == 0 are not touched.  kmax >= every ksize[b] (validated on the host). */

@@ -167,6 +167,49 @@ __global__ void __launch_bounds__(256) degrade_kernel(const float* __restrict__ 
 
 
 // ---------------------------------------------------------------------------------------------
+// The structured half of 'complexN' (utils/degradation_utils.py:296-316: after the non-iid Gaussian noise ONE of deadline /
+// impulse / stripe noise on a third of the bands), in place on the output of degrade_kernel:
+//   deadline (:57-68)  columns of a band set to zero          -> colmul[b,c,x] = 0
+//   stripe   (:41-55)  a per-column offset subtracted          -> coladd[b,c,x] = -stripe
+//   impulse  (:70-84)  pixels flipped with probability p to 1 (salt, probability 1/2) or 0 (pepper) -> impulse[b,c] = p
+// Which bands / columns / amounts is drawn by the host like the reference draws it (a few KB); the per-pixel impulse
+// decisions come from a second Philox4x32-10 stream (counter word 2 = 1) so they are independent of the first pass.
+// Samples with active[b] == 0 are skipped.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) degrade_structured_kernel(float* __restrict__ x, long long total, int C, int H, int W,
+                                                                 const float* __restrict__ colmul, const float* __restrict__ coladd,
+                                                                 const float* __restrict__ impulse, const int* __restrict__ active,
+                                                                 uint32_t seed_lo, uint32_t seed_hi) {
+  const long long hw = (long long)H * W;
+  const long long pairs = (total + 1) / 2;
+  for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < pairs; q += (long long)gridDim.x * 256) {
+    uint32_t w[4];
+    bool drawn = false;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long e = 2 * q + h;
+      if (e >= total) break;
+      const long long bc = e / hw;
+      const int b = (int)(bc / C);
+      if (__ldg(active + b) == 0) continue;
+      const int xcol = (int)((e - bc * hw) % W);
+      float v = x[e] * __ldg(colmul + bc * W + xcol) + __ldg(coladd + bc * W + xcol);
+      const float pflip = __ldg(impulse + bc);
+      if (pflip > 0.f) {
+        if (!drawn) {
+          philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), 1u, 0u, seed_lo, seed_hi, w);
+          drawn = true;
+        }
+        const float uf = (float)((h == 0 ? w[0] : w[2]) >> 8) * (1.0f / 16777216.0f);
+        const float us = (float)((h == 0 ? w[1] : w[3]) >> 8) * (1.0f / 16777216.0f);
+        if (uf < pflip) v = us < 0.5f ? 1.f : 0.f;
+      }
+      x[e] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Gaussian blur degradation (utils/degradation_utils.py:91-108): depthwise conv of every band with the outer product of a
 // normalised 1-D Gaussian, sigma = 0.3 ((k - 1) / 2 - 1) + 0.8, zero padding k / 2.  One CTA per (plane, 32 x 32 tile): the
 // haloed tile is staged in shared memory, a horizontal pass writes a [32 + k - 1][32] strip, a vertical pass the output —
@@ -281,4 +324,15 @@ extern "C" int mphsir_gaussian_blur(const float* in, float* out, const int* ksiz
   metrics::gaussian_blur_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, out, ksize, C, H, W, tiles_x,
                                                                                                     tiles_x * tiles_y);
   return check_launch("gaussian_blur");
+}
+
+extern "C" int mphsir_degrade_structured(float* x, int B, int C, int H, int W, const float* colmul, const float* coladd,
+                                         const float* impulse, const int* active, unsigned long long seed, void* stream) {
+  MPHSIR_REQUIRE(x && colmul && coladd && impulse && active && B > 0 && C > 0 && H > 0 && W > 0, "degrade_structured: bad arguments");
+  const long long total = (long long)B * C * H * W;
+  long long blocks = ((total + 1) / 2 + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  metrics::degrade_structured_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, total, C, H, W, colmul, coladd, impulse, active, (uint32_t)(seed & 0xFFFFFFFFull), (uint32_t)(seed >> 32));
+  return check_launch("degrade_structured");
 }

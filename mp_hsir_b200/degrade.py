@@ -11,6 +11,9 @@ the B*C*H*W random numbers come from a counter-based Philox4x32-10 stream inside
     inpaint   : rand(C,H,W) > ratio, ratio from {0.7, 0.8, 0.9}          (:227-233)
     bandmiss  : int(ratio*C) whole bands zeroed, ratio from {0.1,0.2,0.3} (:275-284)
 
+    complexN (complete, ``complex_full=True``): after the non-iid Gaussian noise ONE of deadline / impulse / stripe noise on a
+                third of the bands (:296-316, :41-84) — drawn per sample on the host (band choice, column positions, amounts; a
+                few KB) and applied by a second in-place launch (``mphsir_degrade_structured``)
     blur      : (optional fifth recipe) Gaussian blur, kernel size from {9, 15, 21}, sigma 0.3((k-1)/2 - 1) + 0.8, zero
                 padding (:91-108) — a second launch (``mphsir_gaussian_blur``) over the blur samples only
 
@@ -66,6 +69,47 @@ def draw_parameters(B: int, C: int, de_types: Sequence[str] = RECIPES, generator
     return tid, sigma.contiguous(), keep.contiguous(), ratio.contiguous()
 
 
+def draw_structured(code: torch.Tensor, C: int, W: int, generator: Optional[torch.Generator] = None):
+    """The structured half of complexN for the samples with code == 1 (utils/degradation_utils.py:296-316):
+    -> (colmul [B,C,W], coladd [B,C,W], impulse [B,C], active [B] int32).  Vectorised restatement of the reference's per-band
+    loops: a third of the bands (floor(C/3), a random subset: `np.random.permutation(B)[:num_bands]`), per chosen band n random
+    columns (`np.random.permutation(range(W))[:n]`) with n ~ randint(ceil(.05 W), ceil(.15 W)) for deadline (:61) and
+    randint(floor(.05 W), floor(.15 W)) for stripes (:48), stripe offsets U(0,1) * 0.5 - 0.25 subtracted (:52-53), impulse
+    amount from (0.1, 0.3, 0.5, 0.7) (:302, dataset_utils.py:112)."""
+    import math
+    g = generator
+    B = code.numel()
+    is_c = code == 1
+    ctype = torch.randint(0, 3, (B,), generator=g)                                   # 0 deadline, 1 impulse, 2 stripe (:304)
+    band_rank = torch.rand(B, C, generator=g).argsort(dim=1).argsort(dim=1)
+    band_sel = band_rank < (C // 3)                                                  # floor(1/3 * B) bands
+    col_rank = torch.rand(B, C, W, generator=g).argsort(dim=2).argsort(dim=2)        # a random permutation rank per column
+    lo_d, hi_d = math.ceil(0.05 * W), math.ceil(0.15 * W)
+    lo_s, hi_s = math.floor(0.05 * W), math.floor(0.15 * W)
+    n_dead = torch.randint(lo_d, max(hi_d, lo_d + 1), (B, C), generator=g)
+    n_stripe = torch.randint(lo_s, max(hi_s, lo_s + 1), (B, C), generator=g)
+    dead = (col_rank < n_dead[:, :, None]) & band_sel[:, :, None] & (is_c & (ctype == 0))[:, None, None]
+    stripe = (col_rank < n_stripe[:, :, None]) & band_sel[:, :, None] & (is_c & (ctype == 2))[:, None, None]
+    offs = torch.rand(B, C, W, generator=g) * 0.5 - 0.25
+    colmul = (~dead).to(torch.float32)
+    coladd = torch.where(stripe, -offs, torch.zeros(()))
+    amount = torch.tensor((0.1, 0.3, 0.5, 0.7))[torch.randint(0, 4, (B,), generator=g)]
+    impulse = torch.where(band_sel & (is_c & (ctype == 1))[:, None], amount[:, None].expand(B, C), torch.zeros(()))
+    return colmul.contiguous(), coladd.contiguous(), impulse.contiguous(), is_c.to(torch.int32).contiguous()
+
+
+def degrade_structured(x: torch.Tensor, colmul: torch.Tensor, coladd: torch.Tensor, impulse: torch.Tensor, active: torch.Tensor,
+                       seed: int) -> torch.Tensor:
+    """in place on the device batch x (the output of `degrade`): deadline / stripe / impulse noise of the active samples"""
+    if not x.is_cuda:
+        raise RuntimeError("mp_hsir_b200.degrade runs on a CUDA device via libmphsir.so; there is no CPU fallback")
+    dev = x.device
+    f = lambda t: t.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()  # noqa: E731
+    with torch.cuda.device(dev):
+        lib.degrade_structured(x, f(colmul), f(coladd), f(impulse), active.to(device=dev, dtype=torch.int32).contiguous(), seed)
+    return x
+
+
 def degrade(clean: torch.Tensor, sigma: torch.Tensor, keep: torch.Tensor, mask_ratio: torch.Tensor, seed: int,
             out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """clean [B,C,H,W] fp32 on the device -> degraded batch (one libmphsir launch); parameters may live on the host."""
@@ -96,11 +140,19 @@ def gaussian_blur(clean: torch.Tensor, ksize: torch.Tensor, out: Optional[torch.
 
 
 def degrade_batch(clean: torch.Tensor, seed: int, de_types: Sequence[str] = RECIPES,
-                  generator: Optional[torch.Generator] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """(degraded [B,C,H,W], task_id [B,1]) for a clean device batch — what the DataLoader's collate hands train.py:50-58."""
+                  generator: Optional[torch.Generator] = None, complex_full: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(degraded [B,C,H,W], task_id [B,1]) for a clean device batch — what the DataLoader's collate hands train.py:50-58.
+    complex_full: complexN samples also get their deadline / impulse / stripe half (one more in-place launch)."""
+    B, C, W = clean.shape[0], clean.shape[1], clean.shape[3]
+    ksize = None
     if "blur" in de_types:
-        tid, sigma, keep, ratio, ksize = draw_parameters(clean.shape[0], clean.shape[1], de_types, generator, with_blur=True)
-        out = degrade(clean, sigma, keep, ratio, seed)          # blur samples leave this pass as copies of the clean patch
-        return gaussian_blur(clean, ksize, out=out), tid
-    tid, sigma, keep, ratio = draw_parameters(clean.shape[0], clean.shape[1], de_types, generator)
-    return degrade(clean, sigma, keep, ratio, seed), tid
+        tid, sigma, keep, ratio, ksize = draw_parameters(B, C, de_types, generator, with_blur=True)
+    else:
+        tid, sigma, keep, ratio = draw_parameters(B, C, de_types, generator)
+    out = degrade(clean, sigma, keep, ratio, seed)              # blur samples leave this pass as copies of the clean patch
+    if complex_full and "complexN" in de_types:
+        code = torch.tensor([ALL_RECIPES.index(k) for k in de_types])[tid[:, 0]]
+        degrade_structured(out, *draw_structured(code, C, W, generator), seed=seed)
+    if ksize is not None:
+        gaussian_blur(clean, ksize, out=out)
+    return out, tid

@@ -181,6 +181,7 @@ SIGNATURES = {
     "mphsir_plane_nonzero": (_I, [_VP, _I, _LL, _VP, _VP]),
     "mphsir_degrade": (_I, [_VP, _VP, _I, _I, _LL, _VP, _VP, _VP, C.c_ulonglong, _VP]),
     "mphsir_gaussian_blur": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
+    "mphsir_degrade_structured": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, C.c_ulonglong, _VP]),
     "mphsir_adamw_step": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _I, _F, _VP, _VP]),
 }
 
@@ -849,6 +850,18 @@ def plane_nonzero(x: torch.Tensor) -> torch.Tensor:
     _launch("plane_nonzero", lambda: load().mphsir_plane_nonzero(xx.data_ptr(), B * Cc, H * W, out.data_ptr(), stream_ptr()),
             lambda: (0.0, 4.0 * xx.numel(), "plane_nonzero"))
     return out
+
+
+def degrade_structured(x: torch.Tensor, colmul: torch.Tensor, coladd: torch.Tensor, impulse: torch.Tensor, active: torch.Tensor,
+                       seed: int) -> None:
+    """in place: x = x * colmul[b,c,col] + coladd[b,c,col], then impulse flips (utils/degradation_utils.py:41-84) for active samples"""
+    B, Cc, H, W = x.shape
+    assert x.is_contiguous() and x.dtype == torch.float32 and colmul.numel() == B * Cc * W and coladd.numel() == B * Cc * W
+    assert impulse.numel() == B * Cc and active.numel() == B and active.dtype == torch.int32
+    _launch("degrade_structured", lambda: load().mphsir_degrade_structured(x.data_ptr(), B, Cc, H, W, colmul.data_ptr(), coladd.data_ptr(),
+                                                                           impulse.data_ptr(), active.data_ptr(),
+                                                                           seed & 0xFFFFFFFFFFFFFFFF, stream_ptr()),
+            lambda: (0.0, 8.0 * x.numel(), "degrade_structured"))
 
 
 def gaussian_blur(x: torch.Tensor, out: torch.Tensor, ksize: torch.Tensor, kmax: int) -> None:

@@ -58,13 +58,13 @@ def compute_psnr_ssim2(recovered: np.ndarray, clean: np.ndarray, degrad: np.ndar
     return (ps / count, ss / count, count) if count else (0, 0, 0)
 
 
-def philox4x32_10(counter: np.ndarray, seed: int) -> np.ndarray:
-    """counter: uint64 array [n] -> uint32 [n, 4]; counter words (lo, hi, 0, 0), key (seed lo, seed hi)."""
+def philox4x32_10(counter: np.ndarray, seed: int, word2: int = 0) -> np.ndarray:
+    """counter: uint64 array [n] -> uint32 [n, 4]; counter words (lo, hi, word2, 0), key (seed lo, seed hi)."""
     M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
     mask = np.uint64(0xFFFFFFFF)
     c0 = counter & mask
     c1 = counter >> np.uint64(32)
-    c2 = np.zeros_like(c0)
+    c2 = np.full_like(c0, np.uint64(word2))
     c3 = np.zeros_like(c0)
     k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
     for _ in range(10):
@@ -114,3 +114,21 @@ def gaussian_blur(clean: np.ndarray, kernel_size: int) -> np.ndarray:
         for dx in range(k):
             out += k2[dy, dx] * pad[:, dy:dy + H, dx:dx + W]     # cross-correlation = F.conv2d
     return out
+
+
+def degrade_structured(x: np.ndarray, colmul: np.ndarray, coladd: np.ndarray, impulse: np.ndarray, active: np.ndarray, seed: int):
+    """utils/degradation_utils.py:41-84 on [B,C,H,W]: deadline columns (colmul 0), stripes (coladd), impulse flips with probability
+    impulse[b,c] (salt with probability 1/2) from the Philox stream with counter word 2 = 1; inactive samples untouched."""
+    B, C, H, W = x.shape
+    total = x.size
+    pairs = (total + 1) // 2
+    w = philox4x32_10(np.arange(pairs, dtype=np.uint64), seed, word2=1).astype(np.float64)
+    f = lambda v: np.floor(v / 256.0) / 16777216.0          # noqa: E731
+    uf = np.stack([f(w[:, 0]), f(w[:, 2])], axis=1).reshape(-1)[:total].reshape(B, C, H, W).astype(np.float32)
+    us = np.stack([f(w[:, 1]), f(w[:, 3])], axis=1).reshape(-1)[:total].reshape(B, C, H, W).astype(np.float32)
+    v = x.astype(np.float32) * colmul.reshape(B, C, 1, W).astype(np.float32) + coladd.reshape(B, C, 1, W).astype(np.float32)
+    p = impulse.reshape(B, C, 1, 1).astype(np.float32)
+    flip = (uf < p) & (p > 0)
+    v = np.where(flip, np.where(us < np.float32(0.5), np.float32(1), np.float32(0)), v)
+    act = active.reshape(B, 1, 1, 1) != 0
+    return np.where(act, v, x.astype(np.float32))

@@ -102,3 +102,29 @@ def test_degrade_batch_with_blur_recipe():
     for b in range(16):
         if int(tid[b, 0]) == 4:   # blurred: smoother than the clean patch, same mean to a few percent
             assert float(noisy[b].var()) < float(clean[b].var()) and abs(float(noisy[b].mean() - clean[b].mean())) < 0.05
+
+
+@pytest.mark.gpu
+def test_degrade_structured_matches_oracle_stream():
+    from mp_hsir_b200.degrade import degrade_structured, draw_structured
+    B, C, H, W = 6, 9, 24, 40
+    x = synthetic_input((B, C, H, W), seed=3)
+    code = torch.tensor([1, 1, 0, 1, 1, 1])
+    colmul, coladd, impulse, active = draw_structured(code, C, W, torch.Generator().manual_seed(8))
+    got = degrade_structured(x.clone().cuda(), colmul, coladd, impulse, active, seed=0xABCDEF0123).cpu().numpy()
+    ref = M.degrade_structured(x.numpy(), colmul.numpy(), coladd.numpy(), impulse.numpy(), active.numpy(), seed=0xABCDEF0123)
+    assert np.array_equal(got, ref)          # integer decisions + one fp32 multiply-add: bit exact
+    assert np.array_equal(got[2], x[2].numpy())
+
+
+@pytest.mark.gpu
+def test_degrade_batch_complex_full():
+    clean = synthetic_input((24, 31, 64, 64), seed=6).cuda()
+    noisy, tid = degrade_batch(clean, seed=5, generator=torch.Generator().manual_seed(2), complex_full=True)
+    plain, tid2 = degrade_batch(clean, seed=5, generator=torch.Generator().manual_seed(2))
+    assert torch.equal(tid, tid2)
+    for b in range(24):
+        if int(tid[b, 0]) == 1:
+            assert not torch.equal(noisy[b], plain[b])       # the structured half changed something
+        else:
+            assert torch.equal(noisy[b], plain[b])
