@@ -52,17 +52,33 @@ constexpr int MAX_RING = 8;
 // p.rev: the launch walks its work items from the last to the first.  Activations at 512 x 512 are slightly larger than the
 // L2 (134 MB per 128-channel tensor against 126 MB): a consumer that starts where its producer STOPPED finds the most
 // recently written part still on chip, while two kernels walking in the same direction evict everything just before it is read.
+__device__ __forceinline__ int tc_items(const TcArgs& p) { return p.n_full + (p.num_tiles - p.n_full) * p.psplit; }
 __device__ __forceinline__ int tc_order(const TcArgs& p, int vt) {
-  const int n = p.num_tiles * p.psplit;
+  const int n = tc_items(p);
   return (p.rev && vt < n) ? n - 1 - vt : vt;
 }
 
-// Work item `vt` of a launch = (row tile, range of 256-column passes [p0, p1)): vt = tile * psplit + group.
-#define TC_WORK_ITEM(vt)                                               \
-  const int vtr_ = tc_order(p, (vt));                                  \
-  const int tile = vtr_ / p.psplit;                                    \
-  const int p0 = (vtr_ - tile * p.psplit) * p.ppg;                     \
-  const int p1 = min(npass, p0 + p.ppg);                               \
+// Work item `vt` of a launch = (row tile, range of 256-column passes [p0, p1)).  The first n_full items are whole row tiles; the
+// remaining tiles are cut into `psplit` pass groups each (item = n_full + (tile - n_full) * psplit + group): either ALL tiles of a
+// few-tile launch (n_full = 0), or the tiles of the last, partly filled round of a many-tile launch, so that the round costs
+// a fraction of a tile time instead of a whole one.
+__device__ __forceinline__ void tc_decode(const TcArgs& p, int npass, int vt, int& tile, int& p0, int& p1) {
+  const int w = tc_order(p, vt);
+  if (w < p.n_full) {
+    tile = w;
+    p0 = 0;
+    p1 = npass;
+  } else {
+    const int idx = w - p.n_full;
+    const int t = idx / p.psplit;
+    tile = p.n_full + t;
+    p0 = (idx - t * p.psplit) * p.ppg;
+    p1 = min(npass, p0 + p.ppg);
+  }
+}
+#define TC_WORK_ITEM(vt)                 \
+  int tile, p0, p1;                      \
+  tc_decode(p, npass, (vt), tile, p0, p1); \
   (void)p0; (void)p1
 
 struct Smem {
@@ -110,14 +126,16 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t*
 
   auto ncols_of = [&](int pass) { return min(PASS_COLS, p.Np - pass * PASS_COLS); };
   // next chunk of this warp after (tile, tit, pass, c0); false when the CTA's work is finished
-  auto p0_of = [&](int vt) { const int w = tc_order(p, vt); return (w - (w / p.psplit) * p.psplit) * p.ppg; };
+  auto p0_of = [&](int vt) { int t_, a_, b_; tc_decode(p, npass, vt, t_, a_, b_); return a_; };
+  auto p1_of = [&](int vt) { int t_, a_, b_; tc_decode(p, npass, vt, t_, a_, b_); return b_; };
+  auto tile_of = [&](int vt) { int t_, a_, b_; tc_decode(p, npass, vt, t_, a_, b_); return t_; };
   auto advance = [&](int& vt, int& tit, int& pass, int& c0) -> bool {
     c0 += 64;
     for (;;) {
       if (c0 < ncols_of(pass)) return true;
       ++pass;
       c0 = half * 32;
-      if (pass >= min(npass, p0_of(vt) + p.ppg)) {
+      if (pass >= p1_of(vt)) {
         vt += gridDim.x;
         ++tit;
         if (tit >= p.iters || vt - crank >= num_tiles) return false;
@@ -137,7 +155,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t*
   };
   auto issue_res = [&](int vt, int pass, int c0, int slot) {  // lane 0 only
     int b, row0;
-    tile_coord(tc_order(p, vt) / p.psplit, b, row0);
+    tile_coord(tile_of(vt), b, row0);
     mbar_expect_tx(rbar0 + 8 * slot, 4096);
     tma_load_3d(slot_a0 + 4096 * slot, &p.tmR, pass * PASS_COLS + c0, row0, b, rbar0 + 8 * slot);
   };
@@ -311,7 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   tc_fence_after();
   pdl_wait();  // everything above overlapped the predecessor's tail; from here on its results are read / its inputs overwritten
   const uint32_t tmem_base = sm->tmem_base;
-  const int num_tiles = p.num_tiles * p.psplit;   // work items (row tile x pass group)
+  const int num_tiles = tc_items(p);   // work items (whole row tiles + pass groups of the split tiles)
   const uint32_t crank = CG == 2 ? cluster_ctarank() : 0;
   constexpr bool pair = CG == 2;   // CTA pair: M = 256 MMAs (cta_group::2) issued by the leader (rank 0) for both tiles
 
@@ -1155,7 +1173,7 @@ void set_cluster_enabled(int on) { g_cluster_enabled = on; }
 void set_debug_buffer(long long* p) { g_dbg = p; }
 
 // How a launch is cut into work: pure host arithmetic (also exported as mphsir_gemm_plan for the CPU tests).
-struct WorkPlan { int cluster, psplit, ppg, grid, iters, rev; };
+struct WorkPlan { int cluster, psplit, ppg, grid, iters, rev, n_full; };
 static WorkPlan plan_work(int M, int Np, int ks, int num_tiles, int tiles_per_batch, bool per_sample_weights, int sm_count) {
   WorkPlan w{};
   // few-tile GEMMs (the 16 x 16 latent of a patch batch: 32-64 row tiles for 148 SMs): the 256-column passes of a row tile are
@@ -1163,11 +1181,24 @@ static WorkPlan plan_work(int M, int Np, int ks, int num_tiles, int tiles_per_ba
   const int npass = (Np + PASS_COLS - 1) / PASS_COLS;
   w.psplit = 1;
   w.ppg = npass;
-  if (g_psplit_enabled && npass >= 2 && num_tiles * 2 <= sm_count) {
-    int want = sm_count / num_tiles;
-    if (want > npass) want = npass;
-    w.ppg = (npass + want - 1) / want;
-    w.psplit = (npass + w.ppg - 1) / w.ppg;
+  w.n_full = num_tiles;
+  if (g_psplit_enabled && npass >= 2) {
+    int split_tiles = 0;
+    if (num_tiles * 2 <= sm_count) {
+      split_tiles = num_tiles;                         // few-tile launch: every tile is split
+    } else if (num_tiles > sm_count && num_tiles % sm_count != 0 && (num_tiles % sm_count) * 2 <= sm_count) {
+      // many-tile launch whose last round is at most half full (512 tiles on 148 SMs: 3 rounds + 68 tiles): its tiles are split
+      // so that the round costs about half a tile time (every item still converts the A slabs it needs)
+      split_tiles = num_tiles % sm_count;
+    }
+    if (split_tiles > 0) {
+      int want = sm_count / split_tiles;
+      if (want > npass) want = npass;
+      w.ppg = (npass + want - 1) / want;
+      w.psplit = (npass + w.ppg - 1) / w.ppg;
+      if (w.psplit > 1) w.n_full = num_tiles - split_tiles;
+      else w.ppg = npass;
+    }
   }
   // CTA pairs run tiles (2 q, 2 q + 1) on one M = 256 instruction stream: both tiles must use the same weights
   // (per-sample weights: an even number of tiles per sample).
@@ -1178,7 +1209,7 @@ static WorkPlan plan_work(int M, int Np, int ks, int num_tiles, int tiles_per_ba
   const bool tensor_heavy = nt_blocks >= 2 && ks * nt_blocks >= 16;
   w.cluster = (g_cluster_enabled && w.psplit == 1 && tensor_heavy && num_tiles >= 2 && Np % 16 == 0 &&
                (!per_sample_weights || tiles_per_batch % 2 == 0)) ? 2 : 1;
-  const int items = num_tiles * w.psplit;
+  const int items = w.n_full + (num_tiles - w.n_full) * w.psplit;
   w.grid = items < sm_count ? items : sm_count;
   if (w.cluster == 2) {
     w.grid = (w.grid + 1) & ~1;
@@ -1231,7 +1262,7 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
   }
   make_a_tensor_map(a, conv);
   const WorkPlan wp = plan_work(a.M, a.Np, a.ks, a.num_tiles, a.tiles_per_batch, a.b_batch_bytes != 0, sm_count);
-  a.psplit = wp.psplit; a.ppg = wp.ppg; a.cluster = wp.cluster; a.iters = wp.iters; a.rev = wp.rev;
+  a.psplit = wp.psplit; a.ppg = wp.ppg; a.cluster = wp.cluster; a.iters = wp.iters; a.rev = wp.rev; a.n_full = wp.n_full;
   const int grid = wp.grid;
   if (a.cluster == 2) a.nb *= 2;   // half-size weight slots: twice the ring depth in the same shared memory
   if (conv && a.epi == MPHSIR_EPI_BIAS) a.epi = TC_OUT_TOKENS;
@@ -1253,7 +1284,7 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
 
 GemmPlanOut gemm_plan(int M, int Np, int ks, int num_tiles, int tiles_per_batch, bool per_sample_weights, int sm_count) {
   const WorkPlan w = plan_work(M, Np, ks, num_tiles, tiles_per_batch, per_sample_weights, sm_count);
-  return GemmPlanOut{w.cluster, w.psplit, w.ppg, w.grid, w.iters, w.rev};
+  return GemmPlanOut{w.cluster, w.psplit, w.ppg, w.grid, w.iters, w.rev, w.n_full};
 }
 
 }  // namespace tc
@@ -1264,12 +1295,12 @@ using namespace mphsir;
 extern "C" MPHSIR_API void mphsir_debug_tc_counters(long long* buf) { tc::set_debug_buffer(buf); }
 extern "C" MPHSIR_API void mphsir_debug_tc_cluster(int enabled) { tc::set_cluster_enabled(enabled); }
 extern "C" MPHSIR_API void mphsir_debug_tc_psplit(int enabled) { tc::set_psplit_enabled(enabled); }
-extern "C" MPHSIR_API int mphsir_gemm_plan(int M, int N, int K, int rows_per_batch, int per_sample_weights, int sm_count, int* out6) {
+extern "C" MPHSIR_API int mphsir_gemm_plan(int M, int N, int K, int rows_per_batch, int per_sample_weights, int sm_count, int* out6) {   /* out6: 7 ints */
   if (M <= 0 || N <= 0 || K <= 0 || sm_count <= 0 || out6 == nullptr) return MPHSIR_ERR_INVALID;
   const int tpb = (per_sample_weights && rows_per_batch > 0) ? (rows_per_batch + 127) / 128 : 0;
   const int tiles = tpb > 0 ? (M / rows_per_batch) * tpb : (M + 127) / 128;
   const tc::GemmPlanOut w = tc::gemm_plan(M, (N + 15) / 16 * 16, (K + 63) / 64, tiles, tpb, per_sample_weights != 0, sm_count);
-  out6[0] = w.cluster; out6[1] = w.psplit; out6[2] = w.ppg; out6[3] = w.grid; out6[4] = w.iters; out6[5] = w.rev;
+  out6[0] = w.cluster; out6[1] = w.psplit; out6[2] = w.ppg; out6[3] = w.grid; out6[4] = w.iters; out6[5] = w.rev; out6[6] = w.n_full;
   return MPHSIR_OK;
 }
 extern "C" MPHSIR_API void mphsir_debug_tc_reverse(int enabled) { tc::set_tile_rev(enabled); }

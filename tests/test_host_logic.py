@@ -97,30 +97,44 @@ def test_synthetic_weights_are_name_seeded():
 def _gemm_plan(M, N, K, rows_per_batch=0, per_sample=0, sms=148):
     import ctypes
     from mp_hsir_b200 import lib
-    out = (ctypes.c_int * 6)()
+    out = (ctypes.c_int * 7)()
     assert lib.load().mphsir_gemm_plan(M, N, K, rows_per_batch, per_sample, sms, out) == 0
-    return dict(zip(("cluster", "psplit", "ppg", "grid", "iters", "rev"), out))
+    return dict(zip(("cluster", "psplit", "ppg", "grid", "iters", "rev", "n_full"), out))
 
 
-@pytest.mark.parametrize("M,N,K", [(262144, 384, 128), (65536, 512, 128), (16384, 768, 256), (4096, 1376, 256), (4096, 256, 688),
-                                   (8192, 1024, 256), (128, 64, 64), (300, 288, 96), (262144, 256, 1152), (4096, 512, 2304)])
+@pytest.mark.parametrize("M,N,K", [(262144, 384, 128), (65536, 512, 128), (65536, 384, 128), (16384, 768, 256), (4096, 1376, 256),
+                                   (4096, 256, 688), (8192, 1024, 256), (128, 64, 64), (300, 288, 96), (262144, 256, 1152),
+                                   (4096, 512, 2304), (65536, 128, 128), (19000, 512, 64)])
 def test_gemm_work_plan_covers_every_pass_exactly_once(M, N, K):
     """mphsir_gemm_plan (the host arithmetic of the tensor-core GEMM launcher, no device needed): every (row tile, 256-column
-    pass) belongs to exactly one work item, the grid fits the machine, pairs are even, few-tile launches are split."""
+    pass) belongs to exactly one work item, the grid fits the machine, pairs are even, few-tile launches and half-empty last
+    rounds are split."""
     pl = _gemm_plan(M, N, K)
     tiles, npass = (M + 127) // 128, ((N + 15) // 16 * 16 + 255) // 256
-    assert pl["cluster"] in (1, 2) and pl["psplit"] >= 1 and pl["ppg"] >= 1
-    # pass groups tile the pass range without gaps or overlap
-    covered = []
-    for g in range(pl["psplit"]):
-        covered += list(range(g * pl["ppg"], min(npass, (g + 1) * pl["ppg"])))
-    assert covered == list(range(npass))
-    items = tiles * pl["psplit"]
+    assert pl["cluster"] in (1, 2) and pl["psplit"] >= 1 and pl["ppg"] >= 1 and 0 <= pl["n_full"] <= tiles
+    # decode every work item exactly as the kernel does (gemm_tc.cu tc_decode) and count the (tile, pass) pairs
+    seen = {}
+    items = pl["n_full"] + (tiles - pl["n_full"]) * pl["psplit"]
+    for w in range(items):
+        if w < pl["n_full"]:
+            t, p0, p1 = w, 0, npass
+        else:
+            idx = w - pl["n_full"]
+            t = pl["n_full"] + idx // pl["psplit"]
+            p0 = (idx % pl["psplit"]) * pl["ppg"]
+            p1 = min(npass, p0 + pl["ppg"])
+        assert p1 > p0
+        for ps in range(p0, p1):
+            seen[(t, ps)] = seen.get((t, ps), 0) + 1
+    assert len(seen) == tiles * npass and set(seen.values()) == {1}
     assert 1 <= pl["grid"] <= 148 and pl["grid"] * pl["iters"] >= items > pl["grid"] * (pl["iters"] - 1) - (pl["cluster"] - 1)
     if pl["cluster"] == 2:
         assert pl["grid"] % 2 == 0 and pl["psplit"] == 1 and tiles >= 2
     if tiles * 2 <= 148 and npass >= 2:
-        assert pl["psplit"] >= 2, "few-tile launches hand the passes of a row tile to several CTAs"
+        assert pl["psplit"] >= 2 and pl["n_full"] == 0, "few-tile launches hand the passes of a row tile to several CTAs"
+    if tiles > 148 and 0 < tiles % 148 <= 74 and npass >= 2:
+        assert pl["psplit"] >= 2 and pl["n_full"] == tiles - tiles % 148, "a half-empty last round is split"
+        assert pl["iters"] == tiles // 148 + 1
     assert pl["rev"] == (1 if M >= 131072 else 0)
 
 
