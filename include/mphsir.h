@@ -122,8 +122,9 @@ MPHSIR_API void mphsir_debug_tc_counters(long long* buf);
 MPHSIR_API void mphsir_debug_tc_cluster(int enabled);
 MPHSIR_API void mphsir_debug_tc_reverse(int enabled);          /* 0: tensor-core GEMM launches never walk their row tiles backwards (default 1: launches over >= 131072 rows do — their input is then read starting with the part the producer wrote last, which is still in L2) */
 /* How mphsir_gemm_fwd (tensor-core precisions) cuts a [M,K] x [K,N] launch into work on a device with `sm_count` SMs — pure host
- * arithmetic, no device needed: out6[7] = {CTAs per cluster (2 = cta_group::2 pairs), pass groups per SPLIT row tile, passes per
- * group, grid size, work-item iterations per CTA, 1 if the tiles are walked backwards, number of leading row tiles that stay whole}. */
+ * arithmetic, no device needed: out6[8] = {CTAs per cluster (2 = cta_group::2 pairs), pass groups per SPLIT row tile, passes per
+ * group, grid size, work-item iterations per CTA, 1 if the tiles are walked backwards, number of leading row tiles that stay whole,
+ * accumulator columns per pass (256 or 128)}. */
 MPHSIR_API int mphsir_gemm_plan(int M, int N, int K, int rows_per_batch, int per_sample_weights, int sm_count, int* out6);
 MPHSIR_API void mphsir_debug_tc_psplit(int enabled);           /* 0: never hand the 256-column passes of a row tile to several CTAs (A/B switch; default 1: few-tile GEMMs do) */
 MPHSIR_API void mphsir_debug_tc_ebox1(int enabled);         /* 0: two store boxes per epilogue warp everywhere (default 1: one box + 4-slot A ring for BIAS GEMMs with 64 < K <= 128) */

@@ -124,7 +124,8 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t*
   const uint32_t rbar0 = smem_u32(&sm->res_full[2 * ew]);          // barrier k at rbar0 + 8 * k
   uint32_t rph = 0u;                                                // bit k: phase of barrier k
 
-  auto ncols_of = [&](int pass) { return min(PASS_COLS, p.Np - pass * PASS_COLS); };
+  const int pc = p.pass_cols;   // accumulator columns per pass: 256, or 128 when a 256-column few-tile GEMM is cut in two
+  auto ncols_of = [&](int pass) { return min(pc, p.Np - pass * pc); };
   // next chunk of this warp after (tile, tit, pass, c0); false when the CTA's work is finished
   auto p0_of = [&](int vt) { int t_, a_, b_; tc_decode(p, npass, vt, t_, a_, b_); return a_; };
   auto p1_of = [&](int vt) { int t_, a_, b_; tc_decode(p, npass, vt, t_, a_, b_); return b_; };
@@ -143,7 +144,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t*
       }
     }
   };
-  auto needs_res = [&](int pass, int c0) { return RES || (PROJ && pass * PASS_COLS + c0 < p.n_split); };
+  auto needs_res = [&](int pass, int c0) { return RES || (PROJ && pass * pc + c0 < p.n_split); };
   auto tile_coord = [&](int tile, int& b, int& row0) {
     if (p.tiles_per_batch > 0) {
       b = tile / p.tiles_per_batch;
@@ -157,7 +158,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t*
     int b, row0;
     tile_coord(tile_of(vt), b, row0);
     mbar_expect_tx(rbar0 + 8 * slot, 4096);
-    tma_load_3d(slot_a0 + 4096 * slot, &p.tmR, pass * PASS_COLS + c0, row0, b, rbar0 + 8 * slot);
+    tma_load_3d(slot_a0 + 4096 * slot, &p.tmR, pass * pc + c0, row0, b, rbar0 + 8 * slot);
   };
 
   uint32_t ck = 0;  // chunks processed by this warp (slot = ck & 1)
@@ -194,7 +195,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& p, Smem* sm, uint8_t*
       const int ncols_pass = ncols_of(pass);
       for (int c0 = half * 32; c0 < ncols_pass; c0 += 64, ++ck) {
         const int s = p.ebox == 2 ? (ck & 1) : 0;
-        const int n0 = pass * PASS_COLS + c0;
+        const int n0 = pass * pc + c0;
         const bool with_res = needs_res(pass, c0);
         const bool left = PROJ && n0 < p.n_split;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * PASS_COLS + c0;
@@ -295,7 +296,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Ks = p.ks;
   const int NT = (p.Np + BN - 1) / BN;             // 64-column n-tiles
-  constexpr int TPP = PASS_COLS / BN;              // n-tiles per pass
+  const int pc = p.pass_cols;                      // accumulator columns per pass (256, or 128: see plan_work)
+  const int TPP = pc / BN;                         // n-tiles per pass
   const int npass = (NT + TPP - 1) / TPP;
   const bool stationary = Ks <= p.na;
 
@@ -564,13 +566,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         mbar_wait(smem_u32(&sm->acc_full[buf]), (acc_it >> 1) & 1);
         TC_ACC(t_wait, tw);
         tc_fence_after();
-        const int ncols_pass = min(PASS_COLS, p.Np - pass * PASS_COLS);
+        const int ncols_pass = min(pc, p.Np - pass * pc);
         // software-pipelined bias: the float4 for the NEXT chunk is requested while this one is processed
         float4 bias_nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!DIRECT && p.bias != nullptr && pass * PASS_COLS + half * 32 + 4 * c4 < p.N)
-          bias_nxt = ldg4(p.bias + pass * PASS_COLS + half * 32 + 4 * c4);
+        if (!DIRECT && p.bias != nullptr && pass * pc + half * 32 + 4 * c4 < p.N)
+          bias_nxt = ldg4(p.bias + pass * pc + half * 32 + 4 * c4);
         for (int c0 = half * 32; c0 < ncols_pass; c0 += 64) {
-          const int n0 = pass * PASS_COLS + c0;
+          const int n0 = pass * pc + c0;
           uint32_t r[32];
           tw = TC_T0();
           asm volatile(
@@ -1173,12 +1175,15 @@ void set_cluster_enabled(int on) { g_cluster_enabled = on; }
 void set_debug_buffer(long long* p) { g_dbg = p; }
 
 // How a launch is cut into work: pure host arithmetic (also exported as mphsir_gemm_plan for the CPU tests).
-struct WorkPlan { int cluster, psplit, ppg, grid, iters, rev, n_full; };
+struct WorkPlan { int cluster, psplit, ppg, grid, iters, rev, n_full, pass_cols; };
 static WorkPlan plan_work(int M, int Np, int ks, int num_tiles, int tiles_per_batch, bool per_sample_weights, int sm_count) {
   WorkPlan w{};
   // few-tile GEMMs (the 16 x 16 latent of a patch batch: 32-64 row tiles for 148 SMs): the 256-column passes of a row tile are
   // handed to several CTAs (each converts the A slabs it needs itself)
-  const int npass = (Np + PASS_COLS - 1) / PASS_COLS;
+  // a few-tile GEMM of exactly two 128-column blocks (N = 256: fc2, the spectral apply, most data gradients of the latent) has a
+  // single 256-column pass; with 128-column passes it has two and can be shared by two CTAs like the wider ones
+  w.pass_cols = (g_psplit_enabled && num_tiles * 2 <= sm_count && Np > BN && Np <= 2 * BN) ? BN : PASS_COLS;
+  const int npass = (Np + w.pass_cols - 1) / w.pass_cols;
   w.psplit = 1;
   w.ppg = npass;
   w.n_full = num_tiles;
@@ -1262,7 +1267,7 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
   }
   make_a_tensor_map(a, conv);
   const WorkPlan wp = plan_work(a.M, a.Np, a.ks, a.num_tiles, a.tiles_per_batch, a.b_batch_bytes != 0, sm_count);
-  a.psplit = wp.psplit; a.ppg = wp.ppg; a.cluster = wp.cluster; a.iters = wp.iters; a.rev = wp.rev; a.n_full = wp.n_full;
+  a.psplit = wp.psplit; a.ppg = wp.ppg; a.cluster = wp.cluster; a.iters = wp.iters; a.rev = wp.rev; a.n_full = wp.n_full; a.pass_cols = wp.pass_cols;
   const int grid = wp.grid;
   if (a.cluster == 2) a.nb *= 2;   // half-size weight slots: twice the ring depth in the same shared memory
   if (conv && a.epi == MPHSIR_EPI_BIAS) a.epi = TC_OUT_TOKENS;
@@ -1284,7 +1289,7 @@ int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st) {
 
 GemmPlanOut gemm_plan(int M, int Np, int ks, int num_tiles, int tiles_per_batch, bool per_sample_weights, int sm_count) {
   const WorkPlan w = plan_work(M, Np, ks, num_tiles, tiles_per_batch, per_sample_weights, sm_count);
-  return GemmPlanOut{w.cluster, w.psplit, w.ppg, w.grid, w.iters, w.rev, w.n_full};
+  return GemmPlanOut{w.cluster, w.psplit, w.ppg, w.grid, w.iters, w.rev, w.n_full, w.pass_cols};
 }
 
 }  // namespace tc
@@ -1295,12 +1300,12 @@ using namespace mphsir;
 extern "C" MPHSIR_API void mphsir_debug_tc_counters(long long* buf) { tc::set_debug_buffer(buf); }
 extern "C" MPHSIR_API void mphsir_debug_tc_cluster(int enabled) { tc::set_cluster_enabled(enabled); }
 extern "C" MPHSIR_API void mphsir_debug_tc_psplit(int enabled) { tc::set_psplit_enabled(enabled); }
-extern "C" MPHSIR_API int mphsir_gemm_plan(int M, int N, int K, int rows_per_batch, int per_sample_weights, int sm_count, int* out6) {   /* out6: 7 ints */
+extern "C" MPHSIR_API int mphsir_gemm_plan(int M, int N, int K, int rows_per_batch, int per_sample_weights, int sm_count, int* out6) {   /* out6: 8 ints */
   if (M <= 0 || N <= 0 || K <= 0 || sm_count <= 0 || out6 == nullptr) return MPHSIR_ERR_INVALID;
   const int tpb = (per_sample_weights && rows_per_batch > 0) ? (rows_per_batch + 127) / 128 : 0;
   const int tiles = tpb > 0 ? (M / rows_per_batch) * tpb : (M + 127) / 128;
   const tc::GemmPlanOut w = tc::gemm_plan(M, (N + 15) / 16 * 16, (K + 63) / 64, tiles, tpb, per_sample_weights != 0, sm_count);
-  out6[0] = w.cluster; out6[1] = w.psplit; out6[2] = w.ppg; out6[3] = w.grid; out6[4] = w.iters; out6[5] = w.rev; out6[6] = w.n_full;
+  out6[0] = w.cluster; out6[1] = w.psplit; out6[2] = w.ppg; out6[3] = w.grid; out6[4] = w.iters; out6[5] = w.rev; out6[6] = w.n_full; out6[7] = w.pass_cols;
   return MPHSIR_OK;
 }
 extern "C" MPHSIR_API void mphsir_debug_tc_reverse(int enabled) { tc::set_tile_rev(enabled); }

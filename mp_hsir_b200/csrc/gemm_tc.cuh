@@ -46,6 +46,7 @@ struct TcArgs {
   int iters;   // work-item iterations per CTA (identical for all CTAs so that a cluster stays in lock-step)
   int psplit;  // work items per row tile: few-tile GEMMs (M < 128 * SMs / 2) hand the 256-column passes of a tile to `psplit` CTAs
   int ppg;     // passes per work item
+  int pass_cols;  // accumulator columns per pass: 256 (two 128-column blocks), or 128
   int n_full;  // the first n_full row tiles are whole work items; tiles n_full .. num_tiles-1 are cut into psplit pass groups
   int rev;     // 1: work items are walked from the last to the first (L2 reuse of the producer's most recent output)
   const float* ln_g;
@@ -69,7 +70,7 @@ struct TcArgs {
 };
 
 int launch_gemm_tc(TcArgs a, bool conv, cudaStream_t st);
-struct GemmPlanOut { int cluster, psplit, ppg, grid, iters, rev, n_full; };
+struct GemmPlanOut { int cluster, psplit, ppg, grid, iters, rev, n_full, pass_cols; };
 GemmPlanOut gemm_plan(int M, int Np, int ks, int num_tiles, int tiles_per_batch, bool per_sample_weights, int sm_count);
 void set_debug_buffer(long long* p);
 void set_cluster_enabled(int on);

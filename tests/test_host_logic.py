@@ -97,9 +97,9 @@ def test_synthetic_weights_are_name_seeded():
 def _gemm_plan(M, N, K, rows_per_batch=0, per_sample=0, sms=148):
     import ctypes
     from mp_hsir_b200 import lib
-    out = (ctypes.c_int * 7)()
+    out = (ctypes.c_int * 8)()
     assert lib.load().mphsir_gemm_plan(M, N, K, rows_per_batch, per_sample, sms, out) == 0
-    return dict(zip(("cluster", "psplit", "ppg", "grid", "iters", "rev", "n_full"), out))
+    return dict(zip(("cluster", "psplit", "ppg", "grid", "iters", "rev", "n_full", "pass_cols"), out))
 
 
 @pytest.mark.parametrize("M,N,K", [(262144, 384, 128), (65536, 512, 128), (65536, 384, 128), (16384, 768, 256), (4096, 1376, 256),
@@ -110,7 +110,8 @@ def test_gemm_work_plan_covers_every_pass_exactly_once(M, N, K):
     pass) belongs to exactly one work item, the grid fits the machine, pairs are even, few-tile launches and half-empty last
     rounds are split."""
     pl = _gemm_plan(M, N, K)
-    tiles, npass = (M + 127) // 128, ((N + 15) // 16 * 16 + 255) // 256
+    assert pl["pass_cols"] in (128, 256)
+    tiles, npass = (M + 127) // 128, ((N + 15) // 16 * 16 + pl["pass_cols"] - 1) // pl["pass_cols"]
     assert pl["cluster"] in (1, 2) and pl["psplit"] >= 1 and pl["ppg"] >= 1 and 0 <= pl["n_full"] <= tiles
     # decode every work item exactly as the kernel does (gemm_tc.cu tc_decode) and count the (tile, pass) pairs
     seen = {}
@@ -130,8 +131,9 @@ def test_gemm_work_plan_covers_every_pass_exactly_once(M, N, K):
     assert 1 <= pl["grid"] <= 148 and pl["grid"] * pl["iters"] >= items > pl["grid"] * (pl["iters"] - 1) - (pl["cluster"] - 1)
     if pl["cluster"] == 2:
         assert pl["grid"] % 2 == 0 and pl["psplit"] == 1 and tiles >= 2
-    if tiles * 2 <= 148 and npass >= 2:
+    if tiles * 2 <= 148 and N > 128:
         assert pl["psplit"] >= 2 and pl["n_full"] == 0, "few-tile launches hand the passes of a row tile to several CTAs"
+        assert pl["pass_cols"] == (128 if N <= 256 else 256)
     if tiles > 148 and 0 < tiles % 148 <= 74 and npass >= 2:
         assert pl["psplit"] >= 2 and pl["n_full"] == tiles - tiles % 148, "a half-empty last round is split"
         assert pl["iters"] == tiles // 148 + 1
