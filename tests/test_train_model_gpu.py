@@ -231,7 +231,11 @@ def test_checkpoint_resume_continues_training(tmp_path):
     assert abs(got - want) < 1e-5 * max(abs(want), 1e-3), (got, want)
     w1 = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
     w2 = torch.cat([p.detach().reshape(-1) for p in net2.parameters()])
-    assert float((w1 - w2).abs().max()) < 1e-6
+    # same weights, moments and step count going in; the step itself is not bit-reproducible (fp32 atomics in the weight-
+    # gradient kernels change the summation order per run) and AdamW's m/sqrt(v) amplifies that jitter where |g| ~ 0:
+    # bound the worst weight by 5 % of one lr-sized update and the average by rounding noise
+    d = (w1 - w2).abs()
+    assert float(d.max()) < 0.05 * 2e-4 and float(d.mean()) < 1e-8, (float(d.max()), float(d.mean()))
 
 
 def test_train_step_at_a_non_square_resolution():
