@@ -25,6 +25,8 @@ Layout choices
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, Optional
 
 import torch
@@ -53,6 +55,10 @@ class TrainEngine(Engine):
         self._flatten_parameters()
         self.loss_buf = torch.zeros(1, device=self.device, dtype=torch.float32)
         self._train_packed_version = None
+        # streams the captured weight re-pack forks into (0 = one chain); env switch for A/B runs
+        self.pack_lanes = int(os.environ.get("MPHSIR_PACK_LANES", "6"))
+        rates = [1.0 - r for st in self.cfg.stages() for r in st.dpr if r > 0.0]   # DropPath keep probabilities, block order
+        self._dp_keep_prob = torch.tensor(rates, device=self.device, dtype=torch.float32).view(-1, 1, 1) if rates else None
         self.time_graphs = False   # bench: CUDA events around the three graphs of the captured step -> self.graph_ms
         self.graph_ms = None
 
@@ -105,13 +111,27 @@ class TrainEngine(Engine):
         cp = _ceil(cout if cout_pad is None else cout_pad, 16)
         return self._W(pack_conv3x3(wt, cin_pad=cp), weight.shape[1], 9 * cp)
 
-    def _pack_all(self):
-        """forward + data-gradient weight images; the ~300 image packs are deferred and issued as a handful of launches"""
+    def _pack_all(self, lanes: int = 0):
+        """forward + data-gradient weight images; the ~300 image packs are deferred and issued as a handful of launches.
+        `lanes` > 0 (graph capture only): fork that many streams off the current one, deal the per-module re-layouts to
+        them (Engine._pack_lane) and join before the image packs."""
         lib.PACK_QUEUE = []
+        main = torch.cuda.current_stream()
+        if lanes > 0:
+            if len(self.__dict__.setdefault("_lane_streams", [])) < lanes:
+                self._lane_streams = [torch.cuda.Stream(self.device) for _ in range(lanes)]
+            self._pack_streams, self._pack_main = self._lane_streams[:lanes], main
+            for s in self._pack_streams:
+                s.wait_stream(main)
         try:
             self.packed = self._pack()
             self._pack_train()
         finally:
+            if lanes > 0:
+                torch.cuda.set_stream(main)
+                for s in self._pack_streams:
+                    main.wait_stream(s)
+                self._pack_streams = self._pack_main = None
             lib.flush_packs()
         self._train_packed_version = self.packed
 
@@ -126,8 +146,11 @@ class TrainEngine(Engine):
     def _pack_train(self):
         net, cfg, P = self.net, self.cfg, self.packed
         f32 = lambda t: t.detach().to(device=self.device, dtype=torch.float32)  # noqa: E731
+        lane = 0   # the same module -> lane dealing as Engine._pack: a lane continues from its own results
         for st in cfg.stages():
             for blk, d in zip(getattr(net, st.name).blocks, P[st.name]):
+                self._pack_lane(lane)
+                lane += 1
                 for k in ("qkv_w", "proj_w", "sqkv_w", "fc1_w", "fc2_w"):
                     d[k + ".d"] = self._dgrad_of(d[k])
                 d["sdw.f"] = _flip_dw(d["sdw"])
@@ -143,6 +166,8 @@ class TrainEngine(Engine):
                 }
                 d["sout"] = f32(blk.gobal_spectral_attn.project_out.weight).reshape(st.dim, st.dim).contiguous()
         for name in ("prompt1", "prompt2"):
+            self._pack_lane(lane)
+            lane += 1
             m, d = getattr(net, name), P[name]
             for k in ("q_w", "kv_w", "pin_w", "pout_w"):
                 d[k + ".d"] = self._dgrad_of(d[k])
@@ -150,11 +175,14 @@ class TrainEngine(Engine):
             d["out"] = f32(m.cross_transformer.attn.project_out.weight).reshape(d["D"], d["D"]).contiguous()
             d["conv_last.d"] = self._conv_dgrad(m.conv_last.weight)
         for name in ("fusion1", "fusion2"):
+            self._pack_lane(lane)
+            lane += 1
             m, d = getattr(net, name), P[name]
             for k in ("qkv_w", "pin_w", "pout_w", "conv_w"):
                 d[k + ".d"] = self._dgrad_of(d[k])
             d["dw.f"], d["ffn_dw.f"] = _flip_dw(d["dw"]), _flip_dw(d["ffn_dw"])
             d["out"] = f32(m.transformer.attn.project_out.weight).reshape(d["C"], d["C"]).contiguous()
+        self._pack_lane(-1)
         P["reduce_chan_level2.d"] = self._dgrad_of(P["reduce_chan_level2"])
         P["cout_p"] = _ceil(cfg.out_channel, 16)
         P["output.d"] = self._conv_dgrad(net.output.weight, cout_pad=P["cout_p"])
@@ -721,15 +749,13 @@ class TrainEngine(Engine):
     def drop_path_scales(self, B: int, generator: Optional[torch.Generator] = None) -> dict:
         """Per-sample DropPath multipliers mask/keep_prob for every block, one draw per call like timm's DropPath
         applied twice per block (net/MP_HSIR.py:718-719)."""
-        keep = {}
-        for st in self.cfg.stages():
-            for i, rate in enumerate(st.dpr):
-                if rate <= 0.0:
-                    continue
-                kp = 1.0 - rate
-                m = (torch.rand(2, B, device=self.device, generator=generator) < kp).to(torch.float32) / kp
-                keep[(st.name, i)] = m.contiguous()
-        return keep
+        slots = [(st.name, i) for st in self.cfg.stages() for i, rate in enumerate(st.dpr) if rate > 0.0]
+        if not slots:
+            return {}
+        # every block's Bernoulli draws in four launches (one uniform draw for all of them) instead of four per block
+        kp = self._dp_keep_prob   # built in __init__: a host-to-device copy must not happen inside a graph capture
+        m = (torch.rand(len(slots), 2, B, device=self.device, generator=generator) < kp).to(torch.float32) / kp
+        return {slot: m[j] for j, slot in enumerate(slots)}
 
     def _fwd_bwd(self, x, cl, weights, out, d_out, keep):
         """launch sequence of forward + clamp/L1 + backward on pre-allocated buffers (CUDA-graph capturable)."""
@@ -851,7 +877,7 @@ class TrainEngine(Engine):
         #    addresses are what the forward/backward graph records
         g_pack = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g_pack, pool=pool):
-            self._pack_all()
+            self._pack_all(lanes=self.pack_lanes)
         self._versions = self._param_versions()
         n_pack = lib.LAUNCHES - n0
         g_pack.replay()
