@@ -508,6 +508,12 @@ MPHSIR_API int mphsir_degrade_structured(float* x, int B, int C, int H, int W, c
  * int array [B]) is convolved with the k x k outer product of the normalised 1-D Gaussian of sigma 0.3((k-1)/2 - 1) + 0.8,
  * zero padding k/2; planes of samples with ksize[b] == 0 are not touched.  kmax >= every ksize[b] (validated on the host). */
 MPHSIR_API int mphsir_gaussian_blur(const float* in, float* out, const int* ksize, int B, int C, int H, int W, int kmax, void* stream);
+/* Super-resolution degradation 'sr' (utils/degradation_utils.py:165-176 `_bicubic_downsample`, then :189-200 `_resize` through
+ * single_degrade :431-432): every band of sample b with factor[b] > 0 (device int array [B]; the reference draws 2, 4 or 8) is
+ * bicubically down-sampled to (H / f, W / f) with torch's align_corners=True convention (A = -0.75, clamped indices) and
+ * replicated f x f back to H x W; planes of samples with factor[b] == 0 are not touched.  H and W need not be multiples of f
+ * (trailing pixels repeat the last low-resolution row / column); f <= min(H, W) is checked on the host. */
+MPHSIR_API int mphsir_sr_degrade(const float* in, float* out, const int* factor, int B, int C, int H, int W, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Collectives of the row-sharded scene over NVLink peer memory (mp_hsir_b200/csrc/peer.cu; one process per GPU of one

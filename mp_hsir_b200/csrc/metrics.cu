@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(256) gaussian_blur_kernel(const float* __restr
                                                             int tiles_per_plane) {
   __shared__ float tile[BLUR_T + BLUR_KMAX - 1][BLUR_T + BLUR_KMAX - 1 + 1];
   __shared__ float hrow[BLUR_T + BLUR_KMAX - 1][BLUR_T + 1];
-  __shared__ float kw[BLUR_KMAX];
+  // padded to whole 16-byte groups: ptxas reads the weights with LDS.128, the last group reaches past kw[k - 1]
+  __shared__ __align__(16) float kw[(BLUR_KMAX + 3) / 4 * 4];
   const int plane = blockIdx.x / tiles_per_plane;
   const int t = blockIdx.x - plane * tiles_per_plane;
   const int b = plane / C;
@@ -266,6 +267,66 @@ __global__ void __launch_bounds__(256) gaussian_blur_kernel(const float* __restr
     float a = 0.f;
     for (int i = 0; i < k; ++i) a = fmaf(kw[i], hrow[yy + i][xx], a);
     out[(long long)plane * H * W + (long long)y * W + x] = a;
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Super-resolution degradation 'sr' (utils/degradation_utils.py:165-176 then :189-200 via single_degrade :431-432): bicubic
+// down-sampling of every band to (H / f, W / f) as torch.nn.functional.interpolate(mode='bicubic', align_corners=True) does
+// it — source coordinate i * (H - 1) / (h - 1), cubic-convolution weights with A = -0.75 on the four rows / columns
+// floor(src) - 1 .. + 2, indices clamped to the image — followed by the f x f pixel replication of `_resize`.  A thread per
+// OUTPUT pixel recomputes its low-resolution sample (16 taps that hit L1): coalesced stores, no intermediate tensor.
+// factor[b] == 0: sample b is not an 'sr' sample and its output planes are left alone.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cubic_taps(int i, float scale, int n, int (&idx)[4], float (&w)[4]) {
+  constexpr float A = -0.75f;
+  const float real = scale * (float)i;
+  int i0 = (int)floorf(real);
+  if (i0 > n - 1) i0 = n - 1;
+  float t = real - (float)i0;
+  t = fminf(fmaxf(t, 0.f), 1.f);
+  const float x0 = t + 1.f, x3 = 2.f - t, x2 = 1.f - t;
+  w[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  w[1] = ((A + 2.f) * t - (A + 3.f)) * t * t + 1.f;
+  w[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  w[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int q = i0 + j - 1;
+    idx[j] = q < 0 ? 0 : (q > n - 1 ? n - 1 : q);
+  }
+}
+
+__global__ void __launch_bounds__(256) sr_degrade_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                         const int* __restrict__ factor, int C, int H, int W, long long total) {
+  const long long hw = (long long)H * W;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    const long long plane = e / hw;
+    const int f = factor[plane / C];
+    if (f <= 0) continue;
+    const int rem = (int)(e - plane * hw);
+    const int y = rem / W, x = rem - y * W;
+    const int h = H / f, w = W / f;
+    // pixels beyond h * f (H not a multiple of f) replicate the last low-resolution row / column
+    const int yl = min(y / f, h - 1), xl = min(x / f, w - 1);
+    const float sy = h > 1 ? (float)(H - 1) / (float)(h - 1) : 0.f;
+    const float sx = w > 1 ? (float)(W - 1) / (float)(w - 1) : 0.f;
+    int iy[4], ix[4];
+    float wy[4], wx[4];
+    cubic_taps(yl, sy, H, iy, wy);
+    cubic_taps(xl, sx, W, ix, wx);
+    const float* src = in + plane * hw;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const float* row = src + (long long)iy[a] * W;
+      float r = 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) r += wx[b] * __ldg(row + ix[b]);
+      acc += wy[a] * r;
+    }
+    out[e] = acc;
   }
 }
 
@@ -324,6 +385,16 @@ extern "C" int mphsir_gaussian_blur(const float* in, float* out, const int* ksiz
   metrics::gaussian_blur_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, out, ksize, C, H, W, tiles_x,
                                                                                                     tiles_x * tiles_y);
   return check_launch("gaussian_blur");
+}
+
+extern "C" int mphsir_sr_degrade(const float* in, float* out, const int* factor, int B, int C, int H, int W, void* stream) {
+  MPHSIR_REQUIRE(in && out && factor && B > 0 && C > 0 && H > 0 && W > 0, "sr_degrade: bad arguments");
+  MPHSIR_REQUIRE(in != out, "sr_degrade: in place is not supported (every output pixel reads a 4 x 4 neighbourhood of the input)");
+  const long long total = (long long)B * C * H * W;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  metrics::sr_degrade_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, out, factor, C, H, W, total);
+  return check_launch("sr_degrade");
 }
 
 extern "C" int mphsir_degrade_structured(float* x, int B, int C, int H, int W, const float* colmul, const float* coladd,

@@ -16,6 +16,10 @@ the B*C*H*W random numbers come from a counter-based Philox4x32-10 stream inside
                 few KB) and applied by a second in-place launch (``mphsir_degrade_structured``)
     blur      : (optional fifth recipe) Gaussian blur, kernel size from {9, 15, 21}, sigma 0.3((k-1)/2 - 1) + 0.8, zero
                 padding (:91-108) — a second launch (``mphsir_gaussian_blur``) over the blur samples only
+    sr        : (optional sixth recipe) bicubic down-sampling by 2, 4 or 8 (``F.interpolate(mode='bicubic', align_corners=True)``,
+                :165-176) and f x f pixel replication back to the patch size (:189-200, chained by single_degrade :431-432) —
+                one launch (``mphsir_sr_degrade``) over the sr samples only.  With it the reference's DEFAULT natural-scene list
+                (options.py:15: gaussianN, complexN, blur, sr, inpaint, bandmiss) is synthesised entirely on the device
 
 The task id of a sample is the index of its degradation in the active ``de_type`` list, shape [B,1] (:140).
 """
@@ -28,22 +32,26 @@ import torch
 from . import lib
 
 RECIPES = ("gaussianN", "complexN", "inpaint", "bandmiss")          # the default set (one elementwise launch)
-ALL_RECIPES = RECIPES + ("blur",)                                    # + recipes that need their own kernel
+ALL_RECIPES = RECIPES + ("blur", "sr")                               # + recipes that need their own kernel
+REFERENCE_DEFAULT = ("gaussianN", "complexN", "blur", "sr", "inpaint", "bandmiss")   # options.py:15 (task ids 0..5 in this order)
 DE_RANGE = {"gaussianN": (30.0, 70.0), "complexN": (10.0, 30.0, 50.0, 70.0), "inpaint": (0.7, 0.8, 0.9), "bandmiss": (0.1, 0.2, 0.3),
-            "blur": (9, 15, 21)}
+            "blur": (9, 15, 21), "sr": (2, 4, 8)}
 
 
 def draw_parameters(B: int, C: int, de_types: Sequence[str] = RECIPES, generator: Optional[torch.Generator] = None,
-                    with_blur: bool = False):
+                    with_blur: bool = False, with_sr: bool = False):
     """Host-side draws of one degradation per sample -> (task_id [B,1] int64, sigma [B,C], keep [B,C], mask_ratio [B]);
-    a few hundred bytes and a dozen vectorised torch calls, the only per-step host work.  with_blur: a fifth element, the
-    Gaussian-blur kernel size per sample (int32 [B], 0 = not a blur sample)."""
+    a few hundred bytes and a dozen vectorised torch calls, the only per-step host work.  with_blur: one more element, the
+    Gaussian-blur kernel size per sample (int32 [B], 0 = not a blur sample); with_sr: one more (after it), the down-sampling
+    factor per sample (int32 [B], 0 = not an sr sample)."""
     g = generator
     for k in de_types:
         if k not in ALL_RECIPES:
             raise ValueError(f"{k!r} is not an array-only recipe ({ALL_RECIPES})")
     if "blur" in de_types and not with_blur:
         raise ValueError("the 'blur' recipe needs with_blur=True (its kernel sizes are a fifth return value)")
+    if "sr" in de_types and not with_sr:
+        raise ValueError("the 'sr' recipe needs with_sr=True (its down-sampling factors are one more return value)")
     tid = torch.randint(0, len(de_types), (B, 1), generator=g)
     code = torch.tensor([ALL_RECIPES.index(k) for k in de_types])[tid[:, 0]]      # recipe of every sample
     r = DE_RANGE
@@ -61,12 +69,17 @@ def draw_parameters(B: int, C: int, de_types: Sequence[str] = RECIPES, generator
     n_lost = (pct * C).floor().to(torch.int64)
     order = torch.rand(B, C, generator=g).argsort(dim=1).argsort(dim=1)          # a random permutation rank per band
     keep = ((order >= n_lost[:, None]) | (code != 3)[:, None]).to(torch.float32)
+    ret = [tid, sigma.contiguous(), keep.contiguous(), ratio.contiguous()]
     if with_blur:
         # blur: kernel size from the list (dataset_utils.py:112 'blur': [(9, 15, 21)]); blur samples pass the elementwise kernel unchanged
         ks = torch.tensor(r["blur"], dtype=torch.int32)[torch.randint(0, len(r["blur"]), (B,), generator=g)]
-        ksize = torch.where(code == 4, ks, torch.zeros(B, dtype=torch.int32))
-        return tid, sigma.contiguous(), keep.contiguous(), ratio.contiguous(), ksize.contiguous()
-    return tid, sigma.contiguous(), keep.contiguous(), ratio.contiguous()
+        ret.append(torch.where(code == 4, ks, torch.zeros(B, dtype=torch.int32)).contiguous())
+    if with_sr:
+        # sr: intensity = randint(0, 2) picks the factor from (2, 4, 8) (degradation_utils.py:373-374); sr samples pass the
+        # elementwise kernel unchanged as well
+        fs = torch.tensor(r["sr"], dtype=torch.int32)[torch.randint(0, len(r["sr"]), (B,), generator=g)]
+        ret.append(torch.where(code == 5, fs, torch.zeros(B, dtype=torch.int32)).contiguous())
+    return tuple(ret)
 
 
 def draw_structured(code: torch.Tensor, C: int, W: int, generator: Optional[torch.Generator] = None):
@@ -139,20 +152,39 @@ def gaussian_blur(clean: torch.Tensor, ksize: torch.Tensor, out: Optional[torch.
     return out
 
 
+def sr_degrade(clean: torch.Tensor, factor: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Bicubic down-sampling by factor[b] + replication back to H x W for the samples with factor[b] > 0
+    (utils/degradation_utils.py:165-176, :189-200); other samples of `out` keep their content (a fresh `out` starts as a copy
+    of `clean`)."""
+    if not clean.is_cuda:
+        raise RuntimeError("mp_hsir_b200.degrade runs on a CUDA device via libmphsir.so; there is no CPU fallback")
+    c = clean.detach().float().contiguous()
+    if out is None:
+        out = c.clone()
+    fmax = int(factor.max()) if factor.numel() else 0
+    if fmax > min(c.shape[2], c.shape[3]):
+        raise ValueError(f"sr factor {fmax} exceeds the patch size {tuple(c.shape[2:])}")
+    if fmax > 0:
+        with torch.cuda.device(c.device):
+            lib.sr_degrade(c, out, factor.to(device=c.device, dtype=torch.int32).contiguous())
+    return out
+
+
 def degrade_batch(clean: torch.Tensor, seed: int, de_types: Sequence[str] = RECIPES,
                   generator: Optional[torch.Generator] = None, complex_full: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """(degraded [B,C,H,W], task_id [B,1]) for a clean device batch — what the DataLoader's collate hands train.py:50-58.
     complex_full: complexN samples also get their deadline / impulse / stripe half (one more in-place launch)."""
     B, C, W = clean.shape[0], clean.shape[1], clean.shape[3]
-    ksize = None
-    if "blur" in de_types:
-        tid, sigma, keep, ratio, ksize = draw_parameters(B, C, de_types, generator, with_blur=True)
-    else:
-        tid, sigma, keep, ratio = draw_parameters(B, C, de_types, generator)
-    out = degrade(clean, sigma, keep, ratio, seed)              # blur samples leave this pass as copies of the clean patch
+    wb, wsr = "blur" in de_types, "sr" in de_types
+    tid, sigma, keep, ratio, *extra = draw_parameters(B, C, de_types, generator, with_blur=wb, with_sr=wsr)
+    ksize = extra.pop(0) if wb else None
+    factor = extra.pop(0) if wsr else None
+    out = degrade(clean, sigma, keep, ratio, seed)              # blur / sr samples leave this pass as copies of the clean patch
     if complex_full and "complexN" in de_types:
         code = torch.tensor([ALL_RECIPES.index(k) for k in de_types])[tid[:, 0]]
         degrade_structured(out, *draw_structured(code, C, W, generator), seed=seed)
     if ksize is not None:
         gaussian_blur(clean, ksize, out=out)
+    if factor is not None:
+        sr_degrade(clean, factor, out=out)
     return out, tid

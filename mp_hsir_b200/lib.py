@@ -181,6 +181,7 @@ SIGNATURES = {
     "mphsir_plane_nonzero": (_I, [_VP, _I, _LL, _VP, _VP]),
     "mphsir_degrade": (_I, [_VP, _VP, _I, _I, _LL, _VP, _VP, _VP, C.c_ulonglong, _VP]),
     "mphsir_gaussian_blur": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
+    "mphsir_sr_degrade": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "mphsir_degrade_structured": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, C.c_ulonglong, _VP]),
     "mphsir_adamw_step": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _I, _F, _VP, _VP]),
 }
@@ -873,6 +874,16 @@ def gaussian_blur(x: torch.Tensor, out: torch.Tensor, ksize: torch.Tensor, kmax:
     _launch("gaussian_blur", lambda: load().mphsir_gaussian_blur(x.data_ptr(), out.data_ptr(), ksize.data_ptr(), B, Cc, H, W, kmax,
                                                                  stream_ptr()),
             lambda: (0.0, 8.0 * x.numel(), "gaussian_blur"))
+
+
+def sr_degrade(x: torch.Tensor, out: torch.Tensor, factor: torch.Tensor) -> None:
+    """out[b] = every band of x[b] bicubically down-sampled by factor[b] and replicated back (utils/degradation_utils.py:165-176,
+    :189-200) where factor[b] > 0; other samples' planes of `out` are left as they are.  factor: int32 [B] on the device."""
+    B, Cc, H, W = x.shape
+    assert x.is_contiguous() and out.is_contiguous() and out.shape == x.shape and x.dtype == torch.float32
+    assert factor.dtype == torch.int32 and factor.numel() == B and factor.is_cuda
+    _launch("sr_degrade", lambda: load().mphsir_sr_degrade(x.data_ptr(), out.data_ptr(), factor.data_ptr(), B, Cc, H, W, stream_ptr()),
+            lambda: (0.0, 8.0 * x.numel(), "sr_degrade"))
 
 
 def degrade(clean: torch.Tensor, out: torch.Tensor, sigma: torch.Tensor, keep: torch.Tensor, mask_ratio: torch.Tensor,

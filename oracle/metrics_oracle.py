@@ -116,6 +116,38 @@ def gaussian_blur(clean: np.ndarray, kernel_size: int) -> np.ndarray:
     return out
 
 
+def sr_degrade(clean: np.ndarray, factor: int) -> np.ndarray:
+    """utils/degradation_utils.py:165-176 (_bicubic_downsample) followed by :189-200 (_resize), as single_degrade :431-432
+    chains them for 'sr', restated on a [C,H,W] cube: torch's bicubic with align_corners=True is the cubic convolution with
+    A = -0.75 on source coordinate i (H-1)/(h-1), rows / columns floor(src)-1 .. +2 clamped to the image; then every
+    low-resolution pixel is repeated factor x factor.  Explicit weights in float64: shares no code with torch or the kernel."""
+    f = int(factor)
+    C, H, W = clean.shape
+    h, w = H // f, W // f
+
+    def taps(n_in: int, n_out: int):
+        A = -0.75
+        scale = np.float32(n_in - 1) / np.float32(n_out - 1) if n_out > 1 else np.float32(0)   # fp32 like torch's opmath
+        idx = np.zeros((n_out, 4), dtype=np.int64)
+        wt = np.zeros((n_out, 4), dtype=np.float64)
+        for i in range(n_out):
+            real = np.float32(scale * np.float32(i))
+            i0 = min(int(np.floor(real)), n_in - 1)
+            t = float(min(max(np.float32(real - np.float32(i0)), 0.0), 1.0))
+            c2 = lambda x: ((A * x - 5 * A) * x + 8 * A) * x - 4 * A          # noqa: E731  1 < |x| < 2
+            c1 = lambda x: ((A + 2) * x - (A + 3)) * x * x + 1                # noqa: E731  |x| <= 1
+            wt[i] = (c2(t + 1), c1(t), c1(1 - t), c2(2 - t))
+            idx[i] = np.clip(i0 + np.arange(-1, 3), 0, n_in - 1)
+        return idx, wt
+
+    iy, wy = taps(H, h)
+    ix, wx = taps(W, w)
+    src = clean.astype(np.float64)
+    rows = np.einsum("ia,ciaw->ciw", wy, src[:, iy, :])            # [C,h,W]
+    low = np.einsum("jb,chjb->chj", wx, rows[:, :, ix])            # [C,h,w]
+    return np.repeat(np.repeat(low, f, axis=1), f, axis=2)
+
+
 def degrade_structured(x: np.ndarray, colmul: np.ndarray, coladd: np.ndarray, impulse: np.ndarray, active: np.ndarray, seed: int):
     """utils/degradation_utils.py:41-84 on [B,C,H,W]: deadline columns (colmul 0), stripes (coladd), impulse flips with probability
     impulse[b,c] (salt with probability 1/2) from the Philox stream with counter word 2 = 1; inactive samples untouched."""

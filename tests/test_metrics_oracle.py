@@ -110,65 +110,48 @@ def test_gaussian_blur_oracle_matches_the_reference_formula():
         assert got.var() < clean.var()
 
 
-def test_blur_parameter_draws():
-    from mp_hsir_b200.degrade import ALL_RECIPES
+def test_blur_and_sr_parameter_draws():
+    from mp_hsir_b200.degrade import ALL_RECIPES, REFERENCE_DEFAULT
     g = torch.Generator().manual_seed(1)
-    tid, sigma, keep, ratio, ksize = draw_parameters(64, 31, ALL_RECIPES, g, with_blur=True)
-    assert ksize.dtype == torch.int32 and set(tid.view(-1).tolist()) == {0, 1, 2, 3, 4}
-    for b in range(64):
-        if ALL_RECIPES[int(tid[b, 0])] == "blur":
-            assert int(ksize[b]) in DE_RANGE["blur"] and torch.all(sigma[b] == 0) and torch.all(keep[b] == 1) and ratio[b] < 0
+    tid, sigma, keep, ratio, ksize, factor = draw_parameters(96, 31, ALL_RECIPES, g, with_blur=True, with_sr=True)
+    assert ksize.dtype == torch.int32 and factor.dtype == torch.int32 and set(tid.view(-1).tolist()) == {0, 1, 2, 3, 4, 5}
+    for b in range(96):
+        kind = ALL_RECIPES[int(tid[b, 0])]
+        untouched = torch.all(sigma[b] == 0) and torch.all(keep[b] == 1) and ratio[b] < 0   # the elementwise pass copies it
+        if kind == "blur":
+            assert int(ksize[b]) in DE_RANGE["blur"] and int(factor[b]) == 0 and untouched
+        elif kind == "sr":
+            assert int(factor[b]) in DE_RANGE["sr"] and int(ksize[b]) == 0 and untouched
         else:
-            assert int(ksize[b]) == 0
+            assert int(ksize[b]) == 0 and int(factor[b]) == 0
     with pytest.raises(ValueError):
         draw_parameters(4, 31, ALL_RECIPES, g)
+    with pytest.raises(ValueError):
+        draw_parameters(4, 31, ALL_RECIPES, g, with_blur=True)
+    # the reference's default natural-scene list (options.py:15): task id = position in THAT list (dataset_utils.py:134-140)
+    tid, *_, ksize, factor = draw_parameters(64, 31, REFERENCE_DEFAULT, g, with_blur=True, with_sr=True)
+    for b in range(64):
+        kind = REFERENCE_DEFAULT[int(tid[b, 0])]
+        assert (int(ksize[b]) > 0) == (kind == "blur") and (int(factor[b]) > 0) == (kind == "sr")
 
 
-def test_structured_draws_follow_the_reference_counts():
-    from mp_hsir_b200.degrade import draw_structured
-    import math
-    B, C, W = 48, 31, 64
-    code = torch.tensor([1, 0, 1, 2] * 12)
-    colmul, coladd, impulse, active = draw_structured(code, C, W, torch.Generator().manual_seed(3))
-    assert torch.equal(active, (code == 1).int())
-    kinds = set()
-    for b in range(B):
-        dead_bands = (colmul[b] == 0).any(dim=1)
-        stripe_bands = (coladd[b] != 0).any(dim=1)
-        imp_bands = impulse[b] > 0
-        if code[b] != 1:
-            assert not dead_bands.any() and not stripe_bands.any() and not imp_bands.any()
-            continue
-        assert int(dead_bands.any()) + int(stripe_bands.any()) + int(imp_bands.any()) == 1     # ONE of the three (:304-314)
-        if dead_bands.any():
-            kinds.add("deadline")
-            assert int(dead_bands.sum()) <= C // 3
-            n = (colmul[b][dead_bands] == 0).sum(dim=1)
-            assert int(n.min()) >= math.ceil(0.05 * W) and int(n.max()) < math.ceil(0.15 * W)
-        elif stripe_bands.any():
-            kinds.add("stripe")
-            assert int(stripe_bands.sum()) <= C // 3 and float(coladd[b].abs().max()) <= 0.25
-            n = (coladd[b][stripe_bands] != 0).sum(dim=1)
-            assert int(n.max()) < math.floor(0.15 * W)
-        else:
-            kinds.add("impulse")
-            assert int(imp_bands.sum()) == C // 3 and round(float(impulse[b][imp_bands][0]), 4) in (0.1, 0.3, 0.5, 0.7)
-    assert kinds == {"deadline", "stripe", "impulse"}
-
-
-def test_degrade_structured_oracle_semantics():
-    x = np.full((2, 6, 16, 20), 0.5, dtype=np.float32)
-    colmul = np.ones((2, 6, 20), dtype=np.float32)
-    coladd = np.zeros((2, 6, 20), dtype=np.float32)
-    impulse = np.zeros((2, 6), dtype=np.float32)
-    colmul[0, 1, [3, 7]] = 0
-    coladd[0, 2, 5] = -0.2
-    impulse[0, 4] = 0.3
-    colmul[1, 0, :] = 0                       # sample 1 is inactive: nothing may change
-    out = M.degrade_structured(x, colmul, coladd, impulse, np.array([1, 0]), seed=11)
-    assert np.all(out[1] == 0.5)
-    assert np.all(out[0, 1][:, [3, 7]] == 0) and np.all(np.delete(out[0, 1], [3, 7], axis=1) == 0.5)
-    assert np.allclose(out[0, 2][:, 5], 0.3) and np.all(np.delete(out[0, 2], 5, axis=1) == 0.5)
-    flipped = out[0, 4] != 0.5
-    assert 0.15 < flipped.mean() < 0.45 and set(np.unique(out[0, 4][flipped]).tolist()) <= {0.0, 1.0}
-    assert 0.2 < (out[0, 4][flipped] == 1.0).mean() < 0.8
+def test_sr_oracle_matches_the_reference_lines():
+    """oracle sr_degrade (explicit cubic-convolution weights, float64) == the reference's own lines (utils/degradation_utils.py:
+    165-176 `_bicubic_downsample` then :189-200 `_resize`, chained by single_degrade :431-432), re-enacted verbatim here because
+    the module itself imports cv2 / skimage / matplotlib"""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(0)
+    for (C, H, W) in ((5, 64, 64), (3, 32, 96), (2, 8, 8)):
+        clean = rng.random((C, H, W), dtype=np.float32)
+        for f in (2, 4, 8):
+            t = torch.from_numpy(clean).float().unsqueeze(0)
+            ms = F.interpolate(t, size=(H // f, W // f), mode='bicubic', align_corners=True).squeeze(0).detach().numpy()
+            cp = torch.from_numpy(ms.astype(np.float32)).float().unsqueeze(0).unsqueeze(3).unsqueeze(5)
+            ref = cp.repeat(1, 1, 1, f, 1, f).view(1, C, H // f * f, W // f * f).squeeze(0).numpy()
+            got = M.sr_degrade(clean, f)
+            assert got.shape == ref.shape and np.abs(got - ref).max() < 2e-6
+    # a constant cube stays constant (the four weights sum to one), and f x f blocks are flat
+    const = M.sr_degrade(np.full((1, 16, 16), 0.37, dtype=np.float32), 4)
+    assert np.abs(const - 0.37).max() < 1e-7
+    got = M.sr_degrade(rng.random((1, 16, 16), dtype=np.float32), 4)
+    assert np.array_equal(got[:, ::4, ::4].repeat(4, 1).repeat(4, 2), got)
