@@ -514,6 +514,16 @@ MPHSIR_API int mphsir_gaussian_blur(const float* in, float* out, const int* ksiz
  * replicated f x f back to H x W; planes of samples with factor[b] == 0 are not touched.  H and W need not be multiples of f
  * (trailing pixels repeat the last low-resolution row / column); f <= min(H, W) is checked on the host. */
 MPHSIR_API int mphsir_sr_degrade(const float* in, float* out, const int* factor, int B, int C, int H, int W, void* stream);
+/* Generic k x k blur degradations — circle blur (utils/degradation_utils.py:110-128), square blur (:150-163), motion blur
+ * (:130-148): F.conv2d(x, kernel.repeat(C,1,1,1), padding=k//2, groups=C) with one host-built kernel.  taps: its k*k values,
+ * row-major, DEVICE memory; k odd, <= 21; zero padding; planes of samples with active[b] == 0 (device int [B]) are not touched. */
+MPHSIR_API int mphsir_blur2d(const float* in, float* out, const float* taps, const int* active, int B, int C, int H, int W, int k,
+                             void* stream);
+/* Poisson noise 'poissonN' (utils/degradation_utils.py:86-89): out = Poisson(max(x, 0) * scale[b]) / scale[b], one Philox4x32-10
+ * uniform per element (key `seed`, counter word 2 = 2) inverted through the Poisson CDF in double precision; samples with
+ * scale[b] <= 0 (device float [B]) are not touched.  chw = elements per sample.  in == out is allowed. */
+MPHSIR_API int mphsir_poisson(const float* in, float* out, const float* scale, int B, long long chw, unsigned long long seed,
+                              void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Collectives of the row-sharded scene over NVLink peer memory (mp_hsir_b200/csrc/peer.cu; one process per GPU of one

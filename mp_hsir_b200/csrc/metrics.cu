@@ -330,6 +330,76 @@ __global__ void __launch_bounds__(256) sr_degrade_kernel(const float* __restrict
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Generic k x k blur degradations: circle blur (utils/degradation_utils.py:110-128), square blur (:150-163) and motion blur
+// (:130-148) all are F.conv2d(x, kernel.repeat(C,1,1,1), padding=k//2, groups=C) with ONE host-built k x k kernel — the caller
+// passes its taps (row-major, device memory), this kernel does the depthwise cross-correlation with zero padding.  Same
+// tiling as the Gaussian blur (a haloed 32 x 32 tile per CTA), k*k taps per output.  active[b] == 0: planes left alone.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) blur2d_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                     const float* __restrict__ taps, const int* __restrict__ active, int C, int H,
+                                                     int W, int k, int tiles_x, int tiles_per_plane) {
+  __shared__ float tile[BLUR_T + BLUR_KMAX - 1][BLUR_T + BLUR_KMAX - 1 + 1];
+  __shared__ __align__(16) float kw[(BLUR_KMAX * BLUR_KMAX + 3) / 4 * 4];
+  const int plane = blockIdx.x / tiles_per_plane;
+  const int t = blockIdx.x - plane * tiles_per_plane;
+  if (active[plane / C] == 0) return;
+  const int r = k >> 1;
+  const int ty0 = (t / tiles_x) * BLUR_T, tx0 = (t % tiles_x) * BLUR_T;
+  const float* src = in + (long long)plane * H * W;
+  for (int e = threadIdx.x; e < k * k; e += 256) kw[e] = __ldg(taps + e);
+  const int ext = BLUR_T + 2 * r;
+  for (int e = threadIdx.x; e < ext * ext; e += 256) {
+    const int yy = e / ext, xx = e - yy * ext;
+    const int y = ty0 + yy - r, x = tx0 + xx - r;
+    tile[yy][xx] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(src + (long long)y * W + x) : 0.f;   // zero padding
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < BLUR_T * BLUR_T; e += 256) {
+    const int yy = e / BLUR_T, xx = e - yy * BLUR_T;
+    const int y = ty0 + yy, x = tx0 + xx;
+    if (y >= H || x >= W) continue;
+    float a = 0.f;
+    for (int i = 0; i < k; ++i)
+      for (int j = 0; j < k; ++j) a = fmaf(kw[i * k + j], tile[yy + i][xx + j], a);
+    out[(long long)plane * H * W + (long long)y * W + x] = a;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Poisson noise 'poissonN' (utils/degradation_utils.py:86-89): out = Poisson(max(x, 0) * scale) / scale.  One uniform per
+// element from the Philox4x32-10 stream with counter word 2 = 2 (element e: word e % 4 of block e / 4), inverted through the
+// Poisson CDF by sequential search in double precision (lambda <= scale: the reference uses scale 10 on [0, 1] data, so a
+// handful of terms).  scale[b] <= 0: sample b is not a Poisson sample and its output is left alone.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) poisson_kernel(const float* __restrict__ in, float* __restrict__ out, long long total,
+                                                      long long chw, const float* __restrict__ scale, uint32_t seed_lo,
+                                                      uint32_t seed_hi) {
+  const long long quads = (total + 3) / 4;
+  for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < quads; q += (long long)gridDim.x * 256) {
+    uint32_t w[4];
+    philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), 2u, 0u, seed_lo, seed_hi, w);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const long long e = 4 * q + h;
+      if (e >= total) break;
+      const float sc = __ldg(scale + e / chw);
+      if (sc <= 0.f) continue;
+      const double u = (double)(w[h] >> 8) * (1.0 / 16777216.0);
+      const double lam = (double)(fmaxf(__ldg(in + e), 0.f) * sc);
+      double p = exp(-lam), cdf = p;
+      int n = 0;
+      while (u > cdf && n < 4096) {
+        ++n;
+        p *= lam / (double)n;
+        cdf += p;
+      }
+      out[e] = (float)n / sc;
+    }
+  }
+}
+
 }  // namespace metrics
 }  // namespace mphsir
 
@@ -395,6 +465,30 @@ extern "C" int mphsir_sr_degrade(const float* in, float* out, const int* factor,
   if (blocks > 148LL * 16) blocks = 148LL * 16;
   metrics::sr_degrade_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, out, factor, C, H, W, total);
   return check_launch("sr_degrade");
+}
+
+extern "C" int mphsir_blur2d(const float* in, float* out, const float* taps, const int* active, int B, int C, int H, int W, int k,
+                             void* stream) {
+  MPHSIR_REQUIRE(in && out && taps && active && B > 0 && C > 0 && H > 0 && W > 0, "blur2d: bad arguments");
+  MPHSIR_REQUIRE(in != out, "blur2d: in place is not supported (every output pixel reads a k x k neighbourhood)");
+  MPHSIR_REQUIRE(k >= 1 && k <= metrics::BLUR_KMAX && (k & 1), "blur2d: odd kernel sizes up to %d (got %d)", metrics::BLUR_KMAX, k);
+  const int tiles_x = (W + metrics::BLUR_T - 1) / metrics::BLUR_T, tiles_y = (H + metrics::BLUR_T - 1) / metrics::BLUR_T;
+  const long long blocks = (long long)B * C * tiles_x * tiles_y;
+  MPHSIR_REQUIRE(blocks < (1LL << 31), "blur2d: too many tiles");
+  metrics::blur2d_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, out, taps, active, C, H, W, k,
+                                                                                             tiles_x, tiles_x * tiles_y);
+  return check_launch("blur2d");
+}
+
+extern "C" int mphsir_poisson(const float* in, float* out, const float* scale, int B, long long chw, unsigned long long seed,
+                              void* stream) {
+  MPHSIR_REQUIRE(in && out && scale && B > 0 && chw > 0, "poisson: bad arguments");
+  const long long total = (long long)B * chw;
+  long long blocks = ((total + 3) / 4 + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  metrics::poisson_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, out, total, chw, scale,
+                                                                                              (uint32_t)seed, (uint32_t)(seed >> 32));
+  return check_launch("poisson");
 }
 
 extern "C" int mphsir_degrade_structured(float* x, int B, int C, int H, int W, const float* colmul, const float* coladd,

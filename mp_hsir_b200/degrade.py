@@ -20,6 +20,9 @@ the B*C*H*W random numbers come from a counter-based Philox4x32-10 stream inside
                 :165-176) and f x f pixel replication back to the patch size (:189-200, chained by single_degrade :431-432) —
                 one launch (``mphsir_sr_degrade``) over the sr samples only.  With it the reference's DEFAULT natural-scene list
                 (options.py:15: gaussianN, complexN, blur, sr, inpaint, bandmiss) is synthesised entirely on the device
+    circle_blur / poissonN : (remote-sensing extras, dataset_utils.py:117) the disc-cut Gaussian blur (:110-128; host-built k x k
+                kernel through the generic ``mphsir_blur2d``, which also serves square / motion blur kernels, :130-163) and Poisson
+                noise Poisson(x * scale) / scale (:86-89; ``mphsir_poisson``, a third Philox stream) — ``draw_recipes``
 
 The task id of a sample is the index of its degradation in the active ``de_type`` list, shape [B,1] (:140).
 """
@@ -32,10 +35,10 @@ import torch
 from . import lib
 
 RECIPES = ("gaussianN", "complexN", "inpaint", "bandmiss")          # the default set (one elementwise launch)
-ALL_RECIPES = RECIPES + ("blur", "sr")                               # + recipes that need their own kernel
+ALL_RECIPES = RECIPES + ("blur", "sr", "circle_blur", "poissonN")    # + recipes that need their own kernel
 REFERENCE_DEFAULT = ("gaussianN", "complexN", "blur", "sr", "inpaint", "bandmiss")   # options.py:15 (task ids 0..5 in this order)
 DE_RANGE = {"gaussianN": (30.0, 70.0), "complexN": (10.0, 30.0, 50.0, 70.0), "inpaint": (0.7, 0.8, 0.9), "bandmiss": (0.1, 0.2, 0.3),
-            "blur": (9, 15, 21), "sr": (2, 4, 8)}
+            "blur": (9, 15, 21), "sr": (2, 4, 8), "circle_blur": (9,), "poissonN": (10.0,)}
 
 
 def draw_parameters(B: int, C: int, de_types: Sequence[str] = RECIPES, generator: Optional[torch.Generator] = None,
@@ -80,6 +83,72 @@ def draw_parameters(B: int, C: int, de_types: Sequence[str] = RECIPES, generator
         fs = torch.tensor(r["sr"], dtype=torch.int32)[torch.randint(0, len(r["sr"]), (B,), generator=g)]
         ret.append(torch.where(code == 5, fs, torch.zeros(B, dtype=torch.int32)).contiguous())
     return tuple(ret)
+
+
+def draw_recipes(B: int, C: int, de_types: Sequence[str], generator: Optional[torch.Generator] = None) -> dict:
+    """``draw_parameters`` for any subset of ALL_RECIPES, as a dict: tid, sigma, keep, ratio and — for the recipes present in
+    `de_types` — ksize (blur), factor (sr), circle (kernel size per sample, 0 = not a circle-blur sample), poisson (scale per
+    sample, 0 = not a Poisson sample)."""
+    wb, wsr = "blur" in de_types, "sr" in de_types
+    tid, sigma, keep, ratio, *extra = draw_parameters(B, C, de_types, generator, with_blur=wb, with_sr=wsr)
+    d = {"tid": tid, "sigma": sigma, "keep": keep, "ratio": ratio}
+    if wb:
+        d["ksize"] = extra.pop(0)
+    if wsr:
+        d["factor"] = extra.pop(0)
+    code = torch.tensor([ALL_RECIPES.index(k) for k in de_types])[tid[:, 0]]
+    if "circle_blur" in de_types:
+        ks = torch.tensor(DE_RANGE["circle_blur"], dtype=torch.int32)[torch.randint(0, len(DE_RANGE["circle_blur"]), (B,), generator=generator)]
+        d["circle"] = torch.where(code == ALL_RECIPES.index("circle_blur"), ks, torch.zeros(B, dtype=torch.int32)).contiguous()
+    if "poissonN" in de_types:
+        sc = torch.tensor(DE_RANGE["poissonN"])[torch.randint(0, len(DE_RANGE["poissonN"]), (B,), generator=generator)]
+        d["poisson"] = torch.where(code == ALL_RECIPES.index("poissonN"), sc, torch.zeros(B)).contiguous()
+    return d
+
+
+def circle_kernel(kernel_size: int) -> torch.Tensor:
+    """the k x k kernel of `_apply_circle_blur` (utils/degradation_utils.py:111-120): exp(-d^2 / (2 r^2)) inside the disc of radius
+    r = k // 2 around the centre, 0 outside, normalised; fp32 [k, k] on the host"""
+    k = int(kernel_size)
+    r = k // 2
+    ax = torch.arange(k, dtype=torch.float64) - r
+    d2 = ax[:, None] ** 2 + ax[None, :] ** 2
+    kern = torch.where(d2.sqrt() <= r, torch.exp(-d2 / (2.0 * r * r)), torch.zeros(())).to(torch.float32)
+    return kern / kern.sum()
+
+
+def blur2d(clean: torch.Tensor, kernel: torch.Tensor, active: Optional[torch.Tensor] = None,
+           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Depthwise k x k blur of the samples with active[b] != 0 (all when None) with ONE kernel, zero padding k // 2 — circle blur
+    (`circle_kernel`), square blur (`torch.full((k, k), 1 / k**2)`) or a motion-blur kernel built with cv2 as the reference does
+    (utils/degradation_utils.py:110-163).  Other samples of `out` keep their content (a fresh `out` starts as a copy of `clean`)."""
+    if not clean.is_cuda:
+        raise RuntimeError("mp_hsir_b200.degrade runs on a CUDA device via libmphsir.so; there is no CPU fallback")
+    k = kernel.shape[-1]
+    if kernel.dim() != 2 or kernel.shape[0] != k or k % 2 == 0 or k > 21:
+        raise ValueError(f"blur2d: a square kernel of odd size <= 21 is needed, got {tuple(kernel.shape)}")
+    c = clean.detach().float().contiguous()
+    if out is None:
+        out = c.clone()
+    act = torch.ones(c.shape[0], dtype=torch.int32) if active is None else (active != 0).to(torch.int32)
+    if int(act.sum()) > 0:
+        with torch.cuda.device(c.device):
+            lib.blur2d(c, out, kernel.to(device=c.device, dtype=torch.float32).contiguous(), act.to(c.device).contiguous())
+    return out
+
+
+def poisson_noise(clean: torch.Tensor, scale: torch.Tensor, seed: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Poisson(max(x, 0) * scale[b]) / scale[b] for the samples with scale[b] > 0 (utils/degradation_utils.py:86-89); other
+    samples of `out` keep their content (a fresh `out` starts as a copy of `clean`)."""
+    if not clean.is_cuda:
+        raise RuntimeError("mp_hsir_b200.degrade runs on a CUDA device via libmphsir.so; there is no CPU fallback")
+    c = clean.detach().float().contiguous()
+    if out is None:
+        out = c.clone()
+    if float(scale.max()) > 0:
+        with torch.cuda.device(c.device):
+            lib.poisson(c, out, scale.to(device=c.device, dtype=torch.float32).contiguous(), seed)
+    return out
 
 
 def draw_structured(code: torch.Tensor, C: int, W: int, generator: Optional[torch.Generator] = None):
@@ -175,16 +244,20 @@ def degrade_batch(clean: torch.Tensor, seed: int, de_types: Sequence[str] = RECI
     """(degraded [B,C,H,W], task_id [B,1]) for a clean device batch — what the DataLoader's collate hands train.py:50-58.
     complex_full: complexN samples also get their deadline / impulse / stripe half (one more in-place launch)."""
     B, C, W = clean.shape[0], clean.shape[1], clean.shape[3]
-    wb, wsr = "blur" in de_types, "sr" in de_types
-    tid, sigma, keep, ratio, *extra = draw_parameters(B, C, de_types, generator, with_blur=wb, with_sr=wsr)
-    ksize = extra.pop(0) if wb else None
-    factor = extra.pop(0) if wsr else None
-    out = degrade(clean, sigma, keep, ratio, seed)              # blur / sr samples leave this pass as copies of the clean patch
+    d = draw_recipes(B, C, de_types, generator)
+    tid = d["tid"]
+    # blur / sr / circle_blur / poissonN samples leave the elementwise pass as copies of the clean patch
+    out = degrade(clean, d["sigma"], d["keep"], d["ratio"], seed)
     if complex_full and "complexN" in de_types:
         code = torch.tensor([ALL_RECIPES.index(k) for k in de_types])[tid[:, 0]]
         degrade_structured(out, *draw_structured(code, C, W, generator), seed=seed)
-    if ksize is not None:
-        gaussian_blur(clean, ksize, out=out)
-    if factor is not None:
-        sr_degrade(clean, factor, out=out)
+    if "ksize" in d:
+        gaussian_blur(clean, d["ksize"], out=out)
+    if "factor" in d:
+        sr_degrade(clean, d["factor"], out=out)
+    if "circle" in d:
+        for k in sorted(set(d["circle"].tolist()) - {0}):
+            blur2d(clean, circle_kernel(k), d["circle"] == k, out=out)
+    if "poisson" in d:
+        poisson_noise(clean, d["poisson"], seed, out=out)
     return out, tid

@@ -182,6 +182,8 @@ SIGNATURES = {
     "mphsir_degrade": (_I, [_VP, _VP, _I, _I, _LL, _VP, _VP, _VP, C.c_ulonglong, _VP]),
     "mphsir_gaussian_blur": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
     "mphsir_sr_degrade": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
+    "mphsir_blur2d": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
+    "mphsir_poisson": (_I, [_VP, _VP, _VP, _I, _LL, C.c_ulonglong, _VP]),
     "mphsir_degrade_structured": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, C.c_ulonglong, _VP]),
     "mphsir_adamw_step": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _I, _F, _VP, _VP]),
 }
@@ -884,6 +886,30 @@ def sr_degrade(x: torch.Tensor, out: torch.Tensor, factor: torch.Tensor) -> None
     assert factor.dtype == torch.int32 and factor.numel() == B and factor.is_cuda
     _launch("sr_degrade", lambda: load().mphsir_sr_degrade(x.data_ptr(), out.data_ptr(), factor.data_ptr(), B, Cc, H, W, stream_ptr()),
             lambda: (0.0, 8.0 * x.numel(), "sr_degrade"))
+
+
+def blur2d(x: torch.Tensor, out: torch.Tensor, taps: torch.Tensor, active: torch.Tensor) -> None:
+    """out[b] = every band of x[b] cross-correlated with the k x k kernel `taps` (zero padding k // 2) where active[b] != 0 — the
+    circle / square / motion blur of utils/degradation_utils.py:110-163; other samples' planes of `out` are left as they are."""
+    B, Cc, H, W = x.shape
+    k = taps.shape[-1]
+    assert x.is_contiguous() and out.is_contiguous() and out.shape == x.shape and x.dtype == torch.float32
+    assert taps.is_cuda and taps.is_contiguous() and taps.dtype == torch.float32 and taps.numel() == k * k
+    assert active.dtype == torch.int32 and active.numel() == B and active.is_cuda
+    _launch("blur2d", lambda: load().mphsir_blur2d(x.data_ptr(), out.data_ptr(), taps.data_ptr(), active.data_ptr(), B, Cc, H, W, k,
+                                                   stream_ptr()),
+            lambda: (2.0 * k * k * x.numel(), 8.0 * x.numel(), "blur2d"))
+
+
+def poisson(x: torch.Tensor, out: torch.Tensor, scale: torch.Tensor, seed: int) -> None:
+    """out[b] = Poisson(max(x[b], 0) * scale[b]) / scale[b] where scale[b] > 0 (utils/degradation_utils.py:86-89); Philox stream
+    keyed by `seed`, counter word 2 = 2."""
+    B = x.shape[0]
+    assert x.is_contiguous() and out.is_contiguous() and out.shape == x.shape and x.dtype == torch.float32
+    assert scale.is_cuda and scale.dtype == torch.float32 and scale.numel() == B
+    _launch("poisson", lambda: load().mphsir_poisson(x.data_ptr(), out.data_ptr(), scale.data_ptr(), B, x.numel() // B,
+                                                     seed & 0xFFFFFFFFFFFFFFFF, stream_ptr()),
+            lambda: (0.0, 8.0 * x.numel(), "poisson"))
 
 
 def degrade(clean: torch.Tensor, out: torch.Tensor, sigma: torch.Tensor, keep: torch.Tensor, mask_ratio: torch.Tensor,

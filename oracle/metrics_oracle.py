@@ -148,6 +148,56 @@ def sr_degrade(clean: np.ndarray, factor: int) -> np.ndarray:
     return np.repeat(np.repeat(low, f, axis=1), f, axis=2)
 
 
+def circle_kernel(kernel_size: int) -> np.ndarray:
+    """utils/degradation_utils.py:111-120 (_apply_circle_blur): a Gaussian of sigma = radius cut to the disc, normalised (fp32)."""
+    k = int(kernel_size)
+    radius = center = k // 2
+    yy, xx = np.mgrid[0:k, 0:k]
+    dist = np.sqrt((xx - center) ** 2 + (yy - center) ** 2)
+    kernel = np.where(dist <= radius, np.exp(-(dist ** 2) / (2 * (radius ** 2))), 0.0).astype(np.float32)
+    return (kernel / kernel.sum(dtype=np.float32)).astype(np.float32)
+
+
+def blur2d(clean: np.ndarray, kernel: np.ndarray) -> np.ndarray:
+    """F.conv2d(x, kernel.repeat(C,1,1,1), padding=k//2, groups=C) of utils/degradation_utils.py:121-127 / :142-147 / :154-161 on a
+    [C,H,W] cube: explicit shifted sums in float64 (cross-correlation, zero padding), odd k."""
+    k = kernel.shape[0]
+    C, H, W = clean.shape
+    r = k // 2
+    pad = np.zeros((C, H + 2 * r, W + 2 * r), dtype=np.float64)
+    pad[:, r:r + H, r:r + W] = clean
+    out = np.zeros((C, H, W), dtype=np.float64)
+    for dy in range(k):
+        for dx in range(k):
+            out += float(kernel[dy, dx]) * pad[:, dy:dy + H, dx:dx + W]
+    return out
+
+
+def poisson(clean: np.ndarray, scale: np.ndarray, seed: int) -> np.ndarray:
+    """utils/degradation_utils.py:86-89 (_apply_poisson) on [B,C,H,W] with the kernel's random stream: element e takes word e % 4
+    of Philox block e // 4 (counter word 2 = 2), u = (w >> 8) 2^-24, and the count is the smallest n with u <= CDF_lambda(n),
+    lambda = max(x, 0) * scale (fp32 product), the CDF summed term by term in float64.  scale[b] <= 0: sample untouched."""
+    B = clean.shape[0]
+    total = clean.size
+    quads = (total + 3) // 4
+    w = philox4x32_10(np.arange(quads, dtype=np.uint64), seed, word2=2).astype(np.float64)
+    u = (np.floor(w / 256.0) / 16777216.0).reshape(-1)[:total].reshape(clean.shape)
+    sc = scale.astype(np.float32).reshape((B,) + (1,) * (clean.ndim - 1))
+    lam = (np.maximum(clean.astype(np.float32), np.float32(0)) * np.where(sc > 0, sc, np.float32(1))).astype(np.float64)
+    p = np.exp(-lam)
+    cdf = p.copy()
+    n = np.zeros(clean.shape, dtype=np.int64)
+    for it in range(1, 4097):
+        go = u > cdf
+        if not go.any():
+            break
+        n = np.where(go, it, n)
+        p = np.where(go, p * lam / it, p)
+        cdf = np.where(go, cdf + p, cdf)
+    out = n.astype(np.float32) / np.where(sc > 0, sc, np.float32(1))
+    return np.where(sc > 0, out, clean.astype(np.float32)).astype(np.float32)
+
+
 def degrade_structured(x: np.ndarray, colmul: np.ndarray, coladd: np.ndarray, impulse: np.ndarray, active: np.ndarray, seed: int):
     """utils/degradation_utils.py:41-84 on [B,C,H,W]: deadline columns (colmul 0), stripes (coladd), impulse flips with probability
     impulse[b,c] (salt with probability 1/2) from the Philox stream with counter word 2 = 1; inactive samples untouched."""

@@ -97,7 +97,7 @@ def test_gaussian_blur_matches_oracle():
 def test_degrade_batch_with_blur_recipe():
     from mp_hsir_b200.degrade import ALL_RECIPES
     clean = synthetic_input((16, 31, 64, 64), seed=5).cuda()
-    noisy, tid = degrade_batch(clean, seed=9, de_types=ALL_RECIPES, generator=torch.Generator().manual_seed(6))
+    noisy, tid = degrade_batch(clean, seed=9, de_types=ALL_RECIPES[:5], generator=torch.Generator().manual_seed(6))
     assert 4 in tid.view(-1).tolist()
     for b in range(16):
         if int(tid[b, 0]) == 4:   # blurred: smoother than the clean patch, same mean to a few percent
@@ -139,6 +139,57 @@ def test_degrade_batch_reference_default_list():
             assert torch.equal(noisy[b][:, ::2, ::2], noisy[b][:, 1::2, 1::2])
         elif kind == "blur":
             assert float(noisy[b].var()) < float(clean[b].var())
+
+
+@pytest.mark.gpu
+def test_blur2d_matches_oracle():
+    """mphsir_blur2d vs explicit shifted sums: the reference's circle kernel (utils/degradation_utils.py:110-128), a square kernel
+    (:150-163) and an asymmetric random kernel (orientation: F.conv2d is a cross-correlation); inactive samples untouched"""
+    from mp_hsir_b200.degrade import blur2d, circle_kernel
+    clean = synthetic_input((3, 4, 72, 50), seed=9)
+    g = torch.Generator().manual_seed(1)
+    for kernel in (circle_kernel(9), torch.full((5, 5), 1.0 / 25.0), torch.rand(7, 7, generator=g), circle_kernel(21)):
+        out = torch.full_like(clean, 7.0).cuda()
+        blur2d(clean.cuda(), kernel, torch.tensor([1, 0, 1]), out=out)
+        out = out.cpu().numpy()
+        assert (out[1] == 7.0).all()
+        for b in (0, 2):
+            ref = M.blur2d(clean[b].numpy(), kernel.numpy())
+            assert abs(out[b] - ref).max() < 1e-5 * max(1.0, float(kernel.sum()))
+    with pytest.raises(ValueError):
+        blur2d(clean.cuda(), torch.ones(4, 4))
+
+
+@pytest.mark.gpu
+def test_poisson_matches_oracle_stream():
+    """mphsir_poisson vs the oracle's restatement of the same Philox stream and CDF inversion: the counts are integers decided
+    by comparisons in float64, so they agree exactly (a last-bit difference of exp() could move at most an isolated element)"""
+    from mp_hsir_b200.degrade import poisson_noise
+    x = synthetic_input((4, 5, 24, 40), seed=2)
+    x[3] = x[3] - 0.5                                           # negative inputs are clipped to lambda = 0
+    scale = torch.tensor([10.0, 0.0, 4.0, 10.0])
+    got = poisson_noise(x.cuda(), scale, seed=0x1234567ABC).cpu().numpy()
+    ref = M.poisson(x.numpy(), scale.numpy(), seed=0x1234567ABC)
+    assert (got != ref).sum() <= 2
+    assert np.array_equal(got[1], x[1].numpy())
+    big = poisson_noise(torch.full((1, 1, 256, 256), 0.5).cuda(), torch.tensor([10.0]), seed=7).cpu().numpy() * 10.0
+    assert abs(big.mean() - 5.0) < 0.05 and abs(big.var() - 5.0) < 0.15
+
+
+@pytest.mark.gpu
+def test_degrade_batch_every_recipe():
+    from mp_hsir_b200.degrade import ALL_RECIPES
+    clean = synthetic_input((48, 31, 64, 64), seed=8).cuda()
+    noisy, tid = degrade_batch(clean, seed=13, de_types=ALL_RECIPES, generator=torch.Generator().manual_seed(5))
+    kinds = [ALL_RECIPES[int(t)] for t in tid.view(-1)]
+    assert set(kinds) == set(ALL_RECIPES)
+    for b, kind in enumerate(kinds):
+        assert not torch.equal(noisy[b], clean[b]) and bool(torch.isfinite(noisy[b]).all())
+        if kind == "circle_blur":
+            assert float(noisy[b].var()) < float(clean[b].var())
+        elif kind == "poissonN":
+            c = noisy[b] * 10.0
+            assert torch.equal(c.round(), c) or float((c.round() - c).abs().max()) < 1e-4
 
 
 @pytest.mark.gpu

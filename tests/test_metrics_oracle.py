@@ -113,6 +113,7 @@ def test_gaussian_blur_oracle_matches_the_reference_formula():
 def test_blur_and_sr_parameter_draws():
     from mp_hsir_b200.degrade import ALL_RECIPES, REFERENCE_DEFAULT
     g = torch.Generator().manual_seed(1)
+    ALL_RECIPES = ALL_RECIPES[:6]                              # the recipes draw_parameters itself parameterises
     tid, sigma, keep, ratio, ksize, factor = draw_parameters(96, 31, ALL_RECIPES, g, with_blur=True, with_sr=True)
     assert ksize.dtype == torch.int32 and factor.dtype == torch.int32 and set(tid.view(-1).tolist()) == {0, 1, 2, 3, 4, 5}
     for b in range(96):
@@ -155,3 +156,52 @@ def test_sr_oracle_matches_the_reference_lines():
     assert np.abs(const - 0.37).max() < 1e-7
     got = M.sr_degrade(rng.random((1, 16, 16), dtype=np.float32), 4)
     assert np.array_equal(got[:, ::4, ::4].repeat(4, 1).repeat(4, 2), got)
+
+
+def test_circle_blur_oracle_matches_the_reference_lines():
+    """oracle circle_kernel / blur2d == utils/degradation_utils.py:110-128 re-enacted verbatim (the module itself imports cv2 /
+    skimage / matplotlib); the host kernel the product uploads (degrade.circle_kernel) is the same to fp32 rounding"""
+    import torch.nn.functional as F
+    from mp_hsir_b200.degrade import circle_kernel
+    rng = np.random.default_rng(2)
+    clean = rng.random((4, 40, 36), dtype=np.float32)
+    for kernel_size in (9, 5, 15):
+        kernel = np.zeros((kernel_size, kernel_size), dtype=np.float32)
+        radius = kernel_size // 2
+        center = kernel_size // 2
+        for y in range(kernel_size):
+            for x in range(kernel_size):
+                distance = np.sqrt((x - center) ** 2 + (y - center) ** 2)
+                if distance <= radius:
+                    kernel[y, x] = np.exp(-(distance ** 2) / (2 * (radius ** 2)))
+        kernel /= kernel.sum()
+        inp = torch.from_numpy(clean).float().unsqueeze(0)
+        k2 = torch.from_numpy(kernel).unsqueeze(0).unsqueeze(0).repeat(inp.shape[1], 1, 1, 1)
+        ref = F.conv2d(inp, k2, padding=kernel_size // 2, groups=inp.shape[1]).squeeze(0).numpy()
+        assert np.array_equal(M.circle_kernel(kernel_size), kernel)
+        assert np.abs(M.blur2d(clean, M.circle_kernel(kernel_size)) - ref).max() < 2e-6
+        assert float((circle_kernel(kernel_size) - torch.from_numpy(kernel)).abs().max()) < 2e-8
+
+
+def test_poisson_oracle_is_poisson():
+    """the inversion restated in the oracle yields Poisson counts: mean = variance = lambda; inactive samples untouched; the
+    counts are integers over the scale like np.random.poisson(x * scale) / scale (utils/degradation_utils.py:86-89)"""
+    x = np.full((2, 1, 256, 256), 0.5, dtype=np.float32)
+    x[1] = 0.3
+    out = M.poisson(x, np.array([10.0, 0.0], dtype=np.float32), seed=1)
+    counts = out[0] * 10.0
+    assert np.array_equal(counts, np.round(counts)) and abs(counts.mean() - 5.0) < 0.05 and abs(counts.var() - 5.0) < 0.15
+    assert np.array_equal(out[1], x[1])
+    neg = M.poisson(np.full((1, 1, 8, 8), -0.2, dtype=np.float32), np.array([10.0], dtype=np.float32), seed=3)
+    assert (neg == 0).all()                                    # np.clip(clean_patch, 0, None)
+
+
+def test_draw_recipes_covers_every_recipe():
+    from mp_hsir_b200.degrade import ALL_RECIPES, draw_recipes
+    d = draw_recipes(128, 31, ALL_RECIPES, torch.Generator().manual_seed(0))
+    kinds = [ALL_RECIPES[int(t)] for t in d["tid"].view(-1)]
+    assert set(kinds) == set(ALL_RECIPES)
+    for b, kind in enumerate(kinds):
+        assert (int(d["circle"][b]) in DE_RANGE["circle_blur"]) == (kind == "circle_blur")
+        assert (float(d["poisson"][b]) in DE_RANGE["poissonN"]) == (kind == "poissonN")
+        assert (int(d["ksize"][b]) > 0) == (kind == "blur") and (int(d["factor"][b]) > 0) == (kind == "sr")
