@@ -205,3 +205,53 @@ def test_draw_recipes_covers_every_recipe():
         assert (int(d["circle"][b]) in DE_RANGE["circle_blur"]) == (kind == "circle_blur")
         assert (float(d["poisson"][b]) in DE_RANGE["poissonN"]) == (kind == "poissonN")
         assert (int(d["ksize"][b]) > 0) == (kind == "blur") and (int(d["factor"][b]) > 0) == (kind == "sr")
+
+
+def test_structured_draws_follow_the_reference_counts():
+    from mp_hsir_b200.degrade import draw_structured
+    import math
+    B, C, W = 48, 31, 64
+    code = torch.tensor([1, 0, 1, 2] * 12)
+    colmul, coladd, impulse, active = draw_structured(code, C, W, torch.Generator().manual_seed(3))
+    assert torch.equal(active, (code == 1).int())
+    kinds = set()
+    for b in range(B):
+        dead_bands = (colmul[b] == 0).any(dim=1)
+        stripe_bands = (coladd[b] != 0).any(dim=1)
+        imp_bands = impulse[b] > 0
+        if code[b] != 1:
+            assert not dead_bands.any() and not stripe_bands.any() and not imp_bands.any()
+            continue
+        assert int(dead_bands.any()) + int(stripe_bands.any()) + int(imp_bands.any()) == 1     # ONE of the three (:304-314)
+        if dead_bands.any():
+            kinds.add("deadline")
+            assert int(dead_bands.sum()) <= C // 3
+            n = (colmul[b][dead_bands] == 0).sum(dim=1)
+            assert int(n.min()) >= math.ceil(0.05 * W) and int(n.max()) < math.ceil(0.15 * W)
+        elif stripe_bands.any():
+            kinds.add("stripe")
+            assert int(stripe_bands.sum()) <= C // 3 and float(coladd[b].abs().max()) <= 0.25
+            n = (coladd[b][stripe_bands] != 0).sum(dim=1)
+            assert int(n.max()) < math.floor(0.15 * W)
+        else:
+            kinds.add("impulse")
+            assert int(imp_bands.sum()) == C // 3 and round(float(impulse[b][imp_bands][0]), 4) in (0.1, 0.3, 0.5, 0.7)
+    assert kinds == {"deadline", "stripe", "impulse"}
+
+
+def test_degrade_structured_oracle_semantics():
+    x = np.full((2, 6, 16, 20), 0.5, dtype=np.float32)
+    colmul = np.ones((2, 6, 20), dtype=np.float32)
+    coladd = np.zeros((2, 6, 20), dtype=np.float32)
+    impulse = np.zeros((2, 6), dtype=np.float32)
+    colmul[0, 1, [3, 7]] = 0
+    coladd[0, 2, 5] = -0.2
+    impulse[0, 4] = 0.3
+    colmul[1, 0, :] = 0                       # sample 1 is inactive: nothing may change
+    out = M.degrade_structured(x, colmul, coladd, impulse, np.array([1, 0]), seed=11)
+    assert np.all(out[1] == 0.5)
+    assert np.all(out[0, 1][:, [3, 7]] == 0) and np.all(np.delete(out[0, 1], [3, 7], axis=1) == 0.5)
+    assert np.allclose(out[0, 2][:, 5], 0.3) and np.all(np.delete(out[0, 2], 5, axis=1) == 0.5)
+    flipped = out[0, 4] != 0.5
+    assert 0.15 < flipped.mean() < 0.45 and set(np.unique(out[0, 4][flipped]).tolist()) <= {0.0, 1.0}
+    assert 0.2 < (out[0, 4][flipped] == 1.0).mean() < 0.8
