@@ -56,7 +56,7 @@ class TrainEngine(Engine):
         self.loss_buf = torch.zeros(1, device=self.device, dtype=torch.float32)
         self._train_packed_version = None
         # streams the captured weight re-pack forks into (0 = one chain); env switch for A/B runs
-        self.pack_lanes = int(os.environ.get("MPHSIR_PACK_LANES", "6"))
+        self.pack_lanes = int(os.environ.get("MPHSIR_PACK_LANES", "13"))
         rates = [1.0 - r for st in self.cfg.stages() for r in st.dpr if r > 0.0]   # DropPath keep probabilities, block order
         self._dp_keep_prob = torch.tensor(rates, device=self.device, dtype=torch.float32).view(-1, 1, 1) if rates else None
         self.time_graphs = False   # bench: CUDA events around the three graphs of the captured step -> self.graph_ms
