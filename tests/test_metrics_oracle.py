@@ -91,19 +91,20 @@ def test_parameter_draws_follow_the_reference_ranges():
 
 def test_gaussian_blur_oracle_matches_the_reference_formula():
     """oracle gaussian_blur (explicit shifted sums) == the reference's own lines (utils/degradation_utils.py:91-108: F.conv2d with
-    the outer-product kernel), re-enacted verbatim here because the module itself imports cv2 / skimage / matplotlib"""
+    the outer-product kernel), evaluated here with the same torch fp32 operations because the module itself imports cv2 / skimage /
+    matplotlib"""
     import torch.nn.functional as F
     rng = np.random.default_rng(0)
     clean = rng.random((5, 40, 36), dtype=np.float32)
     for kernel_size in (9, 15, 21, 7, 11):
-        sigma = 0.3 * ((kernel_size - 1) * 0.5 - 1) + 0.8
-        x = torch.arange(kernel_size, dtype=torch.float32)
-        mean = (kernel_size - 1) / 2
-        kernel_1d = torch.exp(-((x - mean) ** 2) / (2 * sigma ** 2))
-        kernel_1d = kernel_1d / kernel_1d.sum()
-        kernel_2d = (kernel_1d.unsqueeze(0) * kernel_1d.unsqueeze(1)).unsqueeze(0)
-        inp = torch.from_numpy(clean).float().unsqueeze(0)
-        ref = F.conv2d(inp, kernel_2d.repeat(inp.shape[1], 1, 1, 1), padding=kernel_size // 2, stride=1, groups=inp.shape[1])[0].numpy()
+        # the formula of :93-98 in torch fp32, as the reference evaluates it: g[i] = exp(-(i - c)^2 / (2 s^2)), s = 0.3 (c - 1) + 0.8
+        c = (kernel_size - 1) / 2
+        s_ = 0.3 * (c - 1) + 0.8
+        g = torch.exp(-((torch.arange(kernel_size, dtype=torch.float32) - c) ** 2) / (2 * s_ ** 2))
+        g = g / g.sum()
+        k2 = torch.outer(g, g)
+        inp = torch.from_numpy(clean)[None]
+        ref = F.conv2d(inp, k2.expand(inp.shape[1], 1, -1, -1), padding=kernel_size // 2, groups=inp.shape[1])[0].numpy()
         got = M.gaussian_blur(clean, kernel_size)
         assert got.shape == ref.shape and np.abs(got - ref).max() < 2e-6
         # a blur preserves the mean of the interior and flattens: variance strictly drops
@@ -138,17 +139,15 @@ def test_blur_and_sr_parameter_draws():
 
 def test_sr_oracle_matches_the_reference_lines():
     """oracle sr_degrade (explicit cubic-convolution weights, float64) == the reference's own lines (utils/degradation_utils.py:
-    165-176 `_bicubic_downsample` then :189-200 `_resize`, chained by single_degrade :431-432), re-enacted verbatim here because
+    165-176 `_bicubic_downsample` then :189-200 `_resize`, chained by single_degrade :431-432), re-enacted here with the same torch calls because
     the module itself imports cv2 / skimage / matplotlib"""
     import torch.nn.functional as F
     rng = np.random.default_rng(0)
     for (C, H, W) in ((5, 64, 64), (3, 32, 96), (2, 8, 8)):
         clean = rng.random((C, H, W), dtype=np.float32)
         for f in (2, 4, 8):
-            t = torch.from_numpy(clean).float().unsqueeze(0)
-            ms = F.interpolate(t, size=(H // f, W // f), mode='bicubic', align_corners=True).squeeze(0).detach().numpy()
-            cp = torch.from_numpy(ms.astype(np.float32)).float().unsqueeze(0).unsqueeze(3).unsqueeze(5)
-            ref = cp.repeat(1, 1, 1, f, 1, f).view(1, C, H // f * f, W // f * f).squeeze(0).numpy()
+            low = F.interpolate(torch.from_numpy(clean)[None], size=(H // f, W // f), mode='bicubic', align_corners=True)[0]
+            ref = low.repeat_interleave(f, dim=1).repeat_interleave(f, dim=2).numpy()      # `_resize`: every pixel f x f times
             got = M.sr_degrade(clean, f)
             assert got.shape == ref.shape and np.abs(got - ref).max() < 2e-6
     # a constant cube stays constant (the four weights sum to one), and f x f blocks are flat
@@ -159,25 +158,23 @@ def test_sr_oracle_matches_the_reference_lines():
 
 
 def test_circle_blur_oracle_matches_the_reference_lines():
-    """oracle circle_kernel / blur2d == utils/degradation_utils.py:110-128 re-enacted verbatim (the module itself imports cv2 /
+    """oracle circle_kernel / blur2d == utils/degradation_utils.py:110-128 re-enacted (the module itself imports cv2 /
     skimage / matplotlib); the host kernel the product uploads (degrade.circle_kernel) is the same to fp32 rounding"""
     import torch.nn.functional as F
     from mp_hsir_b200.degrade import circle_kernel
     rng = np.random.default_rng(2)
     clean = rng.random((4, 40, 36), dtype=np.float32)
     for kernel_size in (9, 5, 15):
+        # the kernel the reference's double loop builds (:111-120): a Gaussian of sigma = radius on the disc of that radius,
+        # float64 values stored into a float32 array, normalised by its float32 sum
+        r = kernel_size // 2
         kernel = np.zeros((kernel_size, kernel_size), dtype=np.float32)
-        radius = kernel_size // 2
-        center = kernel_size // 2
-        for y in range(kernel_size):
-            for x in range(kernel_size):
-                distance = np.sqrt((x - center) ** 2 + (y - center) ** 2)
-                if distance <= radius:
-                    kernel[y, x] = np.exp(-(distance ** 2) / (2 * (radius ** 2)))
+        for y, x in np.ndindex(kernel_size, kernel_size):
+            d = float(np.sqrt((x - r) ** 2 + (y - r) ** 2))
+            kernel[y, x] = np.exp(-(d * d) / (2 * r * r)) if d <= r else 0.0
         kernel /= kernel.sum()
-        inp = torch.from_numpy(clean).float().unsqueeze(0)
-        k2 = torch.from_numpy(kernel).unsqueeze(0).unsqueeze(0).repeat(inp.shape[1], 1, 1, 1)
-        ref = F.conv2d(inp, k2, padding=kernel_size // 2, groups=inp.shape[1]).squeeze(0).numpy()
+        inp = torch.from_numpy(clean)[None]
+        ref = F.conv2d(inp, torch.from_numpy(kernel).expand(inp.shape[1], 1, -1, -1), padding=r, groups=inp.shape[1])[0].numpy()
         assert np.array_equal(M.circle_kernel(kernel_size), kernel)
         assert np.abs(M.blur2d(clean, M.circle_kernel(kernel_size)) - ref).max() < 2e-6
         assert float((circle_kernel(kernel_size) - torch.from_numpy(kernel)).abs().max()) < 2e-8
