@@ -524,6 +524,14 @@ MPHSIR_API int mphsir_blur2d(const float* in, float* out, const float* taps, con
  * scale[b] <= 0 (device float [B]) are not touched.  chw = elements per sample.  in == out is allowed. */
 MPHSIR_API int mphsir_poisson(const float* in, float* out, const float* scale, int B, long long chw, unsigned long long seed,
                               void* stream);
+/* Haze degradation (utils/degradation_utils.py:235-273) for a caller-supplied cirrus-band map (the reference loads it from .mat
+ * files and resizes it to the patch).  mphsir_topk_mean: mean[p] = mean of the k largest elements of plane p (the atmospheric
+ * light of :257-261 with k = max(int(H*W*top_percent/100), 1); ties counted as a sort counts them).  mphsir_haze:
+ * out = x * T + light[b,c] * (1 - T), T = exp(expo[c] * log(t1)), t1 = 1 - omega[b] * cirrus[b,pixel] (<= 0 -> 1e-10), evaluated
+ * in double; expo[c] = (lambda_0 / lambda_c)^gamma from the host; samples with omega[b] <= 0 are not touched.  in == out allowed. */
+MPHSIR_API int mphsir_topk_mean(const float* X, int planes, long long hw, int k, float* mean, void* stream);
+MPHSIR_API int mphsir_haze(const float* in, float* out, const float* cirrus /* [B*hw] */, const float* omega /* [B] */,
+                           const float* expo /* [C] */, const float* light /* [B*C] */, int B, int C, long long hw, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Collectives of the row-sharded scene over NVLink peer memory (mp_hsir_b200/csrc/peer.cu; one process per GPU of one

@@ -400,6 +400,84 @@ __global__ void __launch_bounds__(256) poisson_kernel(const float* __restrict__ 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Haze degradation (utils/degradation_utils.py:235-273), given the cirrus-band map the reference reads from its .mat files:
+//   A[c]   = mean of the top_k brightest pixels of band c                 (atmospheric light, :257-261)
+//   t1     = 1 - omega * cirrus,  <= 0 -> 1e-10                           (:263-264)
+//   T[c]   = exp((lambda_0 / lambda_c)^gamma * log(t1))                   (:269-270; the exponent per band comes from the host)
+//   out[c] = x[c] * T[c] + A[c] * (1 - T[c])                              (:271)
+// topk_mean_kernel: one CTA per plane; pass j finds the largest value strictly below the previous pass's value and how often it
+// occurs (a (max, count) reduction), so ties are counted like a sort would count them; k passes, sum in double.  k is
+// max(int(HW * 1e-4), 1) in the reference: 1 for a 64 x 64 patch (the maximum), 26 for 512 x 512.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) topk_mean_kernel(const float* __restrict__ X, long long hw, int k, float* __restrict__ mean) {
+  __shared__ float smax[8];
+  __shared__ int scnt[8];
+  __shared__ float bmax;
+  __shared__ int bcnt;
+  const float* p = X + (size_t)blockIdx.x * hw;
+  float bound = INFINITY;
+  double sum = 0.0;
+  int remaining = k;
+  bool first = true;
+  while (remaining > 0) {
+    float m = -INFINITY;
+    int c = 0;
+    for (long long i = threadIdx.x; i < hw; i += 256) {
+      const float v = __ldg(p + i);
+      if (!(first || v < bound)) continue;           // pass 0 takes everything (also +inf); NaN never compares true afterwards
+      if (v > m) { m = v; c = 1; }
+      else if (v == m) ++c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+      const int c2 = __shfl_xor_sync(0xffffffffu, c, o);
+      if (m2 > m) { m = m2; c = c2; }
+      else if (m2 == m) c += c2;
+    }
+    if ((threadIdx.x & 31) == 0) { smax[threadIdx.x >> 5] = m; scnt[threadIdx.x >> 5] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float mm = smax[0];
+      int cc = scnt[0];
+      for (int w = 1; w < 8; ++w) {
+        if (smax[w] > mm) { mm = smax[w]; cc = scnt[w]; }
+        else if (smax[w] == mm) cc += scnt[w];
+      }
+      bmax = mm; bcnt = cc;
+    }
+    __syncthreads();
+    const float mm = bmax;
+    const int cc = bcnt;
+    __syncthreads();
+    if (cc == 0) break;                              // fewer than k comparable values
+    const int take = cc < remaining ? cc : remaining;
+    sum += (double)mm * take;
+    remaining -= take;
+    bound = mm;
+    first = false;
+  }
+  if (threadIdx.x == 0) mean[blockIdx.x] = (float)(sum / (double)(k - remaining > 0 ? k - remaining : 1));
+}
+
+__global__ void __launch_bounds__(256) haze_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                   const float* __restrict__ cirrus, const float* __restrict__ omega,
+                                                   const float* __restrict__ expo, const float* __restrict__ light, int C,
+                                                   long long hw, long long total) {
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    const long long bc = e / hw;
+    const int b = (int)(bc / C), c = (int)(bc - (long long)b * C);
+    const float om = __ldg(omega + b);
+    if (om <= 0.f) continue;
+    double t1 = 1.0 - (double)om * (double)__ldg(cirrus + (long long)b * hw + (e - bc * hw));
+    if (t1 <= 0.0) t1 = 1e-10;
+    const double T = exp((double)__ldg(expo + c) * log(t1));
+    out[e] = (float)((double)__ldg(in + e) * T + (double)__ldg(light + bc) * (1.0 - T));
+  }
+}
+
 }  // namespace metrics
 }  // namespace mphsir
 
@@ -489,6 +567,24 @@ extern "C" int mphsir_poisson(const float* in, float* out, const float* scale, i
   metrics::poisson_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, out, total, chw, scale,
                                                                                               (uint32_t)seed, (uint32_t)(seed >> 32));
   return check_launch("poisson");
+}
+
+extern "C" int mphsir_topk_mean(const float* X, int planes, long long hw, int k, float* mean, void* stream) {
+  MPHSIR_REQUIRE(X && mean && planes > 0 && hw > 0 && k >= 1 && k <= hw, "topk_mean: bad arguments");
+  MPHSIR_REQUIRE(k <= 4096, "topk_mean: k up to 4096 (one pass over the plane per distinct value; got %d)", k);
+  metrics::topk_mean_kernel<<<(unsigned)planes, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(X, hw, k, mean);
+  return check_launch("topk_mean");
+}
+
+extern "C" int mphsir_haze(const float* in, float* out, const float* cirrus, const float* omega, const float* expo,
+                           const float* light, int B, int C, long long hw, void* stream) {
+  MPHSIR_REQUIRE(in && out && cirrus && omega && expo && light && B > 0 && C > 0 && hw > 0, "haze: bad arguments");
+  const long long total = (long long)B * C * hw;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  metrics::haze_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, out, cirrus, omega, expo, light, C, hw,
+                                                                                           total);
+  return check_launch("haze");
 }
 
 extern "C" int mphsir_degrade_structured(float* x, int B, int C, int H, int W, const float* colmul, const float* coladd,

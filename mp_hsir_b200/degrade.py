@@ -23,6 +23,9 @@ the B*C*H*W random numbers come from a counter-based Philox4x32-10 stream inside
     circle_blur / poissonN : (remote-sensing extras, dataset_utils.py:117) the disc-cut Gaussian blur (:110-128; host-built k x k
                 kernel through the generic ``mphsir_blur2d``, which also serves square / motion blur kernels, :130-163) and Poisson
                 noise Poisson(x * scale) / scale (:86-89; ``mphsir_poisson``, a third Philox stream) — ``draw_recipes``
+    haze      : (remote-sensing default list, options.py:17) x T + A (1 - T) with the transmission of a cirrus-band map (:235-273);
+                the map itself comes from the reference's .mat files, so the caller passes it (``cirrus=``) — on the device:
+                the per-band atmospheric light (``mphsir_topk_mean``) and the elementwise pass (``mphsir_haze``)
 
 The task id of a sample is the index of its degradation in the active ``de_type`` list, shape [B,1] (:140).
 """
@@ -35,10 +38,11 @@ import torch
 from . import lib
 
 RECIPES = ("gaussianN", "complexN", "inpaint", "bandmiss")          # the default set (one elementwise launch)
-ALL_RECIPES = RECIPES + ("blur", "sr", "circle_blur", "poissonN")    # + recipes that need their own kernel
+ALL_RECIPES = RECIPES + ("blur", "sr", "circle_blur", "poissonN", "haze")    # + recipes that need their own kernel
+REFERENCE_DEFAULT_RS = ("gaussianN", "complexN", "blur", "sr", "inpaint", "haze", "bandmiss")   # options.py:17 (remote sensing)
 REFERENCE_DEFAULT = ("gaussianN", "complexN", "blur", "sr", "inpaint", "bandmiss")   # options.py:15 (task ids 0..5 in this order)
 DE_RANGE = {"gaussianN": (30.0, 70.0), "complexN": (10.0, 30.0, 50.0, 70.0), "inpaint": (0.7, 0.8, 0.9), "bandmiss": (0.1, 0.2, 0.3),
-            "blur": (9, 15, 21), "sr": (2, 4, 8), "circle_blur": (9,), "poissonN": (10.0,)}
+            "blur": (9, 15, 21), "sr": (2, 4, 8), "circle_blur": (9,), "poissonN": (10.0,), "haze": (0.5, 0.75, 1.0)}
 
 
 def draw_parameters(B: int, C: int, de_types: Sequence[str] = RECIPES, generator: Optional[torch.Generator] = None,
@@ -88,7 +92,7 @@ def draw_parameters(B: int, C: int, de_types: Sequence[str] = RECIPES, generator
 def draw_recipes(B: int, C: int, de_types: Sequence[str], generator: Optional[torch.Generator] = None) -> dict:
     """``draw_parameters`` for any subset of ALL_RECIPES, as a dict: tid, sigma, keep, ratio and — for the recipes present in
     `de_types` — ksize (blur), factor (sr), circle (kernel size per sample, 0 = not a circle-blur sample), poisson (scale per
-    sample, 0 = not a Poisson sample)."""
+    sample, 0 = not a Poisson sample), omega (haze strength per sample, 0 = not a haze sample)."""
     wb, wsr = "blur" in de_types, "sr" in de_types
     tid, sigma, keep, ratio, *extra = draw_parameters(B, C, de_types, generator, with_blur=wb, with_sr=wsr)
     d = {"tid": tid, "sigma": sigma, "keep": keep, "ratio": ratio}
@@ -103,6 +107,9 @@ def draw_recipes(B: int, C: int, de_types: Sequence[str], generator: Optional[to
     if "poissonN" in de_types:
         sc = torch.tensor(DE_RANGE["poissonN"])[torch.randint(0, len(DE_RANGE["poissonN"]), (B,), generator=generator)]
         d["poisson"] = torch.where(code == ALL_RECIPES.index("poissonN"), sc, torch.zeros(B)).contiguous()
+    if "haze" in de_types:
+        om = torch.tensor(DE_RANGE["haze"])[torch.randint(0, len(DE_RANGE["haze"]), (B,), generator=generator)]
+        d["omega"] = torch.where(code == ALL_RECIPES.index("haze"), om, torch.zeros(B)).contiguous()
     return d
 
 
@@ -148,6 +155,34 @@ def poisson_noise(clean: torch.Tensor, scale: torch.Tensor, seed: int, out: Opti
     if float(scale.max()) > 0:
         with torch.cuda.device(c.device):
             lib.poisson(c, out, scale.to(device=c.device, dtype=torch.float32).contiguous(), seed)
+    return out
+
+
+def haze(clean: torch.Tensor, cirrus: torch.Tensor, omega: torch.Tensor, gamma: float = 1.0, top_percent: float = 0.01,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Haze for the samples with omega[b] > 0 (utils/degradation_utils.py:252-273).  cirrus: the cirrus-band map(s) at the patch
+    resolution, [H,W] (shared) or [B,H,W] — what the reference loads from its .mat files and cv2.resize's (:237-253).  The
+    wavelength grid is the reference's hard-coded linspace(400, 1000, 100), so C <= 100.  Other samples of `out` keep their
+    content (a fresh `out` starts as a copy of `clean`)."""
+    if not clean.is_cuda:
+        raise RuntimeError("mp_hsir_b200.degrade runs on a CUDA device via libmphsir.so; there is no CPU fallback")
+    c = clean.detach().float().contiguous()
+    B, C, H, W = c.shape
+    if C > 100:
+        raise ValueError("haze: the reference's wavelength grid has 100 entries (C <= 100)")
+    if cirrus.dim() == 2:
+        cirrus = cirrus[None].expand(B, H, W)
+    if tuple(cirrus.shape) != (B, H, W):
+        raise ValueError(f"haze: cirrus map of shape {tuple(cirrus.shape)} for a batch {tuple(c.shape)}")
+    if out is None:
+        out = c.clone()
+    if float(omega.max()) > 0:
+        wl = torch.linspace(400, 1000, 100, dtype=torch.float64)
+        expo = ((wl[0] / wl[:C]) ** gamma).to(torch.float32)
+        f = lambda t: t.to(device=c.device, dtype=torch.float32).contiguous()  # noqa: E731
+        with torch.cuda.device(c.device):
+            light = lib.topk_mean(c, max(int(H * W * top_percent / 100), 1))
+            lib.haze(c, out, f(cirrus), f(omega), f(expo), light)
     return out
 
 
@@ -240,7 +275,8 @@ def sr_degrade(clean: torch.Tensor, factor: torch.Tensor, out: Optional[torch.Te
 
 
 def degrade_batch(clean: torch.Tensor, seed: int, de_types: Sequence[str] = RECIPES,
-                  generator: Optional[torch.Generator] = None, complex_full: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+                  generator: Optional[torch.Generator] = None, complex_full: bool = False,
+                  cirrus: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """(degraded [B,C,H,W], task_id [B,1]) for a clean device batch — what the DataLoader's collate hands train.py:50-58.
     complex_full: complexN samples also get their deadline / impulse / stripe half (one more in-place launch)."""
     B, C, W = clean.shape[0], clean.shape[1], clean.shape[3]
@@ -260,4 +296,8 @@ def degrade_batch(clean: torch.Tensor, seed: int, de_types: Sequence[str] = RECI
             blur2d(clean, circle_kernel(k), d["circle"] == k, out=out)
     if "poisson" in d:
         poisson_noise(clean, d["poisson"], seed, out=out)
+    if "omega" in d:
+        if cirrus is None:
+            raise ValueError("the 'haze' recipe needs the cirrus-band map(s) of the batch (cirrus=[H,W] or [B,H,W])")
+        haze(clean, cirrus, d["omega"], out=out)
     return out, tid

@@ -184,6 +184,8 @@ SIGNATURES = {
     "mphsir_sr_degrade": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "mphsir_blur2d": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
     "mphsir_poisson": (_I, [_VP, _VP, _VP, _I, _LL, C.c_ulonglong, _VP]),
+    "mphsir_topk_mean": (_I, [_VP, _I, _LL, _I, _VP, _VP]),
+    "mphsir_haze": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _LL, _VP]),
     "mphsir_degrade_structured": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, C.c_ulonglong, _VP]),
     "mphsir_adamw_step": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _I, _F, _VP, _VP]),
 }
@@ -899,6 +901,28 @@ def blur2d(x: torch.Tensor, out: torch.Tensor, taps: torch.Tensor, active: torch
     _launch("blur2d", lambda: load().mphsir_blur2d(x.data_ptr(), out.data_ptr(), taps.data_ptr(), active.data_ptr(), B, Cc, H, W, k,
                                                    stream_ptr()),
             lambda: (2.0 * k * k * x.numel(), 8.0 * x.numel(), "blur2d"))
+
+
+def topk_mean(x: torch.Tensor, k: int) -> torch.Tensor:
+    """[B,C,H,W] -> [B,C]: mean of the k largest pixels of every plane (utils/degradation_utils.py:257-261)"""
+    B, Cc, H, W = x.shape
+    assert x.is_contiguous() and x.dtype == torch.float32
+    mean = torch.empty(B, Cc, device=x.device, dtype=torch.float32)
+    _launch("topk_mean", lambda: load().mphsir_topk_mean(x.data_ptr(), B * Cc, H * W, k, mean.data_ptr(), stream_ptr()),
+            lambda: (0.0, 4.0 * x.numel() * k, "topk_mean"))
+    return mean
+
+
+def haze(x: torch.Tensor, out: torch.Tensor, cirrus: torch.Tensor, omega: torch.Tensor, expo: torch.Tensor,
+         light: torch.Tensor) -> None:
+    """out[b] = x[b] * T + light[b,c] * (1 - T) where omega[b] > 0 (utils/degradation_utils.py:263-271)"""
+    B, Cc, H, W = x.shape
+    assert x.is_contiguous() and out.is_contiguous() and out.shape == x.shape and x.dtype == torch.float32
+    for t, n in ((cirrus, B * H * W), (omega, B), (expo, Cc), (light, B * Cc)):
+        assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float32 and t.numel() == n
+    _launch("haze", lambda: load().mphsir_haze(x.data_ptr(), out.data_ptr(), cirrus.data_ptr(), omega.data_ptr(), expo.data_ptr(),
+                                               light.data_ptr(), B, Cc, H * W, stream_ptr()),
+            lambda: (0.0, 12.0 * x.numel(), "haze"))
 
 
 def poisson(x: torch.Tensor, out: torch.Tensor, scale: torch.Tensor, seed: int) -> None:

@@ -198,6 +198,27 @@ def poisson(clean: np.ndarray, scale: np.ndarray, seed: int) -> np.ndarray:
     return np.where(sc > 0, out, clean.astype(np.float32)).astype(np.float32)
 
 
+def haze(hsi: np.ndarray, cirrus_band: np.ndarray, omega: float, gamma: float = 1.0, top_percent: float = 0.01) -> np.ndarray:
+    """utils/degradation_utils.py:252-273 (_simulate_haze) on a [C,H,W] cube for a GIVEN cirrus-band map [H,W] (the reference
+    picks a random .mat file and cv2.resize's it to the patch, :237-253 — file access, outside this restatement): atmospheric
+    light = mean of the top_k brightest pixels per band, k = max(int(HW top_percent / 100), 1); t1 = 1 - omega cirrus (<= 0 ->
+    1e-10); per band transmission t1 ** ((lambda_0 / lambda_c) ** gamma) with the hard-coded 100-point wavelength grid
+    400..1000 nm; hazy = x T + A (1 - T).  float64 like the reference, cast to float32 at the end."""
+    C, H, W = hsi.shape
+    wavelength = np.linspace(400, 1000, 100)
+    top_k = max(int(H * W * top_percent / 100), 1)
+    flat = hsi.reshape(C, -1)
+    light = np.array([np.mean(np.sort(flat[c])[-top_k:]) for c in range(C)], dtype=np.float64)
+    t1 = 1 - omega * cirrus_band.astype(np.float64)
+    t1 = np.where(t1 <= 0, 1e-10, t1)
+    out = np.zeros(hsi.shape, dtype=np.float64)
+    for c in range(C):
+        expo = (wavelength[0] / wavelength[c]) ** gamma
+        T = np.exp(expo * np.log(t1))
+        out[c] = hsi[c] * T + light[c] * (1 - T)
+    return out.astype(np.float32)
+
+
 def degrade_structured(x: np.ndarray, colmul: np.ndarray, coladd: np.ndarray, impulse: np.ndarray, active: np.ndarray, seed: int):
     """utils/degradation_utils.py:41-84 on [B,C,H,W]: deadline columns (colmul 0), stripes (coladd), impulse flips with probability
     impulse[b,c] (salt with probability 1/2) from the Philox stream with counter word 2 = 1; inactive samples untouched."""

@@ -180,7 +180,10 @@ def test_poisson_matches_oracle_stream():
 def test_degrade_batch_every_recipe():
     from mp_hsir_b200.degrade import ALL_RECIPES
     clean = synthetic_input((48, 31, 64, 64), seed=8).cuda()
-    noisy, tid = degrade_batch(clean, seed=13, de_types=ALL_RECIPES, generator=torch.Generator().manual_seed(5))
+    cirrus = synthetic_input((1, 1, 64, 64), seed=21)[0, 0]
+    with pytest.raises(ValueError):
+        degrade_batch(clean, seed=13, de_types=ALL_RECIPES, generator=torch.Generator().manual_seed(5))   # haze needs its map
+    noisy, tid = degrade_batch(clean, seed=13, de_types=ALL_RECIPES, generator=torch.Generator().manual_seed(5), cirrus=cirrus)
     kinds = [ALL_RECIPES[int(t)] for t in tid.view(-1)]
     assert set(kinds) == set(ALL_RECIPES)
     for b, kind in enumerate(kinds):
@@ -190,6 +193,35 @@ def test_degrade_batch_every_recipe():
         elif kind == "poissonN":
             c = noisy[b] * 10.0
             assert torch.equal(c.round(), c) or float((c.round() - c).abs().max()) < 1e-4
+
+
+@pytest.mark.gpu
+def test_haze_matches_oracle():
+    """mphsir_topk_mean + mphsir_haze vs the float64 restatement of utils/degradation_utils.py:252-273: a 64 x 64 patch (top_k = 1,
+    the band maximum), a 128 x 160 scene (top_k = 2) and top_percent raised so that top_k = 40 with tied values; per-sample
+    cirrus maps; samples with omega 0 untouched"""
+    from mp_hsir_b200 import lib
+    from mp_hsir_b200.degrade import haze
+    for (B, C, H, W), pct in (((3, 31, 64, 64), 0.01), ((2, 100, 128, 160), 0.01), ((2, 5, 64, 64), 1.0)):
+        clean = synthetic_input((B, C, H, W), seed=12)
+        if pct == 1.0:
+            clean = (clean * 50).round() / 50                  # many ties among the brightest pixels
+        cirrus = synthetic_input((B, 1, H, W), seed=13)[:, 0] * 1.6     # some pixels with 1 - omega * cirrus <= 0
+        omega = torch.tensor([0.75, 0.0, 1.0][:B])
+        k = max(int(H * W * pct / 100), 1)
+        light = lib.topk_mean(clean.cuda().contiguous(), k).cpu().numpy()
+        out = torch.full_like(clean, 7.0).cuda()
+        haze(clean.cuda(), cirrus, omega, top_percent=pct, out=out)
+        out = out.cpu().numpy()
+        for b in range(B):
+            flat = clean[b].numpy().reshape(C, -1)
+            want = np.sort(flat, axis=1)[:, -k:].astype(np.float64).mean(axis=1)
+            assert abs(light[b] - want).max() < 1e-6
+            if float(omega[b]) == 0:
+                assert (out[b] == 7.0).all()
+            else:
+                ref = M.haze(clean[b].numpy(), cirrus[b].numpy(), float(omega[b]), top_percent=pct)
+                assert abs(out[b] - ref).max() < 2e-6
 
 
 @pytest.mark.gpu

@@ -202,6 +202,32 @@ def test_draw_recipes_covers_every_recipe():
         assert (int(d["circle"][b]) in DE_RANGE["circle_blur"]) == (kind == "circle_blur")
         assert (float(d["poisson"][b]) in DE_RANGE["poissonN"]) == (kind == "poissonN")
         assert (int(d["ksize"][b]) > 0) == (kind == "blur") and (int(d["factor"][b]) > 0) == (kind == "sr")
+        assert (round(float(d["omega"][b]), 4) in DE_RANGE["haze"]) == (kind == "haze")
+
+
+def test_haze_oracle_follows_the_reference_model():
+    """utils/degradation_utils.py:255-273 on a given cirrus map: the atmospheric light is the mean of the top_k brightest pixels
+    (np.partition in the reference, a sort here), a clear sky (cirrus 0) leaves the cube alone, full opacity (1 - omega cirrus <= 0)
+    returns the atmospheric light, and longer wavelengths see less haze (the exponent (lambda_0 / lambda_c)^gamma falls with c)"""
+    rng = np.random.default_rng(3)
+    x = rng.random((6, 128, 128), dtype=np.float32)
+    k = max(int(128 * 128 * 0.01 / 100), 1)
+    assert k == 1
+    clear = M.haze(x, np.zeros((128, 128)), 0.75)
+    assert np.abs(clear - x).max() < 1e-7
+    opaque = M.haze(x, np.full((128, 128), 2.0), 1.0)
+    light = x.reshape(6, -1).max(axis=1)
+    assert np.abs(opaque - light[:, None, None]).max() < 1e-4            # T = (1e-10)^e ~ 0
+    half = M.haze(np.zeros((6, 128, 128), dtype=np.float32) + 0.2, np.full((128, 128), 0.5), 1.0)
+    # constant cube: A = 0.2, so the result stays 0.2 whatever T is
+    assert np.abs(half - 0.2).max() < 1e-7
+    # top_k > 1: the light is the mean of the k brightest, via np.partition exactly as the reference takes it
+    y = rng.random((3, 256, 256), dtype=np.float32)
+    kk = max(int(256 * 256 * 0.01 / 100), 1)
+    assert kk == 6
+    opaque = M.haze(y, np.full((256, 256), 5.0), 1.0)
+    want = np.array([np.mean(np.partition(y[c].flatten(), -kk)[-kk:]) for c in range(3)])
+    assert np.abs(opaque[:, 0, 0] - want).max() < 1e-4
 
 
 def test_structured_draws_follow_the_reference_counts():
